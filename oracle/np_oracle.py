@@ -1,0 +1,383 @@
+"""CPU oracle: numpy restatement of the reference's PINN hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package imports this module;
+only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs
+may.  It restates, in plain numpy, the algorithms of
+``/root/reference/01_train_pinn_multiphysics_model.py`` ("01:" below) that the
+CUDA path replaces.  Every function runs in ``dtype=np.float32`` (mirrors the
+reference's fp32 op order) or ``np.float64`` (tie-breaker when the reference's
+own fp32 noise exceeds the tolerance, SURVEY.md section 8c / hazard H2).
+
+Pinning: the reference ships no tests or golden vectors,
+so this oracle is pinned against outputs of the reference itself, generated in
+the build container by ``tests/golden/make_golden.py`` (imports the unmodified
+reference by path) and committed as ``tests/golden/*.npz``;
+``tests/test_oracle_golden.py`` holds the comparison.
+
+Parameter dictionaries use the reference's ``state_dict`` keys
+(``layers.layer_{i}.weight`` ... see 01:399-419); weights are ``[out, in]``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+A_CELL = 270.0
+FARADAY = 96485.0
+R_GAS = 8.314
+N_CELLS = 5.0
+ALPHA = 0.5
+GF_LIQ = -220170.0
+
+
+# --------------------------------------------------------------------------- net
+def n_hidden_layers(params) -> int:
+    return sum(1 for k in params if k.startswith("layers.layer_") and k.endswith(".weight"))
+
+
+def dropout_scale(p: float, dtype=np.float32):
+    """Scaled-mask value torch uses: ``bernoulli_(1-p).div_(1-p)``."""
+    keep = dtype(1.0 - p)
+    return dtype(1.0) / keep
+
+
+def softplus_log(v, dtype):
+    """``log(softplus(v) + 1e-6)`` with torch's threshold 20 (01:432-434)."""
+    v = v.astype(dtype)
+    sp = np.where(v > 20, v, np.log1p(np.exp(np.minimum(v, dtype(20)))).astype(dtype))
+    return np.log(sp + dtype(1e-6)).astype(dtype), sp
+
+
+def dnn_forward(params, x, masks=None, dtype=np.float32, return_cache=False):
+    """``DNN.forward`` (01:421-438).
+
+    ``masks``: ``None`` (eval mode) or a list of ``L+1`` *scaled* masks (values in
+    ``{0, 1/(1-p)}``): one per trunk layer ``[N,H]`` and one for the variance
+    head ``[N,H/2]`` -- the order in which ``nn.Dropout`` modules fire.
+    """
+    P = {k: np.asarray(v, dtype=dtype) for k, v in params.items()}
+    L = n_hidden_layers(P)
+    h = np.asarray(x, dtype=dtype)
+    acts, hs = [], [h]
+    for i in range(L):
+        a = np.tanh(h @ P[f"layers.layer_{i}.weight"].T + P[f"layers.layer_{i}.bias"])
+        acts.append(a)
+        h = a * masks[i].astype(dtype) if masks is not None else a
+        hs.append(h)
+    out = h @ P["predict.weight"].T + P["predict.bias"]
+    a_v0 = np.tanh(h @ P["var_layers.0.weight"].T + P["var_layers.0.bias"])
+    v0 = a_v0 * masks[L].astype(dtype) if masks is not None else a_v0
+    v1 = np.tanh(v0 @ P["var_layers.3.weight"].T + P["var_layers.3.bias"])
+    v = v1 @ P["var_layers.5.weight"].T + P["var_layers.5.bias"]
+    logvar, sp = softplus_log(v, dtype)
+    if return_cache:
+        return out, logvar, dict(acts=acts, hs=hs, a_v0=a_v0, v0=v0, v1=v1, v=v, sp=sp)
+    return out, logvar
+
+
+def aleatoric_loss(y, u, s, dtype=np.float32):
+    """``aleatoric_loss`` (01:916-927)."""
+    y, u, s = (np.asarray(t, dtype=dtype) for t in (y, u, s))
+    nll = np.mean(dtype(0.5) * np.exp(-s) * (y - u) ** 2 + dtype(0.5) * s, dtype=dtype)
+    return nll + dtype(0.01) * np.mean(np.abs(s), dtype=dtype)
+
+
+def aleatoric_loss_grads(y, u, s, dtype=np.float64):
+    """dL/du, dL/ds of :func:`aleatoric_loss`."""
+    y, u, s = (np.asarray(t, dtype=dtype) for t in (y, u, s))
+    n = dtype(y.shape[0])
+    e = np.exp(-s)
+    du = -e * (y - u) / n
+    ds = (-0.5 * e * (y - u) ** 2 + 0.5 + 0.01 * np.sign(s)) / n
+    return du, ds
+
+
+def dnn_backward(params, x, masks, du, ds, dtype=np.float64):
+    """Gradients of ``sum(du*out) + sum(ds*logvar)`` w.r.t. every DNN parameter
+    (what ``loss.backward()`` at 01:953 produces through autograd)."""
+    P = {k: np.asarray(v, dtype=dtype) for k, v in params.items()}
+    L = n_hidden_layers(P)
+    _, _, c = dnn_forward(params, x, masks, dtype, return_cache=True)
+    du = np.asarray(du, dtype=dtype)
+    ds = np.asarray(ds, dtype=dtype)
+    g = {}
+    v, sp = c["v"], c["sp"]
+    dsp_dv = np.where(v > 20, 1.0, 1.0 / (1.0 + np.exp(-v)))
+    dv = ds * dsp_dv / (sp + dtype(1e-6))
+    g["var_layers.5.weight"] = dv.T @ c["v1"]
+    g["var_layers.5.bias"] = dv.sum(0)
+    dz1 = (dv @ P["var_layers.5.weight"]) * (1 - c["v1"] ** 2)
+    g["var_layers.3.weight"] = dz1.T @ c["v0"]
+    g["var_layers.3.bias"] = dz1.sum(0)
+    dv0 = dz1 @ P["var_layers.3.weight"]
+    if masks is not None:
+        dv0 = dv0 * masks[L].astype(dtype)
+    dz0 = dv0 * (1 - c["a_v0"] ** 2)
+    hL = c["hs"][L]
+    g["var_layers.0.weight"] = dz0.T @ hL
+    g["var_layers.0.bias"] = dz0.sum(0)
+    g["predict.weight"] = du.T @ hL
+    g["predict.bias"] = du.sum(0)
+    dh = dz0 @ P["var_layers.0.weight"] + du @ P["predict.weight"]
+    for i in reversed(range(L)):
+        if masks is not None:
+            dh = dh * masks[i].astype(dtype)
+        dz = dh * (1 - c["acts"][i] ** 2)
+        g[f"layers.layer_{i}.weight"] = dz.T @ c["hs"][i]
+        g[f"layers.layer_{i}.bias"] = dz.sum(0)
+        dh = dz @ P[f"layers.layer_{i}.weight"]
+    return g
+
+
+# ------------------------------------------------------------------------ scalers
+def inverse_transform(scaler, x, dtype=np.float32):
+    """sklearn ``MinMaxScaler.inverse_transform`` on an fp32 array: each in-place
+    op is computed in fp64 and rounded back to fp32."""
+    x = np.asarray(x)
+    if dtype == np.float64:
+        return (x.astype(np.float64) - scaler.min_) / scaler.scale_
+    t = (x.astype(np.float64) - scaler.min_).astype(np.float32)
+    return (t.astype(np.float64) / scaler.scale_).astype(np.float32)
+
+
+def y_affine(u_scal, dtype=np.float32):
+    """``scale_y, min_y`` as rebuilt every step in ``train_lambda`` (01:1017-1022)."""
+    lo, hi = float(u_scal.feature_range[0]), float(u_scal.feature_range[1])
+    dmin = np.asarray(u_scal.data_min_, dtype=dtype)
+    dmax = np.asarray(u_scal.data_max_, dtype=dtype)
+    scale_y = dtype(hi - lo) / (dmax - dmin + dtype(1e-12))
+    min_y = dtype(lo) - dmin * scale_y
+    return scale_y.astype(dtype), min_y.astype(dtype)
+
+
+# ---------------------------------------------------------------------- residuals
+def p_h2o(dtype=np.float32):
+    """Water-vapour pressure at the constant Tc=55 (01:745,752-753)."""
+    Tc = dtype(55)
+    x = dtype(-2.1794) + dtype(0.02953) * Tc - dtype(9.1837e-5) * (Tc ** 2) + dtype(1.4454e-7) * (Tc ** 3)
+    return (dtype(10) ** x).astype(dtype) if hasattr(x, "astype") else dtype(dtype(10) ** x)
+
+
+def net_f_V(x_norm, u_norm, x_scal, u_scal, lam, dtype=np.float32):
+    """``net_f_V`` (01:724-765).  ``u_norm`` is the DNN prediction (normalised);
+    ``lam = (lambda_1, lambda_2, lambda_3)``.  Returns the reference's 9-tuple."""
+    f = dtype
+    r = inverse_transform(x_scal, x_norm, f)
+    i = r[:, 0:1] / f(A_CELL) + f(1e-5)
+    T_out = r[:, 5:6]
+    V_out = inverse_transform(u_scal, np.asarray(u_norm).reshape(-1, 1), f) / f(N_CELLS)
+    lam1, lam2, lam3 = (f(v) for v in lam)
+    P_H2 = r[:, 3:4] / f(101) + f(1)
+    P_air = r[:, 4:5] / f(101) + f(1)
+    Tk = T_out + f(273.15)
+    PH2O = p_h2o(f)
+    tkp = Tk ** f(1.334)
+    pp_H2 = f(0.5) * (P_H2 / np.exp(f(1.653) * i / tkp) - PH2O)
+    pp_O2 = P_air / np.exp(f(4.192) * i / tkp) - PH2O
+    b = f(R_GAS) * Tk / (f(2.0) * f(ALPHA) * f(FARADAY))
+    V_act = -b * np.log(i / lam2)
+    V_ohm = -(i * lam1)
+    V_conc = f(ALPHA) * b * np.log(f(1) - i / lam3)
+    E = -f(GF_LIQ) / (f(2) * f(FARADAY)) - (f(R_GAS) * Tk) * np.log(PH2O / (pp_H2 * pp_O2 ** f(0.5))) / (f(2) * f(FARADAY))
+    V_est = E + V_act + V_ohm + V_conc
+    fV = V_est - V_out
+    return tuple(np.asarray(t, dtype=f) for t in
+                 (fV, V_act, V_ohm, V_conc, E, V_est * f(5), i, np.array([lam3]), V_out * f(5)))
+
+
+def net_f_T_simple(x_norm, x_scal, lamT, dtype=np.float32):
+    """``net_f_T_simple`` (01:869-914); ``lamT = (T1..T5)``; T2, T4 unused."""
+    f = dtype
+    r = inverse_transform(x_scal, x_norm, f)
+    i = r[:, 0:1] / f(A_CELL) + f(1e-6)
+    m = r[:, 1:2] + f(1e-6)
+    T_in, T_real = r[:, 2:3], r[:, 5:6]
+    I_t = i * f(A_CELL)
+    T_pred = f(lamT[0]) * I_t + f(lamT[2]) * m + f(0.5) * T_in + f(lamT[4])
+    return (T_real - T_pred).astype(f), T_pred.astype(f), T_real.astype(f)
+
+
+def net_f_T(x_norm, u_norm, x_scal, u_scal, lamT, dtype=np.float32):
+    """``net_f_T`` (01:767-867): Euler energy balance, rows t-1 -> t."""
+    f = dtype
+    n = x_norm.shape[0]
+    if n < 2:
+        z = np.zeros((n, 1), f)
+        return z, z.copy(), z.copy()
+    r = inverse_transform(x_scal, x_norm, f)
+    i = r[:, 0:1] / f(A_CELL) + f(1e-5)
+    m = r[:, 1:2] + f(1e-6)
+    T_in, T_out = r[:, 2:3], r[:, 5:6]
+    ip, mp, Tinp, Toutp = i[:-1], m[:-1], T_in[:-1], T_out[:-1]
+    I_t = ip * f(A_CELL)
+    V_rev = f(1.229) - f(0.0009) * ((Toutp + f(273.15)) - f(298.15))
+    V_cell = inverse_transform(u_scal, np.asarray(u_norm).reshape(-1, 1)[:-1], f) / f(N_CELLS)
+    Q_e = (I_t * V_rev - I_t * V_cell) * f(lamT[3])
+    Q_c = mp * f(4180.0) * (Toutp - Tinp) * f(lamT[0])
+    Q_r = f(20.0) * f(0.2) * (Toutp - f(25.0)) * f(lamT[2])
+    dT = (Q_e - Q_c - Q_r) / f(lamT[1])
+    T_next = Toutp + dT * f(0.1)
+    T_pred = np.concatenate([T_out[0:1], T_next], axis=0)
+    return (T_out - T_pred).astype(f), T_pred.astype(f), T_out.astype(f)
+
+
+def net_f_H(x_norm, x_scal, lamH, dtype=np.float32):
+    """``net_f_H`` (01:621-722); ``lamH = (H1..H4)``; H4 unused."""
+    f = dtype
+    r = inverse_transform(x_scal, x_norm, f)
+    i = r[:, 0:1] / f(A_CELL) + f(1e-5)
+    h2 = r[:, 6:7] + f(1e-6)
+    I_t = i * f(A_CELL)
+    Q = I_t / (f(2) * f(FARADAY)) * f(N_CELLS) * f(22.4) * f(60)
+    Q = np.maximum(Q, f(1e-8))
+    H1, H2, H3 = f(lamH[0]), f(lamH[1]), f(lamH[2])
+    target = np.where(I_t <= H3, H1 + H2 * (I_t / f(100.0)), H1 + H2 * (H3 / f(100.0)))
+    actual = h2 / Q
+    return ((actual - target).astype(f), actual.astype(f), target.astype(f), I_t.astype(f),
+            np.array([H3], f))
+
+
+def net_f_O(x_norm, x_scal, lamO, dtype=np.float32):
+    """``net_f_O`` (01:535-619); ``lamO = (O1..O4)``; O4 unused."""
+    f = dtype
+    r = inverse_transform(x_scal, x_norm, f)
+    i = r[:, 0:1] / f(A_CELL) + f(1e-5)
+    air = r[:, 7:8] + f(1e-6)
+    I_t = i * f(A_CELL)
+    Q = (I_t * f(N_CELLS)) / (f(4) * f(FARADAY)) * f(22.4) * f(60)
+    Q = np.maximum(Q, f(1e-8))
+    O1, O2, th = f(lamO[0]), f(lamO[1]), abs(f(lamO[2]))
+    target = np.where(I_t <= th, O1 + O2 * (I_t / f(100.0)), O1 + O2 * (th / f(100.0)))
+    target = np.clip(target, f(1.05), f(15.0))
+    o2 = air * f(0.21)
+    actual = o2 / Q
+    fO = actual - target + np.maximum(f(1.0) - actual, f(0.0)) * f(10.0)
+    return fO.astype(f), actual.astype(f), target.astype(f), Q.astype(f), o2.astype(f)
+
+
+# ------------------------------------------------------- losses + lambda gradients
+def lambda_losses(x_norm, y_norm, u_norm, x_scal, u_scal, lam, dnn_para, dtype=np.float64):
+    """``train_lambda`` loss terms (01:1009-1034): returns
+    ``(total, physics, data, grads[3])`` with analytic d total/d(lambda_1..3)
+    (the residual is detached from the DNN, 01:734-737)."""
+    f = dtype
+    fV, _, _, _, _, V5, i, _, _ = net_f_V(x_norm, u_norm, x_scal, u_scal, lam, f)
+    y = np.asarray(y_norm, f).reshape(-1, 1)
+    u = np.asarray(u_norm, f).reshape(-1, 1)
+    n = f(y.shape[0])
+    scale_y, min_y = y_affine(u_scal, f)
+    if dnn_para:
+        physics = np.mean(fV ** 2, dtype=f)
+        dV = 2 * fV / n                                  # d physics / d V_est (per cell)
+    else:
+        e = y - (V5 * scale_y + min_y)
+        physics = np.mean(e ** 2, dtype=f)
+        dV = -2 * f(5) * scale_y * e / n
+    data = np.mean((y - u) ** 2, dtype=f)
+    r = inverse_transform(x_scal, x_norm, f)
+    Tk = r[:, 5:6] + f(273.15)
+    b = f(R_GAS) * Tk / (f(2.0) * f(ALPHA) * f(FARADAY))
+    l2, l3 = f(lam[1]), f(lam[2])
+    g1 = np.sum(dV * (-i))
+    g2 = np.sum(dV * (b / l2))
+    g3 = np.sum(dV * (f(ALPHA) * b * i / (l3 * (l3 - i))))
+    return physics + data, physics, data, np.array([g1, g2, g3], f)
+
+
+def thermal_loss(x_norm, x_scal, lamT, dtype=np.float64):
+    """``train_thermal`` loss (01:1109-1112) and d/d(T1,T3,T5); also mean|f|."""
+    f = dtype
+    fT, _, _ = net_f_T_simple(x_norm, x_scal, lamT, f)
+    r = inverse_transform(x_scal, x_norm, f)
+    I_t = (r[:, 0:1] / f(A_CELL) + f(1e-6)) * f(A_CELL)
+    m = r[:, 1:2] + f(1e-6)
+    g = np.array([np.mean(-2 * fT * I_t), np.mean(-2 * fT * m), np.mean(-2 * fT)], f)
+    return np.mean(fT ** 2, dtype=f), g, np.mean(np.abs(fT), dtype=f)
+
+
+def hydrogen_loss(x_norm, x_scal, lamH, dtype=np.float64):
+    """``train_hydrogen`` loss (01:1357-1360) and d/d(H1,H2,H3)."""
+    f = dtype
+    fH, _, _, I_t, _ = net_f_H(x_norm, x_scal, lamH, f)
+    H2, H3 = f(lamH[1]), f(lamH[2])
+    lin = I_t <= H3
+    g = np.array([np.mean(-2 * fH),
+                  np.mean(-2 * fH * np.where(lin, I_t, H3) / f(100.0)),
+                  np.mean(-2 * fH * np.where(lin, f(0), H2 / f(100.0)))], f)
+    return np.mean(fH ** 2, dtype=f), g
+
+
+def oxygen_loss(x_norm, x_scal, lamO, dtype=np.float64):
+    """``train_oxygen`` loss (01:1207-1222) and d/d(O1,O2,O3)."""
+    f = dtype
+    fO, _, tgt, _, _ = net_f_O(x_norm, x_scal, lamO, f)
+    r = inverse_transform(x_scal, x_norm, f)
+    I_t = (r[:, 0:1] / f(A_CELL) + f(1e-5)) * f(A_CELL)
+    O1, O2, O3 = f(lamO[0]), f(lamO[1]), f(lamO[2])
+    th = abs(O3)
+    lin = I_t <= th
+    raw = np.where(lin, O1 + O2 * (I_t / f(100.0)), O1 + O2 * (th / f(100.0)))
+    gate = ((raw >= f(1.05)) & (raw <= f(15.0))).astype(f)   # torch.clamp passes grad on the bounds
+    sgn = np.sign(O3)
+    g = np.array([np.mean(-2 * fO * gate),
+                  np.mean(-2 * fO * gate * np.where(lin, I_t, th) / f(100.0)),
+                  np.mean(-2 * fO * gate * np.where(lin, f(0), O2 * sgn / f(100.0)))], f)
+    return np.mean(fO ** 2, dtype=f), g
+
+
+# ----------------------------------------------------------------- optimiser steps
+class Adam:
+    """``torch.optim.Adam`` defaults (betas .9/.999, eps 1e-8) + ``StepLR``; used to
+    restate the phase trainers' update (01:939-940, 999-1002, 1098-1102, ...)."""
+
+    def __init__(self, n, lr, step_size=1000, gamma=0.8, dtype=np.float64):
+        self.m = np.zeros(n, dtype)
+        self.v = np.zeros(n, dtype)
+        self.t = 0
+        self.lr0, self.step_size, self.gamma = lr, step_size, gamma
+        self.dtype = dtype
+
+    def lr(self):
+        return self.lr0 * self.gamma ** (self.t // self.step_size)
+
+    def step(self, p, g, mask=None):
+        """In torch a parameter whose ``.grad`` is ``None`` is skipped entirely;
+        ``mask`` marks the entries that do receive a gradient."""
+        f = self.dtype
+        lr = self.lr()
+        self.t += 1
+        b1, b2 = 0.9, 0.999
+        g = np.asarray(g, f)
+        sel = np.ones(p.shape, bool) if mask is None else np.asarray(mask, bool)
+        self.m[sel] = b1 * self.m[sel] + (1 - b1) * g[sel]
+        self.v[sel] = b2 * self.v[sel] + (1 - b2) * g[sel] ** 2
+        bc1, bc2 = 1 - b1 ** self.t, 1 - b2 ** self.t
+        denom = np.sqrt(self.v[sel]) / np.sqrt(bc2) + 1e-8
+        p = np.array(p, f)
+        p[sel] = p[sel] - (lr / bc1) * self.m[sel] / denom
+        return p
+
+
+# ------------------------------------------------------------------ MC statistics
+def mc_statistics(pred_eval_t, pred_drop_t, logvar_drop_t, dtype=np.float32):
+    """Tail of ``get_MC_samples`` (01:1475-1491) on stacked ``(T, N, 1)`` arrays."""
+    pe = np.asarray(pred_eval_t, dtype)
+    pd = np.asarray(pred_drop_t, dtype)
+    lv = np.asarray(logvar_drop_t, dtype)
+    pred_mean = np.mean(pe, axis=0)
+    a_u = np.sqrt(np.exp(np.mean(lv, axis=0)))
+    e_u = np.sqrt(np.var(pd, axis=0))
+    return pred_mean.squeeze(), a_u.squeeze(), e_u.squeeze()
+
+
+def mc_dropout(params, x, masks_t, dtype=np.float32):
+    """``get_MC_samples`` with injected masks.  ``masks_t[t]`` is the list of
+    ``L+1`` scaled masks of pass ``t`` (the first forward of each ``predict``;
+    the second, inside ``net_f_V``, is discarded: 01:1407)."""
+    T = len(masks_t)
+    pe, _ = dnn_forward(params, x, None, dtype)
+    us, ss = [], []
+    for t in range(T):
+        u, s = dnn_forward(params, x, masks_t[t], dtype)
+        us.append(u)
+        ss.append(s)
+    return mc_statistics(np.stack([pe] * T), np.stack(us), np.stack(ss), dtype)

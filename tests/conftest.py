@@ -1,0 +1,76 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+class Scaler:
+    """Duck-typed sklearn MinMaxScaler rebuilt from a golden file (the reference
+    only touches these attributes: 01:542,1017-1020,1920-1925)."""
+
+    def __init__(self, g, prefix):
+        self.min_ = g[prefix + "_min"]
+        self.scale_ = g[prefix + "_scale"]
+        self.data_min_ = g[prefix + "_data_min"]
+        self.data_max_ = g[prefix + "_data_max"]
+        self.feature_range = (-1, 1)
+
+    def inverse_transform(self, X):
+        X = np.array(X, copy=True)
+        X -= self.min_
+        X /= self.scale_
+        return X
+
+    def transform(self, X):
+        X = np.array(X, copy=True)
+        X *= self.scale_
+        X += self.min_
+        return X
+
+
+def unpack_masks(packed, layers, p, dtype=np.float32):
+    """packed uint8 [N, ceil(D/8)] -> list of L+1 scaled masks ({0, 1/(1-p)})."""
+    L, H = len(layers) - 2, int(layers[1])
+    widths = [H] * L + [H // 2]
+    bits = np.unpackbits(packed, axis=1)[:, : sum(widths)]
+    keep = dtype(1.0 - p)
+    scale = dtype(1.0) / keep
+    out, o = [], 0
+    for w in widths:
+        out.append(bits[:, o:o + w].astype(dtype) * scale)
+        o += w
+    return out
+
+
+def load_golden(name):
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    g["params"] = {k[2:]: v for k, v in g.items() if k.startswith("P:") and not k[2:].startswith("lambda")}
+    g["layers"] = [int(v) for v in g["layers"]]
+    g["p"] = float(g["p"])
+    g["sx"] = Scaler(g, "sx")
+    g["sy"] = Scaler(g, "sy")
+    return g
+
+
+@pytest.fixture(params=["net64", "net32"])
+def golden(request):
+    return load_golden(request.param)
+
+
+def nrel(a, b):
+    """Norm-relative error max|a-b| / max|b| (element-wise relative error
+    is meaningless on near-zero residuals)."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
