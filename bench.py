@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's measurement contract for the PINN hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (our CUDA path, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K ...   (reference algorithm on host cores)
+
+Workload (BASELINE.json configs[1]): the 3x64 stack-voltage PINN on N = 1M synthetic
+normal-operation samples per GPU.  One "step" is one MC-dropout sweep of T = 50 stochastic
+passes over that batch (kernel K4) -- `metric` is MC-dropout sample*passes/s; the same JSON
+line also carries PINN train steps/s (K2 + reduce + Adam) and the lambda-phase step (K3).
+`value` is timed with inputs resident in HBM; `e2e` is the same sweep through the public
+`get_MC_samples` with HOST tensors (H2D of X and D2H of the three result vectors inside).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LAYERS = [8, 64, 64, 64, 1]
+N_PER_GPU = 1_000_000
+T_PASSES = 50
+P_MC = 0.4           # 01:2158 uses dropout=0.4 for the export sweep
+P_TRAIN = 0.2        # 01:2141
+FLOP_PER_SAMPLE_PASS = 21_664      # SURVEY 8d, 3x64, layer 0 hoisted
+FLOP_PER_TRAIN_SAMPLE = 67_040     # SURVEY 8d, fwd + dgrad + wgrad
+RES_BYTES_PER_SAMPLE = 40          # x row 32 B + u 4 B + y 4 B (train_lambda form)
+METRIC = "mc_dropout_sample_passes_per_s"
+UNIT = "sample*passes/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=float(p["hbm_gbs"]), bf16=float(p["bf16_tflops"]), src="measured (MEASURED_PEAKS.json, burst)")
+    return dict(hbm=6650.0, bf16=1590.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [t.strip() for t in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_problem(n, seed):
+    import torch
+    from b200pinn.synthetic import make_scaled_dataset
+
+    x, y, sx, sy = make_scaled_dataset(n, seed)
+    return torch.tensor(x), torch.tensor(y), sx, sy
+
+
+# ------------------------------------------------------------------------- reference arm
+def cpu_port_rates(n_mc, n_train, threads):
+    """Time the reference algorithm (oracle/torch_port.py) on the host cores: one
+    get_MC_samples with T'=1 and one train_dnn step."""
+    import torch
+    from oracle.torch_port import PortPINN, get_MC_samples_port
+
+    torch.set_num_threads(threads)
+    X, Y, sx, sy = build_problem(max(n_mc, n_train), 2)
+    torch.manual_seed(0)
+    net = PortPINN(X[:n_mc], Y[:n_mc], LAYERS, sx, sy, P_TRAIN)
+    get_MC_samples_port(net, X[:2000], sx, 1, P_MC)            # warm-up
+    t0 = time.perf_counter()
+    get_MC_samples_port(net, X[:n_mc], sx, 1, P_MC)
+    t_mc = time.perf_counter() - t0
+    tr = PortPINN(X[:n_train], Y[:n_train], LAYERS, sx, sy, P_TRAIN)
+    step = tr.make_dnn_trainer()
+    t0 = time.perf_counter()
+    step()
+    t_tr = time.perf_counter() - t0
+    return n_mc / t_mc, (n_train / N_PER_GPU) / t_tr * 1.0, t_mc, t_tr
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import io
+    import contextlib
+    import torch
+    from oracle.torch_port import PortPINN, get_MC_samples_port
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    n = 200_000
+    X, Y, sx, sy = build_problem(n, 2)
+    torch.manual_seed(0)
+    net = PortPINN(X, Y, LAYERS, sx, sy, P_TRAIN)
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            get_MC_samples_port(net, X, sx, 1, P_MC)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = n * 1 * len(times) / total
+    sample = f"N={n} x T'=1 per step (1 eval pass + 1 dropout pass, each with the discarded 2nd forward, 01:1407)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: 3x64 PINN, N=1M/GPU, MC-dropout sweep T=50 (CPU arm: bounded sample)",
+                       "layers": LAYERS, "dropout": P_MC},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import b200pinn
+    from b200pinn import _abi, kernels as K
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n = args.n
+    X, Y, sx, sy = build_problem(n, 2 + rank)
+    torch.manual_seed(0)
+    model = b200pinn.PhysicsInformedNN(X, Y, LAYERS, sx, sy, P_TRAIN, True)
+    model.dnn.eval()
+    xd = model.x.detach()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    K_, W_ = args.steps, args.warmup
+
+    def timed(fn, steps, warm, do_flush=True):
+        for _ in range(warm):
+            fn()
+        barrier()
+        evs = []
+        launches0 = K.LAUNCHES
+        for _ in range(steps):
+            if do_flush:
+                flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        tot = sum(a.elapsed_time(b) for a, b in evs) / 1e3
+        return max_over_ranks(tot), K.LAUNCHES - launches0
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    # --- headline: MC-dropout sweep, inputs resident in HBM
+    seed = 1234
+    mc = lambda: b200pinn.mc_dropout_device(model.dnn, xd, T_PASSES, P_MC, seed=seed, sample_offset=rank * n)
+    t_mc, launches = timed(mc, K_, W_)
+    clocks = sampler.stop() if sampler else None
+    value = world * n * T_PASSES * K_ / t_mc
+    # --- train steps (K2 + reduce + [all-reduce] + Adam), back to back
+    steps_tr = max(K_, 5)
+    model.train_dnn(max(W_, 1), verbose=False)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    model.train_dnn(steps_tr, verbose=False)
+    b.record()
+    barrier()
+    t_tr = max_over_ranks(a.elapsed_time(b) / 1e3)
+    # --- lambda-phase step: residual kernel K3 (HBM-bound), L2 flushed every iteration
+    model.dnn.eval()
+    with torch.no_grad():
+        u = model.net_u(xd)[0].reshape(-1).contiguous()
+    yv = model.u.reshape(-1).contiguous()
+    sc, lam = model._scalers(sx), model._lambdas()
+    sums = torch.empty(_abi.S_COUNT, device=dev, dtype=torch.float64)
+    res = lambda: K.residuals(xd, u, yv, sc, lam, _abi.FAM_V | _abi.FAM_DATA, sums=sums)
+    t_res, _ = timed(res, K_, W_)
+    res_acc = lambda: K.residuals(xd, u, yv, sc, lam, _abi.FAM_V | _abi.FAM_DATA, flags=_abi.RES_ACCURATE_MATH, sums=sums)
+    t_res_acc, _ = timed(res_acc, K_, W_)
+    # --- e2e: public API, host tensors in pinned memory, results back on the host
+    Xp = X.pin_memory()
+    import contextlib
+    import io
+
+    def e2e():
+        with contextlib.redirect_stdout(io.StringIO()):
+            b200pinn.get_MC_samples(model, Xp, sx, mc_times=T_PASSES, dropout=P_MC)
+
+    for _ in range(max(1, W_)):
+        e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K_):
+        e2e()
+    barrier()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * n * T_PASSES * K_ / t_e2e
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    mc_tflops = n * T_PASSES * FLOP_PER_SAMPLE_PASS / (t_mc / K_) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": W_,
+        "ms_per_step": 1e3 * t_mc / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: 3x64 PINN (layers [8,64,64,64,1]), N=1M samples per GPU; step = MC-dropout "
+                               "sweep of T=50 passes (kernel K4)", "n_per_gpu": n, "T": T_PASSES, "dropout": P_MC,
+                   "sharding": "samples" if world > 1 else "none",
+                   "l2": "256 MB buffer written between timed steps (inputs 32 MB < 126 MB L2)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 8 * 4, "d2h_bytes_per_step": n * 3 * 4},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "achieved": mc_tflops, "peak": pk["bf16"], "unit": "TFLOP/s",
+                     "frac": mc_tflops / pk["bf16"], "traffic": None, "kernel": "mc_dropout_kernel<64,false>",
+                     "peak_source": pk["src"],
+                     "note": "K4 is an fp32 FFMA2 kernel (parity 1e-5 rules out plain TF32); against the fp32 "
+                             "CUDA-core peak 148 SM x 128 FMA x 2 x 1.965 GHz = 74.5 TFLOP/s the fraction is "
+                             f"{mc_tflops / 74.5:.3f}"},
+        "train": {"steps_per_s": steps_tr / t_tr, "ms_per_step": 1e3 * t_tr / steps_tr,
+                  "global_batch": world * n, "tflops": world * n * FLOP_PER_TRAIN_SAMPLE / (t_tr / steps_tr) / 1e12,
+                  "what": "train_dnn step: K2 (fwd+aleatoric loss+bwd+wgrad) + partial reduce + "
+                          + ("NCCL all-reduce of the flat grad bucket + " if world > 1 else "") + "fused Adam/StepLR"},
+        "roofline_residual": {"bound": "hbm", "achieved": n * RES_BYTES_PER_SAMPLE / (t_res / K_) / 1e9, "peak": pk["hbm"],
+                              "unit": "GB/s", "frac": n * RES_BYTES_PER_SAMPLE / (t_res / K_) / 1e9 / pk["hbm"],
+                              "traffic": None, "kernel": "residual_kernel<V|DATA, fast math>",
+                              "ms": 1e3 * t_res / K_, "accurate_math_ms": 1e3 * t_res_acc / K_,
+                              "lambda_steps_per_s": K_ / t_res},
+    }
+    if world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        mc_rate, tr_rate, t1, t2 = cpu_port_rates(200_000, 100_000, threads)
+        line["cpu_baseline"] = {"value": mc_rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"get_MC_samples port, N=200000 x T'=1 ({t1:.1f} s); train_dnn port 1 step at "
+                                          f"N=100000 ({t2:.1f} s)",
+                                "train_steps_per_s_at_1M": tr_rate}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=N_PER_GPU, help="samples per GPU (default: configs[1], 1M)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

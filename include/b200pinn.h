@@ -1,0 +1,186 @@
+/* b200pinn.h -- C ABI of libb200pinn.so (hand-written sm_100a CUDA kernels).
+ *
+ * The reference (ZhendongS/Physics-Informed-Neural-Network-for-Explainable-Fault-
+ * Diagnosis-in-Fuel-Cells) has no FFI: its hot path is a Python class surface in
+ * 01_train_pinn_multiphysics_model.py ("01:" below).  Each entry point here names
+ * the reference code it replaces.  The Python shims in the package bind these
+ * through ctypes; nothing in a signature is a torch type.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host or the
+ *    parameter is a by-value/by-pointer POD descriptor struct (host memory);
+ *  - all tensors are fp32, dense, row-major; weights are [out, in] like nn.Linear;
+ *  - `stream` is a cudaStream_t passed as void*; kernels never allocate or free;
+ *  - return value: 0 on success, a positive cudaError_t, or a negative PINN_E_*;
+ *  - one process per GPU; entry points are not re-entrant on the same workspace.
+ */
+#ifndef B200PINN_H
+#define B200PINN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PINN_ABI_VERSION 1
+#define PINN_N_IN 8        /* operating-condition features, 01:136-137 */
+#define PINN_MAX_HIDDEN 8  /* hidden (tanh) layers supported */
+#define PINN_N_LAMBDA 17   /* lambda_1..4, T1..5, H1..4, O1..4 (01:453-517) */
+
+enum {
+  PINN_E_ARG = -1,         /* null / inconsistent argument */
+  PINN_E_SHAPE = -2,       /* unsupported layer widths */
+  PINN_E_WORKSPACE = -3,   /* workspace too small */
+  PINN_E_ALIGN = -4        /* pointer not 16-byte aligned */
+};
+
+/* DNN of 01:389-438: n_hidden x [Linear -> Tanh -> Dropout(p)], a linear mean head
+ * `predict`, and the variance head Linear(H,H/2)-Tanh-Dropout-Linear(H/2,H/4)-Tanh-
+ * Linear(H/4,1) followed by log(softplus(.)+1e-6).  width in {32,64,128,256}. */
+typedef struct pinn_net {
+  int32_t n_in;      /* must be PINN_N_IN */
+  int32_t width;     /* H */
+  int32_t n_hidden;  /* L, 1..PINN_MAX_HIDDEN */
+  int32_t reserved;
+  const float* W[PINN_MAX_HIDDEN]; /* layers.layer_i.weight [H, in_i]           */
+  const float* b[PINN_MAX_HIDDEN]; /* layers.layer_i.bias   [H]                 */
+  const float* Wp;  const float* bp;   /* predict        [1,H]     [1]          */
+  const float* Wv0; const float* bv0;  /* var_layers.0   [H/2,H]   [H/2]        */
+  const float* Wv1; const float* bv1;  /* var_layers.3   [H/4,H/2] [H/4]        */
+  const float* Wv2; const float* bv2;  /* var_layers.5   [1,H/4]   [1]          */
+} pinn_net_t;
+
+/* Dropout control.  p == 0 means eval mode.  With masks == NULL the keep mask of
+ * (sample s, pass t, dropout layer l, unit j) is drawn from Philox4x32-10 keyed by
+ * `seed` with counter (s, t, l, j/4) -- identical for any GPU count or sharding.
+ * With masks != NULL the keep bits are read from masks[t][s][D], uint8 0/1,
+ * D = L*H + H/2 (trunk layers in order, then the variance head) -- used to inject
+ * the reference's own masks for parity, since the RNG streams differ.
+ * Scale is 1/(1-p) as in torch (bernoulli_(1-p).div_(1-p)). */
+typedef struct pinn_dropout {
+  float p;
+  int32_t reserved;
+  uint64_t seed;
+  int64_t sample_offset;   /* global index of the shard's first sample          */
+  int64_t pass_offset;     /* global index of the first pass (MC) / step (train) */
+  int64_t mask_sample_stride_n; /* N of the masks array (rows per pass)          */
+  const uint8_t* masks;
+} pinn_dropout_t;
+
+/* Number of fp32 parameters of the DNN in canonical flat order
+ * (W0,b0,...,W{L-1},b{L-1},Wp,bp,Wv0,bv0,Wv1,bv1,Wv2,bv2 == dnn.parameters()). */
+int64_t pinn_param_count(int32_t width, int32_t n_hidden);
+
+/* K1 -- DNN.forward (01:421-438): out_u[n], out_logvar[n]. */
+int pinn_mlp_fwd(const pinn_net_t* net, const float* x, int64_t n,
+                 const pinn_dropout_t* drop, float* out_u, float* out_logvar,
+                 void* workspace, size_t workspace_bytes, void* stream);
+size_t pinn_mlp_fwd_workspace_bytes(int32_t width, int32_t n_hidden, int64_t n);
+
+/* K2 -- backward of DNN.forward (autograd of 01:953) with the forward recomputed
+ * in-kernel.  Upstream gradients are either given (grad_u, grad_logvar: [n]) or,
+ * when both are NULL, produced in-kernel from the aleatoric loss 01:916-927 against
+ * y[n] with mean over n_global samples.  grad_flat[P] receives the (unnormalised-
+ * by-nothing-else) parameter gradients of this shard in canonical flat order;
+ * loss_sums[4] (double) = {sum 0.5*exp(-s)(y-u)^2+0.5 s, sum |s|, sum (y-u)^2, n}. */
+int pinn_mlp_bwd(const pinn_net_t* net, const float* x, int64_t n,
+                 const pinn_dropout_t* drop, const float* grad_u,
+                 const float* grad_logvar, const float* y, int64_t n_global,
+                 float* grad_flat, double* loss_sums, void* workspace,
+                 size_t workspace_bytes, void* stream);
+size_t pinn_mlp_bwd_workspace_bytes(int32_t width, int32_t n_hidden, int64_t n);
+
+/* K3 -- multi-physics residuals + reductions: net_f_V 01:724-765, net_f_T_simple
+ * 01:869-914, net_f_T 01:767-867, net_f_H 01:621-722, net_f_O 01:535-619, the
+ * mean(f^2) losses 01:1029-1034,1112,1222,1360 and their lambda-gradients. */
+typedef struct pinn_scalers {
+  float x_inv_scale[PINN_N_IN]; /* 1/scaler_X.scale_                             */
+  float x_off[PINN_N_IN];       /* scaler_X.min_/scaler_X.scale_                 */
+  float y_inv_scale, y_off;     /* same for scaler_Y (V = u*inv - off)           */
+  float scale_y, min_y;         /* train_lambda's rebuilt affine 01:1017-1022    */
+  float p_h2o;                  /* 10**x at Tc=55, 01:752-753 (fp32 on host)     */
+  float reserved;
+} pinn_scalers_t;
+
+enum { /* families bitmask */
+  PINN_FAM_V = 1, PINN_FAM_TS = 2, PINN_FAM_T = 4, PINN_FAM_H = 8, PINN_FAM_O = 16,
+  PINN_FAM_DATA = 32 /* sum (y-u)^2, needs y */
+};
+enum { /* flags */
+  PINN_RES_ACCURATE_MATH = 1 /* libdevice logf/expf/powf instead of MUFU approximations */
+};
+enum { /* sums[] slots (double) */
+  PINN_S_N = 0,
+  PINN_S_FV2, PINN_S_EA2, PINN_S_DATA2,          /* sum f_V^2, sum (y-Vn)^2, sum (y-u)^2 */
+  PINN_S_GA1, PINN_S_GA2, PINN_S_GA3,            /* d sum (y-Vn)^2 / d lambda_1..3       */
+  PINN_S_GB1, PINN_S_GB2, PINN_S_GB3,            /* d sum f_V^2    / d lambda_1..3       */
+  PINN_S_FT2, PINN_S_FTABS, PINN_S_GT1, PINN_S_GT3, PINN_S_GT5,
+  PINN_S_FTE2,                                   /* sum f_T(Euler)^2                     */
+  PINN_S_FH2, PINN_S_GH1, PINN_S_GH2, PINN_S_GH3, PINN_S_HACT, PINN_S_HTGT,
+  PINN_S_FO2, PINN_S_GO1, PINN_S_GO2, PINN_S_GO3, PINN_S_OACT, PINN_S_OTGT,
+  PINN_S_COUNT
+};
+enum { /* cols[] rows: cols is [PINN_C_COUNT][n] or NULL; a row is written iff its family is on */
+  PINN_C_FV = 0, PINN_C_VACT, PINN_C_VOHM, PINN_C_VCONC, PINN_C_ENERNST, PINN_C_VEST5,
+  PINN_C_I, PINN_C_VOUT5,
+  PINN_C_FTS, PINN_C_TS_PRED, PINN_C_T_REAL,
+  PINN_C_FT, PINN_C_T_PRED,
+  PINN_C_FH, PINN_C_H_ACT, PINN_C_H_TGT, PINN_C_I_TOTAL,
+  PINN_C_FO, PINN_C_O_ACT, PINN_C_O_TGT, PINN_C_O_Q, PINN_C_O2,
+  PINN_C_COUNT
+};
+/* x[n,8] normalised; u[n] DNN prediction (normalised, may be NULL if no family needs
+ * it); y[n] normalised labels (NULL unless FAM_DATA / mode-A sums wanted);
+ * lambdas[17] device; halo_x[8]/halo_u[1]: row preceding x[0] for net_f_T when this
+ * shard is not the start of the series (NULL => T_pred[0] = T_out[0], 01:857). */
+int pinn_residuals(const float* x, const float* u, const float* y, int64_t n,
+                   const pinn_scalers_t* scalers, const float* lambdas,
+                   uint32_t families, uint32_t flags, const float* halo_x,
+                   const float* halo_u, float* cols, double* sums,
+                   void* workspace, size_t workspace_bytes, void* stream);
+size_t pinn_residuals_workspace_bytes(int64_t n);
+
+/* K4 -- get_MC_samples (01:1413-1491): one eval forward + T dropout passes with
+ * running Welford statistics; per-pass activations are never materialised.
+ * Finalised outputs (any may be NULL): pred_mean[n] = eval forward,
+ * a_u[n] = sqrt(exp(mean_t logvar_t)), e_u[n] = sqrt(var_t u_t) (ddof 0).
+ * Raw outputs for pass-sharded merging (any may be NULL): raw_mean[n], raw_m2[n],
+ * raw_sum_logvar[n] over this call's T passes. */
+int pinn_mc_dropout(const pinn_net_t* net, const float* x, int64_t n, int32_t T,
+                    const pinn_dropout_t* drop, float* pred_mean, float* a_u,
+                    float* e_u, float* raw_mean, float* raw_m2,
+                    float* raw_sum_logvar, void* workspace, size_t workspace_bytes,
+                    void* stream);
+size_t pinn_mc_workspace_bytes(int32_t width, int32_t n_hidden, int64_t n);
+
+/* f3 -- torch.optim.Adam (defaults) + StepLR + box clamp, fused, state on device
+ * (01:939-940,999-1002,1040-1047,...).  step_counter is int64[2] on the device, zeroed
+ * once by the caller: [0] = steps taken so far (read, then incremented when
+ * advance_counter != 0), [1] = internal ticket.  lr = lr0 * gamma^(step/step_size).
+ * grad_scale multiplies grads first (1/N for summed gradients).  active (uint8[n],
+ * optional) mirrors torch skipping parameters whose .grad is None.  lo/hi optional. */
+int pinn_adam_step(float* params, const float* grads, float* exp_avg,
+                   float* exp_avg_sq, int64_t n, int64_t* step_counter, double lr0,
+                   double gamma, int64_t step_size, double grad_scale,
+                   const uint8_t* active, const float* lo, const float* hi,
+                   int32_t advance_counter, void* stream);
+/* Same update for the physics scalars (n <= 32); gradients come as the double sums
+ * of pinn_residuals: grad[i] = sums[grad_slot[i]] / sums[PINN_S_N]; slot < 0 => the
+ * scalar gets no gradient (torch skips it) but is still clamped, as 01:1040-1047 do. */
+int pinn_adam_step_from_sums(float* params, const double* sums,
+                             const int32_t* grad_slot, float* exp_avg,
+                             float* exp_avg_sq, int64_t n, int64_t* step_counter,
+                             double lr0, double gamma, int64_t step_size,
+                             const float* lo, const float* hi, void* stream);
+
+int pinn_abi_version(void);
+const char* pinn_error_string(int code);
+/* Device facts the host layer sizes grids with (SM count etc.). */
+int pinn_device_sm_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PINN_H */

@@ -1,0 +1,132 @@
+// adam_misc.cu -- f3: torch.optim.Adam (default betas/eps) + StepLR + box clamp fused into
+// one launch with all state on the device, so a whole training phase of the reference
+// (01:939-955, 999-1055, 1098-1151, 1191-1274, 1344-1391) replays without host syncs.
+// Also: ABI version / error strings / device facts.
+#include "common.cuh"
+
+namespace pinn {
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cached[dev] = v;
+  }
+  return cached[dev];
+}
+
+struct AdamHyper {
+  double lr0, gamma, grad_scale;
+  int64_t step_size;
+};
+
+// torch/optim/adam.py (_single_tensor_adam): exp_avg.lerp_(g, 1-b1); exp_avg_sq = b2*v + (1-b2) g^2;
+// step_size = lr / (1-b1^t); denom = sqrt(v)/sqrt(1-b2^t) + eps; p -= step_size * m/denom.
+PINN_D void adam_update(float& p, float g, float& m, float& v, double lr, int64_t t, float lo, float hi,
+                        bool clamp) {
+  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+  m = m + (g - m) * (1.0f - b1);
+  v = v * b2 + (1.0f - b2) * g * g;
+  const double bc1 = 1.0 - pow(0.9, static_cast<double>(t));
+  const double bc2 = 1.0 - pow(0.999, static_cast<double>(t));
+  const float step = static_cast<float>(lr / bc1);
+  const float denom = sqrtf(v) / static_cast<float>(sqrt(bc2)) + eps;
+  float q = p - step * (m / denom);
+  if (clamp) q = fminf(fmaxf(q, lo), hi);
+  p = q;
+}
+
+__global__ void adam_kernel(float* __restrict__ params, const float* __restrict__ grads, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, int64_t* step_counter, AdamHyper h,
+                            const uint8_t* __restrict__ active, const float* __restrict__ lo,
+                            const float* __restrict__ hi, int advance) {
+  const int64_t t0 = *step_counter;  // steps taken so far
+  const double lr = h.lr0 * pow(h.gamma, static_cast<double>(t0 / h.step_size));
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n && (active == nullptr || active[i])) {
+    float g = static_cast<float>(static_cast<double>(grads[i]) * h.grad_scale);
+    float p = params[i], mm = m[i], vv = v[i];
+    adam_update(p, g, mm, vv, lr, t0 + 1, lo ? lo[i] : 0.f, hi ? hi[i] : 0.f, lo != nullptr && hi != nullptr);
+    params[i] = p; m[i] = mm; v[i] = vv;
+  }
+  if (advance) {
+    // every thread has read t0 before any CTA can finish; the last CTA to arrive bumps it
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int* ticket = reinterpret_cast<unsigned int*>(step_counter + 1);
+      last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+      if (last) { *ticket = 0u; *step_counter = t0 + 1; }
+    }
+  }
+}
+
+// Small-vector variant for the 17 physics scalars: gradients are double sums produced by
+// pinn_residuals; sums[PINN_S_N] is the sample count (mean = sum / count).
+__global__ void adam_from_sums_kernel(float* params, const double* sums, const int32_t* grad_slot, float* m,
+                                      float* v, int n, int64_t* step_counter, AdamHyper h, const float* lo,
+                                      const float* hi) {
+  const int64_t t0 = *step_counter;
+  const double lr = h.lr0 * pow(h.gamma, static_cast<double>(t0 / h.step_size));
+  const int i = threadIdx.x;
+  const double cnt = sums[PINN_S_N];
+  if (i < n && grad_slot[i] >= 0) {
+    float g = static_cast<float>(sums[grad_slot[i]] / (cnt > 0.0 ? cnt : 1.0));
+    float p = params[i], mm = m[i], vv = v[i];
+    adam_update(p, g, mm, vv, lr, t0 + 1, lo ? lo[i] : 0.f, hi ? hi[i] : 0.f, lo != nullptr && hi != nullptr);
+    params[i] = p; m[i] = mm; v[i] = vv;
+  } else if (i < n && lo != nullptr && hi != nullptr) {
+    params[i] = fminf(fmaxf(params[i], lo[i]), hi[i]);  // reference clamps every listed scalar each step
+  }
+  __syncthreads();
+  if (i == 0) *step_counter = t0 + 1;
+}
+
+}  // namespace pinn
+
+using namespace pinn;
+
+extern "C" int pinn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                              int64_t* step_counter, double lr0, double gamma, int64_t step_size,
+                              double grad_scale, const uint8_t* active, const float* lo, const float* hi,
+                              int32_t advance_counter, void* stream) {
+  if (n < 0 || !step_counter || step_size <= 0) return PINN_E_ARG;
+  if (n == 0) return 0;
+  if (!params || !grads || !exp_avg || !exp_avg_sq) return PINN_E_ARG;
+  AdamHyper h{lr0, gamma, grad_scale, step_size};
+  const int grid = static_cast<int>((n + 255) / 256);
+  adam_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, n,
+                                                                  step_counter, h, active, lo, hi, advance_counter);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int pinn_adam_step_from_sums(float* params, const double* sums, const int32_t* grad_slot,
+                                        float* exp_avg, float* exp_avg_sq, int64_t n, int64_t* step_counter,
+                                        double lr0, double gamma, int64_t step_size, const float* lo,
+                                        const float* hi, void* stream) {
+  if (n <= 0 || n > 32 || !params || !sums || !grad_slot || !exp_avg || !exp_avg_sq || !step_counter ||
+      step_size <= 0)
+    return PINN_E_ARG;
+  AdamHyper h{lr0, gamma, 1.0, step_size};
+  adam_from_sums_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(params, sums, grad_slot, exp_avg,
+                                                                        exp_avg_sq, static_cast<int>(n),
+                                                                        step_counter, h, lo, hi);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int pinn_abi_version(void) { return PINN_ABI_VERSION; }
+extern "C" int pinn_device_sm_count(void) { return sm_count(); }
+extern "C" const char* pinn_error_string(int code) {
+  switch (code) {
+    case 0: return "success";
+    case PINN_E_ARG: return "b200pinn: null or inconsistent argument";
+    case PINN_E_SHAPE: return "b200pinn: unsupported network shape (n_in must be 8, width in {32,64,128,256}, 1..8 hidden layers)";
+    case PINN_E_WORKSPACE: return "b200pinn: workspace missing or too small";
+    case PINN_E_ALIGN: return "b200pinn: pointer not 16-byte aligned";
+    default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "b200pinn: unknown error";
+  }
+}

@@ -1,0 +1,197 @@
+// common.cuh -- shared device/host helpers for libb200pinn (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/b200pinn.h"
+
+#define PINN_HD __host__ __device__ __forceinline__
+#define PINN_D __device__ __forceinline__
+
+#define PINN_CUDA_TRY(expr)                          \
+  do {                                               \
+    cudaError_t _e = (expr);                         \
+    if (_e != cudaSuccess) return static_cast<int>(_e); \
+  } while (0)
+
+namespace pinn {
+
+// ------------------------------------------------------------------ Philox4x32-10
+// Counter-based RNG (Salmon et al. 2011).  counter = (sample_lo, sample_hi, pass,
+// layer<<16 | unit/4), key = seed: a mask bit depends only on global indices, so
+// results are identical for any grid, GPU count or sharding.
+struct Philox {
+  static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  static constexpr uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+
+  static PINN_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#ifdef __CUDA_ARCH__
+    lo = a * b;
+    hi = __umulhi(a, b);
+#else
+    uint64_t p = static_cast<uint64_t>(a) * b;
+    lo = static_cast<uint32_t>(p);
+    hi = static_cast<uint32_t>(p >> 32);
+#endif
+  }
+
+  static PINN_HD uint4 gen(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2,
+                           uint32_t c3) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t hi0, lo0, hi1, lo1;
+      mulhilo(M0, c0, hi0, lo0);
+      mulhilo(M1, c2, hi1, lo1);
+      uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+      c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+      k0 += W0; k1 += W1;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+
+// Dropout draw context for one sample and one pass.
+struct DropCtx {
+  uint32_t k0, k1;       // key
+  uint32_t s_lo, s_hi;   // global sample index
+  uint32_t pass;         // global pass / step index
+  uint32_t thresh;       // drop iff r < thresh  (thresh = p * 2^32)
+  float scale;           // 1/(1-p), fp32 like torch
+  float keep;            // (1-p) in fp32
+  const uint8_t* mrow;   // injected keep bits of this (pass, sample): D bytes, or nullptr
+  bool active;           // p > 0
+};
+
+PINN_HD uint32_t drop_threshold(float p) {
+  double t = static_cast<double>(p) * 4294967296.0;
+  if (t <= 0.0) return 0u;
+  if (t >= 4294967295.0) return 0xFFFFFFFFu;
+  return static_cast<uint32_t>(t);
+}
+PINN_HD float drop_scale(float p) {
+  float keep = static_cast<float>(1.0 - static_cast<double>(p));  // torch: double 1-p, cast to fp32
+  return 1.0f / keep;
+}
+
+// Keep-multipliers ({0, scale}) of 4 consecutive units [j0, j0+4) of dropout layer
+// `layer`; `unit_base` is the byte offset of that layer inside an injected mask row.
+PINN_HD void drop4(const DropCtx& c, uint32_t layer, uint32_t j0, uint32_t unit_base, float m[4]) {
+  if (c.mrow != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) m[q] = c.mrow[unit_base + j0 + q] ? c.scale : 0.0f;
+    return;
+  }
+  uint4 r = Philox::gen(c.k0, c.k1, c.s_lo, c.s_hi, c.pass, (layer << 16) | (j0 >> 2));
+  m[0] = r.x < c.thresh ? 0.0f : c.scale;
+  m[1] = r.y < c.thresh ? 0.0f : c.scale;
+  m[2] = r.z < c.thresh ? 0.0f : c.scale;
+  m[3] = r.w < c.thresh ? 0.0f : c.scale;
+}
+
+// Host-built, kernel-parameter form of pinn_dropout_t.
+struct DropParams {
+  float p;
+  uint32_t thresh;
+  float scale, keep;
+  uint32_t k0, k1;
+  int64_t sample_offset, pass_offset, mask_n;
+  const uint8_t* masks;
+};
+inline DropParams make_drop_params(const pinn_dropout_t* d) {
+  DropParams q{};
+  q.scale = 1.f;
+  q.keep = 1.f;
+  if (d && d->p > 0.f) {
+    q.p = d->p;
+    q.thresh = drop_threshold(d->p);
+    q.scale = drop_scale(d->p);
+    q.keep = static_cast<float>(1.0 - static_cast<double>(d->p));
+    q.k0 = static_cast<uint32_t>(d->seed);
+    q.k1 = static_cast<uint32_t>(d->seed >> 32);
+    q.sample_offset = d->sample_offset;
+    q.pass_offset = d->pass_offset;
+    q.mask_n = d->mask_sample_stride_n;
+    q.masks = d->masks;
+  }
+  return q;
+}
+// Context of (shard-local sample s_local, shard-local pass pass_local); D = mask row bytes.
+PINN_HD DropCtx make_ctx(const DropParams& dp, int64_t s_local, int64_t pass_local, int D, bool active,
+                         bool has_mask_row = true) {
+  DropCtx c;
+  c.k0 = dp.k0; c.k1 = dp.k1;
+  uint64_t sg = static_cast<uint64_t>(dp.sample_offset + s_local);
+  c.s_lo = static_cast<uint32_t>(sg); c.s_hi = static_cast<uint32_t>(sg >> 32);
+  c.pass = static_cast<uint32_t>(dp.pass_offset + pass_local);
+  c.thresh = dp.thresh; c.scale = dp.scale; c.keep = dp.keep;
+  c.active = active && dp.p > 0.f;
+  c.mrow = nullptr;
+  if (c.active && dp.masks) {
+    if (has_mask_row) c.mrow = dp.masks + (static_cast<size_t>(pass_local) * dp.mask_n + s_local) * D;
+    else c.active = false;  // tail slot of a tile: no mask row exists, contributes nothing
+  }
+  return c;
+}
+
+// ------------------------------------------------------------------------ math
+// log(softplus(v) + 1e-6), softplus with torch's threshold 20 (01:432-434).
+PINN_HD float softplus_f(float v) { return v > 20.0f ? v : log1pf(expf(v)); }
+PINN_HD float logvar_from_v(float v) { return logf(softplus_f(v) + 1e-6f); }
+// d logvar / d v  
+PINN_HD float dlogvar_dv(float v) {
+  float sp = softplus_f(v);
+  float sg = v > 20.0f ? 1.0f : 1.0f / (1.0f + expf(-v));
+  return sg / (sp + 1e-6f);
+}
+
+// ------------------------------------------------------------- parameter layout
+// Canonical flat order == dnn.parameters() order (01:399-419).
+struct ParamLayout {
+  int H, L;
+  int64_t offW[PINN_MAX_HIDDEN], offb[PINN_MAX_HIDDEN];
+  int64_t offWp, offbp, offWv0, offbv0, offWv1, offbv1, offWv2, offbv2, total;
+};
+PINN_HD ParamLayout make_layout(int H, int L) {
+  ParamLayout p;
+  p.H = H; p.L = L;
+  int64_t o = 0;
+  for (int l = 0; l < PINN_MAX_HIDDEN; ++l) { p.offW[l] = 0; p.offb[l] = 0; }
+  // every tensor starts on a 16-byte boundary (128-bit weight loads); the two
+  // single-element biases are padded to 4 floats.
+  auto pad4 = [](int64_t v) { return (v + 3) & ~static_cast<int64_t>(3); };
+  for (int l = 0; l < L; ++l) {
+    int in = l == 0 ? PINN_N_IN : H;
+    p.offW[l] = o; o = pad4(o + static_cast<int64_t>(H) * in);
+    p.offb[l] = o; o = pad4(o + H);
+  }
+  p.offWp = o; o = pad4(o + H);
+  p.offbp = o; o = pad4(o + 1);
+  p.offWv0 = o; o = pad4(o + static_cast<int64_t>(H / 2) * H);
+  p.offbv0 = o; o = pad4(o + H / 2);
+  p.offWv1 = o; o = pad4(o + static_cast<int64_t>(H / 4) * (H / 2));
+  p.offbv1 = o; o = pad4(o + H / 4);
+  p.offWv2 = o; o = pad4(o + H / 4);
+  p.offbv2 = o; o = pad4(o + 1);
+  p.total = o;
+  return p;
+}
+
+inline int validate_net(const pinn_net_t* net) {
+  if (!net) return PINN_E_ARG;
+  if (net->n_in != PINN_N_IN) return PINN_E_SHAPE;
+  if (net->n_hidden < 1 || net->n_hidden > PINN_MAX_HIDDEN) return PINN_E_SHAPE;
+  int H = net->width;
+  if (!(H == 32 || H == 64 || H == 128 || H == 256)) return PINN_E_SHAPE;
+  for (int l = 0; l < net->n_hidden; ++l)
+    if (!net->W[l] || !net->b[l]) return PINN_E_ARG;
+  if (!net->Wp || !net->bp || !net->Wv0 || !net->bv0 || !net->Wv1 || !net->bv1 || !net->Wv2 ||
+      !net->bv2)
+    return PINN_E_ARG;
+  return 0;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device
+
+}  // namespace pinn

@@ -1,0 +1,295 @@
+// residuals.cu -- K3: one streaming pass over x_norm[N,8] (+u, +y) that evaluates every
+// physics residual of the reference and reduces the losses and analytic lambda-gradients.
+//
+//   net_f_V 01:724-765 | net_f_T_simple 01:869-914 | net_f_T 01:767-867
+//   net_f_H 01:621-722 | net_f_O 01:535-619 | losses 01:1029-1034,1112,1222,1360
+//
+// The reference crosses PCIe twice per residual call (sklearn inverse_transform on host
+// numpy, 01:726-737) and launches ~40 elementwise kernels; here the scaler affine runs
+// in-kernel and the row is read once: 32 B x-row + 4 B u (+4 B y) per sample, HBM-bound.
+// Loads are 128-bit, grid = a multiple of the SM count, reductions go warp-shuffle ->
+// shared -> per-CTA partial (double) -> last-CTA fixed-order sum (deterministic).
+#include "common.cuh"
+
+namespace pinn {
+
+constexpr int kResThreads = 256;
+constexpr int kResCtasPerSm = 3;
+
+template <bool ACC> PINN_D float f_log(float v) { return ACC ? logf(v) : __logf(v); }
+template <bool ACC> PINN_D float f_exp(float v) { return ACC ? expf(v) : __expf(v); }
+template <bool ACC> PINN_D float f_div(float a, float b) { return ACC ? a / b : __fdividef(a, b); }
+template <bool ACC> PINN_D float f_pow(float a, float b) { return ACC ? powf(a, b) : __powf(a, b); }
+
+struct Row { float r[PINN_N_IN]; };
+
+PINN_D Row load_phys(const float* __restrict__ x, int64_t s, const pinn_scalers_t& sc) {
+  const float4* p = reinterpret_cast<const float4*>(x + s * PINN_N_IN);
+  float4 a = __ldg(p), b = __ldg(p + 1);
+  Row o;
+  o.r[0] = fmaf(a.x, sc.x_inv_scale[0], -sc.x_off[0]);
+  o.r[1] = fmaf(a.y, sc.x_inv_scale[1], -sc.x_off[1]);
+  o.r[2] = fmaf(a.z, sc.x_inv_scale[2], -sc.x_off[2]);
+  o.r[3] = fmaf(a.w, sc.x_inv_scale[3], -sc.x_off[3]);
+  o.r[4] = fmaf(b.x, sc.x_inv_scale[4], -sc.x_off[4]);
+  o.r[5] = fmaf(b.y, sc.x_inv_scale[5], -sc.x_off[5]);
+  o.r[6] = fmaf(b.z, sc.x_inv_scale[6], -sc.x_off[6]);
+  o.r[7] = fmaf(b.w, sc.x_inv_scale[7], -sc.x_off[7]);
+  return o;
+}
+
+struct Lam {  // 01:453-517 order
+  float l1, l2, l3, l4, T1, T2, T3, T4, T5, H1, H2, H3, H4, O1, O2, O3, O4;
+};
+
+template <uint32_t FAMC, bool ACC>
+PINN_D void eval_sample(const float* __restrict__ x, const float* __restrict__ u, const float* __restrict__ y,
+                        int64_t s, int64_t n, const pinn_scalers_t& sc, const Lam& L, uint32_t fam,
+                        const float* halo_x, const float* halo_u, float* __restrict__ cols, float* acc) {
+  constexpr float A = 270.0f, F = 96485.0f, R = 8.314f, NC = 5.0f, ALPHA = 0.5f;
+  const Row row = load_phys(x, s, sc);
+  const float* r = row.r;
+  acc[PINN_S_N] += 1.0f;
+  auto put = [&](int c, float v) { if (cols) cols[static_cast<size_t>(c) * n + s] = v; };
+  float us = 0.f, ys = 0.f;
+  if ((FAMC & (PINN_FAM_V | PINN_FAM_DATA | PINN_FAM_T)) && (fam & (PINN_FAM_V | PINN_FAM_DATA | PINN_FAM_T)) && u) us = __ldg(u + s);
+  if ((FAMC & (PINN_FAM_V | PINN_FAM_DATA)) && y) ys = __ldg(y + s);
+
+  if ((FAMC & PINN_FAM_V) && (fam & PINN_FAM_V)) {
+    const float i = f_div<ACC>(r[0], A) + 1e-5f;
+    const float Tk = r[5] + 273.15f;
+    const float PH2 = f_div<ACC>(r[3], 101.0f) + 1.0f;
+    const float Pair = f_div<ACC>(r[4], 101.0f) + 1.0f;
+    const float tkp = f_pow<ACC>(Tk, 1.334f);
+    const float z = f_div<ACC>(i, tkp);
+    float ppH2, ppO2, lnterm;
+    if (ACC) {
+      ppH2 = 0.5f * (PH2 / expf(1.653f * z) - sc.p_h2o);
+      ppO2 = Pair / expf(4.192f * z) - sc.p_h2o;
+      lnterm = logf(sc.p_h2o / (ppH2 * sqrtf(ppO2)));
+    } else {
+      ppH2 = 0.5f * (PH2 * __expf(-1.653f * z) - sc.p_h2o);
+      ppO2 = Pair * __expf(-4.192f * z) - sc.p_h2o;
+      lnterm = __logf(sc.p_h2o) - __logf(ppH2) - 0.5f * __logf(ppO2);
+    }
+    const float b = R * Tk / (2.0f * ALPHA * F);
+    const float Vact = -b * f_log<ACC>(f_div<ACC>(i, L.l2));
+    const float Vohm = -(i * L.l1);
+    const float Vconc = ALPHA * b * f_log<ACC>(1.0f - f_div<ACC>(i, L.l3));
+    const float E = 220170.0f / (2.0f * F) - (R * Tk) * lnterm / (2.0f * F);
+    const float Vest = E + Vact + Vohm + Vconc;
+    const float Vout = fmaf(us, sc.y_inv_scale, -sc.y_off) / NC;
+    const float fV = Vest - Vout;
+    const float d1 = -i, d2 = f_div<ACC>(b, L.l2), d3 = f_div<ACC>(ALPHA * b * i, L.l3 * (L.l3 - i));
+    acc[PINN_S_FV2] = fmaf(fV, fV, acc[PINN_S_FV2]);
+    const float gB = 2.0f * fV;
+    acc[PINN_S_GB1] = fmaf(gB, d1, acc[PINN_S_GB1]);
+    acc[PINN_S_GB2] = fmaf(gB, d2, acc[PINN_S_GB2]);
+    acc[PINN_S_GB3] = fmaf(gB, d3, acc[PINN_S_GB3]);
+    if (y) {
+      const float eA = ys - fmaf(Vest * NC, sc.scale_y, sc.min_y);
+      const float gA = -2.0f * NC * sc.scale_y * eA;
+      acc[PINN_S_EA2] = fmaf(eA, eA, acc[PINN_S_EA2]);
+      acc[PINN_S_GA1] = fmaf(gA, d1, acc[PINN_S_GA1]);
+      acc[PINN_S_GA2] = fmaf(gA, d2, acc[PINN_S_GA2]);
+      acc[PINN_S_GA3] = fmaf(gA, d3, acc[PINN_S_GA3]);
+    }
+    put(PINN_C_FV, fV); put(PINN_C_VACT, Vact); put(PINN_C_VOHM, Vohm); put(PINN_C_VCONC, Vconc);
+    put(PINN_C_ENERNST, E); put(PINN_C_VEST5, Vest * NC); put(PINN_C_I, i); put(PINN_C_VOUT5, Vout * NC);
+  }
+  if ((FAMC & PINN_FAM_DATA) && (fam & PINN_FAM_DATA) && y && u) {
+    const float e = ys - us;
+    acc[PINN_S_DATA2] = fmaf(e, e, acc[PINN_S_DATA2]);
+  }
+  if ((FAMC & PINN_FAM_TS) && (fam & PINN_FAM_TS)) {
+    const float i = f_div<ACC>(r[0], A) + 1e-6f;
+    const float It = i * A, m = r[1] + 1e-6f;
+    const float Tp = L.T1 * It + L.T3 * m + 0.5f * r[2] + L.T5;
+    const float fT = r[5] - Tp;
+    acc[PINN_S_FT2] = fmaf(fT, fT, acc[PINN_S_FT2]);
+    acc[PINN_S_FTABS] += fabsf(fT);
+    const float g = -2.0f * fT;
+    acc[PINN_S_GT1] = fmaf(g, It, acc[PINN_S_GT1]);
+    acc[PINN_S_GT3] = fmaf(g, m, acc[PINN_S_GT3]);
+    acc[PINN_S_GT5] += g;
+    put(PINN_C_FTS, fT); put(PINN_C_TS_PRED, Tp); put(PINN_C_T_REAL, r[5]);
+  }
+  if ((FAMC & PINN_FAM_T) && (fam & PINN_FAM_T)) {
+    float Tp = r[5];
+    const bool first = (s == 0);
+    if (!first || (halo_x && halo_u)) {
+      Row pr;
+      float up;
+      if (first) {
+        for (int j = 0; j < PINN_N_IN; ++j) pr.r[j] = fmaf(__ldg(halo_x + j), sc.x_inv_scale[j], -sc.x_off[j]);
+        up = __ldg(halo_u);
+      } else {
+        pr = load_phys(x, s - 1, sc);
+        up = __ldg(u + s - 1);
+      }
+      const float ip = f_div<ACC>(pr.r[0], A) + 1e-5f;
+      const float It = ip * A, mp = pr.r[1] + 1e-6f;
+      const float Vrev = 1.229f - 0.0009f * ((pr.r[5] + 273.15f) - 298.15f);
+      const float Vcell = fmaf(up, sc.y_inv_scale, -sc.y_off) / NC;
+      const float Qe = (It * Vrev - It * Vcell) * L.T4;
+      const float Qc = mp * 4180.0f * (pr.r[5] - pr.r[2]) * L.T1;
+      const float Qr = 4.0f * (pr.r[5] - 25.0f) * L.T3;
+      Tp = pr.r[5] + ((Qe - Qc - Qr) / L.T2) * 0.1f;
+    }
+    const float fT = r[5] - Tp;
+    acc[PINN_S_FTE2] = fmaf(fT, fT, acc[PINN_S_FTE2]);
+    put(PINN_C_FT, fT); put(PINN_C_T_PRED, Tp);
+    if (!((FAMC & PINN_FAM_TS) && (fam & PINN_FAM_TS))) put(PINN_C_T_REAL, r[5]);
+  }
+  if ((FAMC & (PINN_FAM_H | PINN_FAM_O)) && (fam & (PINN_FAM_H | PINN_FAM_O))) {
+    const float i = f_div<ACC>(r[0], A) + 1e-5f;
+    const float It = i * A;
+    if ((FAMC & PINN_FAM_H) && (fam & PINN_FAM_H)) {
+      float Q = It / (2.0f * F) * NC * 22.4f * 60.0f;
+      Q = fmaxf(Q, 1e-8f);
+      const bool lin = It <= L.H3;
+      const float sel = lin ? It : L.H3;
+      const float tgt = L.H1 + L.H2 * (sel / 100.0f);
+      const float act = f_div<ACC>(r[6] + 1e-6f, Q);
+      const float fH = act - tgt;
+      const float g = -2.0f * fH;
+      acc[PINN_S_FH2] = fmaf(fH, fH, acc[PINN_S_FH2]);
+      acc[PINN_S_GH1] += g;
+      acc[PINN_S_GH2] = fmaf(g, sel / 100.0f, acc[PINN_S_GH2]);
+      acc[PINN_S_GH3] += lin ? 0.0f : g * (L.H2 / 100.0f);
+      acc[PINN_S_HACT] += act;
+      acc[PINN_S_HTGT] += tgt;
+      put(PINN_C_FH, fH); put(PINN_C_H_ACT, act); put(PINN_C_H_TGT, tgt); put(PINN_C_I_TOTAL, It);
+    }
+    if ((FAMC & PINN_FAM_O) && (fam & PINN_FAM_O)) {
+      float Q = (It * NC) / (4.0f * F) * 22.4f * 60.0f;
+      Q = fmaxf(Q, 1e-8f);
+      const float th = fabsf(L.O3);
+      const bool lin = It <= th;
+      const float sel = lin ? It : th;
+      const float raw = L.O1 + L.O2 * (sel / 100.0f);
+      const float tgt = fminf(fmaxf(raw, 1.05f), 15.0f);
+      const float gate = (raw >= 1.05f && raw <= 15.0f) ? 1.0f : 0.0f;
+      const float o2 = (r[7] + 1e-6f) * 0.21f;
+      const float act = f_div<ACC>(o2, Q);
+      const float fO = act - tgt + fmaxf(1.0f - act, 0.0f) * 10.0f;
+      const float g = -2.0f * fO * gate;
+      const float sgn = L.O3 > 0.f ? 1.0f : (L.O3 < 0.f ? -1.0f : 0.0f);
+      acc[PINN_S_FO2] = fmaf(fO, fO, acc[PINN_S_FO2]);
+      acc[PINN_S_GO1] += g;
+      acc[PINN_S_GO2] = fmaf(g, sel / 100.0f, acc[PINN_S_GO2]);
+      acc[PINN_S_GO3] += lin ? 0.0f : g * (L.O2 * sgn / 100.0f);
+      acc[PINN_S_OACT] += act;
+      acc[PINN_S_OTGT] += tgt;
+      put(PINN_C_FO, fO); put(PINN_C_O_ACT, act); put(PINN_C_O_TGT, tgt); put(PINN_C_O_Q, Q); put(PINN_C_O2, o2);
+    }
+  }
+}
+
+// Workspace: double partials[grid][PINN_S_COUNT] followed by one uint32 ticket (zeroed
+// once by the caller; the last CTA resets it).
+template <uint32_t FAMC, bool ACC>
+__global__ void __launch_bounds__(kResThreads, kResCtasPerSm)
+residual_kernel(const float* __restrict__ x, const float* __restrict__ u, const float* __restrict__ y, int64_t n,
+                pinn_scalers_t sc, const float* __restrict__ lam, uint32_t fam, const float* halo_x,
+                const float* halo_u, float* __restrict__ cols, double* __restrict__ partials,
+                unsigned int* ticket, double* __restrict__ sums) {
+  __shared__ double red[kResThreads / 32][PINN_S_COUNT];
+  __shared__ bool is_last;
+  Lam L;
+  {
+    const float* lp = lam;
+    L = Lam{lp[0], lp[1], lp[2], lp[3], lp[4], lp[5], lp[6], lp[7], lp[8], lp[9], lp[10], lp[11], lp[12],
+            lp[13], lp[14], lp[15], lp[16]};
+  }
+  float acc[PINN_S_COUNT];
+#pragma unroll
+  for (int k = 0; k < PINN_S_COUNT; ++k) acc[k] = 0.f;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; s < n; s += stride)
+    eval_sample<FAMC, ACC>(x, u, y, s, n, sc, L, fam, halo_x, halo_u, cols, acc);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < PINN_S_COUNT; ++k) {
+    double v = static_cast<double>(acc[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < PINN_S_COUNT) {
+    double v = 0.0;
+    for (int wdx = 0; wdx < kResThreads / 32; ++wdx) v += red[wdx][threadIdx.x];
+    partials[static_cast<size_t>(blockIdx.x) * PINN_S_COUNT + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (threadIdx.x < PINN_S_COUNT) {
+      double v = 0.0;
+      for (unsigned int b = 0; b < gridDim.x; ++b) v += partials[static_cast<size_t>(b) * PINN_S_COUNT + threadIdx.x];
+      sums[threadIdx.x] = v;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+  }
+}
+
+static int res_grid(int64_t n) {
+  int64_t want = (n + kResThreads - 1) / kResThreads;
+  int64_t cap = static_cast<int64_t>(sm_count()) * kResCtasPerSm;
+  return static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+}  // namespace pinn
+
+using namespace pinn;
+
+extern "C" size_t pinn_residuals_workspace_bytes(int64_t n) {
+  (void)n;
+  size_t cap = static_cast<size_t>(sm_count()) * kResCtasPerSm;
+  return cap * PINN_S_COUNT * sizeof(double) + 16;
+}
+
+extern "C" int pinn_residuals(const float* x, const float* u, const float* y, int64_t n,
+                              const pinn_scalers_t* scalers, const float* lambdas, uint32_t families,
+                              uint32_t flags, const float* halo_x, const float* halo_u, float* cols,
+                              double* sums, void* workspace, size_t workspace_bytes, void* stream) {
+  if (n < 0 || !scalers || !lambdas || !sums || !workspace) return PINN_E_ARG;
+  if (n > 0 && !x) return PINN_E_ARG;
+  if ((families & (PINN_FAM_V | PINN_FAM_T | PINN_FAM_DATA)) && n > 0 && !u) return PINN_E_ARG;
+  if ((families & PINN_FAM_DATA) && n > 0 && !y) return PINN_E_ARG;
+  if (workspace_bytes < pinn_residuals_workspace_bytes(n)) return PINN_E_WORKSPACE;
+  if (!aligned16(x) || !aligned16(workspace)) return PINN_E_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = res_grid(n);
+  double* partials = static_cast<double*>(workspace);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(
+      static_cast<char*>(workspace) + static_cast<size_t>(sm_count()) * kResCtasPerSm * PINN_S_COUNT * sizeof(double));
+  const bool accm = (flags & PINN_RES_ACCURATE_MATH) != 0;
+  const uint32_t f = families;
+#define LAUNCH(FAMC)                                                                                          \
+  do {                                                                                                        \
+    if (accm)                                                                                                 \
+      residual_kernel<FAMC, true><<<grid, kResThreads, 0, st>>>(x, u, y, n, *scalers, lambdas, f, halo_x,   \
+                                                                halo_u, cols, partials, ticket, sums);       \
+    else                                                                                                      \
+      residual_kernel<FAMC, false><<<grid, kResThreads, 0, st>>>(x, u, y, n, *scalers, lambdas, f, halo_x,  \
+                                                                 halo_u, cols, partials, ticket, sums);      \
+  } while (0)
+  constexpr uint32_t VD = PINN_FAM_V | PINN_FAM_DATA;
+  constexpr uint32_t ALL = PINN_FAM_V | PINN_FAM_TS | PINN_FAM_T | PINN_FAM_H | PINN_FAM_O | PINN_FAM_DATA;
+  if ((f & ~VD) == 0) LAUNCH(VD);
+  else if (f == PINN_FAM_TS) LAUNCH(PINN_FAM_TS);
+  else if (f == PINN_FAM_H) LAUNCH(PINN_FAM_H);
+  else if (f == PINN_FAM_O) LAUNCH(PINN_FAM_O);
+  else LAUNCH(ALL);
+#undef LAUNCH
+  return static_cast<int>(cudaGetLastError());
+}

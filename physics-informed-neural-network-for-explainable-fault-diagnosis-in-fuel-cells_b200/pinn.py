@@ -1,0 +1,374 @@
+"""``PhysicsInformedNN`` -- drop-in for the reference's model class (01:441-1410).
+
+Same constructor, attribute names (``x, u, X, x_scal, u_scal, dnn, lambda_*``), method
+names, positional return tuples and ``state_dict`` layout (including the
+``register_parameter('lambda_3', lambda_4)`` aliasing quirk, 01:468).  What changes is
+where the arithmetic runs:
+
+* the 17 physics scalars live in ONE device vector (each ``nn.Parameter`` is a view),
+  the two sklearn scalers are folded once into an in-kernel affine -- the reference's
+  per-call host round trips (01:726-737 etc.) are gone;
+* ``net_f_*`` are one launch of the residual kernel K3; their outputs still carry
+  autograd w.r.t. the lambdas (first-order exact) so external ``.backward()`` works;
+* the five phase trainers run whole steps on the device: K2 (+fused aleatoric loss) or
+  K3 -> [one all-reduce when data-parallel] -> fused Adam/StepLR/clamp; the host only
+  syncs for the 1-in-1000 progress line the reference prints.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _abi, kernels as K
+from ._abi import S
+from .nn import DNN
+
+LAMBDA_NAMES = (["lambda_1", "lambda_2", "lambda_3", "lambda_4"] + [f"lambda_T{i}" for i in range(1, 6)]
+                + [f"lambda_H{i}" for i in range(1, 5)] + [f"lambda_O{i}" for i in range(1, 5)])
+LAMBDA_INIT = [0.167897923477715, 2.36682075851268e-06, 2.43414469188443, 1.0,      # 01:453-456
+               10.0, 10.0, 10.0, 10.0, 10.0,                                         # 01:477-481
+               5.0, -1.559, 197.715, 1.20,                                           # 01:497-500
+               2.0, 0.5, 200.0, 1.0]                                                 # 01:514-517
+_A, _F, _R, _ALPHA = 270.0, 96485.0, 8.314, 0.5
+
+
+def _cuda_device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("b200pinn.PhysicsInformedNN needs a CUDA device (B200, sm_100a); there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _world():
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def _allreduce(t):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t)
+    return t
+
+
+class PhysicsInformedNN:
+    def __init__(self, X, u, layers, x_scal, u_scal, p, logvar):
+        device = _cuda_device()
+        self.device = device
+        self.x = X[:, 0:].clone().detach().requires_grad_(True).float().to(device)
+        self.u = u.clone().detach().float().to(device)
+        self.u_scal = u_scal
+        self.x_scal = x_scal
+        self.X = X
+        self._lam = torch.tensor(LAMBDA_INIT, dtype=torch.float32, device=device)
+        for i, name in enumerate(LAMBDA_NAMES):
+            setattr(self, name, torch.nn.Parameter(self._lam[i:i + 1]))
+        self.dnn = DNN(p, logvar, layers).to(device)
+        for name in LAMBDA_NAMES:
+            # 01:468 registers lambda_4 under the key 'lambda_3' (overwriting it): keep that layout
+            key = "lambda_3" if name == "lambda_4" else name
+            self.dnn.register_parameter(key, getattr(self, name))
+        self._scalers_cache = {}
+        self._flat = None
+
+    # ------------------------------------------------------------------ internals
+    def _lambdas(self) -> torch.Tensor:
+        """The device vector the kernels read; re-adopts any Parameter whose ``.data`` was
+        re-bound from outside (the reference's own clamps do that, 01:1040-1047)."""
+        for i, name in enumerate(LAMBDA_NAMES):
+            prm = getattr(self, name)
+            view = self._lam[i:i + 1]
+            if prm.data_ptr() != view.data_ptr():
+                with torch.no_grad():
+                    view.copy_(prm.detach().reshape(1).to(view.device, torch.float32))
+                prm.data = view
+        return self._lam
+
+    def _scalers(self, x_scal):
+        key = (id(x_scal), id(self.u_scal))
+        if key not in self._scalers_cache:
+            self._scalers_cache[key] = K.make_scalers(x_scal, self.u_scal)
+        return self._scalers_cache[key]
+
+    def _dev(self, X):
+        if X is self.X or X is self.x:
+            return self.x.detach()
+        return X.detach().to(self.device, torch.float32).contiguous()
+
+    def _phys(self, x, x_scal):
+        """Physical-domain columns in torch (only for attaching lambda-Jacobians)."""
+        sc = self._scalers(x_scal)
+        inv = torch.tensor(list(sc.x_inv_scale), device=x.device)
+        off = torch.tensor(list(sc.x_off), device=x.device)
+        return x * inv - off
+
+    @staticmethod
+    def _attach(value, pairs):
+        """value + sum_k J_k * (lambda_k - lambda_k.detach()): same number, exact first-order
+        autograd w.r.t. the lambdas (what the reference's elementwise graph provides)."""
+        if not torch.is_grad_enabled():
+            return value
+        for prm, jac in pairs:
+            if prm.requires_grad:
+                value = value + jac * (prm - prm.detach())
+        return value
+
+    # ------------------------------------------------------------------ network
+    def net_u(self, x):
+        prediction, log_var = self.dnn(x)
+        return prediction, log_var
+
+    # ------------------------------------------------------------------ residuals
+    def _run(self, X, x_scal, fam, need_u):
+        x = self._dev(X)
+        u = None
+        if need_u:
+            uu, _ = self.net_u(x)            # current train/eval mode, like 01:733
+            u = uu.detach().reshape(-1).contiguous()
+        sums, cols = K.residuals(x, u, None, self._scalers(x_scal), self._lambdas(), fam, want_cols=True)
+        return x, cols
+
+    def net_f_V(self, X, x_scal):
+        x, c = self._run(X, x_scal, _abi.FAM_V, True)
+        col = lambda n: c[_abi.COL[n]].view(-1, 1)
+        i = col("I")
+        l2, l3 = self.lambda_2.detach(), self.lambda_3.detach()
+        Tk = self._phys(x, x_scal)[:, 5:6] + 273.15
+        b = _R * Tk / (2.0 * _ALPHA * _F)
+        jac = [(self.lambda_1, -i), (self.lambda_2, b / l2), (self.lambda_3, _ALPHA * b * i / (l3 * (l3 - i)))]
+        f = self._attach(col("FV"), jac)
+        V5 = self._attach(col("VEST5"), [(q, 5.0 * j) for q, j in jac])
+        return (f, col("VACT"), col("VOHM"), col("VCONC"), col("ENERNST"), V5, i, self.lambda_3, col("VOUT5"))
+
+    def net_f_T_simple(self, X, x_scal):
+        x, c = self._run(X, x_scal, _abi.FAM_TS, False)
+        col = lambda n: c[_abi.COL[n]].view(-1, 1)
+        r = self._phys(x, x_scal)
+        It = (r[:, 0:1] / _A + 1e-6) * _A
+        m = r[:, 1:2] + 1e-6
+        one = torch.ones_like(It)
+        f = self._attach(col("FTS"), [(self.lambda_T1, -It), (self.lambda_T3, -m), (self.lambda_T5, -one)])
+        Tp = self._attach(col("TS_PRED"), [(self.lambda_T1, It), (self.lambda_T3, m), (self.lambda_T5, one)])
+        return f, Tp, col("T_REAL")
+
+    def net_f_T(self, X, x_scal):
+        n = X.shape[0]
+        if n < 2:                                   # 01:774-778
+            z = lambda: torch.zeros(n, 1, device=self.device)
+            return z(), z(), z()
+        x, c = self._run(X, x_scal, _abi.FAM_T, True)
+        col = lambda nme: c[_abi.COL[nme]].view(-1, 1)
+        return col("FT"), col("T_PRED"), col("T_REAL")
+
+    def net_f_H(self, X, x_scal):
+        x, c = self._run(X, x_scal, _abi.FAM_H, False)
+        col = lambda n: c[_abi.COL[n]].view(-1, 1)
+        It = col("I_TOTAL")
+        H2, H3 = self.lambda_H2.detach(), self.lambda_H3.detach()
+        lin = It <= H3
+        sel = torch.where(lin, It, H3.expand_as(It)) / 100.0
+        j3 = torch.where(lin, torch.zeros_like(It), (H2 / 100.0).expand_as(It))
+        tgt = self._attach(col("H_TGT"), [(self.lambda_H1, torch.ones_like(It)), (self.lambda_H2, sel), (self.lambda_H3, j3)])
+        f = self._attach(col("FH"), [(self.lambda_H1, -torch.ones_like(It)), (self.lambda_H2, -sel), (self.lambda_H3, -j3)])
+        return f, col("H_ACT"), tgt, It, self.lambda_H3
+
+    def net_f_O(self, X, x_scal):
+        x, c = self._run(X, x_scal, _abi.FAM_O, False)
+        col = lambda n: c[_abi.COL[n]].view(-1, 1)
+        r = self._phys(x, x_scal)
+        It = (r[:, 0:1] / _A + 1e-5) * _A
+        O1, O2, O3 = self.lambda_O1.detach(), self.lambda_O2.detach(), self.lambda_O3.detach()
+        th = O3.abs()
+        lin = It <= th
+        sel = torch.where(lin, It, th.expand_as(It)) / 100.0
+        raw = O1 + O2 * sel
+        gate = ((raw >= 1.05) & (raw <= 15.0)).float()
+        j3 = torch.where(lin, torch.zeros_like(It), (O2 * torch.sign(O3) / 100.0).expand_as(It))
+        tgt = self._attach(col("O_TGT"), [(self.lambda_O1, gate), (self.lambda_O2, gate * sel), (self.lambda_O3, gate * j3)])
+        f = self._attach(col("FO"), [(self.lambda_O1, -gate), (self.lambda_O2, -gate * sel), (self.lambda_O3, -gate * j3)])
+        return f, col("O_ACT"), tgt, col("O_Q"), col("O2")
+
+    def aleatoric_loss(self, gt, pred_y, logvar):
+        """01:916-927, kept as torch ops for callers that build their own graph; the trainers
+        below use the copy fused into kernel K2."""
+        precision = torch.exp(-logvar)
+        loss = torch.mean(0.5 * precision * (gt - pred_y) ** 2 + 0.5 * logvar)
+        return loss + 0.01 * torch.mean(torch.abs(logvar))
+
+    # ------------------------------------------------------------------ trainers
+    def _flatten_dnn(self):
+        """Move the DNN's tensors into one padded flat bucket (views), so one Adam launch and
+        one all-reduce cover the whole network."""
+        names, shapes, offs, total = K.param_layout(self.dnn.layers.layer_0.out_features, self.dnn.depth - 1)
+        params = self.dnn.kernel_params()
+        ok = self._flat is not None and all(
+            q.data_ptr() == self._flat.data_ptr() + 4 * o for q, o in zip(params, offs))
+        if not ok:
+            flat = torch.zeros(total, device=self.device, dtype=torch.float32)
+            for q, shp, o in zip(params, shapes, offs):
+                cnt = int(np.prod(shp))
+                flat[o:o + cnt].copy_(q.detach().reshape(-1))
+                q.data = flat[o:o + cnt].view(shp)
+            self._flat = flat
+        return self._flat
+
+    def _set_requires_grad(self, dnn_flag, groups):
+        for prm in self.dnn.parameters():
+            prm.requires_grad = dnn_flag
+        for name in LAMBDA_NAMES:
+            getattr(self, name).requires_grad = any(name in g for g in groups)
+
+    def train_dnn(self, nIter, verbose=True):
+        """01:929-964: full-batch Adam(lr 1e-2)+StepLR(1000,.8) on the aleatoric loss, dropout on.
+        One step = K2 (fwd+loss+bwd+wgrad) -> grad reduce -> [all-reduce] -> fused Adam."""
+        self._set_requires_grad(True, [])
+        for name in LAMBDA_NAMES[:4]:
+            getattr(self, name).requires_grad = False
+        self.dnn.train()
+        flat = self._flatten_dnn()
+        net = K.net_from_module(self.dnn)
+        m, v = torch.zeros_like(flat), torch.zeros_like(flat)
+        grad = torch.empty_like(flat)
+        sums = torch.zeros(4, device=self.device, dtype=torch.float64)
+        counter = K.new_step_counter(self.device)
+        x, y = self.x.detach(), self.u.reshape(-1).contiguous()
+        n_local = x.shape[0]
+        world = _world()
+        n_global = n_local
+        if world > 1:
+            t = torch.tensor([n_local], device=self.device, dtype=torch.int64)
+            n_global = int(_allreduce(t).item())
+        if verbose:
+            print("================== DNN training ==================")
+            print("  Epoch |    Loss    |    MSE     |    LR    ")
+        loss = float("nan")
+        for epoch in range(nIter):
+            cfg = self.dnn.next_dropout_cfg(n_local, self.dnn.active_dropout_p())
+            drop = K.make_dropout(**cfg) if cfg is not None else None
+            K.mlp_backward(net, x, drop, y=y, n_global=n_global, grad_flat=grad, loss_sums=sums)
+            if world > 1:
+                _allreduce(grad)
+            K.adam_step(flat, grad, m, v, counter, 1e-2, 0.8, 1000)
+            if epoch % 1000 == 0 or epoch == nIter - 1:
+                s = _allreduce(sums.clone()) if world > 1 else sums
+                s = s.cpu().numpy()
+                loss = (s[0] + 0.01 * s[1]) / max(s[3], 1.0)
+                if verbose and epoch % 1000 == 0:
+                    print(f" {epoch:5d}  | {loss:10.3e} | {s[2] / max(s[3], 1.0):10.3e} | {1e-2 * 0.8 ** (epoch // 1000):8.1e}")
+        if verbose:
+            print(f"DNN training done, final loss: {loss:.3e}\n")
+        return loss
+
+    def _train_scalars(self, nIter, lo_idx, hi_idx, slots, bounds, lr, gamma, fam, need_u, need_y, report, verbose):
+        lam = self._lambdas()
+        sl = lam[lo_idx:hi_idx]
+        m, v = torch.zeros_like(sl), torch.zeros_like(sl)
+        slot_t = torch.tensor(slots, device=self.device, dtype=torch.int32)
+        lo = torch.tensor([b[0] for b in bounds], device=self.device, dtype=torch.float32)
+        hi = torch.tensor([b[1] for b in bounds], device=self.device, dtype=torch.float32)
+        counter = K.new_step_counter(self.device)
+        sums = torch.empty(_abi.S_COUNT, device=self.device, dtype=torch.float64)
+        x = self.x.detach()
+        y = self.u.reshape(-1).contiguous() if need_y else None
+        u = None
+        if need_u:
+            # the DNN is frozen for the whole phase (the optimiser only holds lambdas,
+            # 01:999-1001), so its eval-mode prediction is loop-invariant: hoisted.
+            with torch.no_grad():
+                u = self.net_u(x)[0].reshape(-1).contiguous()
+        sc = self._scalers(self.x_scal)
+        world = _world()
+        last = None
+        for epoch in range(nIter):
+            K.residuals(x, u, y, sc, lam, fam, sums=sums)
+            if world > 1:
+                _allreduce(sums)
+            K.adam_step_from_sums(sl, sums, slot_t, m, v, counter, lr, gamma, 1000, lo, hi)
+            if epoch % 1000 == 0 or epoch == nIter - 1:
+                last = sums.cpu().numpy()
+                if verbose and epoch % 1000 == 0:
+                    print(report(epoch, last, lr * gamma ** (epoch // 1000)))
+        return last
+
+    def train_lambda(self, nIter, dnn_para=False, verbose=True):
+        """01:966-1058: Adam(lr 1e-3) on lambda_1..4 with box clamps; loss = physics + data MSE
+        (physics = normalised-domain fit if not dnn_para else mean f_V^2)."""
+        self.dnn.eval()
+        self._set_requires_grad(dnn_para, [LAMBDA_NAMES[:4]])
+        bounds = [(0.167 * 0.5, 0.167 * 5), (2.36e-6 * 0.1, 2.36e-6 * 2.1), (2.0, 2.0 * 5.2), (0.1, 10.0)]
+        g = ("GB1", "GB2", "GB3") if dnn_para else ("GA1", "GA2", "GA3")
+        slots = [S[g[0]], S[g[1]], S[g[2]], -1]
+        phys = "FV2" if dnn_para else "EA2"
+
+        def report(epoch, s, lr):
+            n = max(s[S["N"]], 1.0)
+            lam = self._lam[:3].cpu().numpy()
+            return (f" {epoch:5d}  | {(s[S[phys]] + s[S['DATA2']]) / n:9.3e} | {s[S[phys]] / n:10.3e} | "
+                    f"{lam[0]:7.4f} | {lam[1]:9.2e} | {lam[2]:6.3f} | {lr:8.1e}")
+
+        if verbose:
+            print("================ voltage-parameter training ================")
+        s = self._train_scalars(nIter, 0, 4, slots, bounds, 1e-3, 0.8, _abi.FAM_V | _abi.FAM_DATA, True, True,
+                                report, verbose)
+        return None if s is None else (s[S[phys]] + s[S["DATA2"]]) / max(s[S["N"]], 1.0)
+
+    def train_thermal(self, nIter, verbose=True):
+        """01:1060-1151: Adam(lr 1)+StepLR(1000,.8) on lambda_T1..5, loss mean f_T^2."""
+        self.dnn.eval()
+        self._set_requires_grad(False, [LAMBDA_NAMES[4:9]])
+        slots = [S["GT1"], -1, S["GT3"], -1, S["GT5"]]
+        bounds = [(-10000.0, 10000.0)] * 5
+
+        def report(epoch, s, lr):
+            n = max(s[S["N"]], 1.0)
+            t = self._lam[4:9].cpu().numpy()
+            return (f" {epoch:3d}   | {s[S['FT2']] / n:9.3e} | {s[S['FTABS']] / n:8.2f} | " +
+                    " | ".join(f"{q:7.4f}" for q in t) + f" |{lr:8.1e}")
+
+        if verbose:
+            print("---------------- thermal-parameter training ----------------")
+        s = self._train_scalars(nIter, 4, 9, slots, bounds, 1.0, 0.8, _abi.FAM_TS, False, False, report, verbose)
+        return None if s is None else s[S["FT2"]] / max(s[S["N"]], 1.0)
+
+    def train_hydrogen(self, nIter, verbose=True):
+        """01:1305-1399: Adam(lr 1e-1)+StepLR(1000,.9) on lambda_H1..4, loss mean f_H^2."""
+        self.dnn.eval()
+        self._set_requires_grad(False, [LAMBDA_NAMES[9:13]])
+        slots = [S["GH1"], S["GH2"], S["GH3"], -1]
+        bounds = [(0.5, 50.0), (-20.0, 20.0), (50.0, 1000.0), (0.0, 20.0)]
+
+        def report(epoch, s, lr):
+            n = max(s[S["N"]], 1.0)
+            h = self._lam[9:13].cpu().numpy()
+            return (f" {epoch:3d}   | {s[S['FH2']] / n:9.3e} | {s[S['HACT']] / n:10.3f} | {s[S['HTGT']] / n:10.3f} | " +
+                    " | ".join(f"{q:7.4f}" for q in h) + f" | {lr:8.1e}")
+
+        if verbose:
+            print("================ hydrogen-parameter training ================")
+        s = self._train_scalars(nIter, 9, 13, slots, bounds, 1e-1, 0.9, _abi.FAM_H, False, False, report, verbose)
+        return None if s is None else s[S["FH2"]] / max(s[S["N"]], 1.0)
+
+    def train_oxygen(self, nIter, verbose=True):
+        """01:1153-1303: Adam(lr 1e-2)+StepLR(1000,.9) on lambda_O1..4, loss mean f_O^2."""
+        self.dnn.eval()
+        self._set_requires_grad(False, [LAMBDA_NAMES[13:17]])
+        slots = [S["GO1"], S["GO2"], S["GO3"], -1]
+        bounds = [(1.5, 8.0), (-20.0, 20.0), (50.0, 1000.0), (0.0, 20.0)]
+
+        def report(epoch, s, lr):
+            n = max(s[S["N"]], 1.0)
+            o = self._lam[13:17].cpu().numpy()
+            return (f" {epoch:3d}   | {s[S['FO2']] / n:6.3e} | {s[S['OACT']] / n:6.3f} | {s[S['OTGT']] / n:6.3f} | " +
+                    " | ".join(f"{q:7.3f}" for q in o) + f" | {lr:8.1e}")
+
+        if verbose:
+            print("================ oxygen-parameter training ================")
+        s = self._train_scalars(nIter, 13, 17, slots, bounds, 1e-2, 0.9, _abi.FAM_O, False, False, report, verbose)
+        return None if s is None else s[S["FO2"]] / max(s[S["N"]], 1.0)
+
+    # ------------------------------------------------------------------ inference
+    def predict(self, X, x_scal):
+        """01:1401-1410 minus the discarded ``net_f_V`` call (01:1407): host numpy ``(u, log_var)``."""
+        x = self._dev(X)
+        with torch.no_grad():
+            u, log_var = self.net_u(x)
+        return u.detach().cpu().numpy(), log_var.detach().cpu().numpy()

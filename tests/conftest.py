@@ -74,3 +74,27 @@ def nrel(a, b):
     is meaningless on near-zero residuals)."""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def masks_u8(packed, layers):
+    """packed golden bits -> uint8 keep matrix [N, L*H + H/2] (the C-ABI injection layout)."""
+    L, H = len(layers) - 2, int(layers[1])
+    D = L * H + H // 2
+    return np.ascontiguousarray(np.unpackbits(packed, axis=1)[:, :D])
+
+
+def make_model(g, params_prefix="P:"):
+    """Our PhysicsInformedNN on cuda:0 holding the golden file's data, weights and lambdas."""
+    import torch
+    import b200pinn
+
+    model = b200pinn.PhysicsInformedNN(torch.tensor(g["x"]), torch.tensor(g["y"]), g["layers"], g["sx"], g["sy"],
+                                       g["p"], True)
+    sd = {k[len(params_prefix):]: torch.tensor(v) for k, v in g.items()
+          if k.startswith(params_prefix) and not k[len(params_prefix):].startswith("lambda")}
+    missing, unexpected = model.dnn.load_state_dict(sd, strict=False)
+    assert not unexpected and all(m.startswith("lambda") for m in missing)
+    with torch.no_grad():
+        for name, v in zip(b200pinn.LAMBDA_NAMES, g["lam0"]):
+            getattr(model, name).fill_(float(v))
+    return model

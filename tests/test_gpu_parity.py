@@ -1,0 +1,455 @@
+"""GPU parity tests: every call goes through the C ABI (libb200pinn.so) on cuda:0 and is
+compared with (i) golden vectors recorded from the unmodified reference and (ii) the numpy
+oracle on larger seeded inputs.  Tolerances are the north-star ones, norm-relative
+(SURVEY 8c): predictions / residuals / losses 1e-5, gradients 1e-4, MC statistics 1e-5
+with the reference's dropout masks injected."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, make_model, masks_u8, nrel, unpack_masks
+from oracle import np_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL, GRAD_TOL, MC_TOL, LOSS_TOL = 1e-5, 1e-4, 1e-5, 1e-5
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def t2n(t):
+    return t.detach().cpu().numpy()
+
+
+def grads_by_name(model):
+    return {k: t2n(q.grad) for k, q in model.dnn.named_parameters() if q.grad is not None and not k.startswith("lambda")}
+
+
+# ------------------------------------------------------------------ golden: forward / backward
+def test_forward_eval_golden(golden):
+    m = make_model(golden)
+    m.dnn.eval()
+    out, lv = m.net_u(m.x)
+    assert out.shape == (golden["x"].shape[0], 1) and lv.shape == out.shape
+    assert nrel(t2n(out), golden["eval_out"]) < FWD_TOL
+    assert nrel(t2n(lv), golden["eval_logvar"]) < FWD_TOL
+
+
+def test_forward_train_injected_masks_golden(golden):
+    import b200pinn
+
+    m = make_model(golden)
+    m.dnn.train()
+    mk = torch.tensor(masks_u8(golden["train_masks"], golden["layers"]), device=dev())
+    with b200pinn.inject_masks(m.dnn, mk):
+        out, lv = m.net_u(m.x)
+    assert nrel(t2n(out), golden["train_out"]) < FWD_TOL
+    assert nrel(t2n(lv), golden["train_logvar"]) < FWD_TOL
+
+
+def test_autograd_backward_golden(golden):
+    """Level-A path: reference-style loop -- torch aleatoric loss, .backward() -> kernel K2."""
+    import b200pinn
+
+    m = make_model(golden)
+    m.dnn.train()
+    mk = torch.tensor(masks_u8(golden["train_masks"], golden["layers"]), device=dev())
+    with b200pinn.inject_masks(m.dnn, mk):
+        out, lv = m.net_u(m.x)
+        loss = m.aleatoric_loss(m.u, out, lv)
+        loss.backward()
+    assert abs(loss.item() - golden["aleatoric_loss"]) < LOSS_TOL * abs(golden["aleatoric_loss"]) + 1e-7
+    g = grads_by_name(m)
+    for k, v in golden.items():
+        if k.startswith("G:"):
+            assert nrel(g[k[2:]], v) < GRAD_TOL, k
+
+
+def test_fused_loss_backward_golden(golden):
+    """Level-C path: aleatoric loss fused into K2 (no torch ops)."""
+    from b200pinn import kernels as K
+
+    m = make_model(golden)
+    net = K.net_from_module(m.dnn)
+    mk = torch.tensor(masks_u8(golden["train_masks"], golden["layers"]), device=dev())
+    n = golden["x"].shape[0]
+    drop = K.make_dropout(golden["p"], seed=1, masks=mk, mask_rows=n)
+    flat, sums = K.mlp_backward(net, m.x.detach(), drop, y=m.u.reshape(-1).contiguous(), n_global=n)
+    s = t2n(sums)
+    loss = (s[0] + 0.01 * s[1]) / s[3]
+    assert s[3] == n
+    assert abs(loss - golden["aleatoric_loss"]) < LOSS_TOL * abs(golden["aleatoric_loss"]) + 1e-7
+    names, shapes, offs, _ = K.param_layout(net.width, net.n_hidden)
+    flat = t2n(flat)
+    for nm, shp, o in zip(names, shapes, offs):
+        ref = golden["G:" + nm]
+        assert nrel(flat[o:o + ref.size].reshape(ref.shape), ref) < GRAD_TOL, nm
+
+
+# ------------------------------------------------------------------ golden: residuals
+RES = {"V": ["f", "V_act", "V_ohm", "V_conc", "E", "V_est5", "i", "il", "V_out5"],
+       "Ts": ["f", "T_pred", "T_real"], "T": ["f", "T_pred", "T_real"],
+       "H": ["f", "actual", "target", "I_total", "I_thr"], "O": ["f", "actual", "target", "Q", "o2"]}
+
+
+def test_residual_tuples_golden(golden):
+    m = make_model(golden)
+    m.dnn.eval()
+    X = torch.tensor(golden["x"])
+    fns = {"V": m.net_f_V, "Ts": m.net_f_T_simple, "T": m.net_f_T, "H": m.net_f_H, "O": m.net_f_O}
+    for fam, fn in fns.items():
+        res = fn(X, golden["sx"])
+        assert len(res) == len(RES[fam])
+        for nm, t in zip(RES[fam], res):
+            ref = golden[f"R:{fam}:{nm}"]
+            assert tuple(t.shape) == ref.shape, (fam, nm)
+            assert nrel(t2n(t), ref) < FWD_TOL, (fam, nm)
+
+
+@pytest.mark.parametrize("flags", [0, 1])
+def test_residual_sums_and_lambda_grads_golden(golden, flags):
+    """Kernel K3's reductions vs the reference's losses and autograd lambda-gradients
+    (flags=1: libdevice math; flags=0: MUFU approximations -- both must meet the bar)."""
+    from b200pinn import _abi, kernels as K
+
+    S = _abi.S
+    m = make_model(golden)
+    m.dnn.eval()
+    u = m.net_u(m.x)[0].detach().reshape(-1).contiguous()
+    fam = _abi.FAM_V | _abi.FAM_DATA | _abi.FAM_TS | _abi.FAM_H | _abi.FAM_O | _abi.FAM_T
+    sums, _ = K.residuals(m.x.detach(), u, m.u.reshape(-1).contiguous(), m._scalers(golden["sx"]), m._lambdas(),
+                          fam, flags=flags)
+    s = t2n(sums)
+    n = s[S["N"]]
+    assert n == golden["x"].shape[0]
+
+    def close(a, b, tol):
+        return np.allclose(a, b, rtol=tol, atol=tol * np.abs(b).max())
+
+    for mode, ph, gs in ((0, "EA2", ("GA1", "GA2", "GA3")), (1, "FV2", ("GB1", "GB2", "GB3"))):
+        ref = golden[f"L:lambda:{mode}"]
+        got = np.array([(s[S[ph]] + s[S["DATA2"]]) / n, s[S[ph]] / n, s[S["DATA2"]] / n])
+        assert close(got, ref, LOSS_TOL * 2), (mode, got, ref)
+        # the reference's own fp32 gradient carries cancellation noise (fp32 vs fp64 oracle
+        # differ by up to 6e-4 in mode A, tests/test_oracle_golden.py): allow for that slack.
+        g64 = O.lambda_losses(golden["x"], golden["y"], t2n(u), golden["sx"], golden["sy"], golden["lam0"][:3],
+                              bool(mode), np.float64)[3]
+        refg = golden[f"LG:lambda:{mode}"]
+        got_g = np.array([s[S[k]] / n for k in gs])
+        slack = GRAD_TOL * np.abs(refg) + 1.5 * np.abs(refg - g64)
+        assert np.all(np.abs(got_g - g64) <= slack + 1e-12), (mode, got_g, refg, g64)
+    assert close(np.array([s[S["FT2"]] / n, s[S["FTABS"]] / n]), golden["L:thermal"], LOSS_TOL)
+    assert close(np.array([s[S[k]] / n for k in ("GT1", "GT3", "GT5")]), golden["LG:thermal"][[0, 2, 4]], GRAD_TOL)
+    assert close(s[S["FH2"]] / n, golden["L:hydrogen"][0], LOSS_TOL)
+    assert close(np.array([s[S[k]] / n for k in ("GH1", "GH2", "GH3")]), golden["LG:hydrogen"][:3], GRAD_TOL)
+    assert close(s[S["FO2"]] / n, golden["L:oxygen"][0], LOSS_TOL)
+    assert close(np.array([s[S[k]] / n for k in ("GO1", "GO2", "GO3")]), golden["LG:oxygen"][:3], GRAD_TOL)
+    fT = golden["R:T:f"]
+    assert close(s[S["FTE2"]] / n, np.mean(fT.astype(np.float64) ** 2), LOSS_TOL)
+
+
+def test_net_f_autograd_wrt_lambdas_golden(golden):
+    """External callers may call .backward() on mean(f^2) like the reference's loops do."""
+    m = make_model(golden)
+    m.dnn.eval()
+    X = torch.tensor(golden["x"])
+    for prm in m.dnn.parameters():
+        prm.requires_grad = False
+    cases = [("thermal", lambda: m.net_f_T_simple(X, golden["sx"])[0], ["lambda_T1", "lambda_T3", "lambda_T5"], [0, 2, 4]),
+             ("hydrogen", lambda: m.net_f_H(X, golden["sx"])[0], ["lambda_H1", "lambda_H2", "lambda_H3"], [0, 1, 2]),
+             ("oxygen", lambda: m.net_f_O(X, golden["sx"])[0], ["lambda_O1", "lambda_O2", "lambda_O3"], [0, 1, 2])]
+    for key, fn, names, idx in cases:
+        prms = [getattr(m, nme) for nme in names]
+        for q in prms:
+            q.requires_grad = True
+            q.grad = None
+        torch.mean(fn() ** 2).backward()
+        got = np.array([q.grad.item() for q in prms])
+        ref = golden[f"LG:{key}"][idx]
+        assert np.allclose(got, ref, rtol=GRAD_TOL, atol=GRAD_TOL * np.abs(ref).max()), (key, got, ref)
+    prms = [m.lambda_1, m.lambda_2, m.lambda_3]
+    for q in prms:
+        q.requires_grad = True
+        q.grad = None
+    torch.mean(m.net_f_V(X, golden["sx"])[0] ** 2).backward()
+    got = np.array([q.grad.item() for q in prms])
+    ref = golden["LG:lambda:1"]
+    assert np.allclose(got, ref, rtol=5e-4, atol=5e-4 * np.abs(ref).max()), (got, ref)
+
+
+# ------------------------------------------------------------------ golden: trainers
+def lam_vec(m):
+    return t2n(m._lambdas()).astype(np.float64)
+
+
+def test_phase_trainer_trajectories_golden(golden):
+    """Five steps of each reference trainer (Adam + StepLR + clamps) vs our fused device loops."""
+    m = make_model(golden)
+    K5 = 5
+    m.train_lambda(K5, False, verbose=False)
+    assert np.allclose(lam_vec(m), golden["traj:lambda0"], rtol=2e-5, atol=1e-9), (lam_vec(m), golden["traj:lambda0"])
+    m.train_lambda(K5, True, verbose=False)
+    assert np.allclose(lam_vec(m), golden["traj:lambda1"], rtol=2e-5, atol=1e-9)
+    m.train_thermal(K5, verbose=False)
+    assert np.allclose(lam_vec(m), golden["traj:thermal"], rtol=2e-5, atol=1e-9)
+    m.train_hydrogen(K5, verbose=False)
+    assert np.allclose(lam_vec(m), golden["traj:hydrogen"], rtol=2e-5, atol=1e-9)
+    m.train_oxygen(K5, verbose=False)
+    assert np.allclose(lam_vec(m), golden["traj:oxygen"], rtol=2e-5, atol=1e-9)
+
+
+def test_train_dnn_trajectory_golden(golden):
+    """Three reference train_dnn steps (01:948-955) with the reference's masks injected."""
+    import b200pinn
+
+    m = make_model(golden)
+    mk = np.stack([masks_u8(golden[f"traj:dnn_masks{s}"], golden["layers"]) for s in range(3)])
+    with b200pinn.inject_masks(m.dnn, torch.tensor(mk, device=dev())):
+        m.train_dnn(3, verbose=False)
+    sd = m.dnn.state_dict()
+    for k, v in golden.items():
+        if k.startswith("traj:dnn:"):
+            # three Adam steps of size lr=1e-2: compare the parameters themselves
+            assert nrel(t2n(sd[k[len("traj:dnn:"):]]), v) < 2e-4, k
+
+
+# ------------------------------------------------------------------ golden: MC dropout
+def test_mc_dropout_injected_masks_golden(golden):
+    import b200pinn
+
+    g = golden
+    m = make_model(g, params_prefix="mcP:")
+    T, p = int(g["mc_T"]), float(g["mc_p"])
+    mk = np.stack([masks_u8(g[f"mc_masks{t}"], g["layers"]) for t in range(T)])
+    m.dnn._injected_mc = torch.tensor(mk, device=dev())
+    saved = {n: mod.p for n, mod in m.dnn.named_modules() if isinstance(mod, torch.nn.Dropout)}
+    pm, au, eu = b200pinn.get_MC_samples(m, torch.tensor(g["x"]), g["sx"], mc_times=T, dropout=p)
+    assert pm.shape == (g["x"].shape[0],) and pm.dtype == np.float32
+    assert nrel(pm, g["mc_pred_mean"]) < MC_TOL
+    assert nrel(au, g["mc_a_u"]) < MC_TOL
+    assert nrel(eu, g["mc_e_u"]) < MC_TOL
+    assert {n: mod.p for n, mod in m.dnn.named_modules() if isinstance(mod, torch.nn.Dropout)} == saved
+    assert not m.dnn.training
+
+
+# ------------------------------------------------------------------ oracle: larger / wider / ragged
+def random_net(layers, seed):
+    import b200pinn
+
+    torch.manual_seed(seed)
+    dnn = b200pinn.DNN(0.25, True, layers)
+    with torch.no_grad():       # spread the variance-head output so softplus/log see a real range
+        dnn.var_layers[5].bias.fill_(0.3)
+    return dnn.to(dev())
+
+
+def params_np(dnn):
+    return {k: t2n(v) for k, v in dnn.state_dict().items() if not k.startswith("lambda")}
+
+
+def rand_masks(rng, T, n, layers, p):
+    L, H = len(layers) - 2, layers[1]
+    return (rng.random((T, n, L * H + H // 2)) >= p).astype(np.uint8)
+
+
+def split_masks(mk, layers, p, dtype=np.float32):
+    L, H = len(layers) - 2, layers[1]
+    widths = [H] * L + [H // 2]
+    scale = O.dropout_scale(p, dtype)
+    out, o = [], 0
+    for w in widths:
+        out.append(mk[:, o:o + w].astype(dtype) * scale)
+        o += w
+    return out
+
+
+@pytest.mark.parametrize("layers,n", [([8, 64, 64, 64, 1], 4099), ([8, 32, 1], 33), ([8, 64, 64, 64, 64, 64, 1], 700),
+                                      ([8, 128, 128, 1], 515), ([8, 256, 256, 256, 1], 301),
+                                      ([8, 256, 256, 256, 256, 256, 256, 1], 130)])
+def test_forward_backward_vs_oracle(layers, n):
+    """Ragged sizes, every supported width incl. config 4's 6x256 (global-weight path)."""
+    import b200pinn
+    from b200pinn import kernels as K
+    from b200pinn.synthetic import make_scaled_dataset
+
+    x, y, _, _ = make_scaled_dataset(n, seed=5)
+    dnn = random_net(layers, 3)
+    P = params_np(dnn)
+    rng = np.random.default_rng(9)
+    p = 0.25
+    mk = rand_masks(rng, 1, n, layers, p)[0]
+    xd, yd = torch.tensor(x, device=dev()), torch.tensor(y, device=dev()).reshape(-1)
+    dnn.eval()
+    out, lv = dnn(xd)
+    ro, rl = O.dnn_forward(P, x)
+    assert nrel(t2n(out), ro) < FWD_TOL and nrel(t2n(lv), rl) < FWD_TOL
+    dnn.train()
+    with b200pinn.inject_masks(dnn, torch.tensor(mk, device=dev())):
+        out, lv = dnn(xd)
+    ms = split_masks(mk, layers, p)
+    ro, rl = O.dnn_forward(P, x, ms)
+    assert nrel(t2n(out), ro) < FWD_TOL and nrel(t2n(lv), rl) < FWD_TOL
+    # fused-loss backward vs fp64 oracle backprop
+    net = K.net_from_module(dnn)
+    drop = K.make_dropout(p, seed=1, masks=torch.tensor(mk, device=dev()), mask_rows=n)
+    flat, sums = K.mlp_backward(net, xd, drop, y=yd.contiguous(), n_global=n)
+    ms64 = split_masks(mk, layers, p, np.float64)
+    o64, l64 = O.dnn_forward(P, x, ms64, np.float64)
+    du, ds = O.aleatoric_loss_grads(y, o64, l64)
+    G = O.dnn_backward(P, x, ms64, du, ds)
+    s = t2n(sums)
+    assert abs((s[0] + 0.01 * s[1]) / s[3] - O.aleatoric_loss(y, o64, l64, np.float64)) < LOSS_TOL
+    names, shapes, offs, _ = K.param_layout(net.width, net.n_hidden)
+    flat = t2n(flat)
+    for nm, shp, o in zip(names, shapes, offs):
+        ref = G[nm]
+        assert nrel(flat[o:o + ref.size].reshape(ref.shape), ref.reshape(shp)) < GRAD_TOL, nm
+
+
+@pytest.mark.parametrize("layers,n,T", [([8, 64, 64, 64, 1], 1000, 7), ([8, 256, 256, 256, 1], 150, 3)])
+def test_mc_dropout_vs_oracle(layers, n, T):
+    import b200pinn
+    from b200pinn.synthetic import make_scaled_dataset
+
+    x, _, _, _ = make_scaled_dataset(n, seed=6)
+    dnn = random_net(layers, 4).eval()
+    P = params_np(dnn)
+    p = 0.4
+    mk = rand_masks(np.random.default_rng(1), T, n, layers, p)
+    out = b200pinn.mc_dropout_device(dnn, torch.tensor(x, device=dev()), T, p, masks=torch.tensor(mk, device=dev()), raw=True)
+    pm, au, eu = O.mc_dropout(P, x, [split_masks(mk[t], layers, p, np.float64) for t in range(T)], np.float64)
+    assert nrel(t2n(out["pred_mean"]), pm) < MC_TOL
+    assert nrel(t2n(out["a_u"]), au) < MC_TOL
+    assert nrel(t2n(out["e_u"]), eu) < MC_TOL
+    assert nrel(t2n(out["m2"]) / T, eu ** 2) < 5e-5
+
+
+# ------------------------------------------------------------------ properties at full size
+def test_philox_sweep_is_shard_invariant_and_unbiased():
+    """Size-independent properties: (i) results do not depend on how samples are sharded
+    (global Philox counters), (ii) T-pass statistics are what dropout theory predicts."""
+    import b200pinn
+    from b200pinn.synthetic import make_scaled_dataset
+
+    n, T, p = 50000, 64, 0.4
+    x, _, _, _ = make_scaled_dataset(n, seed=2)
+    xd = torch.tensor(x, device=dev())
+    dnn = random_net([8, 64, 64, 64, 1], 8).eval()
+    full = b200pinn.mc_dropout_device(dnn, xd, T, p, seed=1234, raw=True)
+    cut = 17777
+    a = b200pinn.mc_dropout_device(dnn, xd[:cut], T, p, seed=1234, raw=True)
+    b = b200pinn.mc_dropout_device(dnn, xd[cut:].contiguous(), T, p, seed=1234, sample_offset=cut, raw=True)
+    for k in ("pred_mean", "a_u", "e_u", "mean", "m2", "sum_logvar"):
+        assert torch.equal(full[k], torch.cat([a[k], b[k]])), k
+    # pass sharding: two half-sweeps merged with Chan's update == one sweep
+    from b200pinn.dist import chan_merge, finalize
+    h1 = b200pinn.mc_dropout_device(dnn, xd, T // 2, p, seed=1234, raw=True)
+    h2 = b200pinn.mc_dropout_device(dnn, xd, T - T // 2, p, seed=1234, pass_offset=T // 2, raw=True)
+    cnt, mean, m2, slv = chan_merge(T // 2, h1["mean"], h1["m2"], h1["sum_logvar"], T - T // 2, h2["mean"], h2["m2"],
+                                    h2["sum_logvar"])
+    au, eu = finalize(cnt, m2, slv)
+    assert nrel(t2n(mean), t2n(full["mean"])) < 1e-5 and nrel(t2n(eu), t2n(full["e_u"])) < 1e-5
+    assert nrel(t2n(au), t2n(full["a_u"])) < 1e-5
+    # different seed -> different draws, same distribution; epistemic spread is non-degenerate
+    other = b200pinn.mc_dropout_device(dnn, xd, T, p, seed=99, raw=True)
+    assert not torch.equal(other["mean"], full["mean"])
+    assert float(full["e_u"].min()) > 0
+    rel = (other["e_u"].mean() - full["e_u"].mean()).abs() / full["e_u"].mean()
+    assert float(rel) < 0.02
+
+
+def test_dropout_rate_and_scale():
+    """With zero weights and predict.bias = 0, u_t = sum_k w_k * mask_k exposes the mask mean:
+    keep-rate must be 1-p and the scale 1/(1-p) (E[mask] = 1)."""
+    import b200pinn
+
+    layers, n, T, p = [8, 64, 1], 20000, 128, 0.3
+    dnn = b200pinn.DNN(0.0, True, layers).to(dev())
+    with torch.no_grad():
+        for q in dnn.parameters():
+            q.zero_()
+        dnn.layers.layer_0.bias.fill_(10.0)         # tanh(10) ~ 1
+        dnn.predict.weight.fill_(1.0 / 64)
+    x = torch.zeros(n, 8, device=dev())
+    out = b200pinn.mc_dropout_device(dnn.eval(), x, T, p, seed=7, raw=True)
+    mean = float(out["mean"].mean())
+    assert abs(mean - 1.0) < 2e-3, mean
+    var = float((out["m2"] / T).mean())              # Var[mask]/64 = p/(1-p)/64
+    assert abs(var - p / (1 - p) / 64) < 0.03 * p / (1 - p) / 64, var
+
+
+def test_edge_cases():
+    import b200pinn
+    from b200pinn import _abi, kernels as K
+
+    dnn = random_net([8, 64, 64, 64, 1], 1).eval()
+    e = torch.zeros(0, 8, device=dev())
+    out, lv = dnn(e)
+    assert out.shape == (0, 1) and lv.shape == (0, 1)
+    r = b200pinn.mc_dropout_device(dnn, e, 5, 0.4)
+    assert r["pred_mean"].numel() == 0
+    g = load_golden("net32")
+    m = make_model(g)
+    one = torch.tensor(g["x"][:1])
+    f, tp, tr = m.net_f_T(one, g["sx"])                          # 01:774-778: N < 2 -> zeros
+    assert f.shape == (1, 1) and float(f.abs().sum() + tp.abs().sum() + tr.abs().sum()) == 0.0
+    # T = 1 pass: zero epistemic variance
+    r = b200pinn.mc_dropout_device(dnn, torch.tensor(g["x"], device=dev()), 1, 0.5, raw=True)
+    assert float(r["e_u"].abs().max()) == 0.0
+    # sums with n = 0
+    sums, _ = K.residuals(e, torch.zeros(0, device=dev()), None, m._scalers(g["sx"]), m._lambdas(), _abi.FAM_TS)
+    assert float(sums.abs().sum()) == 0.0
+    with pytest.raises(RuntimeError):
+        K.mlp_forward(K.net_from_module(dnn), torch.zeros(3, 8))  # CPU tensor: loud failure
+
+
+def test_net_f_T_halo_shard_invariance():
+    """net_f_T's 1-row stencil (01:809-857): a shard starting mid-series with the previous row
+    as halo reproduces the unsharded residuals."""
+    from b200pinn import _abi, kernels as K
+
+    g = load_golden("net64")
+    m = make_model(g)
+    m.dnn.eval()
+    x = m.x.detach()
+    u = m.net_u(x)[0].detach().reshape(-1).contiguous()
+    sc, lam = m._scalers(g["sx"]), m._lambdas()
+    _, full = K.residuals(x, u, None, sc, lam, _abi.FAM_T, want_cols=True)
+    cut = 123
+    _, a = K.residuals(x[:cut].contiguous(), u[:cut].contiguous(), None, sc, lam, _abi.FAM_T, want_cols=True)
+    _, b = K.residuals(x[cut:].contiguous(), u[cut:].contiguous(), None, sc, lam, _abi.FAM_T, want_cols=True,
+                       halo_x=x[cut - 1].contiguous(), halo_u=u[cut - 1:cut].contiguous())
+    for c in ("FT", "T_PRED"):
+        i = _abi.COL[c]
+        assert torch.equal(full[i], torch.cat([a[i], b[i]])), c
+
+
+def test_level_a_reference_style_training_loop_matches_fused_trainer():
+    """The same three train_dnn steps driven (a) by a reference-style loop -- torch loss,
+    autograd, torch.optim.Adam + StepLR (01:939-955) over our DNN -- and (b) by our fused
+    train_dnn; with identical injected masks both must land on the same weights."""
+    import copy
+    import b200pinn
+
+    g = load_golden("net64")
+    mk = torch.tensor(np.stack([masks_u8(g[f"traj:dnn_masks{s}"], g["layers"]) for s in range(3)]), device=dev())
+    a, b = make_model(g), make_model(g)
+    opt = torch.optim.Adam(a.dnn.parameters(), lr=0.01)
+    sch = torch.optim.lr_scheduler.StepLR(opt, step_size=1000, gamma=0.8)
+    a.dnn.train()
+    with b200pinn.inject_masks(a.dnn, mk):
+        for _ in range(3):
+            u_pred, log_var = a.net_u(a.x)
+            loss = a.aleatoric_loss(a.u, u_pred, log_var)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            sch.step()
+    with b200pinn.inject_masks(b.dnn, mk):
+        b.train_dnn(3, verbose=False)
+    sa, sb = a.dnn.state_dict(), b.dnn.state_dict()
+    for k in sa:
+        if not k.startswith("lambda"):
+            assert nrel(t2n(sa[k]), t2n(sb[k])) < 2e-5, k
