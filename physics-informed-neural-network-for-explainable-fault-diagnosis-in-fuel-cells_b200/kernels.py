@@ -112,6 +112,7 @@ def make_dropout(p: float, seed: int = 0, sample_offset: int = 0, pass_offset: i
             raise RuntimeError("b200pinn: injected masks must be a contiguous CUDA uint8 tensor")
         d.masks = masks.data_ptr()
         d.mask_sample_stride_n = int(mask_rows)
+        d._keepalive = masks        # the struct only holds a raw pointer: pin the tensor's lifetime to it
     return d
 
 
