@@ -175,6 +175,11 @@ int pinn_adam_step_from_sums(float* params, const double* sums,
                              double lr0, double gamma, int64_t step_size,
                              const float* lo, const float* hi, void* stream);
 
+/* Ablation / test switch.  The 64-wide net's forward and MC-dropout kernels run their
+ * 64x64 contractions on tcgen05 tensor cores (3xTF32, fp32-accurate); 0 routes them through
+ * the fp32 FFMA kernels that serve the other widths.  Returns the previous setting. */
+int pinn_set_tensor_core_path(int enable);
+
 int pinn_abi_version(void);
 const char* pinn_error_string(int code);
 /* Device facts the host layer sizes grids with (SM count etc.). */

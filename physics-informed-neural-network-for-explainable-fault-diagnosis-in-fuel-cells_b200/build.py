@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["mlp_fwd_mc.cu", "mlp_bwd.cu", "residuals.cu", "adam_misc.cu"]
+SOURCES = ["mlp_fwd_mc.cu", "mlp_tc.cu", "mlp_bwd.cu", "residuals.cu", "adam_misc.cu"]
 OUT = os.path.join(HERE, "libb200pinn.so")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -24,16 +24,32 @@ def _stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return OUT
+    from concurrent.futures import ThreadPoolExecutor
+
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", OUT, *[os.path.join(CSRC, s) for s in SOURCES]]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("b200pinn: nvcc failed")
-    if verbose:
-        print(res.stderr)
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *flags, *(["-Xptxas=-v"] if verbose else []), "-c", "-o", obj, os.path.join(CSRC, src)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, res
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    for src, obj, res in results:
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError(f"b200pinn: nvcc failed on {src}")
+        if verbose:
+            print(res.stderr)
+    link = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT,
+                           *[obj for _, obj, _ in results]], capture_output=True, text=True)
+    if link.returncode != 0:
+        sys.stderr.write(link.stdout + link.stderr)
+        raise RuntimeError("b200pinn: link failed")
     return OUT
 
 

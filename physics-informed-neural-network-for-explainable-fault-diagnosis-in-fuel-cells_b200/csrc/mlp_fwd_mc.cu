@@ -7,6 +7,7 @@
 // Welford statistics.  HBM traffic is 32 B in + 12 B out per sample per SWEEP; the
 // (T,N,1) host arrays of 01:1475-1477 never exist.
 #include "net.cuh"
+#include "tc_api.cuh"
 
 namespace pinn {
 
@@ -200,6 +201,13 @@ extern "C" int pinn_mlp_fwd(const pinn_net_t* net, const float* x, int64_t n, co
   if (n == 0) return 0;
   if (!aligned16(x)) return PINN_E_ALIGN;
   const int H = net->width, L = net->n_hidden;
+  {
+    int err = 0;
+    TcOut o{out_u, out_logvar, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const int r = launch_tc(false, net, x, n, 1, make_drop_params(drop), o, static_cast<cudaStream_t>(stream), &err);
+    if (r == 1) return 0;
+    if (r < 0) return err;
+  }
   Plan p = plan_tps(H, L, n, 1);
   if (p.large) {
     if (workspace_bytes < p.scratch_floats * sizeof(float) || !workspace) return PINN_E_WORKSPACE;
@@ -229,6 +237,13 @@ extern "C" int pinn_mc_dropout(const pinn_net_t* net, const float* x, int64_t n,
   if (n == 0) return 0;
   if (!aligned16(x)) return PINN_E_ALIGN;
   const int H = net->width, L = net->n_hidden;
+  {
+    int err = 0;
+    TcOut o{nullptr, nullptr, pred_mean, a_u, e_u, raw_mean, raw_m2, raw_sum_logvar};
+    const int r = launch_tc(true, net, x, n, T, make_drop_params(drop), o, static_cast<cudaStream_t>(stream), &err);
+    if (r == 1) return 0;
+    if (r < 0) return err;
+  }
   Plan p = plan_tps(H, L, n, 2);
   if (p.large) {
     if (workspace_bytes < p.scratch_floats * sizeof(float) || !workspace) return PINN_E_WORKSPACE;

@@ -1,0 +1,329 @@
+// mlp_tc.cu -- tensor-core (tcgen05 + TMEM) path of K1 / K4 for the headline 64-wide net.
+//
+// CTA = 2 warpgroups x 128 threads; each warpgroup owns one 128-sample tile at a time and
+// runs independently (named barrier + its own mbarrier), so one group's MMAs overlap the
+// other group's CUDA-core epilogue.  Thread r of a group owns sample r of the tile (= TMEM
+// lane r), exactly as in the thread-per-sample kernels, so Philox counters, mask layout and
+// Welford state are unchanged -- only the 64x64 contractions moved:
+//
+//   weights  : every hidden layer W_l (l>=1) and the stacked head matrix [Wv0; Wp; 0] are
+//              split once per CTA into tf32 hi/lo planes (UMMA K-major layout) and stay
+//              resident in shared memory for all tiles and passes;
+//   per layer: the group's activations sit as hi/lo A planes; one elected thread issues
+//              3 x 8 tcgen05.mma (lo*hi + hi*lo + hi*hi, fp32 accumulate in TMEM) and commits
+//              to the group's mbarrier; all 128 threads then pull their row out of TMEM
+//              (tcgen05.ld 32x32b), add bias, tanh, draw the Philox mask, re-split and store
+//              the next layer's A planes (conflict-free 128-bit stores);
+//   heads    : one N=48 MMA gives the 32 variance-head pre-activations and the mean head;
+//              the 32->16->1 tail is 528 FMAs per sample on CUDA cores.
+//
+// Layer 0 (K = 8) is pass-invariant: computed once per sample into registers.
+#include "net.cuh"
+#include "tc.cuh"
+#include "tc_api.cuh"
+
+namespace pinn {
+
+constexpr int kTcH = 64;
+constexpr int kTcTile = 128;
+constexpr int kHeadN = 48;  // 32 variance-head rows + 1 mean-head row + 15 zero rows (N % 16 == 0)
+
+struct TcLayout {  // offsets in floats from the dynamic shared-memory base
+  int L, nwg;
+  int b_hi[PINN_MAX_HIDDEN], b_lo[PINN_MAX_HIDDEN];  // hidden layer l >= 1
+  int h_hi, h_lo;                                    // stacked heads
+  int a_hi[2], a_lo[2];                              // per warpgroup
+  int W0, b0, b[PINN_MAX_HIDDEN], bv0, bp, Wv1, bv1, Wv2, bv2;
+  int total;
+};
+PINN_HD TcLayout make_tc_layout(int L, int nwg) {
+  TcLayout t;
+  t.L = L; t.nwg = nwg;
+  int o = 0;
+  for (int l = 0; l < PINN_MAX_HIDDEN; ++l) { t.b_hi[l] = t.b_lo[l] = t.b[l] = 0; }
+  for (int l = 1; l < L; ++l) { t.b_hi[l] = o; o += kTcH * kTcH; t.b_lo[l] = o; o += kTcH * kTcH; }
+  t.h_hi = o; o += kHeadN * kTcH;
+  t.h_lo = o; o += kHeadN * kTcH;
+  for (int g = 0; g < 2; ++g) {
+    t.a_hi[g] = o; if (g < nwg) o += kTcTile * kTcH;
+    t.a_lo[g] = o; if (g < nwg) o += kTcTile * kTcH;
+  }
+  t.W0 = o; o += kTcH * PINN_N_IN;
+  t.b0 = o; o += kTcH;
+  for (int l = 1; l < L; ++l) { t.b[l] = o; o += kTcH; }
+  t.bv0 = o; o += kTcH / 2;
+  t.bp = o; o += 4;
+  t.Wv1 = o; o += (kTcH / 4) * (kTcH / 2);
+  t.bv1 = o; o += kTcH / 4;
+  t.Wv2 = o; o += kTcH / 4;
+  t.bv2 = o; o += 4;
+  t.total = o;
+  return t;
+}
+
+// named barrier for one warpgroup (ids 1, 2; id 0 is __syncthreads)
+PINN_D void wg_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+
+// MC = true : eval pass (if pred_mean) + T dropout passes with Welford.   MC = false: one pass.
+template <bool MC>
+__global__ void __launch_bounds__(256, 1)
+mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t n, int T, DropParams dp, TcOut out) {
+  constexpr int H = kTcH;
+  constexpr uint32_t LBO_A = kTcTile * 16, LBO_B = H * 16, LBO_H = kHeadN * 16;
+  extern __shared__ __align__(1024) float smem[];
+  __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ uint32_t tmem_base_s;
+  const int L = lay.L, tid = threadIdx.x, wg = tid >> 7, row = tid & 127, warp = tid >> 5;
+  const int nwg = blockDim.x >> 7;
+  const int Dm = L * H + H / 2;
+
+  // ---------------------------------------------------------------- one-time CTA set-up
+  if (tid == 0) {
+    tc::mbar_init(&mbar[0], 1);
+    tc::mbar_init(&mbar[1], 1);
+    tc::fence_mbar_init();
+  }
+  __syncwarp();
+  if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 128); tc::tmem_relinquish(); }
+  for (int l = 1; l < L; ++l)
+    for (int idx = tid; idx < H * (H / 4); idx += blockDim.x) {
+      const int nrow = idx % H, kc = idx / H;
+      tc::store_split4(smem + lay.b_hi[l], smem + lay.b_lo[l], LBO_B, nrow, kc,
+                       __ldg(reinterpret_cast<const float4*>(net.W[l] + nrow * H) + kc));
+    }
+  for (int idx = tid; idx < kHeadN * (H / 4); idx += blockDim.x) {
+    const int nrow = idx % kHeadN, kc = idx / kHeadN;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nrow < H / 2) v = __ldg(reinterpret_cast<const float4*>(net.Wv0 + nrow * H) + kc);
+    else if (nrow == H / 2) v = __ldg(reinterpret_cast<const float4*>(net.Wp) + kc);
+    tc::store_split4(smem + lay.h_hi, smem + lay.h_lo, LBO_H, nrow, kc, v);
+  }
+  stage_tensor(smem + lay.W0, net.W[0], H * PINN_N_IN);
+  stage_tensor(smem + lay.b0, net.b[0], H);
+  for (int l = 1; l < L; ++l) stage_tensor(smem + lay.b[l], net.b[l], H);
+  stage_tensor(smem + lay.bv0, net.bv0, H / 2);
+  stage_tensor(smem + lay.bp, net.bp, 1);
+  stage_tensor(smem + lay.Wv1, net.Wv1, (H / 4) * (H / 2));
+  stage_tensor(smem + lay.bv1, net.bv1, H / 4);
+  stage_tensor(smem + lay.Wv2, net.Wv2, H / 4);
+  stage_tensor(smem + lay.bv2, net.bv2, 1);
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+
+  const uint32_t d_tmem = tmem_base_s + static_cast<uint32_t>(wg * 64);            // this group's 64 columns
+  const uint32_t d_lane = d_tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16); // this warp's 32 lanes
+  float* a_hi = smem + lay.a_hi[wg];
+  float* a_lo = smem + lay.a_lo[wg];
+  const uint32_t a_hi_u = tc::smem_u32(a_hi), a_lo_u = tc::smem_u32(a_lo);
+  const uint32_t idesc64 = tc::make_idesc_tf32(kTcTile, H), idesc48 = tc::make_idesc_tf32(kTcTile, kHeadN);
+  uint32_t phase = 0;
+
+  // ---------------------------------------------------------------- tiles of this warpgroup
+  const int64_t n_tiles = (n + kTcTile - 1) / kTcTile;
+  for (int64_t tile = static_cast<int64_t>(blockIdx.x) * nwg + wg; tile < n_tiles;
+       tile += static_cast<int64_t>(gridDim.x) * nwg) {
+    const int64_t s = tile * kTcTile + row;
+    const bool valid = s < n;
+    // layer 0 into registers (pass-invariant)
+    float a0[H];
+    {
+      float xr[PINN_N_IN];
+      if (valid) {
+        const float4* px = reinterpret_cast<const float4*>(x + s * PINN_N_IN);
+        float4 q0 = __ldg(px), q1 = __ldg(px + 1);
+        xr[0] = q0.x; xr[1] = q0.y; xr[2] = q0.z; xr[3] = q0.w; xr[4] = q1.x; xr[5] = q1.y; xr[6] = q1.z; xr[7] = q1.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < PINN_N_IN; ++i) xr[i] = 0.f;
+      }
+      const float* W0 = smem + lay.W0;
+      const float* b0 = smem + lay.b0;
+#pragma unroll
+      for (int j = 0; j < H; ++j) {
+        const float4 w0 = *reinterpret_cast<const float4*>(W0 + j * PINN_N_IN);
+        const float4 w1 = *reinterpret_cast<const float4*>(W0 + j * PINN_N_IN + 4);
+        float z = b0[j];
+        z = fmaf(w0.x, xr[0], z); z = fmaf(w0.y, xr[1], z); z = fmaf(w0.z, xr[2], z); z = fmaf(w0.w, xr[3], z);
+        z = fmaf(w1.x, xr[4], z); z = fmaf(w1.y, xr[5], z); z = fmaf(w1.z, xr[6], z); z = fmaf(w1.w, xr[7], z);
+        a0[j] = tanhf(z);
+      }
+    }
+
+    float mean = 0.f, m2 = 0.f, slv = 0.f;
+    const bool do_eval = MC && out.pred_mean != nullptr;
+    const int n_pass = MC ? T + (do_eval ? 1 : 0) : 1;
+    for (int pi = 0; pi < n_pass; ++pi) {
+      const bool eval_pass = MC && do_eval && pi == 0;
+      const int t = MC ? (do_eval ? pi - 1 : pi) : 0;
+      DropCtx dc = make_ctx(dp, s, t, Dm, !eval_pass, valid);
+      // ---- stage layer-0 activations (masked) as the first A operand
+#pragma unroll
+      for (int kc = 0; kc < H / 4; ++kc) {
+        float m[4] = {1.f, 1.f, 1.f, 1.f};
+        if (dc.active) drop4(dc, 0u, 4 * kc, 0u, m);
+        tc::store_split4(a_hi, a_lo, LBO_A, row, kc,
+                         make_float4(a0[4 * kc] * m[0], a0[4 * kc + 1] * m[1], a0[4 * kc + 2] * m[2], a0[4 * kc + 3] * m[3]));
+      }
+      // ---- hidden layers on the tensor cores
+      for (int l = 1; l < L; ++l) {
+        tc::fence_proxy_async();
+        tc::fence_before_sync();
+        wg_sync(wg);
+        if (row == 0) {
+          tc::fence_after_sync();
+          tc::issue_3xtf32(d_tmem, a_hi_u, a_lo_u, LBO_A, tc::smem_u32(smem + lay.b_hi[l]), tc::smem_u32(smem + lay.b_lo[l]),
+                           LBO_B, H, idesc64);
+          tc::umma_commit(&mbar[wg]);
+        }
+        tc::mbar_wait(&mbar[wg], phase);
+        phase ^= 1u;
+        __syncwarp();
+        tc::fence_after_sync();
+        const float* bl = smem + lay.b[l];
+#pragma unroll
+        for (int c0 = 0; c0 < H; c0 += 16) {
+          float z[16];
+          tc::tmem_ld16(d_lane + c0, z);
+          tc::tmem_wait_ld();
+#pragma unroll
+          for (int g = 0; g < 16; g += 4) {
+            float m[4] = {1.f, 1.f, 1.f, 1.f};
+            if (dc.active) drop4(dc, static_cast<uint32_t>(l), c0 + g, static_cast<uint32_t>(l * H), m);
+            float4 v;
+            v.x = tanhf(z[g] + bl[c0 + g]) * m[0];
+            v.y = tanhf(z[g + 1] + bl[c0 + g + 1]) * m[1];
+            v.z = tanhf(z[g + 2] + bl[c0 + g + 2]) * m[2];
+            v.w = tanhf(z[g + 3] + bl[c0 + g + 3]) * m[3];
+            tc::store_split4(a_hi, a_lo, LBO_A, row, (c0 + g) / 4, v);
+          }
+        }
+      }
+      // ---- heads: [Wv0; Wp] in one N = 48 MMA
+      tc::fence_proxy_async();
+      tc::fence_before_sync();
+      wg_sync(wg);
+      if (row == 0) {
+        tc::fence_after_sync();
+        tc::issue_3xtf32(d_tmem, a_hi_u, a_lo_u, LBO_A, tc::smem_u32(smem + lay.h_hi), tc::smem_u32(smem + lay.h_lo), LBO_H, H,
+                         idesc48);
+        tc::umma_commit(&mbar[wg]);
+      }
+      tc::mbar_wait(&mbar[wg], phase);
+      phase ^= 1u;
+      __syncwarp();
+      tc::fence_after_sync();
+      float v0[H / 2];
+      float u;
+      {
+        const float* bv0 = smem + lay.bv0;
+        float z[16];
+        tc::tmem_ld16(d_lane, z);
+        tc::tmem_ld16(d_lane + 16, v0 + 16);
+        float zz[16];
+        tc::tmem_ld16(d_lane + 32, zz);
+        tc::tmem_wait_ld();
+        u = zz[0] + smem[lay.bp];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v0[i] = z[i];
+#pragma unroll
+        for (int g = 0; g < H / 2; g += 4) {
+          float m[4] = {1.f, 1.f, 1.f, 1.f};
+          if (dc.active) drop4(dc, static_cast<uint32_t>(L), g, static_cast<uint32_t>(L * H), m);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v0[g + q] = tanhf(v0[g + q] + bv0[g + q]) * m[q];
+        }
+      }
+      // tail of the variance head on CUDA cores: 32 -> 16 (tanh) -> 1
+      float vraw = smem[lay.bv2];
+      {
+        const float* Wv1 = smem + lay.Wv1;
+        const float* bv1 = smem + lay.bv1;
+        const float* Wv2 = smem + lay.Wv2;
+#pragma unroll 4
+        for (int k = 0; k < H / 4; ++k) {
+          float2 acc = make_float2(0.f, 0.f), acc2 = acc;
+#pragma unroll
+          for (int i4 = 0; i4 < H / 8; i4 += 2) {
+            const float4 w = *reinterpret_cast<const float4*>(Wv1 + k * (H / 2) + 4 * i4);
+            const float4 w2 = *reinterpret_cast<const float4*>(Wv1 + k * (H / 2) + 4 * i4 + 4);
+            acc = ffma2(make_float2(w.x, w.y), make_float2(v0[4 * i4], v0[4 * i4 + 1]), acc);
+            acc2 = ffma2(make_float2(w.z, w.w), make_float2(v0[4 * i4 + 2], v0[4 * i4 + 3]), acc2);
+            acc = ffma2(make_float2(w2.x, w2.y), make_float2(v0[4 * i4 + 4], v0[4 * i4 + 5]), acc);
+            acc2 = ffma2(make_float2(w2.z, w2.w), make_float2(v0[4 * i4 + 6], v0[4 * i4 + 7]), acc2);
+          }
+          const float a1 = tanhf(((acc.x + acc.y) + (acc2.x + acc2.y)) + bv1[k]);
+          vraw = fmaf(Wv2[k], a1, vraw);
+        }
+      }
+      const float lv = logvar_from_v(vraw);
+      if (!MC) {
+        if (valid) { out.u[s] = u; out.s[s] = lv; }
+      } else if (eval_pass) {
+        if (valid) out.pred_mean[s] = u;
+      } else {
+        const float d = u - mean;
+        mean += d / static_cast<float>(t + 1);
+        m2 = fmaf(d, u - mean, m2);
+        slv += lv;
+      }
+    }
+    if (MC && valid) {
+      if (out.raw_mean) out.raw_mean[s] = mean;
+      if (out.raw_m2) out.raw_m2[s] = m2;
+      if (out.raw_slv) out.raw_slv[s] = slv;
+      const float invT = 1.0f / static_cast<float>(T > 0 ? T : 1);
+      if (out.a_u) out.a_u[s] = sqrtf(expf(slv * invT));
+      if (out.e_u) out.e_u[s] = sqrtf(fmaxf(m2, 0.f) * invT);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base_s, 128);
+}
+
+static int g_tc_enabled = 1;
+
+// Launch helper used by pinn_mlp_fwd / pinn_mc_dropout.  Returns 1 if the TC path took the
+// call, 0 if the shape is not covered (caller falls through to the FFMA kernels), <0 / >1 on error.
+int launch_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, const DropParams& dp, const TcOut& out,
+              cudaStream_t st, int* err) {
+  *err = 0;
+  if (!g_tc_enabled || net->width != kTcH || net->n_hidden < 2 || net->n_hidden > 5) return 0;
+  for (int l = 1; l < net->n_hidden; ++l)
+    if (!aligned16(net->W[l])) return 0;
+  if (!aligned16(net->Wv0) || !aligned16(net->Wp)) return 0;
+  int nwg = 2;
+  TcLayout lay = make_tc_layout(net->n_hidden, nwg);
+  if (static_cast<size_t>(lay.total) * sizeof(float) > 226 * 1024) {
+    nwg = 1;
+    lay = make_tc_layout(net->n_hidden, nwg);
+    if (static_cast<size_t>(lay.total) * sizeof(float) > 226 * 1024) return 0;
+  }
+  const size_t smem = static_cast<size_t>(lay.total) * sizeof(float);
+  const int64_t tiles = (n + kTcTile - 1) / kTcTile;
+  int64_t want = (tiles + nwg - 1) / nwg;
+  const int grid = static_cast<int>(want < sm_count() ? (want > 0 ? want : 1) : sm_count());
+  cudaError_t e;
+  if (mc) {
+    e = cudaFuncSetAttribute(mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) { *err = static_cast<int>(e); return -1; }
+    mlp_tc_kernel<true><<<grid, 128 * nwg, smem, st>>>(*net, lay, x, n, T, dp, out);
+  } else {
+    e = cudaFuncSetAttribute(mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) { *err = static_cast<int>(e); return -1; }
+    mlp_tc_kernel<false><<<grid, 128 * nwg, smem, st>>>(*net, lay, x, n, T, dp, out);
+  }
+  *err = static_cast<int>(cudaGetLastError());
+  return *err == 0 ? 1 : -1;
+}
+
+}  // namespace pinn
+
+// Test / ablation switch: 0 routes the 64-wide net through the FFMA kernels as well.
+extern "C" int pinn_set_tensor_core_path(int enable) {
+  int prev = pinn::g_tc_enabled;
+  pinn::g_tc_enabled = enable ? 1 : 0;
+  return prev;
+}

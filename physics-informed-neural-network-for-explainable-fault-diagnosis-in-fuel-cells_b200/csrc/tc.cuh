@@ -1,0 +1,135 @@
+// tc.cuh -- tcgen05 / TMEM / mbarrier building blocks (inline PTX, sm_100a).
+//
+// The hidden-layer contractions of the DNN are [128 samples] x [64 in] x [64 out] GEMMs.
+// They run on the 5th-gen tensor cores as `tcgen05.mma.kind::tf32` with fp32 accumulation in
+// TMEM.  Plain TF32 (10-bit mantissa) would break the 1e-5 parity bar, so both operands are
+// split x = hi + lo (hi = tf32-rounded x, lo = x - hi, exact) and three MMAs accumulate
+// lo*hi + hi*lo + hi*hi into the same TMEM tile ("3xTF32"): the dropped lo*lo term is
+// 2^-22 relative.  Operands live in shared memory in the canonical K-major, no-swizzle
+// ("interleave") UMMA layout:
+//
+//     byte_offset(row, k) = (k/4) * LBO + (row/8) * SBO + (row%8) * 16 + (k%4) * 4
+//
+// with SBO = 128 B (8-row core matrices back to back) and LBO = rows * 16 B, so the thread
+// that owns sample `row` writes its 16-byte chunks at  kc*LBO + row*16  -- consecutive
+// lanes hit consecutive 16-byte slots: conflict-free 128-bit stores.
+#pragma once
+#include "common.cuh"
+
+namespace pinn {
+namespace tc {
+
+PINN_D uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// ------------------------------------------------------------------------- mbarrier
+PINN_D void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+PINN_D void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+PINN_D void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// generic-proxy smem writes -> visible to the async proxy (UMMA operand reads)
+PINN_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------- TMEM
+PINN_D void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+PINN_D void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// whole warp; ncols power of two >= 32; the TMEM base address lands in *dst (shared memory)
+PINN_D void tmem_alloc(uint32_t* dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst)), "r"(ncols)
+               : "memory");
+}
+PINN_D void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+PINN_D void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// 32 lanes x 32 bit, 16 consecutive columns: thread i of the warp reads TMEM lane (lane_base + i)
+PINN_D void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+PINN_D void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------ UMMA
+// K-major, no swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1).
+PINN_D uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;  // descriptor version (Blackwell)
+  return d;         // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE / interleave)
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major.
+PINN_HD constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, one K = 8 slab.  Issued by ONE thread.
+PINN_D void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on `bar` once every MMA issued so far by this thread has completed (implies
+// tcgen05.fence::before_thread_sync).
+PINN_D void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// ------------------------------------------------------------------- operand staging
+PINN_D float tf32_hi(float x) {
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  return __uint_as_float(h);
+}
+// Write one 16-byte K-chunk (4 consecutive k) of row `row` into the hi and lo planes.
+PINN_D void store_split4(float* hi_plane, float* lo_plane, uint32_t lbo_bytes, int row, int kc, float4 v) {
+  float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+  float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+  const size_t off = (static_cast<size_t>(kc) * lbo_bytes + static_cast<size_t>(row) * 16) / sizeof(float);
+  *reinterpret_cast<float4*>(hi_plane + off) = h;
+  *reinterpret_cast<float4*>(lo_plane + off) = l;
+}
+
+// Issue the 3xTF32 product  D[M x N] = A[M x K] * B[N x K]^T  (K multiple of 8) from one thread.
+// a_hi/a_lo/b_hi/b_lo: shared-memory byte addresses of the operand planes.
+PINN_D void issue_3xtf32(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t lbo_a, uint32_t b_hi, uint32_t b_lo,
+                         uint32_t lbo_b, int K, uint32_t idesc) {
+  uint32_t acc = 0;
+#pragma unroll 1
+  for (int term = 0; term < 3; ++term) {      // small terms first: lo*hi, hi*lo, then hi*hi
+    const uint32_t a = term == 0 ? a_lo : a_hi;
+    const uint32_t b = term == 1 ? b_lo : b_hi;
+#pragma unroll 1
+    for (int k8 = 0; k8 < K / 8; ++k8) {      // one MMA consumes K = 8 tf32 = two 16-byte chunks
+      umma_tf32(d_tmem, make_desc(a + 2 * k8 * lbo_a, lbo_a, 128), make_desc(b + 2 * k8 * lbo_b, lbo_b, 128), idesc, acc);
+      acc = 1;
+    }
+  }
+}
+
+}  // namespace tc
+}  // namespace pinn

@@ -246,6 +246,11 @@ def mc_dropout(net: Net, x: torch.Tensor, T: int, drop: PinnDropout, finalize: b
     return out
 
 
+def set_tensor_core_path(enable: bool) -> bool:
+    """Ablation switch (tests): route the 64-wide net through the FFMA kernels when False."""
+    return bool(_abi.lib().pinn_set_tensor_core_path(1 if enable else 0))
+
+
 def new_step_counter(device) -> torch.Tensor:
     return torch.zeros(2, device=device, dtype=torch.int64)
 

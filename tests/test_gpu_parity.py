@@ -453,3 +453,61 @@ def test_level_a_reference_style_training_loop_matches_fused_trainer():
     for k in sa:
         if not k.startswith("lambda"):
             assert nrel(t2n(sa[k]), t2n(sb[k])) < 2e-5, k
+
+
+# ------------------------------------------------------------------ tensor-core path vs FFMA path
+@pytest.fixture
+def ffma_path():
+    """Route the 64-wide net through the fp32 FFMA kernels for the duration of a test."""
+    from b200pinn import kernels as K
+
+    prev = K.set_tensor_core_path(False)
+    yield
+    K.set_tensor_core_path(prev)
+
+
+def test_golden_forward_and_mc_on_ffma_path(ffma_path):
+    """The golden checks above exercise the tcgen05 path for net64; repeat them on the FFMA path."""
+    import b200pinn
+
+    g = load_golden("net64")
+    m = make_model(g)
+    m.dnn.eval()
+    out, lv = m.net_u(m.x)
+    assert nrel(t2n(out), g["eval_out"]) < FWD_TOL and nrel(t2n(lv), g["eval_logvar"]) < FWD_TOL
+    m.dnn.train()
+    with b200pinn.inject_masks(m.dnn, torch.tensor(masks_u8(g["train_masks"], g["layers"]), device=dev())):
+        out, lv = m.net_u(m.x)
+    assert nrel(t2n(out), g["train_out"]) < FWD_TOL and nrel(t2n(lv), g["train_logvar"]) < FWD_TOL
+    m2 = make_model(g, params_prefix="mcP:")
+    T, p = int(g["mc_T"]), float(g["mc_p"])
+    m2.dnn._injected_mc = torch.tensor(np.stack([masks_u8(g[f"mc_masks{t}"], g["layers"]) for t in range(T)]), device=dev())
+    pm, au, eu = b200pinn.get_MC_samples(m2, torch.tensor(g["x"]), g["sx"], mc_times=T, dropout=p)
+    assert nrel(pm, g["mc_pred_mean"]) < MC_TOL and nrel(au, g["mc_a_u"]) < MC_TOL and nrel(eu, g["mc_e_u"]) < MC_TOL
+
+
+@pytest.mark.parametrize("layers", [[8, 64, 64, 1], [8, 64, 64, 64, 1], [8, 64, 64, 64, 64, 64, 1]])
+def test_tensor_core_path_matches_ffma_path_and_oracle(layers):
+    """Same Philox stream on both paths (counters are per sample/pass/layer/unit), so an MC sweep
+    must agree to rounding; both must match the fp64 oracle under injected masks.  L = 2, 3 use two
+    warpgroups per CTA, L = 5 one (shared-memory budget)."""
+    import b200pinn
+    from b200pinn import kernels as K
+    from b200pinn.synthetic import make_scaled_dataset
+
+    n, T, p = 1500, 9, 0.4
+    x, _, _, _ = make_scaled_dataset(n, seed=11)
+    xd = torch.tensor(x, device=dev())
+    dnn = random_net(layers, 5).eval()
+    a = b200pinn.mc_dropout_device(dnn, xd, T, p, seed=77, raw=True)
+    prev = K.set_tensor_core_path(False)
+    try:
+        b = b200pinn.mc_dropout_device(dnn, xd, T, p, seed=77, raw=True)
+    finally:
+        K.set_tensor_core_path(prev)
+    for k in ("pred_mean", "mean", "a_u", "e_u"):
+        assert nrel(t2n(a[k]), t2n(b[k])) < 5e-6, k
+    mk = rand_masks(np.random.default_rng(3), T, n, layers, p)
+    c = b200pinn.mc_dropout_device(dnn, xd, T, p, masks=torch.tensor(mk, device=dev()))
+    pm, au, eu = O.mc_dropout(params_np(dnn), x, [split_masks(mk[t], layers, p, np.float64) for t in range(T)], np.float64)
+    assert nrel(t2n(c["pred_mean"]), pm) < MC_TOL and nrel(t2n(c["a_u"]), au) < MC_TOL and nrel(t2n(c["e_u"]), eu) < MC_TOL
