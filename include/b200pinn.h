@@ -54,7 +54,8 @@ typedef struct pinn_net {
 
 /* Dropout control.  p == 0 means eval mode.  With masks == NULL the keep mask of
  * (sample s, pass t, dropout layer l, unit j) is drawn from Philox4x32-10 keyed by
- * `seed` with counter (s, t, l, j/4) -- identical for any GPU count or sharding.
+ * `seed` with counter (s, t, l, j/8) -- identical for any GPU count or sharding; each
+ * call yields eight 16-bit draws, a unit is dropped iff its draw < round(p * 2^16).
  * With masks != NULL the keep bits are read from masks[t][s][D], uint8 0/1,
  * D = L*H + H/2 (trunk layers in order, then the variance head) -- used to inject
  * the reference's own masks for parity, since the RNG streams differ.

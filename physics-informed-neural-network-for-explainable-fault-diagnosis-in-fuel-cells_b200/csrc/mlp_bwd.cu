@@ -76,11 +76,11 @@ struct DgradEpi {
   uint32_t layer, unit_base;
   PINN_D void operator()(int c0, float (&z)[CB]) const {
 #pragma unroll
-    for (int g = 0; g < CB; g += 4) {
-      float m[4] = {1.f, 1.f, 1.f, 1.f};
-      if (dc->active) drop4(*dc, layer, c0 + g, unit_base, m);
+    for (int g = 0; g < CB; g += 8) {
+      float m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+      if (dc->active) drop8(*dc, layer, c0 + g, unit_base, m);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 8; ++q) {
         float a = act.get(c0 + g + q) * (dc->active ? dc->keep : 1.0f);
         out.set(c0 + g + q, z[g + q] * m[q] * (1.0f - a * a));
       }

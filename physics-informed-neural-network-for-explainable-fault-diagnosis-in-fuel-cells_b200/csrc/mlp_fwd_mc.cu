@@ -103,11 +103,11 @@ mc_dropout_kernel(pinn_net_t net, ParamLayout lay, const float* __restrict__ x, 
     for (int t = 0; t < T; ++t) {
       dc = make_ctx(dp, s, t, D, true);
 #pragma unroll 1
-      for (int k = 0; k < H; k += 4) {
-        float m[4] = {1.f, 1.f, 1.f, 1.f};
-        if (dc.active) drop4(dc, 0u, k, 0u, m);
+      for (int k = 0; k < H; k += 8) {
+        float m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+        if (dc.active) drop8(dc, 0u, k, 0u, m);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) cols.bufA.set(k + q, cols.a0.get(k + q) * m[q]);
+        for (int q = 0; q < 8; ++q) cols.bufA.set(k + q, cols.a0.get(k + q) * m[q]);
       }
       forward_tail<H, LARGE>(w, lay.L, cols.bufA, cols.bufB, dc, u, v);
       float d = u - mean;

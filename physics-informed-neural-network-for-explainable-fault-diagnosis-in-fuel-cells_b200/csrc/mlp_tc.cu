@@ -1,10 +1,11 @@
 // mlp_tc.cu -- tensor-core (tcgen05 + TMEM) path of K1 / K4 for the headline 64-wide net.
 //
-// CTA = 2 warpgroups x 128 threads; each warpgroup owns one 128-sample tile at a time and
-// runs independently (named barrier + its own mbarrier), so one group's MMAs overlap the
-// other group's CUDA-core epilogue.  Thread r of a group owns sample r of the tile (= TMEM
-// lane r), exactly as in the thread-per-sample kernels, so Philox counters, mask layout and
-// Welford state are unchanged -- only the 64x64 contractions moved:
+// CTA = 2 groups x 256 threads; each group owns one 128-sample tile at a time and runs
+// independently (named barrier + its own mbarrier), so one group's MMAs overlap the other
+// group's CUDA-core epilogue.  Threads (r, 0) and (r, 1) of a group own the two 32-column
+// halves of sample r of the tile (= TMEM lane r); Philox counters are per (sample, pass,
+// layer, unit/8), so the mask stream is identical to the thread-per-sample kernels -- only
+// the 64x64 contractions moved:
 //
 //   weights  : every hidden layer W_l (l>=1) and the stacked head matrix [Wv0; Wp; 0] are
 //              split once per CTA into tf32 hi/lo planes (UMMA K-major layout) and stay
@@ -61,21 +62,25 @@ PINN_HD TcLayout make_tc_layout(int L, int nwg) {
   return t;
 }
 
-// named barrier for one warpgroup (ids 1, 2; id 0 is __syncthreads)
-PINN_D void wg_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+// named barrier for one 256-thread group (ids 1, 2; id 0 is __syncthreads)
+PINN_D void grp_sync(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); }
 
 // MC = true : eval pass (if pred_mean) + T dropout passes with Welford.   MC = false: one pass.
+// A "group" is 256 threads working on one 128-sample tile: thread (row, half) owns columns
+// [32*half, 32*half+32) of sample `row`'s activations (TMEM lane `row`), so 16 warps per SM
+// keep the schedulers fed while each thread's working set stays at 32 values.
 template <bool MC>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(512, 1)
 mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t n, int T, DropParams dp, TcOut out) {
-  constexpr int H = kTcH;
+  constexpr int H = kTcH, HH = kTcH / 2;
   constexpr uint32_t LBO_A = kTcTile * 16, LBO_B = H * 16, LBO_H = kHeadN * 16;
   extern __shared__ __align__(1024) float smem[];
   __shared__ __align__(8) uint64_t mbar[2];
   __shared__ uint32_t tmem_base_s;
-  const int L = lay.L, tid = threadIdx.x, wg = tid >> 7, row = tid & 127, warp = tid >> 5;
-  const int nwg = blockDim.x >> 7;
+  const int L = lay.L, tid = threadIdx.x, grp = tid >> 8, half = (tid >> 7) & 1, row = tid & 127, warp = tid >> 5;
+  const int ngrp = blockDim.x >> 8;
   const int Dm = L * H + H / 2;
+  const int cb = half * HH;  // first column owned by this thread
 
   // ---------------------------------------------------------------- one-time CTA set-up
   if (tid == 0) {
@@ -112,22 +117,23 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
   __syncthreads();
   tc::fence_after_sync();
 
-  const uint32_t d_tmem = tmem_base_s + static_cast<uint32_t>(wg * 64);            // this group's 64 columns
+  const uint32_t d_tmem = tmem_base_s + static_cast<uint32_t>(grp * 64);           // this group's 64 columns
   const uint32_t d_lane = d_tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16); // this warp's 32 lanes
-  float* a_hi = smem + lay.a_hi[wg];
-  float* a_lo = smem + lay.a_lo[wg];
+  float* a_hi = smem + lay.a_hi[grp];
+  float* a_lo = smem + lay.a_lo[grp];
   const uint32_t a_hi_u = tc::smem_u32(a_hi), a_lo_u = tc::smem_u32(a_lo);
   const uint32_t idesc64 = tc::make_idesc_tf32(kTcTile, H), idesc48 = tc::make_idesc_tf32(kTcTile, kHeadN);
+  const bool issuer = (tid & 255) == 0;
   uint32_t phase = 0;
 
-  // ---------------------------------------------------------------- tiles of this warpgroup
+  // ---------------------------------------------------------------- tiles of this group
   const int64_t n_tiles = (n + kTcTile - 1) / kTcTile;
-  for (int64_t tile = static_cast<int64_t>(blockIdx.x) * nwg + wg; tile < n_tiles;
-       tile += static_cast<int64_t>(gridDim.x) * nwg) {
+  for (int64_t tile = static_cast<int64_t>(blockIdx.x) * ngrp + grp; tile < n_tiles;
+       tile += static_cast<int64_t>(gridDim.x) * ngrp) {
     const int64_t s = tile * kTcTile + row;
     const bool valid = s < n;
-    // layer 0 into registers (pass-invariant)
-    float a0[H];
+    // layer 0 into registers (pass-invariant): this thread's 32 columns
+    float a0[HH];
     {
       float xr[PINN_N_IN];
       if (valid) {
@@ -138,16 +144,16 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
 #pragma unroll
         for (int i = 0; i < PINN_N_IN; ++i) xr[i] = 0.f;
       }
-      const float* W0 = smem + lay.W0;
-      const float* b0 = smem + lay.b0;
+      const float* W0 = smem + lay.W0 + cb * PINN_N_IN;
+      const float* b0 = smem + lay.b0 + cb;
 #pragma unroll
-      for (int j = 0; j < H; ++j) {
+      for (int j = 0; j < HH; ++j) {
         const float4 w0 = *reinterpret_cast<const float4*>(W0 + j * PINN_N_IN);
         const float4 w1 = *reinterpret_cast<const float4*>(W0 + j * PINN_N_IN + 4);
         float z = b0[j];
         z = fmaf(w0.x, xr[0], z); z = fmaf(w0.y, xr[1], z); z = fmaf(w0.z, xr[2], z); z = fmaf(w0.w, xr[3], z);
         z = fmaf(w1.x, xr[4], z); z = fmaf(w1.y, xr[5], z); z = fmaf(w1.z, xr[6], z); z = fmaf(w1.w, xr[7], z);
-        a0[j] = tanhf(z);
+        a0[j] = tanh_act(z);
       }
     }
 
@@ -160,84 +166,77 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
       DropCtx dc = make_ctx(dp, s, t, Dm, !eval_pass, valid);
       // ---- stage layer-0 activations (masked) as the first A operand
 #pragma unroll
-      for (int kc = 0; kc < H / 4; ++kc) {
-        float m[4] = {1.f, 1.f, 1.f, 1.f};
-        if (dc.active) drop4(dc, 0u, 4 * kc, 0u, m);
-        tc::store_split4(a_hi, a_lo, LBO_A, row, kc,
-                         make_float4(a0[4 * kc] * m[0], a0[4 * kc + 1] * m[1], a0[4 * kc + 2] * m[2], a0[4 * kc + 3] * m[3]));
+      for (int g = 0; g < HH; g += 8) {
+        float m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+        if (dc.active) drop8(dc, 0u, cb + g, 0u, m);
+        tc::store_split4(a_hi, a_lo, LBO_A, row, (cb + g) / 4,
+                         make_float4(a0[g] * m[0], a0[g + 1] * m[1], a0[g + 2] * m[2], a0[g + 3] * m[3]));
+        tc::store_split4(a_hi, a_lo, LBO_A, row, (cb + g) / 4 + 1,
+                         make_float4(a0[g + 4] * m[4], a0[g + 5] * m[5], a0[g + 6] * m[6], a0[g + 7] * m[7]));
       }
       // ---- hidden layers on the tensor cores
       for (int l = 1; l < L; ++l) {
         tc::fence_proxy_async();
         tc::fence_before_sync();
-        wg_sync(wg);
-        if (row == 0) {
+        grp_sync(grp);
+        if (issuer) {
           tc::fence_after_sync();
           tc::issue_3xtf32(d_tmem, a_hi_u, a_lo_u, LBO_A, tc::smem_u32(smem + lay.b_hi[l]), tc::smem_u32(smem + lay.b_lo[l]),
                            LBO_B, H, idesc64);
-          tc::umma_commit(&mbar[wg]);
+          tc::umma_commit(&mbar[grp]);
         }
-        tc::mbar_wait(&mbar[wg], phase);
+        tc::mbar_wait(&mbar[grp], phase);
         phase ^= 1u;
         __syncwarp();
         tc::fence_after_sync();
-        const float* bl = smem + lay.b[l];
+        const float* bl = smem + lay.b[l] + cb;
+        float z[HH];
+        tc::tmem_ld16(d_lane + cb, z);
+        tc::tmem_ld16(d_lane + cb + 16, z + 16);
+        tc::tmem_wait_ld();
 #pragma unroll
-        for (int c0 = 0; c0 < H; c0 += 16) {
-          float z[16];
-          tc::tmem_ld16(d_lane + c0, z);
-          tc::tmem_wait_ld();
+        for (int g = 0; g < HH; g += 8) {
+          float m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+          if (dc.active) drop8(dc, static_cast<uint32_t>(l), cb + g, static_cast<uint32_t>(l * H), m);
+          float v[8];
 #pragma unroll
-          for (int g = 0; g < 16; g += 4) {
-            float m[4] = {1.f, 1.f, 1.f, 1.f};
-            if (dc.active) drop4(dc, static_cast<uint32_t>(l), c0 + g, static_cast<uint32_t>(l * H), m);
-            float4 v;
-            v.x = tanhf(z[g] + bl[c0 + g]) * m[0];
-            v.y = tanhf(z[g + 1] + bl[c0 + g + 1]) * m[1];
-            v.z = tanhf(z[g + 2] + bl[c0 + g + 2]) * m[2];
-            v.w = tanhf(z[g + 3] + bl[c0 + g + 3]) * m[3];
-            tc::store_split4(a_hi, a_lo, LBO_A, row, (c0 + g) / 4, v);
-          }
+          for (int q = 0; q < 8; ++q) v[q] = tanh_act(z[g + q] + bl[g + q]) * m[q];
+          tc::store_split4(a_hi, a_lo, LBO_A, row, (cb + g) / 4, make_float4(v[0], v[1], v[2], v[3]));
+          tc::store_split4(a_hi, a_lo, LBO_A, row, (cb + g) / 4 + 1, make_float4(v[4], v[5], v[6], v[7]));
         }
       }
       // ---- heads: [Wv0; Wp] in one N = 48 MMA
       tc::fence_proxy_async();
       tc::fence_before_sync();
-      wg_sync(wg);
-      if (row == 0) {
+      grp_sync(grp);
+      if (issuer) {
         tc::fence_after_sync();
         tc::issue_3xtf32(d_tmem, a_hi_u, a_lo_u, LBO_A, tc::smem_u32(smem + lay.h_hi), tc::smem_u32(smem + lay.h_lo), LBO_H, H,
                          idesc48);
-        tc::umma_commit(&mbar[wg]);
+        tc::umma_commit(&mbar[grp]);
       }
-      tc::mbar_wait(&mbar[wg], phase);
+      tc::mbar_wait(&mbar[grp], phase);
       phase ^= 1u;
       __syncwarp();
       tc::fence_after_sync();
-      float v0[H / 2];
-      float u;
-      {
-        const float* bv0 = smem + lay.bv0;
-        float z[16];
-        tc::tmem_ld16(d_lane, z);
-        tc::tmem_ld16(d_lane + 16, v0 + 16);
+      if (half == 0) {   // warp-uniform: warps 0-3 of the group finish the sample
+        float v0[HH];
         float zz[16];
+        tc::tmem_ld16(d_lane, v0);
+        tc::tmem_ld16(d_lane + 16, v0 + 16);
         tc::tmem_ld16(d_lane + 32, zz);
         tc::tmem_wait_ld();
-        u = zz[0] + smem[lay.bp];
+        const float u = zz[0] + smem[lay.bp];
+        const float* bv0 = smem + lay.bv0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v0[i] = z[i];
+        for (int g = 0; g < HH; g += 8) {
+          float m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+          if (dc.active) drop8(dc, static_cast<uint32_t>(L), g, static_cast<uint32_t>(L * H), m);
 #pragma unroll
-        for (int g = 0; g < H / 2; g += 4) {
-          float m[4] = {1.f, 1.f, 1.f, 1.f};
-          if (dc.active) drop4(dc, static_cast<uint32_t>(L), g, static_cast<uint32_t>(L * H), m);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) v0[g + q] = tanhf(v0[g + q] + bv0[g + q]) * m[q];
+          for (int q = 0; q < 8; ++q) v0[g + q] = tanh_act(v0[g + q] + bv0[g + q]) * m[q];
         }
-      }
-      // tail of the variance head on CUDA cores: 32 -> 16 (tanh) -> 1
-      float vraw = smem[lay.bv2];
-      {
+        // tail of the variance head on CUDA cores: 32 -> 16 (tanh) -> 1
+        float vraw = smem[lay.bv2];
         const float* Wv1 = smem + lay.Wv1;
         const float* bv1 = smem + lay.bv1;
         const float* Wv2 = smem + lay.Wv2;
@@ -245,31 +244,28 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
         for (int k = 0; k < H / 4; ++k) {
           float2 acc = make_float2(0.f, 0.f), acc2 = acc;
 #pragma unroll
-          for (int i4 = 0; i4 < H / 8; i4 += 2) {
-            const float4 w = *reinterpret_cast<const float4*>(Wv1 + k * (H / 2) + 4 * i4);
-            const float4 w2 = *reinterpret_cast<const float4*>(Wv1 + k * (H / 2) + 4 * i4 + 4);
+          for (int i4 = 0; i4 < HH / 4; ++i4) {
+            const float4 w = *reinterpret_cast<const float4*>(Wv1 + k * HH + 4 * i4);
             acc = ffma2(make_float2(w.x, w.y), make_float2(v0[4 * i4], v0[4 * i4 + 1]), acc);
             acc2 = ffma2(make_float2(w.z, w.w), make_float2(v0[4 * i4 + 2], v0[4 * i4 + 3]), acc2);
-            acc = ffma2(make_float2(w2.x, w2.y), make_float2(v0[4 * i4 + 4], v0[4 * i4 + 5]), acc);
-            acc2 = ffma2(make_float2(w2.z, w2.w), make_float2(v0[4 * i4 + 6], v0[4 * i4 + 7]), acc2);
           }
-          const float a1 = tanhf(((acc.x + acc.y) + (acc2.x + acc2.y)) + bv1[k]);
+          const float a1 = tanh_act(((acc.x + acc.y) + (acc2.x + acc2.y)) + bv1[k]);
           vraw = fmaf(Wv2[k], a1, vraw);
         }
-      }
-      const float lv = logvar_from_v(vraw);
-      if (!MC) {
-        if (valid) { out.u[s] = u; out.s[s] = lv; }
-      } else if (eval_pass) {
-        if (valid) out.pred_mean[s] = u;
-      } else {
-        const float d = u - mean;
-        mean += d / static_cast<float>(t + 1);
-        m2 = fmaf(d, u - mean, m2);
-        slv += lv;
+        const float lv = logvar_from_v(vraw);
+        if (!MC) {
+          if (valid) { out.u[s] = u; out.s[s] = lv; }
+        } else if (eval_pass) {
+          if (valid) out.pred_mean[s] = u;
+        } else {
+          const float d = u - mean;
+          mean += d / static_cast<float>(t + 1);
+          m2 = fmaf(d, u - mean, m2);
+          slv += lv;
+        }
       }
     }
-    if (MC && valid) {
+    if (MC && valid && half == 0) {
       if (out.raw_mean) out.raw_mean[s] = mean;
       if (out.raw_m2) out.raw_m2[s] = m2;
       if (out.raw_slv) out.raw_slv[s] = slv;
@@ -294,7 +290,7 @@ int launch_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, 
   for (int l = 1; l < net->n_hidden; ++l)
     if (!aligned16(net->W[l])) return 0;
   if (!aligned16(net->Wv0) || !aligned16(net->Wp)) return 0;
-  int nwg = 2;
+  int nwg = 2;  // 256-thread groups (one 128-sample tile each) per CTA
   TcLayout lay = make_tc_layout(net->n_hidden, nwg);
   if (static_cast<size_t>(lay.total) * sizeof(float) > 226 * 1024) {
     nwg = 1;
@@ -309,11 +305,11 @@ int launch_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, 
   if (mc) {
     e = cudaFuncSetAttribute(mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) { *err = static_cast<int>(e); return -1; }
-    mlp_tc_kernel<true><<<grid, 128 * nwg, smem, st>>>(*net, lay, x, n, T, dp, out);
+    mlp_tc_kernel<true><<<grid, 256 * nwg, smem, st>>>(*net, lay, x, n, T, dp, out);
   } else {
     e = cudaFuncSetAttribute(mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) { *err = static_cast<int>(e); return -1; }
-    mlp_tc_kernel<false><<<grid, 128 * nwg, smem, st>>>(*net, lay, x, n, T, dp, out);
+    mlp_tc_kernel<false><<<grid, 256 * nwg, smem, st>>>(*net, lay, x, n, T, dp, out);
   }
   *err = static_cast<int>(cudaGetLastError());
   return *err == 0 ? 1 : -1;

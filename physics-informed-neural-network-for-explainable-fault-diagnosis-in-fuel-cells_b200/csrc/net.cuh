@@ -165,13 +165,13 @@ struct TanhDropStore {
   const DropCtx* dc;
   uint32_t layer, unit_base;
   PINN_HD void operator()(int j0, float (&z)[JB]) const {
-    static_assert(JB % 4 == 0, "mask groups of 4");
+    static_assert(JB % 8 == 0, "mask groups of 8");
 #pragma unroll
-    for (int g = 0; g < JB; g += 4) {
-      float m[4] = {1.f, 1.f, 1.f, 1.f};
-      if (dc->active) drop4(*dc, layer, j0 + g, unit_base, m);
+    for (int g = 0; g < JB; g += 8) {
+      float m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+      if (dc->active) drop8(*dc, layer, j0 + g, unit_base, m);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) out.set(j0 + g + q, tanhf(z[g + q]) * m[q]);
+      for (int q = 0; q < 8; ++q) out.set(j0 + g + q, tanh_act(z[g + q]) * m[q]);
     }
   }
 };
@@ -180,7 +180,7 @@ struct TanhStore {  // no dropout (layer-0 activation kept pass-invariant; var_l
   Col out;
   PINN_HD void operator()(int j0, float (&z)[JB]) const {
 #pragma unroll
-    for (int q = 0; q < JB; ++q) out.set(j0 + q, tanhf(z[q]));
+    for (int q = 0; q < JB; ++q) out.set(j0 + q, tanh_act(z[q]));
   }
 };
 
