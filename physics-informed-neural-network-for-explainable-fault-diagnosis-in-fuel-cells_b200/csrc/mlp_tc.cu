@@ -77,7 +77,8 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
   extern __shared__ __align__(1024) float smem[];
   __shared__ __align__(8) uint64_t mbar[2];
   __shared__ uint32_t tmem_base_s;
-  const int L = lay.L, tid = threadIdx.x, grp = tid >> 8, half = (tid >> 7) & 1, row = tid & 127, warp = tid >> 5;
+  const int L = lay.L, tid = threadIdx.x, row = tid & 127;
+  const int warp = tc::uniform_warp_idx(), grp = warp >> 3, half = (warp >> 2) & 1;  // warp-uniform roles
   const int ngrp = blockDim.x >> 8;
   const int Dm = L * H + H / 2;
   const int cb = half * HH;  // first column owned by this thread
@@ -121,9 +122,11 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
   const uint32_t d_lane = d_tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16); // this warp's 32 lanes
   float* a_hi = smem + lay.a_hi[grp];
   float* a_lo = smem + lay.a_lo[grp];
-  const uint32_t a_hi_u = tc::smem_u32(a_hi), a_lo_u = tc::smem_u32(a_lo);
+  const uint64_t a_hi_d = tc::make_desc(tc::smem_u32(a_hi), LBO_A, 128), a_lo_d = tc::make_desc(tc::smem_u32(a_lo), LBO_A, 128);
+  const uint64_t h_hi_d = tc::make_desc(tc::smem_u32(smem + lay.h_hi), LBO_H, 128);
+  const uint64_t h_lo_d = tc::make_desc(tc::smem_u32(smem + lay.h_lo), LBO_H, 128);
   const uint32_t idesc64 = tc::make_idesc_tf32(kTcTile, H), idesc48 = tc::make_idesc_tf32(kTcTile, kHeadN);
-  const bool issuer = (tid & 255) == 0;
+  const bool issuer_warp = (warp & 7) == 0;
   uint32_t phase = 0;
 
   // ---------------------------------------------------------------- tiles of this group
@@ -179,11 +182,15 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
         tc::fence_proxy_async();
         tc::fence_before_sync();
         grp_sync(grp);
-        if (issuer) {
-          tc::fence_after_sync();
-          tc::issue_3xtf32(d_tmem, a_hi_u, a_lo_u, LBO_A, tc::smem_u32(smem + lay.b_hi[l]), tc::smem_u32(smem + lay.b_lo[l]),
-                           LBO_B, H, idesc64);
-          tc::umma_commit(&mbar[grp]);
+        if (issuer_warp) {
+          const uint64_t b_hi_d = tc::make_desc(tc::smem_u32(smem + lay.b_hi[l]), LBO_B, 128);
+          const uint64_t b_lo_d = tc::make_desc(tc::smem_u32(smem + lay.b_lo[l]), LBO_B, 128);
+          if (tc::elect_one()) {
+            tc::fence_after_sync();
+            tc::issue_3xtf32<H>(d_tmem, a_hi_d, a_lo_d, LBO_A, b_hi_d, b_lo_d, LBO_B, idesc64);
+            tc::umma_commit(&mbar[grp]);
+          }
+          __syncwarp();
         }
         tc::mbar_wait(&mbar[grp], phase);
         phase ^= 1u;
@@ -209,11 +216,13 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
       tc::fence_proxy_async();
       tc::fence_before_sync();
       grp_sync(grp);
-      if (issuer) {
-        tc::fence_after_sync();
-        tc::issue_3xtf32(d_tmem, a_hi_u, a_lo_u, LBO_A, tc::smem_u32(smem + lay.h_hi), tc::smem_u32(smem + lay.h_lo), LBO_H, H,
-                         idesc48);
-        tc::umma_commit(&mbar[grp]);
+      if (issuer_warp) {
+        if (tc::elect_one()) {
+          tc::fence_after_sync();
+          tc::issue_3xtf32<H>(d_tmem, a_hi_d, a_lo_d, LBO_A, h_hi_d, h_lo_d, LBO_H, idesc48);
+          tc::umma_commit(&mbar[grp]);
+        }
+        __syncwarp();
       }
       tc::mbar_wait(&mbar[grp], phase);
       phase ^= 1u;

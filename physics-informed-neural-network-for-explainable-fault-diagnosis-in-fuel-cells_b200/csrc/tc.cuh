@@ -21,6 +21,21 @@ namespace tc {
 
 PINN_D uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
+// One lane of a converged warp (CUTLASS's elect_one_sync): keeps the surrounding code
+// warp-uniform, so UMMA descriptors stay in uniform registers.
+PINN_D bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
+// Warp index as a provably warp-uniform value (shuffle broadcast).
+PINN_D int uniform_warp_idx() { return __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0); }
+
 // ------------------------------------------------------------------------- mbarrier
 PINN_D void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -29,7 +44,7 @@ PINN_D void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluste
 PINN_D void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok;
-  do {
+  for (;;) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -37,7 +52,9 @@ PINN_D void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(addr), "r"(parity)
         : "memory");
-  } while (!ok);
+    if (ok) break;
+    __nanosleep(40);   // do not burn issue slots the other group's epilogue could use
+  }
 }
 // generic-proxy smem writes -> visible to the async proxy (UMMA operand reads)
 PINN_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -114,20 +131,20 @@ PINN_D void store_split4(float* hi_plane, float* lo_plane, uint32_t lbo_bytes, i
   *reinterpret_cast<float4*>(lo_plane + off) = l;
 }
 
-// Issue the 3xTF32 product  D[M x N] = A[M x K] * B[N x K]^T  (K multiple of 8) from one thread.
-// a_hi/a_lo/b_hi/b_lo: shared-memory byte addresses of the operand planes.
-PINN_D void issue_3xtf32(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t lbo_a, uint32_t b_hi, uint32_t b_lo,
-                         uint32_t lbo_b, int K, uint32_t idesc) {
-  uint32_t acc = 0;
-#pragma unroll 1
+// Issue the 3xTF32 product  D[M x N] = A[M x 64] * B[N x 64]^T  from one thread: 24 MMAs
+// back to back.  Descriptors are built once by the caller; stepping one K = 8 slab adds
+// 2*LBO (in 16-byte units) to the start-address field, so each MMA costs one add.
+template <int K>
+PINN_D void issue_3xtf32(uint32_t d_tmem, uint64_t a_hi0, uint64_t a_lo0, uint32_t lbo_a, uint64_t b_hi0, uint64_t b_lo0,
+                         uint32_t lbo_b, uint32_t idesc) {
+  const uint64_t a_step = (2u * lbo_a) >> 4, b_step = (2u * lbo_b) >> 4;
+#pragma unroll
   for (int term = 0; term < 3; ++term) {      // small terms first: lo*hi, hi*lo, then hi*hi
-    const uint32_t a = term == 0 ? a_lo : a_hi;
-    const uint32_t b = term == 1 ? b_lo : b_hi;
-#pragma unroll 1
-    for (int k8 = 0; k8 < K / 8; ++k8) {      // one MMA consumes K = 8 tf32 = two 16-byte chunks
-      umma_tf32(d_tmem, make_desc(a + 2 * k8 * lbo_a, lbo_a, 128), make_desc(b + 2 * k8 * lbo_b, lbo_b, 128), idesc, acc);
-      acc = 1;
-    }
+    const uint64_t a = term == 0 ? a_lo0 : a_hi0;
+    const uint64_t b = term == 1 ? b_lo0 : b_hi0;
+#pragma unroll
+    for (int k8 = 0; k8 < K / 8; ++k8)        // one MMA consumes K = 8 tf32 = two 16-byte chunks
+      umma_tf32(d_tmem, a + k8 * a_step, b + k8 * b_step, idesc, (term | k8) != 0 ? 1u : 0u);
   }
 }
 

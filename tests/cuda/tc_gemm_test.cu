@@ -36,8 +36,9 @@ __global__ void __launch_bounds__(128) gemm_kernel(const float* __restrict__ A, 
   tc::fence_after_sync();
   const uint32_t taddr = tmem_base;
   if (tid == 0) {
-    tc::issue_3xtf32(taddr, tc::smem_u32(a_hi), tc::smem_u32(a_lo), LBO_A, tc::smem_u32(b_hi), tc::smem_u32(b_lo), LBO_B, K,
-                     tc::make_idesc_tf32(M, N));
+    tc::issue_3xtf32<K>(taddr, tc::make_desc(tc::smem_u32(a_hi), LBO_A, 128), tc::make_desc(tc::smem_u32(a_lo), LBO_A, 128), LBO_A,
+                        tc::make_desc(tc::smem_u32(b_hi), LBO_B, 128), tc::make_desc(tc::smem_u32(b_lo), LBO_B, 128), LBO_B,
+                        tc::make_idesc_tf32(M, N));
     tc::umma_commit(&bar);
   }
   tc::mbar_wait(&bar, 0);
