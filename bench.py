@@ -155,7 +155,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------ our arm
@@ -276,6 +276,7 @@ def run_ours(args):
 
     if rank != 0:
         if world > 1:
+            dist.barrier()           # keep every rank alive until rank 0 has printed its line
             dist.destroy_process_group()
         return
     pk = peaks()
@@ -316,8 +317,9 @@ def run_ours(args):
                                 "sample": f"get_MC_samples port, N=200000 x T'=1 ({t1:.1f} s); train_dnn port 1 step at "
                                           f"N=100000 ({t2:.1f} s)",
                                 "train_steps_per_s_at_1M": tr_rate}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
