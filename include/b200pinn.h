@@ -110,7 +110,9 @@ enum { /* families bitmask */
   PINN_FAM_DATA = 32 /* sum (y-u)^2, needs y */
 };
 enum { /* flags */
-  PINN_RES_ACCURATE_MATH = 1 /* libdevice logf/expf/powf instead of MUFU approximations */
+  PINN_RES_ACCURATE_MATH = 1, /* libdevice logf/expf/powf instead of MUFU approximations */
+  PINN_RES_NO_MODE_A = 2,     /* skip the normalised-domain sums EA2/GA* (train_lambda dnn_para=True) */
+  PINN_RES_NO_MODE_B = 4      /* skip FV2/GB* (train_lambda dnn_para=False) */
 };
 enum { /* sums[] slots (double) */
   PINN_S_N = 0,

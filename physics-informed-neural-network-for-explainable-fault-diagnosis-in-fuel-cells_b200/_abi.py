@@ -19,7 +19,7 @@ N_LAMBDA = 17
 
 # families / flags / slots: keep in sync with include/b200pinn.h (tests check the header)
 FAM_V, FAM_TS, FAM_T, FAM_H, FAM_O, FAM_DATA = 1, 2, 4, 8, 16, 32
-RES_ACCURATE_MATH = 1
+RES_ACCURATE_MATH, RES_NO_MODE_A, RES_NO_MODE_B = 1, 2, 4
 SUM_NAMES = ["N", "FV2", "EA2", "DATA2", "GA1", "GA2", "GA3", "GB1", "GB2", "GB3",
              "FT2", "FTABS", "GT1", "GT3", "GT5", "FTE2",
              "FH2", "GH1", "GH2", "GH3", "HACT", "HTGT",

@@ -38,9 +38,86 @@ PINN_D Row load_phys(const float* __restrict__ x, int64_t s, const pinn_scalers_
   return o;
 }
 
+PINN_D float mufu_lg2(float v) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+PINN_D float mufu_ex2(float v) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+PINN_D float mufu_rcp(float v) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+
 struct Lam {  // 01:453-517 order
   float l1, l2, l3, l4, T1, T2, T3, T4, T5, H1, H2, H3, H4, O1, O2, O3, O4;
 };
+
+// Loop-invariant constants of the fast voltage path: scaler affines folded with the physical
+// constants of 01:729-761, and everything that depends only on lambda_1..3 hoisted.
+struct VConst {
+  float i_a, i_b;        // i   = x0*i_a + i_b            (I/270 + 1e-5)
+  float tk_a, tk_b;      // Tk  = x5*tk_a + tk_b          (T_out + 273.15)
+  float ph_a, ph_b;      // PH2 = x3*ph_a + ph_b          (P_H/101 + 1)
+  float pa_a, pa_b;      // Pair likewise with x4
+  float vo_a, vo_b;      // V_out = u*vo_a + vo_b         (stack volts / 5)
+  float lg_ph2o;         // log2(P_H2O)
+  float inv_l2, inv_l3, l1, l3;
+  float ea_a, ea_b;      // (5 V_est) scale_y + min_y = V_est*ea_a + ea_b
+  float ga;              // -2 * 5 * scale_y
+};
+PINN_D VConst make_vconst(const pinn_scalers_t& sc, const Lam& L) {
+  VConst c;
+  c.i_a = sc.x_inv_scale[0] / 270.0f; c.i_b = 1e-5f - sc.x_off[0] / 270.0f;
+  c.tk_a = sc.x_inv_scale[5];         c.tk_b = 273.15f - sc.x_off[5];
+  c.ph_a = sc.x_inv_scale[3] / 101.0f; c.ph_b = 1.0f - sc.x_off[3] / 101.0f;
+  c.pa_a = sc.x_inv_scale[4] / 101.0f; c.pa_b = 1.0f - sc.x_off[4] / 101.0f;
+  c.vo_a = sc.y_inv_scale / 5.0f;     c.vo_b = -sc.y_off / 5.0f;
+  c.lg_ph2o = log2f(sc.p_h2o);
+  c.inv_l2 = 1.0f / L.l2; c.inv_l3 = 1.0f / L.l3; c.l1 = L.l1; c.l3 = L.l3;
+  c.ea_a = 5.0f * sc.scale_y; c.ea_b = sc.min_y; c.ga = -10.0f * sc.scale_y;
+  return c;
+}
+// ~70 instructions and 9 MUFU per sample (the generic path is ~230): same formulas as
+// net_f_V with logs taken base 2 and products folded; absolute deviations ~1e-8 V.
+PINN_D void eval_V_fast(const VConst& c, float p_h2o, float x0, float x3, float x4, float x5, float us, float ys, bool has_y,
+                        bool mode_a, bool mode_b, float* acc, float* __restrict__ cols, int64_t n, int64_t s) {
+  constexpr float LN2 = 0.6931471805599453f, LOG2E = 1.4426950408889634f;
+  constexpr float CB = 8.314f / 96485.0f;                 // b = R Tk / (2 alpha F), alpha = 0.5
+  const float i = fmaf(x0, c.i_a, c.i_b);
+  const float Tk = fmaf(x5, c.tk_a, c.tk_b);
+  const float PH2 = fmaf(x3, c.ph_a, c.ph_b), Pair = fmaf(x4, c.pa_a, c.pa_b);
+  const float z = i * mufu_ex2(-1.334f * mufu_lg2(Tk));    // i / Tk^1.334
+  const float ppH2 = 0.5f * fmaf(PH2, mufu_ex2(-1.653f * LOG2E * z), -p_h2o);
+  const float ppO2 = fmaf(Pair, mufu_ex2(-4.192f * LOG2E * z), -p_h2o);
+  const float b = CB * Tk;
+  const float bl = b * LN2;
+  const float lg_i = mufu_lg2(i * c.inv_l2);
+  const float lg_c = mufu_lg2(fmaf(-i, c.inv_l3, 1.0f));
+  const float lg_n = c.lg_ph2o - mufu_lg2(ppH2) - 0.5f * mufu_lg2(ppO2);
+  const float Vact = -bl * lg_i;
+  const float Vconc = 0.5f * bl * lg_c;
+  const float E = fmaf(-0.5f * bl, lg_n, 220170.0f / (2.0f * 96485.0f));
+  const float Vohm = -i * c.l1;
+  const float Vest = (E + Vact) + (Vohm + Vconc);
+  const float Vout = fmaf(us, c.vo_a, c.vo_b);
+  const float fV = Vest - Vout;
+  const float d2 = b * c.inv_l2;
+  const float d3 = 0.5f * b * i * mufu_rcp(c.l3 * (c.l3 - i));
+  if (mode_b) {
+    const float g = 2.0f * fV;
+    acc[PINN_S_FV2] = fmaf(fV, fV, acc[PINN_S_FV2]);
+    acc[PINN_S_GB1] = fmaf(-g, i, acc[PINN_S_GB1]);
+    acc[PINN_S_GB2] = fmaf(g, d2, acc[PINN_S_GB2]);
+    acc[PINN_S_GB3] = fmaf(g, d3, acc[PINN_S_GB3]);
+  }
+  if (mode_a && has_y) {
+    const float eA = ys - fmaf(Vest, c.ea_a, c.ea_b);
+    const float g = c.ga * eA;
+    acc[PINN_S_EA2] = fmaf(eA, eA, acc[PINN_S_EA2]);
+    acc[PINN_S_GA1] = fmaf(-g, i, acc[PINN_S_GA1]);
+    acc[PINN_S_GA2] = fmaf(g, d2, acc[PINN_S_GA2]);
+    acc[PINN_S_GA3] = fmaf(g, d3, acc[PINN_S_GA3]);
+  }
+  if (cols) {
+    auto put = [&](int col, float v) { cols[static_cast<size_t>(col) * n + s] = v; };
+    put(PINN_C_FV, fV); put(PINN_C_VACT, Vact); put(PINN_C_VOHM, Vohm); put(PINN_C_VCONC, Vconc);
+    put(PINN_C_ENERNST, E); put(PINN_C_VEST5, Vest * 5.0f); put(PINN_C_I, i); put(PINN_C_VOUT5, Vout * 5.0f);
+  }
+}
 
 template <uint32_t FAMC, bool ACC>
 PINN_D void eval_sample(const float* __restrict__ x, const float* __restrict__ u, const float* __restrict__ y,
@@ -186,29 +263,13 @@ PINN_D void eval_sample(const float* __restrict__ x, const float* __restrict__ u
   }
 }
 
-// Workspace: double partials[grid][PINN_S_COUNT] followed by one uint32 ticket (zeroed
-// once by the caller; the last CTA resets it).
-template <uint32_t FAMC, bool ACC>
-__global__ void __launch_bounds__(kResThreads, kResCtasPerSm)
-residual_kernel(const float* __restrict__ x, const float* __restrict__ u, const float* __restrict__ y, int64_t n,
-                pinn_scalers_t sc, const float* __restrict__ lam, uint32_t fam, const float* halo_x,
-                const float* halo_u, float* __restrict__ cols, double* __restrict__ partials,
-                unsigned int* ticket, double* __restrict__ sums) {
+// Block reduce of the per-thread accumulators -> this CTA's double partial; the last CTA to
+// arrive sums all partials in a fixed order (deterministic) with the whole block: thread
+// (slot = t % 32, lane-group = t / 32) adds every 8th CTA's partial, then the 8 groups are
+// folded in order.
+PINN_D void finish_sums(const float* acc, double* __restrict__ partials, unsigned int* ticket, double* __restrict__ sums) {
   __shared__ double red[kResThreads / 32][PINN_S_COUNT];
   __shared__ bool is_last;
-  Lam L;
-  {
-    const float* lp = lam;
-    L = Lam{lp[0], lp[1], lp[2], lp[3], lp[4], lp[5], lp[6], lp[7], lp[8], lp[9], lp[10], lp[11], lp[12],
-            lp[13], lp[14], lp[15], lp[16]};
-  }
-  float acc[PINN_S_COUNT];
-#pragma unroll
-  for (int k = 0; k < PINN_S_COUNT; ++k) acc[k] = 0.f;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; s < n; s += stride)
-    eval_sample<FAMC, ACC>(x, u, y, s, n, sc, L, fam, halo_x, halo_u, cols, acc);
-
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < PINN_S_COUNT; ++k) {
@@ -232,18 +293,89 @@ residual_kernel(const float* __restrict__ x, const float* __restrict__ u, const 
   __syncthreads();
   if (is_last) {
     __threadfence();
+    const int slot = lane, grp = warp;       // 8 warps: warp g sums CTAs g, g+8, ...
+    double v = 0.0;
+    if (slot < PINN_S_COUNT)
+      for (unsigned int b = grp; b < gridDim.x; b += kResThreads / 32)
+        v += partials[static_cast<size_t>(b) * PINN_S_COUNT + slot];
+    __syncthreads();
+    if (slot < PINN_S_COUNT) red[grp][slot] = v;
+    __syncthreads();
     if (threadIdx.x < PINN_S_COUNT) {
-      double v = 0.0;
-      for (unsigned int b = 0; b < gridDim.x; ++b) v += partials[static_cast<size_t>(b) * PINN_S_COUNT + threadIdx.x];
-      sums[threadIdx.x] = v;
+      double t = 0.0;
+      for (int g = 0; g < kResThreads / 32; ++g) t += red[g][threadIdx.x];
+      sums[threadIdx.x] = t;
     }
     if (threadIdx.x == 0) *ticket = 0u;
   }
 }
 
-static int res_grid(int64_t n) {
-  int64_t want = (n + kResThreads - 1) / kResThreads;
-  int64_t cap = static_cast<int64_t>(sm_count()) * kResCtasPerSm;
+// Training-form kernel of the voltage phase (train_lambda, 01:1008-1055), MUFU math: consumes
+// columns 0,3,4,5 of the row plus u and y -- 40 algorithmic bytes per sample; two samples per
+// loop trip so four 128-bit loads are in flight per thread.
+__global__ void __launch_bounds__(kResThreads, 4)
+residual_v_fast_kernel(const float* __restrict__ x, const float* __restrict__ u, const float* __restrict__ y, int64_t n,
+                       pinn_scalers_t sc, const float* __restrict__ lam, uint32_t fam, uint32_t flags,
+                       double* __restrict__ partials, unsigned int* ticket, double* __restrict__ sums) {
+  Lam L;
+  L = Lam{lam[0], lam[1], lam[2], lam[3], lam[4], lam[5], lam[6], lam[7], lam[8], lam[9], lam[10], lam[11], lam[12],
+          lam[13], lam[14], lam[15], lam[16]};
+  const VConst c = make_vconst(sc, L);
+  const bool do_v = (fam & PINN_FAM_V) != 0, do_d = (fam & PINN_FAM_DATA) != 0 && y != nullptr;
+  const bool mode_a = !(flags & PINN_RES_NO_MODE_A), mode_b = !(flags & PINN_RES_NO_MODE_B), has_y = y != nullptr;
+  float acc[PINN_S_COUNT];
+#pragma unroll
+  for (int k = 0; k < PINN_S_COUNT; ++k) acc[k] = 0.f;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  auto one = [&](float4 a, float4 b, float us, float ys, int64_t idx) {
+    acc[PINN_S_N] += 1.0f;
+    if (do_v) eval_V_fast(c, sc.p_h2o, a.x, a.w, b.x, b.y, us, ys, has_y, mode_a, mode_b, acc, nullptr, n, idx);
+    if (do_d) { const float e = ys - us; acc[PINN_S_DATA2] = fmaf(e, e, acc[PINN_S_DATA2]); }
+  };
+  for (; s + stride < n; s += 2 * stride) {
+    const float4* p0 = reinterpret_cast<const float4*>(x + s * PINN_N_IN);
+    const float4* p1 = reinterpret_cast<const float4*>(x + (s + stride) * PINN_N_IN);
+    const float4 a0 = __ldg(p0), b0 = __ldg(p0 + 1), a1 = __ldg(p1), b1 = __ldg(p1 + 1);
+    const float u0 = __ldg(u + s), u1 = __ldg(u + s + stride);
+    const float y0 = has_y ? __ldg(y + s) : 0.f, y1 = has_y ? __ldg(y + s + stride) : 0.f;
+    one(a0, b0, u0, y0, s);
+    one(a1, b1, u1, y1, s + stride);
+  }
+  if (s < n) {
+    const float4* p0 = reinterpret_cast<const float4*>(x + s * PINN_N_IN);
+    one(__ldg(p0), __ldg(p0 + 1), __ldg(u + s), has_y ? __ldg(y + s) : 0.f, s);
+  }
+  finish_sums(acc, partials, ticket, sums);
+}
+
+// Workspace: double partials[grid][PINN_S_COUNT] followed by one uint32 ticket (zeroed
+// once by the caller; the last CTA resets it).
+template <uint32_t FAMC, bool ACC>
+__global__ void __launch_bounds__(kResThreads, kResCtasPerSm)
+residual_kernel(const float* __restrict__ x, const float* __restrict__ u, const float* __restrict__ y, int64_t n,
+                pinn_scalers_t sc, const float* __restrict__ lam, uint32_t fam, const float* halo_x,
+                const float* halo_u, float* __restrict__ cols, double* __restrict__ partials,
+                unsigned int* ticket, double* __restrict__ sums) {
+  Lam L;
+  {
+    const float* lp = lam;
+    L = Lam{lp[0], lp[1], lp[2], lp[3], lp[4], lp[5], lp[6], lp[7], lp[8], lp[9], lp[10], lp[11], lp[12],
+            lp[13], lp[14], lp[15], lp[16]};
+  }
+  float acc[PINN_S_COUNT];
+#pragma unroll
+  for (int k = 0; k < PINN_S_COUNT; ++k) acc[k] = 0.f;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; s < n; s += stride)
+    eval_sample<FAMC, ACC>(x, u, y, s, n, sc, L, fam, halo_x, halo_u, cols, acc);
+
+  finish_sums(acc, partials, ticket, sums);
+}
+
+static int res_grid(int64_t n, int ctas_per_sm = kResCtasPerSm, int samples_per_thread = 1) {
+  int64_t want = (n + static_cast<int64_t>(kResThreads) * samples_per_thread - 1) / (static_cast<int64_t>(kResThreads) * samples_per_thread);
+  int64_t cap = static_cast<int64_t>(sm_count()) * ctas_per_sm;
   return static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
@@ -253,7 +385,7 @@ using namespace pinn;
 
 extern "C" size_t pinn_residuals_workspace_bytes(int64_t n) {
   (void)n;
-  size_t cap = static_cast<size_t>(sm_count()) * kResCtasPerSm;
+  size_t cap = static_cast<size_t>(sm_count()) * 4;
   return cap * PINN_S_COUNT * sizeof(double) + 16;
 }
 
@@ -271,7 +403,7 @@ extern "C" int pinn_residuals(const float* x, const float* u, const float* y, in
   const int grid = res_grid(n);
   double* partials = static_cast<double*>(workspace);
   unsigned int* ticket = reinterpret_cast<unsigned int*>(
-      static_cast<char*>(workspace) + static_cast<size_t>(sm_count()) * kResCtasPerSm * PINN_S_COUNT * sizeof(double));
+      static_cast<char*>(workspace) + static_cast<size_t>(sm_count()) * 4 * PINN_S_COUNT * sizeof(double));
   const bool accm = (flags & PINN_RES_ACCURATE_MATH) != 0;
   const uint32_t f = families;
 #define LAUNCH(FAMC)                                                                                          \
@@ -284,6 +416,11 @@ extern "C" int pinn_residuals(const float* x, const float* u, const float* y, in
                                                                  halo_u, cols, partials, ticket, sums);      \
   } while (0)
   constexpr uint32_t VD = PINN_FAM_V | PINN_FAM_DATA;
+  if ((f & ~VD) == 0 && !accm && cols == nullptr && (n == 0 || u != nullptr)) {
+    const int g4 = res_grid(n, 4, 2);
+    residual_v_fast_kernel<<<g4, kResThreads, 0, st>>>(x, u, y, n, *scalers, lambdas, f, flags, partials, ticket, sums);
+    return static_cast<int>(cudaGetLastError());
+  }
   constexpr uint32_t ALL = PINN_FAM_V | PINN_FAM_TS | PINN_FAM_T | PINN_FAM_H | PINN_FAM_O | PINN_FAM_DATA;
   if ((f & ~VD) == 0) LAUNCH(VD);
   else if (f == PINN_FAM_TS) LAUNCH(PINN_FAM_TS);

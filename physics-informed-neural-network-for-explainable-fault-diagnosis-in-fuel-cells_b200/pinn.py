@@ -258,7 +258,8 @@ class PhysicsInformedNN:
             print(f"DNN training done, final loss: {loss:.3e}\n")
         return loss
 
-    def _train_scalars(self, nIter, lo_idx, hi_idx, slots, bounds, lr, gamma, fam, need_u, need_y, report, verbose):
+    def _train_scalars(self, nIter, lo_idx, hi_idx, slots, bounds, lr, gamma, fam, need_u, need_y, report, verbose,
+                       flags=0):
         lam = self._lambdas()
         sl = lam[lo_idx:hi_idx]
         m, v = torch.zeros_like(sl), torch.zeros_like(sl)
@@ -279,7 +280,7 @@ class PhysicsInformedNN:
         world = _world()
         last = None
         for epoch in range(nIter):
-            K.residuals(x, u, y, sc, lam, fam, sums=sums)
+            K.residuals(x, u, y, sc, lam, fam, flags=flags, sums=sums)
             if world > 1:
                 _allreduce(sums)
             K.adam_step_from_sums(sl, sums, slot_t, m, v, counter, lr, gamma, 1000, lo, hi)
@@ -308,7 +309,7 @@ class PhysicsInformedNN:
         if verbose:
             print("================ voltage-parameter training ================")
         s = self._train_scalars(nIter, 0, 4, slots, bounds, 1e-3, 0.8, _abi.FAM_V | _abi.FAM_DATA, True, True,
-                                report, verbose)
+                                report, verbose, flags=_abi.RES_NO_MODE_A if dnn_para else _abi.RES_NO_MODE_B)
         return None if s is None else (s[S[phys]] + s[S["DATA2"]]) / max(s[S["N"]], 1.0)
 
     def train_thermal(self, nIter, verbose=True):

@@ -60,6 +60,9 @@ def test_python_constants_match_header():
     c = enum_values("PINN_C_")
     assert c.pop("PINN_C_COUNT") == abi.C_COUNT
     assert {k[len("PINN_C_"):]: v for k, v in c.items()} == abi.COL
+    r = enum_values("PINN_RES_")
+    assert (r["PINN_RES_ACCURATE_MATH"], r["PINN_RES_NO_MODE_A"], r["PINN_RES_NO_MODE_B"]) == \
+        (abi.RES_ACCURATE_MATH, abi.RES_NO_MODE_A, abi.RES_NO_MODE_B)
     f = enum_values("PINN_FAM_")
     assert (f["PINN_FAM_V"], f["PINN_FAM_TS"], f["PINN_FAM_T"], f["PINN_FAM_H"], f["PINN_FAM_O"],
             f["PINN_FAM_DATA"]) == (abi.FAM_V, abi.FAM_TS, abi.FAM_T, abi.FAM_H, abi.FAM_O, abi.FAM_DATA)

@@ -150,6 +150,33 @@ def test_residual_sums_and_lambda_grads_golden(golden, flags):
     assert close(s[S["FTE2"]] / n, np.mean(fT.astype(np.float64) ** 2), LOSS_TOL)
 
 
+def test_voltage_phase_fast_kernel_modes_golden(golden):
+    """The dedicated train_lambda kernel (V|DATA families, MUFU math, no column output) with each
+    mode switched off in turn: the active mode's sums must match the reference, the other's be 0."""
+    from b200pinn import _abi, kernels as K
+
+    S = _abi.S
+    m = make_model(golden)
+    m.dnn.eval()
+    u = m.net_u(m.x)[0].detach().reshape(-1).contiguous()
+    y = m.u.reshape(-1).contiguous()
+    n = golden["x"].shape[0]
+    for flag, mode, ph, gs, off in ((_abi.RES_NO_MODE_B, 0, "EA2", ("GA1", "GA2", "GA3"), ("FV2", "GB1")),
+                                    (_abi.RES_NO_MODE_A, 1, "FV2", ("GB1", "GB2", "GB3"), ("EA2", "GA1"))):
+        sums, _ = K.residuals(m.x.detach(), u, y, m._scalers(golden["sx"]), m._lambdas(), _abi.FAM_V | _abi.FAM_DATA,
+                              flags=flag)
+        s = t2n(sums)
+        ref = golden[f"L:lambda:{mode}"]
+        got = np.array([(s[S[ph]] + s[S["DATA2"]]) / n, s[S[ph]] / n, s[S["DATA2"]] / n])
+        assert np.allclose(got, ref, rtol=2 * LOSS_TOL), (got, ref)
+        g64 = O.lambda_losses(golden["x"], golden["y"], t2n(u), golden["sx"], golden["sy"], golden["lam0"][:3],
+                              bool(mode), np.float64)[3]
+        refg = golden[f"LG:lambda:{mode}"]
+        got_g = np.array([s[S[k]] / n for k in gs])
+        assert np.all(np.abs(got_g - g64) <= GRAD_TOL * np.abs(refg) + 1.5 * np.abs(refg - g64) + 1e-12), (got_g, refg)
+        assert all(s[S[k]] == 0.0 for k in off)
+
+
 def test_net_f_autograd_wrt_lambdas_golden(golden):
     """External callers may call .backward() on mean(f^2) like the reference's loops do."""
     m = make_model(golden)
