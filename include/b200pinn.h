@@ -158,6 +158,42 @@ int pinn_mc_dropout(const pinn_net_t* net, const float* x, int64_t n, int32_t T,
                     void* stream);
 size_t pinn_mc_workspace_bytes(int32_t width, int32_t n_hidden, int64_t n);
 
+/* f1 -- export row writer: the 22-column float64 `comprehensive_results` row of
+ * create_comprehensive_results_array_v2 (01:1907-2010), incl. the segment-wise centred
+ * moving average of both uncertainties (smooth_by_segments 01:1848-1872; pandas window
+ * span [i-w/2, i+w/2-1], min_periods=1) and the segment labels (create_fault_labels
+ * 01:2013-2031).  `cols` is the [PINN_C_COUNT][n] output of pinn_residuals; seg_ends[n_seg]
+ * (device, int64) are the exclusive segment ends; segments 1..n_labeled get label = index. */
+typedef struct pinn_export_scalers {
+  double x_min[PINN_N_IN], x_scale[PINN_N_IN]; /* scaler_X.min_, scaler_X.scale_       */
+  double y_min, y_scale;                       /* scaler_Y.min_[0], scaler_Y.scale_[0] */
+  double min_y, scale_y;                       /* float64 affine rebuilt at 01:1920-1925 */
+} pinn_export_scalers_t;
+int pinn_export_rows(const float* x, const float* y, const float* pred_mean,
+                     const float* a_u, const float* e_u, const float* cols,
+                     const int64_t* seg_ends, int32_t n_seg, int32_t n_labeled,
+                     int32_t window, const pinn_export_scalers_t* scalers, int64_t n,
+                     double* out, void* stream);
+
+/* f2 -- RF(t) risk function of 04_risk_function_early_warning_index.py, float64, for
+ * n_series independent stacks laid out as results[n_series][n][22]:
+ * pinn_rf_stats  = estimate_mu_sigma_normal (04:181-197): nan-mean / nan-std (ddof 1) of
+ *                  columns 12..16 over label-0 rows -> mu_sigma[n_series][10] (mu, sigma);
+ * pinn_rf_series = compute_rf_time_series (04:201-285) + find_first_alarm_index
+ *                  (04:289-300): outputs [n_series][n]; first_alarm[n_series] = first index
+ *                  with RF_smooth >= warn_threshold, -1 if none.  c_out / s_out optional. */
+typedef struct pinn_rf_params {
+  double z_safe, lambda_decay, k_logistic, c0_logistic, c_max, alpha_smooth, warn_threshold;
+} pinn_rf_params_t;
+size_t pinn_rf_workspace_bytes(int64_t n, int32_t n_series);
+int pinn_rf_stats(const double* results, int64_t n, int32_t n_series, double* mu_sigma,
+                  void* workspace, size_t workspace_bytes, void* stream);
+int pinn_rf_series(const double* results, int64_t n, int32_t n_series,
+                   const double* mu_sigma, const pinn_rf_params_t* params,
+                   double* rf_inst, double* rf_smooth, double* c_out, double* s_out,
+                   int64_t* first_alarm, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
 /* f3 -- torch.optim.Adam (defaults) + StepLR + box clamp, fused, state on device
  * (01:939-940,999-1002,1040-1047,...).  step_counter is int64[2] on the device, zeroed
  * once by the caller: [0] = steps taken so far (read, then incremented when

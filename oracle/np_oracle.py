@@ -381,3 +381,101 @@ def mc_dropout(params, x, masks_t, dtype=np.float32):
         us.append(u)
         ss.append(s)
     return mc_statistics(np.stack([pe] * T), np.stack(us), np.stack(ss), dtype)
+
+
+# ------------------------------------------------------------- export rows (f1) / RF(t) (f2)
+def moving_average_centered(arr, window):
+    """``_moving_average_centered`` (01:1830-1846): pandas ``rolling(window, center=True,
+    min_periods=1).mean()``; for an even window the span of element i is [i-w/2, i+w/2-1]
+    (SURVEY section 5 [probe])."""
+    a = np.asarray(arr, np.float64)
+    n, half = a.shape[0], window // 2
+    out = np.empty(n, np.float64)
+    c = np.concatenate([[0.0], np.cumsum(a)])
+    for i in range(n):
+        lo, hi = max(0, i - half), min(n, i + (window - half))
+        out[i] = (c[hi] - c[lo]) / (hi - lo)
+    return out
+
+
+def smooth_by_segments(values, boundary_lines, window):
+    """``smooth_by_segments`` (01:1848-1872): smooth each [start, end) segment on its own."""
+    v = np.asarray(values, np.float64)
+    n = v.shape[0]
+    if not boundary_lines or boundary_lines[-1] < n:
+        return moving_average_centered(v, window)
+    bl = [b for b in boundary_lines if 0 < b <= n] if boundary_lines[-1] != n else list(boundary_lines)
+    out = np.empty(n, np.float64)
+    for s, e in zip([0] + bl[:-1], bl):
+        out[s:e] = moving_average_centered(v[s:e], window)
+    return out
+
+
+def fault_labels(n, boundary_lines, n_faults):
+    """``create_fault_labels`` (01:2013-2047): 0 for the normal block, i+1 for fault segment i."""
+    lab = np.zeros(n)
+    for i in range(n_faults):
+        lab[boundary_lines[i]:boundary_lines[i + 1]] = i + 1
+    return lab
+
+
+def export_rows(x_norm, y_norm, pred_mean, a_u, e_u, fV, fT, fH, fO, V5, T_pred, actH, actO, labels, x_scal, u_scal,
+                boundaries, window=200):
+    """22-column ``comprehensive_results`` of ``create_comprehensive_results_array_v2``
+    (01:1907-2010); inputs are the fp32 arrays the reference has at that point."""
+    n = x_norm.shape[0]
+    out = np.zeros((n, 22))
+    out[:, 0:8] = inverse_transform(x_scal, x_norm, np.float32)
+    yr = inverse_transform(u_scal, np.asarray(y_norm).reshape(-1, 1), np.float32).flatten()
+    lo, hi = float(u_scal.feature_range[0]), float(u_scal.feature_range[1])
+    dmin, dmax = u_scal.data_min_.astype(np.float64), u_scal.data_max_.astype(np.float64)
+    scale_y = (hi - lo) / (dmax - dmin + 1e-12)
+    min_y = lo - dmin * scale_y
+    pm = ((np.asarray(pred_mean) - min_y) / (scale_y + 1e-12)).reshape(-1)
+    ale = (np.asarray(a_u) / (scale_y + 1e-12)).reshape(-1)
+    epi = (np.asarray(e_u) / (scale_y + 1e-12)).reshape(-1)
+    out[:, 8], out[:, 9] = yr, pm
+    out[:, 10] = smooth_by_segments(ale, boundaries, window)
+    out[:, 11] = smooth_by_segments(epi, boundaries, window)
+    out[:, 12] = yr - pm
+    for c, v in ((13, fV), (14, fT), (15, fH), (16, fO), (17, labels), (18, V5), (19, T_pred), (20, actH), (21, actO)):
+        out[:, c] = np.asarray(v).reshape(-1)
+    return out
+
+
+RF_COLS = (12, 13, 14, 15, 16)      # res, pV, pT, pH, pO   (04:58-62, 80)
+
+
+def rf_mu_sigma(results, normal_labels=(0,)):
+    """``estimate_mu_sigma_normal`` (04:181-197)."""
+    lab = results[:, 17].astype(int)
+    R = results[np.isin(lab, normal_labels)][:, RF_COLS].astype(float)
+    mu, sigma = np.nanmean(R, axis=0), np.nanstd(R, axis=0, ddof=1)
+    sigma[sigma == 0] = 1e-6
+    return mu, sigma
+
+
+def rf_series(results, mu, sigma, z_safe=2.0, lam=0.9971, k=0.0005, C0=500.0, C_max=1000.0, alpha=0.2):
+    """``compute_rf_time_series`` (04:201-285) with the script's constants (04:84-101): layers
+    {res,pV}, {pH,pO}, {pT}, 2-norm per layer, unit weights."""
+    R = results[:, RF_COLS].astype(float)
+    a = np.maximum(0.0, np.abs((R - mu) / sigma) - z_safe)
+    S = np.sqrt(a[:, 0] ** 2 + a[:, 1] ** 2) + np.sqrt(a[:, 3] ** 2 + a[:, 4] ** 2) + np.sqrt(a[:, 2] ** 2)
+    n = R.shape[0]
+    C = np.zeros(n)
+    for t in range(1, n):
+        C[t] = lam * C[t - 1] + S[t]
+    L0 = 1.0 / (1.0 + np.exp(-k * (0.0 - C0)))
+    Lm = 1.0 / (1.0 + np.exp(-k * (C_max - C0)))
+    rf = np.clip((1.0 / (1.0 + np.exp(-k * (np.clip(C, 0.0, C_max) - C0))) - L0) / (Lm - L0), 0.0, 1.0)
+    sm = np.zeros(n)
+    sm[0] = rf[0]
+    for t in range(1, n):
+        sm[t] = alpha * rf[t] + (1 - alpha) * sm[t - 1]
+    return rf, sm, S, C
+
+
+def first_alarm(series, threshold):
+    """``find_first_alarm_index`` (04:289-300), mode 'above'; -1 when never reached."""
+    idx = np.where(np.asarray(series) >= threshold)[0]
+    return int(idx[0]) if len(idx) else -1

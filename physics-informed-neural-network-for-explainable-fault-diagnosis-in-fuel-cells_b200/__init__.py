@@ -7,6 +7,8 @@ Public names mirror ``01_train_pinn_multiphysics_model.py``: ``DNN`` (01:389),
 from .nn import DNN, inject_masks  # noqa: F401
 from .pinn import PhysicsInformedNN, LAMBDA_NAMES  # noqa: F401
 from .mc import get_MC_samples, mc_dropout_device  # noqa: F401
+from .export import create_comprehensive_results_array_v2, create_fault_labels, export_rows_device  # noqa: F401
+from . import rf  # noqa: F401
 from .dropin import install  # noqa: F401
 
 __all__ = ["DNN", "PhysicsInformedNN", "get_MC_samples", "mc_dropout_device", "inject_masks", "install",

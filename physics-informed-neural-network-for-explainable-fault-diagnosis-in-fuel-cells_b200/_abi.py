@@ -54,6 +54,17 @@ class PinnScalers(C.Structure):
                 ("p_h2o", C.c_float), ("reserved", C.c_float)]
 
 
+class PinnExportScalers(C.Structure):
+    _fields_ = [("x_min", C.c_double * N_IN), ("x_scale", C.c_double * N_IN), ("y_min", C.c_double),
+                ("y_scale", C.c_double), ("min_y", C.c_double), ("scale_y", C.c_double)]
+
+
+class PinnRfParams(C.Structure):
+    _fields_ = [("z_safe", C.c_double), ("lambda_decay", C.c_double), ("k_logistic", C.c_double),
+                ("c0_logistic", C.c_double), ("c_max", C.c_double), ("alpha_smooth", C.c_double),
+                ("warn_threshold", C.c_double)]
+
+
 _vp, _i64, _i32, _u32, _sz, _dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_size_t, C.c_double
 _SIGNATURES = {
     "pinn_abi_version": (C.c_int, []),
@@ -72,6 +83,11 @@ _SIGNATURES = {
                                  _vp, _vp, _vp, _sz, _vp]),
     "pinn_mc_dropout": (C.c_int, [C.POINTER(PinnNet), _vp, _i64, _i32, C.POINTER(PinnDropout),
                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pinn_export_rows": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, C.POINTER(PinnExportScalers),
+                                   _i64, _vp, _vp]),
+    "pinn_rf_workspace_bytes": (_sz, [_i64, _i32]),
+    "pinn_rf_stats": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _sz, _vp]),
+    "pinn_rf_series": (C.c_int, [_vp, _i64, _i32, _vp, C.POINTER(PinnRfParams), _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pinn_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _dbl, _dbl, _i64, _dbl, _vp, _vp, _vp,
                                  _i32, _vp]),
     "pinn_adam_step_from_sums": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _dbl, _dbl, _i64, _vp, _vp,

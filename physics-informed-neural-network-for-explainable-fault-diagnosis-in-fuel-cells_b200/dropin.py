@@ -10,7 +10,8 @@ its own ``__main__`` body / helper functions drive the sm_100a kernels unchanged
 
 * level "A": ``ref.DNN`` -> ours (reference loops + autograd, kernels K1/K2);
 * level "B": also ``ref.get_MC_samples`` -> ours (kernel K4);
-* level "C": also ``ref.PhysicsInformedNN`` -> ours (device-resident scalers, K3, fused trainers).
+* level "C": also ``ref.PhysicsInformedNN`` -> ours (device-resident scalers, K3, fused trainers)
+  and ``ref.create_comprehensive_results_array_v2`` -> the device row writer (K5).
 """
 from __future__ import annotations
 
@@ -27,5 +28,9 @@ def install(ref_module, level: str = "C"):
     if level in ("B", "C"):
         ref_module.get_MC_samples = get_MC_samples
     if level == "C":
+        from .export import create_comprehensive_results_array_v2, create_fault_labels
+
         ref_module.PhysicsInformedNN = PhysicsInformedNN
+        ref_module.create_comprehensive_results_array_v2 = create_comprehensive_results_array_v2
+        ref_module.create_fault_labels = create_fault_labels
     return ref_module

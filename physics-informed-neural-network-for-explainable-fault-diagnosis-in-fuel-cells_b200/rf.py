@@ -1,0 +1,94 @@
+"""RF(t) risk function -- drop-in for ``estimate_mu_sigma_normal``, ``compute_rf_time_series``
+and ``find_first_alarm_index`` of ``04_risk_function_early_warning_index.py`` (04:181-300).
+
+Inputs are ``comprehensive_results`` matrices ``[N, 22]`` (one stack) or ``[S, N, 22]`` (a
+fleet of independent stacks, BASELINE config 5); the two first-order recurrences are scans on
+the device in float64 like the reference.  Constants default to the script's (04:84-101,163).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _abi, kernels as K
+from ._abi import PinnRfParams, check, ptr
+
+RF_Z_SAFE, RF_LAMBDA_DECAY = 2.0, 0.9971                     # 04:97-98
+RF_K_LOGISTIC, RF_C0_LOGISTIC, RF_C_MAX = 0.0005, 500.0, 1000.0   # 04:99-101
+RF_ALPHA_SMOOTH, RF_WARN_THRESHOLD = 0.2, 0.3                # 04:112,163
+
+
+def _as_device(results, device=None):
+    t = results if torch.is_tensor(results) else torch.as_tensor(np.ascontiguousarray(results, np.float64))
+    if not t.is_cuda:
+        if not torch.cuda.is_available():
+            raise RuntimeError("b200pinn.rf: needs a CUDA device; there is no CPU path")
+        t = t.to(device or torch.device("cuda", torch.cuda.current_device()))
+    t = t.to(torch.float64).contiguous()
+    return (t.unsqueeze(0), True) if t.dim() == 2 else (t, False)
+
+
+def rf_device(results: torch.Tensor, z_safe=RF_Z_SAFE, lambda_decay=RF_LAMBDA_DECAY, k_logistic=RF_K_LOGISTIC,
+              C0_logistic=RF_C0_LOGISTIC, C_max=RF_C_MAX, alpha_smooth=RF_ALPHA_SMOOTH,
+              warn_threshold=RF_WARN_THRESHOLD, mu_sigma=None, want_extra=False):
+    """``results``: CUDA float64 ``[S, N, 22]``.  Returns dict of CUDA tensors: ``mu_sigma [S,10]``,
+    ``rf_inst, rf_smooth [S,N]``, ``first_alarm [S]`` (-1 = never), optionally ``C, S_tot``."""
+    S_, n = results.shape[0], results.shape[1]
+    dev = results.device
+    L = _abi.lib()
+    nb = L.pinn_rf_workspace_bytes(n, S_)
+    ws = K._workspace("rf", nb, dev)
+    prm = PinnRfParams(z_safe, lambda_decay, k_logistic, C0_logistic, C_max, alpha_smooth, warn_threshold)
+    out = {}
+    with torch.cuda.device(dev):
+        if mu_sigma is None:
+            mu_sigma = torch.empty(S_, 10, device=dev, dtype=torch.float64)
+            check(L.pinn_rf_stats(ptr(results), n, S_, ptr(mu_sigma), ptr(ws), nb, K._stream()), "pinn_rf_stats")
+            K.LAUNCHES += 4
+        out["mu_sigma"] = mu_sigma
+        out["rf_inst"] = torch.empty(S_, n, device=dev, dtype=torch.float64)
+        out["rf_smooth"] = torch.empty(S_, n, device=dev, dtype=torch.float64)
+        out["first_alarm"] = torch.empty(S_, device=dev, dtype=torch.int64)
+        if want_extra:
+            out["C"] = torch.empty(S_, n, device=dev, dtype=torch.float64)
+            out["S_tot"] = torch.empty(S_, n, device=dev, dtype=torch.float64)
+        check(L.pinn_rf_series(ptr(results), n, S_, ptr(mu_sigma), C.byref(prm), ptr(out["rf_inst"]), ptr(out["rf_smooth"]),
+                               ptr(out.get("C")), ptr(out.get("S_tot")), ptr(out["first_alarm"]), ptr(ws), nb, K._stream()),
+              "pinn_rf_series")
+        K.LAUNCHES += 5
+    return out
+
+
+def estimate_mu_sigma_normal(results):
+    """04:181-197 -> ``(mu[5], sigma[5])`` numpy (order res, pV, pT, pH, pO)."""
+    r, _ = _as_device(results)
+    dev = r.device
+    L = _abi.lib()
+    nb = L.pinn_rf_workspace_bytes(r.shape[1], r.shape[0])
+    ws = K._workspace("rf", nb, dev)
+    ms = torch.empty(r.shape[0], 10, device=dev, dtype=torch.float64)
+    with torch.cuda.device(dev):
+        check(L.pinn_rf_stats(ptr(r), r.shape[1], r.shape[0], ptr(ms), ptr(ws), nb, K._stream()), "pinn_rf_stats")
+    m = ms[0].cpu().numpy()
+    return m[:5].copy(), m[5:].copy()
+
+
+def compute_rf_time_series(results, mu, sigma, z_safe=RF_Z_SAFE, lambda_decay=RF_LAMBDA_DECAY,
+                           k_logistic=RF_K_LOGISTIC, C0_logistic=RF_C0_LOGISTIC, C_max=RF_C_MAX,
+                           alpha_smooth=RF_ALPHA_SMOOTH):
+    """04:201-285 -> ``(RF_inst, RF_smooth, extra)`` numpy, ``extra`` holding ``S_tot`` and ``C``."""
+    r, _ = _as_device(results)
+    ms = torch.tensor(np.concatenate([np.asarray(mu, np.float64), np.asarray(sigma, np.float64)])[None, :],
+                      device=r.device)
+    o = rf_device(r, z_safe, lambda_decay, k_logistic, C0_logistic, C_max, alpha_smooth, mu_sigma=ms, want_extra=True)
+    return (o["rf_inst"][0].cpu().numpy(), o["rf_smooth"][0].cpu().numpy(),
+            {"S_tot": o["S_tot"][0].cpu().numpy(), "C": o["C"][0].cpu().numpy()})
+
+
+def find_first_alarm_index(series, threshold, mode="above"):
+    """04:289-300 (host helper for already-downloaded series)."""
+    s = np.asarray(series)
+    idx = np.where(s >= threshold)[0] if mode == "above" else np.where(s <= threshold)[0]
+    return None if len(idx) == 0 else int(idx[0])
