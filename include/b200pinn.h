@@ -218,6 +218,8 @@ int pinn_adam_step_from_sums(float* params, const double* sums,
  * 64x64 contractions on tcgen05 tensor cores (3xTF32, fp32-accurate); 0 routes them through
  * the fp32 FFMA kernels that serve the other widths.  Returns the previous setting. */
 int pinn_set_tensor_core_path(int enable);
+/* Same switch for the backward kernels (pinn_mlp_bwd). */
+int pinn_set_tensor_core_bwd(int enable);
 
 int pinn_abi_version(void);
 const char* pinn_error_string(int code);

@@ -69,6 +69,7 @@ _vp, _i64, _i32, _u32, _sz, _dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32,
 _SIGNATURES = {
     "pinn_abi_version": (C.c_int, []),
     "pinn_set_tensor_core_path": (C.c_int, [C.c_int]),
+    "pinn_set_tensor_core_bwd": (C.c_int, [C.c_int]),
     "pinn_device_sm_count": (C.c_int, []),
     "pinn_error_string": (C.c_char_p, [C.c_int]),
     "pinn_param_count": (_i64, [_i32, _i32]),

@@ -14,6 +14,7 @@
 // float atomics.  dL/dx of layer 0 -- computed and thrown away by the reference every
 // step because self.x has requires_grad (01:446) -- is never formed.
 #include "net.cuh"
+#include "tc_api.cuh"
 
 namespace pinn {
 
@@ -366,7 +367,12 @@ extern "C" int64_t pinn_param_count(int32_t width, int32_t n_hidden) {
 }
 
 extern "C" size_t pinn_mlp_bwd_workspace_bytes(int32_t width, int32_t n_hidden, int64_t n) {
-  return plan_bwd(width, n_hidden, n).bytes;
+  size_t a = plan_bwd(width, n_hidden, n).bytes;
+  if (width == 64 && n_hidden >= 2 && n_hidden <= 4) {
+    size_t b = tc_bwd_workspace_bytes(n_hidden, n);
+    if (b > a) a = b;
+  }
+  return a;
 }
 
 extern "C" int pinn_mlp_bwd(const pinn_net_t* net, const float* x, int64_t n, const pinn_dropout_t* drop,
@@ -380,6 +386,9 @@ extern "C" int pinn_mlp_bwd(const pinn_net_t* net, const float* x, int64_t n, co
   if (!grad_u && n_global <= 0) return PINN_E_ARG;
   if (!aligned16(x) || !aligned16(workspace)) return PINN_E_ALIGN;
   const int H = net->width, L = net->n_hidden;
+  if (n > 0 && tc_bwd_covers(net))
+    return launch_tc_bwd(net, x, n, make_drop_params(drop), grad_u, grad_logvar, y, n_global, grad_flat, loss_sums, workspace,
+                         workspace_bytes, static_cast<cudaStream_t>(stream));
   BwdPlan p = plan_bwd(H, L, n);
   if (workspace_bytes < p.bytes) return PINN_E_WORKSPACE;
   if (p.large) {

@@ -1,0 +1,672 @@
+// mlp_tc_bwd.cu -- K2 for the 64-wide net on the tensor cores, as two kernels:
+//
+//  K2a  mlp_tc_bwd_kernel : per 128-sample tile (two independent 256-thread groups per CTA,
+//       as in mlp_tc.cu) forward recompute AND dgrad on tcgen05 (3xTF32, fp32-accurate):
+//         stage a0 -> [W1] -> a1 -> [W2] -> a2 -> [Wv0;Wp] -> heads + loss gradients
+//         -> [ (Wv0;Wp)^T ] -> d a2 -> [W2^T] -> d a1 -> [W1^T] -> d a0
+//       Every contraction is a K-major x K-major MMA: the B operand (one layer's weights, or
+//       their transpose for dgrad) is re-split into the group's 32 KB B planes right before
+//       use -- 16 values per thread -- instead of keeping 2 x 88 KB of planes resident, so
+//       two groups fit in 192 KB and overlap each other's MMAs and epilogues.  Masked
+//       activations and pre-activation deltas of every layer go to HBM ([N][width] fp32 rows,
+//       128 B per thread per layer); keep-bits ride in registers so Philox runs once.
+//  K2b  wgrad_kernel : dW_l = delta_l^T a_{l-1} for all seven weight tensors and the bias
+//       column sums, contraction over the batch, register-tiled FFMA over shared-memory
+//       staged [32 samples][width] tiles; per-CTA partials -> grad_reduce_kernel (fixed-order,
+//       deterministic).
+//
+// (MN-major TF32 operands, which would allow an all-on-chip variant, require CUTLASS's
+// SW128_32B swizzled layout; with the plain interleaved layout the MMA is silently dropped --
+// tests/cuda/tc_mn_test.cu documents that.)
+#include "net.cuh"
+#include "tc.cuh"
+#include "tc_api.cuh"
+
+namespace pinn {
+
+constexpr int kBH = 64, kBTile = 128;
+
+// Global scratch: per-sample rows written by K2a, read by K2b (float offsets per sample).
+struct BwdScratch {
+  float* act[PINN_MAX_HIDDEN];   // masked activations a_l            [n][64]
+  float* del[PINN_MAX_HIDDEN];   // pre-activation deltas dz_l        [n][64]
+  float* av0; float* dv0;        // variance head layer 0             [n][32]
+  float* av1; float* dv1;        // variance head layer 1             [n][16]
+  float* du;  float* dvs;        // d loss / d u, d loss / d v        [n]
+};
+PINN_HD size_t bwd_scratch_floats_per_sample(int L) { return static_cast<size_t>(L) * 2 * kBH + 2 * 32 + 2 * 16 + 2; }
+
+inline BwdScratch carve_scratch(float* base, int64_t n, int L) {
+  BwdScratch s{};
+  float* p = base;
+  const size_t N = static_cast<size_t>(n);
+  for (int l = 0; l < L; ++l) { s.act[l] = p; p += N * kBH; }
+  for (int l = 0; l < L; ++l) { s.del[l] = p; p += N * kBH; }
+  s.av0 = p; p += N * 32; s.dv0 = p; p += N * 32;
+  s.av1 = p; p += N * 16; s.dv1 = p; p += N * 16;
+  s.du = p; p += N; s.dvs = p; p += N;
+  return s;
+}
+
+// ------------------------------------------------------------------------------- K2b
+// One CTA accumulates every gradient over its samples; thread (jt, kt) of a 16 x 16 grid owns
+// the 4 x 4 block (j0 = 4 jt, k0 = 4 kt) of each 64 x 64 product and sub-blocks of the rest.
+constexpr int kWgS = 32;   // samples per shared-memory stage
+
+struct WgradArgs {
+  const float* x; int64_t n; int L;
+  BwdScratch sc;
+  float* partial;          // [grid][lay.total]
+};
+
+template <int L>
+__global__ void __launch_bounds__(256, 2)
+wgrad_kernel(WgradArgs a, ParamLayout lay) {
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x, jt = tid >> 4, kt = tid & 15;
+  // shared stage: D_l, A_{l-1} for every trunk layer (+ x), heads
+  float* sD = sm;                                   // [L][kWgS][64]
+  float* sA = sD + L * kWgS * 64;                   // [L][kWgS][64]   (a_0 .. a_{L-1})
+  float* sX = sA + L * kWgS * 64;                   // [kWgS][8]
+  float* sDV0 = sX + kWgS * 8;                      // [kWgS][32]
+  float* sAV0 = sDV0 + kWgS * 32;                   // [kWgS][32]
+  float* sDV1 = sAV0 + kWgS * 32;                   // [kWgS][16]
+  float* sAV1 = sDV1 + kWgS * 16;                   // [kWgS][16]
+  float* sDU = sAV1 + kWgS * 16;                    // [kWgS]
+  float* sDVS = sDU + kWgS;                         // [kWgS]
+
+  float accW[L - 1][16];                            // dW_l, l >= 1: 4x4 block
+  float accV0[8];                                   // dWv0 [32][64]: rows 2jt..2jt+1, cols 4kt..4kt+3
+  float accW0[2];                                   // dW0 [64][8]: flat index 2 tid, 2 tid + 1
+  float accV1[2];                                   // dWv1 [16][32]: flat index 2 tid, 2 tid + 1
+  float accS = 0.f;                                 // trunk bias sums: thread t < 64 L owns db_{t/64}[t%64]   (L <= 4)
+  float accS2 = 0.f;                                // head bias sums: t < 32 dbv0, 32..47 dbv1, 48 dbp, 49 dbv2
+  float accP = 0.f;                                 // dWp[tid] (tid < 64), dWv2[tid-64] (64 <= tid < 80)
+#pragma unroll
+  for (int l = 0; l < L - 1; ++l)
+#pragma unroll
+    for (int q = 0; q < 16; ++q) accW[l][q] = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) accV0[q] = 0.f;
+  accW0[0] = accW0[1] = accV1[0] = accV1[1] = 0.f;
+
+  const int64_t per = (a.n + gridDim.x - 1) / gridDim.x;
+  const int64_t s_begin = static_cast<int64_t>(blockIdx.x) * per;
+  const int64_t s_end = s_begin + per < a.n ? s_begin + per : a.n;
+  for (int64_t s0 = s_begin; s0 < s_end; s0 += kWgS) {
+    const int cnt = static_cast<int>(s_end - s0 < kWgS ? s_end - s0 : kWgS);
+    __syncthreads();
+    // ---- stage (zero-fill the tail so no branch is needed in the FMA loops)
+    for (int l = 0; l < L; ++l)
+      for (int i = tid; i < kWgS * 16; i += 256) {
+        const int r = i >> 4, c4 = i & 15;
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f), v = d;
+        if (r < cnt) {
+          d = __ldg(reinterpret_cast<const float4*>(a.sc.del[l] + (s0 + r) * 64) + c4);
+          v = __ldg(reinterpret_cast<const float4*>(a.sc.act[l] + (s0 + r) * 64) + c4);
+        }
+        reinterpret_cast<float4*>(sD + (l * kWgS + r) * 64)[c4] = d;
+        reinterpret_cast<float4*>(sA + (l * kWgS + r) * 64)[c4] = v;
+      }
+    for (int i = tid; i < kWgS * 8; i += 256) {
+      const int r = i >> 3, c4 = i & 7;
+      float4 d = make_float4(0.f, 0.f, 0.f, 0.f), v = d;
+      if (r < cnt) {
+        d = __ldg(reinterpret_cast<const float4*>(a.sc.dv0 + (s0 + r) * 32) + c4);
+        v = __ldg(reinterpret_cast<const float4*>(a.sc.av0 + (s0 + r) * 32) + c4);
+      }
+      reinterpret_cast<float4*>(sDV0 + r * 32)[c4] = d;
+      reinterpret_cast<float4*>(sAV0 + r * 32)[c4] = v;
+    }
+    for (int i = tid; i < kWgS * 4; i += 256) {
+      const int r = i >> 2, c4 = i & 3;
+      float4 d = make_float4(0.f, 0.f, 0.f, 0.f), v = d;
+      if (r < cnt) {
+        d = __ldg(reinterpret_cast<const float4*>(a.sc.dv1 + (s0 + r) * 16) + c4);
+        v = __ldg(reinterpret_cast<const float4*>(a.sc.av1 + (s0 + r) * 16) + c4);
+      }
+      reinterpret_cast<float4*>(sDV1 + r * 16)[c4] = d;
+      reinterpret_cast<float4*>(sAV1 + r * 16)[c4] = v;
+    }
+    if (tid < kWgS * 2) {
+      const int r = tid >> 1, c4 = tid & 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < cnt) v = __ldg(reinterpret_cast<const float4*>(a.x + (s0 + r) * 8) + c4);
+      reinterpret_cast<float4*>(sX + r * 8)[c4] = v;
+    }
+    if (tid < kWgS) { sDU[tid] = tid < cnt ? __ldg(a.sc.du + s0 + tid) : 0.f; sDVS[tid] = tid < cnt ? __ldg(a.sc.dvs + s0 + tid) : 0.f; }
+    __syncthreads();
+    // ---- accumulate
+#pragma unroll 4
+    for (int r = 0; r < kWgS; ++r) {
+#pragma unroll
+      for (int l = 1; l < L; ++l) {
+        const float4 d = *reinterpret_cast<const float4*>(sD + (l * kWgS + r) * 64 + 4 * jt);
+        const float4 v = *reinterpret_cast<const float4*>(sA + ((l - 1) * kWgS + r) * 64 + 4 * kt);
+        const float dd[4] = {d.x, d.y, d.z, d.w}, vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) accW[l - 1][4 * p + q] = fmaf(dd[p], vv[q], accW[l - 1][4 * p + q]);
+      }
+      {   // dWv0[i][c] += dz_v0[i] * a_{L-1}[c]
+        const float2 d = *reinterpret_cast<const float2*>(sDV0 + r * 32 + 2 * jt);
+        const float4 v = *reinterpret_cast<const float4*>(sA + ((L - 1) * kWgS + r) * 64 + 4 * kt);
+        accV0[0] = fmaf(d.x, v.x, accV0[0]); accV0[1] = fmaf(d.x, v.y, accV0[1]);
+        accV0[2] = fmaf(d.x, v.z, accV0[2]); accV0[3] = fmaf(d.x, v.w, accV0[3]);
+        accV0[4] = fmaf(d.y, v.x, accV0[4]); accV0[5] = fmaf(d.y, v.y, accV0[5]);
+        accV0[6] = fmaf(d.y, v.z, accV0[6]); accV0[7] = fmaf(d.y, v.w, accV0[7]);
+      }
+      {   // dW0[j][i] (64 x 8) and dWv1[k][i] (16 x 32): two consecutive flat entries per thread
+        const int e0 = 2 * tid;
+        const float d0 = sD[r * 64 + (e0 >> 3)];
+        accW0[0] = fmaf(d0, sX[r * 8 + (e0 & 7)], accW0[0]);
+        accW0[1] = fmaf(d0, sX[r * 8 + (e0 & 7) + 1], accW0[1]);
+        const float d1 = sDV1[r * 16 + (e0 >> 5)];
+        accV1[0] = fmaf(d1, sAV0[r * 32 + (e0 & 31)], accV1[0]);
+        accV1[1] = fmaf(d1, sAV0[r * 32 + (e0 & 31) + 1], accV1[1]);
+      }
+      if (tid < 64) accP = fmaf(sDU[r], sA[((L - 1) * kWgS + r) * 64 + tid], accP);          // dWp
+      else if (tid < 80) accP = fmaf(sDVS[r], sAV1[r * 16 + tid - 64], accP);                // dWv2
+      if (tid < 64 * L) accS += sD[((tid >> 6) * kWgS + r) * 64 + (tid & 63)];
+      if (tid < 32) accS2 += sDV0[r * 32 + tid];
+      else if (tid < 48) accS2 += sDV1[r * 16 + tid - 32];
+      else if (tid == 48) accS2 += sDU[r];
+      else if (tid == 49) accS2 += sDVS[r];
+    }
+  }
+  // ---------------------------------------------------------------- write this CTA's partial
+  float* part = a.partial + static_cast<size_t>(blockIdx.x) * lay.total;
+#pragma unroll
+  for (int l = 1; l < L; ++l)
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) part[lay.offW[l] + (4 * jt + p) * 64 + 4 * kt + q] = accW[l - 1][4 * p + q];
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) part[lay.offWv0 + (2 * jt + p) * 64 + 4 * kt + q] = accV0[4 * p + q];
+  part[lay.offW[0] + 2 * tid] = accW0[0];
+  part[lay.offW[0] + 2 * tid + 1] = accW0[1];
+  part[lay.offWv1 + 2 * tid] = accV1[0];
+  part[lay.offWv1 + 2 * tid + 1] = accV1[1];
+  if (tid < 64) part[lay.offWp + tid] = accP;
+  else if (tid < 80) part[lay.offWv2 + tid - 64] = accP;
+  if (tid < 64 * L) part[lay.offb[tid >> 6] + (tid & 63)] = accS;
+  if (tid < 32) part[lay.offbv0 + tid] = accS2;
+  else if (tid < 48) part[lay.offbv1 + tid - 32] = accS2;
+  else if (tid == 48) part[lay.offbp] = accS2;
+  else if (tid == 49) part[lay.offbv2] = accS2;
+}
+
+// ------------------------------------------------------------------------------- K2a
+struct TcbLayout {   // float offsets into dynamic shared memory
+  int pn_hi[2], pn_lo[2];      // per group: activation / delta planes, 128 rows x 64 cols
+  int b_hi[2], b_lo[2];        // per group: one layer's weight planes (K-major; padded LBO for transposes)
+  int W0, b0, b[PINN_MAX_HIDDEN], bv0, bp, Wv1, bv1, Wv2, bv2;
+  int total;
+};
+constexpr int kBPlaneFloats = 16 * 1040 / 4;    // 16 chunks x 1040 B (padded LBO, see stage_B_transposed)
+PINN_HD TcbLayout make_tcb_layout(int L) {
+  TcbLayout t;
+  int o = 0;
+  for (int g = 0; g < 2; ++g) { t.pn_hi[g] = o; o += kBTile * kBH; t.pn_lo[g] = o; o += kBTile * kBH; }
+  for (int g = 0; g < 2; ++g) { t.b_hi[g] = o; o += kBPlaneFloats; t.b_lo[g] = o; o += kBPlaneFloats; }
+  t.W0 = o; o += kBH * PINN_N_IN;
+  t.b0 = o; o += kBH;
+  for (int l = 0; l < PINN_MAX_HIDDEN; ++l) t.b[l] = 0;
+  for (int l = 1; l < L; ++l) { t.b[l] = o; o += kBH; }
+  t.bv0 = o; o += 32; t.bp = o; o += 4;
+  t.Wv1 = o; o += 16 * 32; t.bv1 = o; o += 16; t.Wv2 = o; o += 16; t.bv2 = o; o += 4;
+  t.total = o;
+  return t;
+}
+
+PINN_D void grp_sync256(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); }
+
+// B planes <- rows of a row-major [nrows][64] matrix (K-major B: row n, contraction index k).
+PINN_D void stage_B_rows(float* hi, float* lo, const float* __restrict__ src, int nrows, int t256) {
+  const uint32_t lbo = static_cast<uint32_t>(nrows) * 16;
+  for (int idx = t256; idx < nrows * 16; idx += 256) {
+    const int nrow = idx % nrows, kc = idx / nrows;
+    tc::store_split4(hi, lo, lbo, nrow, kc, __ldg(reinterpret_cast<const float4*>(src + nrow * 64) + kc));
+  }
+}
+// B planes <- TRANSPOSE of a row-major [J][64] matrix: B[n = k][col j] = src[j][k], columns j >= J
+// zero (dgrad: d a_{l-1} = d z_l * W_l).  Scalar stores; LBO is padded to 1040 B so that the eight
+// 4-column chunks a warp touches fall into different banks.
+constexpr uint32_t kLboT = 1040;
+PINN_D void stage_B_transposed(float* hi, float* lo, const float* __restrict__ src, const float* __restrict__ extra_row, int J,
+                               int t256) {
+  for (int idx = t256; idx < 64 * 16; idx += 256) {
+    const int j = idx & 63, kc = idx >> 6;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < J) v = __ldg(reinterpret_cast<const float4*>(src + j * 64) + kc);
+    else if (j == J && extra_row != nullptr) v = __ldg(reinterpret_cast<const float4*>(extra_row) + kc);
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float h = tc::tf32_hi(vv[r]);
+      const size_t off = (static_cast<size_t>(j >> 2) * kLboT + static_cast<size_t>(4 * kc + r) * 16 + (j & 3) * 4) / 4;
+      hi[off] = h;
+      lo[off] = vv[r] - h;
+    }
+  }
+}
+
+struct TcbArgs {
+  const float* x; int64_t n;
+  const float* grad_u; const float* grad_s; const float* y; float inv_n_global;
+  BwdScratch sc;
+  double* loss_partial;     // [2 * grid][4]
+};
+
+template <int L>
+__global__ void __launch_bounds__(512, 1)
+mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
+  constexpr int H = kBH, HH = 32;
+  constexpr uint32_t LBO_A = kBTile * 16;
+  extern __shared__ __align__(1024) float smem[];
+  __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ double lred[2][4][4];
+  const int tid = threadIdx.x, row = tid & 127, t256 = tid & 255;
+  const int warp = tc::uniform_warp_idx(), grp = warp >> 3, half = (warp >> 2) & 1;
+  const int Dm = L * H + H / 2;
+  const int cb = half * HH;
+
+  if (tid == 0) { tc::mbar_init(&mbar[0], 1); tc::mbar_init(&mbar[1], 1); tc::fence_mbar_init(); }
+  __syncwarp();
+  if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 128); tc::tmem_relinquish(); }
+  stage_tensor(smem + lay.W0, net.W[0], H * PINN_N_IN);
+  stage_tensor(smem + lay.b0, net.b[0], H);
+  for (int l = 1; l < L; ++l) stage_tensor(smem + lay.b[l], net.b[l], H);
+  stage_tensor(smem + lay.bv0, net.bv0, 32);
+  stage_tensor(smem + lay.bp, net.bp, 1);
+  stage_tensor(smem + lay.Wv1, net.Wv1, 16 * 32);
+  stage_tensor(smem + lay.bv1, net.bv1, 16);
+  stage_tensor(smem + lay.Wv2, net.Wv2, 16);
+  stage_tensor(smem + lay.bv2, net.bv2, 1);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+
+  const uint32_t d_tmem = tmem_base_s + static_cast<uint32_t>(grp * 64);
+  const uint32_t d_lane = d_tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  float* pn_hi = smem + lay.pn_hi[grp];
+  float* pn_lo = smem + lay.pn_lo[grp];
+  float* b_hi = smem + lay.b_hi[grp];
+  float* b_lo = smem + lay.b_lo[grp];
+  const uint64_t a_hi_d = tc::make_desc(tc::smem_u32(pn_hi), LBO_A, 128), a_lo_d = tc::make_desc(tc::smem_u32(pn_lo), LBO_A, 128);
+  const uint32_t bh_u = tc::smem_u32(b_hi), bl_u = tc::smem_u32(b_lo);
+  const uint32_t idesc64 = tc::make_idesc_tf32(kBTile, 64), idesc48 = tc::make_idesc_tf32(kBTile, 48);
+  const bool issuer_warp = (warp & 7) == 0;
+  uint32_t phase = 0;
+  double l_nll = 0.0, l_abs = 0.0, l_mse = 0.0, l_cnt = 0.0;
+
+  // publish PN + B (generic-proxy writes) to the async proxy, run one 3xTF32 product, wait for it
+  auto run_mma = [&](uint32_t lbo_b, uint32_t idesc) {
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    grp_sync256(grp);
+    if (issuer_warp) {
+      const uint64_t bhd = tc::make_desc(bh_u, lbo_b, 128), bld = tc::make_desc(bl_u, lbo_b, 128);
+      if (tc::elect_one()) {
+        tc::fence_after_sync();
+        tc::issue_3xtf32<64>(d_tmem, a_hi_d, a_lo_d, LBO_A, bhd, bld, lbo_b, idesc);
+        tc::umma_commit(&mbar[grp]);
+      }
+      __syncwarp();
+    }
+    tc::mbar_wait(&mbar[grp], phase);
+    phase ^= 1u;
+    __syncwarp();
+    tc::fence_after_sync();
+  };
+  auto store_pn8 = [&](int c0, const float* v) {   // 8 consecutive columns of this thread's row
+    tc::store_split4(pn_hi, pn_lo, LBO_A, row, c0 / 4, make_float4(v[0], v[1], v[2], v[3]));
+    tc::store_split4(pn_hi, pn_lo, LBO_A, row, c0 / 4 + 1, make_float4(v[4], v[5], v[6], v[7]));
+  };
+
+  const int64_t n_tiles = (a.n + kBTile - 1) / kBTile;
+  for (int64_t tile = static_cast<int64_t>(blockIdx.x) * 2 + grp; tile < n_tiles; tile += static_cast<int64_t>(gridDim.x) * 2) {
+    const int64_t s = tile * kBTile + row;
+    const bool valid = s < a.n;
+    const DropCtx dc = make_ctx(dp, s, 0, Dm, true, valid);
+    uint32_t kb[L + 1];      // keep bits of this thread's 32 columns, per dropout layer (bit q = column cb + q)
+    // ============================ forward ============================
+    {
+      float xr[PINN_N_IN];
+      if (valid) {
+        const float4* px = reinterpret_cast<const float4*>(a.x + s * PINN_N_IN);
+        float4 q0 = __ldg(px), q1 = __ldg(px + 1);
+        xr[0] = q0.x; xr[1] = q0.y; xr[2] = q0.z; xr[3] = q0.w; xr[4] = q1.x; xr[5] = q1.y; xr[6] = q1.z; xr[7] = q1.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < PINN_N_IN; ++i) xr[i] = 0.f;
+      }
+      const float* W0 = smem + lay.W0 + cb * PINN_N_IN;
+      const float* b0 = smem + lay.b0 + cb;
+      kb[0] = 0u;
+#pragma unroll
+      for (int g = 0; g < HH; g += 8) {
+        float m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+        if (dc.active) drop8(dc, 0u, cb + g, 0u, m);
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 w0 = *reinterpret_cast<const float4*>(W0 + (g + q) * PINN_N_IN);
+          const float4 w1 = *reinterpret_cast<const float4*>(W0 + (g + q) * PINN_N_IN + 4);
+          float z = b0[g + q];
+          z = fmaf(w0.x, xr[0], z); z = fmaf(w0.y, xr[1], z); z = fmaf(w0.z, xr[2], z); z = fmaf(w0.w, xr[3], z);
+          z = fmaf(w1.x, xr[4], z); z = fmaf(w1.y, xr[5], z); z = fmaf(w1.z, xr[6], z); z = fmaf(w1.w, xr[7], z);
+          v[q] = tanh_act(z) * m[q];
+          kb[0] |= (m[q] != 0.f ? 1u : 0u) << (g + q);
+        }
+        store_pn8(cb + g, v);
+        if (valid) {
+          float4* o = reinterpret_cast<float4*>(a.sc.act[0] + s * H + cb + g);
+          o[0] = make_float4(v[0], v[1], v[2], v[3]); o[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      }
+    }
+#pragma unroll
+    for (int l = 1; l < L; ++l) {
+      stage_B_rows(b_hi, b_lo, net.W[l], H, t256);
+      run_mma(H * 16, idesc64);
+      const float* bl = smem + lay.b[l] + cb;
+      float z[HH];
+      tc::tmem_ld16(d_lane + cb, z);
+      tc::tmem_ld16(d_lane + cb + 16, z + 16);
+      tc::tmem_wait_ld();
+      kb[l] = 0u;
+#pragma unroll
+      for (int g = 0; g < HH; g += 8) {
+        float m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+        if (dc.active) drop8(dc, static_cast<uint32_t>(l), cb + g, static_cast<uint32_t>(l * H), m);
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          v[q] = tanh_act(z[g + q] + bl[g + q]) * m[q];
+          kb[l] |= (m[q] != 0.f ? 1u : 0u) << (g + q);
+        }
+        store_pn8(cb + g, v);
+        if (valid) {
+          float4* o = reinterpret_cast<float4*>(a.sc.act[l] + s * H + cb + g);
+          o[0] = make_float4(v[0], v[1], v[2], v[3]); o[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      }
+    }
+    // ---- heads: rows 0..31 = Wv0, row 32 = Wp, rows 33..47 = 0
+    for (int idx = t256; idx < 48 * 16; idx += 256) {
+      const int nrow = idx % 48, kc = idx / 48;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (nrow < 32) v = __ldg(reinterpret_cast<const float4*>(net.Wv0 + nrow * H) + kc);
+      else if (nrow == 32) v = __ldg(reinterpret_cast<const float4*>(net.Wp) + kc);
+      tc::store_split4(b_hi, b_lo, 48 * 16, nrow, kc, v);
+    }
+    run_mma(48 * 16, idesc48);
+    float du = 0.f;
+    float dzv0[HH];                      // half 0: d z of the variance head's first layer; half 1: unused
+    kb[L] = 0u;
+    if (half == 0) {
+      float v0[HH], zz[16];
+      tc::tmem_ld16(d_lane, v0);
+      tc::tmem_ld16(d_lane + 16, v0 + 16);
+      tc::tmem_ld16(d_lane + 32, zz);
+      tc::tmem_wait_ld();
+      const float u = zz[0] + smem[lay.bp];
+      const float* bv0 = smem + lay.bv0;
+#pragma unroll
+      for (int g = 0; g < HH; g += 8) {
+        float m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+        if (dc.active) drop8(dc, static_cast<uint32_t>(L), g, static_cast<uint32_t>(L * H), m);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          v0[g + q] = tanh_act(v0[g + q] + bv0[g + q]) * m[q];
+          kb[L] |= (m[q] != 0.f ? 1u : 0u) << (g + q);
+        }
+      }
+      const float* Wv1 = smem + lay.Wv1;
+      const float* bv1 = smem + lay.bv1;
+      const float* Wv2 = smem + lay.Wv2;
+      float v1[16];
+      float vraw = smem[lay.bv2];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        float2 acc = make_float2(0.f, 0.f), acc2 = acc;
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 w = *reinterpret_cast<const float4*>(Wv1 + k * 32 + 4 * i4);
+          acc = ffma2(make_float2(w.x, w.y), make_float2(v0[4 * i4], v0[4 * i4 + 1]), acc);
+          acc2 = ffma2(make_float2(w.z, w.w), make_float2(v0[4 * i4 + 2], v0[4 * i4 + 3]), acc2);
+        }
+        v1[k] = tanh_act(((acc.x + acc.y) + (acc2.x + acc2.y)) + bv1[k]);
+        vraw = fmaf(Wv2[k], v1[k], vraw);
+      }
+      const float lv = logvar_from_v(vraw);
+      float ds = 0.f;
+      if (valid) {
+        if (a.grad_u != nullptr) {
+          du = __ldg(a.grad_u + s);
+          ds = a.grad_s ? __ldg(a.grad_s + s) : 0.f;
+        } else {
+          const float yv = __ldg(a.y + s);
+          const float e = expf(-lv), diff = yv - u;
+          du = -e * diff * a.inv_n_global;
+          const float sg = lv > 0.f ? 1.f : (lv < 0.f ? -1.f : 0.f);
+          ds = (-0.5f * e * diff * diff + 0.5f + 0.01f * sg) * a.inv_n_global;
+          l_nll += static_cast<double>(0.5f * e * diff * diff + 0.5f * lv);
+          l_abs += static_cast<double>(fabsf(lv));
+          l_mse += static_cast<double>(diff * diff);
+          l_cnt += 1.0;
+        }
+      }
+      const float dv = ds * dlogvar_dv(vraw);
+      float dz1[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) dz1[k] = dv * Wv2[k] * (1.0f - v1[k] * v1[k]);
+      // d v0[i] = sum_k Wv1[k][i] dz1[k];  dz_v0 = d v0 * keep-mask * (1 - a^2)
+#pragma unroll
+      for (int i = 0; i < HH; ++i) dzv0[i] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 w = *reinterpret_cast<const float4*>(Wv1 + k * 32 + 4 * i4);
+          dzv0[4 * i4] = fmaf(w.x, dz1[k], dzv0[4 * i4]);         dzv0[4 * i4 + 1] = fmaf(w.y, dz1[k], dzv0[4 * i4 + 1]);
+          dzv0[4 * i4 + 2] = fmaf(w.z, dz1[k], dzv0[4 * i4 + 2]); dzv0[4 * i4 + 3] = fmaf(w.w, dz1[k], dzv0[4 * i4 + 3]);
+        }
+#pragma unroll
+      for (int i = 0; i < HH; ++i) {
+        const float av = v0[i] * (dc.active ? dc.keep : 1.0f);
+        const float mk = dc.active ? (((kb[L] >> i) & 1u) ? dc.scale : 0.f) : 1.0f;
+        dzv0[i] = dzv0[i] * mk * (1.0f - av * av);
+      }
+      if (valid) {
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          reinterpret_cast<float4*>(a.sc.av0 + s * 32)[i4] = make_float4(v0[4 * i4], v0[4 * i4 + 1], v0[4 * i4 + 2], v0[4 * i4 + 3]);
+          reinterpret_cast<float4*>(a.sc.dv0 + s * 32)[i4] = make_float4(dzv0[4 * i4], dzv0[4 * i4 + 1], dzv0[4 * i4 + 2], dzv0[4 * i4 + 3]);
+        }
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          reinterpret_cast<float4*>(a.sc.av1 + s * 16)[i4] = make_float4(v1[4 * i4], v1[4 * i4 + 1], v1[4 * i4 + 2], v1[4 * i4 + 3]);
+          reinterpret_cast<float4*>(a.sc.dv1 + s * 16)[i4] = make_float4(dz1[4 * i4], dz1[4 * i4 + 1], dz1[4 * i4 + 2], dz1[4 * i4 + 3]);
+        }
+        a.sc.du[s] = du;
+        a.sc.dvs[s] = dv;
+      }
+    }
+    // ============================ backward ============================
+    // A operand = [dz_v0 (32 cols) | du | 0 ...]; B = ([Wv0; Wp])^T  ->  d a_{L-1}
+    if (half == 0) {
+#pragma unroll
+      for (int g = 0; g < HH; g += 8) store_pn8(g, dzv0 + g);
+      tc::store_split4(pn_hi, pn_lo, LBO_A, row, 8, make_float4(du, 0.f, 0.f, 0.f));
+    } else {
+#pragma unroll
+      for (int kc = 9; kc < 16; ++kc) tc::store_split4(pn_hi, pn_lo, LBO_A, row, kc, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    stage_B_transposed(b_hi, b_lo, net.Wv0, net.Wp, 32, t256);
+#pragma unroll
+    for (int l = L - 1; l >= 0; --l) {
+      run_mma(kLboT, idesc64);
+      float z[HH];
+      tc::tmem_ld16(d_lane + cb, z);
+      tc::tmem_ld16(d_lane + cb + 16, z + 16);
+      tc::tmem_wait_ld();
+      float dz[HH];
+#pragma unroll
+      for (int g4 = 0; g4 < HH / 4; ++g4) {
+        float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) av = *reinterpret_cast<const float4*>(a.sc.act[l] + s * H + cb + 4 * g4);
+        const float aa[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = 4 * g4 + q;
+          const float ak = aa[q] * (dc.active ? dc.keep : 1.0f);
+          const float mk = dc.active ? (((kb[l] >> c) & 1u) ? dc.scale : 0.f) : 1.0f;
+          dz[c] = z[c] * mk * (1.0f - ak * ak);
+        }
+      }
+      if (valid) {
+#pragma unroll
+        for (int g4 = 0; g4 < HH / 4; ++g4)
+          reinterpret_cast<float4*>(a.sc.del[l] + s * H + cb)[g4] = make_float4(dz[4 * g4], dz[4 * g4 + 1], dz[4 * g4 + 2], dz[4 * g4 + 3]);
+      }
+      if (l > 0) {
+#pragma unroll
+        for (int g = 0; g < HH; g += 8) store_pn8(cb + g, dz + g);
+        stage_B_transposed(b_hi, b_lo, net.W[l], nullptr, H, t256);
+      }
+    }
+  }
+  // ---------------------------------------------------------------- loss partials per group
+  {
+    double vals[4] = {l_nll, l_abs, l_mse, l_cnt};
+    const int lane = tid & 31, wq = warp & 7;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      double t = vals[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0 && wq < 4) lred[grp][wq][k] = t;
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (tid < 8) {
+    const int g = tid >> 2, k = tid & 3;
+    double t = 0.0;
+    for (int wq = 0; wq < 4; ++wq) t += lred[g][wq][k];
+    a.loss_partial[(static_cast<size_t>(blockIdx.x) * 2 + g) * 4 + k] = t;
+  }
+  if (warp == 0) tc::tmem_dealloc(tmem_base_s, 128);
+}
+
+__global__ void grad_reduce2_kernel(const float* __restrict__ partial, const double* __restrict__ loss_partial, int nblk,
+                                    int nloss, int64_t total, float* __restrict__ grad, double* __restrict__ loss) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < total) {
+    double acc = 0.0;
+    for (int b = 0; b < nblk; ++b) acc += static_cast<double>(partial[static_cast<size_t>(b) * total + i]);
+    grad[i] = static_cast<float>(acc);
+  }
+  if (loss != nullptr && blockIdx.x == 0 && threadIdx.x < 4) {
+    double acc = 0.0;
+    for (int b = 0; b < nloss; ++b) acc += loss_partial[static_cast<size_t>(b) * 4 + threadIdx.x];
+    loss[threadIdx.x] = acc;
+  }
+}
+
+static int g_tc_bwd_enabled = 1;
+
+struct TcBwdPlan { int grid_a, grid_b; size_t smem_a, smem_b, off_partial, off_scratch, bytes; };
+static TcBwdPlan plan_tc_bwd(int L, int64_t n) {
+  TcBwdPlan p{};
+  ParamLayout lay = make_layout(kBH, L);
+  const int sms = sm_count();
+  const int64_t tiles = (n + kBTile - 1) / kBTile;
+  int64_t want = (tiles + 1) / 2;
+  p.grid_a = static_cast<int>(want < sms ? (want > 0 ? want : 1) : sms);
+  int64_t wb = (n + 1023) / 1024;
+  p.grid_b = static_cast<int>(wb < 2 * sms ? (wb > 0 ? wb : 1) : 2 * sms);
+  p.smem_a = static_cast<size_t>(make_tcb_layout(L).total) * sizeof(float);
+  p.smem_b = (static_cast<size_t>(2 * L) * kWgS * 64 + kWgS * (8 + 32 + 32 + 16 + 16 + 2)) * sizeof(float);
+  size_t off = static_cast<size_t>(2 * p.grid_a) * 4 * sizeof(double);
+  p.off_partial = off;
+  off += static_cast<size_t>(p.grid_b) * lay.total * sizeof(float);
+  off = (off + 255) & ~static_cast<size_t>(255);
+  p.off_scratch = off;
+  off += bwd_scratch_floats_per_sample(L) * static_cast<size_t>(n > 0 ? n : 1) * sizeof(float);
+  p.bytes = off;
+  return p;
+}
+
+bool tc_bwd_covers(const pinn_net_t* net) {
+  if (!g_tc_bwd_enabled || net->width != kBH || net->n_hidden < 2 || net->n_hidden > 4) return false;
+  for (int l = 0; l < net->n_hidden; ++l)
+    if (!aligned16(net->W[l])) return false;
+  return aligned16(net->Wv0) && aligned16(net->Wp);
+}
+size_t tc_bwd_workspace_bytes(int L, int64_t n) { return plan_tc_bwd(L, n).bytes; }
+
+int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropParams& dp, const float* grad_u,
+                  const float* grad_s, const float* y, int64_t n_global, float* grad_flat, double* loss_sums, void* workspace,
+                  size_t workspace_bytes, cudaStream_t st) {
+  const int L = net->n_hidden;
+  TcBwdPlan p = plan_tc_bwd(L, n);
+  if (workspace_bytes < p.bytes) return PINN_E_WORKSPACE;
+  ParamLayout lay = make_layout(kBH, L);
+  char* ws = static_cast<char*>(workspace);
+  TcbArgs a{};
+  a.x = x; a.n = n; a.grad_u = grad_u; a.grad_s = grad_s; a.y = y;
+  a.inv_n_global = grad_u ? 0.f : static_cast<float>(1.0 / static_cast<double>(n_global));
+  a.sc = carve_scratch(reinterpret_cast<float*>(ws + p.off_scratch), n, L);
+  a.loss_partial = reinterpret_cast<double*>(ws);
+  TcbLayout tl = make_tcb_layout(L);
+#define LAUNCH_A(LL)                                                                                              \
+  {                                                                                                               \
+    PINN_CUDA_TRY(cudaFuncSetAttribute(mlp_tc_bwd_kernel<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                       static_cast<int>(p.smem_a)));                                              \
+    mlp_tc_bwd_kernel<LL><<<p.grid_a, 512, p.smem_a, st>>>(*net, tl, dp, a);                                      \
+  }
+  switch (L) {
+    case 2: LAUNCH_A(2) break;
+    case 3: LAUNCH_A(3) break;
+    case 4: LAUNCH_A(4) break;
+    default: return PINN_E_SHAPE;
+  }
+#undef LAUNCH_A
+  PINN_CUDA_TRY(cudaGetLastError());
+  WgradArgs w{};
+  w.x = x; w.n = n; w.L = L; w.sc = a.sc;
+  w.partial = reinterpret_cast<float*>(ws + p.off_partial);
+#define LAUNCH_B(LL)                                                                                              \
+  {                                                                                                               \
+    PINN_CUDA_TRY(cudaFuncSetAttribute(wgrad_kernel<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+                                       static_cast<int>(p.smem_b)));                                              \
+    wgrad_kernel<LL><<<p.grid_b, 256, p.smem_b, st>>>(w, lay);                                                    \
+  }
+  switch (L) {
+    case 2: LAUNCH_B(2) break;
+    case 3: LAUNCH_B(3) break;
+    default: LAUNCH_B(4) break;
+  }
+#undef LAUNCH_B
+  PINN_CUDA_TRY(cudaGetLastError());
+  const int rg = static_cast<int>((lay.total + 255) / 256);
+  grad_reduce2_kernel<<<rg, 256, 0, st>>>(w.partial, a.loss_partial, p.grid_b, 2 * p.grid_a, lay.total, grad_flat, loss_sums);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace pinn
+
+// Ablation / test switch for the tensor-core backward path (1 = on).
+extern "C" int pinn_set_tensor_core_bwd(int enable) {
+  int prev = pinn::g_tc_bwd_enabled;
+  pinn::g_tc_bwd_enabled = enable ? 1 : 0;
+  return prev;
+}

@@ -95,11 +95,16 @@ PINN_D uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_b
   d |= 1ull << 46;  // descriptor version (Blackwell)
   return d;         // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE / interleave)
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major.
-PINN_HD constexpr uint32_t make_idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
-         (static_cast<uint32_t>(M >> 4) << 24);
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32; a_mn / b_mn
+// select MN-major (bit 15 / 16) instead of K-major operands.
+PINN_HD constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn = false, bool b_mn = false) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) |
+         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
+// The same plane  off(row, col) = (col/4)*LBO + row*16 + (col%4)*4  read as an MN-major operand
+// (MN index = col, K index = row): canonical layout ((1,n),(8,k)):((X,SBO'),(1,LBO')) in 16-byte
+// units with SBO' = LBO (distance between 4-column chunks) and LBO' = 128 B (8 rows).
+PINN_D uint64_t make_desc_mn(uint32_t smem_addr, uint32_t plane_lbo_bytes) { return make_desc(smem_addr, 128, plane_lbo_bytes); }
 // D[tmem] (+)= A[smem] * B[smem]^T, one K = 8 slab.  Issued by ONE thread.
 PINN_D void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(

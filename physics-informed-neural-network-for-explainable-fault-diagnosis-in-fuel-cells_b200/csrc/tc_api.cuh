@@ -10,4 +10,10 @@ struct TcOut {
 // 1: launched on the tcgen05 path; 0: shape not covered (use the FFMA kernels); -1: error in *err.
 int launch_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, const DropParams& dp, const TcOut& out,
               cudaStream_t st, int* err);
+// Tensor-core backward (mlp_tc_bwd.cu): 64-wide nets with 2..4 hidden layers.
+bool tc_bwd_covers(const pinn_net_t* net);
+size_t tc_bwd_workspace_bytes(int L, int64_t n);
+int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropParams& dp, const float* grad_u,
+                  const float* grad_s, const float* y, int64_t n_global, float* grad_flat, double* loss_sums, void* workspace,
+                  size_t workspace_bytes, cudaStream_t st);
 }  // namespace pinn

@@ -1,0 +1,136 @@
+// tc_mn_test.cu -- standalone check of MN-major UMMA operands (needed by the tensor-core
+// backward kernel):
+//   (B) dgrad form  D[128 x 64] = A[128 x 64] * W[64 x 64]     (W planes read MN-major)
+//   (C) wgrad form  G[64 x 64]  = Delta[128 x 64]^T * A[128 x 64]  (both planes MN-major,
+//       M = 128 by stacking Delta's hi and lo planes, K = 128 samples; G = D[0:64] + D[64:128])
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cmath>
+#include "tc.cuh"
+using namespace pinn;
+
+__global__ void __launch_bounds__(128) mn_kernel(const float* __restrict__ A, const float* __restrict__ W,
+                                                 const float* __restrict__ Dl, float* __restrict__ outB, float* __restrict__ outC, float* __restrict__ outK) {
+  constexpr int M = 128, K = 64;
+  constexpr uint32_t LBO_A = M * 16, LBO_B = 64 * 16;
+  extern __shared__ __align__(128) float smem[];
+  float* a_hi = smem;            float* a_lo = a_hi + M * K;
+  float* d_hi = a_lo + M * K;    float* d_lo = d_hi + M * K;     // Delta planes: hi directly followed by lo
+  float* b_hi = d_lo + M * K;    float* b_lo = b_hi + 64 * K;
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tc::uniform_warp_idx();
+  if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+  __syncwarp();
+  if (warp == 0) { tc::tmem_alloc(&tmem_base, 256); tc::tmem_relinquish(); }
+  for (int kc = 0; kc < K / 4; ++kc) {
+    tc::store_split4(a_hi, a_lo, LBO_A, tid, kc, *reinterpret_cast<const float4*>(A + tid * K + 4 * kc));
+    tc::store_split4(d_hi, d_lo, LBO_A, tid, kc, *reinterpret_cast<const float4*>(Dl + tid * K + 4 * kc));
+  }
+  for (int idx = tid; idx < 64 * (K / 4); idx += blockDim.x) {
+    const int n = idx % 64, kc = idx / 64;
+    tc::store_split4(b_hi, b_lo, LBO_B, n, kc, *reinterpret_cast<const float4*>(W + n * K + 4 * kc));
+  }
+  tc::fence_proxy_async(); tc::fence_before_sync(); __syncthreads(); tc::fence_after_sync();
+  const uint32_t tB = tmem_base, tC = tmem_base + 64, tK = tmem_base + 128;
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      // (B): A K-major (rows = samples), B = W planes as MN-major (N index = column k, K index = row j)
+      const uint32_t idB = tc::make_idesc_tf32(128, 64, false, true);
+      const uint64_t ah = tc::make_desc(tc::smem_u32(a_hi), LBO_A, 128), al = tc::make_desc(tc::smem_u32(a_lo), LBO_A, 128);
+      const uint64_t bh = tc::make_desc_mn(tc::smem_u32(b_hi), LBO_B), bl = tc::make_desc_mn(tc::smem_u32(b_lo), LBO_B);
+      uint32_t acc = 0;
+      for (int term = 0; term < 3; ++term) {
+        const uint64_t a = term == 0 ? al : ah, b = term == 1 ? bl : bh;
+        for (int k8 = 0; k8 < 8; ++k8) {       // A: K step = 2 chunks of 16 B; B (MN-major): K step = 8 rows = 128 B
+          tc::umma_tf32(tB, a + k8 * ((2 * LBO_A) >> 4), b + k8 * (128 >> 4), idB, acc);
+          acc = 1;
+        }
+      }
+      // (C): A = [Delta_hi ; Delta_lo] MN-major (M = 128 = 32 chunks of 4 columns), B = A planes MN-major, K = 128 samples
+      const uint32_t idC = tc::make_idesc_tf32(128, 64, true, true);
+      const uint64_t dh = tc::make_desc_mn(tc::smem_u32(d_hi), LBO_A);
+      const uint64_t xh = tc::make_desc_mn(tc::smem_u32(a_hi), LBO_A), xl = tc::make_desc_mn(tc::smem_u32(a_lo), LBO_A);
+      acc = 0;
+      for (int term = 0; term < 2; ++term) {
+        const uint64_t b = term == 0 ? xl : xh;
+        for (int k8 = 0; k8 < 16; ++k8) {
+          tc::umma_tf32(tC, dh + k8 * (128 >> 4), b + k8 * (128 >> 4), idC, acc);
+          acc = 1;
+        }
+      }
+      // control: K-major product A * W^T (the layout the forward kernel uses)
+      {
+        const uint32_t idK = tc::make_idesc_tf32(128, 64);
+        const uint64_t ah2 = tc::make_desc(tc::smem_u32(a_hi), LBO_A, 128), bh2 = tc::make_desc(tc::smem_u32(b_hi), LBO_B, 128);
+        for (int k8 = 0; k8 < 8; ++k8) tc::umma_tf32(tK, ah2 + k8 * ((2 * LBO_A) >> 4), bh2 + k8 * ((2 * LBO_B) >> 4), idK, k8 ? 1u : 0u);
+      }
+      tc::umma_commit(&bar);
+    }
+    __syncwarp();
+  }
+  tc::mbar_wait(&bar, 0);
+  __syncwarp();
+  tc::fence_after_sync();
+  float v[64], g[64], kq[64];
+  const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  for (int c = 0; c < 64; c += 16) { tc::tmem_ld16(tB + lane_off + c, v + c); tc::tmem_ld16(tC + lane_off + c, g + c); tc::tmem_ld16(tK + lane_off + c, kq + c); }
+  tc::tmem_wait_ld();
+  for (int c = 0; c < 64; ++c) { outB[tid * 64 + c] = v[c]; outC[tid * 64 + c] = g[c]; outK[tid * 64 + c] = kq[c]; }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, 256);
+}
+
+int main() {
+  std::vector<float> A(128 * 64), W(64 * 64), Dl(128 * 64);
+  srand(2);
+  for (auto& v : A) v = (rand() / (float)RAND_MAX) * 2.f - 1.f;
+  for (auto& v : Dl) v = ((rand() / (float)RAND_MAX) * 2.f - 1.f) * 0.01f;
+  for (auto& v : W) v = ((rand() / (float)RAND_MAX) * 2.f - 1.f) * 0.125f;
+  float *dA, *dW, *dD, *oB, *oC, *oK;
+  cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dW, W.size() * 4); cudaMalloc(&dD, Dl.size() * 4);
+  cudaMalloc(&oB, 128 * 64 * 4); cudaMalloc(&oC, 128 * 64 * 4); cudaMalloc(&oK, 128 * 64 * 4);
+  cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dW, W.data(), W.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dD, Dl.data(), Dl.size() * 4, cudaMemcpyHostToDevice);
+  size_t smem = (4 * 128 * 64 + 2 * 64 * 64) * sizeof(float);
+  cudaFuncSetAttribute(mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  mn_kernel<<<1, 128, smem>>>(dA, dW, dD, oB, oC, oK);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
+  std::vector<float> B(128 * 64), C(128 * 64);
+  cudaMemcpy(B.data(), oB, B.size() * 4, cudaMemcpyDeviceToHost);
+  cudaMemcpy(C.data(), oC, C.size() * 4, cudaMemcpyDeviceToHost);
+  std::vector<float> Kq(128 * 64);
+  cudaMemcpy(Kq.data(), oK, Kq.size() * 4, cudaMemcpyDeviceToHost);
+  double ek = 0, rk = 0;
+  for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < 64; ++n) {
+      double ref = 0;
+      for (int k = 0; k < 64; ++k) ref += (double)A[m * 64 + k] * (double)W[n * 64 + k];
+      ek = fmax(ek, fabs(ref - Kq[m * 64 + n])); rk = fmax(rk, fabs(ref));
+    }
+  printf("control (K-major, 1xTF32):      norm-rel %.3e   K[0][0..3] = %g %g %g %g\n", ek / rk, Kq[0], Kq[1], Kq[2], Kq[3]);
+  printf("B[0][0..3] = %g %g %g %g    C[0][0..3] = %g %g %g %g\n", B[0], B[1], B[2], B[3], C[0], C[1], C[2], C[3]);
+  double eb = 0, rb = 0, ec = 0, rc = 0;
+  for (int m = 0; m < 128; ++m)
+    for (int k = 0; k < 64; ++k) {
+      double ref = 0;
+      for (int j = 0; j < 64; ++j) ref += (double)A[m * 64 + j] * (double)W[j * 64 + k];
+      eb = fmax(eb, fabs(ref - B[m * 64 + k])); rb = fmax(rb, fabs(ref));
+    }
+  for (int j = 0; j < 64; ++j)
+    for (int k = 0; k < 64; ++k) {
+      double ref = 0;
+      for (int m = 0; m < 128; ++m) ref += (double)Dl[m * 64 + j] * (double)A[m * 64 + k];
+      double got = (double)C[j * 64 + k] + (double)C[(64 + j) * 64 + k];
+      ec = fmax(ec, fabs(ref - got)); rc = fmax(rc, fabs(ref));
+    }
+  printf("dgrad form (MN-major B):        norm-rel %.3e\n", eb / rb);
+  printf("wgrad form (MN-major A+B, M=128 hi/lo stack): norm-rel %.3e\n", ec / rc);
+  bool ok = eb / rb < 2e-6 && ec / rc < 2e-6;
+  printf(ok ? "TC_MN_TEST PASS\n" : "TC_MN_TEST FAIL\n");
+  return ok ? 0 : 1;
+}

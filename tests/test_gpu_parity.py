@@ -538,3 +538,69 @@ def test_tensor_core_path_matches_ffma_path_and_oracle(layers):
     c = b200pinn.mc_dropout_device(dnn, xd, T, p, masks=torch.tensor(mk, device=dev()))
     pm, au, eu = O.mc_dropout(params_np(dnn), x, [split_masks(mk[t], layers, p, np.float64) for t in range(T)], np.float64)
     assert nrel(t2n(c["pred_mean"]), pm) < MC_TOL and nrel(t2n(c["a_u"]), au) < MC_TOL and nrel(t2n(c["e_u"]), eu) < MC_TOL
+
+
+@pytest.fixture
+def ffma_bwd():
+    from b200pinn import kernels as K
+
+    prev = K.set_tensor_core_bwd(False)
+    yield
+    K.set_tensor_core_bwd(prev)
+
+
+def test_golden_backward_on_ffma_path(ffma_bwd):
+    """The golden backward checks above run the tcgen05 K2 for net64; repeat on the FFMA kernel."""
+    from b200pinn import kernels as K
+
+    g = load_golden("net64")
+    m = make_model(g)
+    net = K.net_from_module(m.dnn)
+    mk = torch.tensor(masks_u8(g["train_masks"], g["layers"]), device=dev())
+    n = g["x"].shape[0]
+    flat, sums = K.mlp_backward(net, m.x.detach(), K.make_dropout(g["p"], seed=1, masks=mk, mask_rows=n),
+                                y=m.u.reshape(-1).contiguous(), n_global=n)
+    s = t2n(sums)
+    assert abs((s[0] + 0.01 * s[1]) / s[3] - g["aleatoric_loss"]) < LOSS_TOL * abs(g["aleatoric_loss"]) + 1e-7
+    names, shapes, offs, _ = K.param_layout(net.width, net.n_hidden)
+    flat = t2n(flat)
+    for nm, shp, o in zip(names, shapes, offs):
+        ref = g["G:" + nm]
+        assert nrel(flat[o:o + ref.size].reshape(ref.shape), ref) < GRAD_TOL, nm
+
+
+@pytest.mark.parametrize("layers,n", [([8, 64, 64, 1], 700), ([8, 64, 64, 64, 1], 5001), ([8, 64, 64, 64, 64, 1], 1111)])
+def test_tensor_core_backward_matches_ffma_and_oracle(layers, n):
+    """tcgen05 forward+dgrad + FFMA wgrad (K2a/K2b) vs the all-FFMA kernel vs fp64 backprop; Philox
+    masks (same counters on both paths), ragged n, 2..4 hidden layers."""
+    from b200pinn import kernels as K
+    from b200pinn.synthetic import make_scaled_dataset
+
+    x, y, _, _ = make_scaled_dataset(n, seed=13)
+    dnn = random_net(layers, 6)
+    net = K.net_from_module(dnn)
+    xd, yd = torch.tensor(x, device=dev()), torch.tensor(y, device=dev()).reshape(-1).contiguous()
+    p = 0.2
+    a, sa = K.mlp_backward(net, xd, K.make_dropout(p, seed=5, pass_offset=3), y=yd, n_global=n)
+    prev = K.set_tensor_core_bwd(False)
+    try:
+        b, sb = K.mlp_backward(net, xd, K.make_dropout(p, seed=5, pass_offset=3), y=yd, n_global=n)
+    finally:
+        K.set_tensor_core_bwd(prev)
+    assert np.allclose(t2n(sa), t2n(sb), rtol=1e-5)
+    names, shapes, offs, _ = K.param_layout(net.width, net.n_hidden)
+    fa, fb = t2n(a), t2n(b)
+    for nm, shp, o in zip(names, shapes, offs):
+        cnt = int(np.prod(shp))
+        assert nrel(fa[o:o + cnt], fb[o:o + cnt]) < GRAD_TOL, nm
+    # injected masks vs the fp64 oracle
+    mk = rand_masks(np.random.default_rng(2), 1, n, layers, p)[0]
+    c, sc = K.mlp_backward(net, xd, K.make_dropout(p, seed=1, masks=torch.tensor(mk, device=dev()), mask_rows=n), y=yd, n_global=n)
+    ms64 = split_masks(mk, layers, p, np.float64)
+    P = params_np(dnn)
+    o64, l64 = O.dnn_forward(P, x, ms64, np.float64)
+    G = O.dnn_backward(P, x, ms64, *O.aleatoric_loss_grads(y, o64, l64))
+    fc = t2n(c)
+    for nm, shp, o in zip(names, shapes, offs):
+        ref = G[nm]
+        assert nrel(fc[o:o + ref.size].reshape(shp), ref.reshape(shp)) < GRAD_TOL, nm
