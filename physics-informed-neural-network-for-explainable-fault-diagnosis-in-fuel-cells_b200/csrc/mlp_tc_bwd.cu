@@ -349,8 +349,8 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
       const float* W0 = smem + lay.W0 + cb * PINN_N_IN;
       const float* b0 = smem + lay.b0 + cb;
       kb[0] = 0u;
-#pragma unroll
-      for (int g = 0; g < HH; g += 8) {
+#pragma unroll 1
+      for (int g = 0; g < HH; g += 8) {     // rolled (code size): 8 columns per trip
         float m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
         if (dc.active) drop8(dc, 0u, cb + g, 0u, m);
         float v[8];
@@ -371,25 +371,24 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
         }
       }
     }
-#pragma unroll
-    for (int l = 1; l < L; ++l) {
+#pragma unroll 1
+    for (int l = 1; l < L; ++l) {       // rolled: one copy of the layer body keeps the kernel inside the I-cache
       stage_B_rows(b_hi, b_lo, net.W[l], H, t256);
       run_mma(H * 16, idesc64);
       const float* bl = smem + lay.b[l] + cb;
-      float z[HH];
-      tc::tmem_ld16(d_lane + cb, z);
-      tc::tmem_ld16(d_lane + cb + 16, z + 16);
-      tc::tmem_wait_ld();
-      kb[l] = 0u;
-#pragma unroll
+      uint32_t bits = 0u;
+#pragma unroll 1
       for (int g = 0; g < HH; g += 8) {
+        float z[8];
+        tc::tmem_ld8(d_lane + cb + g, z);
+        tc::tmem_wait_ld();
         float m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
         if (dc.active) drop8(dc, static_cast<uint32_t>(l), cb + g, static_cast<uint32_t>(l * H), m);
         float v[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          v[q] = tanh_act(z[g + q] + bl[g + q]) * m[q];
-          kb[l] |= (m[q] != 0.f ? 1u : 0u) << (g + q);
+          v[q] = tanh_act(z[q] + bl[g + q]) * m[q];
+          bits |= (m[q] != 0.f ? 1u : 0u) << (g + q);
         }
         store_pn8(cb + g, v);
         if (valid) {
@@ -397,6 +396,7 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
           o[0] = make_float4(v[0], v[1], v[2], v[3]); o[1] = make_float4(v[4], v[5], v[6], v[7]);
         }
       }
+      kb[l] = bits;
     }
     // ---- heads: rows 0..31 = Wv0, row 32 = Wp, rows 33..47 = 0
     for (int idx = t256; idx < 48 * 16; idx += 256) {
@@ -510,37 +510,35 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
       for (int kc = 9; kc < 16; ++kc) tc::store_split4(pn_hi, pn_lo, LBO_A, row, kc, make_float4(0.f, 0.f, 0.f, 0.f));
     }
     stage_B_transposed(b_hi, b_lo, net.Wv0, net.Wp, 32, t256);
-#pragma unroll
+#pragma unroll 1
     for (int l = L - 1; l >= 0; --l) {
       run_mma(kLboT, idesc64);
-      float z[HH];
-      tc::tmem_ld16(d_lane + cb, z);
-      tc::tmem_ld16(d_lane + cb + 16, z + 16);
-      tc::tmem_wait_ld();
-      float dz[HH];
-#pragma unroll
-      for (int g4 = 0; g4 < HH / 4; ++g4) {
-        float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) av = *reinterpret_cast<const float4*>(a.sc.act[l] + s * H + cb + 4 * g4);
-        const float aa[4] = {av.x, av.y, av.z, av.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int c = 4 * g4 + q;
-          const float ak = aa[q] * (dc.active ? dc.keep : 1.0f);
-          const float mk = dc.active ? (((kb[l] >> c) & 1u) ? dc.scale : 0.f) : 1.0f;
-          dz[c] = z[c] * mk * (1.0f - ak * ak);
+      const uint32_t kbl = kb[l];
+      const float keep = dc.active ? dc.keep : 1.0f;
+#pragma unroll 1
+      for (int g = 0; g < HH; g += 8) {
+        float z[8], dz[8];
+        tc::tmem_ld8(d_lane + cb + g, z);
+        float4 av0 = make_float4(0.f, 0.f, 0.f, 0.f), av1 = av0;
+        if (valid) {
+          av0 = *reinterpret_cast<const float4*>(a.sc.act[l] + s * H + cb + g);
+          av1 = *reinterpret_cast<const float4*>(a.sc.act[l] + s * H + cb + g + 4);
         }
-      }
-      if (valid) {
+        tc::tmem_wait_ld();
+        const float aa[8] = {av0.x, av0.y, av0.z, av0.w, av1.x, av1.y, av1.z, av1.w};
 #pragma unroll
-        for (int g4 = 0; g4 < HH / 4; ++g4)
-          reinterpret_cast<float4*>(a.sc.del[l] + s * H + cb)[g4] = make_float4(dz[4 * g4], dz[4 * g4 + 1], dz[4 * g4 + 2], dz[4 * g4 + 3]);
+        for (int q = 0; q < 8; ++q) {
+          const float ak = aa[q] * keep;
+          const float mk = dc.active ? (((kbl >> (g + q)) & 1u) ? dc.scale : 0.f) : 1.0f;
+          dz[q] = z[q] * mk * (1.0f - ak * ak);
+        }
+        if (valid) {
+          float4* o = reinterpret_cast<float4*>(a.sc.del[l] + s * H + cb + g);
+          o[0] = make_float4(dz[0], dz[1], dz[2], dz[3]); o[1] = make_float4(dz[4], dz[5], dz[6], dz[7]);
+        }
+        if (l > 0) store_pn8(cb + g, dz);
       }
-      if (l > 0) {
-#pragma unroll
-        for (int g = 0; g < HH; g += 8) store_pn8(cb + g, dz + g);
-        stage_B_transposed(b_hi, b_lo, net.W[l], nullptr, H, t256);
-      }
+      if (l > 0) stage_B_transposed(b_hi, b_lo, net.W[l], nullptr, H, t256);
     }
   }
   // ---------------------------------------------------------------- loss partials per group
