@@ -51,7 +51,7 @@ inline BwdScratch carve_scratch(float* base, int64_t n, int L) {
 // ------------------------------------------------------------------------------- K2b
 // One CTA accumulates every gradient over its samples; thread (jt, kt) of a 16 x 16 grid owns
 // the 4 x 4 block (j0 = 4 jt, k0 = 4 kt) of each 64 x 64 product and sub-blocks of the rest.
-constexpr int kWgS = 32;   // samples per shared-memory stage
+constexpr int kWgS = 16;   // samples per shared-memory stage (two stages in flight)
 
 struct WgradArgs {
   const float* x; int64_t n; int L;
@@ -59,26 +59,84 @@ struct WgradArgs {
   float* partial;          // [grid][lay.total]
 };
 
+PINN_D void cp_async16(float* dst_smem, const float* src_gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst_smem))),
+               "l"(src_gmem) : "memory");
+}
+PINN_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> PINN_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// floats per stage: D[L][S][64], A[L][S][64], X[S][8], DV0[S][32], AV0[S][32], DV1[S][16], AV1[S][16], DU[S], DVS[S]
+PINN_HD constexpr int wg_stage_floats(int L) { return 2 * L * kWgS * 64 + kWgS * (8 + 32 + 32 + 16 + 16 + 2); }
+
+// Issue the asynchronous copies of one stage (rows beyond `cnt` are zero-filled with plain stores).
+template <int L>
+PINN_D void wg_issue_stage(float* st, const WgradArgs& a, int64_t s0, int cnt, int tid) {
+  float* sD = st;
+  float* sA = sD + L * kWgS * 64;
+  float* sX = sA + L * kWgS * 64;
+  float* sDV0 = sX + kWgS * 8;
+  float* sAV0 = sDV0 + kWgS * 32;
+  float* sDV1 = sAV0 + kWgS * 32;
+  float* sAV1 = sDV1 + kWgS * 16;
+  float* sDU = sAV1 + kWgS * 16;
+  float* sDVS = sDU + kWgS;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int l = 0; l < L; ++l)
+    for (int i = tid; i < kWgS * 16; i += 256) {
+      const int r = i >> 4, c4 = i & 15;
+      float* dD = sD + (l * kWgS + r) * 64 + 4 * c4;
+      float* dA = sA + (l * kWgS + r) * 64 + 4 * c4;
+      if (r < cnt) {
+        cp_async16(dD, a.sc.del[l] + (s0 + r) * 64 + 4 * c4);
+        cp_async16(dA, a.sc.act[l] + (s0 + r) * 64 + 4 * c4);
+      } else {
+        *reinterpret_cast<float4*>(dD) = zero;
+        *reinterpret_cast<float4*>(dA) = zero;
+      }
+    }
+  for (int i = tid; i < kWgS * 8; i += 256) {
+    const int r = i >> 3, c4 = i & 7;
+    if (r < cnt) {
+      cp_async16(sDV0 + r * 32 + 4 * c4, a.sc.dv0 + (s0 + r) * 32 + 4 * c4);
+      cp_async16(sAV0 + r * 32 + 4 * c4, a.sc.av0 + (s0 + r) * 32 + 4 * c4);
+    } else {
+      *reinterpret_cast<float4*>(sDV0 + r * 32 + 4 * c4) = zero;
+      *reinterpret_cast<float4*>(sAV0 + r * 32 + 4 * c4) = zero;
+    }
+  }
+  if (tid < kWgS * 4) {
+    const int r = tid >> 2, c4 = tid & 3;
+    if (r < cnt) {
+      cp_async16(sDV1 + r * 16 + 4 * c4, a.sc.dv1 + (s0 + r) * 16 + 4 * c4);
+      cp_async16(sAV1 + r * 16 + 4 * c4, a.sc.av1 + (s0 + r) * 16 + 4 * c4);
+    } else {
+      *reinterpret_cast<float4*>(sDV1 + r * 16 + 4 * c4) = zero;
+      *reinterpret_cast<float4*>(sAV1 + r * 16 + 4 * c4) = zero;
+    }
+  } else if (tid < kWgS * 4 + kWgS * 2) {
+    const int t = tid - kWgS * 4, r = t >> 1, c4 = t & 1;
+    if (r < cnt) cp_async16(sX + r * 8 + 4 * c4, a.x + (s0 + r) * 8 + 4 * c4);
+    else *reinterpret_cast<float4*>(sX + r * 8 + 4 * c4) = zero;
+  } else if (tid < kWgS * 4 + kWgS * 2 + kWgS) {
+    const int r = tid - kWgS * 6;
+    sDU[r] = r < cnt ? a.sc.du[s0 + r] : 0.f;
+    sDVS[r] = r < cnt ? a.sc.dvs[s0 + r] : 0.f;
+  }
+}
+
 template <int L>
 __global__ void __launch_bounds__(256, 2)
 wgrad_kernel(WgradArgs a, ParamLayout lay) {
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x, jt = tid >> 4, kt = tid & 15;
-  // shared stage: D_l, A_{l-1} for every trunk layer (+ x), heads
-  float* sD = sm;                                   // [L][kWgS][64]
-  float* sA = sD + L * kWgS * 64;                   // [L][kWgS][64]   (a_0 .. a_{L-1})
-  float* sX = sA + L * kWgS * 64;                   // [kWgS][8]
-  float* sDV0 = sX + kWgS * 8;                      // [kWgS][32]
-  float* sAV0 = sDV0 + kWgS * 32;                   // [kWgS][32]
-  float* sDV1 = sAV0 + kWgS * 32;                   // [kWgS][16]
-  float* sAV1 = sDV1 + kWgS * 16;                   // [kWgS][16]
-  float* sDU = sAV1 + kWgS * 16;                    // [kWgS]
-  float* sDVS = sDU + kWgS;                         // [kWgS]
+  constexpr int SF = wg_stage_floats(L);
 
-  float accW[L - 1][16];                            // dW_l, l >= 1: 4x4 block
+  float accW[L - 1][16];                            // dW_l, l >= 1: 4x4 block (j0 = 4 jt, k0 = 4 kt)
   float accV0[8];                                   // dWv0 [32][64]: rows 2jt..2jt+1, cols 4kt..4kt+3
-  float accW0[2];                                   // dW0 [64][8]: flat index 2 tid, 2 tid + 1
-  float accV1[2];                                   // dWv1 [16][32]: flat index 2 tid, 2 tid + 1
+  float accW0[2];                                   // dW0 [64][8]:  row tid/4, cols 2(tid%4)..+1
+  float accV1[2];                                   // dWv1 [16][32]: row tid/16, cols 2(tid%16)..+1
   float accS = 0.f;                                 // trunk bias sums: thread t < 64 L owns db_{t/64}[t%64]   (L <= 4)
   float accS2 = 0.f;                                // head bias sums: t < 32 dbv0, 32..47 dbv1, 48 dbp, 49 dbv2
   float accP = 0.f;                                 // dWp[tid] (tid < 64), dWv2[tid-64] (64 <= tid < 80)
@@ -93,50 +151,25 @@ wgrad_kernel(WgradArgs a, ParamLayout lay) {
   const int64_t per = (a.n + gridDim.x - 1) / gridDim.x;
   const int64_t s_begin = static_cast<int64_t>(blockIdx.x) * per;
   const int64_t s_end = s_begin + per < a.n ? s_begin + per : a.n;
-  for (int64_t s0 = s_begin; s0 < s_end; s0 += kWgS) {
-    const int cnt = static_cast<int>(s_end - s0 < kWgS ? s_end - s0 : kWgS);
+  const int n_stage = s_end > s_begin ? static_cast<int>((s_end - s_begin + kWgS - 1) / kWgS) : 0;
+  auto cnt_of = [&](int it) { const int64_t s0 = s_begin + static_cast<int64_t>(it) * kWgS; return static_cast<int>(s_end - s0 < kWgS ? s_end - s0 : kWgS); };
+  if (n_stage > 0) wg_issue_stage<L>(sm, a, s_begin, cnt_of(0), tid);
+  cp_async_commit();
+  for (int it = 0; it < n_stage; ++it) {
+    if (it + 1 < n_stage) wg_issue_stage<L>(sm + ((it + 1) & 1) * SF, a, s_begin + static_cast<int64_t>(it + 1) * kWgS, cnt_of(it + 1), tid);
+    cp_async_commit();
+    cp_async_wait<1>();          // stage `it` has landed (the newest group may still be in flight)
     __syncthreads();
-    // ---- stage (zero-fill the tail so no branch is needed in the FMA loops)
-    for (int l = 0; l < L; ++l)
-      for (int i = tid; i < kWgS * 16; i += 256) {
-        const int r = i >> 4, c4 = i & 15;
-        float4 d = make_float4(0.f, 0.f, 0.f, 0.f), v = d;
-        if (r < cnt) {
-          d = __ldg(reinterpret_cast<const float4*>(a.sc.del[l] + (s0 + r) * 64) + c4);
-          v = __ldg(reinterpret_cast<const float4*>(a.sc.act[l] + (s0 + r) * 64) + c4);
-        }
-        reinterpret_cast<float4*>(sD + (l * kWgS + r) * 64)[c4] = d;
-        reinterpret_cast<float4*>(sA + (l * kWgS + r) * 64)[c4] = v;
-      }
-    for (int i = tid; i < kWgS * 8; i += 256) {
-      const int r = i >> 3, c4 = i & 7;
-      float4 d = make_float4(0.f, 0.f, 0.f, 0.f), v = d;
-      if (r < cnt) {
-        d = __ldg(reinterpret_cast<const float4*>(a.sc.dv0 + (s0 + r) * 32) + c4);
-        v = __ldg(reinterpret_cast<const float4*>(a.sc.av0 + (s0 + r) * 32) + c4);
-      }
-      reinterpret_cast<float4*>(sDV0 + r * 32)[c4] = d;
-      reinterpret_cast<float4*>(sAV0 + r * 32)[c4] = v;
-    }
-    for (int i = tid; i < kWgS * 4; i += 256) {
-      const int r = i >> 2, c4 = i & 3;
-      float4 d = make_float4(0.f, 0.f, 0.f, 0.f), v = d;
-      if (r < cnt) {
-        d = __ldg(reinterpret_cast<const float4*>(a.sc.dv1 + (s0 + r) * 16) + c4);
-        v = __ldg(reinterpret_cast<const float4*>(a.sc.av1 + (s0 + r) * 16) + c4);
-      }
-      reinterpret_cast<float4*>(sDV1 + r * 16)[c4] = d;
-      reinterpret_cast<float4*>(sAV1 + r * 16)[c4] = v;
-    }
-    if (tid < kWgS * 2) {
-      const int r = tid >> 1, c4 = tid & 1;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < cnt) v = __ldg(reinterpret_cast<const float4*>(a.x + (s0 + r) * 8) + c4);
-      reinterpret_cast<float4*>(sX + r * 8)[c4] = v;
-    }
-    if (tid < kWgS) { sDU[tid] = tid < cnt ? __ldg(a.sc.du + s0 + tid) : 0.f; sDVS[tid] = tid < cnt ? __ldg(a.sc.dvs + s0 + tid) : 0.f; }
-    __syncthreads();
-    // ---- accumulate
+    const float* st = sm + (it & 1) * SF;
+    const float* sD = st;
+    const float* sA = sD + L * kWgS * 64;
+    const float* sX = sA + L * kWgS * 64;
+    const float* sDV0 = sX + kWgS * 8;
+    const float* sAV0 = sDV0 + kWgS * 32;
+    const float* sDV1 = sAV0 + kWgS * 32;
+    const float* sAV1 = sDV1 + kWgS * 16;
+    const float* sDU = sAV1 + kWgS * 16;
+    const float* sDVS = sDU + kWgS;
 #pragma unroll 4
     for (int r = 0; r < kWgS; ++r) {
 #pragma unroll
@@ -157,14 +190,15 @@ wgrad_kernel(WgradArgs a, ParamLayout lay) {
         accV0[4] = fmaf(d.y, v.x, accV0[4]); accV0[5] = fmaf(d.y, v.y, accV0[5]);
         accV0[6] = fmaf(d.y, v.z, accV0[6]); accV0[7] = fmaf(d.y, v.w, accV0[7]);
       }
-      {   // dW0[j][i] (64 x 8) and dWv1[k][i] (16 x 32): two consecutive flat entries per thread
-        const int e0 = 2 * tid;
-        const float d0 = sD[r * 64 + (e0 >> 3)];
-        accW0[0] = fmaf(d0, sX[r * 8 + (e0 & 7)], accW0[0]);
-        accW0[1] = fmaf(d0, sX[r * 8 + (e0 & 7) + 1], accW0[1]);
-        const float d1 = sDV1[r * 16 + (e0 >> 5)];
-        accV1[0] = fmaf(d1, sAV0[r * 32 + (e0 & 31)], accV1[0]);
-        accV1[1] = fmaf(d1, sAV0[r * 32 + (e0 & 31) + 1], accV1[1]);
+      {   // dW0[j][i] (64 x 8): row tid/4; dWv1[k][i] (16 x 32): row tid/16
+        const float d0 = sD[r * 64 + (tid >> 2)];
+        const float2 xv = *reinterpret_cast<const float2*>(sX + r * 8 + 2 * (tid & 3));
+        accW0[0] = fmaf(d0, xv.x, accW0[0]);
+        accW0[1] = fmaf(d0, xv.y, accW0[1]);
+        const float d1 = sDV1[r * 16 + (tid >> 4)];
+        const float2 av = *reinterpret_cast<const float2*>(sAV0 + r * 32 + 2 * (tid & 15));
+        accV1[0] = fmaf(d1, av.x, accV1[0]);
+        accV1[1] = fmaf(d1, av.y, accV1[1]);
       }
       if (tid < 64) accP = fmaf(sDU[r], sA[((L - 1) * kWgS + r) * 64 + tid], accP);          // dWp
       else if (tid < 80) accP = fmaf(sDVS[r], sAV1[r * 16 + tid - 64], accP);                // dWv2
@@ -174,6 +208,7 @@ wgrad_kernel(WgradArgs a, ParamLayout lay) {
       else if (tid == 48) accS2 += sDU[r];
       else if (tid == 49) accS2 += sDVS[r];
     }
+    __syncthreads();             // everyone is done with this stage before it is refilled
   }
   // ---------------------------------------------------------------- write this CTA's partial
   float* part = a.partial + static_cast<size_t>(blockIdx.x) * lay.total;
@@ -187,10 +222,10 @@ wgrad_kernel(WgradArgs a, ParamLayout lay) {
   for (int p = 0; p < 2; ++p)
 #pragma unroll
     for (int q = 0; q < 4; ++q) part[lay.offWv0 + (2 * jt + p) * 64 + 4 * kt + q] = accV0[4 * p + q];
-  part[lay.offW[0] + 2 * tid] = accW0[0];
-  part[lay.offW[0] + 2 * tid + 1] = accW0[1];
-  part[lay.offWv1 + 2 * tid] = accV1[0];
-  part[lay.offWv1 + 2 * tid + 1] = accV1[1];
+  part[lay.offW[0] + (tid >> 2) * 8 + 2 * (tid & 3)] = accW0[0];
+  part[lay.offW[0] + (tid >> 2) * 8 + 2 * (tid & 3) + 1] = accW0[1];
+  part[lay.offWv1 + (tid >> 4) * 32 + 2 * (tid & 15)] = accV1[0];
+  part[lay.offWv1 + (tid >> 4) * 32 + 2 * (tid & 15) + 1] = accV1[1];
   if (tid < 64) part[lay.offWp + tid] = accP;
   else if (tid < 80) part[lay.offWv2 + tid - 64] = accP;
   if (tid < 64 * L) part[lay.offb[tid >> 6] + (tid & 63)] = accS;
@@ -592,7 +627,7 @@ static TcBwdPlan plan_tc_bwd(int L, int64_t n) {
   int64_t wb = (n + 1023) / 1024;
   p.grid_b = static_cast<int>(wb < 2 * sms ? (wb > 0 ? wb : 1) : 2 * sms);
   p.smem_a = static_cast<size_t>(make_tcb_layout(L).total) * sizeof(float);
-  p.smem_b = (static_cast<size_t>(2 * L) * kWgS * 64 + kWgS * (8 + 32 + 32 + 16 + 16 + 2)) * sizeof(float);
+  p.smem_b = static_cast<size_t>(2) * wg_stage_floats(L) * sizeof(float);
   size_t off = static_cast<size_t>(2 * p.grid_a) * 4 * sizeof(double);
   p.off_partial = off;
   off += static_cast<size_t>(p.grid_b) * lay.total * sizeof(float);

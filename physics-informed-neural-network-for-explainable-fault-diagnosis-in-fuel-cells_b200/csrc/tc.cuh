@@ -42,19 +42,19 @@ PINN_D void mbar_init(uint64_t* bar, uint32_t count) {
 }
 PINN_D void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 PINN_D void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // try_wait with a suspend-time hint: the hardware parks the thread until the phase completes
+  // (event-driven wake-up) or the hint expires, so waiting warps neither poll nor oversleep.
   const uint32_t addr = smem_u32(bar);
   uint32_t ok;
-  for (;;) {
+  do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(20000u)
         : "memory");
-    if (ok) break;
-    __nanosleep(40);   // do not burn issue slots the other group's epilogue could use
-  }
+  } while (!ok);
 }
 // generic-proxy smem writes -> visible to the async proxy (UMMA operand reads)
 PINN_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
