@@ -84,7 +84,7 @@ PINN_D void wg_issue_stage(float* st, const WgradArgs& a, int64_t s0, int cnt, i
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int l = 0; l < L; ++l)
-    for (int i = tid; i < kWgS * 16; i += 256) {
+    for (int i = tid; i < kWgS * 16; i += blockDim.x) {
       const int r = i >> 4, c4 = i & 15;
       float* dD = sD + (l * kWgS + r) * 64 + 4 * c4;
       float* dA = sA + (l * kWgS + r) * 64 + 4 * c4;
@@ -96,7 +96,7 @@ PINN_D void wg_issue_stage(float* st, const WgradArgs& a, int64_t s0, int cnt, i
         *reinterpret_cast<float4*>(dA) = zero;
       }
     }
-  for (int i = tid; i < kWgS * 8; i += 256) {
+  for (int i = tid; i < kWgS * 8; i += blockDim.x) {
     const int r = i >> 3, c4 = i & 7;
     if (r < cnt) {
       cp_async16(sDV0 + r * 32 + 4 * c4, a.sc.dv0 + (s0 + r) * 32 + 4 * c4);
@@ -126,27 +126,43 @@ PINN_D void wg_issue_stage(float* st, const WgradArgs& a, int64_t s0, int cnt, i
   }
 }
 
+// 8x8 register tile of  out[j0..j0+8][k0..k0+8] += sum_r D[r][j0..] * A[r][k0..]  over one stage.
+PINN_D void wg_tile8x8(const float* __restrict__ sDl, const float* __restrict__ sAl, int j0, int k0, float (&acc)[64]) {
+#pragma unroll 2
+  for (int r = 0; r < kWgS; ++r) {
+    const float4 d0 = *reinterpret_cast<const float4*>(sDl + r * 64 + j0), d1 = *reinterpret_cast<const float4*>(sDl + r * 64 + j0 + 4);
+    const float4 v0 = *reinterpret_cast<const float4*>(sAl + r * 64 + k0), v1 = *reinterpret_cast<const float4*>(sAl + r * 64 + k0 + 4);
+    const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    const float2 vv[4] = {make_float2(v0.x, v0.y), make_float2(v0.z, v0.w), make_float2(v1.x, v1.y), make_float2(v1.z, v1.w)};
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const float2 dp = make_float2(dd[p], dd[p]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float2 c = make_float2(acc[8 * p + 2 * q], acc[8 * p + 2 * q + 1]);
+        c = ffma2(dp, vv[q], c);
+        acc[8 * p + 2 * q] = c.x; acc[8 * p + 2 * q + 1] = c.y;
+      }
+    }
+  }
+}
+
+// Warp-specialised contraction over the batch.  Roles (warp index w, 32 L_big = L-1 products):
+//   w in [0, 2(L-1))        : dW_l (64x64), l = 1 + w/2, 8x8 tiles, 64 threads per product
+//   w == 2(L-1)             : dWv0 (32x64), 8x8 tiles
+//   w == 2(L-1) + 1         : dW0 (64x8) and dWv1 (16x32): 16 + 16 outputs per thread
+//   w == 2(L-1) + 2         : bias column sums, dWp, dWv2
 template <int L>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(32 * (2 * (L - 1) + 3), 2)
 wgrad_kernel(WgradArgs a, ParamLayout lay) {
   extern __shared__ __align__(16) float sm[];
-  const int tid = threadIdx.x, jt = tid >> 4, kt = tid & 15;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   constexpr int SF = wg_stage_floats(L);
-
-  float accW[L - 1][16];                            // dW_l, l >= 1: 4x4 block (j0 = 4 jt, k0 = 4 kt)
-  float accV0[8];                                   // dWv0 [32][64]: rows 2jt..2jt+1, cols 4kt..4kt+3
-  float accW0[2];                                   // dW0 [64][8]:  row tid/4, cols 2(tid%4)..+1
-  float accV1[2];                                   // dWv1 [16][32]: row tid/16, cols 2(tid%16)..+1
-  float accS = 0.f;                                 // trunk bias sums: thread t < 64 L owns db_{t/64}[t%64]   (L <= 4)
-  float accS2 = 0.f;                                // head bias sums: t < 32 dbv0, 32..47 dbv1, 48 dbp, 49 dbv2
-  float accP = 0.f;                                 // dWp[tid] (tid < 64), dWv2[tid-64] (64 <= tid < 80)
+  constexpr int NB = 2 * (L - 1);          // warps on the big products
+  float acc[64];
 #pragma unroll
-  for (int l = 0; l < L - 1; ++l)
-#pragma unroll
-    for (int q = 0; q < 16; ++q) accW[l][q] = 0.f;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) accV0[q] = 0.f;
-  accW0[0] = accW0[1] = accV1[0] = accV1[1] = 0.f;
+  for (int q = 0; q < 64; ++q) acc[q] = 0.f;
 
   const int64_t per = (a.n + gridDim.x - 1) / gridDim.x;
   const int64_t s_begin = static_cast<int64_t>(blockIdx.x) * per;
@@ -170,69 +186,93 @@ wgrad_kernel(WgradArgs a, ParamLayout lay) {
     const float* sAV1 = sDV1 + kWgS * 16;
     const float* sDU = sAV1 + kWgS * 16;
     const float* sDVS = sDU + kWgS;
-#pragma unroll 4
-    for (int r = 0; r < kWgS; ++r) {
+    if (warp < NB) {
+      const int l = 1 + (warp >> 1), t = ((warp & 1) << 5) | lane;
+      wg_tile8x8(sD + l * kWgS * 64, sA + (l - 1) * kWgS * 64, 8 * (t >> 3), 8 * (t & 7), acc);
+    } else if (warp == NB) {
+      // dWv0[i][c]: 32 x 64 -> thread (it4 = lane/8, ct = lane%8) owns rows 8 it4.., cols 8 ct..
+      const int i0 = 8 * (lane >> 3), c0 = 8 * (lane & 7);
+      const float* sAl = sA + (L - 1) * kWgS * 64;
+#pragma unroll 2
+      for (int r = 0; r < kWgS; ++r) {
+        const float4 d0 = *reinterpret_cast<const float4*>(sDV0 + r * 32 + i0), d1 = *reinterpret_cast<const float4*>(sDV0 + r * 32 + i0 + 4);
+        const float4 v0 = *reinterpret_cast<const float4*>(sAl + r * 64 + c0), v1 = *reinterpret_cast<const float4*>(sAl + r * 64 + c0 + 4);
+        const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-      for (int l = 1; l < L; ++l) {
-        const float4 d = *reinterpret_cast<const float4*>(sD + (l * kWgS + r) * 64 + 4 * jt);
-        const float4 v = *reinterpret_cast<const float4*>(sA + ((l - 1) * kWgS + r) * 64 + 4 * kt);
-        const float dd[4] = {d.x, d.y, d.z, d.w}, vv[4] = {v.x, v.y, v.z, v.w};
+        for (int p = 0; p < 8; ++p)
 #pragma unroll
-        for (int p = 0; p < 4; ++p)
+          for (int q = 0; q < 8; ++q) acc[8 * p + q] = fmaf(dd[p], vv[q], acc[8 * p + q]);
+      }
+    } else if (warp == NB + 1) {
+      // acc[0..16): dW0 rows 2 lane, 2 lane + 1 (8 cols each); acc[16..32): dWv1 row lane/2, cols 16 (lane%2)..+16
+      const int k1 = lane >> 1, c1 = 16 * (lane & 1);
+#pragma unroll 2
+      for (int r = 0; r < kWgS; ++r) {
+        const float2 d = *reinterpret_cast<const float2*>(sD + r * 64 + 2 * lane);
+        const float4 x0 = *reinterpret_cast<const float4*>(sX + r * 8), x1 = *reinterpret_cast<const float4*>(sX + r * 8 + 4);
+        const float xx[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-          for (int q = 0; q < 4; ++q) accW[l - 1][4 * p + q] = fmaf(dd[p], vv[q], accW[l - 1][4 * p + q]);
+        for (int q = 0; q < 8; ++q) { acc[q] = fmaf(d.x, xx[q], acc[q]); acc[8 + q] = fmaf(d.y, xx[q], acc[8 + q]); }
+        const float d1 = sDV1[r * 16 + k1];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const float4 av = *reinterpret_cast<const float4*>(sAV0 + r * 32 + c1 + 4 * q4);
+          acc[16 + 4 * q4] = fmaf(d1, av.x, acc[16 + 4 * q4]);     acc[16 + 4 * q4 + 1] = fmaf(d1, av.y, acc[16 + 4 * q4 + 1]);
+          acc[16 + 4 * q4 + 2] = fmaf(d1, av.z, acc[16 + 4 * q4 + 2]); acc[16 + 4 * q4 + 3] = fmaf(d1, av.w, acc[16 + 4 * q4 + 3]);
+        }
       }
-      {   // dWv0[i][c] += dz_v0[i] * a_{L-1}[c]
-        const float2 d = *reinterpret_cast<const float2*>(sDV0 + r * 32 + 2 * jt);
-        const float4 v = *reinterpret_cast<const float4*>(sA + ((L - 1) * kWgS + r) * 64 + 4 * kt);
-        accV0[0] = fmaf(d.x, v.x, accV0[0]); accV0[1] = fmaf(d.x, v.y, accV0[1]);
-        accV0[2] = fmaf(d.x, v.z, accV0[2]); accV0[3] = fmaf(d.x, v.w, accV0[3]);
-        accV0[4] = fmaf(d.y, v.x, accV0[4]); accV0[5] = fmaf(d.y, v.y, accV0[5]);
-        accV0[6] = fmaf(d.y, v.z, accV0[6]); accV0[7] = fmaf(d.y, v.w, accV0[7]);
+    } else {
+      // acc[2 l], acc[2 l + 1]: db_l[2 lane], db_l[2 lane + 1];  acc[16]: dbv0[lane]; acc[17]: dbv1 / dbp / dbv2;
+      // acc[18], acc[19]: dWp[2 lane], dWp[2 lane + 1];  acc[20]: dWv2[lane] (lane < 16)
+#pragma unroll 2
+      for (int r = 0; r < kWgS; ++r) {
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+          const float2 d = *reinterpret_cast<const float2*>(sD + (l * kWgS + r) * 64 + 2 * lane);
+          acc[2 * l] += d.x; acc[2 * l + 1] += d.y;
+        }
+        acc[16] += sDV0[r * 32 + lane];
+        if (lane < 16) acc[17] += sDV1[r * 16 + lane];
+        else if (lane == 16) acc[17] += sDU[r];
+        else if (lane == 17) acc[17] += sDVS[r];
+        const float du = sDU[r];
+        const float2 aL = *reinterpret_cast<const float2*>(sA + ((L - 1) * kWgS + r) * 64 + 2 * lane);
+        acc[18] = fmaf(du, aL.x, acc[18]); acc[19] = fmaf(du, aL.y, acc[19]);
+        if (lane < 16) acc[20] = fmaf(sDVS[r], sAV1[r * 16 + lane], acc[20]);
       }
-      {   // dW0[j][i] (64 x 8): row tid/4; dWv1[k][i] (16 x 32): row tid/16
-        const float d0 = sD[r * 64 + (tid >> 2)];
-        const float2 xv = *reinterpret_cast<const float2*>(sX + r * 8 + 2 * (tid & 3));
-        accW0[0] = fmaf(d0, xv.x, accW0[0]);
-        accW0[1] = fmaf(d0, xv.y, accW0[1]);
-        const float d1 = sDV1[r * 16 + (tid >> 4)];
-        const float2 av = *reinterpret_cast<const float2*>(sAV0 + r * 32 + 2 * (tid & 15));
-        accV1[0] = fmaf(d1, av.x, accV1[0]);
-        accV1[1] = fmaf(d1, av.y, accV1[1]);
-      }
-      if (tid < 64) accP = fmaf(sDU[r], sA[((L - 1) * kWgS + r) * 64 + tid], accP);          // dWp
-      else if (tid < 80) accP = fmaf(sDVS[r], sAV1[r * 16 + tid - 64], accP);                // dWv2
-      if (tid < 64 * L) accS += sD[((tid >> 6) * kWgS + r) * 64 + (tid & 63)];
-      if (tid < 32) accS2 += sDV0[r * 32 + tid];
-      else if (tid < 48) accS2 += sDV1[r * 16 + tid - 32];
-      else if (tid == 48) accS2 += sDU[r];
-      else if (tid == 49) accS2 += sDVS[r];
     }
     __syncthreads();             // everyone is done with this stage before it is refilled
   }
   // ---------------------------------------------------------------- write this CTA's partial
   float* part = a.partial + static_cast<size_t>(blockIdx.x) * lay.total;
+  if (warp < NB) {
+    const int l = 1 + (warp >> 1), t = ((warp & 1) << 5) | lane, j0 = 8 * (t >> 3), k0 = 8 * (t & 7);
 #pragma unroll
-  for (int l = 1; l < L; ++l)
+    for (int p = 0; p < 8; ++p)
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
+      for (int q = 0; q < 8; ++q) part[lay.offW[l] + (j0 + p) * 64 + k0 + q] = acc[8 * p + q];
+  } else if (warp == NB) {
+    const int i0 = 8 * (lane >> 3), c0 = 8 * (lane & 7);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) part[lay.offW[l] + (4 * jt + p) * 64 + 4 * kt + q] = accW[l - 1][4 * p + q];
+    for (int p = 0; p < 8; ++p)
 #pragma unroll
-  for (int p = 0; p < 2; ++p)
+      for (int q = 0; q < 8; ++q) part[lay.offWv0 + (i0 + p) * 64 + c0 + q] = acc[8 * p + q];
+  } else if (warp == NB + 1) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) part[lay.offWv0 + (2 * jt + p) * 64 + 4 * kt + q] = accV0[4 * p + q];
-  part[lay.offW[0] + (tid >> 2) * 8 + 2 * (tid & 3)] = accW0[0];
-  part[lay.offW[0] + (tid >> 2) * 8 + 2 * (tid & 3) + 1] = accW0[1];
-  part[lay.offWv1 + (tid >> 4) * 32 + 2 * (tid & 15)] = accV1[0];
-  part[lay.offWv1 + (tid >> 4) * 32 + 2 * (tid & 15) + 1] = accV1[1];
-  if (tid < 64) part[lay.offWp + tid] = accP;
-  else if (tid < 80) part[lay.offWv2 + tid - 64] = accP;
-  if (tid < 64 * L) part[lay.offb[tid >> 6] + (tid & 63)] = accS;
-  if (tid < 32) part[lay.offbv0 + tid] = accS2;
-  else if (tid < 48) part[lay.offbv1 + tid - 32] = accS2;
-  else if (tid == 48) part[lay.offbp] = accS2;
-  else if (tid == 49) part[lay.offbv2] = accS2;
+    for (int q = 0; q < 8; ++q) { part[lay.offW[0] + (2 * lane) * 8 + q] = acc[q]; part[lay.offW[0] + (2 * lane + 1) * 8 + q] = acc[8 + q]; }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) part[lay.offWv1 + (lane >> 1) * 32 + 16 * (lane & 1) + q] = acc[16 + q];
+  } else {
+#pragma unroll
+    for (int l = 0; l < L; ++l) { part[lay.offb[l] + 2 * lane] = acc[2 * l]; part[lay.offb[l] + 2 * lane + 1] = acc[2 * l + 1]; }
+    part[lay.offbv0 + lane] = acc[16];
+    if (lane < 16) part[lay.offbv1 + lane] = acc[17];
+    else if (lane == 16) part[lay.offbp] = acc[17];
+    else if (lane == 17) part[lay.offbv2] = acc[17];
+    part[lay.offWp + 2 * lane] = acc[18]; part[lay.offWp + 2 * lane + 1] = acc[19];
+    if (lane < 16) part[lay.offWv2 + lane] = acc[20];
+  }
 }
 
 // ------------------------------------------------------------------------------- K2a
@@ -681,7 +721,7 @@ int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropPa
   {                                                                                                               \
     PINN_CUDA_TRY(cudaFuncSetAttribute(wgrad_kernel<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
                                        static_cast<int>(p.smem_b)));                                              \
-    wgrad_kernel<LL><<<p.grid_b, 256, p.smem_b, st>>>(w, lay);                                                    \
+    wgrad_kernel<LL><<<p.grid_b, 32 * (2 * (LL - 1) + 3), p.smem_b, st>>>(w, lay);                                                   \
   }
   switch (L) {
     case 2: LAUNCH_B(2) break;
