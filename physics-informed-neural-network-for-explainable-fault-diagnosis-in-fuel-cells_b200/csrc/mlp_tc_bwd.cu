@@ -147,22 +147,30 @@ PINN_D void wg_tile8x8(const float* __restrict__ sDl, const float* __restrict__ 
   }
 }
 
-// Warp-specialised contraction over the batch.  Roles (warp index w, 32 L_big = L-1 products):
-//   w in [0, 2(L-1))        : dW_l (64x64), l = 1 + w/2, 8x8 tiles, 64 threads per product
-//   w == 2(L-1)             : dWv0 (32x64), 8x8 tiles
-//   w == 2(L-1) + 1         : dW0 (64x8) and dWv1 (16x32): 16 + 16 outputs per thread
-//   w == 2(L-1) + 2         : bias column sums, dWp, dWv2
+// Contraction over the batch with uniform warps.  NBT = 64 (L-1) + 32 threads each own one 8x8
+// register tile of the big products (dW_l 64x64 for l >= 1: 64 threads each; dWv0 32x64: 32
+// threads); the small outputs are spread evenly on top:
+//   dW0 (64x8): thread t < 128 -> row t/2, 4 columns;   dWv1 (16x32): t < 128 -> row t/8, 4 columns
+//   trunk bias sums db_l[c]: entry e = t, t + blockDim (< 64 L);   dWp[c]: t < 64;   dWv2[k]: 64 <= t < 80
+//   head bias sums (dbv0 32, dbv1 16, dbp, dbv2): 80 <= t < 130
+PINN_HD constexpr int wg_threads(int L) { return 64 * (L - 1) + 32 < 160 ? 160 : 64 * (L - 1) + 32; }   // >= 130 needed by the small outputs
 template <int L>
-__global__ void __launch_bounds__(32 * (2 * (L - 1) + 3), 2)
+__global__ void __launch_bounds__(wg_threads(L), (L >= 4 ? 2 : 3))
 wgrad_kernel(WgradArgs a, ParamLayout lay) {
   extern __shared__ __align__(16) float sm[];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  constexpr int NBT = 64 * (L - 1) + 32, NT = wg_threads(L);
   constexpr int SF = wg_stage_floats(L);
-  constexpr int NB = 2 * (L - 1);          // warps on the big products
+  const int tid = threadIdx.x;
+  // big tile of this thread
+  const bool is_v0 = tid >= 64 * (L - 1);
+  const int lbig = 1 + (tid >> 6), tt = is_v0 ? tid - 64 * (L - 1) : (tid & 63);
+  const int j0 = 8 * (tt >> 3), k0 = 8 * (tt & 7);
   float acc[64];
 #pragma unroll
   for (int q = 0; q < 64; ++q) acc[q] = 0.f;
+  float aW0[4] = {0.f, 0.f, 0.f, 0.f}, aV1[4] = {0.f, 0.f, 0.f, 0.f}, aB[2] = {0.f, 0.f}, aP = 0.f;
+  const int e0 = tid, e1 = tid + NT;                        // trunk-bias entries (flat over [L][64])
+  const bool has_big = tid < NBT;
 
   const int64_t per = (a.n + gridDim.x - 1) / gridDim.x;
   const int64_t s_begin = static_cast<int64_t>(blockIdx.x) * per;
@@ -186,93 +194,76 @@ wgrad_kernel(WgradArgs a, ParamLayout lay) {
     const float* sAV1 = sDV1 + kWgS * 16;
     const float* sDU = sAV1 + kWgS * 16;
     const float* sDVS = sDU + kWgS;
-    if (warp < NB) {
-      const int l = 1 + (warp >> 1), t = ((warp & 1) << 5) | lane;
-      wg_tile8x8(sD + l * kWgS * 64, sA + (l - 1) * kWgS * 64, 8 * (t >> 3), 8 * (t & 7), acc);
-    } else if (warp == NB) {
-      // dWv0[i][c]: 32 x 64 -> thread (it4 = lane/8, ct = lane%8) owns rows 8 it4.., cols 8 ct..
-      const int i0 = 8 * (lane >> 3), c0 = 8 * (lane & 7);
+    // ---- big tile
+    if (!has_big) {
+    } else if (!is_v0) {
+      wg_tile8x8(sD + lbig * kWgS * 64, sA + (lbig - 1) * kWgS * 64, j0, k0, acc);
+    } else {
       const float* sAl = sA + (L - 1) * kWgS * 64;
 #pragma unroll 2
       for (int r = 0; r < kWgS; ++r) {
-        const float4 d0 = *reinterpret_cast<const float4*>(sDV0 + r * 32 + i0), d1 = *reinterpret_cast<const float4*>(sDV0 + r * 32 + i0 + 4);
-        const float4 v0 = *reinterpret_cast<const float4*>(sAl + r * 64 + c0), v1 = *reinterpret_cast<const float4*>(sAl + r * 64 + c0 + 4);
+        const float4 d0 = *reinterpret_cast<const float4*>(sDV0 + r * 32 + j0), d1 = *reinterpret_cast<const float4*>(sDV0 + r * 32 + j0 + 4);
+        const float4 v0 = *reinterpret_cast<const float4*>(sAl + r * 64 + k0), v1 = *reinterpret_cast<const float4*>(sAl + r * 64 + k0 + 4);
         const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-        const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        const float2 vv[4] = {make_float2(v0.x, v0.y), make_float2(v0.z, v0.w), make_float2(v1.x, v1.y), make_float2(v1.z, v1.w)};
 #pragma unroll
-        for (int p = 0; p < 8; ++p)
+        for (int p = 0; p < 8; ++p) {
+          const float2 dp = make_float2(dd[p], dd[p]);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) acc[8 * p + q] = fmaf(dd[p], vv[q], acc[8 * p + q]);
-      }
-    } else if (warp == NB + 1) {
-      // acc[0..16): dW0 rows 2 lane, 2 lane + 1 (8 cols each); acc[16..32): dWv1 row lane/2, cols 16 (lane%2)..+16
-      const int k1 = lane >> 1, c1 = 16 * (lane & 1);
-#pragma unroll 2
-      for (int r = 0; r < kWgS; ++r) {
-        const float2 d = *reinterpret_cast<const float2*>(sD + r * 64 + 2 * lane);
-        const float4 x0 = *reinterpret_cast<const float4*>(sX + r * 8), x1 = *reinterpret_cast<const float4*>(sX + r * 8 + 4);
-        const float xx[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { acc[q] = fmaf(d.x, xx[q], acc[q]); acc[8 + q] = fmaf(d.y, xx[q], acc[8 + q]); }
-        const float d1 = sDV1[r * 16 + k1];
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const float4 av = *reinterpret_cast<const float4*>(sAV0 + r * 32 + c1 + 4 * q4);
-          acc[16 + 4 * q4] = fmaf(d1, av.x, acc[16 + 4 * q4]);     acc[16 + 4 * q4 + 1] = fmaf(d1, av.y, acc[16 + 4 * q4 + 1]);
-          acc[16 + 4 * q4 + 2] = fmaf(d1, av.z, acc[16 + 4 * q4 + 2]); acc[16 + 4 * q4 + 3] = fmaf(d1, av.w, acc[16 + 4 * q4 + 3]);
+          for (int q = 0; q < 4; ++q) {
+            float2 c = make_float2(acc[8 * p + 2 * q], acc[8 * p + 2 * q + 1]);
+            c = ffma2(dp, vv[q], c);
+            acc[8 * p + 2 * q] = c.x; acc[8 * p + 2 * q + 1] = c.y;
+          }
         }
       }
-    } else {
-      // acc[2 l], acc[2 l + 1]: db_l[2 lane], db_l[2 lane + 1];  acc[16]: dbv0[lane]; acc[17]: dbv1 / dbp / dbv2;
-      // acc[18], acc[19]: dWp[2 lane], dWp[2 lane + 1];  acc[20]: dWv2[lane] (lane < 16)
-#pragma unroll 2
-      for (int r = 0; r < kWgS; ++r) {
-#pragma unroll
-        for (int l = 0; l < L; ++l) {
-          const float2 d = *reinterpret_cast<const float2*>(sD + (l * kWgS + r) * 64 + 2 * lane);
-          acc[2 * l] += d.x; acc[2 * l + 1] += d.y;
-        }
-        acc[16] += sDV0[r * 32 + lane];
-        if (lane < 16) acc[17] += sDV1[r * 16 + lane];
-        else if (lane == 16) acc[17] += sDU[r];
-        else if (lane == 17) acc[17] += sDVS[r];
-        const float du = sDU[r];
-        const float2 aL = *reinterpret_cast<const float2*>(sA + ((L - 1) * kWgS + r) * 64 + 2 * lane);
-        acc[18] = fmaf(du, aL.x, acc[18]); acc[19] = fmaf(du, aL.y, acc[19]);
-        if (lane < 16) acc[20] = fmaf(sDVS[r], sAV1[r * 16 + lane], acc[20]);
+    }
+    // ---- small outputs
+#pragma unroll 4
+    for (int r = 0; r < kWgS; ++r) {
+      if (tid < 128) {
+        const float d0 = sD[r * 64 + (tid >> 1)];
+        const float4 xv = *reinterpret_cast<const float4*>(sX + r * 8 + 4 * (tid & 1));
+        aW0[0] = fmaf(d0, xv.x, aW0[0]); aW0[1] = fmaf(d0, xv.y, aW0[1]); aW0[2] = fmaf(d0, xv.z, aW0[2]); aW0[3] = fmaf(d0, xv.w, aW0[3]);
+        const float d1 = sDV1[r * 16 + (tid >> 3)];
+        const float4 av = *reinterpret_cast<const float4*>(sAV0 + r * 32 + 4 * (tid & 7));
+        aV1[0] = fmaf(d1, av.x, aV1[0]); aV1[1] = fmaf(d1, av.y, aV1[1]); aV1[2] = fmaf(d1, av.z, aV1[2]); aV1[3] = fmaf(d1, av.w, aV1[3]);
       }
+      if (e0 < 64 * L) aB[0] += sD[((e0 >> 6) * kWgS + r) * 64 + (e0 & 63)];
+      if (e1 < 64 * L) aB[1] += sD[((e1 >> 6) * kWgS + r) * 64 + (e1 & 63)];
+      if (tid < 64) aP = fmaf(sDU[r], sA[((L - 1) * kWgS + r) * 64 + tid], aP);
+      else if (tid < 80) aP = fmaf(sDVS[r], sAV1[r * 16 + tid - 64], aP);
+      else if (tid < 112) aP += sDV0[r * 32 + tid - 80];
+      else if (tid < 128) aP += sDV1[r * 16 + tid - 112];
+      else if (tid == 128) aP += sDU[r];
+      else if (tid == 129) aP += sDVS[r];
     }
     __syncthreads();             // everyone is done with this stage before it is refilled
   }
   // ---------------------------------------------------------------- write this CTA's partial
   float* part = a.partial + static_cast<size_t>(blockIdx.x) * lay.total;
-  if (warp < NB) {
-    const int l = 1 + (warp >> 1), t = ((warp & 1) << 5) | lane, j0 = 8 * (t >> 3), k0 = 8 * (t & 7);
+  if (has_big) {
+    const int64_t base = is_v0 ? lay.offWv0 : lay.offW[lbig];
 #pragma unroll
     for (int p = 0; p < 8; ++p)
 #pragma unroll
-      for (int q = 0; q < 8; ++q) part[lay.offW[l] + (j0 + p) * 64 + k0 + q] = acc[8 * p + q];
-  } else if (warp == NB) {
-    const int i0 = 8 * (lane >> 3), c0 = 8 * (lane & 7);
-#pragma unroll
-    for (int p = 0; p < 8; ++p)
-#pragma unroll
-      for (int q = 0; q < 8; ++q) part[lay.offWv0 + (i0 + p) * 64 + c0 + q] = acc[8 * p + q];
-  } else if (warp == NB + 1) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) { part[lay.offW[0] + (2 * lane) * 8 + q] = acc[q]; part[lay.offW[0] + (2 * lane + 1) * 8 + q] = acc[8 + q]; }
-#pragma unroll
-    for (int q = 0; q < 16; ++q) part[lay.offWv1 + (lane >> 1) * 32 + 16 * (lane & 1) + q] = acc[16 + q];
-  } else {
-#pragma unroll
-    for (int l = 0; l < L; ++l) { part[lay.offb[l] + 2 * lane] = acc[2 * l]; part[lay.offb[l] + 2 * lane + 1] = acc[2 * l + 1]; }
-    part[lay.offbv0 + lane] = acc[16];
-    if (lane < 16) part[lay.offbv1 + lane] = acc[17];
-    else if (lane == 16) part[lay.offbp] = acc[17];
-    else if (lane == 17) part[lay.offbv2] = acc[17];
-    part[lay.offWp + 2 * lane] = acc[18]; part[lay.offWp + 2 * lane + 1] = acc[19];
-    if (lane < 16) part[lay.offWv2 + lane] = acc[20];
+      for (int q = 0; q < 8; ++q) part[base + (j0 + p) * 64 + k0 + q] = acc[8 * p + q];
   }
+  if (tid < 128) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      part[lay.offW[0] + (tid >> 1) * 8 + 4 * (tid & 1) + q] = aW0[q];
+      part[lay.offWv1 + (tid >> 3) * 32 + 4 * (tid & 7) + q] = aV1[q];
+    }
+  }
+  if (e0 < 64 * L) part[lay.offb[e0 >> 6] + (e0 & 63)] = aB[0];
+  if (e1 < 64 * L) part[lay.offb[e1 >> 6] + (e1 & 63)] = aB[1];
+  if (tid < 64) part[lay.offWp + tid] = aP;
+  else if (tid < 80) part[lay.offWv2 + tid - 64] = aP;
+  else if (tid < 112) part[lay.offbv0 + tid - 80] = aP;
+  else if (tid < 128) part[lay.offbv1 + tid - 112] = aP;
+  else if (tid == 128) part[lay.offbp] = aP;
+  else if (tid == 129) part[lay.offbv2] = aP;
 }
 
 // ------------------------------------------------------------------------------- K2a
@@ -665,7 +656,7 @@ static TcBwdPlan plan_tc_bwd(int L, int64_t n) {
   int64_t want = (tiles + 1) / 2;
   p.grid_a = static_cast<int>(want < sms ? (want > 0 ? want : 1) : sms);
   int64_t wb = (n + 1023) / 1024;
-  p.grid_b = static_cast<int>(wb < 2 * sms ? (wb > 0 ? wb : 1) : 2 * sms);
+  p.grid_b = static_cast<int>(wb < 3 * sms ? (wb > 0 ? wb : 1) : 3 * sms);
   p.smem_a = static_cast<size_t>(make_tcb_layout(L).total) * sizeof(float);
   p.smem_b = static_cast<size_t>(2) * wg_stage_floats(L) * sizeof(float);
   size_t off = static_cast<size_t>(2 * p.grid_a) * 4 * sizeof(double);
@@ -721,7 +712,7 @@ int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropPa
   {                                                                                                               \
     PINN_CUDA_TRY(cudaFuncSetAttribute(wgrad_kernel<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
                                        static_cast<int>(p.smem_b)));                                              \
-    wgrad_kernel<LL><<<p.grid_b, 32 * (2 * (LL - 1) + 3), p.smem_b, st>>>(w, lay);                                                   \
+    wgrad_kernel<LL><<<p.grid_b, wg_threads(LL), p.smem_b, st>>>(w, lay);                                                                  \
   }
   switch (L) {
     case 2: LAUNCH_B(2) break;
