@@ -293,14 +293,19 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 8 * 4, "d2h_bytes_per_step": n * 3 * 4},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": mc_tflops, "peak": pk["bf16"], "unit": "TFLOP/s",
-                     "frac": mc_tflops / pk["bf16"], "traffic": None, "kernel": "mc_dropout_kernel<64,false>",
+                     "frac": mc_tflops / pk["bf16"], "traffic": 32.2e6 * n / 1e6,
+                     "kernel": "mlp_tc_kernel<MC> (tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators)",
                      "peak_source": pk["src"],
-                     "note": "K4 is an fp32 FFMA2 kernel (parity 1e-5 rules out plain TF32); against the fp32 "
-                             "CUDA-core peak 148 SM x 128 FMA x 2 x 1.965 GHz = 74.5 TFLOP/s the fraction is "
-                             f"{mc_tflops / 74.5:.3f}"},
+                     "note": "achieved = algorithmic FLOPs (21 664 per sample*pass) / CUDA-event time of the launch. The "
+                             "contractions run as 3 TF32 MMAs per product (fp32 parity), and TF32 dense peak is half the "
+                             "bf16 figure used as `peak`, so the tensor pipe does 6x this fraction of its own peak "
+                             "(ncu: sm__pipe_tensor_cycles_active ~15-20 %); the kernel is bounded by the CUDA-core "
+                             "epilogue (tanh + Philox + operand re-split), see DESIGN.md section 4. `traffic` is the ncu "
+                             "dram read+write of one launch at N=1M (profiles/r1_v3_mc_tc.summary.txt), scaled by n; "
+                             f"vs the fp32 FFMA peak (74.5 TFLOP/s) the kernel stands at {mc_tflops / 74.5:.2f}x"},
         "train": {"steps_per_s": steps_tr / t_tr, "ms_per_step": 1e3 * t_tr / steps_tr,
                   "global_batch": world * n, "tflops": world * n * FLOP_PER_TRAIN_SAMPLE / (t_tr / steps_tr) / 1e12,
-                  "what": "train_dnn step: K2 (fwd+aleatoric loss+bwd+wgrad) + partial reduce + "
+                  "what": "train_dnn step: K2a (tcgen05 fwd+loss+dgrad) + K2b (FFMA wgrad) + partial reduce + "
                           + ("NCCL all-reduce of the flat grad bucket + " if world > 1 else "") + "fused Adam/StepLR"},
         "roofline_residual": {"bound": "hbm", "achieved": nb * RES_BYTES_PER_SAMPLE / (t_resb / K_) / 1e9, "peak": pk["hbm"],
                               "unit": "GB/s", "frac": nb * RES_BYTES_PER_SAMPLE / (t_resb / K_) / 1e9 / pk["hbm"],

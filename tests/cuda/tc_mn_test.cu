@@ -130,7 +130,14 @@ int main() {
     }
   printf("dgrad form (MN-major B):        norm-rel %.3e\n", eb / rb);
   printf("wgrad form (MN-major A+B, M=128 hi/lo stack): norm-rel %.3e\n", ec / rc);
-  bool ok = eb / rb < 2e-6 && ec / rc < 2e-6;
-  printf(ok ? "TC_MN_TEST PASS\n" : "TC_MN_TEST FAIL\n");
-  return ok ? 0 : 1;
+  const bool control_ok = ek / rk < 1e-3;
+  const bool mn_ok = eb / rb < 2e-6 && ec / rc < 2e-6;
+  // Finding on B200 / CUDA 12.9 (recorded in DESIGN.md): with the plain interleaved (no-swizzle)
+  // layout both MN-major products come back as exact zeros -- the MMA is dropped without an error.
+  // CUTLASS states the same constraint: "for mn-major tf32 operands, SW128_32B is the only
+  // available smem layout".  The backward kernels therefore use K-major operands only.
+  printf(mn_ok ? "MN-major interleaved TF32: WORKS on this toolchain\n"
+               : "MN-major interleaved TF32: dropped/unsupported (expected, see DESIGN.md)\n");
+  printf(control_ok ? "TC_MN_TEST PASS (control)\n" : "TC_MN_TEST FAIL (control)\n");
+  return control_ok ? 0 : 1;
 }
