@@ -11,8 +11,9 @@
 //       activations and pre-activation deltas of every layer go to HBM ([N][width] fp32 rows,
 //       128 B per thread per layer); keep-bits ride in registers so Philox runs once.
 //  K2b  wgrad_kernel : dW_l = delta_l^T a_{l-1} for all seven weight tensors and the bias
-//       column sums, contraction over the batch, register-tiled FFMA over shared-memory
-//       staged [32 samples][width] tiles; per-CTA partials -> grad_reduce_kernel (fixed-order,
+//       column sums, contraction over the batch, 8x8 FFMA2 register tiles over 16-sample stages
+//       that TMA bulk copies (cp.async.bulk + mbarrier transaction bytes) double-buffer into
+//       shared memory; per-CTA partials -> grad_reduce_kernel (fixed-order,
 //       deterministic).
 //
 // (MN-major TF32 operands, which would allow an all-on-chip variant, require CUTLASS's
@@ -39,7 +40,7 @@ PINN_HD size_t bwd_scratch_floats_per_sample(int L) { return static_cast<size_t>
 inline BwdScratch carve_scratch(float* base, int64_t n, int L) {
   BwdScratch s{};
   float* p = base;
-  const size_t N = static_cast<size_t>(n);
+  const size_t N = (static_cast<size_t>(n) + 3) & ~static_cast<size_t>(3);   // every array 16-byte aligned (TMA sources)
   for (int l = 0; l < L; ++l) { s.act[l] = p; p += N * kBH; }
   for (int l = 0; l < L; ++l) { s.del[l] = p; p += N * kBH; }
   s.av0 = p; p += N * 32; s.dv0 = p; p += N * 32;
@@ -153,6 +154,34 @@ PINN_D void wg_tile8x8(const float* __restrict__ sDl, const float* __restrict__ 
 //   dW0 (64x8): thread t < 128 -> row t/2, 4 columns;   dWv1 (16x32): t < 128 -> row t/8, 4 columns
 //   trunk bias sums db_l[c]: entry e = t, t + blockDim (< 64 L);   dWp[c]: t < 64;   dWv2[k]: 64 <= t < 80
 //   head bias sums (dbv0 32, dbv1 16, dbp, dbv2): 80 <= t < 130
+// One FULL stage (kWgS samples) by TMA: every array's slab is contiguous in HBM, so the stage is
+// 2L + 7 bulk copies issued by a single thread; the mbarrier counts the bytes as they land.
+template <int L>
+PINN_D void wg_issue_stage_bulk(float* st, uint64_t* bar, const WgradArgs& a, int64_t s0) {
+  float* sD = st;
+  float* sA = sD + L * kWgS * 64;
+  float* sX = sA + L * kWgS * 64;
+  float* sDV0 = sX + kWgS * 8;
+  float* sAV0 = sDV0 + kWgS * 32;
+  float* sDV1 = sAV0 + kWgS * 32;
+  float* sAV1 = sDV1 + kWgS * 16;
+  float* sDU = sAV1 + kWgS * 16;
+  float* sDVS = sDU + kWgS;
+  tc::mbar_expect_tx(bar, static_cast<uint32_t>(wg_stage_floats(L) * sizeof(float)));
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    tc::bulk_g2s(sD + l * kWgS * 64, a.sc.del[l] + s0 * 64, kWgS * 64 * 4, bar);
+    tc::bulk_g2s(sA + l * kWgS * 64, a.sc.act[l] + s0 * 64, kWgS * 64 * 4, bar);
+  }
+  tc::bulk_g2s(sX, a.x + s0 * 8, kWgS * 8 * 4, bar);
+  tc::bulk_g2s(sDV0, a.sc.dv0 + s0 * 32, kWgS * 32 * 4, bar);
+  tc::bulk_g2s(sAV0, a.sc.av0 + s0 * 32, kWgS * 32 * 4, bar);
+  tc::bulk_g2s(sDV1, a.sc.dv1 + s0 * 16, kWgS * 16 * 4, bar);
+  tc::bulk_g2s(sAV1, a.sc.av1 + s0 * 16, kWgS * 16 * 4, bar);
+  tc::bulk_g2s(sDU, a.sc.du + s0, kWgS * 4, bar);
+  tc::bulk_g2s(sDVS, a.sc.dvs + s0, kWgS * 4, bar);
+}
+
 PINN_HD constexpr int wg_threads(int L) { return 64 * (L - 1) + 32 < 160 ? 160 : 64 * (L - 1) + 32; }   // >= 130 needed by the small outputs
 template <int L>
 __global__ void __launch_bounds__(wg_threads(L), (L >= 4 ? 2 : 3))
@@ -172,18 +201,29 @@ wgrad_kernel(WgradArgs a, ParamLayout lay) {
   const int e0 = tid, e1 = tid + NT;                        // trunk-bias entries (flat over [L][64])
   const bool has_big = tid < NBT;
 
-  const int64_t per = (a.n + gridDim.x - 1) / gridDim.x;
-  const int64_t s_begin = static_cast<int64_t>(blockIdx.x) * per;
+  // sample range of this CTA: a multiple of the stage size (keeps every TMA source 16-byte aligned)
+  int64_t per = (a.n + gridDim.x - 1) / gridDim.x;
+  per = (per + kWgS - 1) / kWgS * kWgS;
+  const int64_t s_begin = static_cast<int64_t>(blockIdx.x) * per < a.n ? static_cast<int64_t>(blockIdx.x) * per : a.n;
   const int64_t s_end = s_begin + per < a.n ? s_begin + per : a.n;
   const int n_stage = s_end > s_begin ? static_cast<int>((s_end - s_begin + kWgS - 1) / kWgS) : 0;
   auto cnt_of = [&](int it) { const int64_t s0 = s_begin + static_cast<int64_t>(it) * kWgS; return static_cast<int>(s_end - s0 < kWgS ? s_end - s0 : kWgS); };
-  if (n_stage > 0) wg_issue_stage<L>(sm, a, s_begin, cnt_of(0), tid);
-  cp_async_commit();
+  __shared__ __align__(8) uint64_t full[2];
+  if (tid == 0) { tc::mbar_init(&full[0], 1); tc::mbar_init(&full[1], 1); tc::fence_mbar_init(); }
+  __syncthreads();
+  uint32_t ph[2] = {0u, 0u};
+  // full stages arrive by TMA (one thread issues), a ragged last stage by per-thread cp.async
+  auto issue = [&](int it) {
+    float* st = sm + (it & 1) * SF;
+    const int64_t s0 = s_begin + static_cast<int64_t>(it) * kWgS;
+    if (cnt_of(it) == kWgS) { if (tid == 0) wg_issue_stage_bulk<L>(st, &full[it & 1], a, s0); }
+    else { wg_issue_stage<L>(st, a, s0, cnt_of(it), tid); cp_async_commit(); }
+  };
+  if (n_stage > 0) issue(0);
   for (int it = 0; it < n_stage; ++it) {
-    if (it + 1 < n_stage) wg_issue_stage<L>(sm + ((it + 1) & 1) * SF, a, s_begin + static_cast<int64_t>(it + 1) * kWgS, cnt_of(it + 1), tid);
-    cp_async_commit();
-    cp_async_wait<1>();          // stage `it` has landed (the newest group may still be in flight)
-    __syncthreads();
+    if (it + 1 < n_stage) issue(it + 1);
+    if (cnt_of(it) == kWgS) { tc::mbar_wait(&full[it & 1], ph[it & 1]); ph[it & 1] ^= 1u; }
+    else { cp_async_wait<0>(); __syncthreads(); }
     const float* st = sm + (it & 1) * SF;
     const float* sD = st;
     const float* sA = sD + L * kWgS * 64;
@@ -664,7 +704,7 @@ static TcBwdPlan plan_tc_bwd(int L, int64_t n) {
   off += static_cast<size_t>(p.grid_b) * lay.total * sizeof(float);
   off = (off + 255) & ~static_cast<size_t>(255);
   p.off_scratch = off;
-  off += bwd_scratch_floats_per_sample(L) * static_cast<size_t>(n > 0 ? n : 1) * sizeof(float);
+  off += bwd_scratch_floats_per_sample(L) * ((static_cast<size_t>(n > 0 ? n : 1) + 3) & ~static_cast<size_t>(3)) * sizeof(float);
   p.bytes = off;
   return p;
 }
