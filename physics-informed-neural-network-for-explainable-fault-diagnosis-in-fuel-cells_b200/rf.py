@@ -18,6 +18,20 @@ from ._abi import PinnRfParams, check, ptr
 RF_Z_SAFE, RF_LAMBDA_DECAY = 2.0, 0.9971                     # 04:97-98
 RF_K_LOGISTIC, RF_C0_LOGISTIC, RF_C_MAX = 0.0005, 500.0, 1000.0   # 04:99-101
 RF_ALPHA_SMOOTH, RF_WARN_THRESHOLD = 0.2, 0.3                # 04:112,163
+RF_RES_KEYS = ("res", "pV", "pT", "pH", "pO")                # 04:80  (columns 12..16)
+NORMAL_LABELS = (0,)                                         # 04:79
+RF_LAYER_CONFIG = {"voltage": ["res", "pV"], "gas": ["pH", "pO"], "temp": ["pT"]}     # 04:84-88
+RF_LAYER_WEIGHTS = {"voltage": 1.0, "gas": 1.0, "temp": 1.0}                          # 04:92-96
+RF_FEATURE_WEIGHTS = np.array([1.0, 1.0, 1.0, 1.0, 1.0])                              # 04:90
+RF_P_LAYER = 2.0                                                                      # 04:97
+
+
+def _only_default(name, value, default):
+    """The kernels implement the script's configuration; other layer layouts are not built."""
+    same = np.array_equal(np.asarray(value, dtype=object), np.asarray(default, dtype=object)) \
+        if not isinstance(default, dict) else value == default
+    if value is not None and not same:
+        raise NotImplementedError(f"b200pinn.rf: only the reference's default `{name}` is implemented on the device")
 
 
 def _as_device(results, device=None):
@@ -61,8 +75,10 @@ def rf_device(results: torch.Tensor, z_safe=RF_Z_SAFE, lambda_decay=RF_LAMBDA_DE
     return out
 
 
-def estimate_mu_sigma_normal(results):
+def estimate_mu_sigma_normal(results, res_keys=RF_RES_KEYS, normal_labels=NORMAL_LABELS):
     """04:181-197 -> ``(mu[5], sigma[5])`` numpy (order res, pV, pT, pH, pO)."""
+    _only_default("res_keys", tuple(res_keys), RF_RES_KEYS)
+    _only_default("normal_labels", tuple(normal_labels), NORMAL_LABELS)
     r, _ = _as_device(results)
     dev = r.device
     L = _abi.lib()
@@ -75,10 +91,16 @@ def estimate_mu_sigma_normal(results):
     return m[:5].copy(), m[5:].copy()
 
 
-def compute_rf_time_series(results, mu, sigma, z_safe=RF_Z_SAFE, lambda_decay=RF_LAMBDA_DECAY,
-                           k_logistic=RF_K_LOGISTIC, C0_logistic=RF_C0_LOGISTIC, C_max=RF_C_MAX,
-                           alpha_smooth=RF_ALPHA_SMOOTH):
+def compute_rf_time_series(results, mu, sigma, res_keys=RF_RES_KEYS, feature_weights=RF_FEATURE_WEIGHTS,
+                           layer_config=RF_LAYER_CONFIG, layer_weights=RF_LAYER_WEIGHTS, p_layer=RF_P_LAYER,
+                           z_safe=RF_Z_SAFE, lambda_decay=RF_LAMBDA_DECAY, k_logistic=RF_K_LOGISTIC,
+                           C0_logistic=RF_C0_LOGISTIC, C_max=RF_C_MAX, alpha_smooth=RF_ALPHA_SMOOTH):
     """04:201-285 -> ``(RF_inst, RF_smooth, extra)`` numpy, ``extra`` holding ``S_tot`` and ``C``."""
+    _only_default("res_keys", tuple(res_keys), RF_RES_KEYS)
+    _only_default("feature_weights", feature_weights, RF_FEATURE_WEIGHTS)
+    _only_default("layer_config", layer_config, RF_LAYER_CONFIG)
+    _only_default("layer_weights", layer_weights, RF_LAYER_WEIGHTS)
+    _only_default("p_layer", p_layer, RF_P_LAYER)
     r, _ = _as_device(results)
     ms = torch.tensor(np.concatenate([np.asarray(mu, np.float64), np.asarray(sigma, np.float64)])[None, :],
                       device=r.device)

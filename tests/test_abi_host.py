@@ -159,3 +159,50 @@ def test_chan_merge_equals_single_pass():
     a_u, e_u = finalize(acc[0], acc[2], acc[3])
     assert torch.allclose(acc[1], u.mean(0)) and torch.allclose(e_u, u.var(0, unbiased=False).sqrt())
     assert torch.allclose(a_u, torch.sqrt(torch.exp(s.mean(0))))
+
+
+def test_abi_error_codes_without_gpu():
+    """Argument / shape validation precedes any CUDA call, so the error contract is testable on CPU:
+    negative PINN_E_* codes, readable messages, Python wrappers raising RuntimeError."""
+    import ctypes as C
+    import b200pinn._abi as abi
+
+    L = abi.lib()
+    e = enum_values("PINN_E_")
+    assert e == {"PINN_E_ARG": -1, "PINN_E_SHAPE": -2, "PINN_E_WORKSPACE": -3, "PINN_E_ALIGN": -4}
+    for code in e.values():
+        assert L.pinn_error_string(code).decode().startswith("b200pinn:")
+    assert L.pinn_error_string(0) == b"success"
+    assert L.pinn_mlp_fwd(None, None, 0, None, None, None, None, 0, None) == e["PINN_E_ARG"]
+    net = abi.PinnNet()
+    net.n_in, net.width, net.n_hidden = 8, 48, 3                 # unsupported width
+    assert L.pinn_mlp_fwd(C.byref(net), None, 0, None, None, None, None, 0, None) == e["PINN_E_SHAPE"]
+    net.n_in, net.width, net.n_hidden = 7, 64, 3                 # wrong feature count
+    assert L.pinn_mc_dropout(C.byref(net), None, 0, 1, None, None, None, None, None, None, None, None, 0, None) == e["PINN_E_SHAPE"]
+    net.n_in, net.width, net.n_hidden = 8, 64, 9                 # too deep
+    assert L.pinn_mlp_bwd(C.byref(net), None, 0, None, None, None, None, 0, None, None, None, 0, None) == e["PINN_E_SHAPE"]
+    net.n_in, net.width, net.n_hidden = 8, 64, 3                 # right shape, null weight pointers
+    assert L.pinn_mlp_fwd(C.byref(net), None, 0, None, None, None, None, 0, None) == e["PINN_E_ARG"]
+    assert L.pinn_residuals(None, None, None, 5, None, None, 1, 0, None, None, None, None, None, 0, None) == e["PINN_E_ARG"]
+    assert L.pinn_rf_series(None, 0, 1, None, None, None, None, None, None, None, None, 0, None) == e["PINN_E_ARG"]
+    assert L.pinn_export_rows(None, None, None, None, None, None, None, 0, 0, 0, None, 5, None, None) == e["PINN_E_ARG"]
+    assert L.pinn_param_count(64, 0) == e["PINN_E_SHAPE"]
+    with pytest.raises(RuntimeError, match="null or inconsistent"):
+        abi.check(e["PINN_E_ARG"], "unit test")
+
+
+def test_dropin_install_rebinds_reference_names():
+    import types
+    import b200pinn
+
+    ref = types.ModuleType("ref01")
+    ref.DNN = ref.get_MC_samples = ref.PhysicsInformedNN = ref.create_comprehensive_results_array_v2 = None
+    b200pinn.install(ref, "A")
+    assert ref.DNN is b200pinn.DNN and ref.get_MC_samples is None
+    b200pinn.install(ref, "B")
+    assert ref.get_MC_samples is b200pinn.get_MC_samples and ref.PhysicsInformedNN is None
+    b200pinn.install(ref, "C")
+    assert ref.PhysicsInformedNN is b200pinn.PhysicsInformedNN
+    assert ref.create_comprehensive_results_array_v2 is b200pinn.create_comprehensive_results_array_v2
+    with pytest.raises(ValueError):
+        b200pinn.install(ref, "Z")
