@@ -146,9 +146,10 @@ PINN_HD DropCtx make_ctx(const DropParams& dp, int64_t s_local, int64_t pass_loc
 // per call and was a quarter of the MC kernel's instructions (profiles/r1_*).
 PINN_HD float tanh_act(float x) {
 #ifdef __CUDA_ARCH__
-  float e;
+  float e, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-2.885390082f * fabsf(x)));
-  return copysignf(__fdividef(1.0f - e, 1.0f + e), x);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));     // 1+e in [1,2]: no range fix-ups needed
+  return copysignf((1.0f - e) * r, x);
 #else
   return tanhf(x);
 #endif
