@@ -313,7 +313,7 @@ struct TcbLayout {   // float offsets into dynamic shared memory
   int W0, b0, b[PINN_MAX_HIDDEN], bv0, bp, Wv1, bv1, Wv2, bv2;
   int total;
 };
-constexpr int kBPlaneFloats = 16 * 1040 / 4;    // 16 chunks x 1040 B (padded LBO, see stage_B_transposed)
+constexpr int kBPlaneFloats = 16 * 1040 / 4;    // 16 chunks x 1040 B (padded LBO, see wcommit_transposed)
 PINN_HD TcbLayout make_tcb_layout(int L) {
   TcbLayout t;
   int o = 0;
@@ -331,26 +331,36 @@ PINN_HD TcbLayout make_tcb_layout(int L) {
 
 PINN_D void grp_sync256(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); }
 
-// B planes <- rows of a row-major [nrows][64] matrix (K-major B: row n, contraction index k).
-PINN_D void stage_B_rows(float* hi, float* lo, const float* __restrict__ src, int nrows, int t256) {
-  const uint32_t lbo = static_cast<uint32_t>(nrows) * 16;
-  for (int idx = t256; idx < nrows * 16; idx += 256) {
-    const int nrow = idx % nrows, kc = idx / nrows;
-    tc::store_split4(hi, lo, lbo, nrow, kc, __ldg(reinterpret_cast<const float4*>(src + nrow * 64) + kc));
-  }
-}
-// B planes <- TRANSPOSE of a row-major [J][64] matrix: B[n = k][col j] = src[j][k], columns j >= J
-// zero (dgrad: d a_{l-1} = d z_l * W_l).  Scalar stores; LBO is padded to 1040 B so that the eight
-// 4-column chunks a warp touches fall into different banks.
+// Weight staging is split in two so the L2 latency hides behind the previous MMA:
+//   wprefetch : 4 x 128-bit global loads per thread into registers (item idx = t256 + 256 it ->
+//               source row j = idx % 64, 4-column chunk kc = idx / 64; rows >= J read as zero,
+//               row J optionally comes from `extra_row`, e.g. the mean head stacked under Wv0);
+//   wcommit_rows       : B[n = j][k]  (K-major rows, forward:  z = a W^T)
+//   wcommit_transposed : B[n = k][col j] = src[j][k]  (dgrad:  d a = d z W); scalar stores, the
+//               plane LBO is padded to 1040 B so a warp's eight 4-column chunks hit distinct banks.
 constexpr uint32_t kLboT = 1040;
-PINN_D void stage_B_transposed(float* hi, float* lo, const float* __restrict__ src, const float* __restrict__ extra_row, int J,
-                               int t256) {
-  for (int idx = t256; idx < 64 * 16; idx += 256) {
-    const int j = idx & 63, kc = idx >> 6;
+PINN_D void wprefetch(float4 (&w)[4], const float* __restrict__ src, const float* __restrict__ extra_row, int J, int t256) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int idx = t256 + 256 * it, j = idx & 63, kc = idx >> 6;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (j < J) v = __ldg(reinterpret_cast<const float4*>(src + j * 64) + kc);
     else if (j == J && extra_row != nullptr) v = __ldg(reinterpret_cast<const float4*>(extra_row) + kc);
-    const float vv[4] = {v.x, v.y, v.z, v.w};
+    w[it] = v;
+  }
+}
+PINN_D void wcommit_rows(float* hi, float* lo, const float4 (&w)[4], int t256) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int idx = t256 + 256 * it;
+    tc::store_split4(hi, lo, 64 * 16, idx & 63, idx >> 6, w[it]);
+  }
+}
+PINN_D void wcommit_transposed(float* hi, float* lo, const float4 (&w)[4], int t256) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int idx = t256 + 256 * it, j = idx & 63, kc = idx >> 6;
+    const float vv[4] = {w[it].x, w[it].y, w[it].z, w[it].w};
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const float h = tc::tf32_hi(vv[r]);
@@ -412,7 +422,7 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
   double l_nll = 0.0, l_abs = 0.0, l_mse = 0.0, l_cnt = 0.0;
 
   // publish PN + B (generic-proxy writes) to the async proxy, run one 3xTF32 product, wait for it
-  auto run_mma = [&](uint32_t lbo_b, uint32_t idesc) {
+  auto run_mma = [&](uint32_t lbo_b, uint32_t idesc, auto&& prefetch) {
     tc::fence_proxy_async();
     tc::fence_before_sync();
     grp_sync256(grp);
@@ -425,6 +435,7 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
       }
       __syncwarp();
     }
+    prefetch();                 // global loads for the NEXT phase fly while the tensor core works
     tc::mbar_wait(&mbar[grp], phase);
     phase ^= 1u;
     __syncwarp();
@@ -441,6 +452,8 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
     const bool valid = s < a.n;
     const DropCtx dc = make_ctx(dp, s, 0, Dm, true, valid);
     uint32_t kb[L + 1];      // keep bits of this thread's 32 columns, per dropout layer (bit q = column cb + q)
+    float4 wpre[4];
+    wprefetch(wpre, net.W[1], nullptr, H, t256);
     // ============================ forward ============================
     {
       float xr[PINN_N_IN];
@@ -479,8 +492,11 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
     }
 #pragma unroll 1
     for (int l = 1; l < L; ++l) {       // rolled: one copy of the layer body keeps the kernel inside the I-cache
-      stage_B_rows(b_hi, b_lo, net.W[l], H, t256);
-      run_mma(H * 16, idesc64);
+      wcommit_rows(b_hi, b_lo, wpre, t256);
+      run_mma(H * 16, idesc64, [&] {
+        if (l + 1 < L) wprefetch(wpre, net.W[l + 1], nullptr, H, t256);
+        else wprefetch(wpre, net.Wv0, net.Wp, 32, t256);
+      });
       const float* bl = smem + lay.b[l] + cb;
       uint32_t bits = 0u;
 #pragma unroll 1
@@ -504,15 +520,9 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
       }
       kb[l] = bits;
     }
-    // ---- heads: rows 0..31 = Wv0, row 32 = Wp, rows 33..47 = 0
-    for (int idx = t256; idx < 48 * 16; idx += 256) {
-      const int nrow = idx % 48, kc = idx / 48;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (nrow < 32) v = __ldg(reinterpret_cast<const float4*>(net.Wv0 + nrow * H) + kc);
-      else if (nrow == 32) v = __ldg(reinterpret_cast<const float4*>(net.Wp) + kc);
-      tc::store_split4(b_hi, b_lo, 48 * 16, nrow, kc, v);
-    }
-    run_mma(48 * 16, idesc48);
+    // ---- heads: rows 0..31 = Wv0, row 32 = Wp, rows 33.. = 0 (N = 48 of the 64 staged rows are read)
+    wcommit_rows(b_hi, b_lo, wpre, t256);
+    run_mma(H * 16, idesc48, [&] { wprefetch(wpre, net.Wv0, net.Wp, 32, t256); });
     float du = 0.f;
     float dzv0[HH];                      // half 0: d z of the variance head's first layer; half 1: unused
     kb[L] = 0u;
@@ -615,23 +625,25 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
 #pragma unroll
       for (int kc = 9; kc < 16; ++kc) tc::store_split4(pn_hi, pn_lo, LBO_A, row, kc, make_float4(0.f, 0.f, 0.f, 0.f));
     }
-    stage_B_transposed(b_hi, b_lo, net.Wv0, net.Wp, 32, t256);
+    wcommit_transposed(b_hi, b_lo, wpre, t256);
 #pragma unroll 1
     for (int l = L - 1; l >= 0; --l) {
-      run_mma(kLboT, idesc64);
+      float4 apre[HH / 4];       // this thread's masked activations of layer l, prefetched during the MMA
+      run_mma(kLboT, idesc64, [&] {
+#pragma unroll
+        for (int g4 = 0; g4 < HH / 4; ++g4)
+          apre[g4] = valid ? *reinterpret_cast<const float4*>(a.sc.act[l] + s * H + cb + 4 * g4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (l > 0) wprefetch(wpre, net.W[l], nullptr, H, t256);
+      });
       const uint32_t kbl = kb[l];
       const float keep = dc.active ? dc.keep : 1.0f;
-#pragma unroll 1
+#pragma unroll
       for (int g = 0; g < HH; g += 8) {
         float z[8], dz[8];
         tc::tmem_ld8(d_lane + cb + g, z);
-        float4 av0 = make_float4(0.f, 0.f, 0.f, 0.f), av1 = av0;
-        if (valid) {
-          av0 = *reinterpret_cast<const float4*>(a.sc.act[l] + s * H + cb + g);
-          av1 = *reinterpret_cast<const float4*>(a.sc.act[l] + s * H + cb + g + 4);
-        }
         tc::tmem_wait_ld();
-        const float aa[8] = {av0.x, av0.y, av0.z, av0.w, av1.x, av1.y, av1.z, av1.w};
+        const float aa[8] = {apre[g / 4].x, apre[g / 4].y, apre[g / 4].z, apre[g / 4].w,
+                             apre[g / 4 + 1].x, apre[g / 4 + 1].y, apre[g / 4 + 1].z, apre[g / 4 + 1].w};
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float ak = aa[q] * keep;
@@ -644,7 +656,7 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
         }
         if (l > 0) store_pn8(cb + g, dz);
       }
-      if (l > 0) stage_B_transposed(b_hi, b_lo, net.W[l], nullptr, H, t256);
+      if (l > 0) wcommit_transposed(b_hi, b_lo, wpre, t256);
     }
   }
   // ---------------------------------------------------------------- loss partials per group
