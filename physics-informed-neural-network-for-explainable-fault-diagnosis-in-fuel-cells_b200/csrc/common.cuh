@@ -48,6 +48,22 @@ struct Philox {
     }
     return make_uint4(c0, c1, c2, c3);
   }
+
+  // Same generator with the ten round keys precomputed on the host (rk[2r] = k0 + r W0,
+  // rk[2r+1] = k1 + r W1).  `rk` lives in the kernel-parameter constant bank and is indexed
+  // with compile-time constants, so every key is a c[0x0][..] operand of the LOP3 that consumes
+  // it: no key-schedule adds and no key registers in the hot loop.
+  static PINN_HD uint4 gen_rk(const uint32_t (&rk)[20], uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t hi0, lo0, hi1, lo1;
+      mulhilo(M0, c0, hi0, lo0);
+      mulhilo(M1, c2, hi1, lo1);
+      uint32_t n0 = hi1 ^ c1 ^ rk[2 * r], n2 = hi0 ^ c3 ^ rk[2 * r + 1];
+      c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
 };
 
 // Dropout draw context for one sample and one pass.
@@ -68,7 +84,7 @@ struct DropCtx {
 PINN_HD uint32_t drop_threshold(float p) {
   double t = static_cast<double>(p) * 65536.0 + 0.5;
   if (t <= 0.0) return 0u;
-  if (t >= 65536.0) return 65536u;
+  if (t >= 65535.0) return 65535u;     // p < 1 always; keeps thresh << 16 representable
   return static_cast<uint32_t>(t);
 }
 PINN_HD float drop_scale(float p) {
@@ -101,6 +117,8 @@ struct DropParams {
   uint32_t k0, k1;
   int64_t sample_offset, pass_offset, mask_n;
   const uint8_t* masks;
+  uint32_t rk[20];       // Philox round keys (Philox::gen_rk)
+  uint32_t thresh_hi;    // thresh << 16: "high 16-bit field >= thresh" is one unsigned compare
 };
 inline DropParams make_drop_params(const pinn_dropout_t* d) {
   DropParams q{};
@@ -118,6 +136,11 @@ inline DropParams make_drop_params(const pinn_dropout_t* d) {
     q.mask_n = d->mask_sample_stride_n;
     q.masks = d->masks;
   }
+  for (int r = 0; r < 10; ++r) {
+    q.rk[2 * r] = q.k0 + static_cast<uint32_t>(r) * Philox::W0;
+    q.rk[2 * r + 1] = q.k1 + static_cast<uint32_t>(r) * Philox::W1;
+  }
+  q.thresh_hi = q.thresh << 16;
   return q;
 }
 // Context of (shard-local sample s_local, shard-local pass pass_local); D = mask row bytes.
@@ -138,6 +161,28 @@ PINN_HD DropCtx make_ctx(const DropParams& dp, int64_t s_local, int64_t pass_loc
   return c;
 }
 
+// Keep decisions of 8 consecutive units [j0, j0+8) of dropout layer `layer` for one (sample, pass):
+// Philox mode draws the same 16-bit fields as drop8() (common.cuh), compared without extracting
+// them: the high field is kept iff  w >= thresh<<16,  the low field iff  (w<<16) >= thresh<<16.
+template <bool INJ>
+struct KeepSrc {
+  uint32_t s_lo, s_hi, pass;
+  const uint8_t* mrow;     // INJ: keep bytes of this (pass, sample)
+  PINN_D void get8(const DropParams& dp, uint32_t layer, uint32_t j0, uint32_t unit_base, bool (&k)[8]) const {
+    if constexpr (INJ) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) k[q] = mrow[unit_base + j0 + q] != 0;
+    } else {
+      const uint4 r = Philox::gen_rk(dp.rk, s_lo, s_hi, pass, (layer << 16) | (j0 >> 3));
+      const uint32_t th = dp.thresh_hi;
+      k[0] = (r.x << 16) >= th; k[1] = r.x >= th;
+      k[2] = (r.y << 16) >= th; k[3] = r.y >= th;
+      k[4] = (r.z << 16) >= th; k[5] = r.z >= th;
+      k[6] = (r.w << 16) >= th; k[7] = r.w >= th;
+    }
+  }
+};
+
 // ------------------------------------------------------------------------ math
 // tanh(x) = sign(x) (1 - e)/(1 + e), e = exp(-2|x|) from MUFU.EX2 + MUFU.RCP: 8 instructions,
 // branch-free.  Its ABSOLUTE error is <= ~3e-7 everywhere (the relative error grows as
@@ -153,6 +198,18 @@ PINN_HD float tanh_act(float x) {
 #else
   return tanhf(x);
 #endif
+}
+
+// The tensor-core kernels use the sign-free form  tanh(x) = 1 - 2 / (1 + 2^(c x)),  c = 2 log2(e):
+// with biases (and the layer-0 weights) pre-scaled by c the argument is one FFMA (or comes out
+// of the dot product directly) and the whole activation is FFMA, EX2, FADD, RCP, FFMA.  Same
+// absolute error (<= ~3e-7); saturates cleanly (2^a -> inf gives rcp -> 0 -> 1; 2^a -> 0 gives -1).
+constexpr float kTanhArg = 2.8853900817779268f;
+PINN_D float tanh_pre(float a) {       // a = kTanhArg * x
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return fmaf(-2.0f, r, 1.0f);
 }
 
 // log(softplus(v) + 1e-6), softplus with torch's threshold 20 (01:432-434).

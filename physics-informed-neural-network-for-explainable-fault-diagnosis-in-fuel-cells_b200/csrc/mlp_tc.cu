@@ -66,12 +66,22 @@ PINN_HD TcLayout make_tc_layout(int L, int nwg) {
 PINN_D void grp_sync(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); }
 
 // MC = true : eval pass (if pred_mean) + T dropout passes with Welford.   MC = false: one pass.
+// INJ = true: keep decisions come from an injected mask tensor (parity runs) instead of Philox.
 // A "group" is 256 threads working on one 128-sample tile: thread (row, half) owns columns
 // [32*half, 32*half+32) of sample `row`'s activations (TMEM lane `row`), so 16 warps per SM
 // keep the schedulers fed while each thread's working set stays at 32 values.
-template <bool MC>
+//
+// Instruction diet of the epilogue (it, not the tensor pipe, bounds this kernel):
+//  * the dropout scale 1/(1-p) is folded into the resident weight planes (and into Wv1), so a
+//    kept activation is stored as is: one FSEL per unit instead of FSEL + FMUL; passes without
+//    dropout (the eval pass) multiply by (1-p) instead;
+//  * biases (and layer 0's weights) are pre-scaled by 2 log2(e): tanh = FFMA, EX2, FADD, RCP, FFMA;
+//  * Philox round keys are constant-bank operands, 16-bit draws are compared in place;
+//  * the tf32 split of an activation is IADD + LOP3 + FADD.
+template <bool MC, bool INJ>
 __global__ void __launch_bounds__(512, 1)
-mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t n, int T, DropParams dp, TcOut out) {
+mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t n, int T, const __grid_constant__ DropParams dp,
+              TcOut out) {
   constexpr int H = kTcH, HH = kTcH / 2;
   constexpr uint32_t LBO_A = kTcTile * 16, LBO_B = H * 16, LBO_H = kHeadN * 16;
   extern __shared__ __align__(1024) float smem[];
@@ -82,6 +92,9 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
   const int ngrp = blockDim.x >> 8;
   const int Dm = L * H + H / 2;
   const int cb = half * HH;  // first column owned by this thread
+  const bool drop_on = dp.p > 0.f;
+  const float wscale = drop_on ? dp.scale : 1.0f;    // folded into every matrix that consumes masked activations
+  const float inact = drop_on ? dp.keep : 1.0f;      // multiplier of an un-masked activation (undoes the fold)
 
   // ---------------------------------------------------------------- one-time CTA set-up
   if (tid == 0) {
@@ -91,26 +104,27 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
   }
   __syncwarp();
   if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 128); tc::tmem_relinquish(); }
+  auto scaled4 = [](float4 v, float c) { return make_float4(v.x * c, v.y * c, v.z * c, v.w * c); };
   for (int l = 1; l < L; ++l)
     for (int idx = tid; idx < H * (H / 4); idx += blockDim.x) {
       const int nrow = idx % H, kc = idx / H;
       tc::store_split4(smem + lay.b_hi[l], smem + lay.b_lo[l], LBO_B, nrow, kc,
-                       __ldg(reinterpret_cast<const float4*>(net.W[l] + nrow * H) + kc));
+                       scaled4(__ldg(reinterpret_cast<const float4*>(net.W[l] + nrow * H) + kc), wscale));
     }
   for (int idx = tid; idx < kHeadN * (H / 4); idx += blockDim.x) {
     const int nrow = idx % kHeadN, kc = idx / kHeadN;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (nrow < H / 2) v = __ldg(reinterpret_cast<const float4*>(net.Wv0 + nrow * H) + kc);
     else if (nrow == H / 2) v = __ldg(reinterpret_cast<const float4*>(net.Wp) + kc);
-    tc::store_split4(smem + lay.h_hi, smem + lay.h_lo, LBO_H, nrow, kc, v);
+    tc::store_split4(smem + lay.h_hi, smem + lay.h_lo, LBO_H, nrow, kc, scaled4(v, wscale));
   }
-  stage_tensor(smem + lay.W0, net.W[0], H * PINN_N_IN);
-  stage_tensor(smem + lay.b0, net.b[0], H);
-  for (int l = 1; l < L; ++l) stage_tensor(smem + lay.b[l], net.b[l], H);
-  stage_tensor(smem + lay.bv0, net.bv0, H / 2);
+  stage_tensor_scaled(smem + lay.W0, net.W[0], H * PINN_N_IN, kTanhArg);
+  stage_tensor_scaled(smem + lay.b0, net.b[0], H, kTanhArg);
+  for (int l = 1; l < L; ++l) stage_tensor_scaled(smem + lay.b[l], net.b[l], H, kTanhArg);
+  stage_tensor_scaled(smem + lay.bv0, net.bv0, H / 2, kTanhArg);
   stage_tensor(smem + lay.bp, net.bp, 1);
-  stage_tensor(smem + lay.Wv1, net.Wv1, (H / 4) * (H / 2));
-  stage_tensor(smem + lay.bv1, net.bv1, H / 4);
+  stage_tensor_scaled(smem + lay.Wv1, net.Wv1, (H / 4) * (H / 2), kTanhArg * wscale);
+  stage_tensor_scaled(smem + lay.bv1, net.bv1, H / 4, kTanhArg);
   stage_tensor(smem + lay.Wv2, net.Wv2, H / 4);
   stage_tensor(smem + lay.bv2, net.bv2, 1);
   tc::fence_proxy_async();
@@ -128,6 +142,21 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
   const uint32_t idesc64 = tc::make_idesc_tf32(kTcTile, H), idesc48 = tc::make_idesc_tf32(kTcTile, kHeadN);
   const bool issuer_warp = (warp & 7) == 0;
   uint32_t phase = 0;
+
+  // activations t[0..8) of columns c0.. -> masked (or rescaled) -> split -> A planes
+  auto stage8 = [&](const KeepSrc<INJ>& ks, bool active, uint32_t layer, int c0, const float (&t)[8]) {
+    float v[8];
+    if (active) {
+      bool k[8];
+      ks.get8(dp, layer, static_cast<uint32_t>(c0), layer * H, k);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = k[q] ? t[q] : 0.f;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = t[q] * inact;
+    }
+    tc::store_split8_fast(a_hi, a_lo, LBO_A, row, c0, v);
+  };
 
   // ---------------------------------------------------------------- tiles of this group
   const int64_t n_tiles = (n + kTcTile - 1) / kTcTile;
@@ -156,26 +185,28 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
         float z = b0[j];
         z = fmaf(w0.x, xr[0], z); z = fmaf(w0.y, xr[1], z); z = fmaf(w0.z, xr[2], z); z = fmaf(w0.w, xr[3], z);
         z = fmaf(w1.x, xr[4], z); z = fmaf(w1.y, xr[5], z); z = fmaf(w1.z, xr[6], z); z = fmaf(w1.w, xr[7], z);
-        a0[j] = tanh_act(z);
+        a0[j] = tanh_pre(z);
       }
     }
 
     float mean = 0.f, m2 = 0.f, slv = 0.f;
     const bool do_eval = MC && out.pred_mean != nullptr;
     const int n_pass = MC ? T + (do_eval ? 1 : 0) : 1;
+    const uint64_t sg = static_cast<uint64_t>(dp.sample_offset + s);
     for (int pi = 0; pi < n_pass; ++pi) {
       const bool eval_pass = MC && do_eval && pi == 0;
       const int t = MC ? (do_eval ? pi - 1 : pi) : 0;
-      DropCtx dc = make_ctx(dp, s, t, Dm, !eval_pass, valid);
+      // dropout is active on this pass?  (injected masks: tail rows of the last tile have no mask row)
+      const bool active = drop_on && !eval_pass && (!INJ || valid);
+      KeepSrc<INJ> ks;
+      ks.s_lo = static_cast<uint32_t>(sg); ks.s_hi = static_cast<uint32_t>(sg >> 32);
+      ks.pass = static_cast<uint32_t>(dp.pass_offset + t);
+      ks.mrow = INJ ? dp.masks + (static_cast<size_t>(t) * dp.mask_n + (valid ? s : 0)) * Dm : nullptr;
       // ---- stage layer-0 activations (masked) as the first A operand
 #pragma unroll
       for (int g = 0; g < HH; g += 8) {
-        float m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
-        if (dc.active) drop8(dc, 0u, cb + g, 0u, m);
-        tc::store_split4(a_hi, a_lo, LBO_A, row, (cb + g) / 4,
-                         make_float4(a0[g] * m[0], a0[g + 1] * m[1], a0[g + 2] * m[2], a0[g + 3] * m[3]));
-        tc::store_split4(a_hi, a_lo, LBO_A, row, (cb + g) / 4 + 1,
-                         make_float4(a0[g + 4] * m[4], a0[g + 5] * m[5], a0[g + 6] * m[6], a0[g + 7] * m[7]));
+        const float t8[8] = {a0[g], a0[g + 1], a0[g + 2], a0[g + 3], a0[g + 4], a0[g + 5], a0[g + 6], a0[g + 7]};
+        stage8(ks, active, 0u, cb + g, t8);
       }
       // ---- hidden layers on the tensor cores
       for (int l = 1; l < L; ++l) {
@@ -203,13 +234,12 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
         tc::tmem_wait_ld();
 #pragma unroll
         for (int g = 0; g < HH; g += 8) {
-          float m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
-          if (dc.active) drop8(dc, static_cast<uint32_t>(l), cb + g, static_cast<uint32_t>(l * H), m);
-          float v[8];
+          const float4 bA = *reinterpret_cast<const float4*>(bl + g), bB = *reinterpret_cast<const float4*>(bl + g + 4);
+          const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+          float t8[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) v[q] = tanh_act(z[g + q] + bl[g + q]) * m[q];
-          tc::store_split4(a_hi, a_lo, LBO_A, row, (cb + g) / 4, make_float4(v[0], v[1], v[2], v[3]));
-          tc::store_split4(a_hi, a_lo, LBO_A, row, (cb + g) / 4 + 1, make_float4(v[4], v[5], v[6], v[7]));
+          for (int q = 0; q < 8; ++q) t8[q] = tanh_pre(fmaf(z[g + q], kTanhArg, bb[q]));
+          stage8(ks, active, static_cast<uint32_t>(l), cb + g, t8);
         }
       }
       // ---- heads: [Wv0; Wp] in one N = 48 MMA
@@ -239,12 +269,22 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
         const float* bv0 = smem + lay.bv0;
 #pragma unroll
         for (int g = 0; g < HH; g += 8) {
-          float m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
-          if (dc.active) drop8(dc, static_cast<uint32_t>(L), g, static_cast<uint32_t>(L * H), m);
+          const float4 bA = *reinterpret_cast<const float4*>(bv0 + g), bB = *reinterpret_cast<const float4*>(bv0 + g + 4);
+          const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+          float t8[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) v0[g + q] = tanh_act(v0[g + q] + bv0[g + q]) * m[q];
+          for (int q = 0; q < 8; ++q) t8[q] = tanh_pre(fmaf(v0[g + q], kTanhArg, bb[q]));
+          if (active) {
+            bool k[8];
+            ks.get8(dp, static_cast<uint32_t>(L), static_cast<uint32_t>(g), static_cast<uint32_t>(L * H), k);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v0[g + q] = k[q] ? t8[q] : 0.f;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v0[g + q] = t8[q] * inact;
+          }
         }
-        // tail of the variance head on CUDA cores: 32 -> 16 (tanh) -> 1
+        // tail of the variance head on CUDA cores: 32 -> 16 (tanh) -> 1   (Wv1, bv1 pre-scaled)
         float vraw = smem[lay.bv2];
         const float* Wv1 = smem + lay.Wv1;
         const float* bv1 = smem + lay.bv1;
@@ -258,7 +298,7 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
             acc = ffma2(make_float2(w.x, w.y), make_float2(v0[4 * i4], v0[4 * i4 + 1]), acc);
             acc2 = ffma2(make_float2(w.z, w.w), make_float2(v0[4 * i4 + 2], v0[4 * i4 + 3]), acc2);
           }
-          const float a1 = tanh_act(((acc.x + acc.y) + (acc2.x + acc2.y)) + bv1[k]);
+          const float a1 = tanh_pre(((acc.x + acc.y) + (acc2.x + acc2.y)) + bv1[k]);
           vraw = fmaf(Wv2[k], a1, vraw);
         }
         const float lv = logvar_from_v(vraw);
@@ -310,16 +350,17 @@ int launch_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, 
   const int64_t tiles = (n + kTcTile - 1) / kTcTile;
   int64_t want = (tiles + nwg - 1) / nwg;
   const int grid = static_cast<int>(want < sm_count() ? (want > 0 ? want : 1) : sm_count());
+  const bool inj = dp.p > 0.f && dp.masks != nullptr;
+  auto go = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    kern<<<grid, 256 * nwg, smem, st>>>(*net, lay, x, n, T, dp, out);
+    return cudaSuccess;
+  };
   cudaError_t e;
-  if (mc) {
-    e = cudaFuncSetAttribute(mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) { *err = static_cast<int>(e); return -1; }
-    mlp_tc_kernel<true><<<grid, 256 * nwg, smem, st>>>(*net, lay, x, n, T, dp, out);
-  } else {
-    e = cudaFuncSetAttribute(mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) { *err = static_cast<int>(e); return -1; }
-    mlp_tc_kernel<false><<<grid, 256 * nwg, smem, st>>>(*net, lay, x, n, T, dp, out);
-  }
+  if (mc) e = inj ? go(mlp_tc_kernel<true, true>) : go(mlp_tc_kernel<true, false>);
+  else e = inj ? go(mlp_tc_kernel<false, true>) : go(mlp_tc_kernel<false, false>);
+  if (e != cudaSuccess) { *err = static_cast<int>(e); return -1; }
   *err = static_cast<int>(cudaGetLastError());
   return *err == 0 ? 1 : -1;
 }

@@ -58,6 +58,7 @@ struct WgradArgs {
   const float* x; int64_t n; int L;
   BwdScratch sc;
   float* partial;          // [grid][lay.total]
+  float act_scale;         // dropout scale 1/(1-p) missing from the stored trunk activations (K2a)
 };
 
 PINN_D void cp_async16(float* dst_smem, const float* src_gmem) {
@@ -287,7 +288,7 @@ wgrad_kernel(WgradArgs a, ParamLayout lay) {
 #pragma unroll
     for (int p = 0; p < 8; ++p)
 #pragma unroll
-      for (int q = 0; q < 8; ++q) part[base + (j0 + p) * 64 + k0 + q] = acc[8 * p + q];
+      for (int q = 0; q < 8; ++q) part[base + (j0 + p) * 64 + k0 + q] = acc[8 * p + q] * a.act_scale;
   }
   if (tid < 128) {
 #pragma unroll
@@ -298,7 +299,7 @@ wgrad_kernel(WgradArgs a, ParamLayout lay) {
   }
   if (e0 < 64 * L) part[lay.offb[e0 >> 6] + (e0 & 63)] = aB[0];
   if (e1 < 64 * L) part[lay.offb[e1 >> 6] + (e1 & 63)] = aB[1];
-  if (tid < 64) part[lay.offWp + tid] = aP;
+  if (tid < 64) part[lay.offWp + tid] = aP * a.act_scale;
   else if (tid < 80) part[lay.offWv2 + tid - 64] = aP;
   else if (tid < 112) part[lay.offbv0 + tid - 80] = aP;
   else if (tid < 128) part[lay.offbv1 + tid - 112] = aP;
@@ -349,18 +350,20 @@ PINN_D void wprefetch(float4 (&w)[4], const float* __restrict__ src, const float
     w[it] = v;
   }
 }
-PINN_D void wcommit_rows(float* hi, float* lo, const float4 (&w)[4], int t256) {
+// `c` = the dropout scale 1/(1-p), folded into every plane (see mlp_tc.cu): masked activations and
+// masked deltas are then plain selects.
+PINN_D void wcommit_rows(float* hi, float* lo, const float4 (&w)[4], int t256, float c) {
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const int idx = t256 + 256 * it;
-    tc::store_split4(hi, lo, 64 * 16, idx & 63, idx >> 6, w[it]);
+    tc::store_split4(hi, lo, 64 * 16, idx & 63, idx >> 6, make_float4(w[it].x * c, w[it].y * c, w[it].z * c, w[it].w * c));
   }
 }
-PINN_D void wcommit_transposed(float* hi, float* lo, const float4 (&w)[4], int t256) {
+PINN_D void wcommit_transposed(float* hi, float* lo, const float4 (&w)[4], int t256, float c) {
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const int idx = t256 + 256 * it, j = idx & 63, kc = idx >> 6;
-    const float vv[4] = {w[it].x, w[it].y, w[it].z, w[it].w};
+    const float vv[4] = {w[it].x * c, w[it].y * c, w[it].z * c, w[it].w * c};
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const float h = tc::tf32_hi(vv[r]);
@@ -378,9 +381,12 @@ struct TcbArgs {
   double* loss_partial;     // [2 * grid][4]
 };
 
-template <int L>
+// Trunk activations are written to the scratch (and staged as MMA operands) as  keep ? tanh : 0,
+// WITHOUT the dropout scale: the scale lives in the weight planes here and is applied once to the
+// finished dW sums in K2b.  The variance head's CUDA-core tail keeps scaled activations.
+template <int L, bool INJ>
 __global__ void __launch_bounds__(512, 1)
-mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
+mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropParams dp, TcbArgs a) {
   constexpr int H = kBH, HH = 32;
   constexpr uint32_t LBO_A = kBTile * 16;
   extern __shared__ __align__(1024) float smem[];
@@ -395,13 +401,15 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
   if (tid == 0) { tc::mbar_init(&mbar[0], 1); tc::mbar_init(&mbar[1], 1); tc::fence_mbar_init(); }
   __syncwarp();
   if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 128); tc::tmem_relinquish(); }
-  stage_tensor(smem + lay.W0, net.W[0], H * PINN_N_IN);
-  stage_tensor(smem + lay.b0, net.b[0], H);
-  for (int l = 1; l < L; ++l) stage_tensor(smem + lay.b[l], net.b[l], H);
-  stage_tensor(smem + lay.bv0, net.bv0, 32);
+  const bool drop_on = dp.p > 0.f;
+  const float wscale = drop_on ? dp.scale : 1.0f;
+  stage_tensor_scaled(smem + lay.W0, net.W[0], H * PINN_N_IN, kTanhArg);    // tanh_pre arguments (common.cuh)
+  stage_tensor_scaled(smem + lay.b0, net.b[0], H, kTanhArg);
+  for (int l = 1; l < L; ++l) stage_tensor_scaled(smem + lay.b[l], net.b[l], H, kTanhArg);
+  stage_tensor_scaled(smem + lay.bv0, net.bv0, 32, kTanhArg);
   stage_tensor(smem + lay.bp, net.bp, 1);
   stage_tensor(smem + lay.Wv1, net.Wv1, 16 * 32);
-  stage_tensor(smem + lay.bv1, net.bv1, 16);
+  stage_tensor_scaled(smem + lay.bv1, net.bv1, 16, kTanhArg);
   stage_tensor(smem + lay.Wv2, net.Wv2, 16);
   stage_tensor(smem + lay.bv2, net.bv2, 1);
   tc::fence_before_sync();
@@ -441,16 +449,20 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
     __syncwarp();
     tc::fence_after_sync();
   };
-  auto store_pn8 = [&](int c0, const float* v) {   // 8 consecutive columns of this thread's row
-    tc::store_split4(pn_hi, pn_lo, LBO_A, row, c0 / 4, make_float4(v[0], v[1], v[2], v[3]));
-    tc::store_split4(pn_hi, pn_lo, LBO_A, row, c0 / 4 + 1, make_float4(v[4], v[5], v[6], v[7]));
+  auto store_pn8 = [&](int c0, const float (&v)[8]) {   // 8 consecutive columns of this thread's row
+    tc::store_split8_fast(pn_hi, pn_lo, LBO_A, row, c0, v);
   };
 
   const int64_t n_tiles = (a.n + kBTile - 1) / kBTile;
   for (int64_t tile = static_cast<int64_t>(blockIdx.x) * 2 + grp; tile < n_tiles; tile += static_cast<int64_t>(gridDim.x) * 2) {
     const int64_t s = tile * kBTile + row;
     const bool valid = s < a.n;
-    const DropCtx dc = make_ctx(dp, s, 0, Dm, true, valid);
+    const bool active = drop_on && (!INJ || valid);     // injected masks: tail rows of the last tile have no mask row
+    const uint64_t sg = static_cast<uint64_t>(dp.sample_offset + s);
+    KeepSrc<INJ> ks;
+    ks.s_lo = static_cast<uint32_t>(sg); ks.s_hi = static_cast<uint32_t>(sg >> 32);
+    ks.pass = static_cast<uint32_t>(dp.pass_offset);
+    ks.mrow = INJ ? dp.masks + static_cast<size_t>(valid ? s : 0) * Dm : nullptr;
     uint32_t kb[L + 1];      // keep bits of this thread's 32 columns, per dropout layer (bit q = column cb + q)
     float4 wpre[4];
     wprefetch(wpre, net.W[1], nullptr, H, t256);
@@ -470,8 +482,8 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
       kb[0] = 0u;
 #pragma unroll 1
       for (int g = 0; g < HH; g += 8) {     // rolled (code size): 8 columns per trip
-        float m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
-        if (dc.active) drop8(dc, 0u, cb + g, 0u, m);
+        bool k[8] = {true, true, true, true, true, true, true, true};
+        if (active) ks.get8(dp, 0u, static_cast<uint32_t>(cb + g), 0u, k);
         float v[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -480,8 +492,8 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
           float z = b0[g + q];
           z = fmaf(w0.x, xr[0], z); z = fmaf(w0.y, xr[1], z); z = fmaf(w0.z, xr[2], z); z = fmaf(w0.w, xr[3], z);
           z = fmaf(w1.x, xr[4], z); z = fmaf(w1.y, xr[5], z); z = fmaf(w1.z, xr[6], z); z = fmaf(w1.w, xr[7], z);
-          v[q] = tanh_act(z) * m[q];
-          kb[0] |= (m[q] != 0.f ? 1u : 0u) << (g + q);
+          v[q] = k[q] ? tanh_pre(z) : 0.f;
+          kb[0] |= (k[q] ? 1u : 0u) << (g + q);
         }
         store_pn8(cb + g, v);
         if (valid) {
@@ -492,7 +504,7 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
     }
 #pragma unroll 1
     for (int l = 1; l < L; ++l) {       // rolled: one copy of the layer body keeps the kernel inside the I-cache
-      wcommit_rows(b_hi, b_lo, wpre, t256);
+      wcommit_rows(b_hi, b_lo, wpre, t256, wscale);
       run_mma(H * 16, idesc64, [&] {
         if (l + 1 < L) wprefetch(wpre, net.W[l + 1], nullptr, H, t256);
         else wprefetch(wpre, net.Wv0, net.Wp, 32, t256);
@@ -504,13 +516,15 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
         float z[8];
         tc::tmem_ld8(d_lane + cb + g, z);
         tc::tmem_wait_ld();
-        float m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
-        if (dc.active) drop8(dc, static_cast<uint32_t>(l), cb + g, static_cast<uint32_t>(l * H), m);
+        bool k[8] = {true, true, true, true, true, true, true, true};
+        if (active) ks.get8(dp, static_cast<uint32_t>(l), static_cast<uint32_t>(cb + g), static_cast<uint32_t>(l * H), k);
+        const float4 bA = *reinterpret_cast<const float4*>(bl + g), bB = *reinterpret_cast<const float4*>(bl + g + 4);
+        const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
         float v[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          v[q] = tanh_act(z[q] + bl[g + q]) * m[q];
-          bits |= (m[q] != 0.f ? 1u : 0u) << (g + q);
+          v[q] = k[q] ? tanh_pre(fmaf(z[q], kTanhArg, bb[q])) : 0.f;
+          bits |= (k[q] ? 1u : 0u) << (g + q);
         }
         store_pn8(cb + g, v);
         if (valid) {
@@ -521,7 +535,7 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
       kb[l] = bits;
     }
     // ---- heads: rows 0..31 = Wv0, row 32 = Wp, rows 33.. = 0 (N = 48 of the 64 staged rows are read)
-    wcommit_rows(b_hi, b_lo, wpre, t256);
+    wcommit_rows(b_hi, b_lo, wpre, t256, wscale);
     run_mma(H * 16, idesc48, [&] { wprefetch(wpre, net.Wv0, net.Wp, 32, t256); });
     float du = 0.f;
     float dzv0[HH];                      // half 0: d z of the variance head's first layer; half 1: unused
@@ -536,12 +550,12 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
       const float* bv0 = smem + lay.bv0;
 #pragma unroll
       for (int g = 0; g < HH; g += 8) {
-        float m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
-        if (dc.active) drop8(dc, static_cast<uint32_t>(L), g, static_cast<uint32_t>(L * H), m);
+        bool k[8] = {true, true, true, true, true, true, true, true};
+        if (active) ks.get8(dp, static_cast<uint32_t>(L), static_cast<uint32_t>(g), static_cast<uint32_t>(L * H), k);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          v0[g + q] = tanh_act(v0[g + q] + bv0[g + q]) * m[q];
-          kb[L] |= (m[q] != 0.f ? 1u : 0u) << (g + q);
+          v0[g + q] = k[q] ? tanh_pre(fmaf(v0[g + q], kTanhArg, bv0[g + q])) * wscale : 0.f;   // scaled, as K2b expects
+          kb[L] |= (k[q] ? 1u : 0u) << (g + q);
         }
       }
       const float* Wv1 = smem + lay.Wv1;
@@ -558,7 +572,7 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
           acc = ffma2(make_float2(w.x, w.y), make_float2(v0[4 * i4], v0[4 * i4 + 1]), acc);
           acc2 = ffma2(make_float2(w.z, w.w), make_float2(v0[4 * i4 + 2], v0[4 * i4 + 3]), acc2);
         }
-        v1[k] = tanh_act(((acc.x + acc.y) + (acc2.x + acc2.y)) + bv1[k]);
+        v1[k] = tanh_pre(fmaf((acc.x + acc.y) + (acc2.x + acc2.y), kTanhArg, bv1[k]));
         vraw = fmaf(Wv2[k], v1[k], vraw);
       }
       const float lv = logvar_from_v(vraw);
@@ -596,8 +610,8 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
         }
 #pragma unroll
       for (int i = 0; i < HH; ++i) {
-        const float av = v0[i] * (dc.active ? dc.keep : 1.0f);
-        const float mk = dc.active ? (((kb[L] >> i) & 1u) ? dc.scale : 0.f) : 1.0f;
+        const float av = v0[i] * (drop_on ? dp.keep : 1.0f);
+        const float mk = ((kb[L] >> i) & 1u) ? wscale : 0.f;
         dzv0[i] = dzv0[i] * mk * (1.0f - av * av);
       }
       if (valid) {
@@ -619,13 +633,16 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
     // A operand = [dz_v0 (32 cols) | du | 0 ...]; B = ([Wv0; Wp])^T  ->  d a_{L-1}
     if (half == 0) {
 #pragma unroll
-      for (int g = 0; g < HH; g += 8) store_pn8(g, dzv0 + g);
+      for (int g = 0; g < HH; g += 8) {
+        const float d8[8] = {dzv0[g], dzv0[g + 1], dzv0[g + 2], dzv0[g + 3], dzv0[g + 4], dzv0[g + 5], dzv0[g + 6], dzv0[g + 7]};
+        store_pn8(g, d8);
+      }
       tc::store_split4(pn_hi, pn_lo, LBO_A, row, 8, make_float4(du, 0.f, 0.f, 0.f));
     } else {
 #pragma unroll
       for (int kc = 9; kc < 16; ++kc) tc::store_split4(pn_hi, pn_lo, LBO_A, row, kc, make_float4(0.f, 0.f, 0.f, 0.f));
     }
-    wcommit_transposed(b_hi, b_lo, wpre, t256);
+    wcommit_transposed(b_hi, b_lo, wpre, t256, wscale);
 #pragma unroll 1
     for (int l = L - 1; l >= 0; --l) {
       float4 apre[HH / 4];       // this thread's masked activations of layer l, prefetched during the MMA
@@ -636,7 +653,6 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
         if (l > 0) wprefetch(wpre, net.W[l], nullptr, H, t256);
       });
       const uint32_t kbl = kb[l];
-      const float keep = dc.active ? dc.keep : 1.0f;
 #pragma unroll
       for (int g = 0; g < HH; g += 8) {
         float z[8], dz[8];
@@ -645,18 +661,15 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, DropParams dp, TcbArgs a) {
         const float aa[8] = {apre[g / 4].x, apre[g / 4].y, apre[g / 4].z, apre[g / 4].w,
                              apre[g / 4 + 1].x, apre[g / 4 + 1].y, apre[g / 4 + 1].z, apre[g / 4 + 1].w};
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float ak = aa[q] * keep;
-          const float mk = dc.active ? (((kbl >> (g + q)) & 1u) ? dc.scale : 0.f) : 1.0f;
-          dz[q] = z[q] * mk * (1.0f - ak * ak);
-        }
+        for (int q = 0; q < 8; ++q)    // z already carries the dropout scale (folded into W^T); dropped units have a = 0
+          dz[q] = ((kbl >> (g + q)) & 1u) ? z[q] * fmaf(-aa[q], aa[q], 1.0f) : 0.f;
         if (valid) {
           float4* o = reinterpret_cast<float4*>(a.sc.del[l] + s * H + cb + g);
           o[0] = make_float4(dz[0], dz[1], dz[2], dz[3]); o[1] = make_float4(dz[4], dz[5], dz[6], dz[7]);
         }
         if (l > 0) store_pn8(cb + g, dz);
       }
-      if (l > 0) wcommit_transposed(b_hi, b_lo, wpre, t256);
+      if (l > 0) wcommit_transposed(b_hi, b_lo, wpre, t256, wscale);
     }
   }
   // ---------------------------------------------------------------- loss partials per group
@@ -743,11 +756,13 @@ int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropPa
   a.sc = carve_scratch(reinterpret_cast<float*>(ws + p.off_scratch), n, L);
   a.loss_partial = reinterpret_cast<double*>(ws);
   TcbLayout tl = make_tcb_layout(L);
+  const bool inj = dp.p > 0.f && dp.masks != nullptr;
 #define LAUNCH_A(LL)                                                                                              \
   {                                                                                                               \
-    PINN_CUDA_TRY(cudaFuncSetAttribute(mlp_tc_bwd_kernel<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+    auto kern = inj ? mlp_tc_bwd_kernel<LL, true> : mlp_tc_bwd_kernel<LL, false>;                                 \
+    PINN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                         \
                                        static_cast<int>(p.smem_a)));                                              \
-    mlp_tc_bwd_kernel<LL><<<p.grid_a, 512, p.smem_a, st>>>(*net, tl, dp, a);                                      \
+    kern<<<p.grid_a, 512, p.smem_a, st>>>(*net, tl, dp, a);                                                       \
   }
   switch (L) {
     case 2: LAUNCH_A(2) break;
@@ -759,6 +774,7 @@ int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropPa
   PINN_CUDA_TRY(cudaGetLastError());
   WgradArgs w{};
   w.x = x; w.n = n; w.L = L; w.sc = a.sc;
+  w.act_scale = dp.p > 0.f ? dp.scale : 1.0f;
   w.partial = reinterpret_cast<float*>(ws + p.off_partial);
 #define LAUNCH_B(LL)                                                                                              \
   {                                                                                                               \

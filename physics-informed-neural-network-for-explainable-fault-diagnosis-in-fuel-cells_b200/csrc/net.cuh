@@ -67,6 +67,9 @@ struct Weights {
 __device__ inline void stage_tensor(float* dst, const float* src, int count) {
   for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = __ldg(src + i);
 }
+__device__ inline void stage_tensor_scaled(float* dst, const float* src, int count, float c) {
+  for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = __ldg(src + i) * c;
+}
 __device__ inline void stage_weights(float* arena, const pinn_net_t& net, const ParamLayout& lay) {
   const int H = lay.H;
   for (int l = 0; l < lay.L; ++l) {

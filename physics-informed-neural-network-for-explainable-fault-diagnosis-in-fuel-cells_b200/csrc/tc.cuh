@@ -154,6 +154,23 @@ PINN_D void store_split4(float* hi_plane, float* lo_plane, uint32_t lbo_bytes, i
   *reinterpret_cast<float4*>(lo_plane + off) = l;
 }
 
+// Activations are finite and far from overflow, so their tf32 rounding needs no NaN/Inf
+// guard: add half an ulp (bit 12) to the magnitude and clear the low 13 bits -- two integer
+// ops instead of the four cvt.rna.tf32 expands to; identical result (ties away from zero).
+PINN_D float tf32_hi_fast(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+// Eight consecutive columns c0..c0+7 (c0 % 8 == 0) of row `row` into the hi and lo planes.
+PINN_D void store_split8_fast(float* hi_plane, float* lo_plane, uint32_t lbo_bytes, int row, int c0, const float (&v)[8]) {
+  float h[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) h[q] = tf32_hi_fast(v[q]);
+  const size_t off = (static_cast<size_t>(c0 >> 2) * lbo_bytes + static_cast<size_t>(row) * 16) / sizeof(float);
+  const size_t off2 = off + lbo_bytes / sizeof(float);
+  *reinterpret_cast<float4*>(hi_plane + off) = make_float4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<float4*>(lo_plane + off) = make_float4(v[0] - h[0], v[1] - h[1], v[2] - h[2], v[3] - h[3]);
+  *reinterpret_cast<float4*>(hi_plane + off2) = make_float4(h[4], h[5], h[6], h[7]);
+  *reinterpret_cast<float4*>(lo_plane + off2) = make_float4(v[4] - h[4], v[5] - h[5], v[6] - h[6], v[7] - h[7]);
+}
+
 // Issue the 3xTF32 product  D[M x N] = A[M x 64] * B[N x 64]^T  from one thread: 24 MMAs
 // back to back.  Descriptors are built once by the caller; stepping one K = 8 slab adds
 // 2*LBO (in 16-byte units) to the start-address field, so each MMA costs one add.
