@@ -21,15 +21,15 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str = OUT, objdir: str | None = None) -> str:
+    if not force and not _stale() and out == OUT:
         return OUT
     from concurrent.futures import ThreadPoolExecutor
 
     nvcc = os.environ.get("NVCC", "nvcc")
-    objdir = os.path.join(HERE, "build")
+    objdir = objdir or os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + list(extra_flags)
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
@@ -45,12 +45,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"b200pinn: nvcc failed on {src}")
         if verbose:
             print(res.stderr)
-    link = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT,
+    link = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out,
                            *[obj for _, obj, _ in results]], capture_output=True, text=True)
     if link.returncode != 0:
         sys.stderr.write(link.stdout + link.stderr)
         raise RuntimeError("b200pinn: link failed")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

@@ -54,6 +54,9 @@ struct Philox {
   // with compile-time constants, so every key is a c[0x0][..] operand of the LOP3 that consumes
   // it: no key-schedule adds and no key registers in the hot loop.
   static PINN_HD uint4 gen_rk(const uint32_t (&rk)[20], uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+#if defined(PINN_ABL) && (PINN_ABL & 2)     // ablation build (profiles/ablate_mc.py): no Philox rounds
+    return make_uint4(c0 * M0 + c3, c1 ^ (c3 * M1), c2 + c3 * W0, c3 * W1 ^ rk[0]);
+#endif
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
       uint32_t hi0, lo0, hi1, lo1;
@@ -206,6 +209,9 @@ PINN_HD float tanh_act(float x) {
 // absolute error (<= ~3e-7); saturates cleanly (2^a -> inf gives rcp -> 0 -> 1; 2^a -> 0 gives -1).
 constexpr float kTanhArg = 2.8853900817779268f;
 PINN_D float tanh_pre(float a) {       // a = kTanhArg * x
+#if defined(PINN_ABL) && (PINN_ABL & 1)     // ablation build: no MUFU
+  return a * 0.25f;
+#endif
   float e, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));

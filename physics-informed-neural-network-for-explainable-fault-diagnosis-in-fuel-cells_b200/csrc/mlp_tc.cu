@@ -45,10 +45,7 @@ PINN_HD TcLayout make_tc_layout(int L, int nwg) {
   for (int l = 1; l < L; ++l) { t.b_hi[l] = o; o += kTcH * kTcH; t.b_lo[l] = o; o += kTcH * kTcH; }
   t.h_hi = o; o += kHeadN * kTcH;
   t.h_lo = o; o += kHeadN * kTcH;
-  for (int g = 0; g < 2; ++g) {
-    t.a_hi[g] = o; if (g < nwg) o += kTcTile * kTcH;
-    t.a_lo[g] = o; if (g < nwg) o += kTcTile * kTcH;
-  }
+  for (int g = 0; g < 2; ++g) t.a_hi[g] = t.a_lo[g] = 0;      // activations live in tensor memory
   t.W0 = o; o += kTcH * PINN_N_IN;
   t.b0 = o; o += kTcH;
   for (int l = 1; l < L; ++l) { t.b[l] = o; o += kTcH; }
@@ -64,6 +61,17 @@ PINN_HD TcLayout make_tc_layout(int L, int nwg) {
 
 // named barrier for one 256-thread group (ids 1, 2; id 0 is __syncthreads)
 PINN_D void grp_sync(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); }
+
+#ifdef PINN_TIMELINE
+// Debug build (profiles/timeline_mc.py): clock stamps of CTA 0 / group 0, warps 0 (half 0) and 4 (half 1).
+__device__ long long g_tl[2][64][8];
+#define TL(slot, k) do { if (tl_on && tl_i < 64) g_tl[half][tl_i][k] = clock64(); } while (0)
+#else
+#define TL(slot, k) do {} while (0)
+#endif
+
+PINN_D void bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+PINN_D void bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // MC = true : eval pass (if pred_mean) + T dropout passes with Welford.   MC = false: one pass.
 // INJ = true: keep decisions come from an injected mask tensor (parity runs) instead of Philox.
@@ -103,7 +111,7 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
     tc::fence_mbar_init();
   }
   __syncwarp();
-  if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 128); tc::tmem_relinquish(); }
+  if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
   auto scaled4 = [](float4 v, float c) { return make_float4(v.x * c, v.y * c, v.z * c, v.w * c); };
   for (int l = 1; l < L; ++l)
     for (int idx = tid; idx < H * (H / 4); idx += blockDim.x) {
@@ -134,14 +142,20 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
 
   const uint32_t d_tmem = tmem_base_s + static_cast<uint32_t>(grp * 64);           // this group's 64 columns
   const uint32_t d_lane = d_tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16); // this warp's 32 lanes
-  float* a_hi = smem + lay.a_hi[grp];
-  float* a_lo = smem + lay.a_lo[grp];
-  const uint64_t a_hi_d = tc::make_desc(tc::smem_u32(a_hi), LBO_A, 128), a_lo_d = tc::make_desc(tc::smem_u32(a_lo), LBO_A, 128);
+  // Tensor-memory map (512 columns, one CTA per SM): accumulators [64 g, +64); activation planes of
+  // group g: hi [128 + 128 g, +64), lo [192 + 128 g, +64); tail hand-over [384 + 16 g, +16).
+  const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const uint32_t x_lane = tmem_base_s + static_cast<uint32_t>(384 + grp * 16) + lane_sel;
+  const uint32_t a_hi_t = tmem_base_s + static_cast<uint32_t>(128 + grp * 128), a_lo_t = a_hi_t + 64u;
   const uint64_t h_hi_d = tc::make_desc(tc::smem_u32(smem + lay.h_hi), LBO_H, 128);
   const uint64_t h_lo_d = tc::make_desc(tc::smem_u32(smem + lay.h_lo), LBO_H, 128);
   const uint32_t idesc64 = tc::make_idesc_tf32(kTcTile, H), idesc48 = tc::make_idesc_tf32(kTcTile, kHeadN);
   const bool issuer_warp = (warp & 7) == 0;
   uint32_t phase = 0;
+#ifdef PINN_TIMELINE
+  const bool tl_on = blockIdx.x == 0 && grp == 0 && (warp & 3) == 0 && (tid & 31) == 0;
+  int tl_i = 0;
+#endif
 
   // activations t[0..8) of columns c0.. -> masked (or rescaled) -> split -> A planes
   auto stage8 = [&](const KeepSrc<INJ>& ks, bool active, uint32_t layer, int c0, const float (&t)[8]) {
@@ -155,7 +169,11 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
 #pragma unroll
       for (int q = 0; q < 8; ++q) v[q] = t[q] * inact;
     }
-    tc::store_split8_fast(a_hi, a_lo, LBO_A, row, c0, v);
+    float h[8], lo[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { h[q] = tc::tf32_hi_fast(v[q]); lo[q] = v[q] - h[q]; }
+    tc::tmem_st8(a_hi_t + lane_sel + static_cast<uint32_t>(c0), h);
+    tc::tmem_st8(a_lo_t + lane_sel + static_cast<uint32_t>(c0), lo);
   };
 
   // ---------------------------------------------------------------- tiles of this group
@@ -210,28 +228,33 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
       }
       // ---- hidden layers on the tensor cores
       for (int l = 1; l < L; ++l) {
-        tc::fence_proxy_async();
+        TL(tl_i, 0);
+        tc::tmem_wait_st();
         tc::fence_before_sync();
         grp_sync(grp);
+        TL(tl_i, 1);
         if (issuer_warp) {
           const uint64_t b_hi_d = tc::make_desc(tc::smem_u32(smem + lay.b_hi[l]), LBO_B, 128);
           const uint64_t b_lo_d = tc::make_desc(tc::smem_u32(smem + lay.b_lo[l]), LBO_B, 128);
           if (tc::elect_one()) {
             tc::fence_after_sync();
-            tc::issue_3xtf32<H>(d_tmem, a_hi_d, a_lo_d, LBO_A, b_hi_d, b_lo_d, LBO_B, idesc64);
+            tc::issue_3xtf32_ts<H>(d_tmem, a_hi_t, a_lo_t, b_hi_d, b_lo_d, LBO_B, idesc64);
             tc::umma_commit(&mbar[grp]);
           }
           __syncwarp();
         }
+        TL(tl_i, 2);
         tc::mbar_wait(&mbar[grp], phase);
         phase ^= 1u;
         __syncwarp();
         tc::fence_after_sync();
+        TL(tl_i, 3);
         const float* bl = smem + lay.b[l] + cb;
         float z[HH];
         tc::tmem_ld16(d_lane + cb, z);
         tc::tmem_ld16(d_lane + cb + 16, z + 16);
         tc::tmem_wait_ld();
+        TL(tl_i, 4);
 #pragma unroll
         for (int g = 0; g < HH; g += 8) {
           const float4 bA = *reinterpret_cast<const float4*>(bl + g), bB = *reinterpret_cast<const float4*>(bl + g + 4);
@@ -241,15 +264,19 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
           for (int q = 0; q < 8; ++q) t8[q] = tanh_pre(fmaf(z[g + q], kTanhArg, bb[q]));
           stage8(ks, active, static_cast<uint32_t>(l), cb + g, t8);
         }
+        TL(tl_i, 5);
+#ifdef PINN_TIMELINE
+        ++tl_i;
+#endif
       }
       // ---- heads: [Wv0; Wp] in one N = 48 MMA
-      tc::fence_proxy_async();
+      tc::tmem_wait_st();
       tc::fence_before_sync();
       grp_sync(grp);
       if (issuer_warp) {
         if (tc::elect_one()) {
           tc::fence_after_sync();
-          tc::issue_3xtf32<H>(d_tmem, a_hi_d, a_lo_d, LBO_A, h_hi_d, h_lo_d, LBO_H, idesc48);
+          tc::issue_3xtf32_ts<H>(d_tmem, a_hi_t, a_lo_t, h_hi_d, h_lo_d, LBO_H, idesc48);
           tc::umma_commit(&mbar[grp]);
         }
         __syncwarp();
@@ -258,17 +285,19 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
       phase ^= 1u;
       __syncwarp();
       tc::fence_after_sync();
-      if (half == 0) {   // warp-uniform: warps 0-3 of the group finish the sample
-        float v0[HH];
-        float zz[16];
-        tc::tmem_ld16(d_lane, v0);
-        tc::tmem_ld16(d_lane + 16, v0 + 16);
-        tc::tmem_ld16(d_lane + 32, zz);
-        tc::tmem_wait_ld();
-        const float u = zz[0] + smem[lay.bp];
-        const float* bv0 = smem + lay.bv0;
+      {
+        // Variance head, split between the row's two threads: each activates 16 of the 32 head units
+        // and forms its share of the sixteen 32 -> 16 sums; thread (row, 1) parks its share in spare
+        // TMEM columns of the row's lane and moves on to the next pass, thread (row, 0) adds the two
+        // shares and finishes the sample.  Hand-over = named barrier (producers arrive, consumers sync).
+        float v0[16], part[16];
+        float u = 0.f;
+        tc::tmem_ld16(d_lane + 16 * half, v0);
+        if (half == 0) { float zz[8]; tc::tmem_ld8(d_lane + 32, zz); tc::tmem_wait_ld(); u = zz[0] + smem[lay.bp]; }
+        else tc::tmem_wait_ld();
+        const float* bv0 = smem + lay.bv0 + 16 * half;
 #pragma unroll
-        for (int g = 0; g < HH; g += 8) {
+        for (int g = 0; g < 16; g += 8) {
           const float4 bA = *reinterpret_cast<const float4*>(bv0 + g), bB = *reinterpret_cast<const float4*>(bv0 + g + 4);
           const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
           float t8[8];
@@ -276,7 +305,7 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
           for (int q = 0; q < 8; ++q) t8[q] = tanh_pre(fmaf(v0[g + q], kTanhArg, bb[q]));
           if (active) {
             bool k[8];
-            ks.get8(dp, static_cast<uint32_t>(L), static_cast<uint32_t>(g), static_cast<uint32_t>(L * H), k);
+            ks.get8(dp, static_cast<uint32_t>(L), static_cast<uint32_t>(16 * half + g), static_cast<uint32_t>(L * H), k);
 #pragma unroll
             for (int q = 0; q < 8; ++q) v0[g + q] = k[q] ? t8[q] : 0.f;
           } else {
@@ -284,33 +313,48 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
             for (int q = 0; q < 8; ++q) v0[g + q] = t8[q] * inact;
           }
         }
-        // tail of the variance head on CUDA cores: 32 -> 16 (tanh) -> 1   (Wv1, bv1 pre-scaled)
-        float vraw = smem[lay.bv2];
-        const float* Wv1 = smem + lay.Wv1;
-        const float* bv1 = smem + lay.bv1;
-        const float* Wv2 = smem + lay.Wv2;
-#pragma unroll 4
-        for (int k = 0; k < H / 4; ++k) {
+        const float* Wv1 = smem + lay.Wv1 + 16 * half;     // pre-scaled by 2 log2(e) / (1-p)
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
           float2 acc = make_float2(0.f, 0.f), acc2 = acc;
 #pragma unroll
-          for (int i4 = 0; i4 < HH / 4; ++i4) {
+          for (int i4 = 0; i4 < 4; ++i4) {
             const float4 w = *reinterpret_cast<const float4*>(Wv1 + k * HH + 4 * i4);
             acc = ffma2(make_float2(w.x, w.y), make_float2(v0[4 * i4], v0[4 * i4 + 1]), acc);
             acc2 = ffma2(make_float2(w.z, w.w), make_float2(v0[4 * i4 + 2], v0[4 * i4 + 3]), acc2);
           }
-          const float a1 = tanh_pre(((acc.x + acc.y) + (acc2.x + acc2.y)) + bv1[k]);
-          vraw = fmaf(Wv2[k], a1, vraw);
+          part[k] = (acc.x + acc.y) + (acc2.x + acc2.y);
         }
-        const float lv = logvar_from_v(vraw);
-        if (!MC) {
-          if (valid) { out.u[s] = u; out.s[s] = lv; }
-        } else if (eval_pass) {
-          if (valid) out.pred_mean[s] = u;
+        if (half == 1) {
+          tc::tmem_st16(x_lane, part);
+          tc::tmem_wait_st();
+          tc::fence_before_sync();
+          bar_arrive_n(3 + grp, 256);
         } else {
-          const float d = u - mean;
-          mean += d / static_cast<float>(t + 1);
-          m2 = fmaf(d, u - mean, m2);
-          slv += lv;
+          bar_sync_n(3 + grp, 256);
+          tc::fence_after_sync();
+          float p1[16];
+          tc::tmem_ld16(x_lane, p1);
+          tc::tmem_wait_ld();
+          float vraw = smem[lay.bv2];
+          const float* bv1 = smem + lay.bv1;
+          const float* Wv2 = smem + lay.Wv2;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const float a1 = tanh_pre((part[k] + p1[k]) + bv1[k]);
+            vraw = fmaf(Wv2[k], a1, vraw);
+          }
+          const float lv = logvar_from_v(vraw);
+          if (!MC) {
+            if (valid) { out.u[s] = u; out.s[s] = lv; }
+          } else if (eval_pass) {
+            if (valid) out.pred_mean[s] = u;
+          } else {
+            const float d = u - mean;
+            mean += d / static_cast<float>(t + 1);
+            m2 = fmaf(d, u - mean, m2);
+            slv += lv;
+          }
         }
       }
     }
@@ -325,10 +369,11 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem_base_s, 128);
+  if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
 }
 
 static int g_tc_enabled = 1;
+
 
 // Launch helper used by pinn_mlp_fwd / pinn_mc_dropout.  Returns 1 if the TC path took the
 // call, 0 if the shape is not covered (caller falls through to the FFMA kernels), <0 / >1 on error.
@@ -367,6 +412,11 @@ int launch_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, 
 
 }  // namespace pinn
 
+#ifdef PINN_TIMELINE
+extern "C" int pinn_debug_timeline(long long* host_out) {
+  return static_cast<int>(cudaMemcpyFromSymbol(host_out, pinn::g_tl, sizeof(pinn::g_tl)));
+}
+#endif
 // Test / ablation switch: 0 routes the 64-wide net through the FFMA kernels as well.
 extern "C" int pinn_set_tensor_core_path(int enable) {
   int prev = pinn::g_tc_enabled;

@@ -101,6 +101,24 @@ PINN_D void tmem_ld8(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 32 lanes x 32 bit, 16 consecutive columns: thread i of the warp writes TMEM lane (lane_base + i)
+PINN_D void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+PINN_D void tmem_st8(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                 "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+PINN_D void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 PINN_D void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------ UMMA
@@ -132,6 +150,18 @@ PINN_D void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t 
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with the A operand in TENSOR MEMORY (lane = row, one 32-bit column per k): the tensor core
+// then fetches only B from shared memory.  With both operands in shared memory an M128 N64 K8 tf32
+// MMA pulls 6 KB through the 128 B/clk shared-memory port -- 48 clk against a 32 clk math floor --
+// and those reads compete with the epilogue's own LDS/STS (profiles/README.md, timeline_mc).
+PINN_D void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on `bar` once every MMA issued so far by this thread has completed (implies
 // tcgen05.fence::before_thread_sync).
 PINN_D void umma_commit(uint64_t* bar) {
@@ -157,7 +187,11 @@ PINN_D void store_split4(float* hi_plane, float* lo_plane, uint32_t lbo_bytes, i
 // Activations are finite and far from overflow, so their tf32 rounding needs no NaN/Inf
 // guard: add half an ulp (bit 12) to the magnitude and clear the low 13 bits -- two integer
 // ops instead of the four cvt.rna.tf32 expands to; identical result (ties away from zero).
+#ifdef PINN_TF32_TRUNC
+PINN_D float tf32_hi_fast(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+#else
 PINN_D float tf32_hi_fast(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+#endif
 // Eight consecutive columns c0..c0+7 (c0 % 8 == 0) of row `row` into the hi and lo planes.
 PINN_D void store_split8_fast(float* hi_plane, float* lo_plane, uint32_t lbo_bytes, int row, int c0, const float (&v)[8]) {
   float h[8];
@@ -178,6 +212,10 @@ template <int K>
 PINN_D void issue_3xtf32(uint32_t d_tmem, uint64_t a_hi0, uint64_t a_lo0, uint32_t lbo_a, uint64_t b_hi0, uint64_t b_lo0,
                          uint32_t lbo_b, uint32_t idesc) {
   const uint64_t a_step = (2u * lbo_a) >> 4, b_step = (2u * lbo_b) >> 4;
+#if defined(PINN_ABL) && (PINN_ABL & 4)     // ablation build: one MMA instead of 24
+  umma_tf32(d_tmem, a_hi0, b_hi0, idesc, 0u);
+  return;
+#endif
 #pragma unroll
   for (int term = 0; term < 3; ++term) {      // small terms first: lo*hi, hi*lo, then hi*hi
     const uint64_t a = term == 0 ? a_lo0 : a_hi0;
@@ -185,6 +223,21 @@ PINN_D void issue_3xtf32(uint32_t d_tmem, uint64_t a_hi0, uint64_t a_lo0, uint32
 #pragma unroll
     for (int k8 = 0; k8 < K / 8; ++k8)        // one MMA consumes K = 8 tf32 = two 16-byte chunks
       umma_tf32(d_tmem, a + k8 * a_step, b + k8 * b_step, idesc, (term | k8) != 0 ? 1u : 0u);
+  }
+}
+
+// 3xTF32 product with A (hi and lo planes, K columns each) in tensor memory.
+template <int K>
+PINN_D void issue_3xtf32_ts(uint32_t d_tmem, uint32_t a_hi_t, uint32_t a_lo_t, uint64_t b_hi0, uint64_t b_lo0, uint32_t lbo_b,
+                            uint32_t idesc) {
+  const uint64_t b_step = (2u * lbo_b) >> 4;
+#pragma unroll
+  for (int term = 0; term < 3; ++term) {      // small terms first: lo*hi, hi*lo, then hi*hi
+    const uint32_t a = term == 0 ? a_lo_t : a_hi_t;
+    const uint64_t b = term == 1 ? b_lo0 : b_hi0;
+#pragma unroll
+    for (int k8 = 0; k8 < K / 8; ++k8)
+      umma_tf32_ts(d_tmem, a + 8u * k8, b + k8 * b_step, idesc, (term | k8) != 0 ? 1u : 0u);
   }
 }
 
