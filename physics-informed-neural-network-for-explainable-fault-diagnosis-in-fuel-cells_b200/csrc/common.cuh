@@ -167,6 +167,13 @@ PINN_HD DropCtx make_ctx(const DropParams& dp, int64_t s_local, int64_t pass_loc
 // Keep decisions of 8 consecutive units [j0, j0+8) of dropout layer `layer` for one (sample, pass):
 // Philox mode draws the same 16-bit fields as drop8() (common.cuh), compared without extracting
 // them: the high field is kept iff  w >= thresh<<16,  the low field iff  (w<<16) >= thresh<<16.
+// keep decisions of the eight 16-bit fields of one Philox block (field 2q = low half of word q)
+PINN_HD void keep8_from(const uint4& r, uint32_t th, bool (&k)[8]) {
+  k[0] = (r.x << 16) >= th; k[1] = r.x >= th;
+  k[2] = (r.y << 16) >= th; k[3] = r.y >= th;
+  k[4] = (r.z << 16) >= th; k[5] = r.z >= th;
+  k[6] = (r.w << 16) >= th; k[7] = r.w >= th;
+}
 template <bool INJ>
 struct KeepSrc {
   uint32_t s_lo, s_hi, pass;
@@ -177,11 +184,7 @@ struct KeepSrc {
       for (int q = 0; q < 8; ++q) k[q] = mrow[unit_base + j0 + q] != 0;
     } else {
       const uint4 r = Philox::gen_rk(dp.rk, s_lo, s_hi, pass, (layer << 16) | (j0 >> 3));
-      const uint32_t th = dp.thresh_hi;
-      k[0] = (r.x << 16) >= th; k[1] = r.x >= th;
-      k[2] = (r.y << 16) >= th; k[3] = r.y >= th;
-      k[4] = (r.z << 16) >= th; k[5] = r.z >= th;
-      k[6] = (r.w << 16) >= th; k[7] = r.w >= th;
+      keep8_from(r, dp.thresh_hi, k);
     }
   }
 };

@@ -158,6 +158,42 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
 #endif
 
   // activations t[0..8) of columns c0.. -> masked (or rescaled) -> split -> A planes
+  auto store8 = [&](int c0, const float (&v)[8]) {        // split -> this row's hi / lo columns in tensor memory
+    float h[8], lo[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { h[q] = tc::tf32_hi_fast(v[q]); lo[q] = v[q] - h[q]; }
+    tc::tmem_st8(a_hi_t + lane_sel + static_cast<uint32_t>(c0), h);
+    tc::tmem_st8(a_lo_t + lane_sel + static_cast<uint32_t>(c0), lo);
+  };
+  // Philox blocks are drawn AHEAD of the MMA wait that precedes their use (they depend on nothing the
+  // tensor core produces), so the integer work fills the group's otherwise idle wait window.
+  auto draw4 = [&](uint4 (&r)[4], const KeepSrc<INJ>& ks, uint32_t pass, uint32_t layer, int c0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      r[c] = Philox::gen_rk(dp.rk, ks.s_lo, ks.s_hi, pass, (layer << 16) | static_cast<uint32_t>((c0 >> 3) + c));
+#pragma unroll
+    for (int c = 0; c < 4; ++c) asm volatile("" : "+r"(r[c].x), "+r"(r[c].y), "+r"(r[c].z), "+r"(r[c].w));   // pin before the wait
+  };
+  auto stage8r = [&](const uint4& r, const KeepSrc<INJ>& ks, bool active, uint32_t layer, int c0, const float (&t)[8]) {
+    float v[8];
+    if (INJ || !active) {
+      if (active) {
+        bool k[8];
+        ks.get8(dp, layer, static_cast<uint32_t>(c0), layer * H, k);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = k[q] ? t[q] : 0.f;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = t[q] * inact;
+      }
+    } else {
+      bool k[8];
+      keep8_from(r, dp.thresh_hi, k);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = k[q] ? t[q] : 0.f;
+    }
+    store8(c0, v);
+  };
   auto stage8 = [&](const KeepSrc<INJ>& ks, bool active, uint32_t layer, int c0, const float (&t)[8]) {
     float v[8];
     if (active) {
@@ -169,11 +205,7 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
 #pragma unroll
       for (int q = 0; q < 8; ++q) v[q] = t[q] * inact;
     }
-    float h[8], lo[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) { h[q] = tc::tf32_hi_fast(v[q]); lo[q] = v[q] - h[q]; }
-    tc::tmem_st8(a_hi_t + lane_sel + static_cast<uint32_t>(c0), h);
-    tc::tmem_st8(a_lo_t + lane_sel + static_cast<uint32_t>(c0), lo);
+    store8(c0, v);
   };
 
   // ---------------------------------------------------------------- tiles of this group
@@ -211,6 +243,12 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
     const bool do_eval = MC && out.pred_mean != nullptr;
     const int n_pass = MC ? T + (do_eval ? 1 : 0) : 1;
     const uint64_t sg = static_cast<uint64_t>(dp.sample_offset + s);
+    uint4 r0[4] = {};        // draws of the coming pass's layer-0 staging
+    if (!INJ && drop_on && !do_eval) {
+      KeepSrc<INJ> k0;
+      k0.s_lo = static_cast<uint32_t>(sg); k0.s_hi = static_cast<uint32_t>(sg >> 32); k0.pass = 0; k0.mrow = nullptr;
+      draw4(r0, k0, static_cast<uint32_t>(dp.pass_offset), 0u, cb);
+    }
     for (int pi = 0; pi < n_pass; ++pi) {
       const bool eval_pass = MC && do_eval && pi == 0;
       const int t = MC ? (do_eval ? pi - 1 : pi) : 0;
@@ -224,7 +262,7 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
 #pragma unroll
       for (int g = 0; g < HH; g += 8) {
         const float t8[8] = {a0[g], a0[g + 1], a0[g + 2], a0[g + 3], a0[g + 4], a0[g + 5], a0[g + 6], a0[g + 7]};
-        stage8(ks, active, 0u, cb + g, t8);
+        stage8r(r0[g / 8], ks, active, 0u, cb + g, t8);
       }
       // ---- hidden layers on the tensor cores
       for (int l = 1; l < L; ++l) {
@@ -244,6 +282,8 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
           __syncwarp();
         }
         TL(tl_i, 2);
+        uint4 rl[4] = {};
+        if (!INJ && active) draw4(rl, ks, ks.pass, static_cast<uint32_t>(l), cb);
         tc::mbar_wait(&mbar[grp], phase);
         phase ^= 1u;
         __syncwarp();
@@ -262,7 +302,7 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
           float t8[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) t8[q] = tanh_pre(fmaf(z[g + q], kTanhArg, bb[q]));
-          stage8(ks, active, static_cast<uint32_t>(l), cb + g, t8);
+          stage8r(rl[g / 8], ks, active, static_cast<uint32_t>(l), cb + g, t8);
         }
         TL(tl_i, 5);
 #ifdef PINN_TIMELINE
@@ -281,6 +321,15 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
         }
         __syncwarp();
       }
+      uint4 rv[2] = {};
+      if (!INJ && active) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          rv[c] = Philox::gen_rk(dp.rk, ks.s_lo, ks.s_hi, ks.pass, (static_cast<uint32_t>(L) << 16) | static_cast<uint32_t>(2 * half + c));
+#pragma unroll
+        for (int c = 0; c < 2; ++c) asm volatile("" : "+r"(rv[c].x), "+r"(rv[c].y), "+r"(rv[c].z), "+r"(rv[c].w));
+      }
+      if (!INJ && drop_on && pi + 1 < n_pass) draw4(r0, ks, static_cast<uint32_t>(dp.pass_offset + t + 1), 0u, cb);
       tc::mbar_wait(&mbar[grp], phase);
       phase ^= 1u;
       __syncwarp();
@@ -305,7 +354,8 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
           for (int q = 0; q < 8; ++q) t8[q] = tanh_pre(fmaf(v0[g + q], kTanhArg, bb[q]));
           if (active) {
             bool k[8];
-            ks.get8(dp, static_cast<uint32_t>(L), static_cast<uint32_t>(16 * half + g), static_cast<uint32_t>(L * H), k);
+            if (INJ) ks.get8(dp, static_cast<uint32_t>(L), static_cast<uint32_t>(16 * half + g), static_cast<uint32_t>(L * H), k);
+            else keep8_from(rv[g / 8], dp.thresh_hi, k);
 #pragma unroll
             for (int q = 0; q < 8; ++q) v0[g + q] = k[q] ? t8[q] : 0.f;
           } else {
