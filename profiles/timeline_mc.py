@@ -23,18 +23,19 @@ else:
     for _ in range(3):
         b200pinn.mc_dropout_device(model.dnn, xd, T_PASSES, P_MC, seed=1234)
     torch.cuda.synchronize()
-    buf = (ctypes.c_longlong * (2 * 64 * 8))()
+    buf = (ctypes.c_longlong * (3 * 64 * 8))()
     lib = abi.lib()
     lib.pinn_debug_timeline.argtypes = [ctypes.c_void_p]
     assert lib.pinn_debug_timeline(buf) == 0
     import numpy as np
-    t = np.array(buf, dtype=np.int64).reshape(2, 64, 8)
+    t = np.array(buf, dtype=np.int64).reshape(3, 64, 8)
     t0 = t[0, 0, 0]
-    names = ["pre-fence", "post-bar", "post-issue", "post-mbar", "post-ldtm", "post-epi"]
+    names = ["pre-signal", "post-signal", "post-draw", "post-done", "post-ldtm", "post-epi"]
     for half in (0, 1):
         print(f"half {half}:  phase  start   " + "  ".join(f"d({n})" for n in names[1:]) + "   gap-to-next")
         for i in range(2, 26):
             r = t[half, i]
             d = [r[k] - r[k - 1] for k in range(1, 6)]
             gap = t[half, i + 1, 0] - r[5]
-            print(f"   {i:3d} {r[0] - t0:9d}   " + "  ".join(f"{x:10d}" for x in d) + f"   {gap:8d}")
+            print(f"   {i:3d} {r[0] - t0:9d}   " + "  ".join(f"{x:10d}" for x in d) + f"   {gap:8d}"
+                  + (f"   mma: wake@{t[2, i, 0] - t0} (+{t[2, i, 0] - r[1]} after this thread's signal), issue {t[2, i, 1] - t[2, i, 0]}, done seen +{r[3] - t[2, i, 1]}" if half == 0 else ""))
