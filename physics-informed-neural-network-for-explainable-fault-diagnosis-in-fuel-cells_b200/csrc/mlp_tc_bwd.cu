@@ -318,7 +318,7 @@ constexpr int kBPlaneFloats = 16 * 1040 / 4;    // 16 chunks x 1040 B (padded LB
 PINN_HD TcbLayout make_tcb_layout(int L) {
   TcbLayout t;
   int o = 0;
-  for (int g = 0; g < 2; ++g) { t.pn_hi[g] = o; o += kBTile * kBH; t.pn_lo[g] = o; o += kBTile * kBH; }
+  for (int g = 0; g < 2; ++g) t.pn_hi[g] = t.pn_lo[g] = 0;     // activation / delta planes live in tensor memory
   for (int g = 0; g < 2; ++g) { t.b_hi[g] = o; o += kBPlaneFloats; t.b_lo[g] = o; o += kBPlaneFloats; }
   t.W0 = o; o += kBH * PINN_N_IN;
   t.b0 = o; o += kBH;
@@ -400,7 +400,7 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
 
   if (tid == 0) { tc::mbar_init(&mbar[0], 1); tc::mbar_init(&mbar[1], 1); tc::fence_mbar_init(); }
   __syncwarp();
-  if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 128); tc::tmem_relinquish(); }
+  if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
   const bool drop_on = dp.p > 0.f;
   const float wscale = drop_on ? dp.scale : 1.0f;
   stage_tensor_scaled(smem + lay.W0, net.W[0], H * PINN_N_IN, kTanhArg);    // tanh_pre arguments (common.cuh)
@@ -418,11 +418,12 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
 
   const uint32_t d_tmem = tmem_base_s + static_cast<uint32_t>(grp * 64);
   const uint32_t d_lane = d_tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-  float* pn_hi = smem + lay.pn_hi[grp];
-  float* pn_lo = smem + lay.pn_lo[grp];
+  // A operand (activations forward, deltas backward) in tensor memory: hi plane [128 + 128 g, +64), lo plane +64
+  // (lane = sample row), see mlp_tc.cu.
+  const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const uint32_t a_hi_t = tmem_base_s + static_cast<uint32_t>(128 + grp * 128), a_lo_t = a_hi_t + 64u;
   float* b_hi = smem + lay.b_hi[grp];
   float* b_lo = smem + lay.b_lo[grp];
-  const uint64_t a_hi_d = tc::make_desc(tc::smem_u32(pn_hi), LBO_A, 128), a_lo_d = tc::make_desc(tc::smem_u32(pn_lo), LBO_A, 128);
   const uint32_t bh_u = tc::smem_u32(b_hi), bl_u = tc::smem_u32(b_lo);
   const uint32_t idesc64 = tc::make_idesc_tf32(kBTile, 64), idesc48 = tc::make_idesc_tf32(kBTile, 48);
   const bool issuer_warp = (warp & 7) == 0;
@@ -431,6 +432,7 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
 
   // publish PN + B (generic-proxy writes) to the async proxy, run one 3xTF32 product, wait for it
   auto run_mma = [&](uint32_t lbo_b, uint32_t idesc, auto&& prefetch) {
+    tc::tmem_wait_st();
     tc::fence_proxy_async();
     tc::fence_before_sync();
     grp_sync256(grp);
@@ -438,7 +440,7 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
       const uint64_t bhd = tc::make_desc(bh_u, lbo_b, 128), bld = tc::make_desc(bl_u, lbo_b, 128);
       if (tc::elect_one()) {
         tc::fence_after_sync();
-        tc::issue_3xtf32<64>(d_tmem, a_hi_d, a_lo_d, LBO_A, bhd, bld, lbo_b, idesc);
+        tc::issue_3xtf32_ts<64>(d_tmem, a_hi_t, a_lo_t, bhd, bld, lbo_b, idesc);
         tc::umma_commit(&mbar[grp]);
       }
       __syncwarp();
@@ -450,7 +452,11 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
     tc::fence_after_sync();
   };
   auto store_pn8 = [&](int c0, const float (&v)[8]) {   // 8 consecutive columns of this thread's row
-    tc::store_split8_fast(pn_hi, pn_lo, LBO_A, row, c0, v);
+    float h[8], lo[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { h[q] = tc::tf32_hi_fast(v[q]); lo[q] = v[q] - h[q]; }
+    tc::tmem_st8(a_hi_t + lane_sel + static_cast<uint32_t>(c0), h);
+    tc::tmem_st8(a_lo_t + lane_sel + static_cast<uint32_t>(c0), lo);
   };
 
   const int64_t n_tiles = (a.n + kBTile - 1) / kBTile;
@@ -637,10 +643,12 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
         const float d8[8] = {dzv0[g], dzv0[g + 1], dzv0[g + 2], dzv0[g + 3], dzv0[g + 4], dzv0[g + 5], dzv0[g + 6], dzv0[g + 7]};
         store_pn8(g, d8);
       }
-      tc::store_split4(pn_hi, pn_lo, LBO_A, row, 8, make_float4(du, 0.f, 0.f, 0.f));
+      const float d8[8] = {du, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      store_pn8(32, d8);
     } else {
+      const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int kc = 9; kc < 16; ++kc) tc::store_split4(pn_hi, pn_lo, LBO_A, row, kc, make_float4(0.f, 0.f, 0.f, 0.f));
+      for (int c0 = 40; c0 < 64; c0 += 8) store_pn8(c0, z8);
     }
     wcommit_transposed(b_hi, b_lo, wpre, t256, wscale);
 #pragma unroll 1
@@ -692,7 +700,7 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
     for (int wq = 0; wq < 4; ++wq) t += lred[g][wq][k];
     a.loss_partial[(static_cast<size_t>(blockIdx.x) * 2 + g) * 4 + k] = t;
   }
-  if (warp == 0) tc::tmem_dealloc(tmem_base_s, 128);
+  if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
 }
 
 __global__ void grad_reduce2_kernel(const float* __restrict__ partial, const double* __restrict__ loss_partial, int nblk,
