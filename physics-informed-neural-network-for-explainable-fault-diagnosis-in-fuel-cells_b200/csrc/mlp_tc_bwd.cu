@@ -310,7 +310,9 @@ wgrad_kernel(WgradArgs a, ParamLayout lay) {
 // ------------------------------------------------------------------------------- K2a
 struct TcbLayout {   // float offsets into dynamic shared memory
   int pn_hi[2], pn_lo[2];      // per group: activation / delta planes, 128 rows x 64 cols
-  int b_hi[2], b_lo[2];        // per group: one layer's weight planes (K-major; padded LBO for transposes)
+  int b_hi[2], b_lo[2];        // streaming mode (L > 3), per group: one layer's weight planes
+  int wf_hi[PINN_MAX_HIDDEN + 1], wf_lo[PINN_MAX_HIDDEN + 1];   // resident mode: forward planes of W_l (l >= 1); index L = heads
+  int wt_hi[PINN_MAX_HIDDEN + 1], wt_lo[PINN_MAX_HIDDEN + 1];   // resident mode: transposed planes (dgrad)
   int W0, b0, b[PINN_MAX_HIDDEN], bv0, bp, Wv1, bv1, Wv2, bv2;
   int total;
 };
@@ -319,7 +321,16 @@ PINN_HD TcbLayout make_tcb_layout(int L) {
   TcbLayout t;
   int o = 0;
   for (int g = 0; g < 2; ++g) t.pn_hi[g] = t.pn_lo[g] = 0;     // activation / delta planes live in tensor memory
-  for (int g = 0; g < 2; ++g) { t.b_hi[g] = o; o += kBPlaneFloats; t.b_lo[g] = o; o += kBPlaneFloats; }
+  for (int l = 0; l <= PINN_MAX_HIDDEN; ++l) t.wf_hi[l] = t.wf_lo[l] = t.wt_hi[l] = t.wt_lo[l] = 0;
+  for (int g = 0; g < 2; ++g) t.b_hi[g] = t.b_lo[g] = 0;
+  if (L <= 3) {     // every weight plane resident: L x 66 KB
+    for (int l = 1; l <= L; ++l) {
+      t.wf_hi[l] = o; o += kBH * kBH; t.wf_lo[l] = o; o += kBH * kBH;
+      t.wt_hi[l] = o; o += kBPlaneFloats; t.wt_lo[l] = o; o += kBPlaneFloats;
+    }
+  } else {
+    for (int g = 0; g < 2; ++g) { t.b_hi[g] = o; o += kBPlaneFloats; t.b_lo[g] = o; o += kBPlaneFloats; }
+  }
   t.W0 = o; o += kBH * PINN_N_IN;
   t.b0 = o; o += kBH;
   for (int l = 0; l < PINN_MAX_HIDDEN; ++l) t.b[l] = 0;
@@ -374,6 +385,33 @@ PINN_D void wcommit_transposed(float* hi, float* lo, const float4 (&w)[4], int t
   }
 }
 
+// Resident mode (L <= 3): all forward and transposed planes are built once per CTA by all threads.
+PINN_D void stage_plane_rows(float* hi, float* lo, const float* __restrict__ src, const float* __restrict__ extra_row, int J, float c) {
+  for (int idx = threadIdx.x; idx < 64 * 16; idx += blockDim.x) {
+    const int j = idx & 63, kc = idx >> 6;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < J) v = __ldg(reinterpret_cast<const float4*>(src + j * 64) + kc);
+    else if (j == J && extra_row != nullptr) v = __ldg(reinterpret_cast<const float4*>(extra_row) + kc);
+    tc::store_split4(hi, lo, 64 * 16, j, kc, make_float4(v.x * c, v.y * c, v.z * c, v.w * c));
+  }
+}
+PINN_D void stage_plane_transposed(float* hi, float* lo, const float* __restrict__ src, const float* __restrict__ extra_row, int J, float c) {
+  for (int idx = threadIdx.x; idx < 64 * 16; idx += blockDim.x) {
+    const int j = idx & 63, kc = idx >> 6;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < J) v = __ldg(reinterpret_cast<const float4*>(src + j * 64) + kc);
+    else if (j == J && extra_row != nullptr) v = __ldg(reinterpret_cast<const float4*>(extra_row) + kc);
+    const float vv[4] = {v.x * c, v.y * c, v.z * c, v.w * c};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float h = tc::tf32_hi(vv[r]);
+      const size_t off = (static_cast<size_t>(j >> 2) * kLboT + static_cast<size_t>(4 * kc + r) * 16 + (j & 3) * 4) / 4;
+      hi[off] = h;
+      lo[off] = vv[r] - h;
+    }
+  }
+}
+
 struct TcbArgs {
   const float* x; int64_t n;
   const float* grad_u; const float* grad_s; const float* y; float inv_n_global;
@@ -388,7 +426,7 @@ template <int L, bool INJ>
 __global__ void __launch_bounds__(512, 1)
 mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropParams dp, TcbArgs a) {
   constexpr int H = kBH, HH = 32;
-  constexpr uint32_t LBO_A = kBTile * 16;
+  constexpr bool RES = L <= 3;     // weight planes resident in shared memory (else re-staged per phase)
   extern __shared__ __align__(1024) float smem[];
   __shared__ __align__(8) uint64_t mbar[2];
   __shared__ uint32_t tmem_base_s;
@@ -412,6 +450,15 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
   stage_tensor_scaled(smem + lay.bv1, net.bv1, 16, kTanhArg);
   stage_tensor(smem + lay.Wv2, net.Wv2, 16);
   stage_tensor(smem + lay.bv2, net.bv2, 1);
+  if constexpr (RES) {
+    for (int l = 1; l < L; ++l) {
+      stage_plane_rows(smem + lay.wf_hi[l], smem + lay.wf_lo[l], net.W[l], nullptr, H, wscale);
+      stage_plane_transposed(smem + lay.wt_hi[l], smem + lay.wt_lo[l], net.W[l], nullptr, H, wscale);
+    }
+    stage_plane_rows(smem + lay.wf_hi[L], smem + lay.wf_lo[L], net.Wv0, net.Wp, 32, wscale);
+    stage_plane_transposed(smem + lay.wt_hi[L], smem + lay.wt_lo[L], net.Wv0, net.Wp, 32, wscale);
+    tc::fence_proxy_async();
+  }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -431,13 +478,14 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
   double l_nll = 0.0, l_abs = 0.0, l_mse = 0.0, l_cnt = 0.0;
 
   // publish PN + B (generic-proxy writes) to the async proxy, run one 3xTF32 product, wait for it
-  auto run_mma = [&](uint32_t lbo_b, uint32_t idesc, auto&& prefetch) {
+  auto run_mma = [&](int res_hi, int res_lo, uint32_t lbo_b, uint32_t idesc, auto&& prefetch) {
+    const uint32_t bh_a = RES ? tc::smem_u32(smem + res_hi) : bh_u, bl_a = RES ? tc::smem_u32(smem + res_lo) : bl_u;
     tc::tmem_wait_st();
     tc::fence_proxy_async();
     tc::fence_before_sync();
     grp_sync256(grp);
     if (issuer_warp) {
-      const uint64_t bhd = tc::make_desc(bh_u, lbo_b, 128), bld = tc::make_desc(bl_u, lbo_b, 128);
+      const uint64_t bhd = tc::make_desc(bh_a, lbo_b, 128), bld = tc::make_desc(bl_a, lbo_b, 128);
       if (tc::elect_one()) {
         tc::fence_after_sync();
         tc::issue_3xtf32_ts<64>(d_tmem, a_hi_t, a_lo_t, bhd, bld, lbo_b, idesc);
@@ -471,7 +519,7 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
     ks.mrow = INJ ? dp.masks + static_cast<size_t>(valid ? s : 0) * Dm : nullptr;
     uint32_t kb[L + 1];      // keep bits of this thread's 32 columns, per dropout layer (bit q = column cb + q)
     float4 wpre[4];
-    wprefetch(wpre, net.W[1], nullptr, H, t256);
+    if constexpr (!RES) wprefetch(wpre, net.W[1], nullptr, H, t256);
     // ============================ forward ============================
     {
       float xr[PINN_N_IN];
@@ -510,10 +558,12 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
     }
 #pragma unroll 1
     for (int l = 1; l < L; ++l) {       // rolled: one copy of the layer body keeps the kernel inside the I-cache
-      wcommit_rows(b_hi, b_lo, wpre, t256, wscale);
-      run_mma(H * 16, idesc64, [&] {
-        if (l + 1 < L) wprefetch(wpre, net.W[l + 1], nullptr, H, t256);
-        else wprefetch(wpre, net.Wv0, net.Wp, 32, t256);
+      if constexpr (!RES) wcommit_rows(b_hi, b_lo, wpre, t256, wscale);
+      run_mma(lay.wf_hi[l], lay.wf_lo[l], H * 16, idesc64, [&] {
+        if constexpr (!RES) {
+          if (l + 1 < L) wprefetch(wpre, net.W[l + 1], nullptr, H, t256);
+          else wprefetch(wpre, net.Wv0, net.Wp, 32, t256);
+        }
       });
       const float* bl = smem + lay.b[l] + cb;
       uint32_t bits = 0u;
@@ -541,8 +591,8 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
       kb[l] = bits;
     }
     // ---- heads: rows 0..31 = Wv0, row 32 = Wp, rows 33.. = 0 (N = 48 of the 64 staged rows are read)
-    wcommit_rows(b_hi, b_lo, wpre, t256, wscale);
-    run_mma(H * 16, idesc48, [&] { wprefetch(wpre, net.Wv0, net.Wp, 32, t256); });
+    if constexpr (!RES) wcommit_rows(b_hi, b_lo, wpre, t256, wscale);
+    run_mma(lay.wf_hi[L], lay.wf_lo[L], H * 16, idesc48, [&] { if constexpr (!RES) wprefetch(wpre, net.Wv0, net.Wp, 32, t256); });
     float du = 0.f;
     float dzv0[HH];                      // half 0: d z of the variance head's first layer; half 1: unused
     kb[L] = 0u;
@@ -650,15 +700,15 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
 #pragma unroll
       for (int c0 = 40; c0 < 64; c0 += 8) store_pn8(c0, z8);
     }
-    wcommit_transposed(b_hi, b_lo, wpre, t256, wscale);
+    if constexpr (!RES) wcommit_transposed(b_hi, b_lo, wpre, t256, wscale);
 #pragma unroll 1
     for (int l = L - 1; l >= 0; --l) {
       float4 apre[HH / 4];       // this thread's masked activations of layer l, prefetched during the MMA
-      run_mma(kLboT, idesc64, [&] {
+      run_mma(lay.wt_hi[l + 1], lay.wt_lo[l + 1], kLboT, idesc64, [&] {
 #pragma unroll
         for (int g4 = 0; g4 < HH / 4; ++g4)
           apre[g4] = valid ? *reinterpret_cast<const float4*>(a.sc.act[l] + s * H + cb + 4 * g4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (l > 0) wprefetch(wpre, net.W[l], nullptr, H, t256);
+        if constexpr (!RES) { if (l > 0) wprefetch(wpre, net.W[l], nullptr, H, t256); }
       });
       const uint32_t kbl = kb[l];
 #pragma unroll
@@ -677,7 +727,7 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
         }
         if (l > 0) store_pn8(cb + g, dz);
       }
-      if (l > 0) wcommit_transposed(b_hi, b_lo, wpre, t256, wscale);
+      if constexpr (!RES) { if (l > 0) wcommit_transposed(b_hi, b_lo, wpre, t256, wscale); }
     }
   }
   // ---------------------------------------------------------------- loss partials per group
