@@ -27,284 +27,346 @@ namespace pinn {
 
 constexpr int kBH = 64, kBTile = 128;
 
-// Global scratch: per-sample rows written by K2a, read by K2b (float offsets per sample).
-struct BwdScratch {
-  float* act[PINN_MAX_HIDDEN];   // masked activations a_l            [n][64]
-  float* del[PINN_MAX_HIDDEN];   // pre-activation deltas dz_l        [n][64]
-  float* av0; float* dv0;        // variance head layer 0             [n][32]
-  float* av1; float* dv1;        // variance head layer 1             [n][16]
-  float* du;  float* dvs;        // d loss / d u, d loss / d v        [n]
+// Global scratch written by K2a and read by K2b: per 128-sample tile a table of ROWS, one row per
+// feature, 128 samples (512 B) per row -- i.e. every array is stored TRANSPOSED.  Two reasons:
+//  * the weight-gradient contraction runs over SAMPLES, so sample-contiguous rows are K-major
+//    tensor-core operands (the plain interleaved layout cannot feed MN-major TF32 operands,
+//    tests/cuda/tc_mn_test.cu);
+//  * a warp of K2a (32 consecutive samples) writes / re-reads one 128-byte line per feature:
+//    fully coalesced.  The former [sample][feature] rows cost 32 sectors per warp access and made
+//    K2a's stores and re-loads 0.48 ms of its 1.23 ms (profiles/README.md, ablate_k2a).
+// Row order inside a tile (L hidden layers, nbig = ceil((L-1)/2) blocks of 128 rows):
+//   [0, 128 nbig)          : deltas of layers 1..L-1, 64 rows each          (A operands "big")
+//   RA + [0, 64)           : deltas of layer 0                               (A operand "small", 128 rows)
+//   RA + [64, 96), +96     : variance-head layer-0 deltas, d loss / d u
+//   RA + [97, 113), +113   : variance-head layer-1 deltas, d loss / d v      (rows 114..127 unused)
+//   RB + 64 l + [0, 64)    : masked activations of layer l (WITHOUT the dropout scale)   (B operands)
+//   RV0 + [0, 32)          : variance-head layer-0 activations (scaled),   RV1 + [0, 16): layer 1
+struct RowMap {
+  int L, nbig, RA, RB, RV0, RV1, rows;
 };
-PINN_HD size_t bwd_scratch_floats_per_sample(int L) { return static_cast<size_t>(L) * 2 * kBH + 2 * 32 + 2 * 16 + 2; }
-
-inline BwdScratch carve_scratch(float* base, int64_t n, int L) {
-  BwdScratch s{};
-  float* p = base;
-  const size_t N = (static_cast<size_t>(n) + 3) & ~static_cast<size_t>(3);   // every array 16-byte aligned (TMA sources)
-  for (int l = 0; l < L; ++l) { s.act[l] = p; p += N * kBH; }
-  for (int l = 0; l < L; ++l) { s.del[l] = p; p += N * kBH; }
-  s.av0 = p; p += N * 32; s.dv0 = p; p += N * 32;
-  s.av1 = p; p += N * 16; s.dv1 = p; p += N * 16;
-  s.du = p; p += N; s.dvs = p; p += N;
-  return s;
+PINN_HD RowMap make_rowmap(int L) {
+  RowMap m;
+  m.L = L;
+  m.nbig = (L - 1 + 1) / 2;
+  m.RA = 128 * m.nbig;
+  m.RB = m.RA + 128;
+  m.RV0 = m.RB + 64 * L;
+  m.RV1 = m.RV0 + 32;
+  m.rows = m.RV1 + 16;
+  return m;
+}
+PINN_HD int row_del(const RowMap& m, int l) { return l == 0 ? m.RA : 64 * (l - 1); }
+PINN_HD int row_act(const RowMap& m, int l) { return m.RB + 64 * l; }
+PINN_HD size_t bwd_scratch_floats(int L, int64_t n) {
+  const size_t tiles = static_cast<size_t>((n + kBTile - 1) / kBTile);
+  return (tiles > 0 ? tiles : 1) * static_cast<size_t>(make_rowmap(L).rows) * kBTile;
 }
 
 // ------------------------------------------------------------------------------- K2b
-// One CTA accumulates every gradient over its samples; thread (jt, kt) of a 16 x 16 grid owns
-// the 4 x 4 block (j0 = 4 jt, k0 = 4 kt) of each 64 x 64 product and sub-blocks of the rest.
-constexpr int kWgS = 16;   // samples per shared-memory stage (two stages in flight)
+// Every weight / bias gradient as ONE accumulation over samples on the tensor cores (3xTF32):
+//   D[m][n] += sum_s A[m][s] * B[n][s],   A = delta rows, B = activation rows + a row of ones
+// (the ones row turns the bias column sums into column 64 / 8 / 32 / 16 of the same product).
+// M is always 128: the rows of several delta arrays are stacked in one A block and each product
+// only reads back the lanes it owns (cross terms are computed and ignored -- an M = 64 MMA costs
+// the same 128-row issue slot).  For L = 3:
+//   big block   = [delta_1 ; delta_2]                x  [a_0 ; 1]  -> lanes   0..63  = dW1, db1
+//                                                     x  [a_1 ; 1]  -> lanes  64..127 = dW2, db2
+//   small block = [delta_0 ; dv0 ; du ; dv1 ; dvs]   x  [x^T ; 1]  -> lanes   0..63  = dW0, db0
+//                                                     x  [a_2 ; 1]  -> lanes  64..96  = dWv0, dbv0, dWp, dbp
+//                                                     x  [av0 ; 1]  -> lanes  97..112 = dWv1, dbv1
+//                                                     x  [av1 ; 1]  -> lane  113      = dWv2, dbv2
+// Accumulators stay in tensor memory for the CTA's whole sample range.  Pipeline: 256 loader
+// threads bring 16-sample stages (64 B per row) from HBM into registers, split them into tf32
+// hi / lo planes (K-major canonical layout, LBO padded so that the 4 x 8 chunk pattern of a warp
+// is bank-conflict free) in one of two shared-memory buffers and arrive on `full`; a dedicated
+// MMA warp issues the stage's products and commits to `done`, which frees the buffer.
+constexpr int kWgStage = 16;                 // samples per stage
+constexpr int kWgLoaders = 256;
+constexpr int kNAct = 80, kNX = 16, kNV0 = 48, kNV1 = 32;     // B-block rows (N of the MMA): data + ones row + zero rows, N % 16 == 0
+PINN_HD constexpr int wg_lbo(int rows) { return (rows + 2) * 16; }     // bytes; (rows + 2) % 8 == 2 for every block used here
+
+struct WgLayout {      // byte offsets of the hi plane of every operand block inside ONE stage buffer; lo plane = hi + plane_bytes
+  int a_big[2], a_small, b_act[PINN_MAX_HIDDEN], b_x, b_v0, b_v1;
+  int plane_bytes, buffer_bytes;
+};
+PINN_HD WgLayout make_wg_layout(int L) {
+  WgLayout w{};
+  const int nbig = (L - 1 + 1) / 2;
+  int o = 0;
+  for (int i = 0; i < 2; ++i) { w.a_big[i] = o; if (i < nbig) o += 4 * wg_lbo(128); }
+  w.a_small = o; o += 4 * wg_lbo(128);
+  for (int l = 0; l < PINN_MAX_HIDDEN; ++l) { w.b_act[l] = o; if (l < L) o += 4 * wg_lbo(kNAct); }
+  w.b_x = o; o += 4 * wg_lbo(kNX);
+  w.b_v0 = o; o += 4 * wg_lbo(kNV0);
+  w.b_v1 = o; o += 4 * wg_lbo(kNV1);
+  w.plane_bytes = o;
+  w.buffer_bytes = 2 * o;
+  return w;
+}
 
 struct WgradArgs {
-  const float* x; int64_t n; int L;
-  BwdScratch sc;
+  const float* x; int64_t n; int64_t n_tiles;
+  const float* rows;       // scratch, [tile][RowMap.rows][128]
   float* partial;          // [grid][lay.total]
   float act_scale;         // dropout scale 1/(1-p) missing from the stored trunk activations (K2a)
 };
 
-PINN_D void cp_async16(float* dst_smem, const float* src_gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst_smem))),
-               "l"(src_gmem) : "memory");
-}
-PINN_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> PINN_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// TMEM columns of the products
+template <int L> struct WgCols {
+  static constexpr int act0 = 0;                   // product against a_l: columns [80 l, 80 l + 80)
+  static constexpr int x = kNAct * L;
+  static constexpr int v0 = x + kNX;
+  static constexpr int v1 = v0 + kNV0;
+  static constexpr int total = v1 + kNV1;
+};
 
-// floats per stage: D[L][S][64], A[L][S][64], X[S][8], DV0[S][32], AV0[S][32], DV1[S][16], AV1[S][16], DU[S], DVS[S]
-PINN_HD constexpr int wg_stage_floats(int L) { return 2 * L * kWgS * 64 + kWgS * (8 + 32 + 32 + 16 + 16 + 2); }
-
-// Issue the asynchronous copies of one stage (rows beyond `cnt` are zero-filled with plain stores).
 template <int L>
-PINN_D void wg_issue_stage(float* st, const WgradArgs& a, int64_t s0, int cnt, int tid) {
-  float* sD = st;
-  float* sA = sD + L * kWgS * 64;
-  float* sX = sA + L * kWgS * 64;
-  float* sDV0 = sX + kWgS * 8;
-  float* sAV0 = sDV0 + kWgS * 32;
-  float* sDV1 = sAV0 + kWgS * 32;
-  float* sAV1 = sDV1 + kWgS * 16;
-  float* sDU = sAV1 + kWgS * 16;
-  float* sDVS = sDU + kWgS;
-  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int l = 0; l < L; ++l)
-    for (int i = tid; i < kWgS * 16; i += blockDim.x) {
-      const int r = i >> 4, c4 = i & 15;
-      float* dD = sD + (l * kWgS + r) * 64 + 4 * c4;
-      float* dA = sA + (l * kWgS + r) * 64 + 4 * c4;
-      if (r < cnt) {
-        cp_async16(dD, a.sc.del[l] + (s0 + r) * 64 + 4 * c4);
-        cp_async16(dA, a.sc.act[l] + (s0 + r) * 64 + 4 * c4);
-      } else {
-        *reinterpret_cast<float4*>(dD) = zero;
-        *reinterpret_cast<float4*>(dA) = zero;
+__global__ void __launch_bounds__(kWgLoaders + 32, 1)
+wgrad_tc_kernel(WgradArgs a, ParamLayout lay, WgLayout wl, RowMap rm) {
+  extern __shared__ __align__(1024) unsigned char wsm[];
+  __shared__ __align__(8) uint64_t full[2], done[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tc::uniform_warp_idx();
+  const bool mma_warp = warp == kWgLoaders / 32;
+  static_assert(WgCols<L>::total <= 512, "TMEM");
+
+  if (tid == 0) {
+    tc::mbar_init(&full[0], kWgLoaders); tc::mbar_init(&full[1], kWgLoaders);
+    tc::mbar_init(&done[0], 1); tc::mbar_init(&done[1], 1);
+    tc::fence_mbar_init();
+  }
+  __syncwarp();
+  if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
+  // constant rows of the B blocks (ones row, zero rows): written once into both buffers, both planes
+  {
+    auto fill = [&](int blk_off, int data_rows, int n_rows) {
+      const int lbo = wg_lbo(n_rows);
+      for (int i = tid; i < 2 * 2 * 4 * (n_rows - data_rows); i += blockDim.x) {
+        const int r = data_rows + i % (n_rows - data_rows), rest = i / (n_rows - data_rows);
+        const int kc = rest & 3, plane = (rest >> 2) & 1, buf = rest >> 3;
+        const float v = (r == data_rows && plane == 0) ? 1.0f : 0.0f;
+        *reinterpret_cast<float4*>(wsm + buf * wl.buffer_bytes + plane * wl.plane_bytes + blk_off + kc * lbo + r * 16) = make_float4(v, v, v, v);
       }
-    }
-  for (int i = tid; i < kWgS * 8; i += blockDim.x) {
-    const int r = i >> 3, c4 = i & 7;
-    if (r < cnt) {
-      cp_async16(sDV0 + r * 32 + 4 * c4, a.sc.dv0 + (s0 + r) * 32 + 4 * c4);
-      cp_async16(sAV0 + r * 32 + 4 * c4, a.sc.av0 + (s0 + r) * 32 + 4 * c4);
-    } else {
-      *reinterpret_cast<float4*>(sDV0 + r * 32 + 4 * c4) = zero;
-      *reinterpret_cast<float4*>(sAV0 + r * 32 + 4 * c4) = zero;
-    }
+    };
+    for (int l = 0; l < L; ++l) fill(wl.b_act[l], 64, kNAct);
+    fill(wl.b_x, 8, kNX);
+    fill(wl.b_v0, 32, kNV0);
+    fill(wl.b_v1, 16, kNV1);
+    // unused A rows (114..127 of the small block; 64..127 of a half-filled big block) only feed lanes nobody reads
   }
-  if (tid < kWgS * 4) {
-    const int r = tid >> 2, c4 = tid & 3;
-    if (r < cnt) {
-      cp_async16(sDV1 + r * 16 + 4 * c4, a.sc.dv1 + (s0 + r) * 16 + 4 * c4);
-      cp_async16(sAV1 + r * 16 + 4 * c4, a.sc.av1 + (s0 + r) * 16 + 4 * c4);
-    } else {
-      *reinterpret_cast<float4*>(sDV1 + r * 16 + 4 * c4) = zero;
-      *reinterpret_cast<float4*>(sAV1 + r * 16 + 4 * c4) = zero;
-    }
-  } else if (tid < kWgS * 4 + kWgS * 2) {
-    const int t = tid - kWgS * 4, r = t >> 1, c4 = t & 1;
-    if (r < cnt) cp_async16(sX + r * 8 + 4 * c4, a.x + (s0 + r) * 8 + 4 * c4);
-    else *reinterpret_cast<float4*>(sX + r * 8 + 4 * c4) = zero;
-  } else if (tid < kWgS * 4 + kWgS * 2 + kWgS) {
-    const int r = tid - kWgS * 6;
-    sDU[r] = r < cnt ? a.sc.du[s0 + r] : 0.f;
-    sDVS[r] = r < cnt ? a.sc.dvs[s0 + r] : 0.f;
-  }
-}
-
-// 8x8 register tile of  out[j0..j0+8][k0..k0+8] += sum_r D[r][j0..] * A[r][k0..]  over one stage.
-PINN_D void wg_tile8x8(const float* __restrict__ sDl, const float* __restrict__ sAl, int j0, int k0, float (&acc)[64]) {
-#pragma unroll 2
-  for (int r = 0; r < kWgS; ++r) {
-    const float4 d0 = *reinterpret_cast<const float4*>(sDl + r * 64 + j0), d1 = *reinterpret_cast<const float4*>(sDl + r * 64 + j0 + 4);
-    const float4 v0 = *reinterpret_cast<const float4*>(sAl + r * 64 + k0), v1 = *reinterpret_cast<const float4*>(sAl + r * 64 + k0 + 4);
-    const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-    const float2 vv[4] = {make_float2(v0.x, v0.y), make_float2(v0.z, v0.w), make_float2(v1.x, v1.y), make_float2(v1.z, v1.w)};
-#pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      const float2 dp = make_float2(dd[p], dd[p]);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float2 c = make_float2(acc[8 * p + 2 * q], acc[8 * p + 2 * q + 1]);
-        c = ffma2(dp, vv[q], c);
-        acc[8 * p + 2 * q] = c.x; acc[8 * p + 2 * q + 1] = c.y;
-      }
-    }
-  }
-}
-
-// Contraction over the batch with uniform warps.  NBT = 64 (L-1) + 32 threads each own one 8x8
-// register tile of the big products (dW_l 64x64 for l >= 1: 64 threads each; dWv0 32x64: 32
-// threads); the small outputs are spread evenly on top:
-//   dW0 (64x8): thread t < 128 -> row t/2, 4 columns;   dWv1 (16x32): t < 128 -> row t/8, 4 columns
-//   trunk bias sums db_l[c]: entry e = t, t + blockDim (< 64 L);   dWp[c]: t < 64;   dWv2[k]: 64 <= t < 80
-//   head bias sums (dbv0 32, dbv1 16, dbp, dbv2): 80 <= t < 130
-// One FULL stage (kWgS samples) by TMA: every array's slab is contiguous in HBM, so the stage is
-// 2L + 7 bulk copies issued by a single thread; the mbarrier counts the bytes as they land.
-template <int L>
-PINN_D void wg_issue_stage_bulk(float* st, uint64_t* bar, const WgradArgs& a, int64_t s0) {
-  float* sD = st;
-  float* sA = sD + L * kWgS * 64;
-  float* sX = sA + L * kWgS * 64;
-  float* sDV0 = sX + kWgS * 8;
-  float* sAV0 = sDV0 + kWgS * 32;
-  float* sDV1 = sAV0 + kWgS * 32;
-  float* sAV1 = sDV1 + kWgS * 16;
-  float* sDU = sAV1 + kWgS * 16;
-  float* sDVS = sDU + kWgS;
-  tc::mbar_expect_tx(bar, static_cast<uint32_t>(wg_stage_floats(L) * sizeof(float)));
-#pragma unroll
-  for (int l = 0; l < L; ++l) {
-    tc::bulk_g2s(sD + l * kWgS * 64, a.sc.del[l] + s0 * 64, kWgS * 64 * 4, bar);
-    tc::bulk_g2s(sA + l * kWgS * 64, a.sc.act[l] + s0 * 64, kWgS * 64 * 4, bar);
-  }
-  tc::bulk_g2s(sX, a.x + s0 * 8, kWgS * 8 * 4, bar);
-  tc::bulk_g2s(sDV0, a.sc.dv0 + s0 * 32, kWgS * 32 * 4, bar);
-  tc::bulk_g2s(sAV0, a.sc.av0 + s0 * 32, kWgS * 32 * 4, bar);
-  tc::bulk_g2s(sDV1, a.sc.dv1 + s0 * 16, kWgS * 16 * 4, bar);
-  tc::bulk_g2s(sAV1, a.sc.av1 + s0 * 16, kWgS * 16 * 4, bar);
-  tc::bulk_g2s(sDU, a.sc.du + s0, kWgS * 4, bar);
-  tc::bulk_g2s(sDVS, a.sc.dvs + s0, kWgS * 4, bar);
-}
-
-PINN_HD constexpr int wg_threads(int L) { return 64 * (L - 1) + 32 < 160 ? 160 : 64 * (L - 1) + 32; }   // >= 130 needed by the small outputs
-template <int L>
-__global__ void __launch_bounds__(wg_threads(L), (L >= 4 ? 2 : 3))
-wgrad_kernel(WgradArgs a, ParamLayout lay) {
-  extern __shared__ __align__(16) float sm[];
-  constexpr int NBT = 64 * (L - 1) + 32, NT = wg_threads(L);
-  constexpr int SF = wg_stage_floats(L);
-  const int tid = threadIdx.x;
-  // big tile of this thread
-  const bool is_v0 = tid >= 64 * (L - 1);
-  const int lbig = 1 + (tid >> 6), tt = is_v0 ? tid - 64 * (L - 1) : (tid & 63);
-  const int j0 = 8 * (tt >> 3), k0 = 8 * (tt & 7);
-  float acc[64];
-#pragma unroll
-  for (int q = 0; q < 64; ++q) acc[q] = 0.f;
-  float aW0[4] = {0.f, 0.f, 0.f, 0.f}, aV1[4] = {0.f, 0.f, 0.f, 0.f}, aB[2] = {0.f, 0.f}, aP = 0.f;
-  const int e0 = tid, e1 = tid + NT;                        // trunk-bias entries (flat over [L][64])
-  const bool has_big = tid < NBT;
-
-  // sample range of this CTA: a multiple of the stage size (keeps every TMA source 16-byte aligned)
-  int64_t per = (a.n + gridDim.x - 1) / gridDim.x;
-  per = (per + kWgS - 1) / kWgS * kWgS;
-  const int64_t s_begin = static_cast<int64_t>(blockIdx.x) * per < a.n ? static_cast<int64_t>(blockIdx.x) * per : a.n;
-  const int64_t s_end = s_begin + per < a.n ? s_begin + per : a.n;
-  const int n_stage = s_end > s_begin ? static_cast<int>((s_end - s_begin + kWgS - 1) / kWgS) : 0;
-  auto cnt_of = [&](int it) { const int64_t s0 = s_begin + static_cast<int64_t>(it) * kWgS; return static_cast<int>(s_end - s0 < kWgS ? s_end - s0 : kWgS); };
-  __shared__ __align__(8) uint64_t full[2];
-  if (tid == 0) { tc::mbar_init(&full[0], 1); tc::mbar_init(&full[1], 1); tc::fence_mbar_init(); }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
   __syncthreads();
-  uint32_t ph[2] = {0u, 0u};
-  // full stages arrive by TMA (one thread issues), a ragged last stage by per-thread cp.async
-  auto issue = [&](int it) {
-    float* st = sm + (it & 1) * SF;
-    const int64_t s0 = s_begin + static_cast<int64_t>(it) * kWgS;
-    if (cnt_of(it) == kWgS) { if (tid == 0) wg_issue_stage_bulk<L>(st, &full[it & 1], a, s0); }
-    else { wg_issue_stage<L>(st, a, s0, cnt_of(it), tid); cp_async_commit(); }
-  };
-  if (n_stage > 0) issue(0);
-  for (int it = 0; it < n_stage; ++it) {
-    if (it + 1 < n_stage) issue(it + 1);
-    if (cnt_of(it) == kWgS) { tc::mbar_wait(&full[it & 1], ph[it & 1]); ph[it & 1] ^= 1u; }
-    else { cp_async_wait<0>(); __syncthreads(); }
-    const float* st = sm + (it & 1) * SF;
-    const float* sD = st;
-    const float* sA = sD + L * kWgS * 64;
-    const float* sX = sA + L * kWgS * 64;
-    const float* sDV0 = sX + kWgS * 8;
-    const float* sAV0 = sDV0 + kWgS * 32;
-    const float* sDV1 = sAV0 + kWgS * 32;
-    const float* sAV1 = sDV1 + kWgS * 16;
-    const float* sDU = sAV1 + kWgS * 16;
-    const float* sDVS = sDU + kWgS;
-    // ---- big tile
-    if (!has_big) {
-    } else if (!is_v0) {
-      wg_tile8x8(sD + lbig * kWgS * 64, sA + (lbig - 1) * kWgS * 64, j0, k0, acc);
-    } else {
-      const float* sAl = sA + (L - 1) * kWgS * 64;
-#pragma unroll 2
-      for (int r = 0; r < kWgS; ++r) {
-        const float4 d0 = *reinterpret_cast<const float4*>(sDV0 + r * 32 + j0), d1 = *reinterpret_cast<const float4*>(sDV0 + r * 32 + j0 + 4);
-        const float4 v0 = *reinterpret_cast<const float4*>(sAl + r * 64 + k0), v1 = *reinterpret_cast<const float4*>(sAl + r * 64 + k0 + 4);
-        const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-        const float2 vv[4] = {make_float2(v0.x, v0.y), make_float2(v0.z, v0.w), make_float2(v1.x, v1.y), make_float2(v1.z, v1.w)};
+  tc::fence_after_sync();
+
+  // tile range of this CTA
+  const int64_t per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t t_begin = static_cast<int64_t>(blockIdx.x) * per < a.n_tiles ? static_cast<int64_t>(blockIdx.x) * per : a.n_tiles;
+  const int64_t t_end = t_begin + per < a.n_tiles ? t_begin + per : a.n_tiles;
+  const int64_t n_stage = (t_end - t_begin) * (kBTile / kWgStage);
+
+  if (mma_warp) {
+    // ================================================================== MMA warp
+    const uint32_t idesc_act = tc::make_idesc_tf32(128, kNAct), idesc_x = tc::make_idesc_tf32(128, kNX);
+    const uint32_t idesc_v0 = tc::make_idesc_tf32(128, kNV0), idesc_v1 = tc::make_idesc_tf32(128, kNV1);
+    const uint32_t base = tc::smem_u32(wsm);
+    uint32_t par[2] = {0u, 0u};
+    for (int64_t st = 0; st < n_stage; ++st) {
+      const int buf = static_cast<int>(st & 1);
+      tc::mbar_wait(&full[buf], par[buf]);
+      par[buf] ^= 1u;
+      __syncwarp();
+      if (tc::elect_one()) {
+        tc::fence_after_sync();
+        const uint32_t hi = base + buf * wl.buffer_bytes, lo = hi + wl.plane_bytes;
+        const uint32_t first = st == 0 ? 0u : 1u;
+        // one 3xTF32 product over the stage's two K = 8 slabs
+        auto prod = [&](int a_off, int b_off, int n_rows, uint32_t idesc, int col) {
+          const uint32_t lbo_a = wg_lbo(128), lbo_b = wg_lbo(n_rows);
+          const uint64_t a_hi = tc::make_desc(hi + a_off, lbo_a, 128), a_lo = tc::make_desc(lo + a_off, lbo_a, 128);
+          const uint64_t b_hi = tc::make_desc(hi + b_off, lbo_b, 128), b_lo = tc::make_desc(lo + b_off, lbo_b, 128);
+          const uint64_t as = (2u * lbo_a) >> 4, bs = (2u * lbo_b) >> 4;
+          const uint32_t d = tmem_base_s + static_cast<uint32_t>(col);
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          const float2 dp = make_float2(dd[p], dd[p]);
+          for (int term = 0; term < 3; ++term) {
+            const uint64_t aa = term == 0 ? a_lo : a_hi, bb = term == 1 ? b_lo : b_hi;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float2 c = make_float2(acc[8 * p + 2 * q], acc[8 * p + 2 * q + 1]);
-            c = ffma2(dp, vv[q], c);
-            acc[8 * p + 2 * q] = c.x; acc[8 * p + 2 * q + 1] = c.y;
+            for (int k8 = 0; k8 < kWgStage / 8; ++k8)
+              tc::umma_tf32(d, aa + k8 * as, bb + k8 * bs, idesc, (term | k8) != 0 ? 1u : first);
+          }
+        };
+#pragma unroll
+        for (int l = 0; l < L; ++l)       // a_l pairs with delta_{l+1} (big blocks) or, for l = L-1, with the heads (small block)
+          prod(l + 1 < L ? wl.a_big[l / 2] : wl.a_small, wl.b_act[l], kNAct, idesc_act, WgCols<L>::act0 + kNAct * l);
+        prod(wl.a_small, wl.b_x, kNX, idesc_x, WgCols<L>::x);
+        prod(wl.a_small, wl.b_v0, kNV0, idesc_v0, WgCols<L>::v0);
+        prod(wl.a_small, wl.b_v1, kNV1, idesc_v1, WgCols<L>::v1);
+        tc::umma_commit(&done[buf]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================================================================== loaders
+    // work items of a stage: (row, 4-sample chunk), 4 chunks per row; item i -> row i / 4, chunk i % 4.
+    // rows [0, rm.RV1 + 16) minus the unused ones; plus the 8 x-rows handled by the first 32 threads.
+    constexpr int kItems = (4 * (128 * (L / 2) + 128 + 64 * L + 48) + kWgLoaders - 1) / kWgLoaders;    // ceil(rows * 4 / 256)
+    const int n_items = rm.rows * 4;
+    float4 ld[kItems];
+    float4 ldx = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto row_ok = [&](int r) {       // rows K2a never writes
+      if (r < rm.RA) return r < 64 * (L - 1);
+      if (r < rm.RB) return r - rm.RA < 114;
+      return true;
+    };
+    auto load_stage = [&](int64_t st) {
+      const int64_t tile = t_begin + st / (kBTile / kWgStage);
+      const int s0 = static_cast<int>(st % (kBTile / kWgStage)) * kWgStage;
+      const float* base = a.rows + static_cast<size_t>(tile) * rm.rows * kBTile + s0;
+#pragma unroll
+      for (int it = 0; it < kItems; ++it) {
+        const int i = tid + it * kWgLoaders, r = i >> 2, c = i & 3;
+        ld[it] = (i < n_items && row_ok(r)) ? __ldcs(reinterpret_cast<const float4*>(base + static_cast<size_t>(r) * kBTile) + c)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (tid < 32) {             // x[N][8]: thread -> (sample tid / 2, 4 features)
+        const int64_t s = tile * kBTile + s0 + (tid >> 1);
+        ldx = s < a.n ? __ldg(reinterpret_cast<const float4*>(a.x + s * PINN_N_IN) + (tid & 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto store_stage = [&](int buf) {
+      unsigned char* hi = wsm + buf * wl.buffer_bytes;
+      unsigned char* lo = hi + wl.plane_bytes;
+#pragma unroll
+      for (int it = 0; it < kItems; ++it) {
+        const int i = tid + it * kWgLoaders, r = i >> 2, c = i & 3;
+        if (i >= n_items || !row_ok(r)) continue;
+        int blk, lr, lbo;
+        if (r < rm.RA) { blk = wl.a_big[r >> 7]; lr = r & 127; lbo = wg_lbo(128); }
+        else if (r < rm.RB) { blk = wl.a_small; lr = r - rm.RA; lbo = wg_lbo(128); }
+        else if (r < rm.RV0) { blk = wl.b_act[(r - rm.RB) >> 6]; lr = (r - rm.RB) & 63; lbo = wg_lbo(kNAct); }
+        else if (r < rm.RV1) { blk = wl.b_v0; lr = r - rm.RV0; lbo = wg_lbo(kNV0); }
+        else { blk = wl.b_v1; lr = r - rm.RV1; lbo = wg_lbo(kNV1); }
+        const float4 v = ld[it];
+        const float4 h = make_float4(tc::tf32_hi(v.x), tc::tf32_hi(v.y), tc::tf32_hi(v.z), tc::tf32_hi(v.w));
+        const int off = blk + c * lbo + lr * 16;
+        *reinterpret_cast<float4*>(hi + off) = h;
+        *reinterpret_cast<float4*>(lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+      }
+      if (tid < 32) {             // x^T: feature rows 4 (tid & 1) .. +3, sample tid / 2 of the stage
+        const int sl = tid >> 1, f0 = 4 * (tid & 1);
+        const float vv[4] = {ldx.x, ldx.y, ldx.z, ldx.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float h = tc::tf32_hi(vv[q]);
+          const int off = wl.b_x + (sl >> 2) * wg_lbo(kNX) + (f0 + q) * 16 + (sl & 3) * 4;
+          *reinterpret_cast<float*>(hi + off) = h;
+          *reinterpret_cast<float*>(lo + off) = vv[q] - h;
+        }
+      }
+    };
+    uint32_t dpar[2] = {0u, 0u};
+    if (n_stage > 0) load_stage(0);
+    for (int64_t st = 0; st < n_stage; ++st) {
+      const int buf = static_cast<int>(st & 1);
+      if (st >= 2) { tc::mbar_wait(&done[buf], dpar[buf]); dpar[buf] ^= 1u; }     // the MMAs of stage st-2 have drained this buffer
+      store_stage(buf);
+      if (st + 1 < n_stage) load_stage(st + 1);
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&full[buf]);
+    }
+    // drain: the last (up to) two commits
+    for (int64_t st = n_stage > 2 ? n_stage - 2 : 0; st < n_stage; ++st) {
+      const int buf = static_cast<int>(st & 1);
+      tc::mbar_wait(&done[buf], dpar[buf]);
+      dpar[buf] ^= 1u;
+    }
+    tc::fence_after_sync();
+    // ---------------------------------------------------------------- accumulators -> this CTA's partial
+    float* part = a.partial + static_cast<size_t>(blockIdx.x) * lay.total;
+    if (warp < 4) {
+      const int lane_row = warp * 32 + (tid & 31);
+      const uint32_t tl = tmem_base_s + (static_cast<uint32_t>(warp * 32) << 16);
+      const bool have = n_stage > 0;
+      auto read16 = [&](int col, float* v) {
+        if (have) { tc::tmem_ld16(tl + static_cast<uint32_t>(col), v); tc::tmem_wait_ld(); }
+        else {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = 0.f;
+        }
+      };
+      float v[16];
+      // trunk layers l >= 1: delta_l sits in big block (l-1)/2, lanes 64 ((l-1) % 2) + j; product column block of a_{l-1}
+#pragma unroll
+      for (int l = 1; l < L; ++l) {
+        const int j = lane_row - 64 * ((l - 1) & 1);
+        const int col = WgCols<L>::act0 + kNAct * (l - 1);
+#pragma unroll
+        for (int c = 0; c < kNAct; c += 16) {
+          read16(col + c, v);
+          if (j >= 0 && j < 64) {
+            if (c < 64) {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) part[lay.offW[l] + j * 64 + c + q] = v[q] * a.act_scale;
+            } else part[lay.offb[l] + j] = v[0];
           }
         }
       }
-    }
-    // ---- small outputs
-#pragma unroll 4
-    for (int r = 0; r < kWgS; ++r) {
-      if (tid < 128) {
-        const float d0 = sD[r * 64 + (tid >> 1)];
-        const float4 xv = *reinterpret_cast<const float4*>(sX + r * 8 + 4 * (tid & 1));
-        aW0[0] = fmaf(d0, xv.x, aW0[0]); aW0[1] = fmaf(d0, xv.y, aW0[1]); aW0[2] = fmaf(d0, xv.z, aW0[2]); aW0[3] = fmaf(d0, xv.w, aW0[3]);
-        const float d1 = sDV1[r * 16 + (tid >> 3)];
-        const float4 av = *reinterpret_cast<const float4*>(sAV0 + r * 32 + 4 * (tid & 7));
-        aV1[0] = fmaf(d1, av.x, aV1[0]); aV1[1] = fmaf(d1, av.y, aV1[1]); aV1[2] = fmaf(d1, av.z, aV1[2]); aV1[3] = fmaf(d1, av.w, aV1[3]);
+      // small block against a_{L-1}: lanes 64..95 = dWv0 / dbv0, lane 96 = dWp / dbp
+      {
+        const int col = WgCols<L>::act0 + kNAct * (L - 1);
+#pragma unroll
+        for (int c = 0; c < kNAct; c += 16) {
+          read16(col + c, v);
+          if (lane_row >= 64 && lane_row < 96) {
+            const int j = lane_row - 64;
+            if (c < 64) {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) part[lay.offWv0 + j * 64 + c + q] = v[q] * a.act_scale;
+            } else part[lay.offbv0 + j] = v[0];
+          } else if (lane_row == 96) {
+            if (c < 64) {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) part[lay.offWp + c + q] = v[q] * a.act_scale;
+            } else part[lay.offbp] = v[0];
+          }
+        }
       }
-      if (e0 < 64 * L) aB[0] += sD[((e0 >> 6) * kWgS + r) * 64 + (e0 & 63)];
-      if (e1 < 64 * L) aB[1] += sD[((e1 >> 6) * kWgS + r) * 64 + (e1 & 63)];
-      if (tid < 64) aP = fmaf(sDU[r], sA[((L - 1) * kWgS + r) * 64 + tid], aP);
-      else if (tid < 80) aP = fmaf(sDVS[r], sAV1[r * 16 + tid - 64], aP);
-      else if (tid < 112) aP += sDV0[r * 32 + tid - 80];
-      else if (tid < 128) aP += sDV1[r * 16 + tid - 112];
-      else if (tid == 128) aP += sDU[r];
-      else if (tid == 129) aP += sDVS[r];
+      // against x^T: lanes 0..63 = dW0 (8 columns) / db0 (column 8)
+      read16(WgCols<L>::x, v);
+      if (lane_row < 64) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) part[lay.offW[0] + lane_row * 8 + q] = v[q];
+        part[lay.offb[0] + lane_row] = v[8];
+      }
+      // against av0: lanes 97..112 = dWv1 (32 columns) / dbv1 (column 32)
+#pragma unroll
+      for (int c = 0; c < kNV0; c += 16) {
+        read16(WgCols<L>::v0 + c, v);
+        if (lane_row >= 97 && lane_row < 113) {
+          const int j = lane_row - 97;
+          if (c < 32) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) part[lay.offWv1 + j * 32 + c + q] = v[q];
+          } else part[lay.offbv1 + j] = v[0];
+        }
+      }
+      // against av1: lane 113 = dWv2 (16 columns) / dbv2 (column 16)
+#pragma unroll
+      for (int c = 0; c < kNV1; c += 16) {
+        read16(WgCols<L>::v1 + c, v);
+        if (lane_row == 113) {
+          if (c < 16) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) part[lay.offWv2 + q] = v[q];
+          } else part[lay.offbv2] = v[0];
+        }
+      }
     }
-    __syncthreads();             // everyone is done with this stage before it is refilled
   }
-  // ---------------------------------------------------------------- write this CTA's partial
-  float* part = a.partial + static_cast<size_t>(blockIdx.x) * lay.total;
-  if (has_big) {
-    const int64_t base = is_v0 ? lay.offWv0 : lay.offW[lbig];
-#pragma unroll
-    for (int p = 0; p < 8; ++p)
-#pragma unroll
-      for (int q = 0; q < 8; ++q) part[base + (j0 + p) * 64 + k0 + q] = acc[8 * p + q] * a.act_scale;
-  }
-  if (tid < 128) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      part[lay.offW[0] + (tid >> 1) * 8 + 4 * (tid & 1) + q] = aW0[q];
-      part[lay.offWv1 + (tid >> 3) * 32 + 4 * (tid & 7) + q] = aV1[q];
-    }
-  }
-  if (e0 < 64 * L) part[lay.offb[e0 >> 6] + (e0 & 63)] = aB[0];
-  if (e1 < 64 * L) part[lay.offb[e1 >> 6] + (e1 & 63)] = aB[1];
-  if (tid < 64) part[lay.offWp + tid] = aP * a.act_scale;
-  else if (tid < 80) part[lay.offWv2 + tid - 64] = aP;
-  else if (tid < 112) part[lay.offbv0 + tid - 80] = aP;
-  else if (tid < 128) part[lay.offbv1 + tid - 112] = aP;
-  else if (tid == 128) part[lay.offbp] = aP;
-  else if (tid == 129) part[lay.offbv2] = aP;
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
 }
 
 // ------------------------------------------------------------------------------- K2a
@@ -415,7 +477,8 @@ PINN_D void stage_plane_transposed(float* hi, float* lo, const float* __restrict
 struct TcbArgs {
   const float* x; int64_t n;
   const float* grad_u; const float* grad_s; const float* y; float inv_n_global;
-  BwdScratch sc;
+  float* rows;              // transposed scratch, [tile][rm.rows][128] (see RowMap)
+  RowMap rm;
   double* loss_partial;     // [2 * grid][4]
 };
 
@@ -511,6 +574,7 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
   for (int64_t tile = static_cast<int64_t>(blockIdx.x) * 2 + grp; tile < n_tiles; tile += static_cast<int64_t>(gridDim.x) * 2) {
     const int64_t s = tile * kBTile + row;
     const bool valid = s < a.n;
+    float* const trow = a.rows + static_cast<size_t>(tile) * a.rm.rows * kBTile + row;     // this sample's column of the tile's row table
     const bool active = drop_on && (!INJ || valid);     // injected masks: tail rows of the last tile have no mask row
     const uint64_t sg = static_cast<uint64_t>(dp.sample_offset + s);
     KeepSrc<INJ> ks;
@@ -550,10 +614,8 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
           kb[0] |= (k[q] ? 1u : 0u) << (g + q);
         }
         store_pn8(cb + g, v);
-        if (valid) {
-          float4* o = reinterpret_cast<float4*>(a.sc.act[0] + s * H + cb + g);
-          o[0] = make_float4(v[0], v[1], v[2], v[3]); o[1] = make_float4(v[4], v[5], v[6], v[7]);
-        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) trow[static_cast<size_t>(row_act(a.rm, 0) + cb + g + q) * kBTile] = valid ? v[q] : 0.f;
       }
     }
 #pragma unroll 1
@@ -583,10 +645,8 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
           bits |= (k[q] ? 1u : 0u) << (g + q);
         }
         store_pn8(cb + g, v);
-        if (valid) {
-          float4* o = reinterpret_cast<float4*>(a.sc.act[l] + s * H + cb + g);
-          o[0] = make_float4(v[0], v[1], v[2], v[3]); o[1] = make_float4(v[4], v[5], v[6], v[7]);
-        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) trow[static_cast<size_t>(row_act(a.rm, l) + cb + g + q) * kBTile] = valid ? v[q] : 0.f;
       }
       kb[l] = bits;
     }
@@ -670,19 +730,20 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
         const float mk = ((kb[L] >> i) & 1u) ? wscale : 0.f;
         dzv0[i] = dzv0[i] * mk * (1.0f - av * av);
       }
-      if (valid) {
+      {   // rows of an invalid sample (tail of the last tile) are written as zeros: K2b sums whole tiles
+        float* const pa = trow + static_cast<size_t>(a.rm.RA) * kBTile;
 #pragma unroll
-        for (int i4 = 0; i4 < 8; ++i4) {
-          reinterpret_cast<float4*>(a.sc.av0 + s * 32)[i4] = make_float4(v0[4 * i4], v0[4 * i4 + 1], v0[4 * i4 + 2], v0[4 * i4 + 3]);
-          reinterpret_cast<float4*>(a.sc.dv0 + s * 32)[i4] = make_float4(dzv0[4 * i4], dzv0[4 * i4 + 1], dzv0[4 * i4 + 2], dzv0[4 * i4 + 3]);
+        for (int i = 0; i < 32; ++i) {
+          trow[static_cast<size_t>(a.rm.RV0 + i) * kBTile] = valid ? v0[i] : 0.f;
+          pa[static_cast<size_t>(64 + i) * kBTile] = dzv0[i];
         }
 #pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-          reinterpret_cast<float4*>(a.sc.av1 + s * 16)[i4] = make_float4(v1[4 * i4], v1[4 * i4 + 1], v1[4 * i4 + 2], v1[4 * i4 + 3]);
-          reinterpret_cast<float4*>(a.sc.dv1 + s * 16)[i4] = make_float4(dz1[4 * i4], dz1[4 * i4 + 1], dz1[4 * i4 + 2], dz1[4 * i4 + 3]);
+        for (int k = 0; k < 16; ++k) {
+          trow[static_cast<size_t>(a.rm.RV1 + k) * kBTile] = valid ? v1[k] : 0.f;
+          pa[static_cast<size_t>(97 + k) * kBTile] = dz1[k];
         }
-        a.sc.du[s] = du;
-        a.sc.dvs[s] = dv;
+        pa[static_cast<size_t>(96) * kBTile] = du;
+        pa[static_cast<size_t>(113) * kBTile] = dv;
       }
     }
     // ============================ backward ============================
@@ -703,11 +764,10 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
     if constexpr (!RES) wcommit_transposed(b_hi, b_lo, wpre, t256, wscale);
 #pragma unroll 1
     for (int l = L - 1; l >= 0; --l) {
-      float4 apre[HH / 4];       // this thread's masked activations of layer l, prefetched during the MMA
+      float apre[HH];            // this thread's masked activations of layer l, prefetched during the MMA
       run_mma(lay.wt_hi[l + 1], lay.wt_lo[l + 1], kLboT, idesc64, [&] {
 #pragma unroll
-        for (int g4 = 0; g4 < HH / 4; ++g4)
-          apre[g4] = valid ? *reinterpret_cast<const float4*>(a.sc.act[l] + s * H + cb + 4 * g4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < HH; ++q) apre[q] = trow[static_cast<size_t>(row_act(a.rm, l) + cb + q) * kBTile];
         if constexpr (!RES) { if (l > 0) wprefetch(wpre, net.W[l], nullptr, H, t256); }
       });
       const uint32_t kbl = kb[l];
@@ -716,15 +776,12 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
         float z[8], dz[8];
         tc::tmem_ld8(d_lane + cb + g, z);
         tc::tmem_wait_ld();
-        const float aa[8] = {apre[g / 4].x, apre[g / 4].y, apre[g / 4].z, apre[g / 4].w,
-                             apre[g / 4 + 1].x, apre[g / 4 + 1].y, apre[g / 4 + 1].z, apre[g / 4 + 1].w};
+        const float* aa = apre + g;
 #pragma unroll
         for (int q = 0; q < 8; ++q)    // z already carries the dropout scale (folded into W^T); dropped units have a = 0
           dz[q] = ((kbl >> (g + q)) & 1u) ? z[q] * fmaf(-aa[q], aa[q], 1.0f) : 0.f;
-        if (valid) {
-          float4* o = reinterpret_cast<float4*>(a.sc.del[l] + s * H + cb + g);
-          o[0] = make_float4(dz[0], dz[1], dz[2], dz[3]); o[1] = make_float4(dz[4], dz[5], dz[6], dz[7]);
-        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) trow[static_cast<size_t>(row_del(a.rm, l) + cb + g + q) * kBTile] = dz[q];
         if (l > 0) store_pn8(cb + g, dz);
       }
       if constexpr (!RES) { if (l > 0) wcommit_transposed(b_hi, b_lo, wpre, t256, wscale); }
@@ -778,16 +835,15 @@ static TcBwdPlan plan_tc_bwd(int L, int64_t n) {
   const int64_t tiles = (n + kBTile - 1) / kBTile;
   int64_t want = (tiles + 1) / 2;
   p.grid_a = static_cast<int>(want < sms ? (want > 0 ? want : 1) : sms);
-  int64_t wb = (n + 1023) / 1024;
-  p.grid_b = static_cast<int>(wb < 3 * sms ? (wb > 0 ? wb : 1) : 3 * sms);
+  p.grid_b = static_cast<int>(tiles < sms ? (tiles > 0 ? tiles : 1) : sms);
   p.smem_a = static_cast<size_t>(make_tcb_layout(L).total) * sizeof(float);
-  p.smem_b = static_cast<size_t>(2) * wg_stage_floats(L) * sizeof(float);
+  p.smem_b = static_cast<size_t>(2) * make_wg_layout(L).buffer_bytes;
   size_t off = static_cast<size_t>(2 * p.grid_a) * 4 * sizeof(double);
   p.off_partial = off;
   off += static_cast<size_t>(p.grid_b) * lay.total * sizeof(float);
   off = (off + 255) & ~static_cast<size_t>(255);
   p.off_scratch = off;
-  off += bwd_scratch_floats_per_sample(L) * ((static_cast<size_t>(n > 0 ? n : 1) + 3) & ~static_cast<size_t>(3)) * sizeof(float);
+  off += bwd_scratch_floats(L, n) * sizeof(float);
   p.bytes = off;
   return p;
 }
@@ -811,7 +867,8 @@ int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropPa
   TcbArgs a{};
   a.x = x; a.n = n; a.grad_u = grad_u; a.grad_s = grad_s; a.y = y;
   a.inv_n_global = grad_u ? 0.f : static_cast<float>(1.0 / static_cast<double>(n_global));
-  a.sc = carve_scratch(reinterpret_cast<float*>(ws + p.off_scratch), n, L);
+  a.rows = reinterpret_cast<float*>(ws + p.off_scratch);
+  a.rm = make_rowmap(L);
   a.loss_partial = reinterpret_cast<double*>(ws);
   TcbLayout tl = make_tcb_layout(L);
   const bool inj = dp.p > 0.f && dp.masks != nullptr;
@@ -831,14 +888,15 @@ int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropPa
 #undef LAUNCH_A
   PINN_CUDA_TRY(cudaGetLastError());
   WgradArgs w{};
-  w.x = x; w.n = n; w.L = L; w.sc = a.sc;
+  w.x = x; w.n = n; w.n_tiles = (n + kBTile - 1) / kBTile; w.rows = a.rows;
   w.act_scale = dp.p > 0.f ? dp.scale : 1.0f;
   w.partial = reinterpret_cast<float*>(ws + p.off_partial);
+  const WgLayout wl = make_wg_layout(L);
 #define LAUNCH_B(LL)                                                                                              \
   {                                                                                                               \
-    PINN_CUDA_TRY(cudaFuncSetAttribute(wgrad_kernel<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+    PINN_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                        static_cast<int>(p.smem_b)));                                              \
-    wgrad_kernel<LL><<<p.grid_b, wg_threads(LL), p.smem_b, st>>>(w, lay);                                                                  \
+    wgrad_tc_kernel<LL><<<p.grid_b, kWgLoaders + 32, p.smem_b, st>>>(w, lay, wl, a.rm);                           \
   }
   switch (L) {
     case 2: LAUNCH_B(2) break;
