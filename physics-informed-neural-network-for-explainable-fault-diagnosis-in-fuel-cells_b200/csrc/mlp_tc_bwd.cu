@@ -66,45 +66,49 @@ PINN_HD size_t bwd_scratch_floats(int L, int64_t n) {
 // ------------------------------------------------------------------------------- K2b
 // Every weight / bias gradient as ONE accumulation over samples on the tensor cores (3xTF32):
 //   D[m][n] += sum_s A[m][s] * B[n][s],   A = delta rows, B = activation rows + a row of ones
-// (the ones row turns the bias column sums into column 64 / 8 / 32 / 16 of the same product).
-// M is always 128: the rows of several delta arrays are stacked in one A block and each product
-// only reads back the lanes it owns (cross terms are computed and ignored -- an M = 64 MMA costs
-// the same 128-row issue slot).  For L = 3:
-//   big block   = [delta_1 ; delta_2]                x  [a_0 ; 1]  -> lanes   0..63  = dW1, db1
-//                                                     x  [a_1 ; 1]  -> lanes  64..127 = dW2, db2
-//   small block = [delta_0 ; dv0 ; du ; dv1 ; dvs]   x  [x^T ; 1]  -> lanes   0..63  = dW0, db0
-//                                                     x  [a_2 ; 1]  -> lanes  64..96  = dWv0, dbv0, dWp, dbp
-//                                                     x  [av0 ; 1]  -> lanes  97..112 = dWv1, dbv1
-//                                                     x  [av1 ; 1]  -> lane  113      = dWv2, dbv2
+// (the ones row turns every bias column sum into one more column of the same product).
+// M is always 128: delta arrays are stacked in A blocks of 128 rows, and the B rows of everything
+// those deltas pair with are concatenated into ONE B block per A block, so each A slab (4 KB) is
+// fetched once per MMA instead of once per product -- with both operands in shared memory the
+// operand fetch, not the math, paces tcgen05.mma.  Cross terms are computed and never read.  L = 3:
+//   big block   [delta_1 ; delta_2]                 x  [a_0 | a_1 | 1]              (N = 144)
+//        lanes   0..63 , columns   0..63  = dW1      column 128 = db1
+//        lanes  64..127, columns  64..127 = dW2      column 128 = db2
+//   small block [delta_0 ; dv0 ; du ; dv1 ; dvs]    x  [a_2 | 1 | x^T | av0 | av1]  (N = 128)
+//        lanes   0..63  x columns  65..72  = dW0     lanes 64..95 x columns 0..63 = dWv0    lane 96 = dWp
+//        lanes  97..112 x columns  73..104 = dWv1    lane 113 x columns 105..120 = dWv2     column 64 = every bias
 // Accumulators stay in tensor memory for the CTA's whole sample range.  Pipeline: 256 loader
-// threads bring 16-sample stages (64 B per row) from HBM into registers, split them into tf32
-// hi / lo planes (K-major canonical layout, LBO padded so that the 4 x 8 chunk pattern of a warp
-// is bank-conflict free) in one of two shared-memory buffers and arrive on `full`; a dedicated
-// MMA warp issues the stage's products and commits to `done`, which frees the buffer.
+// threads bring 16-sample stages (64 B per row, two stages in flight) from HBM into registers,
+// split them into tf32 hi / lo planes (K-major canonical layout, LBO padded so that the 4 x 8
+// chunk pattern of a warp is bank-conflict free) in one of two shared-memory buffers and arrive
+// on `full`; a dedicated MMA warp issues the stage's products and commits to `done`, which frees
+// the buffer.
 constexpr int kWgStage = 16;                 // samples per stage
 constexpr int kWgLoaders = 256;
-constexpr int kNAct = 80, kNX = 16, kNV0 = 48, kNV1 = 32;     // B-block rows (N of the MMA): data + ones row + zero rows, N % 16 == 0
-PINN_HD constexpr int wg_lbo(int rows) { return (rows + 2) * 16; }     // bytes; (rows + 2) % 8 == 2 for every block used here
+constexpr int kSmOnes = 64, kSmX = 65, kSmV0 = 73, kSmV1 = 105, kSmN = 128;     // rows of the small B block
+PINN_HD constexpr int wg_lbo(int rows) { return (rows + 2) * 16; }     // bytes; (rows + 2) % 8 == 2 for 80, 128 and 144 rows
+PINN_HD constexpr int wg_big_n(int L, int i) { return 2 * i + 2 <= L - 1 ? 144 : 80; }     // N of big block i: two activation arrays + ones, or one
 
 struct WgLayout {      // byte offsets of the hi plane of every operand block inside ONE stage buffer; lo plane = hi + plane_bytes
-  int a_big[2], a_small, b_act[PINN_MAX_HIDDEN], b_x, b_v0, b_v1;
+  int a_big[2], a_small, b_big[2], b_small;
   int plane_bytes, buffer_bytes;
 };
 PINN_HD WgLayout make_wg_layout(int L) {
   WgLayout w{};
-  const int nbig = (L - 1 + 1) / 2;
+  const int nbig = L / 2;          // ceil((L - 1) / 2)
   int o = 0;
   for (int i = 0; i < 2; ++i) { w.a_big[i] = o; if (i < nbig) o += 4 * wg_lbo(128); }
   w.a_small = o; o += 4 * wg_lbo(128);
-  for (int l = 0; l < PINN_MAX_HIDDEN; ++l) { w.b_act[l] = o; if (l < L) o += 4 * wg_lbo(kNAct); }
-  w.b_x = o; o += 4 * wg_lbo(kNX);
-  w.b_v0 = o; o += 4 * wg_lbo(kNV0);
-  w.b_v1 = o; o += 4 * wg_lbo(kNV1);
+  for (int i = 0; i < 2; ++i) { w.b_big[i] = o; if (i < nbig) o += 4 * wg_lbo(wg_big_n(L, i)); }
+  w.b_small = o; o += 4 * wg_lbo(kSmN);
   w.plane_bytes = o;
   w.buffer_bytes = 2 * o;
   return w;
 }
 
+#ifdef PINN_TIMELINE
+__device__ long long g_tlw[2][64][4];     // [0]: MMA warp {wake, issued}; [1]: loader thread 0 {pre-wait, post-wait, post-store, post-arrive}
+#endif
 struct WgradArgs {
   const float* x; int64_t n; int64_t n_tiles;
   const float* rows;       // scratch, [tile][RowMap.rows][128]
@@ -112,24 +116,17 @@ struct WgradArgs {
   float act_scale;         // dropout scale 1/(1-p) missing from the stored trunk activations (K2a)
 };
 
-// TMEM columns of the products
-template <int L> struct WgCols {
-  static constexpr int act0 = 0;                   // product against a_l: columns [80 l, 80 l + 80)
-  static constexpr int x = kNAct * L;
-  static constexpr int v0 = x + kNX;
-  static constexpr int v1 = v0 + kNV0;
-  static constexpr int total = v1 + kNV1;
-};
-
 template <int L>
 __global__ void __launch_bounds__(kWgLoaders + 32, 1)
 wgrad_tc_kernel(WgradArgs a, ParamLayout lay, WgLayout wl, RowMap rm) {
+  constexpr int NBIG = L / 2;
+  constexpr int COL_SMALL = (NBIG > 0 ? wg_big_n(L, 0) : 0) + (NBIG > 1 ? wg_big_n(L, 1) : 0);      // TMEM column of the small product
+  static_assert(COL_SMALL + kSmN <= 512, "TMEM");
   extern __shared__ __align__(1024) unsigned char wsm[];
   __shared__ __align__(8) uint64_t full[2], done[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tc::uniform_warp_idx();
   const bool mma_warp = warp == kWgLoaders / 32;
-  static_assert(WgCols<L>::total <= 512, "TMEM");
 
   if (tid == 0) {
     tc::mbar_init(&full[0], kWgLoaders); tc::mbar_init(&full[1], kWgLoaders);
@@ -138,21 +135,20 @@ wgrad_tc_kernel(WgradArgs a, ParamLayout lay, WgLayout wl, RowMap rm) {
   }
   __syncwarp();
   if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
-  // constant rows of the B blocks (ones row, zero rows): written once into both buffers, both planes
+  // constant rows of the B blocks (the ones row, zero padding): written once into both buffers, both planes
   {
-    auto fill = [&](int blk_off, int data_rows, int n_rows) {
-      const int lbo = wg_lbo(n_rows);
-      for (int i = tid; i < 2 * 2 * 4 * (n_rows - data_rows); i += blockDim.x) {
-        const int r = data_rows + i % (n_rows - data_rows), rest = i / (n_rows - data_rows);
+    auto fill = [&](int blk_off, int n_rows, int row0, int ones_row) {
+      const int lbo = wg_lbo(n_rows), cnt = n_rows - row0;
+      for (int i = tid; i < 2 * 2 * 4 * cnt; i += blockDim.x) {
+        const int r = row0 + i % cnt, rest = i / cnt;
         const int kc = rest & 3, plane = (rest >> 2) & 1, buf = rest >> 3;
-        const float v = (r == data_rows && plane == 0) ? 1.0f : 0.0f;
+        const float v = (r == ones_row && plane == 0) ? 1.0f : 0.0f;
         *reinterpret_cast<float4*>(wsm + buf * wl.buffer_bytes + plane * wl.plane_bytes + blk_off + kc * lbo + r * 16) = make_float4(v, v, v, v);
       }
     };
-    for (int l = 0; l < L; ++l) fill(wl.b_act[l], 64, kNAct);
-    fill(wl.b_x, 8, kNX);
-    fill(wl.b_v0, 32, kNV0);
-    fill(wl.b_v1, 16, kNV1);
+#pragma unroll
+    for (int i = 0; i < NBIG; ++i) { const int nb = wg_big_n(L, i); fill(wl.b_big[i], nb, nb - 16, nb - 16); }
+    fill(wl.b_small, kSmN, kSmOnes, kSmOnes);       // rows 64..127: ones + (overwritten every stage) x^T, av0, av1 + padding
     // unused A rows (114..127 of the small block; 64..127 of a half-filled big block) only feed lanes nobody reads
   }
   tc::fence_proxy_async();
@@ -168,8 +164,6 @@ wgrad_tc_kernel(WgradArgs a, ParamLayout lay, WgLayout wl, RowMap rm) {
 
   if (mma_warp) {
     // ================================================================== MMA warp
-    const uint32_t idesc_act = tc::make_idesc_tf32(128, kNAct), idesc_x = tc::make_idesc_tf32(128, kNX);
-    const uint32_t idesc_v0 = tc::make_idesc_tf32(128, kNV0), idesc_v1 = tc::make_idesc_tf32(128, kNV1);
     const uint32_t base = tc::smem_u32(wsm);
     uint32_t par[2] = {0u, 0u};
     for (int64_t st = 0; st < n_stage; ++st) {
@@ -177,13 +171,16 @@ wgrad_tc_kernel(WgradArgs a, ParamLayout lay, WgLayout wl, RowMap rm) {
       tc::mbar_wait(&full[buf], par[buf]);
       par[buf] ^= 1u;
       __syncwarp();
+#ifdef PINN_TIMELINE
+      if (blockIdx.x == 0 && (tid & 31) == 0 && st >= 16 && st < 80) g_tlw[0][st - 16][0] = clock64();
+#endif
       if (tc::elect_one()) {
         tc::fence_after_sync();
         const uint32_t hi = base + buf * wl.buffer_bytes, lo = hi + wl.plane_bytes;
         const uint32_t first = st == 0 ? 0u : 1u;
         // one 3xTF32 product over the stage's two K = 8 slabs
-        auto prod = [&](int a_off, int b_off, int n_rows, uint32_t idesc, int col) {
-          const uint32_t lbo_a = wg_lbo(128), lbo_b = wg_lbo(n_rows);
+        auto prod = [&](int a_off, int b_off, int n_rows, int col) {
+          const uint32_t lbo_a = wg_lbo(128), lbo_b = wg_lbo(n_rows), idesc = tc::make_idesc_tf32(128, n_rows);
           const uint64_t a_hi = tc::make_desc(hi + a_off, lbo_a, 128), a_lo = tc::make_desc(lo + a_off, lbo_a, 128);
           const uint64_t b_hi = tc::make_desc(hi + b_off, lbo_b, 128), b_lo = tc::make_desc(lo + b_off, lbo_b, 128);
           const uint64_t as = (2u * lbo_a) >> 4, bs = (2u * lbo_b) >> 4;
@@ -196,84 +193,103 @@ wgrad_tc_kernel(WgradArgs a, ParamLayout lay, WgLayout wl, RowMap rm) {
               tc::umma_tf32(d, aa + k8 * as, bb + k8 * bs, idesc, (term | k8) != 0 ? 1u : first);
           }
         };
-#pragma unroll
-        for (int l = 0; l < L; ++l)       // a_l pairs with delta_{l+1} (big blocks) or, for l = L-1, with the heads (small block)
-          prod(l + 1 < L ? wl.a_big[l / 2] : wl.a_small, wl.b_act[l], kNAct, idesc_act, WgCols<L>::act0 + kNAct * l);
-        prod(wl.a_small, wl.b_x, kNX, idesc_x, WgCols<L>::x);
-        prod(wl.a_small, wl.b_v0, kNV0, idesc_v0, WgCols<L>::v0);
-        prod(wl.a_small, wl.b_v1, kNV1, idesc_v1, WgCols<L>::v1);
+        if (NBIG > 0) prod(wl.a_big[0], wl.b_big[0], wg_big_n(L, 0), 0);
+        if (NBIG > 1) prod(wl.a_big[1], wl.b_big[1], wg_big_n(L, 1), wg_big_n(L, 0));
+        prod(wl.a_small, wl.b_small, kSmN, COL_SMALL);
         tc::umma_commit(&done[buf]);
       }
       __syncwarp();
+#ifdef PINN_TIMELINE
+      if (blockIdx.x == 0 && (tid & 31) == 0 && st >= 16 && st < 80) g_tlw[0][st - 16][1] = clock64();
+#endif
     }
   } else {
     // ================================================================== loaders
-    // work items of a stage: (row, 4-sample chunk), 4 chunks per row; item i -> row i / 4, chunk i % 4.
-    // rows [0, rm.RV1 + 16) minus the unused ones; plus the 8 x-rows handled by the first 32 threads.
+    // work items of a stage: (row, 4-sample chunk), 4 chunks per row; item i -> row i / 4, chunk i % 4 of the
+    // tile's row table.  The (row -> operand block, block row) map is the same every stage: resolved once.
     constexpr int kItems = (4 * (128 * (L / 2) + 128 + 64 * L + 48) + kWgLoaders - 1) / kWgLoaders;    // ceil(rows * 4 / 256)
-    const int n_items = rm.rows * 4;
-    float4 ld[kItems];
-    float4 ldx = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto row_ok = [&](int r) {       // rows K2a never writes
-      if (r < rm.RA) return r < 64 * (L - 1);
-      if (r < rm.RB) return r - rm.RA < 114;
-      return true;
-    };
-    auto load_stage = [&](int64_t st) {
+    int dst[kItems];          // byte offset inside a plane, or -1: row not used
+#pragma unroll
+    for (int it = 0; it < kItems; ++it) {
+      const int i = tid + it * kWgLoaders, r = i >> 2, c = i & 3;
+      int off = -1;
+      if (r < rm.RA) { if (r < 64 * (L - 1)) off = wl.a_big[r >> 7] + c * wg_lbo(128) + (r & 127) * 16; }
+      else if (r < rm.RB) { if (r - rm.RA < 114) off = wl.a_small + c * wg_lbo(128) + (r - rm.RA) * 16; }
+      else if (r < rm.RV0) {
+        const int l = (r - rm.RB) >> 6, j = (r - rm.RB) & 63;
+        if (l == L - 1) off = wl.b_small + c * wg_lbo(kSmN) + j * 16;
+        else off = wl.b_big[l >> 1] + c * wg_lbo(wg_big_n(L, l >> 1)) + (64 * (l & 1) + j) * 16;
+      }
+      else if (r < rm.RV1) off = wl.b_small + c * wg_lbo(kSmN) + (kSmV0 + r - rm.RV0) * 16;
+      else if (r < rm.rows) off = wl.b_small + c * wg_lbo(kSmN) + (kSmV1 + r - rm.RV1) * 16;
+      dst[it] = off;
+    }
+    float4 ldA[kItems], ldB[kItems];                            // two stages of loads in flight per thread (HBM latency)
+    float4 ldxA = make_float4(0.f, 0.f, 0.f, 0.f), ldxB = ldxA;
+    auto load_stage = [&](int64_t st, float4 (&ld)[kItems], float4& ldx) {
       const int64_t tile = t_begin + st / (kBTile / kWgStage);
       const int s0 = static_cast<int>(st % (kBTile / kWgStage)) * kWgStage;
       const float* base = a.rows + static_cast<size_t>(tile) * rm.rows * kBTile + s0;
 #pragma unroll
       for (int it = 0; it < kItems; ++it) {
-        const int i = tid + it * kWgLoaders, r = i >> 2, c = i & 3;
-        ld[it] = (i < n_items && row_ok(r)) ? __ldcs(reinterpret_cast<const float4*>(base + static_cast<size_t>(r) * kBTile) + c)
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int i = tid + it * kWgLoaders;
+        if (dst[it] >= 0) ld[it] = __ldcs(reinterpret_cast<const float4*>(base + static_cast<size_t>(i >> 2) * kBTile) + (i & 3));
       }
       if (tid < 32) {             // x[N][8]: thread -> (sample tid / 2, 4 features)
         const int64_t s = tile * kBTile + s0 + (tid >> 1);
         ldx = s < a.n ? __ldg(reinterpret_cast<const float4*>(a.x + s * PINN_N_IN) + (tid & 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    auto store_stage = [&](int buf) {
+    auto store_stage = [&](int buf, const float4 (&ld)[kItems], const float4& ldx) {
       unsigned char* hi = wsm + buf * wl.buffer_bytes;
       unsigned char* lo = hi + wl.plane_bytes;
 #pragma unroll
       for (int it = 0; it < kItems; ++it) {
-        const int i = tid + it * kWgLoaders, r = i >> 2, c = i & 3;
-        if (i >= n_items || !row_ok(r)) continue;
-        int blk, lr, lbo;
-        if (r < rm.RA) { blk = wl.a_big[r >> 7]; lr = r & 127; lbo = wg_lbo(128); }
-        else if (r < rm.RB) { blk = wl.a_small; lr = r - rm.RA; lbo = wg_lbo(128); }
-        else if (r < rm.RV0) { blk = wl.b_act[(r - rm.RB) >> 6]; lr = (r - rm.RB) & 63; lbo = wg_lbo(kNAct); }
-        else if (r < rm.RV1) { blk = wl.b_v0; lr = r - rm.RV0; lbo = wg_lbo(kNV0); }
-        else { blk = wl.b_v1; lr = r - rm.RV1; lbo = wg_lbo(kNV1); }
+        if (dst[it] < 0) continue;
         const float4 v = ld[it];
-        const float4 h = make_float4(tc::tf32_hi(v.x), tc::tf32_hi(v.y), tc::tf32_hi(v.z), tc::tf32_hi(v.w));
-        const int off = blk + c * lbo + lr * 16;
-        *reinterpret_cast<float4*>(hi + off) = h;
-        *reinterpret_cast<float4*>(lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        const float4 h = make_float4(tc::tf32_hi_fast(v.x), tc::tf32_hi_fast(v.y), tc::tf32_hi_fast(v.z), tc::tf32_hi_fast(v.w));
+        *reinterpret_cast<float4*>(hi + dst[it]) = h;
+        *reinterpret_cast<float4*>(lo + dst[it]) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
       }
       if (tid < 32) {             // x^T: feature rows 4 (tid & 1) .. +3, sample tid / 2 of the stage
         const int sl = tid >> 1, f0 = 4 * (tid & 1);
         const float vv[4] = {ldx.x, ldx.y, ldx.z, ldx.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float h = tc::tf32_hi(vv[q]);
-          const int off = wl.b_x + (sl >> 2) * wg_lbo(kNX) + (f0 + q) * 16 + (sl & 3) * 4;
+          const float h = tc::tf32_hi_fast(vv[q]);
+          const int off = wl.b_small + (sl >> 2) * wg_lbo(kSmN) + (kSmX + f0 + q) * 16 + (sl & 3) * 4;
           *reinterpret_cast<float*>(hi + off) = h;
           *reinterpret_cast<float*>(lo + off) = vv[q] - h;
         }
       }
     };
     uint32_t dpar[2] = {0u, 0u};
-    if (n_stage > 0) load_stage(0);
-    for (int64_t st = 0; st < n_stage; ++st) {
+    if (n_stage > 0) load_stage(0, ldA, ldxA);
+    if (n_stage > 1) load_stage(1, ldB, ldxB);
+    auto step = [&](int64_t st, float4 (&ld)[kItems], float4& ldx) {
       const int buf = static_cast<int>(st & 1);
+#ifdef PINN_TIMELINE
+      const bool tlon = blockIdx.x == 0 && tid == 0 && st >= 16 && st < 80;
+      if (tlon) g_tlw[1][st - 16][0] = clock64();
+#endif
       if (st >= 2) { tc::mbar_wait(&done[buf], dpar[buf]); dpar[buf] ^= 1u; }     // the MMAs of stage st-2 have drained this buffer
-      store_stage(buf);
-      if (st + 1 < n_stage) load_stage(st + 1);
+#ifdef PINN_TIMELINE
+      if (tlon) g_tlw[1][st - 16][1] = clock64();
+#endif
+      store_stage(buf, ld, ldx);
+#ifdef PINN_TIMELINE
+      if (tlon) g_tlw[1][st - 16][2] = clock64();
+#endif
+      if (st + 2 < n_stage) load_stage(st + 2, ld, ldx);
       tc::fence_proxy_async();
       tc::mbar_arrive(&full[buf]);
+#ifdef PINN_TIMELINE
+      if (tlon) g_tlw[1][st - 16][3] = clock64();
+#endif
+    };
+    for (int64_t st = 0; st < n_stage; st += 2) {
+      step(st, ldA, ldxA);
+      if (st + 1 < n_stage) step(st + 1, ldB, ldxB);
     }
     // drain: the last (up to) two commits
     for (int64_t st = n_stage > 2 ? n_stage - 2 : 0; st < n_stage; ++st) {
@@ -288,7 +304,7 @@ wgrad_tc_kernel(WgradArgs a, ParamLayout lay, WgLayout wl, RowMap rm) {
       const int lane_row = warp * 32 + (tid & 31);
       const uint32_t tl = tmem_base_s + (static_cast<uint32_t>(warp * 32) << 16);
       const bool have = n_stage > 0;
-      auto read16 = [&](int col, float* v) {
+      auto read16 = [&](int col, float (&v)[16]) {
         if (have) { tc::tmem_ld16(tl + static_cast<uint32_t>(col), v); tc::tmem_wait_ld(); }
         else {
 #pragma unroll
@@ -296,70 +312,57 @@ wgrad_tc_kernel(WgradArgs a, ParamLayout lay, WgLayout wl, RowMap rm) {
         }
       };
       float v[16];
-      // trunk layers l >= 1: delta_l sits in big block (l-1)/2, lanes 64 ((l-1) % 2) + j; product column block of a_{l-1}
+      // trunk layers l >= 1: delta_l = lanes 64 h + j of big block i, a_{l-1} = columns 64 h + k of its B block (i = (l-1)/2, h = (l-1)%2)
 #pragma unroll
       for (int l = 1; l < L; ++l) {
-        const int j = lane_row - 64 * ((l - 1) & 1);
-        const int col = WgCols<L>::act0 + kNAct * (l - 1);
+        const int i = (l - 1) >> 1, h = (l - 1) & 1;
+        const int col0 = (i == 0 ? 0 : wg_big_n(L, 0)), ones_col = col0 + wg_big_n(L, i) - 16;
+        const int j = lane_row - 64 * h;
+        const bool mine = j >= 0 && j < 64;
 #pragma unroll
-        for (int c = 0; c < kNAct; c += 16) {
-          read16(col + c, v);
-          if (j >= 0 && j < 64) {
-            if (c < 64) {
+        for (int c = 0; c < 64; c += 16) {
+          read16(col0 + 64 * h + c, v);
+          if (mine) {
 #pragma unroll
-              for (int q = 0; q < 16; ++q) part[lay.offW[l] + j * 64 + c + q] = v[q] * a.act_scale;
-            } else part[lay.offb[l] + j] = v[0];
+            for (int q = 0; q < 16; ++q) part[lay.offW[l] + j * 64 + c + q] = v[q] * a.act_scale;
           }
         }
+        read16(ones_col, v);
+        if (mine) part[lay.offb[l] + j] = v[0];
       }
-      // small block against a_{L-1}: lanes 64..95 = dWv0 / dbv0, lane 96 = dWp / dbp
-      {
-        const int col = WgCols<L>::act0 + kNAct * (L - 1);
+      // small product
 #pragma unroll
-        for (int c = 0; c < kNAct; c += 16) {
-          read16(col + c, v);
-          if (lane_row >= 64 && lane_row < 96) {
-            const int j = lane_row - 64;
-            if (c < 64) {
+      for (int c = 0; c < 64; c += 16) {        // columns 0..63 = a_{L-1}: lanes 64..95 -> dWv0, lane 96 -> dWp
+        read16(COL_SMALL + c, v);
+        if (lane_row >= 64 && lane_row < 96) {
 #pragma unroll
-              for (int q = 0; q < 16; ++q) part[lay.offWv0 + j * 64 + c + q] = v[q] * a.act_scale;
-            } else part[lay.offbv0 + j] = v[0];
-          } else if (lane_row == 96) {
-            if (c < 64) {
+          for (int q = 0; q < 16; ++q) part[lay.offWv0 + (lane_row - 64) * 64 + c + q] = v[q] * a.act_scale;
+        } else if (lane_row == 96) {
 #pragma unroll
-              for (int q = 0; q < 16; ++q) part[lay.offWp + c + q] = v[q] * a.act_scale;
-            } else part[lay.offbp] = v[0];
-          }
+          for (int q = 0; q < 16; ++q) part[lay.offWp + c + q] = v[q] * a.act_scale;
         }
       }
-      // against x^T: lanes 0..63 = dW0 (8 columns) / db0 (column 8)
-      read16(WgCols<L>::x, v);
+      read16(COL_SMALL + 64, v);                // column 64 = ones (every bias); 65..72 = x^T; 73..79 = av0[0..7)
       if (lane_row < 64) {
+        part[lay.offb[0] + lane_row] = v[0];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) part[lay.offW[0] + lane_row * 8 + q] = v[q];
-        part[lay.offb[0] + lane_row] = v[8];
+        for (int q = 0; q < 8; ++q) part[lay.offW[0] + lane_row * 8 + q] = v[1 + q];
+      } else if (lane_row < 96) part[lay.offbv0 + lane_row - 64] = v[0];
+      else if (lane_row == 96) part[lay.offbp] = v[0];
+      else if (lane_row < 113) part[lay.offbv1 + lane_row - 97] = v[0];
+      else if (lane_row == 113) part[lay.offbv2] = v[0];
+      if (lane_row >= 97 && lane_row < 113) {
+#pragma unroll
+        for (int q = 0; q < 7; ++q) part[lay.offWv1 + (lane_row - 97) * 32 + q] = v[9 + q];
       }
-      // against av0: lanes 97..112 = dWv1 (32 columns) / dbv1 (column 32)
 #pragma unroll
-      for (int c = 0; c < kNV0; c += 16) {
-        read16(WgCols<L>::v0 + c, v);
-        if (lane_row >= 97 && lane_row < 113) {
-          const int j = lane_row - 97;
-          if (c < 32) {
+      for (int c = 80; c < 128; c += 16) {      // columns 80..104 = av0[7..32), 105..120 = av1
+        read16(COL_SMALL + c, v);
 #pragma unroll
-            for (int q = 0; q < 16; ++q) part[lay.offWv1 + j * 32 + c + q] = v[q];
-          } else part[lay.offbv1 + j] = v[0];
-        }
-      }
-      // against av1: lane 113 = dWv2 (16 columns) / dbv2 (column 16)
-#pragma unroll
-      for (int c = 0; c < kNV1; c += 16) {
-        read16(WgCols<L>::v1 + c, v);
-        if (lane_row == 113) {
-          if (c < 16) {
-#pragma unroll
-            for (int q = 0; q < 16; ++q) part[lay.offWv2 + q] = v[q];
-          } else part[lay.offbv2] = v[0];
+        for (int q = 0; q < 16; ++q) {
+          const int col = c + q;
+          if (col < kSmV1) { if (lane_row >= 97 && lane_row < 113) part[lay.offWv1 + (lane_row - 97) * 32 + col - kSmV0] = v[q]; }
+          else if (col < kSmV1 + 16) { if (lane_row == 113) part[lay.offWv2 + col - kSmV1] = v[q]; }
         }
       }
     }
@@ -912,6 +915,11 @@ int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropPa
 
 }  // namespace pinn
 
+#ifdef PINN_TIMELINE
+extern "C" int pinn_debug_timeline_wgrad(long long* host_out) {
+  return static_cast<int>(cudaMemcpyFromSymbol(host_out, pinn::g_tlw, sizeof(pinn::g_tlw)));
+}
+#endif
 // Ablation / test switch for the tensor-core backward path (1 = on).
 extern "C" int pinn_set_tensor_core_bwd(int enable) {
   int prev = pinn::g_tc_bwd_enabled;
