@@ -573,6 +573,22 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
     tc::tmem_st8(a_lo_t + lane_sel + static_cast<uint32_t>(c0), lo);
   };
 
+  // keep bits of this thread's 32 units [c0, c0 + 32) of dropout layer `layer` (bit q = unit c0 + q); computed
+  // while the tensor core works (they depend on nothing it produces)
+  auto keep_bits32 = [&](const KeepSrc<INJ>& ks, bool active, uint32_t layer, int c0) {
+    uint32_t bits = 0xffffffffu;
+    if (active) {
+      bits = 0u;
+#pragma unroll
+      for (int g = 0; g < 32; g += 8) {
+        bool k[8];
+        ks.get8(dp, layer, static_cast<uint32_t>(c0 + g), layer * H, k);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) bits |= (k[q] ? 1u : 0u) << (g + q);
+      }
+    }
+    return bits;
+  };
   const int64_t n_tiles = (a.n + kBTile - 1) / kBTile;
   for (int64_t tile = static_cast<int64_t>(blockIdx.x) * 2 + grp; tile < n_tiles; tile += static_cast<int64_t>(gridDim.x) * 2) {
     const int64_t s = tile * kBTile + row;
@@ -624,29 +640,26 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
 #pragma unroll 1
     for (int l = 1; l < L; ++l) {       // rolled: one copy of the layer body keeps the kernel inside the I-cache
       if constexpr (!RES) wcommit_rows(b_hi, b_lo, wpre, t256, wscale);
+      uint32_t bits = 0u;
       run_mma(lay.wf_hi[l], lay.wf_lo[l], H * 16, idesc64, [&] {
         if constexpr (!RES) {
           if (l + 1 < L) wprefetch(wpre, net.W[l + 1], nullptr, H, t256);
           else wprefetch(wpre, net.Wv0, net.Wp, 32, t256);
         }
+        bits = keep_bits32(ks, active, static_cast<uint32_t>(l), cb);
       });
       const float* bl = smem + lay.b[l] + cb;
-      uint32_t bits = 0u;
 #pragma unroll 1
       for (int g = 0; g < HH; g += 8) {
         float z[8];
         tc::tmem_ld8(d_lane + cb + g, z);
         tc::tmem_wait_ld();
-        bool k[8] = {true, true, true, true, true, true, true, true};
-        if (active) ks.get8(dp, static_cast<uint32_t>(l), static_cast<uint32_t>(cb + g), static_cast<uint32_t>(l * H), k);
         const float4 bA = *reinterpret_cast<const float4*>(bl + g), bB = *reinterpret_cast<const float4*>(bl + g + 4);
         const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+        const uint32_t kbg = bits >> g;
         float v[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          v[q] = k[q] ? tanh_pre(fmaf(z[q], kTanhArg, bb[q])) : 0.f;
-          bits |= (k[q] ? 1u : 0u) << (g + q);
-        }
+        for (int q = 0; q < 8; ++q) v[q] = ((kbg >> q) & 1u) ? tanh_pre(fmaf(z[q], kTanhArg, bb[q])) : 0.f;
         store_pn8(cb + g, v);
 #pragma unroll
         for (int q = 0; q < 8; ++q) trow[static_cast<size_t>(row_act(a.rm, l) + cb + g + q) * kBTile] = valid ? v[q] : 0.f;
@@ -655,10 +668,13 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
     }
     // ---- heads: rows 0..31 = Wv0, row 32 = Wp, rows 33.. = 0 (N = 48 of the 64 staged rows are read)
     if constexpr (!RES) wcommit_rows(b_hi, b_lo, wpre, t256, wscale);
-    run_mma(lay.wf_hi[L], lay.wf_lo[L], H * 16, idesc48, [&] { if constexpr (!RES) wprefetch(wpre, net.Wv0, net.Wp, 32, t256); });
+    kb[L] = 0u;
+    run_mma(lay.wf_hi[L], lay.wf_lo[L], H * 16, idesc48, [&] {
+      if constexpr (!RES) wprefetch(wpre, net.Wv0, net.Wp, 32, t256);
+      if (half == 0) kb[L] = keep_bits32(ks, active, static_cast<uint32_t>(L), 0);
+    });
     float du = 0.f;
     float dzv0[HH];                      // half 0: d z of the variance head's first layer; half 1: unused
-    kb[L] = 0u;
     if (half == 0) {
       float v0[HH], zz[16];
       tc::tmem_ld16(d_lane, v0);
@@ -669,13 +685,9 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
       const float* bv0 = smem + lay.bv0;
 #pragma unroll
       for (int g = 0; g < HH; g += 8) {
-        bool k[8] = {true, true, true, true, true, true, true, true};
-        if (active) ks.get8(dp, static_cast<uint32_t>(L), static_cast<uint32_t>(g), static_cast<uint32_t>(L * H), k);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          v0[g + q] = k[q] ? tanh_pre(fmaf(v0[g + q], kTanhArg, bv0[g + q])) * wscale : 0.f;   // scaled, as K2b expects
-          kb[L] |= (k[q] ? 1u : 0u) << (g + q);
-        }
+        for (int q = 0; q < 8; ++q)
+          v0[g + q] = ((kb[L] >> (g + q)) & 1u) ? tanh_pre(fmaf(v0[g + q], kTanhArg, bv0[g + q])) * wscale : 0.f;   // scaled, as K2b expects
       }
       const float* Wv1 = smem + lay.Wv1;
       const float* bv1 = smem + lay.bv1;
