@@ -293,19 +293,26 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 8 * 4, "d2h_bytes_per_step": n * 3 * 4},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": mc_tflops, "peak": pk["bf16"], "unit": "TFLOP/s",
-                     "frac": mc_tflops / pk["bf16"], "traffic": 32.2e6 * n / 1e6,
-                     "kernel": "mlp_tc_kernel<MC> (tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators)",
+                     "frac": mc_tflops / pk["bf16"], "traffic": 32.1e6 * n / 1e6,
+                     "kernel": "mlp_tc_kernel<MC> (tcgen05.mma kind::tf32 with A in tensor memory, 3xTF32 split, "
+                               "one MMA warp per 128-sample group)",
                      "peak_source": pk["src"],
                      "note": "achieved = algorithmic FLOPs (21 664 per sample*pass) / CUDA-event time of the launch. The "
                              "contractions run as 3 TF32 MMAs per product (fp32 parity), and TF32 dense peak is half the "
                              "bf16 figure used as `peak`, so the tensor pipe does 6x this fraction of its own peak "
-                             "(ncu: sm__pipe_tensor_cycles_active ~15-20 %); the kernel is bounded by the CUDA-core "
-                             "epilogue (tanh + Philox + operand re-split), see DESIGN.md section 4. `traffic` is the ncu "
-                             "dram read+write of one launch at N=1M (profiles/r1_v3_mc_tc.summary.txt), scaled by n; "
+                             "(ncu: sm__pipe_tensor_cycles_active, profiles/r1_final2_mc.summary.txt); the kernel is "
+                             "bounded by the CUDA-core epilogue (2 MUFU + ~12 ALU/FMA ops per activation, 5.6 Philox "
+                             "instructions per draw) and by the ~1000-clk latency of each 24-MMA batch, see DESIGN.md "
+                             "section 4. `traffic` is the ncu dram read+write of one launch at N=1M, scaled by n; "
                              f"vs the fp32 FFMA peak (74.5 TFLOP/s) the kernel stands at {mc_tflops / 74.5:.2f}x"},
         "train": {"steps_per_s": steps_tr / t_tr, "ms_per_step": 1e3 * t_tr / steps_tr,
                   "global_batch": world * n, "tflops": world * n * FLOP_PER_TRAIN_SAMPLE / (t_tr / steps_tr) / 1e12,
-                  "what": "train_dnn step: K2a (tcgen05 fwd+loss+dgrad) + K2b (FFMA wgrad) + partial reduce + "
+                  # K2a writes and K2b reads a 496-row x 512 B table per 128-sample tile (3x64 net): 2 x 1.98 KB per sample
+                  "hbm": {"bytes_per_sample": 2 * 496 * 4 + 36, "unit": "GB/s",
+                          "achieved": n * (2 * 496 * 4 + 36) / (t_tr / steps_tr) / 1e9,
+                          "frac_of_peak": n * (2 * 496 * 4 + 36) / (t_tr / steps_tr) / 1e9 / pk["hbm"]},
+                  "what": "train_dnn step: K2a (tcgen05 fwd+loss+dgrad, writes a transposed 2 KB/sample row table) + K2b "
+                          "(tcgen05 3xTF32 weight gradients, HBM-bound on that table: see profiles/) + partial reduce + "
                           + ("NCCL all-reduce of the flat grad bucket + " if world > 1 else "") + "fused Adam/StepLR"},
         "roofline_residual": {"bound": "hbm", "achieved": nb * RES_BYTES_PER_SAMPLE / (t_resb / K_) / 1e9, "peak": pk["hbm"],
                               "unit": "GB/s", "frac": nb * RES_BYTES_PER_SAMPLE / (t_resb / K_) / 1e9 / pk["hbm"],
@@ -317,10 +324,10 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        mc_rate, tr_rate, t1, t2 = cpu_port_rates(200_000, 100_000, threads)
+        mc_rate, tr_rate, t1, t2 = cpu_port_rates(1_000_000, 200_000, threads)
         line["cpu_baseline"] = {"value": mc_rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"get_MC_samples port, N=200000 x T'=1 ({t1:.1f} s); train_dnn port 1 step at "
-                                          f"N=100000 ({t2:.1f} s)",
+                                "sample": f"get_MC_samples port, N=1000000 x T'=1 ({t1:.1f} s); train_dnn port 1 step at "
+                                          f"N=200000 ({t2:.1f} s)",
                                 "train_steps_per_s_at_1M": tr_rate}
     print(json.dumps(line), flush=True)
     if world > 1:
