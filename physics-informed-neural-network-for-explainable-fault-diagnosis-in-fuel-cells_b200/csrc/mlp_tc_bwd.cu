@@ -4,17 +4,15 @@
 //       as in mlp_tc.cu) forward recompute AND dgrad on tcgen05 (3xTF32, fp32-accurate):
 //         stage a0 -> [W1] -> a1 -> [W2] -> a2 -> [Wv0;Wp] -> heads + loss gradients
 //         -> [ (Wv0;Wp)^T ] -> d a2 -> [W2^T] -> d a1 -> [W1^T] -> d a0
-//       Every contraction is a K-major x K-major MMA: the B operand (one layer's weights, or
-//       their transpose for dgrad) is re-split into the group's 32 KB B planes right before
-//       use -- 16 values per thread -- instead of keeping 2 x 88 KB of planes resident, so
-//       two groups fit in 192 KB and overlap each other's MMAs and epilogues.  Masked
-//       activations and pre-activation deltas of every layer go to HBM ([N][width] fp32 rows,
-//       128 B per thread per layer); keep-bits ride in registers so Philox runs once.
-//  K2b  wgrad_kernel : dW_l = delta_l^T a_{l-1} for all seven weight tensors and the bias
-//       column sums, contraction over the batch, 8x8 FFMA2 register tiles over 16-sample stages
-//       that TMA bulk copies (cp.async.bulk + mbarrier transaction bytes) double-buffer into
-//       shared memory; per-CTA partials -> grad_reduce_kernel (fixed-order,
-//       deterministic).
+//       The A operand (activations forward, deltas backward) lives in tensor memory; every B
+//       operand is a K-major weight plane pair (forward: W rows; dgrad: W^T), resident in
+//       shared memory for L <= 3 and re-split per phase for deeper nets.  Masked activations
+//       and pre-activation deltas of every layer go to HBM as a TRANSPOSED per-tile row table
+//       (RowMap below); keep-bits ride in registers so Philox runs once.
+//  K2b  wgrad_tc_kernel : every weight and bias gradient as one 3xTF32 accumulation over
+//       samples, reading that row table (K-major: the contraction index is the sample);
+//       accumulators resident in tensor memory; per-CTA partials -> grad_reduce2_kernel
+//       (fixed-order, deterministic).
 //
 // (MN-major TF32 operands, which would allow an all-on-chip variant, require CUTLASS's
 // SW128_32B swizzled layout; with the plain interleaved layout the MMA is silently dropped --
