@@ -33,6 +33,8 @@ constexpr int kBH = 64, kBTile = 128;
 //  * a warp of K2a (32 consecutive samples) writes / re-reads one 128-byte line per feature:
 //    fully coalesced.  The former [sample][feature] rows cost 32 sectors per warp access and made
 //    K2a's stores and re-loads 0.48 ms of its 1.23 ms (profiles/README.md, ablate_k2a).
+// Inside a tile the table is stored as 8 slabs of 16 samples ([slab][row][16]): the 16-sample stage K2b
+// streams is one contiguous 31 KB block, and a K2a warp still touches two full 64-byte segments per feature.
 // Row order inside a tile (L hidden layers, nbig = ceil((L-1)/2) blocks of 128 rows):
 //   [0, 128 nbig)          : deltas of layers 1..L-1, 64 rows each          (A operands "big")
 //   RA + [0, 64)           : deltas of layer 0                               (A operand "small", 128 rows)
@@ -40,6 +42,7 @@ constexpr int kBH = 64, kBTile = 128;
 //   RA + [97, 113), +113   : variance-head layer-1 deltas, d loss / d v      (rows 114..127 unused)
 //   RB + 64 l + [0, 64)    : masked activations of layer l (WITHOUT the dropout scale)   (B operands)
 //   RV0 + [0, 32)          : variance-head layer-0 activations (scaled),   RV1 + [0, 16): layer 1
+constexpr int kRowStride = 16;       // floats between consecutive feature rows inside a slab (= samples per slab = K2b stage)
 struct RowMap {
   int L, nbig, RA, RB, RV0, RV1, rows;
 };
@@ -227,11 +230,11 @@ wgrad_tc_kernel(WgradArgs a, ParamLayout lay, WgLayout wl, RowMap rm) {
     auto load_stage = [&](int64_t st, float4 (&ld)[kItems], float4& ldx) {
       const int64_t tile = t_begin + st / (kBTile / kWgStage);
       const int s0 = static_cast<int>(st % (kBTile / kWgStage)) * kWgStage;
-      const float* base = a.rows + static_cast<size_t>(tile) * rm.rows * kBTile + s0;
+      const float* base = a.rows + static_cast<size_t>(tile) * rm.rows * kBTile + static_cast<size_t>(s0 / kWgStage) * rm.rows * kRowStride;   // one contiguous slab
 #pragma unroll
       for (int it = 0; it < kItems; ++it) {
         const int i = tid + it * kWgLoaders;
-        if (dst[it] >= 0) ld[it] = __ldcs(reinterpret_cast<const float4*>(base + static_cast<size_t>(i >> 2) * kBTile) + (i & 3));
+        if (dst[it] >= 0) ld[it] = __ldcs(reinterpret_cast<const float4*>(base) + i);
       }
       if (tid < 32) {             // x[N][8]: thread -> (sample tid / 2, 4 features)
         const int64_t s = tile * kBTile + s0 + (tid >> 1);
@@ -591,7 +594,8 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
   for (int64_t tile = static_cast<int64_t>(blockIdx.x) * 2 + grp; tile < n_tiles; tile += static_cast<int64_t>(gridDim.x) * 2) {
     const int64_t s = tile * kBTile + row;
     const bool valid = s < a.n;
-    float* const trow = a.rows + static_cast<size_t>(tile) * a.rm.rows * kBTile + row;     // this sample's column of the tile's row table
+    // this sample's column of the tile's row table: slab (row / 16) of the tile, position row % 16 inside each 16-sample row
+    float* const trow = a.rows + static_cast<size_t>(tile) * a.rm.rows * kBTile + static_cast<size_t>(row >> 4) * a.rm.rows * kRowStride + (row & 15);
     const bool active = drop_on && (!INJ || valid);     // injected masks: tail rows of the last tile have no mask row
     const uint64_t sg = static_cast<uint64_t>(dp.sample_offset + s);
     KeepSrc<INJ> ks;
@@ -632,7 +636,7 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
         }
         store_pn8(cb + g, v);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) trow[static_cast<size_t>(row_act(a.rm, 0) + cb + g + q) * kBTile] = valid ? v[q] : 0.f;
+        for (int q = 0; q < 8; ++q) trow[static_cast<size_t>(row_act(a.rm, 0) + cb + g + q) * kRowStride] = valid ? v[q] : 0.f;
       }
     }
 #pragma unroll 1
@@ -660,7 +664,7 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
         for (int q = 0; q < 8; ++q) v[q] = ((kbg >> q) & 1u) ? tanh_pre(fmaf(z[q], kTanhArg, bb[q])) : 0.f;
         store_pn8(cb + g, v);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) trow[static_cast<size_t>(row_act(a.rm, l) + cb + g + q) * kBTile] = valid ? v[q] : 0.f;
+        for (int q = 0; q < 8; ++q) trow[static_cast<size_t>(row_act(a.rm, l) + cb + g + q) * kRowStride] = valid ? v[q] : 0.f;
       }
       kb[l] = bits;
     }
@@ -744,19 +748,19 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
         dzv0[i] = dzv0[i] * mk * (1.0f - av * av);
       }
       {   // rows of an invalid sample (tail of the last tile) are written as zeros: K2b sums whole tiles
-        float* const pa = trow + static_cast<size_t>(a.rm.RA) * kBTile;
+        float* const pa = trow + static_cast<size_t>(a.rm.RA) * kRowStride;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          trow[static_cast<size_t>(a.rm.RV0 + i) * kBTile] = valid ? v0[i] : 0.f;
-          pa[static_cast<size_t>(64 + i) * kBTile] = dzv0[i];
+          trow[static_cast<size_t>(a.rm.RV0 + i) * kRowStride] = valid ? v0[i] : 0.f;
+          pa[static_cast<size_t>(64 + i) * kRowStride] = dzv0[i];
         }
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          trow[static_cast<size_t>(a.rm.RV1 + k) * kBTile] = valid ? v1[k] : 0.f;
-          pa[static_cast<size_t>(97 + k) * kBTile] = dz1[k];
+          trow[static_cast<size_t>(a.rm.RV1 + k) * kRowStride] = valid ? v1[k] : 0.f;
+          pa[static_cast<size_t>(97 + k) * kRowStride] = dz1[k];
         }
-        pa[static_cast<size_t>(96) * kBTile] = du;
-        pa[static_cast<size_t>(113) * kBTile] = dv;
+        pa[static_cast<size_t>(96) * kRowStride] = du;
+        pa[static_cast<size_t>(113) * kRowStride] = dv;
       }
     }
     // ============================ backward ============================
@@ -780,7 +784,7 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
       float apre[HH];            // this thread's masked activations of layer l, prefetched during the MMA
       run_mma(lay.wt_hi[l + 1], lay.wt_lo[l + 1], kLboT, idesc64, [&] {
 #pragma unroll
-        for (int q = 0; q < HH; ++q) apre[q] = trow[static_cast<size_t>(row_act(a.rm, l) + cb + q) * kBTile];
+        for (int q = 0; q < HH; ++q) apre[q] = trow[static_cast<size_t>(row_act(a.rm, l) + cb + q) * kRowStride];
         if constexpr (!RES) { if (l > 0) wprefetch(wpre, net.W[l], nullptr, H, t256); }
       });
       const uint32_t kbl = kb[l];
@@ -794,7 +798,7 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
         for (int q = 0; q < 8; ++q)    // z already carries the dropout scale (folded into W^T); dropped units have a = 0
           dz[q] = ((kbl >> (g + q)) & 1u) ? z[q] * fmaf(-aa[q], aa[q], 1.0f) : 0.f;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) trow[static_cast<size_t>(row_del(a.rm, l) + cb + g + q) * kBTile] = dz[q];
+        for (int q = 0; q < 8; ++q) trow[static_cast<size_t>(row_del(a.rm, l) + cb + g + q) * kRowStride] = dz[q];
         if (l > 0) store_pn8(cb + g, dz);
       }
       if constexpr (!RES) { if (l > 0) wcommit_transposed(b_hi, b_lo, wpre, t256, wscale); }
