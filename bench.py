@@ -255,6 +255,20 @@ def run_ours(args):
     res_exp = lambda: K.residuals(xb, ub, None, sc, lam, fam_all, sums=sums, cols=cols, want_cols=True)
     t_exp, _ = timed(res_exp, K_, W_)
     del xb, ub, yb, cols
+    # --- config 5 share (fleet export): one stack of n timesteps -> 22-column float64 rows (K4 sweep at T_PASSES,
+    # eval forward, export-form K3, row writer K5) and the RF(t) risk series of 8 such stacks (K5 scans)
+    from b200pinn.export import export_rows_device
+    from b200pinn.rf import rf_device
+    seg = [0] + [n * (i + 1) // 13 for i in range(13)]                   # normal segment + 12 labelled fault segments (04:75-80)
+    yv32 = model.u.reshape(-1).contiguous()
+    exp = lambda: export_rows_device(model, xd, yv32, seg, 12, T_PASSES, P_MC, sx, sy, seed=seed)
+    t_export, _ = timed(exp, max(3, K_ // 2), 2)
+    rows = exp()
+    fleet = rows.unsqueeze(0).expand(8, -1, -1).contiguous()
+    rfk = lambda: rf_device(fleet)
+    t_rf, _ = timed(rfk, max(3, K_ // 2), 2)
+    n_exp = max(3, K_ // 2)
+    del fleet, rows
     # --- e2e: public API, host tensors in pinned memory, results back on the host
     Xp = X.pin_memory()
     import contextlib
@@ -322,6 +336,12 @@ def run_ours(args):
                               "export_form": {"bytes_per_sample": 36 + 4 * 21, "ms": 1e3 * t_exp / K_,
                                               "gbs": nb * (36 + 4 * 21) / (t_exp / K_) / 1e9}},
     }
+    line["fleet"] = {"what": "config 5 per-GPU share: export of one 1M-timestep stack (MC sweep T=50 + eval forward + export-form "
+                             "residuals + float64 22-column row writer with segment smoothing) and RF(t) for 8 stacks "
+                             "(mu/sigma, dead-zone norms, C(t) scan, logistic, EMA, first alarm)",
+                     "export_rows_per_s": world * n * n_exp / t_export, "export_ms_per_stack": 1e3 * t_export / n_exp,
+                     "rf_rows_per_s": world * 8 * n * n_exp / t_rf, "rf_ms_per_8_stacks": 1e3 * t_rf / n_exp,
+                     "rf_hbm_gbs": 8 * n * (22 * 8 + 2 * 8) * n_exp / t_rf / 1e9}
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
         mc_rate, tr_rate, t1, t2 = cpu_port_rates(1_000_000, 200_000, threads)
