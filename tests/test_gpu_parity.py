@@ -604,3 +604,66 @@ def test_tensor_core_backward_matches_ffma_and_oracle(layers, n):
     for nm, shp, o in zip(names, shapes, offs):
         ref = G[nm]
         assert nrel(fc[o:o + ref.size].reshape(shp), ref.reshape(shp)) < GRAD_TOL, nm
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 127, 128, 129, 257, 40000])
+def test_tensor_core_backward_tile_edges(n):
+    """K2a's transposed row table + tensor-core K2b at tile / stage boundaries (1 sample, 16-sample
+    stage edges, 128-sample tile edges, more tiles than SMs x 2): gradients and loss sums vs the FFMA
+    kernel on the same Philox stream, and vs the fp64 oracle with injected masks (small n)."""
+    from b200pinn import kernels as K
+    from b200pinn.synthetic import make_scaled_dataset
+
+    layers, p = [8, 64, 64, 64, 1], 0.3
+    x, y, _, _ = make_scaled_dataset(max(n, 64), seed=21)
+    x, y = x[:n], y[:n]
+    dnn = random_net(layers, 9)
+    net = K.net_from_module(dnn)
+    xd, yd = torch.tensor(x, device=dev()), torch.tensor(y, device=dev()).reshape(-1).contiguous()
+    a, sa = K.mlp_backward(net, xd, K.make_dropout(p, seed=11, pass_offset=2), y=yd, n_global=n)
+    prev = K.set_tensor_core_bwd(False)
+    try:
+        b, sb = K.mlp_backward(net, xd, K.make_dropout(p, seed=11, pass_offset=2), y=yd, n_global=n)
+    finally:
+        K.set_tensor_core_bwd(prev)
+    assert np.allclose(t2n(sa), t2n(sb), rtol=1e-5)
+    names, shapes, offs, _ = K.param_layout(net.width, net.n_hidden)
+    fa, fb = t2n(a), t2n(b)
+    for nm, shp, o in zip(names, shapes, offs):
+        cnt = int(np.prod(shp))
+        assert nrel(fa[o:o + cnt], fb[o:o + cnt]) < GRAD_TOL, nm
+    if n <= 300:
+        mk = rand_masks(np.random.default_rng(4), 1, n, layers, p)[0]
+        c, _ = K.mlp_backward(net, xd, K.make_dropout(p, seed=1, masks=torch.tensor(mk, device=dev()), mask_rows=n), y=yd, n_global=n)
+        ms64 = split_masks(mk, layers, p, np.float64)
+        P = params_np(dnn)
+        o64, l64 = O.dnn_forward(P, x, ms64, np.float64)
+        G = O.dnn_backward(P, x, ms64, *O.aleatoric_loss_grads(y, o64, l64))
+        fc = t2n(c)
+        for nm, shp, o in zip(names, shapes, offs):
+            ref = G[nm]
+            assert nrel(fc[o:o + ref.size].reshape(shp), ref.reshape(shp)) < GRAD_TOL, nm
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,T", [(1, 3), (127, 5), (129, 4), (38000, 2)])
+def test_mc_tensor_core_tile_edges(n, T):
+    """Warp-specialised MC kernel at tile boundaries and with more tiles than two per SM: tensor-core
+    vs FFMA path on the same Philox stream."""
+    import b200pinn
+    from b200pinn import kernels as K
+    from b200pinn.synthetic import make_scaled_dataset
+
+    layers, p = [8, 64, 64, 64, 1], 0.4
+    x, _, _, _ = make_scaled_dataset(max(n, 64), seed=23)
+    xd = torch.tensor(x[:n], device=dev())
+    dnn = random_net(layers, 10)
+    a = b200pinn.mc_dropout_device(dnn, xd, T, p, seed=77)
+    prev = K.set_tensor_core_path(False)
+    try:
+        b = b200pinn.mc_dropout_device(dnn, xd, T, p, seed=77)
+    finally:
+        K.set_tensor_core_path(prev)
+    for k in ("pred_mean", "a_u", "e_u"):
+        assert nrel(t2n(a[k]), t2n(b[k])) < MC_TOL, k
