@@ -28,6 +28,50 @@ def mc_dropout_device(dnn, x: torch.Tensor, mc_times: int, dropout: float, seed=
     return K.mc_dropout(net, x.detach().float(), int(mc_times), drop, finalize=True, raw=raw)
 
 
+_SIDE_STREAMS: dict = {}
+PIPELINE_MIN_ROWS = 1 << 16      # host inputs at least this long are swept in chunks (copy / compute overlap)
+PIPELINE_CHUNKS = 4
+
+
+def _mc_host_pipelined(dnn, X, mc_times, dropout, pass_offset, dev):
+    """Host tensor in, host arrays out, for long inputs: the rows are cut into a few chunks whose
+    H2D copy, sweep (K4) and D2H copy run on three streams, so only the first chunk's upload and the
+    last chunk's download are exposed.  Philox counters are keyed on the global row index
+    (``sample_offset``), so the result is identical to the single-launch sweep."""
+    n = X.shape[0]
+    Xc = X.detach()
+    if Xc.dtype != torch.float32 or not Xc.is_contiguous():
+        Xc = Xc.float().contiguous()
+    host = torch.empty(3, n, dtype=torch.float32, pin_memory=True)
+    xd = torch.empty(n, Xc.shape[1], device=dev, dtype=torch.float32)
+    cur = torch.cuda.current_stream(dev)
+    if dev not in _SIDE_STREAMS:
+        _SIDE_STREAMS[dev] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+    s_in, s_out = _SIDE_STREAMS[dev]
+    s_in.wait_stream(cur)
+    # chunk = a whole number of "waves" (two 128-row tiles per SM) so that no chunk but the last ends on a partial wave
+    wave = 256 * torch.cuda.get_device_properties(dev).multi_processor_count
+    step = max(wave, (-(-n // PIPELINE_CHUNKS) + wave - 1) // wave * wave)
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        with torch.cuda.stream(s_in):
+            xd[lo:hi].copy_(Xc[lo:hi], non_blocking=True)
+            up = torch.cuda.Event()
+            up.record(s_in)
+        cur.wait_event(up)
+        out = mc_dropout_device(dnn, xd[lo:hi], mc_times, dropout, sample_offset=lo, pass_offset=pass_offset)
+        done = torch.cuda.Event()
+        done.record(cur)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(done)
+            for i, k in enumerate(("pred_mean", "a_u", "e_u")):
+                host[i, lo:hi].copy_(out[k], non_blocking=True)
+                out[k].record_stream(s_out)
+    xd.record_stream(s_in)
+    s_out.synchronize()
+    return host[0].numpy(), host[1].numpy(), host[2].numpy()
+
+
 def get_MC_samples(network, X, x_scal, mc_times=64, dropout=0.6):
     dnn = network.dnn
     original = {}
@@ -43,10 +87,14 @@ def get_MC_samples(network, X, x_scal, mc_times=64, dropout=0.6):
         dev = next(dnn.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("b200pinn.get_MC_samples: the network is on the CPU; there is no CPU path")
-        x = X[:, 0:].detach().to(dev, torch.float32).contiguous()
         masks = getattr(dnn, "_injected_mc", None)
         calls = getattr(dnn, "_drop_calls", 0)
-        out = mc_dropout_device(dnn, x, mc_times, float(dropout), pass_offset=calls, masks=masks)
+        host_result = None
+        if masks is None and X.device.type == "cpu" and X.shape[0] >= PIPELINE_MIN_ROWS:
+            host_result = _mc_host_pipelined(dnn, X[:, 0:], int(mc_times), float(dropout), calls, dev)
+        else:
+            x = X[:, 0:].detach().to(dev, torch.float32).contiguous()
+            out = mc_dropout_device(dnn, x, mc_times, float(dropout), pass_offset=calls, masks=masks)
         if hasattr(dnn, "_drop_calls"):
             dnn._drop_calls = calls + int(mc_times)
     finally:
@@ -54,6 +102,8 @@ def get_MC_samples(network, X, x_scal, mc_times=64, dropout=0.6):
             if isinstance(module, torch.nn.Dropout):
                 module.p = original[name]
         dnn.eval()                                           # 01:1473
+    if host_result is not None:
+        return host_result
     pm = out["pred_mean"].cpu().numpy()
     au = out["a_u"].cpu().numpy()
     eu = out["e_u"].cpu().numpy()

@@ -667,3 +667,30 @@ def test_mc_tensor_core_tile_edges(n, T):
         K.set_tensor_core_path(prev)
     for k in ("pred_mean", "a_u", "e_u"):
         assert nrel(t2n(a[k]), t2n(b[k])) < MC_TOL, k
+
+
+@pytest.mark.gpu
+def test_get_mc_samples_pipelined_host_path_matches_single_launch():
+    """Long host inputs take the chunked copy/compute-overlap path: identical (bitwise) to the one-launch sweep."""
+    import b200pinn
+    from b200pinn import mc as MC
+    from b200pinn.synthetic import make_scaled_dataset
+
+    n = 70001
+    x, y, sx, sy = make_scaled_dataset(n, seed=31)
+    torch.manual_seed(3)
+    model = b200pinn.PhysicsInformedNN(torch.tensor(x), torch.tensor(y), [8, 64, 64, 64, 1], sx, sy, 0.2, True)
+    model.dnn._drop_seed = 4242
+    X = torch.tensor(x)
+    a = b200pinn.get_MC_samples(model, X.pin_memory(), sx, mc_times=5, dropout=0.4)
+    calls = getattr(model.dnn, "_drop_calls", None)
+    if calls is not None:
+        model.dnn._drop_calls = 0
+    prev = MC.PIPELINE_MIN_ROWS
+    MC.PIPELINE_MIN_ROWS = 1 << 60
+    try:
+        b = b200pinn.get_MC_samples(model, X, sx, mc_times=5, dropout=0.4)
+    finally:
+        MC.PIPELINE_MIN_ROWS = prev
+    for u, v in zip(a, b):
+        assert u.shape == (n,) and np.array_equal(u, v)
