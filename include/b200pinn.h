@@ -220,6 +220,9 @@ int pinn_adam_step_from_sums(float* params, const double* sums,
 int pinn_set_tensor_core_path(int enable);
 /* Same switch for the backward kernels (pinn_mlp_bwd). */
 int pinn_set_tensor_core_bwd(int enable);
+/* Same switch for the 128- / 256-wide nets' forward and MC-dropout sweep (one tcgen05 GEMM launch
+ * per layer, operands as pre-split tf32 planes; 0 = thread-per-sample FFMA kernels). */
+int pinn_set_wide_tensor_core_path(int enable);
 
 int pinn_abi_version(void);
 const char* pinn_error_string(int code);

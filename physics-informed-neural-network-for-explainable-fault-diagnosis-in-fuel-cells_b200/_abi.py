@@ -70,6 +70,7 @@ _SIGNATURES = {
     "pinn_abi_version": (C.c_int, []),
     "pinn_set_tensor_core_path": (C.c_int, [C.c_int]),
     "pinn_set_tensor_core_bwd": (C.c_int, [C.c_int]),
+    "pinn_set_wide_tensor_core_path": (C.c_int, [C.c_int]),
     "pinn_device_sm_count": (C.c_int, []),
     "pinn_error_string": (C.c_char_p, [C.c_int]),
     "pinn_param_count": (_i64, [_i32, _i32]),

@@ -186,11 +186,13 @@ using namespace pinn;
 
 extern "C" size_t pinn_mlp_fwd_workspace_bytes(int32_t width, int32_t n_hidden, int64_t n) {
   Plan p = plan_tps(width, n_hidden, n, 1);
-  return p.scratch_floats * sizeof(float);
+  const size_t a = p.scratch_floats * sizeof(float), b = wide_tc_workspace_bytes(width, n_hidden, n);
+  return a > b ? a : b;
 }
 extern "C" size_t pinn_mc_workspace_bytes(int32_t width, int32_t n_hidden, int64_t n) {
   Plan p = plan_tps(width, n_hidden, n, 2);
-  return p.scratch_floats * sizeof(float);
+  const size_t a = p.scratch_floats * sizeof(float), b = wide_tc_workspace_bytes(width, n_hidden, n);
+  return a > b ? a : b;
 }
 
 extern "C" int pinn_mlp_fwd(const pinn_net_t* net, const float* x, int64_t n, const pinn_dropout_t* drop,
@@ -207,6 +209,10 @@ extern "C" int pinn_mlp_fwd(const pinn_net_t* net, const float* x, int64_t n, co
     const int r = launch_tc(false, net, x, n, 1, make_drop_params(drop), o, static_cast<cudaStream_t>(stream), &err);
     if (r == 1) return 0;
     if (r < 0) return err;
+    const int rw = launch_wide_tc(false, net, x, n, 1, make_drop_params(drop), o, workspace, workspace_bytes,
+                                  static_cast<cudaStream_t>(stream), &err);
+    if (rw == 1) return 0;
+    if (rw < 0) return err;
   }
   Plan p = plan_tps(H, L, n, 1);
   if (p.large) {
@@ -243,6 +249,10 @@ extern "C" int pinn_mc_dropout(const pinn_net_t* net, const float* x, int64_t n,
     const int r = launch_tc(true, net, x, n, T, make_drop_params(drop), o, static_cast<cudaStream_t>(stream), &err);
     if (r == 1) return 0;
     if (r < 0) return err;
+    const int rw = launch_wide_tc(true, net, x, n, T, make_drop_params(drop), o, workspace, workspace_bytes,
+                                  static_cast<cudaStream_t>(stream), &err);
+    if (rw == 1) return 0;
+    if (rw < 0) return err;
   }
   Plan p = plan_tps(H, L, n, 2);
   if (p.large) {

@@ -10,6 +10,10 @@ struct TcOut {
 // 1: launched on the tcgen05 path; 0: shape not covered (use the FFMA kernels); -1: error in *err.
 int launch_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, const DropParams& dp, const TcOut& out,
               cudaStream_t st, int* err);
+// Wide nets (H = 128 / 256) on the tensor cores, one GEMM launch per layer (mlp_wide_tc.cu); same return convention.
+size_t wide_tc_workspace_bytes(int H, int L, int64_t n);
+int launch_wide_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, const DropParams& dp, const TcOut& out,
+                   void* workspace, size_t workspace_bytes, cudaStream_t st, int* err);
 // Tensor-core backward (mlp_tc_bwd.cu): 64-wide nets with 2..4 hidden layers.
 bool tc_bwd_covers(const pinn_net_t* net);
 size_t tc_bwd_workspace_bytes(int L, int64_t n);

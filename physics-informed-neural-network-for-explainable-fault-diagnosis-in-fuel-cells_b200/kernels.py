@@ -251,6 +251,11 @@ def set_tensor_core_path(enable: bool) -> bool:
     return bool(_abi.lib().pinn_set_tensor_core_path(1 if enable else 0))
 
 
+def set_wide_tensor_core_path(enable: bool) -> bool:
+    """Ablation switch (tests): route the 128/256-wide nets' forward / MC sweep through the FFMA kernels when False."""
+    return bool(_abi.lib().pinn_set_wide_tensor_core_path(1 if enable else 0))
+
+
 def set_tensor_core_bwd(enable: bool) -> bool:
     """Ablation switch (tests): route the 64-wide net's backward through the FFMA kernel when False."""
     return bool(_abi.lib().pinn_set_tensor_core_bwd(1 if enable else 0))
