@@ -694,3 +694,38 @@ def test_get_mc_samples_pipelined_host_path_matches_single_launch():
         MC.PIPELINE_MIN_ROWS = prev
     for u, v in zip(a, b):
         assert u.shape == (n,) and np.array_equal(u, v)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layers,n,T", [([8, 256, 256, 256, 1], 1, 2), ([8, 256, 256, 256, 1], 129, 3), ([8, 256, 256, 1], 1000, 2),
+                                        ([8, 128, 128, 128, 1], 700, 3), ([8, 256, 256, 256, 256, 256, 256, 1], 300, 2)])
+def test_wide_tensor_core_path_matches_ffma_path(layers, n, T):
+    """Per-layer tcgen05 GEMM path of the 128 / 256-wide nets vs the thread-per-sample FFMA kernels on the same
+    Philox stream: eval forward, train-mode forward and the MC sweep (tile edges, 2..6 hidden layers)."""
+    import b200pinn
+    from b200pinn import kernels as K
+    from b200pinn.synthetic import make_scaled_dataset
+
+    p = 0.3
+    x, _, _, _ = make_scaled_dataset(max(n, 64), seed=41)
+    xd = torch.tensor(x[:n], device=dev())
+    dnn = random_net(layers, 12)
+    net = K.net_from_module(dnn)
+
+    def run():
+        u0, s0 = K.mlp_forward(net, xd)
+        u1, s1 = K.mlp_forward(net, xd, K.make_dropout(p, seed=9, pass_offset=4))
+        mc = b200pinn.mc_dropout_device(dnn, xd, T, p, seed=77)
+        return [t2n(v) for v in (u0, s0, u1, s1, mc["pred_mean"], mc["a_u"], mc["e_u"])]
+
+    a = run()
+    prev = K.set_wide_tensor_core_path(False)
+    try:
+        b = run()
+    finally:
+        K.set_wide_tensor_core_path(prev)
+    # two fp32 evaluations against each other (not against fp64): six 256-wide layers with a near-cancelling
+    # output leave ~1e-5 of rounding noise between them; the fp64 comparison is test_forward_backward_vs_oracle
+    tol = MC_TOL * (3.0 if len(layers) > 6 else 1.0)
+    for i, (u, v) in enumerate(zip(a, b)):
+        assert nrel(u, v) < tol, i
