@@ -269,6 +269,32 @@ def run_ours(args):
     t_rf, _ = timed(rfk, max(3, K_ // 2), 2)
     n_exp = max(3, K_ // 2)
     del fleet, rows
+    # --- wide nets (the reference's own Layers = [8,256,256,256,1], 01:2139; config 4 is 6x256): MC sweep on the per-layer
+    # tcgen05 GEMM path (mlp_wide_tc.cu) and the train step (still the FFMA kernel), N = 262144
+    wide = {}
+    n_w, T_w = 262144, 10
+    for tag, lay_w, fl_pass, fl_train in (("3x256", [8, 256, 256, 256, 1], 344_704, 1_042_304),
+                                          ("6x256", [8, 256, 256, 256, 256, 256, 256, 1], 737_920, 2_221_952)):
+        torch.manual_seed(0)
+        mw = b200pinn.PhysicsInformedNN(X[:n_w], Y[:n_w], lay_w, sx, sy, P_TRAIN, True)
+        mw.dnn.eval()
+        xw = mw.x.detach()
+        t_w, _ = timed(lambda: b200pinn.mc_dropout_device(mw.dnn, xw, T_w, P_MC, seed=seed), 3, 1)
+        mw.train_dnn(1, verbose=False)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        mw.train_dnn(2, verbose=False)
+        b.record()
+        barrier()
+        t_wt = a.elapsed_time(b) / 2e3
+        wide[tag] = {"mc_ms": 1e3 * t_w / 3, "mc_sample_passes_per_s": n_w * T_w * 3 / t_w,
+                     "mc_tflops": n_w * T_w * 3 * fl_pass / t_w / 1e12, "train_ms": 1e3 * t_wt,
+                     "train_tflops": n_w * fl_train / t_wt / 1e12}
+        del mw, xw
+    wide["what"] = ("N=262144 per GPU; MC sweep T=10 on the per-layer tcgen05 3xTF32 GEMM path (operands as pre-split tf32 "
+                    "planes, TMA bulk copies); train step on the thread-per-sample FFMA kernel (tensor-core backward for "
+                    "wide nets: next round)")
     # --- e2e: public API, host tensors in pinned memory, results back on the host
     Xp = X.pin_memory()
     import contextlib
@@ -342,6 +368,7 @@ def run_ours(args):
                      "export_rows_per_s": world * n * n_exp / t_export, "export_ms_per_stack": 1e3 * t_export / n_exp,
                      "rf_rows_per_s": world * 8 * n * n_exp / t_rf, "rf_ms_per_8_stacks": 1e3 * t_rf / n_exp,
                      "rf_hbm_gbs": 8 * n * (22 * 8 + 2 * 8) * n_exp / t_rf / 1e9}
+    line["wide"] = wide
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
         mc_rate, tr_rate, t1, t2 = cpu_port_rates(1_000_000, 200_000, threads)
