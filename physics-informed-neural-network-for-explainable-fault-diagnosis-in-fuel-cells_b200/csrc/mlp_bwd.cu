@@ -372,6 +372,8 @@ extern "C" size_t pinn_mlp_bwd_workspace_bytes(int32_t width, int32_t n_hidden, 
     size_t b = tc_bwd_workspace_bytes(n_hidden, n);
     if (b > a) a = b;
   }
+  const size_t w = wide_tc_bwd_workspace_bytes(width, n_hidden, n);
+  if (w > a) a = w;
   return a;
 }
 
@@ -386,6 +388,9 @@ extern "C" int pinn_mlp_bwd(const pinn_net_t* net, const float* x, int64_t n, co
   if (!grad_u && n_global <= 0) return PINN_E_ARG;
   if (!aligned16(x) || !aligned16(workspace)) return PINN_E_ALIGN;
   const int H = net->width, L = net->n_hidden;
+  if (n > 0 && wide_tc_bwd_covers(net))
+    return launch_wide_tc_bwd(net, x, n, make_drop_params(drop), grad_u, grad_logvar, y, n_global, grad_flat, loss_sums, workspace,
+                              workspace_bytes, static_cast<cudaStream_t>(stream));
   if (n > 0 && tc_bwd_covers(net))
     return launch_tc_bwd(net, x, n, make_drop_params(drop), grad_u, grad_logvar, y, n_global, grad_flat, loss_sums, workspace,
                          workspace_bytes, static_cast<cudaStream_t>(stream));

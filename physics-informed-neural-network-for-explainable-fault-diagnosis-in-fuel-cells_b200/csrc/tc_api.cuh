@@ -14,6 +14,11 @@ int launch_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, 
 size_t wide_tc_workspace_bytes(int H, int L, int64_t n);
 int launch_wide_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, const DropParams& dp, const TcOut& out,
                    void* workspace, size_t workspace_bytes, cudaStream_t st, int* err);
+bool wide_tc_bwd_covers(const pinn_net_t* net);
+size_t wide_tc_bwd_workspace_bytes(int H, int L, int64_t n);
+int launch_wide_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropParams& dp, const float* grad_u, const float* grad_s,
+                       const float* y, int64_t n_global, float* grad_flat, double* loss_sums, void* workspace, size_t workspace_bytes,
+                       cudaStream_t st);
 // Tensor-core backward (mlp_tc_bwd.cu): 64-wide nets with 2..4 hidden layers.
 bool tc_bwd_covers(const pinn_net_t* net);
 size_t tc_bwd_workspace_bytes(int L, int64_t n);
