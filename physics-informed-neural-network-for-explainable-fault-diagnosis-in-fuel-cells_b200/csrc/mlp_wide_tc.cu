@@ -547,19 +547,30 @@ __global__ void wide_wgrad_reduce_kernel(const float* __restrict__ partial, int 
   if (kk < ncols) dstW[static_cast<size_t>(j) * ld + kk] = static_cast<float>(acc) * scale;
   else dstB[j] = static_cast<float>(acc);
 }
-// dWv2 / dbv2 and the loss sums from the per-tile partials of EPI_V1_TRAIN
-__global__ void wide_tail_reduce_kernel(const float* __restrict__ tail_partial, const double* __restrict__ loss_partial, int tiles, int n1,
-                                        float* __restrict__ dWv2, float* __restrict__ dbv2, double* __restrict__ loss) {
-  const int k = threadIdx.x;
+// dWv2 / dbv2 and the loss sums from the per-tile partials of EPI_V1_TRAIN: block k < n1 -> dWv2[k], block n1 -> dbv2,
+// blocks n1+1 .. n1+4 -> the four loss sums.  Strided per-thread sums, then a fixed-order shared-memory tree: deterministic.
+__global__ void __launch_bounds__(256)
+wide_tail_reduce_kernel(const float* __restrict__ tail_partial, const double* __restrict__ loss_partial, int tiles, int n1,
+                        float* __restrict__ dWv2, float* __restrict__ dbv2, double* __restrict__ loss) {
+  __shared__ double sh[256];
+  const int k = blockIdx.x, t0 = threadIdx.x;
+  double acc = 0.0;
   if (k <= n1) {
-    double acc = 0.0;
-    for (int t = 0; t < tiles; ++t) acc += static_cast<double>(tail_partial[static_cast<size_t>(t) * (n1 + 1) + k]);
-    if (k < n1) dWv2[k] = static_cast<float>(acc); else dbv2[0] = static_cast<float>(acc);
+    for (int t = t0; t < tiles; t += 256) acc += static_cast<double>(tail_partial[static_cast<size_t>(t) * (n1 + 1) + k]);
+  } else {
+    if (loss == nullptr) return;
+    for (int t = t0; t < tiles; t += 256) acc += loss_partial[static_cast<size_t>(t) * 4 + (k - n1 - 1)];
   }
-  if (loss != nullptr && k < 4) {
-    double acc = 0.0;
-    for (int t = 0; t < tiles; ++t) acc += loss_partial[static_cast<size_t>(t) * 4 + k];
-    loss[k] = acc;
+  sh[t0] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t0 < o) sh[t0] += sh[t0 + o];
+    __syncthreads();
+  }
+  if (t0 == 0) {
+    if (k < n1) dWv2[k] = static_cast<float>(sh[0]);
+    else if (k == n1) dbv2[0] = static_cast<float>(sh[0]);
+    else loss[k - n1 - 1] = sh[0];
   }
 }
 
@@ -828,7 +839,7 @@ static int run_wide_bwd(const pinn_net_t* net, const float* x, int64_t n, const 
   a.A = ws + p.off_pv0; a.W = ws + p.off_wfv1; a.out = ws + p.off_pdz1; a.bias = net->bv1; a.bias2 = net->bv2; a.w2 = net->Wv2;
   a.outT = ws + p.off_dt; a.T_rows = 0; a.nch = (H / 2) / kWKc;
   k_v1t<<<tiles, 320, smem_of(H / 4), st>>>(dp, a);
-  wide_tail_reduce_kernel<<<1, 128, 0, st>>>(a.tail_partial, a.loss_partial, tiles, H / 4, grad_flat + lay.offWv2, grad_flat + lay.offbv2,
+  wide_tail_reduce_kernel<<<H / 4 + 5, 256, 0, st>>>(a.tail_partial, a.loss_partial, tiles, H / 4, grad_flat + lay.offWv2, grad_flat + lay.offbv2,
                                              grad_u ? nullptr : loss_sums);
   // weight-gradient GEMM + reduce helpers
   const int per_split = static_cast<int>((chunks + p.splits - 1) / p.splits);

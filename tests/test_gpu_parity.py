@@ -729,3 +729,43 @@ def test_wide_tensor_core_path_matches_ffma_path(layers, n, T):
     tol = MC_TOL * (3.0 if len(layers) > 6 else 1.0)
     for i, (u, v) in enumerate(zip(a, b)):
         assert nrel(u, v) < tol, i
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layers,n", [([8, 256, 256, 256, 1], 1), ([8, 256, 256, 256, 1], 129), ([8, 256, 256, 1], 2000),
+                                      ([8, 128, 128, 128, 1], 700), ([8, 256, 256, 256, 256, 256, 256, 1], 300),
+                                      ([8, 256, 256, 256, 1], 20000)])
+def test_wide_tensor_core_backward_matches_ffma_path(layers, n):
+    """Training step of the 128 / 256-wide nets on the per-layer tcgen05 GEMM path (saved planes, dgrad and split-K
+    weight-gradient GEMMs) vs the thread-per-sample FFMA kernel on the same Philox stream: loss sums and every
+    gradient tensor; both the fused aleatoric loss and caller-supplied output gradients."""
+    from b200pinn import kernels as K
+    from b200pinn.synthetic import make_scaled_dataset
+
+    p = 0.25
+    x, y, _, _ = make_scaled_dataset(max(n, 64), seed=43)
+    x, y = x[:n], y[:n]
+    dnn = random_net(layers, 14)
+    net = K.net_from_module(dnn)
+    xd, yd = torch.tensor(x, device=dev()), torch.tensor(y, device=dev()).reshape(-1).contiguous()
+    gu = torch.tensor(np.random.default_rng(5).standard_normal(n).astype(np.float32) / n, device=dev())
+    gs = torch.tensor(np.random.default_rng(6).standard_normal(n).astype(np.float32) / n, device=dev())
+
+    def run():
+        a, sa = K.mlp_backward(net, xd, K.make_dropout(p, seed=15, pass_offset=1), y=yd, n_global=n)
+        b, _ = K.mlp_backward(net, xd, K.make_dropout(p, seed=15, pass_offset=1), grad_u=gu, grad_logvar=gs)
+        return t2n(a).copy(), t2n(sa).copy(), t2n(b).copy()
+
+    a = run()
+    prev = K.set_wide_tensor_core_path(False)
+    try:
+        b = run()
+    finally:
+        K.set_wide_tensor_core_path(prev)
+    assert np.allclose(a[1], b[1], rtol=1e-5)
+    names, shapes, offs, _ = K.param_layout(net.width, net.n_hidden)
+    tol = GRAD_TOL * (3.0 if len(layers) > 6 else 1.0)          # fp32 vs fp32, see the forward test above
+    for fa, fb in ((a[0], b[0]), (a[2], b[2])):
+        for nm, shp, o in zip(names, shapes, offs):
+            cnt = int(np.prod(shp))
+            assert nrel(fa[o:o + cnt], fb[o:o + cnt]) < tol, nm
