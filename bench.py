@@ -270,7 +270,7 @@ def run_ours(args):
     n_exp = max(3, K_ // 2)
     del fleet, rows
     # --- wide nets (the reference's own Layers = [8,256,256,256,1], 01:2139; config 4 is 6x256): MC sweep on the per-layer
-    # tcgen05 GEMM path (mlp_wide_tc.cu) and the train step (still the FFMA kernel), N = 262144
+    # tcgen05 GEMM path (mlp_wide_tc.cu): MC sweep and train step, N = 262144
     wide = {}
     n_w, T_w = 262144, 10
     for tag, lay_w, fl_pass, fl_train in (("3x256", [8, 256, 256, 256, 1], 344_704, 1_042_304),
@@ -292,9 +292,9 @@ def run_ours(args):
                      "mc_tflops": n_w * T_w * 3 * fl_pass / t_w / 1e12, "train_ms": 1e3 * t_wt,
                      "train_tflops": n_w * fl_train / t_wt / 1e12}
         del mw, xw
-    wide["what"] = ("N=262144 per GPU; MC sweep T=10 on the per-layer tcgen05 3xTF32 GEMM path (operands as pre-split tf32 "
-                    "planes, TMA bulk copies); train step on the thread-per-sample FFMA kernel (tensor-core backward for "
-                    "wide nets: next round)")
+    wide["what"] = ("N=262144 per GPU; MC sweep T=10 and train_dnn step on the per-layer tcgen05 3xTF32 GEMM path (operands as "
+                    "pre-split tf32 planes, TMA bulk copies; dgrad = same kernel on transposed weight planes, weight gradients "
+                    "= split-K GEMMs over sample-contiguous copies)")
     # --- e2e: public API, host tensors in pinned memory, results back on the host
     Xp = X.pin_memory()
     import contextlib

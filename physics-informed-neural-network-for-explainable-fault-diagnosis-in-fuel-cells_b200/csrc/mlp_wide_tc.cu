@@ -1,5 +1,5 @@
-// mlp_wide_tc.cu -- tensor-core forward / MC-dropout path for the WIDE nets (H = 256: the reference's own
-// `Layers = [8,256,256,256,1]` (01:2139) and config 4's 6x256; H = 128 rides along).
+// mlp_wide_tc.cu -- tensor-core forward / MC-dropout / training-step path for the WIDE nets (H = 256: the reference's
+// own `Layers = [8,256,256,256,1]` (01:2139) and config 4's 6x256; H = 128 rides along).
 //
 // A 256-wide layer does not fit the resident-operand design of mlp_tc.cu (hi/lo activation planes alone would
 // need 512 + 256 TMEM columns, one layer's split weights 512 KB), so each layer is ONE GEMM launch
@@ -20,6 +20,10 @@
 // ([Wv0; Wp], N = H/2 + 16) + variance-head GEMM (H/2 -> H/4) whose epilogue finishes the sample (last dot,
 // log-variance, Welford update of the per-sample statistics in global memory).
 // The mask stream (Philox counters per (sample, pass, layer, unit / 8)) is the one every other path uses.
+//
+// Training step (run_wide_bwd): the same kernel serves dgrad (A = delta planes, W = transposed weight planes, epilogue
+// delta' = D * keep * (1 - a^2)) and the weight gradients (split-K over samples: A = transposed delta blocks, W =
+// transposed activations + a row of ones for the biases; per-split partials -> deterministic reduce).
 #include "net.cuh"
 #include "tc.cuh"
 #include "tc_api.cuh"
