@@ -102,25 +102,41 @@ PINN_D void wide_store8(unsigned char* tile_planes, int c0, int r, const float (
 //     byte = (sl / 4) * 16 * ROWS + f * 16 + (sl % 4) * 4      (hi plane; lo plane follows)
 // B-side copies (activations) keep all their rows in one block per chunk (ROWS = features + 16: a row of ones and
 // zero padding follow the data); A-side copies (deltas) are cut into 128-row blocks, block stride = T_chunks chunks.
-PINN_D void wide_storeT8(const WideArgs& a, int64_t tile, int r, int c0, const float (&v)[8]) {
-  const int64_t chunk = tile * (kWT / kWKc) + (r >> 4);
-  const int sl = r & 15;
+// The whole warp calls this together (32 consecutive samples x 8 features): the values are transposed through a
+// per-warp shared-memory patch (2 planes x 8 rows x 36 floats, conflict-free both ways) so that every lane ends up
+// with two (feature, 4 consecutive samples) units per plane and the global stores are 16 bytes wide, eight features
+// (128 contiguous bytes) per quarter-warp -- the scattered 4-byte version halved the forward GEMM's speed.
+constexpr int kTPatch = 2 * 8 * 36;          // floats per warp
+PINN_D void wide_storeT8(const WideArgs& a, int64_t tile, int r, int c0, const float (&v)[8], float* patch) {
+  const int lane = r & 31;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const int f = c0 + q;
     const float h = tc::tf32_hi_fast(v[q]);
+    patch[q * 36 + lane] = h;
+    patch[8 * 36 + q * 36 + lane] = v[q] - h;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int u2 = 0; u2 < 2; ++u2) {
+    const int u = lane + 32 * u2, q = u & 7, quad = u >> 3;            // unit: feature c0 + q, samples 4 quad .. 4 quad + 3 of the warp
+    const float4 h4 = *reinterpret_cast<const float4*>(patch + q * 36 + 4 * quad);
+    const float4 l4 = *reinterpret_cast<const float4*>(patch + 8 * 36 + q * 36 + 4 * quad);
+    const int rs = (r & ~31) + 4 * quad;                               // first sample (row of the tile) of the unit
+    const int64_t chunk = tile * (kWT / kWKc) + (rs >> 4);
+    const int k4 = (rs & 15) >> 2, f = c0 + q;
     unsigned char* p;
     int plane;
     if (a.T_rows > 0) {
       plane = 4 * a.T_rows * 16;
-      p = a.outT + static_cast<size_t>(chunk) * (2 * plane) + (sl >> 2) * (a.T_rows * 16) + f * 16 + (sl & 3) * 4;
+      p = a.outT + static_cast<size_t>(chunk) * (2 * plane) + k4 * (a.T_rows * 16) + f * 16;
     } else {
       plane = w_plane(kWT);
-      p = a.outT + (static_cast<size_t>(f >> 7) * a.T_chunks + chunk) * w_chunk(kWT) + (sl >> 2) * (kWT * 16) + (f & 127) * 16 + (sl & 3) * 4;
+      p = a.outT + (static_cast<size_t>(f >> 7) * a.T_chunks + chunk) * w_chunk(kWT) + k4 * (kWT * 16) + (f & 127) * 16;
     }
-    *reinterpret_cast<float*>(p) = h;
-    *reinterpret_cast<float*>(p + plane) = v[q] - h;
+    *reinterpret_cast<float4*>(p) = h4;
+    *reinterpret_cast<float4*>(p + plane) = l4;
   }
+  __syncwarp();
 }
 // a = hi + lo of 8 saved activations (K-major planes of a tile with 128 rows)
 PINN_D void wide_load8(const unsigned char* tile_planes, int c0, int r, float (&v)[8]) {
@@ -189,6 +205,7 @@ wide_layer0_kernel(const float* __restrict__ x, const float* __restrict__ W0, co
                    const __grid_constant__ DropParams dp, WideArgs a) {
   __shared__ float sW[H * PINN_N_IN];
   __shared__ float sb[H];
+  __shared__ __align__(16) float tpatch[8][kTPatch];
   for (int i = threadIdx.x; i < H * PINN_N_IN; i += blockDim.x) sW[i] = __ldg(W0 + i) * kTanhArg;
   for (int i = threadIdx.x; i < H; i += blockDim.x) sb[i] = __ldg(b0 + i) * kTanhArg;
   __syncthreads();
@@ -228,7 +245,7 @@ wide_layer0_kernel(const float* __restrict__ x, const float* __restrict__ W0, co
       for (int q = 0; q < 8; ++q) v[q] = valid ? v[q] * a.inact : 0.f;
     }
     wide_store8(tp, c0, r, v);
-    if (a.outT != nullptr) wide_storeT8(a, tile, r, c0, v);
+    if (a.outT != nullptr) wide_storeT8(a, tile, r, c0, v, tpatch[threadIdx.x >> 5]);
   }
   if (a.act != nullptr && half == 0) {      // training: x^T (8 rows) as the B operand of dW0; `act` carries the buffer here
     unsigned char* xt = const_cast<unsigned char*>(a.act);
@@ -342,6 +359,7 @@ wide_gemm_kernel(const __grid_constant__ DropParams dp, WideArgs a) {
     __syncwarp();
     tc::fence_after_sync();
     const bool act = a.active && valid;
+    float* patch = reinterpret_cast<float*>(smem) + warp * kTPatch;      // the operand ring is idle once `accum` has fired
     if constexpr (EPI == EPI_HIDDEN || EPI == EPI_HEADS) {
       constexpr int ND = EPI == EPI_HIDDEN ? N : N - 16;          // activation columns produced (heads: H/2 + the mean column)
       unsigned char* tp = a.out + static_cast<size_t>(tile) * w_tile_bytes(ND);
@@ -365,7 +383,7 @@ wide_gemm_kernel(const __grid_constant__ DropParams dp, WideArgs a) {
             for (int q = 0; q < 8; ++q) v[q] = valid ? v[q] * a.inact : 0.f;
           }
           wide_store8(tp, c0 + g, r, v);
-          if (a.outT != nullptr) wide_storeT8(a, tile, r, c0 + g, v);
+          if (a.outT != nullptr) wide_storeT8(a, tile, r, c0 + g, v, patch);
         }
       }
       if constexpr (EPI == EPI_HEADS) {
@@ -457,7 +475,7 @@ wide_gemm_kernel(const __grid_constant__ DropParams dp, WideArgs a) {
             col[q] = dv * a1;
           }
           wide_store8(tp, c0, r, dz);
-          wide_storeT8(a, tile, r, c0, dz);
+          wide_storeT8(a, tile, r, c0, dz, patch);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             float t = col[q];
@@ -503,7 +521,7 @@ wide_gemm_kernel(const __grid_constant__ DropParams dp, WideArgs a) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) v[q] = (k[q] && valid) ? z[g + q] * fmaf(-av[q], av[q], 1.0f) : 0.f;
           wide_store8(tp, c0 + g, r, v);
-          wide_storeT8(a, tile, r, c0 + g, v);
+          wide_storeT8(a, tile, r, c0 + g, v, patch);
         }
       }
       if constexpr (EPI == EPI_DV0) {
@@ -512,7 +530,7 @@ wide_gemm_kernel(const __grid_constant__ DropParams dp, WideArgs a) {
           const float d8[8] = {du, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
           wide_store8(tp, N, r, d8);
           wide_store8(tp, N + 8, r, z8);
-          wide_storeT8(a, tile, r, N, d8);        // block 1, rows 0..7: row 0 = du
+          wide_storeT8(a, tile, r, N, d8, patch);        // delta rows N .. N+7: row N = du
         }
       }
     } else {
