@@ -752,7 +752,9 @@ static WideBwdPlan<H> wide_bwd_plan(int L, int64_t n) {
   p.off_tail = take(tiles * (H / 4 + 1) * sizeof(float));
   p.off_loss = take(tiles * 4 * sizeof(double));
   const int sms = sm_count();
-  int64_t sp = static_cast<int64_t>(chunks) < sms ? static_cast<int64_t>(chunks) : sms;
+  // the big products have two 128-row delta blocks and one CTA per SM (512 TMEM columns): splits x 2 = one wave
+  const int64_t want = sms / 2 > 0 ? sms / 2 : 1;
+  int64_t sp = static_cast<int64_t>(chunks) < want ? static_cast<int64_t>(chunks) : want;
   p.splits = static_cast<int>(sp > 0 ? sp : 1);
   p.off_wg = take(static_cast<size_t>(p.splits) * 2 * kWT * P::RB * sizeof(float));
   p.bytes = o;
