@@ -343,7 +343,8 @@ def run_ours(args):
                              "(ncu: sm__pipe_tensor_cycles_active, profiles/r1_final2_mc.summary.txt); the kernel is "
                              "bounded by the CUDA-core epilogue (2 MUFU + ~12 ALU/FMA ops per activation, 5.6 Philox "
                              "instructions per draw) and by the ~1000-clk latency of each 24-MMA batch, see DESIGN.md "
-                             "section 4. `traffic` is the ncu dram read+write of one launch at N=1M, scaled by n; "
+                             "section 4 (tensor pipe active: 29 % here, 43 % in the weight-gradient kernel K2b, 47-51 % in the "
+                             "wide-net GEMMs). `traffic` is the ncu dram read+write of one launch at N=1M, scaled by n; "
                              f"vs the fp32 FFMA peak (74.5 TFLOP/s) the kernel stands at {mc_tflops / 74.5:.2f}x"},
         "train": {"steps_per_s": steps_tr / t_tr, "ms_per_step": 1e3 * t_tr / steps_tr,
                   "global_batch": world * n, "tflops": world * n * FLOP_PER_TRAIN_SAMPLE / (t_tr / steps_tr) / 1e12,
