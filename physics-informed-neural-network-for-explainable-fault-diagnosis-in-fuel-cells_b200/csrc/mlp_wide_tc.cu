@@ -563,9 +563,18 @@ __global__ void wide_wgrad_reduce_kernel(const float* __restrict__ partial, int 
   if (idx >= nrows * per) return;
   const int j = idx / per, kk = idx % per;
   const int col = kk < ncols ? kk : bias_col;
+  const float* src = partial + (static_cast<size_t>(mb) * kWT + row0 + j) * N + col;
+  const size_t stride = static_cast<size_t>(nmb) * kWT * N;
   double acc = 0.0;
-  for (int sp = 0; sp < splits; ++sp)
-    acc += static_cast<double>(partial[((static_cast<size_t>(sp) * nmb + mb) * kWT + row0 + j) * N + col]);
+  int sp = 0;
+  for (; sp + 8 <= splits; sp += 8) {          // eight loads in flight; the summation order stays fixed
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = __ldg(src + (sp + q) * stride);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc += static_cast<double>(v[q]);
+  }
+  for (; sp < splits; ++sp) acc += static_cast<double>(__ldg(src + sp * stride));
   if (kk < ncols) dstW[static_cast<size_t>(j) * ld + kk] = static_cast<float>(acc) * scale;
   else dstB[j] = static_cast<float>(acc);
 }
