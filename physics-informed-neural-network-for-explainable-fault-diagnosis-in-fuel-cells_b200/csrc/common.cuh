@@ -221,6 +221,27 @@ PINN_D float tanh_pre(float a) {       // a = kTanhArg * x
   return fmaf(-2.0f, r, 1.0f);
 }
 
+// Two activations per instruction where the ISA allows it: sm_100 has packed fp32x2 FFMA2 / FADD2 (same FLOP rate,
+// half the issue slots -- and issue slots, not FLOPs, bound the tensor-core kernels' epilogues).
+PINN_D float2 tanh_pre2(float2 a) {     // a = kTanhArg * x, two lanes
+  float ex, ey, rx, ry;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(a.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ey) : "f"(a.y));
+  const float2 d = __fadd2_rn(make_float2(ex, ey), make_float2(1.0f, 1.0f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rx) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ry) : "f"(d.y));
+  return __ffma2_rn(make_float2(rx, ry), make_float2(-2.0f, -2.0f), make_float2(1.0f, 1.0f));
+}
+// t[q] = tanh(z[q] + b[q]) for eight units, biases pre-scaled by kTanhArg
+PINN_D void tanh8_prescaled(const float* z, const float (&bs)[8], float (&t)[8]) {
+#pragma unroll
+  for (int q = 0; q < 8; q += 2) {
+    const float2 a2 = __ffma2_rn(make_float2(z[q], z[q + 1]), make_float2(kTanhArg, kTanhArg), make_float2(bs[q], bs[q + 1]));
+    const float2 t2 = tanh_pre2(a2);
+    t[q] = t2.x; t[q + 1] = t2.y;
+  }
+}
+
 // log(softplus(v) + 1e-6), softplus with torch's threshold 20 (01:432-434).
 PINN_HD float softplus_f(float v) { return v > 20.0f ? v : log1pf(expf(v)); }
 PINN_HD float logvar_from_v(float v) { return logf(softplus_f(v) + 1e-6f); }

@@ -210,7 +210,11 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
     auto store8 = [&](int c0, const float (&v)[8]) {        // split -> this row's hi / lo columns in tensor memory
       float h[8], lo[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) { h[q] = tc::tf32_hi_fast(v[q]); lo[q] = v[q] - h[q]; }
+      for (int q = 0; q < 8; q += 2) {
+        h[q] = tc::tf32_hi_fast(v[q]); h[q + 1] = tc::tf32_hi_fast(v[q + 1]);
+        const float2 l2 = __ffma2_rn(make_float2(h[q], h[q + 1]), make_float2(-1.0f, -1.0f), make_float2(v[q], v[q + 1]));   // v - h, exact
+        lo[q] = l2.x; lo[q + 1] = l2.y;
+      }
       tc::tmem_st8(a_hi_l + static_cast<uint32_t>(c0), h);
       tc::tmem_st8(a_lo_l + static_cast<uint32_t>(c0), lo);
     };
@@ -334,8 +338,7 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
             const float4 bA = *reinterpret_cast<const float4*>(bl + g), bB = *reinterpret_cast<const float4*>(bl + g + 4);
             const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
             float t8[8], v[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) t8[q] = tanh_pre(fmaf(z[g + q], kTanhArg, bb[q]));
+            tanh8_prescaled(z + g, bb, t8);
             select8(rl[g / 8], ks, active, static_cast<uint32_t>(l), cb + g, t8, v);
             store8(cb + g, v);
           }
@@ -364,8 +367,7 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
             const float4 bA = *reinterpret_cast<const float4*>(bv0 + g), bB = *reinterpret_cast<const float4*>(bv0 + g + 4);
             const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
             float t8[8], v[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) t8[q] = tanh_pre(fmaf(v0[g + q], kTanhArg, bb[q]));
+            tanh8_prescaled(v0 + g, bb, t8);
             select8(rv[g / 8], ks, active, static_cast<uint32_t>(L), 16 * half + g, t8, v);
 #pragma unroll
             for (int q = 0; q < 8; ++q) v0[g + q] = v[q];

@@ -569,7 +569,11 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
   auto store_pn8 = [&](int c0, const float (&v)[8]) {   // 8 consecutive columns of this thread's row
     float h[8], lo[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) { h[q] = tc::tf32_hi_fast(v[q]); lo[q] = v[q] - h[q]; }
+    for (int q = 0; q < 8; q += 2) {
+      h[q] = tc::tf32_hi_fast(v[q]); h[q + 1] = tc::tf32_hi_fast(v[q + 1]);
+      const float2 l2 = __ffma2_rn(make_float2(h[q], h[q + 1]), make_float2(-1.0f, -1.0f), make_float2(v[q], v[q + 1]));   // v - h, exact
+      lo[q] = l2.x; lo[q + 1] = l2.y;
+    }
     tc::tmem_st8(a_hi_t + lane_sel + static_cast<uint32_t>(c0), h);
     tc::tmem_st8(a_lo_t + lane_sel + static_cast<uint32_t>(c0), lo);
   };
@@ -659,9 +663,10 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
         const float4 bA = *reinterpret_cast<const float4*>(bl + g), bB = *reinterpret_cast<const float4*>(bl + g + 4);
         const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
         const uint32_t kbg = bits >> g;
-        float v[8];
+        float t8[8], v[8];
+        tanh8_prescaled(z, bb, t8);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = ((kbg >> q) & 1u) ? tanh_pre(fmaf(z[q], kTanhArg, bb[q])) : 0.f;
+        for (int q = 0; q < 8; ++q) v[q] = ((kbg >> q) & 1u) ? t8[q] : 0.f;
         store_pn8(cb + g, v);
 #pragma unroll
         for (int q = 0; q < 8; ++q) trow[static_cast<size_t>(row_act(a.rm, l) + cb + g + q) * kRowStride] = valid ? v[q] : 0.f;
