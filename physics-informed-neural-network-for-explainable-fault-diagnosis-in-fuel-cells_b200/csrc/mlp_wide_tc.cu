@@ -268,8 +268,13 @@ wide_layer0_kernel(const float* __restrict__ x, const float* __restrict__ W0, co
 template <int N, int EPI>
 __global__ void __launch_bounds__(320, N > 256 ? 1 : 2)
 wide_gemm_kernel(const __grid_constant__ DropParams dp, WideArgs a) {
-  constexpr int S = N >= 256 ? 2 : 3;                            // pipeline stages
-  constexpr int A_CH = w_chunk(kWT), W_CH = w_chunk(N), STAGE = A_CH + W_CH;
+  // A pipeline stage is HALF a plane chunk (8 of its 16 k: the first or second pair of 4-wide sub-chunks of the hi and
+  // of the lo plane): four bulk copies, three MMAs.  Twice as many, half as large stages as chunk-sized ones keep more
+  // loads in flight per CTA in the same shared memory (TMA latency ~2000 clk vs 384 clk of MMA work per stage).
+  constexpr int S = N >= 256 ? 4 : 6;                            // pipeline stages
+  constexpr int A_CH = w_chunk(kWT), W_CH = w_chunk(N);          // bytes of a whole [hi | lo] chunk in global memory
+  constexpr int A_H = w_plane(kWT) / 2, W_H = w_plane(N) / 2;    // bytes of half a plane
+  constexpr int STAGE = 2 * A_H + 2 * W_H;                       // [A hi half | A lo half | W hi half | W lo half]
   constexpr uint32_t TCOLS = N > 256 ? 512u : (N > 128 ? 256u : (N > 64 ? 128u : 64u));
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t full[S], empty[S], accum;
@@ -309,12 +314,17 @@ wide_gemm_kernel(const __grid_constant__ DropParams dp, WideArgs a) {
         At = a.A + static_cast<size_t>(tile) * a.nch * A_CH;
         Wt = a.W;
       }
-      for (int64_t c = 0; c < nch; ++c) {
+      for (int64_t c = 0; c < 2 * nch; ++c) {            // c = 2 * chunk + half
         const int s = static_cast<int>(c % S);
         if (c >= S) tc::mbar_wait(&empty[s], static_cast<uint32_t>((c / S - 1) & 1));
         tc::mbar_expect_tx(&full[s], STAGE);
-        tc::bulk_g2s(smem + s * STAGE, At + static_cast<size_t>(c) * A_CH, A_CH, &full[s]);
-        tc::bulk_g2s(smem + s * STAGE + A_CH, Wt + static_cast<size_t>(c) * W_CH, W_CH, &full[s]);
+        unsigned char* d = smem + s * STAGE;
+        const unsigned char* ga = At + static_cast<size_t>(c >> 1) * A_CH + (c & 1) * A_H;
+        const unsigned char* gw = Wt + static_cast<size_t>(c >> 1) * W_CH + (c & 1) * W_H;
+        tc::bulk_g2s(d, ga, A_H, &full[s]);
+        tc::bulk_g2s(d + A_H, ga + w_plane(kWT), A_H, &full[s]);
+        tc::bulk_g2s(d + 2 * A_H, gw, W_H, &full[s]);
+        tc::bulk_g2s(d + 2 * A_H + W_H, gw + w_plane(N), W_H, &full[s]);
       }
     }
     __syncwarp();
@@ -323,28 +333,24 @@ wide_gemm_kernel(const __grid_constant__ DropParams dp, WideArgs a) {
     constexpr int N1 = N > 256 ? 256 : N, N2 = N - N1;            // one tcgen05.mma covers at most 256 columns
     const uint32_t idesc = tc::make_idesc_tf32(kWT, N1), idesc2 = tc::make_idesc_tf32(kWT, N2 > 0 ? N2 : 16);
     constexpr uint32_t LBO_A = kWT * 16, LBO_B = N * 16;
-    for (int64_t c = 0; c < nch; ++c) {
+    for (int64_t c = 0; c < 2 * nch; ++c) {
       const int s = static_cast<int>(c % S);
       tc::mbar_wait(&full[s], static_cast<uint32_t>((c / S) & 1));
       __syncwarp();
       if (tc::elect_one()) {
         tc::fence_after_sync();
-        const uint32_t sa = tc::smem_u32(smem + s * STAGE), sw = sa + A_CH;
-        const uint64_t a_hi = tc::make_desc(sa, LBO_A, 128), a_lo = tc::make_desc(sa + w_plane(kWT), LBO_A, 128);
-        const uint64_t b_hi = tc::make_desc(sw, LBO_B, 128), b_lo = tc::make_desc(sw + w_plane(N), LBO_B, 128);
-        const uint64_t as = (2u * LBO_A) >> 4, bs = (2u * LBO_B) >> 4;
+        const uint32_t sa = tc::smem_u32(smem + s * STAGE), sw = sa + 2 * A_H;
+        const uint64_t a_hi = tc::make_desc(sa, LBO_A, 128), a_lo = tc::make_desc(sa + A_H, LBO_A, 128);
+        const uint64_t b_hi = tc::make_desc(sw, LBO_B, 128), b_lo = tc::make_desc(sw + W_H, LBO_B, 128);
 #pragma unroll
         for (int term = 0; term < 3; ++term) {      // lo*hi, hi*lo, hi*hi
           const uint64_t aa = term == 0 ? a_lo : a_hi, bb = term == 1 ? b_lo : b_hi;
-#pragma unroll
-          for (int k8 = 0; k8 < kWKc / 8; ++k8) {
-            const uint32_t acc = (c != 0 || term != 0 || k8 != 0) ? 1u : 0u;
-            tc::umma_tf32(tb, aa + k8 * as, bb + k8 * bs, idesc, acc);
-            if constexpr (N2 > 0) tc::umma_tf32(tb + N1, aa + k8 * as, bb + k8 * bs + ((N1 * 16u) >> 4), idesc2, acc);
-          }
+          const uint32_t acc = (c != 0 || term != 0) ? 1u : 0u;
+          tc::umma_tf32(tb, aa, bb, idesc, acc);
+          if constexpr (N2 > 0) tc::umma_tf32(tb + N1, aa, bb + ((N1 * 16u) >> 4), idesc2, acc);
         }
         tc::umma_commit(&empty[s]);
-        if (c == nch - 1) tc::umma_commit(&accum);
+        if (c == 2 * nch - 1) tc::umma_commit(&accum);
       }
       __syncwarp();
     }
@@ -661,9 +667,8 @@ static int run_wide(bool mc, const pinn_net_t* net, const float* x, int64_t n, i
   auto k_hidden = wide_gemm_kernel<H, EPI_HIDDEN>;
   auto k_heads = wide_gemm_kernel<NH, EPI_HEADS>;
   auto k_v1 = wide_gemm_kernel<H / 4, EPI_V1>;
-  const int sm_hidden = (H >= 256 ? 2 : 3) * (w_chunk(kWT) + w_chunk(H));
-  const int sm_heads = 3 * (w_chunk(kWT) + w_chunk(NH));
-  const int sm_v1 = 3 * (w_chunk(kWT) + w_chunk(H / 4));
+  auto smem_of = [](int N) { return (N >= 256 ? 4 : 6) * (w_plane(kWT) + w_plane(N)); };
+  const int sm_hidden = smem_of(H), sm_heads = smem_of(NH), sm_v1 = smem_of(H / 4);
   PINN_CUDA_TRY(cudaFuncSetAttribute(k_hidden, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_hidden));
   PINN_CUDA_TRY(cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_heads));
   PINN_CUDA_TRY(cudaFuncSetAttribute(k_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_v1));
@@ -829,7 +834,7 @@ static int run_wide_bwd(const pinn_net_t* net, const float* x, int64_t n, const 
   auto k_wg_b = wide_gemm_kernel<RB, EPI_WGRAD>;
   auto k_wg_v = wide_gemm_kernel<RV, EPI_WGRAD>;
   auto k_wg_x = wide_gemm_kernel<16, EPI_WGRAD>;
-  auto smem_of = [](int N) { return (N >= 256 ? 2 : 3) * (w_chunk(kWT) + w_chunk(N)); };
+  auto smem_of = [](int N) { return (N >= 256 ? 4 : 6) * (w_plane(kWT) + w_plane(N)); };
   PINN_CUDA_TRY(cudaFuncSetAttribute(k_hidden, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(H)));
   PINN_CUDA_TRY(cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(NH)));
   PINN_CUDA_TRY(cudaFuncSetAttribute(k_v1t, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(H / 4)));
