@@ -214,6 +214,16 @@ int pinn_adam_step_from_sums(float* params, const double* sums,
                              double lr0, double gamma, int64_t step_size,
                              const float* lo, const float* hi, void* stream);
 
+/* Data-parallel variant of pinn_adam_step: the gradient all-reduce is fused into the Adam launch over NVLink peer
+ * memory (replaces `dist.all_reduce(grad)` + `optimizer.step()` of a DDP-style loop around 01:948-955).
+ * peer_buffers: DEVICE array of `world` pointers, entry r = rank r's symmetric buffer laid out as
+ * [64 x uint32 flags | slot 0: n floats | slot 1: n floats]; the caller has written this step's local gradient
+ * bucket into slot `slot` of its own buffer (stream order); step_tag must increase by one per call on every rank. */
+int pinn_adam_step_p2p(float* params, const uint64_t* peer_buffers, int32_t rank,
+                       int32_t world, int32_t slot, uint32_t step_tag, float* exp_avg,
+                       float* exp_avg_sq, int64_t n, int64_t* step_counter, double lr0,
+                       double gamma, int64_t step_size, void* stream);
+
 /* Ablation / test switch.  The 64-wide net's forward and MC-dropout kernels run their
  * 64x64 contractions on tcgen05 tensor cores (3xTF32, fp32-accurate); 0 routes them through
  * the fp32 FFMA kernels that serve the other widths.  Returns the previous setting. */

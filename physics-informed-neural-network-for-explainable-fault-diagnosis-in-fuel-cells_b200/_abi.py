@@ -72,6 +72,7 @@ _SIGNATURES = {
     "pinn_set_tensor_core_bwd": (C.c_int, [C.c_int]),
     "pinn_set_wide_tensor_core_path": (C.c_int, [C.c_int]),
     "pinn_device_sm_count": (C.c_int, []),
+    "pinn_adam_step_p2p": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _u32, _vp, _vp, _i64, _vp, _dbl, _dbl, _i64, _vp]),
     "pinn_error_string": (C.c_char_p, [C.c_int]),
     "pinn_param_count": (_i64, [_i32, _i32]),
     "pinn_mlp_fwd_workspace_bytes": (_sz, [_i32, _i32, _i64]),

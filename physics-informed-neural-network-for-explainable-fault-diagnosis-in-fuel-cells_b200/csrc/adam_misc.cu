@@ -65,6 +65,62 @@ __global__ void adam_kernel(float* __restrict__ params, const float* __restrict_
   }
 }
 
+// Data-parallel train step: gradient all-reduce FUSED into the Adam launch over NVLink peer memory.
+// Every rank owns a symmetric buffer  [64 x uint32 flags | slot 0: n floats | slot 1: n floats]  (torch symmetric
+// memory: the same allocation is mapped into every rank's address space; `peers[r]` = rank r's buffer).  K2 writes
+// this step's gradient bucket into slot (step & 1) of the local buffer; this kernel then
+//   1. announces "my bucket of step `tag` is complete" by storing `tag` into flags[rank] of EVERY peer (release.sys),
+//   2. waits until flags[r] of its OWN buffer has reached `tag` for all r (acquire.sys): a local poll, no NVLink traffic,
+//   3. sums element i over the ranks IN RANK ORDER straight out of the peers' buffers (identical result on every
+//      rank, so the replicas stay bit-identical) and applies Adam to it.
+// Two slots make the hand-over race-free without a second barrier: a rank can run at most one step ahead of the
+// slowest one (step t+1's wait needs everybody's announcement of t+1, which a rank only makes after it has finished
+// reading step t), so slot (t+1) & 1 is never the one a straggler still reads.
+// For the 46 KB bucket of the 3x64 net this replaces an NCCL launch (~25 us + host overhead) by a few microseconds.
+PINN_D void st_release_sys(unsigned int* p, unsigned int v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+PINN_D unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+PINN_D float ld_volatile_f32(const float* p) {
+  float v;
+  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+constexpr int kP2PFlagWords = 64;
+__global__ void adam_p2p_kernel(float* __restrict__ params, const unsigned long long* __restrict__ peers, int rank, int world,
+                                int slot, unsigned int tag, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                int64_t* step_counter, AdamHyper h) {
+  if (blockIdx.x == 0 && threadIdx.x < world)
+    st_release_sys(reinterpret_cast<unsigned int*>(peers[threadIdx.x]) + rank, tag);
+  if (threadIdx.x < world) {
+    const unsigned int* mine = reinterpret_cast<const unsigned int*>(peers[rank]) + threadIdx.x;
+    while (static_cast<int>(ld_acquire_sys(mine) - tag) < 0) { __nanosleep(100); }
+  }
+  __syncthreads();
+  const int64_t t0 = *step_counter;
+  const double lr = h.lr0 * pow(h.gamma, static_cast<double>(t0 / h.step_size));
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float g = 0.f;
+    for (int r = 0; r < world; ++r)
+      g += ld_volatile_f32(reinterpret_cast<const float*>(peers[r]) + kP2PFlagWords + static_cast<size_t>(slot) * n + i);
+    g = static_cast<float>(static_cast<double>(g) * h.grad_scale);
+    float p = params[i], mm = m[i], vv = v[i];
+    adam_update(p, g, mm, vv, lr, t0 + 1, 0.f, 0.f, false);
+    params[i] = p; m[i] = mm; v[i] = vv;
+  }
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(step_counter + 1);
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    if (last) { *ticket = 0u; *step_counter = t0 + 1; }
+  }
+}
+
 // Small-vector variant for the 17 physics scalars: gradients are double sums produced by
 // pinn_residuals; sums[PINN_S_N] is the sample count (mean = sum / count).
 __global__ void adam_from_sums_kernel(float* params, const double* sums, const int32_t* grad_slot, float* m,
@@ -101,6 +157,18 @@ extern "C" int pinn_adam_step(float* params, const float* grads, float* exp_avg,
   const int grid = static_cast<int>((n + 255) / 256);
   adam_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, n,
                                                                   step_counter, h, active, lo, hi, advance_counter);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int pinn_adam_step_p2p(float* params, const uint64_t* peer_buffers, int32_t rank, int32_t world, int32_t slot,
+                                  uint32_t step_tag, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t* step_counter, double lr0,
+                                  double gamma, int64_t step_size, void* stream) {
+  if (n <= 0 || !params || !peer_buffers || !exp_avg || !exp_avg_sq || !step_counter || step_size <= 0) return PINN_E_ARG;
+  if (world < 1 || world > kP2PFlagWords || rank < 0 || rank >= world || (slot != 0 && slot != 1)) return PINN_E_ARG;
+  AdamHyper h{lr0, gamma, 1.0, step_size};
+  const int grid = static_cast<int>((n + 255) / 256);
+  adam_p2p_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(params, reinterpret_cast<const unsigned long long*>(peer_buffers),
+                                                                      rank, world, slot, step_tag, exp_avg, exp_avg_sq, n, step_counter, h);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -73,3 +73,42 @@ def allreduce_bucket(bucket: torch.Tensor, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(bucket, group=group)
     return bucket
+
+
+class SymmetricBucket:
+    """Gradient bucket in torch symmetric memory (NVLink peer-mapped): ``[64 flag words | slot 0 | slot 1]`` per rank.
+    ``slot(i)`` is the view K2 writes the local gradients of a step into; ``ptrs`` the device array of every rank's
+    buffer address for ``kernels.adam_step_p2p``.  ``SymmetricBucket.create`` returns None when symmetric memory is not
+    available (single process, gloo, no peer access): the caller then keeps the NCCL all-reduce."""
+
+    def __init__(self, buf, handle, n, device):
+        self.buf, self.handle, self.n = buf, handle, n
+        self.ptrs = torch.tensor([int(p) for p in handle.buffer_ptrs], dtype=torch.int64, device=device)
+        self.rank, self.world = handle.rank, handle.world_size
+        self.tag = 0
+
+    def slot(self, i):
+        from .kernels import P2P_FLAG_WORDS
+        return self.buf[P2P_FLAG_WORDS + i * self.n: P2P_FLAG_WORDS + (i + 1) * self.n]
+
+    @staticmethod
+    def create(n, device, group=None):
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) < 2:
+            return None
+        if dist.get_backend(group) != "nccl":
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            from .kernels import P2P_FLAG_WORDS
+            buf = symm.empty(P2P_FLAG_WORDS + 2 * n, dtype=torch.float32, device=device)
+            buf.zero_()
+            handle = symm.rendezvous(buf, group if group is not None else dist.group.WORLD)
+            torch.cuda.synchronize(device)
+            handle.barrier()
+            ok = torch.ones(1, device=device)
+        except Exception:                       # noqa: BLE001 -- any failure means "not available here"
+            ok, buf, handle = torch.zeros(1, device=device), None, None
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)      # all ranks take the same path
+        if ok.item() < 1:
+            return None
+        return SymmetricBucket(buf, handle, n, device)

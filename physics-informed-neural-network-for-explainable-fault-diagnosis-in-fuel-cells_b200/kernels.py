@@ -277,6 +277,20 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, step_counter, lr0, gamma, step
     LAUNCHES += 1
 
 
+P2P_FLAG_WORDS = 64
+
+
+def adam_step_p2p(params, peer_ptrs, rank, world, slot, step_tag, exp_avg, exp_avg_sq, step_counter, lr0, gamma, step_size):
+    """Fused gradient all-reduce (NVLink peer loads, rank-ordered sum) + Adam + StepLR; see ``pinn_adam_step_p2p``."""
+    global LAUNCHES
+    L = _abi.lib()
+    with torch.cuda.device(params.device):
+        check(L.pinn_adam_step_p2p(ptr(params), ptr(peer_ptrs), int(rank), int(world), int(slot), int(step_tag) & 0xFFFFFFFF,
+                                   ptr(exp_avg), ptr(exp_avg_sq), params.numel(), ptr(step_counter), float(lr0), float(gamma),
+                                   int(step_size), _stream()), "pinn_adam_step_p2p")
+    LAUNCHES += 1
+
+
 def adam_step_from_sums(params, sums, grad_slot, exp_avg, exp_avg_sq, step_counter, lr0, gamma, step_size,
                         lo=None, hi=None):
     """f3 for the physics scalars: gradient i = sums[grad_slot[i]] / sums[N]."""

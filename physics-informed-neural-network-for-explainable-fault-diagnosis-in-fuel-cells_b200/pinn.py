@@ -16,6 +16,8 @@ where the arithmetic runs:
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -237,6 +239,15 @@ class PhysicsInformedNN:
         if world > 1:
             t = torch.tensor([n_local], device=self.device, dtype=torch.int64)
             n_global = int(_allreduce(t).item())
+        # data parallel: the all-reduce of the gradient bucket is fused into the Adam launch over NVLink peer memory
+        # (dist.SymmetricBucket); without symmetric memory (gloo, no peer access) it is one NCCL / gloo all-reduce
+        bucket = None
+        if world > 1 and flat.is_cuda and os.environ.get("B200PINN_P2P_ALLREDUCE", "1") != "0":
+            from .dist import SymmetricBucket
+            bucket = getattr(self, "_p2p_bucket", None)
+            if bucket is None or bucket.n != flat.numel():
+                bucket = SymmetricBucket.create(flat.numel(), self.device)
+                self._p2p_bucket = bucket
         if verbose:
             print("================== DNN training ==================")
             print("  Epoch |    Loss    |    MSE     |    LR    ")
@@ -244,10 +255,16 @@ class PhysicsInformedNN:
         for epoch in range(nIter):
             cfg = self.dnn.next_dropout_cfg(n_local, self.dnn.active_dropout_p())
             drop = K.make_dropout(**cfg) if cfg is not None else None
-            K.mlp_backward(net, x, drop, y=y, n_global=n_global, grad_flat=grad, loss_sums=sums)
-            if world > 1:
-                _allreduce(grad)
-            K.adam_step(flat, grad, m, v, counter, 1e-2, 0.8, 1000)
+            if bucket is not None:
+                bucket.tag += 1
+                sl = bucket.tag & 1
+                K.mlp_backward(net, x, drop, y=y, n_global=n_global, grad_flat=bucket.slot(sl), loss_sums=sums)
+                K.adam_step_p2p(flat, bucket.ptrs, bucket.rank, bucket.world, sl, bucket.tag, m, v, counter, 1e-2, 0.8, 1000)
+            else:
+                K.mlp_backward(net, x, drop, y=y, n_global=n_global, grad_flat=grad, loss_sums=sums)
+                if world > 1:
+                    _allreduce(grad)
+                K.adam_step(flat, grad, m, v, counter, 1e-2, 0.8, 1000)
             if epoch % 1000 == 0 or epoch == nIter - 1:
                 s = _allreduce(sums.clone()) if world > 1 else sums
                 s = s.cpu().numpy()
