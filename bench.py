@@ -337,6 +337,10 @@ def run_ours(args):
                      "kernel": "mlp_tc_kernel<MC> (tcgen05.mma kind::tf32 with A in tensor memory, 3xTF32 split, "
                                "one MMA warp per 128-sample group)",
                      "peak_source": pk["src"],
+                     "ncu": {"source": "profiles/r1_final2_mc.summary.txt (same kernel structure, 10.97 ms capture)",
+                             "sm__pipe_tensor_cycles_active_pct": 29.0, "smsp__issue_active_pct": 61.2,
+                             "sm__inst_executed_pipe_alu_pct": 43.8, "sm__inst_executed_pipe_xu_pct": 39.3,
+                             "dram_bytes_per_launch": 32.1e6},
                      "note": "achieved = algorithmic FLOPs (21 664 per sample*pass) / CUDA-event time of the launch. The "
                              "contractions run as 3 TF32 MMAs per product (fp32 parity), and TF32 dense peak is half the "
                              "bf16 figure used as `peak`, so the tensor pipe does 6x this fraction of its own peak "
