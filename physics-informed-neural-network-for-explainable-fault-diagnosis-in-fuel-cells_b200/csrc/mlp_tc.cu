@@ -440,12 +440,13 @@ static int g_tc_enabled = 1;
 int launch_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, const DropParams& dp, const TcOut& out,
               cudaStream_t st, int* err) {
   *err = 0;
-  if (!g_tc_enabled || net->width != kTcH || net->n_hidden < 2 || net->n_hidden > 5) return 0;
+  if (!g_tc_enabled || net->width != kTcH || net->n_hidden < 2 || net->n_hidden > PINN_MAX_HIDDEN) return 0;
   for (int l = 1; l < net->n_hidden; ++l)
     if (!aligned16(net->W[l])) return 0;
   if (!aligned16(net->Wv0) || !aligned16(net->Wp)) return 0;
   const TcLayout lay = make_tc_layout(net->n_hidden);
   const size_t smem = static_cast<size_t>(lay.total) * sizeof(float);
+  if (smem > 226 * 1024) return 0;          // resident weight planes: 32 KB per hidden layer (7 hidden layers fit)
   const int64_t tiles = (n + kTcTile - 1) / kTcTile;
   const int64_t want = (tiles + 1) / 2;        // two 128-sample tiles in flight per CTA
   const int grid = static_cast<int>(want < sm_count() ? (want > 0 ? want : 1) : sm_count());

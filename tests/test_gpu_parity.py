@@ -513,7 +513,7 @@ def test_golden_forward_and_mc_on_ffma_path(ffma_path):
     assert nrel(pm, g["mc_pred_mean"]) < MC_TOL and nrel(au, g["mc_a_u"]) < MC_TOL and nrel(eu, g["mc_e_u"]) < MC_TOL
 
 
-@pytest.mark.parametrize("layers", [[8, 64, 64, 1], [8, 64, 64, 64, 1], [8, 64, 64, 64, 64, 64, 1]])
+@pytest.mark.parametrize("layers", [[8, 64, 64, 1], [8, 64, 64, 64, 1], [8, 64, 64, 64, 64, 64, 1], [8] + [64] * 7 + [1]])
 def test_tensor_core_path_matches_ffma_path_and_oracle(layers):
     """Same Philox stream on both paths (counters are per sample/pass/layer/unit), so an MC sweep
     must agree to rounding; both must match the fp64 oracle under injected masks.  L = 2, 3 use two
