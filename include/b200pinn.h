@@ -93,6 +93,20 @@ int pinn_mlp_bwd(const pinn_net_t* net, const float* x, int64_t n,
                  size_t workspace_bytes, void* stream);
 size_t pinn_mlp_bwd_workspace_bytes(int32_t width, int32_t n_hidden, int64_t n);
 
+/* One train_dnn step (the loop body 01:948-955: train-mode forward, aleatoric loss, backward,
+ * Adam.step with torch's default betas / eps, StepLR.step) as ONE call for a single-GPU trainer.
+ * `net`'s tensors must be views into params_flat in the pinn_param_count layout; exp_avg /
+ * exp_avg_sq: P floats; step_counter as in pinn_adam_step.  Same results as pinn_mlp_bwd followed
+ * by pinn_adam_step (grad_scale 1, no clamp): on the tensor-core backward path the optimiser runs
+ * inside the gradient-reduce launch.  grad_flat[P] still receives the gradients.
+ * workspace >= pinn_mlp_bwd_workspace_bytes(). */
+int pinn_train_dnn_step(const pinn_net_t* net, const float* x, int64_t n,
+                        const pinn_dropout_t* drop, const float* y, int64_t n_global,
+                        float* params_flat, float* exp_avg, float* exp_avg_sq,
+                        int64_t* step_counter, double lr0, double gamma, int64_t step_size,
+                        float* grad_flat, double* loss_sums, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* K3 -- multi-physics residuals + reductions: net_f_V 01:724-765, net_f_T_simple
  * 01:869-914, net_f_T 01:767-867, net_f_H 01:621-722, net_f_O 01:535-619, the
  * mean(f^2) losses 01:1029-1034,1112,1222,1360 and their lambda-gradients. */
@@ -213,6 +227,27 @@ int pinn_adam_step_from_sums(float* params, const double* sums,
                              float* exp_avg_sq, int64_t n, int64_t* step_counter,
                              double lr0, double gamma, int64_t step_size,
                              const float* lo, const float* hi, void* stream);
+
+/* A whole block of `n_steps` optimiser steps of one scalar phase in ONE cooperative launch -- the loop
+ * bodies of train_lambda (01:1008-1055; families = PINN_FAM_V | PINN_FAM_DATA, flags select the physics
+ * term), train_thermal (01:1107-1151; PINN_FAM_TS), train_hydrogen (01:1354-1391; PINN_FAM_H) and
+ * train_oxygen (01:1204-1274; PINN_FAM_O): residual sums -> mean gradients -> Adam + StepLR + clamp,
+ * repeated on the device with one grid barrier per step.  Step for step it computes what
+ * pinn_residuals (fast math) followed by pinn_adam_step_from_sums computes.
+ * lambdas: all PINN_N_LAMBDA scalars (device, updated in place: only [first, first+count));
+ * grad_slot / lo / hi: HOST arrays of `count` (<= 8) entries, meaning as in pinn_adam_step_from_sums
+ * (slots must belong to the chosen family); exp_avg / exp_avg_sq: device, `count` floats;
+ * sums: PINN_S_COUNT doubles, totals of the LAST step (evaluated before its update, as the
+ * reference prints them).  Needs n > 0 and a device that supports cooperative launches;
+ * workspace >= pinn_scalar_phase_workspace_bytes(). */
+size_t pinn_scalar_phase_workspace_bytes(void);
+int pinn_scalar_phase(const float* x, const float* u, const float* y, int64_t n,
+                      const pinn_scalers_t* scalers, float* lambdas, uint32_t families,
+                      uint32_t flags, int32_t first, int32_t count,
+                      const int32_t* grad_slot, const float* lo, const float* hi,
+                      float* exp_avg, float* exp_avg_sq, int64_t* step_counter,
+                      double lr0, double gamma, int64_t step_size, int64_t n_steps,
+                      double* sums, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Data-parallel variant of pinn_adam_step: the gradient all-reduce is fused into the Adam launch over NVLink peer
  * memory (replaces `dist.all_reduce(grad)` + `optimizer.step()` of a DDP-style loop around 01:948-955).

@@ -82,6 +82,8 @@ _SIGNATURES = {
     "pinn_mlp_fwd": (C.c_int, [C.POINTER(PinnNet), _vp, _i64, C.POINTER(PinnDropout), _vp, _vp, _vp, _sz, _vp]),
     "pinn_mlp_bwd": (C.c_int, [C.POINTER(PinnNet), _vp, _i64, C.POINTER(PinnDropout), _vp, _vp, _vp, _i64,
                                _vp, _vp, _vp, _sz, _vp]),
+    "pinn_train_dnn_step": (C.c_int, [C.POINTER(PinnNet), _vp, _i64, C.POINTER(PinnDropout), _vp, _i64, _vp, _vp, _vp, _vp,
+                                      _dbl, _dbl, _i64, _vp, _vp, _vp, _sz, _vp]),
     "pinn_residuals": (C.c_int, [_vp, _vp, _vp, _i64, C.POINTER(PinnScalers), _vp, _u32, _u32, _vp, _vp,
                                  _vp, _vp, _vp, _sz, _vp]),
     "pinn_mc_dropout": (C.c_int, [C.POINTER(PinnNet), _vp, _i64, _i32, C.POINTER(PinnDropout),
@@ -93,6 +95,10 @@ _SIGNATURES = {
     "pinn_rf_series": (C.c_int, [_vp, _i64, _i32, _vp, C.POINTER(PinnRfParams), _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pinn_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _dbl, _dbl, _i64, _dbl, _vp, _vp, _vp,
                                  _i32, _vp]),
+    "pinn_scalar_phase_workspace_bytes": (_sz, []),
+    "pinn_scalar_phase": (C.c_int, [_vp, _vp, _vp, _i64, C.POINTER(PinnScalers), _vp, _u32, _u32, _i32, _i32,
+                                    C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_float), _vp, _vp, _vp,
+                                    _dbl, _dbl, _i64, _i64, _vp, _vp, _sz, _vp]),
     "pinn_adam_step_from_sums": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _dbl, _dbl, _i64, _vp, _vp,
                                            _vp]),
 }

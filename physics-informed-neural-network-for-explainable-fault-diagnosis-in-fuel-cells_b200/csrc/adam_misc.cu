@@ -18,27 +18,6 @@ int sm_count() {
   return cached[dev];
 }
 
-struct AdamHyper {
-  double lr0, gamma, grad_scale;
-  int64_t step_size;
-};
-
-// torch/optim/adam.py (_single_tensor_adam): exp_avg.lerp_(g, 1-b1); exp_avg_sq = b2*v + (1-b2) g^2;
-// step_size = lr / (1-b1^t); denom = sqrt(v)/sqrt(1-b2^t) + eps; p -= step_size * m/denom.
-PINN_D void adam_update(float& p, float g, float& m, float& v, double lr, int64_t t, float lo, float hi,
-                        bool clamp) {
-  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
-  m = m + (g - m) * (1.0f - b1);
-  v = v * b2 + (1.0f - b2) * g * g;
-  const double bc1 = 1.0 - pow(0.9, static_cast<double>(t));
-  const double bc2 = 1.0 - pow(0.999, static_cast<double>(t));
-  const float step = static_cast<float>(lr / bc1);
-  const float denom = sqrtf(v) / static_cast<float>(sqrt(bc2)) + eps;
-  float q = p - step * (m / denom);
-  if (clamp) q = fminf(fmaxf(q, lo), hi);
-  p = q;
-}
-
 __global__ void adam_kernel(float* __restrict__ params, const float* __restrict__ grads, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, int64_t* step_counter, AdamHyper h,
                             const uint8_t* __restrict__ active, const float* __restrict__ lo,

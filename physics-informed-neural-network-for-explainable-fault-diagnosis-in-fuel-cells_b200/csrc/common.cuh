@@ -302,4 +302,42 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device
 
+struct AdamHyper {
+  double lr0, gamma, grad_scale;
+  int64_t step_size;
+};
+
+// torch/optim/adam.py (_single_tensor_adam): exp_avg.lerp_(g, 1-b1); exp_avg_sq = b2*v + (1-b2) g^2;
+// step_size = lr / (1-b1^t); denom = sqrt(v)/sqrt(1-b2^t) + eps; p -= step_size * m/denom.
+// The per-step constants are split off so a kernel can compute them once per CTA.
+PINN_D void adam_consts(double lr, int64_t t, float& step, float& sqrt_bc2) {
+  const double bc1 = 1.0 - pow(0.9, static_cast<double>(t));
+  const double bc2 = 1.0 - pow(0.999, static_cast<double>(t));
+  step = static_cast<float>(lr / bc1);
+  sqrt_bc2 = static_cast<float>(sqrt(bc2));
+}
+PINN_D void adam_apply(float& p, float g, float& m, float& v, float step, float sqrt_bc2, float lo, float hi, bool clamp) {
+  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+  m = m + (g - m) * (1.0f - b1);
+  v = v * b2 + (1.0f - b2) * g * g;
+  const float denom = sqrtf(v) / sqrt_bc2 + eps;
+  float q = p - step * (m / denom);
+  if (clamp) q = fminf(fmaxf(q, lo), hi);
+  p = q;
+}
+PINN_D void adam_update(float& p, float g, float& m, float& v, double lr, int64_t t, float lo, float hi,
+                        bool clamp) {
+  float step, sqrt_bc2;
+  adam_consts(lr, t, step, sqrt_bc2);
+  adam_apply(p, g, m, v, step, sqrt_bc2, lo, hi, clamp);
+}
+
+// Optimiser state handed to a gradient-reduce kernel that applies Adam + StepLR in the same launch
+// (params == nullptr: plain reduce).  step_counter as in pinn_adam_step: [0] steps so far, [1] ticket.
+struct FusedAdam {
+  float* params; float* m; float* v;
+  int64_t* step_counter;
+  AdamHyper h;
+};
+
 }  // namespace pinn

@@ -432,3 +432,29 @@ extern "C" int pinn_mlp_bwd(const pinn_net_t* net, const float* x, int64_t n, co
   grad_reduce_kernel<<<rg, rb, 0, st>>>(a.partial, a.loss_partial, p.grid, lay.total, grad_flat, loss_sums);
   return static_cast<int>(cudaGetLastError());
 }
+
+// One whole train_dnn step (01:948-955: forward in train mode, aleatoric loss, backward, Adam.step, StepLR.step) as
+// ONE call.  On the tensor-core backward path the gradient reduce and the optimiser are the same launch; on the other
+// paths it is pinn_mlp_bwd followed by pinn_adam_step.  `net`'s tensors must be views into `params_flat` in the
+// pinn_param_count layout (that is what makes one flat optimiser launch possible).
+extern "C" int pinn_train_dnn_step(const pinn_net_t* net, const float* x, int64_t n, const pinn_dropout_t* drop, const float* y,
+                                   int64_t n_global, float* params_flat, float* exp_avg, float* exp_avg_sq, int64_t* step_counter,
+                                   double lr0, double gamma, int64_t step_size, float* grad_flat, double* loss_sums, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  if (int e = validate_net(net)) return e;
+  if (n <= 0 || !x || !y || n_global <= 0 || !params_flat || !exp_avg || !exp_avg_sq || !step_counter || step_size <= 0 ||
+      !grad_flat || !workspace)
+    return PINN_E_ARG;
+  ParamLayout lay = make_layout(net->width, net->n_hidden);
+  if (net->W[0] != params_flat + lay.offW[0] || net->bv2 != params_flat + lay.offbv2) return PINN_E_ARG;
+  if (!aligned16(x) || !aligned16(workspace)) return PINN_E_ALIGN;
+  if (!wide_tc_bwd_covers(net) && tc_bwd_covers(net)) {
+    FusedAdam fa{params_flat, exp_avg, exp_avg_sq, step_counter, AdamHyper{lr0, gamma, 1.0, step_size}};
+    return launch_tc_bwd(net, x, n, make_drop_params(drop), nullptr, nullptr, y, n_global, grad_flat, loss_sums, workspace,
+                         workspace_bytes, static_cast<cudaStream_t>(stream), &fa);
+  }
+  if (int e = pinn_mlp_bwd(net, x, n, drop, nullptr, nullptr, y, n_global, grad_flat, loss_sums, workspace, workspace_bytes, stream))
+    return e;
+  return pinn_adam_step(params_flat, grad_flat, exp_avg, exp_avg_sq, lay.total, step_counter, lr0, gamma, step_size, 1.0, nullptr,
+                        nullptr, nullptr, 1, stream);
+}

@@ -832,18 +832,74 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
   if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
 }
 
-__global__ void grad_reduce2_kernel(const float* __restrict__ partial, const double* __restrict__ loss_partial, int nblk,
-                                    int nloss, int64_t total, float* __restrict__ grad, double* __restrict__ loss) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < total) {
-    double acc = 0.0;
-    for (int b = 0; b < nblk; ++b) acc += static_cast<double>(partial[static_cast<size_t>(b) * total + i]);
-    grad[i] = static_cast<float>(acc);
+// Per-CTA partials -> gradient bucket, fixed order (deterministic): a CTA owns 32 consecutive bucket entries (one
+// 128-byte line per partial), its 8 warps sum every 8th partial with four loads in flight, the 8 sub-sums are
+// folded in warp order.  (The first version walked all partials serially in one thread per entry -- 24 us at
+// N = 20 000, a quarter of the whole train_dnn step there.)  With `fa.params` set the same launch applies
+// Adam + StepLR to the bucket entry it just reduced (single-GPU train_dnn: no all-reduce sits in between).
+constexpr int kRedCols = 32, kRedGroups = 8;
+__global__ void __launch_bounds__(kRedCols * kRedGroups)
+grad_reduce2_kernel(const float* __restrict__ partial, const double* __restrict__ loss_partial, int nblk, int nloss, int64_t total,
+                    float* __restrict__ grad, double* __restrict__ loss, const FusedAdam fa) {
+  __shared__ double fold[kRedGroups][kRedCols];
+  __shared__ float consts[2];
+  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kRedCols + c;
+  int64_t t0 = 0;
+  if (fa.params != nullptr) {
+    t0 = *fa.step_counter;
+    if (threadIdx.x == 0) {
+      const double lr = fa.h.lr0 * pow(fa.h.gamma, static_cast<double>(t0 / fa.h.step_size));
+      adam_consts(lr, t0 + 1, consts[0], consts[1]);
+    }
   }
-  if (loss != nullptr && blockIdx.x == 0 && threadIdx.x < 4) {
-    double acc = 0.0;
-    for (int b = 0; b < nloss; ++b) acc += loss_partial[static_cast<size_t>(b) * 4 + threadIdx.x];
-    loss[threadIdx.x] = acc;
+  double acc = 0.0;
+  if (i < total) {
+    const float* p = partial + i;
+    int b = g;
+    for (; b + 3 * kRedGroups < nblk; b += 4 * kRedGroups) {
+      const float v0 = p[static_cast<size_t>(b) * total], v1 = p[static_cast<size_t>(b + kRedGroups) * total];
+      const float v2 = p[static_cast<size_t>(b + 2 * kRedGroups) * total], v3 = p[static_cast<size_t>(b + 3 * kRedGroups) * total];
+      acc += static_cast<double>(v0); acc += static_cast<double>(v1); acc += static_cast<double>(v2); acc += static_cast<double>(v3);
+    }
+    for (; b < nblk; b += kRedGroups) acc += static_cast<double>(p[static_cast<size_t>(b) * total]);
+  }
+  fold[g][c] = acc;
+  __syncthreads();
+  if (g == 0 && i < total) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < kRedGroups; ++k) t += fold[k][c];
+    const float gr = static_cast<float>(t);
+    if (grad != nullptr) grad[i] = gr;
+    if (fa.params != nullptr) {
+      float pp = fa.params[i], mm = fa.m[i], vv = fa.v[i];
+      adam_apply(pp, static_cast<float>(static_cast<double>(gr) * fa.h.grad_scale), mm, vv, consts[0], consts[1], 0.f, 0.f, false);
+      fa.params[i] = pp; fa.m[i] = mm; fa.v[i] = vv;
+    }
+  }
+  if (loss != nullptr && blockIdx.x == 0 && g == 1) {
+    // lane l sums entries l, l+32, ...; xor tree over the lanes (fixed order)
+    double a4[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int b = c; b < nloss; b += 32) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a4[k] += loss_partial[static_cast<size_t>(b) * 4 + k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a4[k] += __shfl_xor_sync(0xffffffffu, a4[k], o);
+      if (c == 0) loss[k] = a4[k];
+    }
+  }
+  if (fa.params != nullptr) {
+    // every thread has read t0; the last CTA to arrive bumps the counter (same protocol as adam_kernel)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int* ticket = reinterpret_cast<unsigned int*>(fa.step_counter + 1);
+      if (atomicAdd(ticket, 1u) == gridDim.x - 1) { *ticket = 0u; *fa.step_counter = t0 + 1; }
+    }
   }
 }
 
@@ -880,7 +936,7 @@ size_t tc_bwd_workspace_bytes(int L, int64_t n) { return plan_tc_bwd(L, n).bytes
 
 int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropParams& dp, const float* grad_u,
                   const float* grad_s, const float* y, int64_t n_global, float* grad_flat, double* loss_sums, void* workspace,
-                  size_t workspace_bytes, cudaStream_t st) {
+                  size_t workspace_bytes, cudaStream_t st, const FusedAdam* fused) {
   const int L = net->n_hidden;
   TcBwdPlan p = plan_tc_bwd(L, n);
   if (workspace_bytes < p.bytes) return PINN_E_WORKSPACE;
@@ -927,8 +983,11 @@ int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropPa
   }
 #undef LAUNCH_B
   PINN_CUDA_TRY(cudaGetLastError());
-  const int rg = static_cast<int>((lay.total + 255) / 256);
-  grad_reduce2_kernel<<<rg, 256, 0, st>>>(w.partial, a.loss_partial, p.grid_b, 2 * p.grid_a, lay.total, grad_flat, loss_sums);
+  const int rg = static_cast<int>((lay.total + kRedCols - 1) / kRedCols);
+  FusedAdam fa{};
+  if (fused != nullptr) fa = *fused;
+  grad_reduce2_kernel<<<rg, kRedCols * kRedGroups, 0, st>>>(w.partial, a.loss_partial, p.grid_b, 2 * p.grid_a, lay.total, grad_flat,
+                                                          loss_sums, fa);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -379,6 +379,182 @@ static int res_grid(int64_t n, int ctas_per_sm = kResCtasPerSm, int samples_per_
   return static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Persistent scalar-phase trainer: a whole block of optimiser steps of train_lambda / train_thermal /
+// train_hydrogen / train_oxygen (01:1008-1055, 1107-1151, 1354-1391, 1204-1274) in ONE cooperative
+// launch.  The per-step form (pinn_residuals + pinn_adam_step_from_sums) is bound by launch latency
+// at the reference's own data sizes (N ~ 2e4: 25 us per step for ~2 us of work).  Here every CTA keeps
+// the 17 scalars in shared memory and runs, per step:
+//   residual sums of its samples -> per-CTA double partial (double-buffered by step parity)
+//   -> ONE grid barrier -> every CTA sums all partials in the same fixed order (identical totals
+//   everywhere, so no broadcast is needed) -> Adam + StepLR + clamp on its private copy.
+// x / u / y never change during a phase, so after the first step they are served from L1 / L2.
+// Two partial buffers make one barrier per step enough: a CTA can be at most one step ahead of the
+// slowest one, so the buffer it writes is never the one a straggler still reads.
+constexpr int kPhaseThreads = 256;
+constexpr int kPhaseMaxParams = 8;
+constexpr int kPhaseFold = 16;
+
+struct PhaseArgs {
+  const float* x; const float* u; const float* y;
+  int64_t n;
+  pinn_scalers_t sc;
+  float* lam;                    // all 17 scalars (read once, slice written back at the end)
+  uint32_t fam, flags;
+  int first, count;              // the optimiser's slice lam[first .. first+count)
+  int slot[kPhaseMaxParams];     // PINN_S_* gradient slot per scalar, < 0: no gradient (clamp only)
+  float lo[kPhaseMaxParams], hi[kPhaseMaxParams];
+  float* m; float* v;            // Adam moments of the slice
+  int64_t* step_counter;
+  AdamHyper h;
+  int64_t n_steps;
+  double* partials;              // [2][grid][R]
+  unsigned int* barrier;         // zeroed by the host before the launch
+  double* sums;                  // PINN_S_COUNT totals of the LAST step (its loss is the one reported)
+};
+
+PINN_D unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <uint32_t FAMC, int R0, int R1>
+__global__ void __launch_bounds__(kPhaseThreads, 4) scalar_phase_kernel(const PhaseArgs a) {
+  constexpr int R = R1 - R0;
+  static_assert(R <= kPhaseFold, "fold layout holds 16 slots");
+  __shared__ double red[kPhaseThreads / 32][R];
+  __shared__ double fold[kPhaseFold][R];
+  __shared__ double tot[R];
+  __shared__ float lam_s[PINN_N_LAMBDA];
+  __shared__ int slot_s[kPhaseMaxParams];
+  __shared__ float lo_s[kPhaseMaxParams], hi_s[kPhaseMaxParams];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < PINN_N_LAMBDA) lam_s[tid] = a.lam[tid];
+  if (tid < kPhaseMaxParams) { slot_s[tid] = a.slot[tid]; lo_s[tid] = a.lo[tid]; hi_s[tid] = a.hi[tid]; }
+  float mm = 0.f, vv = 0.f;
+  if (tid < a.count) { mm = a.m[tid]; vv = a.v[tid]; }
+  int64_t t0 = *a.step_counter;
+  const bool has_y = a.y != nullptr;
+  const bool do_v = (a.fam & PINN_FAM_V) != 0, do_d = (a.fam & PINN_FAM_DATA) != 0 && has_y;
+  const bool mode_a = !(a.flags & PINN_RES_NO_MODE_A), mode_b = !(a.flags & PINN_RES_NO_MODE_B);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t s0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + tid;
+  const double cnt = a.n > 0 ? static_cast<double>(a.n) : 1.0;
+  __syncthreads();
+
+  for (int64_t step = 0; step < a.n_steps; ++step) {
+    const Lam L{lam_s[0], lam_s[1], lam_s[2], lam_s[3], lam_s[4], lam_s[5], lam_s[6], lam_s[7], lam_s[8],
+                lam_s[9], lam_s[10], lam_s[11], lam_s[12], lam_s[13], lam_s[14], lam_s[15], lam_s[16]};
+    float acc[PINN_S_COUNT];
+#pragma unroll
+    for (int k = 0; k < PINN_S_COUNT; ++k) acc[k] = 0.f;
+    if constexpr ((FAMC & PINN_FAM_V) != 0) {
+      const VConst c = make_vconst(a.sc, L);
+      for (int64_t s = s0; s < a.n; s += stride) {
+        const float4* p0 = reinterpret_cast<const float4*>(a.x + s * PINN_N_IN);
+        const float4 r0 = __ldg(p0), r1 = __ldg(p0 + 1);
+        const float us = __ldg(a.u + s), ys = has_y ? __ldg(a.y + s) : 0.f;
+        if (do_v) eval_V_fast(c, a.sc.p_h2o, r0.x, r0.w, r1.x, r1.y, us, ys, has_y, mode_a, mode_b, acc, nullptr, a.n, s);
+        if (do_d) { const float e = ys - us; acc[PINN_S_DATA2] = fmaf(e, e, acc[PINN_S_DATA2]); }
+      }
+    } else {
+      for (int64_t s = s0; s < a.n; s += stride)
+        eval_sample<FAMC, false>(a.x, a.u, a.y, s, a.n, a.sc, L, a.fam, nullptr, nullptr, nullptr, acc);
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      double v = static_cast<double>(acc[R0 + k]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[warp][k] = v;
+    }
+    __syncthreads();
+    const size_t buf = static_cast<size_t>(step & 1) * gridDim.x * R;
+    if (tid < R) {
+      double v = 0.0;
+      for (int w = 0; w < kPhaseThreads / 32; ++w) v += red[w][tid];
+      a.partials[buf + static_cast<size_t>(blockIdx.x) * R + tid] = v;
+    }
+    // grid barrier: arrivals are counted monotonically, step k completes at (k+1) * gridDim.x
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(a.barrier, 1u);
+      const unsigned int target = static_cast<unsigned int>(step + 1) * gridDim.x;
+      while (ld_acquire_gpu_u32(a.barrier) < target) {}
+      __threadfence();
+    }
+    __syncthreads();
+    {
+      const int k = tid & (kPhaseFold - 1), g = tid >> 4;   // 16 slots x 16 groups
+      if (k < R) {
+        double v = 0.0;
+        for (unsigned int b = g; b < gridDim.x; b += kPhaseThreads / kPhaseFold)
+          v += __ldcg(a.partials + buf + static_cast<size_t>(b) * R + k);
+        fold[g][k] = v;
+      }
+    }
+    __syncthreads();
+    if (tid < R) {
+      double t = 0.0;
+      for (int g = 0; g < kPhaseFold; ++g) t += fold[g][tid];
+      tot[tid] = t;
+    }
+    __syncthreads();
+    if (tid < a.count) {
+      const int sl = slot_s[tid];
+      float p = lam_s[a.first + tid];
+      if (sl >= 0) {
+        const double lr = a.h.lr0 * pow(a.h.gamma, static_cast<double>(t0 / a.h.step_size));
+        const float g = static_cast<float>(tot[sl - R0] / cnt);
+        adam_update(p, g, mm, vv, lr, t0 + 1, lo_s[tid], hi_s[tid], true);
+      } else {
+        p = fminf(fmaxf(p, lo_s[tid]), hi_s[tid]);   // the reference clamps every listed scalar each step
+      }
+      lam_s[a.first + tid] = p;
+    }
+    ++t0;
+    __syncthreads();
+  }
+  if (blockIdx.x == 0) {
+    if (tid < a.count) { a.lam[a.first + tid] = lam_s[a.first + tid]; a.m[tid] = mm; a.v[tid] = vv; }
+    if (tid < PINN_S_COUNT) {
+      double v = 0.0;
+      if (tid == PINN_S_N) v = static_cast<double>(a.n);
+      else if (tid >= R0 && tid < R1 && a.n_steps > 0) v = tot[tid - R0];
+      a.sums[tid] = v;
+    }
+    if (tid == 0) *a.step_counter = t0;
+  }
+}
+
+template <uint32_t FAMC, int R0, int R1>
+static int launch_phase(PhaseArgs& a, size_t workspace_bytes, void* workspace, cudaStream_t st) {
+  for (int i = 0; i < a.count; ++i)
+    if (a.slot[i] >= 0 && (a.slot[i] < R0 || a.slot[i] >= R1)) return PINN_E_ARG;
+  int occ = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scalar_phase_kernel<FAMC, R0, R1>, kPhaseThreads, 0);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (occ < 1) return PINN_E_ARG;
+  if (occ > 4) occ = 4;
+  const int64_t want = (a.n + kPhaseThreads - 1) / kPhaseThreads;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * occ;
+  const int grid = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
+  if (static_cast<uint64_t>(a.n_steps) * static_cast<uint64_t>(grid) >= 0x7fffffffull) return PINN_E_ARG;
+  const size_t part_bytes = static_cast<size_t>(2) * sm_count() * 4 * kPhaseFold * sizeof(double);
+  if (workspace_bytes < part_bytes + 16) return PINN_E_WORKSPACE;
+  a.partials = static_cast<double*>(workspace);
+  a.barrier = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + part_bytes);
+  e = cudaMemsetAsync(a.barrier, 0, 16, st);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  void* params[] = {&a};
+  e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(scalar_phase_kernel<FAMC, R0, R1>), dim3(grid),
+                                  dim3(kPhaseThreads), params, 0, st);
+  return static_cast<int>(e);
+}
+
 }  // namespace pinn
 
 using namespace pinn;
@@ -429,4 +605,43 @@ extern "C" int pinn_residuals(const float* x, const float* u, const float* y, in
   else LAUNCH(ALL);
 #undef LAUNCH
   return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" size_t pinn_scalar_phase_workspace_bytes(void) {
+  return static_cast<size_t>(2) * sm_count() * 4 * kPhaseFold * sizeof(double) + 16;
+}
+
+extern "C" int pinn_scalar_phase(const float* x, const float* u, const float* y, int64_t n,
+                                 const pinn_scalers_t* scalers, float* lambdas, uint32_t families, uint32_t flags,
+                                 int32_t first, int32_t count, const int32_t* grad_slot, const float* lo,
+                                 const float* hi, float* exp_avg, float* exp_avg_sq, int64_t* step_counter,
+                                 double lr0, double gamma, int64_t step_size, int64_t n_steps, double* sums,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (n <= 0 || !x || !scalers || !lambdas || !grad_slot || !lo || !hi || !exp_avg || !exp_avg_sq || !step_counter ||
+      !sums || !workspace || step_size <= 0 || n_steps < 0)
+    return PINN_E_ARG;
+  if (first < 0 || count < 1 || count > kPhaseMaxParams || first + count > PINN_N_LAMBDA) return PINN_E_ARG;
+  if (!aligned16(x) || !aligned16(workspace)) return PINN_E_ALIGN;
+  PhaseArgs a{};
+  a.x = x; a.u = u; a.y = y; a.n = n; a.sc = *scalers; a.lam = lambdas; a.fam = families; a.flags = flags;
+  a.first = first; a.count = count;
+  for (int i = 0; i < kPhaseMaxParams; ++i) {
+    a.slot[i] = i < count ? grad_slot[i] : -1;
+    a.lo[i] = i < count ? lo[i] : 0.f;
+    a.hi[i] = i < count ? hi[i] : 0.f;
+  }
+  a.m = exp_avg; a.v = exp_avg_sq; a.step_counter = step_counter;
+  a.h = AdamHyper{lr0, gamma, 1.0, step_size};
+  a.n_steps = n_steps; a.sums = sums;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  constexpr uint32_t VD = PINN_FAM_V | PINN_FAM_DATA;
+  if (families != 0 && (families & ~VD) == 0) {
+    if (!u) return PINN_E_ARG;
+    if ((families & PINN_FAM_DATA) && !y) return PINN_E_ARG;
+    return launch_phase<VD, PINN_S_FV2, PINN_S_GB3 + 1>(a, workspace_bytes, workspace, st);
+  }
+  if (families == PINN_FAM_TS) return launch_phase<PINN_FAM_TS, PINN_S_FT2, PINN_S_GT5 + 1>(a, workspace_bytes, workspace, st);
+  if (families == PINN_FAM_H) return launch_phase<PINN_FAM_H, PINN_S_FH2, PINN_S_HTGT + 1>(a, workspace_bytes, workspace, st);
+  if (families == PINN_FAM_O) return launch_phase<PINN_FAM_O, PINN_S_FO2, PINN_S_OTGT + 1>(a, workspace_bytes, workspace, st);
+  return PINN_E_ARG;
 }

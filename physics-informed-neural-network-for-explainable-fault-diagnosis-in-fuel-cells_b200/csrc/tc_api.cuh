@@ -24,5 +24,5 @@ bool tc_bwd_covers(const pinn_net_t* net);
 size_t tc_bwd_workspace_bytes(int L, int64_t n);
 int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropParams& dp, const float* grad_u,
                   const float* grad_s, const float* y, int64_t n_global, float* grad_flat, double* loss_sums, void* workspace,
-                  size_t workspace_bytes, cudaStream_t st);
+                  size_t workspace_bytes, cudaStream_t st, const FusedAdam* fused = nullptr);
 }  // namespace pinn

@@ -302,3 +302,52 @@ def adam_step_from_sums(params, sums, grad_slot, exp_avg, exp_avg_sq, step_count
                                          int(step_size), ptr(lo), ptr(hi), _stream()),
               "pinn_adam_step_from_sums")
     LAUNCHES += 1
+
+
+def scalar_phase(x, u, y, scalers: PinnScalers, lambdas, families: int, flags: int, first: int, slots, bounds,
+                 exp_avg, exp_avg_sq, step_counter, lr0, gamma, step_size, n_steps: int, sums):
+    """f3, persistent form: ``n_steps`` optimiser steps of one scalar phase (residual sums -> Adam -> clamp)
+    in one cooperative launch; ``sums`` receives the totals of the last step.  See ``pinn_scalar_phase``."""
+    global LAUNCHES
+    _require_cuda(x, "x")
+    if not x.is_contiguous():
+        raise RuntimeError("b200pinn: `x` must be contiguous")
+    for t, nm in ((u, "u"), (y, "y"), (lambdas, "lambdas")):
+        if t is not None:
+            _require_cuda(t, nm)
+            if not t.is_contiguous():
+                raise RuntimeError(f"b200pinn: `{nm}` must be contiguous")
+    cnt = len(slots)
+    c_slot = (C.c_int32 * cnt)(*[int(s) for s in slots])
+    c_lo = (C.c_float * cnt)(*[float(b[0]) for b in bounds])
+    c_hi = (C.c_float * cnt)(*[float(b[1]) for b in bounds])
+    L = _abi.lib()
+    nb = L.pinn_scalar_phase_workspace_bytes()
+    ws = _workspace("phase", nb, x.device, zero=True)
+    with torch.cuda.device(x.device):
+        check(L.pinn_scalar_phase(ptr(x), ptr(u), ptr(y), x.shape[0], C.byref(scalers), ptr(lambdas), families, flags,
+                                  int(first), cnt, c_slot, c_lo, c_hi, ptr(exp_avg), ptr(exp_avg_sq), ptr(step_counter),
+                                  float(lr0), float(gamma), int(step_size), int(n_steps), ptr(sums), ptr(ws), nb,
+                                  _stream()), "pinn_scalar_phase")
+    LAUNCHES += 1
+
+
+def train_dnn_step(net: Net, x, drop: Optional[PinnDropout], y, n_global: int, params_flat, exp_avg, exp_avg_sq,
+                   step_counter, lr0, gamma, step_size, grad_flat, loss_sums):
+    """One ``train_dnn`` step (01:948-955) in one call: K2a, K2b and the gradient reduce with Adam + StepLR fused
+    into it.  ``net``'s tensors must be views into ``params_flat``.  See ``pinn_train_dnn_step``."""
+    global LAUNCHES
+    _require_cuda(x, "x")
+    if not x.is_contiguous() or not y.is_contiguous():
+        raise RuntimeError("b200pinn: `x` and `y` must be contiguous")
+    _require_cuda(y, "y")
+    n = x.shape[0]
+    L = _abi.lib()
+    nb = L.pinn_mlp_bwd_workspace_bytes(net.width, net.n_hidden, n)
+    ws = _workspace("bwd", nb, x.device)
+    with torch.cuda.device(x.device):
+        check(L.pinn_train_dnn_step(C.byref(net.desc), ptr(x), n, C.byref(drop) if drop is not None else None, ptr(y),
+                                    int(n_global), ptr(params_flat), ptr(exp_avg), ptr(exp_avg_sq), ptr(step_counter),
+                                    float(lr0), float(gamma), int(step_size), ptr(grad_flat), ptr(loss_sums), ptr(ws), nb,
+                                    _stream()), "pinn_train_dnn_step")
+    LAUNCHES += 3

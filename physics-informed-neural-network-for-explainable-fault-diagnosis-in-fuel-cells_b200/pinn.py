@@ -252,6 +252,7 @@ class PhysicsInformedNN:
             print("================== DNN training ==================")
             print("  Epoch |    Loss    |    MSE     |    LR    ")
         loss = float("nan")
+        fused_step = n_local > 0 and os.environ.get("B200PINN_FUSED_DNN_STEP", "1") != "0"
         for epoch in range(nIter):
             cfg = self.dnn.next_dropout_cfg(n_local, self.dnn.active_dropout_p())
             drop = K.make_dropout(**cfg) if cfg is not None else None
@@ -260,6 +261,8 @@ class PhysicsInformedNN:
                 sl = bucket.tag & 1
                 K.mlp_backward(net, x, drop, y=y, n_global=n_global, grad_flat=bucket.slot(sl), loss_sums=sums)
                 K.adam_step_p2p(flat, bucket.ptrs, bucket.rank, bucket.world, sl, bucket.tag, m, v, counter, 1e-2, 0.8, 1000)
+            elif world == 1 and fused_step:
+                K.train_dnn_step(net, x, drop, y, n_global, flat, m, v, counter, 1e-2, 0.8, 1000, grad, sums)
             else:
                 K.mlp_backward(net, x, drop, y=y, n_global=n_global, grad_flat=grad, loss_sums=sums)
                 if world > 1:
@@ -296,6 +299,19 @@ class PhysicsInformedNN:
         sc = self._scalers(self.x_scal)
         world = _world()
         last = None
+        if world == 1 and x.shape[0] > 0 and os.environ.get("B200PINN_PHASE_KERNEL", "1") != "0":
+            # single GPU: every stretch of epochs up to the next progress line (1 in 1000, 01:1049 etc.)
+            # is ONE persistent launch -- residual sums, Adam, StepLR and clamps iterate on the device
+            epoch = 0
+            while epoch < nIter:
+                stop = min(((epoch + 999) // 1000) * 1000, nIter - 1)     # next epoch whose sums are read
+                K.scalar_phase(x, u, y, sc, lam, fam, flags, lo_idx, slots, bounds, m, v, counter, lr, gamma, 1000,
+                               stop - epoch + 1, sums)
+                last = sums.cpu().numpy()
+                if verbose and stop % 1000 == 0:
+                    print(report(stop, last, lr * gamma ** (stop // 1000)))
+                epoch = stop + 1
+            return last
         for epoch in range(nIter):
             K.residuals(x, u, y, sc, lam, fam, flags=flags, sums=sums)
             if world > 1:

@@ -1,0 +1,23 @@
+"""train_dnn at configs[0] size (N = 20 000, 3x64): a few warm-up steps, then `steps` timed ones.  Run plain for the
+per-step wall / device time, or under `ncu --metrics gpu__time_duration.sum` for the per-kernel launch list.
+usage: python profiles/c1_train_dnn_launches.py [n] [steps]"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import b200pinn
+from b200pinn.synthetic import make_scaled_dataset
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+x, y, sx, sy = make_scaled_dataset(n, seed=1)
+torch.manual_seed(0)
+m = b200pinn.PhysicsInformedNN(torch.tensor(x), torch.tensor(y), [8, 64, 64, 64, 1], sx, sy, 0.2, True)
+m.train_dnn(5, verbose=False)
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+t0 = time.perf_counter()
+a.record()
+m.train_dnn(steps, verbose=False)
+b.record()
+torch.cuda.synchronize()
+print(f"n={n} steps={steps}: wall {1e6 * (time.perf_counter() - t0) / steps:.1f} us/step, device {1e3 * a.elapsed_time(b) / steps:.1f} us/step")
