@@ -317,11 +317,13 @@ PINN_D void adam_consts(double lr, int64_t t, float& step, float& sqrt_bc2) {
   sqrt_bc2 = static_cast<float>(sqrt(bc2));
 }
 PINN_D void adam_apply(float& p, float g, float& m, float& v, float step, float sqrt_bc2, float lo, float hi, bool clamp) {
+  // explicit roundings / fusions: every kernel that inlines this produces the same bits (the compiler's own
+  // contraction choices depend on the surrounding code)
   const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
-  m = m + (g - m) * (1.0f - b1);
-  v = v * b2 + (1.0f - b2) * g * g;
-  const float denom = sqrtf(v) / sqrt_bc2 + eps;
-  float q = p - step * (m / denom);
+  m = __fmaf_rn(__fsub_rn(g, m), 1.0f - b1, m);
+  v = __fmaf_rn(v, b2, __fmul_rn(__fmul_rn(1.0f - b2, g), g));
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), sqrt_bc2), eps);
+  float q = __fmaf_rn(-step, __fdiv_rn(m, denom), p);
   if (clamp) q = fminf(fmaxf(q, lo), hi);
   p = q;
 }

@@ -157,11 +157,13 @@ wgrad_tc_kernel(WgradArgs a, ParamLayout lay, WgLayout wl, RowMap rm) {
   __syncthreads();
   tc::fence_after_sync();
 
-  // tile range of this CTA
-  const int64_t per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
-  const int64_t t_begin = static_cast<int64_t>(blockIdx.x) * per < a.n_tiles ? static_cast<int64_t>(blockIdx.x) * per : a.n_tiles;
-  const int64_t t_end = t_begin + per < a.n_tiles ? t_begin + per : a.n_tiles;
-  const int64_t n_stage = (t_end - t_begin) * (kBTile / kWgStage);
+  // stage range of this CTA: the work unit is one 16-sample slab, not a tile, so that small batches spread over
+  // every SM (N = 20 000 is 157 tiles: by tiles 79 CTAs would take two each and 69 SMs none)
+  const int64_t total_st = a.n_tiles * (kBTile / kWgStage);
+  const int64_t per = (total_st + gridDim.x - 1) / gridDim.x;
+  const int64_t g_begin = static_cast<int64_t>(blockIdx.x) * per < total_st ? static_cast<int64_t>(blockIdx.x) * per : total_st;
+  const int64_t g_end = g_begin + per < total_st ? g_begin + per : total_st;
+  const int64_t n_stage = g_end - g_begin;
 
   if (mma_warp) {
     // ================================================================== MMA warp
@@ -228,8 +230,9 @@ wgrad_tc_kernel(WgradArgs a, ParamLayout lay, WgLayout wl, RowMap rm) {
     float4 ldA[kItems], ldB[kItems];                            // two stages of loads in flight per thread (HBM latency)
     float4 ldxA = make_float4(0.f, 0.f, 0.f, 0.f), ldxB = ldxA;
     auto load_stage = [&](int64_t st, float4 (&ld)[kItems], float4& ldx) {
-      const int64_t tile = t_begin + st / (kBTile / kWgStage);
-      const int s0 = static_cast<int>(st % (kBTile / kWgStage)) * kWgStage;
+      const int64_t gs = g_begin + st;
+      const int64_t tile = gs / (kBTile / kWgStage);
+      const int s0 = static_cast<int>(gs % (kBTile / kWgStage)) * kWgStage;
       const float* base = a.rows + static_cast<size_t>(tile) * rm.rows * kBTile + static_cast<size_t>(s0 / kWgStage) * rm.rows * kRowStride;   // one contiguous slab
 #pragma unroll
       for (int it = 0; it < kItems; ++it) {
@@ -913,7 +916,8 @@ static TcBwdPlan plan_tc_bwd(int L, int64_t n) {
   const int64_t tiles = (n + kBTile - 1) / kBTile;
   int64_t want = (tiles + 1) / 2;
   p.grid_a = static_cast<int>(want < sms ? (want > 0 ? want : 1) : sms);
-  p.grid_b = static_cast<int>(tiles < sms ? (tiles > 0 ? tiles : 1) : sms);
+  const int64_t want_b = (tiles * (kBTile / kWgStage) + 3) / 4;       // K2b splits by 16-sample stages: at least four per CTA
+  p.grid_b = static_cast<int>(want_b < sms ? (want_b > 0 ? want_b : 1) : sms);
   p.smem_a = static_cast<size_t>(make_tcb_layout(L).total) * sizeof(float);
   p.smem_b = static_cast<size_t>(2) * make_wg_layout(L).buffer_bytes;
   size_t off = static_cast<size_t>(2 * p.grid_a) * 4 * sizeof(double);

@@ -289,9 +289,12 @@ def test_fused_train_dnn_step_matches_bwd_plus_adam(layers, n, monkeypatch):
 
     loss_f, sd_f = run("1")
     loss_u, sd_u = run("0")
-    assert np.isfinite(loss_f) and loss_f == loss_u
-    for k in sd_f:
-        assert np.array_equal(sd_f[k], sd_u[k]), k
+    loss_u2, sd_u2 = run("0")
+    assert np.isfinite(loss_f) and np.isfinite(loss_u)
+    for k in sd_u:
+        assert np.array_equal(sd_u[k], sd_u2[k]), ("step is not deterministic run to run", k)
+    worst = max(nrel(sd_f[k], sd_u[k]) for k in sd_f)
+    assert worst == 0.0 and loss_f == loss_u, (worst, loss_f, loss_u)
 
 
 def test_train_dnn_trajectory_golden(golden):
