@@ -295,6 +295,36 @@ def run_ours(args):
     wide["what"] = ("N=262144 per GPU; MC sweep T=10 and train_dnn step on the per-layer tcgen05 3xTF32 GEMM path (operands as "
                     "pre-split tf32 planes, TMA bulk copies; dgrad = same kernel on transposed weight planes, weight gradients "
                     "= split-K GEMMs over sample-contiguous copies)")
+    # --- configs[0] scale (N = 20 000, the reference's own CPU-runnable case): every step is latency-bound here.
+    # train_dnn = K2a + K2b + (gradient reduce + Adam) per step; the scalar phases run as persistent launches
+    # (pinn_scalar_phase: 1000 optimiser steps per launch, one grid barrier per step)
+    c1 = None
+    if world == 1:
+        n1 = 20_000
+        torch.manual_seed(0)
+        m1 = b200pinn.PhysicsInformedNN(X[:n1], Y[:n1], LAYERS, sx, sy, P_TRAIN, True)
+
+        def wall(fn, k):
+            fn(3)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn(k)
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / k
+
+        c1 = {"n": n1,
+              "train_dnn_us_per_step": 1e6 * wall(lambda k: m1.train_dnn(k, verbose=False), 500),
+              "train_lambda_us_per_step": 1e6 * wall(lambda k: m1.train_lambda(k, True, verbose=False), 2001),
+              "train_thermal_us_per_step": 1e6 * wall(lambda k: m1.train_thermal(k, verbose=False), 2001),
+              "train_hydrogen_us_per_step": 1e6 * wall(lambda k: m1.train_hydrogen(k, verbose=False), 2001),
+              "train_oxygen_us_per_step": 1e6 * wall(lambda k: m1.train_oxygen(k, verbose=False), 2001),
+              "what": "configs[0] size, wall clock per optimiser step through the drop-in trainers (includes the 1-in-1000 "
+                      "progress read-back); the reference's schedule 01:2143-2153 is 12 002 train_dnn + 34 005 scalar-phase "
+                      "steps (profiles/c1_pipeline.py runs it end to end)"}
+        c1["schedule_s_estimate"] = 1e-6 * (12002 * c1["train_dnn_us_per_step"] + 8002 * c1["train_lambda_us_per_step"]
+                                            + 10001 * c1["train_thermal_us_per_step"] + 8001 * c1["train_hydrogen_us_per_step"]
+                                            + 8001 * c1["train_oxygen_us_per_step"])
+        del m1
     # --- e2e: public API, host tensors in pinned memory, results back on the host
     Xp = X.pin_memory()
     import contextlib
@@ -357,8 +387,9 @@ def run_ours(args):
                           "achieved": n * (2 * 496 * 4 + 36) / (t_tr / steps_tr) / 1e9,
                           "frac_of_peak": n * (2 * 496 * 4 + 36) / (t_tr / steps_tr) / 1e9 / pk["hbm"]},
                   "what": "train_dnn step: K2a (tcgen05 fwd+loss+dgrad, writes a transposed 2 KB/sample row table) + K2b "
-                          "(tcgen05 3xTF32 weight gradients, HBM-bound on that table: see profiles/) + partial reduce + "
-                          + ("NCCL all-reduce of the flat grad bucket + " if world > 1 else "") + "fused Adam/StepLR"},
+                          "(tcgen05 3xTF32 weight gradients, HBM-bound on that table: see profiles/) + "
+                          + ("partial reduce + gradient sum over NVLink peer memory fused into the Adam/StepLR launch"
+                             if world > 1 else "partial reduce with Adam/StepLR applied in the same launch")},
         "roofline_residual": {"bound": "hbm", "achieved": nb * RES_BYTES_PER_SAMPLE / (t_resb / K_) / 1e9, "peak": pk["hbm"],
                               "unit": "GB/s", "frac": nb * RES_BYTES_PER_SAMPLE / (t_resb / K_) / 1e9 / pk["hbm"],
                               "traffic": None, "kernel": "residual_kernel<V|DATA, fast math>", "rows": nb,
@@ -374,6 +405,8 @@ def run_ours(args):
                      "rf_rows_per_s": world * 8 * n * n_exp / t_rf, "rf_ms_per_8_stacks": 1e3 * t_rf / n_exp,
                      "rf_hbm_gbs": 8 * n * (22 * 8 + 2 * 8) * n_exp / t_rf / 1e9}
     line["wide"] = wide
+    if c1 is not None:
+        line["c1"] = c1
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
         mc_rate, tr_rate, t1, t2 = cpu_port_rates(1_000_000, 200_000, threads)

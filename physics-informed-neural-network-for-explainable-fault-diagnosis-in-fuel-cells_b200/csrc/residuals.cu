@@ -392,7 +392,7 @@ static int res_grid(int64_t n, int ctas_per_sm = kResCtasPerSm, int samples_per_
 // x / u / y never change during a phase, so after the first step they are served from L1 / L2.
 // Two partial buffers make one barrier per step enough: a CTA can be at most one step ahead of the
 // slowest one, so the buffer it writes is never the one a straggler still reads.
-constexpr int kPhaseThreads = 256;
+constexpr int kPhaseMaxThreads = 1024;
 constexpr int kPhaseMaxParams = 8;
 constexpr int kPhaseFold = 16;
 
@@ -420,28 +420,41 @@ PINN_D unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
   return v;
 }
 
+// Block size 512 (n <= 512 x SMs: one sample per thread, few CTAs -> cheap barrier) or 1024 (one CTA per SM,
+// grid-stride).  What is on the critical path of a step besides the samples themselves: one global store +
+// fence + atomic per CTA, the barrier, one round of L2 loads for the fold, and the optimiser arithmetic --
+// so the bias corrections 1 - beta^t are carried as running products (one multiply per step; `pow` only at
+// launch start and at StepLR boundaries; three double-precision `pow` calls cost more than everything else
+// in the step) and every thread folds at most four partials with all loads in flight at once.
 template <uint32_t FAMC, int R0, int R1>
-__global__ void __launch_bounds__(kPhaseThreads, 4) scalar_phase_kernel(const PhaseArgs a) {
+__global__ void __launch_bounds__(kPhaseMaxThreads, 1) scalar_phase_kernel(const PhaseArgs a) {
   constexpr int R = R1 - R0;
   static_assert(R <= kPhaseFold, "fold layout holds 16 slots");
-  __shared__ double red[kPhaseThreads / 32][R];
-  __shared__ double fold[kPhaseFold][R];
-  __shared__ double tot[R];
+  __shared__ double red[kPhaseMaxThreads / 32][kPhaseFold];
+  __shared__ double tot[kPhaseFold];
   __shared__ float lam_s[PINN_N_LAMBDA];
   __shared__ int slot_s[kPhaseMaxParams];
   __shared__ float lo_s[kPhaseMaxParams], hi_s[kPhaseMaxParams];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   if (tid < PINN_N_LAMBDA) lam_s[tid] = a.lam[tid];
   if (tid < kPhaseMaxParams) { slot_s[tid] = a.slot[tid]; lo_s[tid] = a.lo[tid]; hi_s[tid] = a.hi[tid]; }
   float mm = 0.f, vv = 0.f;
   if (tid < a.count) { mm = a.m[tid]; vv = a.v[tid]; }
   int64_t t0 = *a.step_counter;
+  // optimiser constants of the thread that owns a scalar (redundant per owner: no broadcast needed)
+  double pw1 = 1.0, pw2 = 1.0, lr = a.h.lr0;
+  if (tid < a.count) {
+    pw1 = pow(0.9, static_cast<double>(t0));
+    pw2 = pow(0.999, static_cast<double>(t0));
+    lr = a.h.lr0 * pow(a.h.gamma, static_cast<double>(t0 / a.h.step_size));
+  }
   const bool has_y = a.y != nullptr;
   const bool do_v = (a.fam & PINN_FAM_V) != 0, do_d = (a.fam & PINN_FAM_DATA) != 0 && has_y;
   const bool mode_a = !(a.flags & PINN_RES_NO_MODE_A), mode_b = !(a.flags & PINN_RES_NO_MODE_B);
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   const int64_t s0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + tid;
   const double cnt = a.n > 0 ? static_cast<double>(a.n) : 1.0;
+  const int fk = tid & (kPhaseFold - 1), fg = tid >> 4, nfg = blockDim.x >> 4;     // fold: slot fk, CTAs fg, fg + nfg, ...
   __syncthreads();
 
   for (int64_t step = 0; step < a.n_steps; ++step) {
@@ -474,7 +487,7 @@ __global__ void __launch_bounds__(kPhaseThreads, 4) scalar_phase_kernel(const Ph
     const size_t buf = static_cast<size_t>(step & 1) * gridDim.x * R;
     if (tid < R) {
       double v = 0.0;
-      for (int w = 0; w < kPhaseThreads / 32; ++w) v += red[w][tid];
+      for (int w = 0; w < nwarp; ++w) v += red[w][tid];
       a.partials[buf + static_cast<size_t>(blockIdx.x) * R + tid] = v;
     }
     // grid barrier: arrivals are counted monotonically, step k completes at (k+1) * gridDim.x
@@ -487,29 +500,41 @@ __global__ void __launch_bounds__(kPhaseThreads, 4) scalar_phase_kernel(const Ph
       __threadfence();
     }
     __syncthreads();
+    // fold: identical order in every CTA.  Thread (fk, fg) adds CTAs fg, fg + nfg, ... (<= 4 per batch, loads issued
+    // together), the two groups of a warp meet by shuffle, warp sub-sums go through shared memory, warp 0 finishes.
     {
-      const int k = tid & (kPhaseFold - 1), g = tid >> 4;   // 16 slots x 16 groups
-      if (k < R) {
-        double v = 0.0;
-        for (unsigned int b = g; b < gridDim.x; b += kPhaseThreads / kPhaseFold)
-          v += __ldcg(a.partials + buf + static_cast<size_t>(b) * R + k);
-        fold[g][k] = v;
+      double v = 0.0;
+      if (fk < R) {
+        const double* base = a.partials + buf + fk;
+        for (unsigned int b = fg; b < gridDim.x; b += 4 * nfg) {
+          const unsigned int b1 = b + nfg, b2 = b + 2 * nfg, b3 = b + 3 * nfg;
+          const double v0 = __ldcg(base + static_cast<size_t>(b) * R);
+          const double v1 = b1 < gridDim.x ? __ldcg(base + static_cast<size_t>(b1) * R) : 0.0;
+          const double v2 = b2 < gridDim.x ? __ldcg(base + static_cast<size_t>(b2) * R) : 0.0;
+          const double v3 = b3 < gridDim.x ? __ldcg(base + static_cast<size_t>(b3) * R) : 0.0;
+          v += v0; v += v1; v += v2; v += v3;
+        }
       }
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < kPhaseFold) red[warp][lane] = v;
     }
     __syncthreads();
-    if (tid < R) {
+    if (warp == 0) {
       double t = 0.0;
-      for (int g = 0; g < kPhaseFold; ++g) t += fold[g][tid];
-      tot[tid] = t;
+      const int half = lane >> 4, k = lane & 15, per = (nwarp + 1) >> 1;
+      for (int w = half * per; w < (half + 1) * per && w < nwarp; ++w) t += red[w][k];
+      t += __shfl_xor_sync(0xffffffffu, t, 16);
+      if (lane < kPhaseFold) tot[lane] = t;
     }
     __syncthreads();
     if (tid < a.count) {
       const int sl = slot_s[tid];
       float p = lam_s[a.first + tid];
+      pw1 *= 0.9; pw2 *= 0.999;
+      if (t0 > 0 && t0 % a.h.step_size == 0) lr = a.h.lr0 * pow(a.h.gamma, static_cast<double>(t0 / a.h.step_size));
       if (sl >= 0) {
-        const double lr = a.h.lr0 * pow(a.h.gamma, static_cast<double>(t0 / a.h.step_size));
         const float g = static_cast<float>(tot[sl - R0] / cnt);
-        adam_update(p, g, mm, vv, lr, t0 + 1, lo_s[tid], hi_s[tid], true);
+        adam_apply(p, g, mm, vv, static_cast<float>(lr / (1.0 - pw1)), static_cast<float>(sqrt(1.0 - pw2)), lo_s[tid], hi_s[tid], true);
       } else {
         p = fminf(fmaxf(p, lo_s[tid]), hi_s[tid]);   // the reference clamps every listed scalar each step
       }
@@ -534,16 +559,16 @@ template <uint32_t FAMC, int R0, int R1>
 static int launch_phase(PhaseArgs& a, size_t workspace_bytes, void* workspace, cudaStream_t st) {
   for (int i = 0; i < a.count; ++i)
     if (a.slot[i] >= 0 && (a.slot[i] < R0 || a.slot[i] >= R1)) return PINN_E_ARG;
+  const int sms = sm_count();
+  const int threads = a.n <= static_cast<int64_t>(512) * sms ? 512 : kPhaseMaxThreads;
   int occ = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scalar_phase_kernel<FAMC, R0, R1>, kPhaseThreads, 0);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scalar_phase_kernel<FAMC, R0, R1>, threads, 0);
   if (e != cudaSuccess) return static_cast<int>(e);
   if (occ < 1) return PINN_E_ARG;
-  if (occ > 4) occ = 4;
-  const int64_t want = (a.n + kPhaseThreads - 1) / kPhaseThreads;
-  const int64_t cap = static_cast<int64_t>(sm_count()) * occ;
-  const int grid = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
+  const int64_t want = (a.n + threads - 1) / threads;
+  const int grid = static_cast<int>(want < sms ? (want > 0 ? want : 1) : sms);      // never more than one CTA per SM
   if (static_cast<uint64_t>(a.n_steps) * static_cast<uint64_t>(grid) >= 0x7fffffffull) return PINN_E_ARG;
-  const size_t part_bytes = static_cast<size_t>(2) * sm_count() * 4 * kPhaseFold * sizeof(double);
+  const size_t part_bytes = static_cast<size_t>(2) * sms * kPhaseFold * sizeof(double);
   if (workspace_bytes < part_bytes + 16) return PINN_E_WORKSPACE;
   a.partials = static_cast<double*>(workspace);
   a.barrier = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + part_bytes);
@@ -551,7 +576,7 @@ static int launch_phase(PhaseArgs& a, size_t workspace_bytes, void* workspace, c
   if (e != cudaSuccess) return static_cast<int>(e);
   void* params[] = {&a};
   e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(scalar_phase_kernel<FAMC, R0, R1>), dim3(grid),
-                                  dim3(kPhaseThreads), params, 0, st);
+                                  dim3(threads), params, 0, st);
   return static_cast<int>(e);
 }
 
@@ -608,7 +633,7 @@ extern "C" int pinn_residuals(const float* x, const float* u, const float* y, in
 }
 
 extern "C" size_t pinn_scalar_phase_workspace_bytes(void) {
-  return static_cast<size_t>(2) * sm_count() * 4 * kPhaseFold * sizeof(double) + 16;
+  return static_cast<size_t>(2) * sm_count() * kPhaseFold * sizeof(double) + 16;
 }
 
 extern "C" int pinn_scalar_phase(const float* x, const float* u, const float* y, int64_t n,

@@ -266,7 +266,8 @@ def test_persistent_phase_kernel_matches_step_by_step_path(n, monkeypatch):
     lo, hi = np.array([0.0835, 2.36e-7, 2.0, 0.1]), np.array([0.835, 4.956e-6, 10.4, 10.0])    # 01:992-997
     for snap in (snap_p[1], snap_s[1]):
         assert np.all(snap >= lo * (1 - 1e-6)) and np.all(snap <= hi * (1 + 1e-6)), snap
-    assert np.allclose(lam_p[4:], lam_s[4:], rtol=2e-5, atol=1e-9), (lam_p, lam_s)
+    # lambda_H2 / lambda_O2 converge towards 0 from O(1) starts: absolute tolerance on those
+    assert np.allclose(lam_p[4:], lam_s[4:], rtol=2e-5, atol=2e-6), (lam_p, lam_s)
     assert np.allclose(loss_p[4:], loss_s[4:], rtol=2e-5), (loss_p, loss_s)
 
 
