@@ -187,6 +187,14 @@ def test_abi_error_codes_without_gpu():
     assert L.pinn_rf_series(None, 0, 1, None, None, None, None, None, None, None, None, 0, None) == e["PINN_E_ARG"]
     assert L.pinn_export_rows(None, None, None, None, None, None, None, 0, 0, 0, None, 5, None, None) == e["PINN_E_ARG"]
     assert L.pinn_param_count(64, 0) == e["PINN_E_SHAPE"]
+    # the two whole-step entry points validate before touching the device as well
+    assert L.pinn_train_dnn_step(None, None, 0, None, None, 0, None, None, None, None, 1e-2, 0.8, 1000, None, None, None, 0,
+                                 None) == e["PINN_E_ARG"]
+    net.n_in, net.width, net.n_hidden = 8, 48, 3
+    assert L.pinn_train_dnn_step(C.byref(net), None, 0, None, None, 0, None, None, None, None, 1e-2, 0.8, 1000, None, None,
+                                 None, 0, None) == e["PINN_E_SHAPE"]
+    assert L.pinn_scalar_phase(None, None, None, 5, None, None, abi.FAM_TS, 0, 4, 5, None, None, None, None, None, None,
+                               1.0, 0.8, 1000, 10, None, None, 0, None) == e["PINN_E_ARG"]
     with pytest.raises(RuntimeError, match="null or inconsistent"):
         abi.check(e["PINN_E_ARG"], "unit test")
 

@@ -271,6 +271,43 @@ def test_persistent_phase_kernel_matches_step_by_step_path(n, monkeypatch):
     assert np.allclose(loss_p[4:], loss_s[4:], rtol=2e-5), (loss_p, loss_s)
 
 
+def test_scalar_phase_argument_checks_and_zero_steps():
+    """pinn_scalar_phase: gradient slots of another family, too many scalars and mixed families are refused;
+    zero steps leave the scalars, the moments and the step counter untouched."""
+    from b200pinn import _abi, kernels as K
+    from b200pinn.synthetic import make_scaled_dataset
+
+    x, y, sx, sy = make_scaled_dataset(1000, seed=2)
+    xd = torch.tensor(x, device=dev())
+    sc = K.make_scalers(sx, sy)
+    lam = torch.tensor(__import__("b200pinn").pinn.LAMBDA_INIT, device=dev(), dtype=torch.float32)
+    lam0 = lam.clone()
+    m, v = torch.zeros(5, device=dev()), torch.zeros(5, device=dev())
+    counter = K.new_step_counter(dev())
+    sums = torch.full((_abi.S_COUNT,), -1.0, device=dev(), dtype=torch.float64)
+    S = _abi.S
+    good = dict(slots=[S["GT1"], -1, S["GT3"], -1, S["GT5"]], bounds=[(-1e4, 1e4)] * 5)
+    call = lambda fam, first, slots, bounds, steps: K.scalar_phase(xd, None, None, sc, lam, fam, 0, first, slots, bounds,
+                                                                   m, v, counter, 1.0, 0.8, 1000, steps, sums)
+    with pytest.raises(RuntimeError, match="inconsistent"):
+        call(_abi.FAM_TS, 4, [S["GH1"], -1, S["GT3"], -1, S["GT5"]], good["bounds"], 3)       # hydrogen slot in the thermal phase
+    with pytest.raises(RuntimeError, match="inconsistent"):
+        call(_abi.FAM_TS | _abi.FAM_H, 4, good["slots"], good["bounds"], 3)                    # one family per phase
+    with pytest.raises(RuntimeError, match="inconsistent"):
+        call(_abi.FAM_TS, 4, [-1] * 9, [(-1.0, 1.0)] * 9, 3)                                   # more than 8 scalars
+    with pytest.raises(RuntimeError, match="inconsistent"):
+        call(_abi.FAM_TS, 14, good["slots"], good["bounds"], 3)                                # slice runs past the 17 scalars
+    call(_abi.FAM_TS, 4, good["slots"], good["bounds"], 0)
+    torch.cuda.synchronize()
+    assert torch.equal(lam, lam0) and int(counter[0]) == 0 and float(m.abs().sum()) == 0.0
+    s = t2n(sums)
+    assert s[S["N"]] == 1000.0 and np.all(np.delete(s, S["N"]) == 0.0)
+    call(_abi.FAM_TS, 4, good["slots"], good["bounds"], 7)
+    torch.cuda.synchronize()
+    assert int(counter[0]) == 7 and not torch.equal(lam[4:9], lam0[4:9]) and torch.equal(lam[:4], lam0[:4])
+    assert torch.equal(lam[9:], lam0[9:]) and t2n(sums)[S["FT2"]] > 0.0
+
+
 @pytest.mark.parametrize("layers,n", [([8, 64, 64, 64, 1], 5000), ([8, 64, 64, 1], 300), ([8, 32, 32, 1], 1000)])
 def test_fused_train_dnn_step_matches_bwd_plus_adam(layers, n, monkeypatch):
     """pinn_train_dnn_step (gradient reduce + Adam + StepLR in one launch on the tensor-core path) vs
