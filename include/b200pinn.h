@@ -265,6 +265,12 @@ int pinn_adam_step_p2p(float* params, const uint64_t* peer_buffers, int32_t rank
 int pinn_set_tensor_core_path(int enable);
 /* Same switch for the backward kernels (pinn_mlp_bwd). */
 int pinn_set_tensor_core_bwd(int enable);
+/* Ablation switch: the tensor-core backward's three launches (forward+dgrad, weight
+ * gradients, reduce[+Adam]) are chained with programmatic dependent launch so that each
+ * kernel's launch and prologue overlap its predecessor's tail.  1 (default): for batches
+ * up to 2 tiles per SM, where launch latency is a visible share of the step; 2: always;
+ * 0: never.  Results are identical.  Returns the previous setting. */
+int pinn_set_dependent_launch(int enable);
 /* Same switch for the 128- / 256-wide nets' forward and MC-dropout sweep (one tcgen05 GEMM launch
  * per layer, operands as pre-split tf32 planes; 0 = thread-per-sample FFMA kernels). */
 int pinn_set_wide_tensor_core_path(int enable);

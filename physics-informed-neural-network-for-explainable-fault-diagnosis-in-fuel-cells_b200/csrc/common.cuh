@@ -302,6 +302,24 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device
 
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start (and run its prologue) while its predecessor in the stream is still running; `griddep_wait` blocks until the
+// predecessor grid has completed and its memory is visible, `griddep_launch` lets the successor start launching.  Both
+// are no-ops in a kernel launched the ordinary way.
+PINN_D void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+PINN_D void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Launch helper: <<<grid, block, smem, st>>> with (pdl = true) or without the programmatic-serialization attribute.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 struct AdamHyper {
   double lr0, gamma, grad_scale;
   int64_t step_size;

@@ -109,6 +109,10 @@ PINN_HD WgLayout make_wg_layout(int L) {
 
 #ifdef PINN_TIMELINE
 __device__ long long g_tlw[2][64][4];     // [0]: MMA warp {wake, issued}; [1]: loader thread 0 {pre-wait, post-wait, post-store, post-arrive}
+__device__ long long g_tlp[2][8];         // coarse phase stamps of CTA 0: [0] = K2b {entry, prologue done, streaming done, partial written}, [1] = K2a {entry, weights staged, tiles done, end}
+#define TLP(k, i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_tlp[k][i] = clock64(); } while (0)
+#else
+#define TLP(k, i) do { } while (0)
 #endif
 struct WgradArgs {
   const float* x; int64_t n; int64_t n_tiles;
@@ -128,6 +132,8 @@ wgrad_tc_kernel(WgradArgs a, ParamLayout lay, WgLayout wl, RowMap rm) {
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tc::uniform_warp_idx();
   const bool mma_warp = warp == kWgLoaders / 32;
+  TLP(0, 0);
+  griddep_launch();
 
   if (tid == 0) {
     tc::mbar_init(&full[0], kWgLoaders); tc::mbar_init(&full[1], kWgLoaders);
@@ -157,6 +163,8 @@ wgrad_tc_kernel(WgradArgs a, ParamLayout lay, WgLayout wl, RowMap rm) {
   __syncthreads();
   tc::fence_after_sync();
 
+  griddep_wait();          // everything above is independent of K2a's output (the row table)
+  TLP(0, 1);
   // stage range of this CTA: the work unit is one 16-sample slab, not a tile, so that small batches spread over
   // every SM (N = 20 000 is 157 tiles: by tiles 79 CTAs would take two each and 69 SMs none)
   const int64_t total_st = a.n_tiles * (kBTile / kWgStage);
@@ -302,11 +310,15 @@ wgrad_tc_kernel(WgradArgs a, ParamLayout lay, WgLayout wl, RowMap rm) {
       dpar[buf] ^= 1u;
     }
     tc::fence_after_sync();
+    TLP(0, 2);
     // ---------------------------------------------------------------- accumulators -> this CTA's partial
     float* part = a.partial + static_cast<size_t>(blockIdx.x) * lay.total;
-    if (warp < 4) {
-      const int lane_row = warp * 32 + (tid & 31);
-      const uint32_t tl = tmem_base_s + (static_cast<uint32_t>(warp * 32) << 16);
+    {
+      // All eight loader warps read out: warp w owns TMEM lanes 32 (w & 3) .. +31 (the hardware's lane quadrant rule),
+      // and the two warps of a quadrant take alternate 16-column groups.  Weight rows go out as 16-byte stores.
+      const int wq = warp & 3, wh = warp >> 2;
+      const int lane_row = wq * 32 + (tid & 31);
+      const uint32_t tl = tmem_base_s + (static_cast<uint32_t>(wq * 32) << 16);
       const bool have = n_stage > 0;
       auto read16 = [&](int col, float (&v)[16]) {
         if (have) { tc::tmem_ld16(tl + static_cast<uint32_t>(col), v); tc::tmem_wait_ld(); }
@@ -315,7 +327,13 @@ wgrad_tc_kernel(WgradArgs a, ParamLayout lay, WgLayout wl, RowMap rm) {
           for (int q = 0; q < 16; ++q) v[q] = 0.f;
         }
       };
+      auto store16_scaled = [&](float* dst, const float (&v)[16]) {     // dst 16-byte aligned
+#pragma unroll
+        for (int q = 0; q < 16; q += 4)
+          *reinterpret_cast<float4*>(dst + q) = make_float4(v[q] * a.act_scale, v[q + 1] * a.act_scale, v[q + 2] * a.act_scale, v[q + 3] * a.act_scale);
+      };
       float v[16];
+      int item = 0;        // compile-time after unrolling: work item counter, item & 1 selects the warp of the quadrant
       // trunk layers l >= 1: delta_l = lanes 64 h + j of big block i, a_{l-1} = columns 64 h + k of its B block (i = (l-1)/2, h = (l-1)%2)
 #pragma unroll
       for (int l = 1; l < L; ++l) {
@@ -325,54 +343,57 @@ wgrad_tc_kernel(WgradArgs a, ParamLayout lay, WgLayout wl, RowMap rm) {
         const bool mine = j >= 0 && j < 64;
 #pragma unroll
         for (int c = 0; c < 64; c += 16) {
-          read16(col0 + 64 * h + c, v);
-          if (mine) {
-#pragma unroll
-            for (int q = 0; q < 16; ++q) part[lay.offW[l] + j * 64 + c + q] = v[q] * a.act_scale;
+          if ((item++ & 1) == wh) {
+            read16(col0 + 64 * h + c, v);
+            if (mine) store16_scaled(part + lay.offW[l] + j * 64 + c, v);
           }
         }
-        read16(ones_col, v);
-        if (mine) part[lay.offb[l] + j] = v[0];
+        if ((item++ & 1) == wh) {
+          read16(ones_col, v);
+          if (mine) part[lay.offb[l] + j] = v[0];
+        }
       }
       // small product
 #pragma unroll
       for (int c = 0; c < 64; c += 16) {        // columns 0..63 = a_{L-1}: lanes 64..95 -> dWv0, lane 96 -> dWp
-        read16(COL_SMALL + c, v);
-        if (lane_row >= 64 && lane_row < 96) {
-#pragma unroll
-          for (int q = 0; q < 16; ++q) part[lay.offWv0 + (lane_row - 64) * 64 + c + q] = v[q] * a.act_scale;
-        } else if (lane_row == 96) {
-#pragma unroll
-          for (int q = 0; q < 16; ++q) part[lay.offWp + c + q] = v[q] * a.act_scale;
+        if ((item++ & 1) == wh) {
+          read16(COL_SMALL + c, v);
+          if (lane_row >= 64 && lane_row < 96) store16_scaled(part + lay.offWv0 + (lane_row - 64) * 64 + c, v);
+          else if (lane_row == 96) store16_scaled(part + lay.offWp + c, v);
         }
       }
-      read16(COL_SMALL + 64, v);                // column 64 = ones (every bias); 65..72 = x^T; 73..79 = av0[0..7)
-      if (lane_row < 64) {
-        part[lay.offb[0] + lane_row] = v[0];
+      if ((item++ & 1) == wh) {
+        read16(COL_SMALL + 64, v);                // column 64 = ones (every bias); 65..72 = x^T; 73..79 = av0[0..7)
+        if (lane_row < 64) {
+          part[lay.offb[0] + lane_row] = v[0];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) part[lay.offW[0] + lane_row * 8 + q] = v[1 + q];
-      } else if (lane_row < 96) part[lay.offbv0 + lane_row - 64] = v[0];
-      else if (lane_row == 96) part[lay.offbp] = v[0];
-      else if (lane_row < 113) part[lay.offbv1 + lane_row - 97] = v[0];
-      else if (lane_row == 113) part[lay.offbv2] = v[0];
-      if (lane_row >= 97 && lane_row < 113) {
+          for (int q = 0; q < 8; ++q) part[lay.offW[0] + lane_row * 8 + q] = v[1 + q];
+        } else if (lane_row < 96) part[lay.offbv0 + lane_row - 64] = v[0];
+        else if (lane_row == 96) part[lay.offbp] = v[0];
+        else if (lane_row < 113) part[lay.offbv1 + lane_row - 97] = v[0];
+        else if (lane_row == 113) part[lay.offbv2] = v[0];
+        if (lane_row >= 97 && lane_row < 113) {
 #pragma unroll
-        for (int q = 0; q < 7; ++q) part[lay.offWv1 + (lane_row - 97) * 32 + q] = v[9 + q];
+          for (int q = 0; q < 7; ++q) part[lay.offWv1 + (lane_row - 97) * 32 + q] = v[9 + q];
+        }
       }
 #pragma unroll
       for (int c = 80; c < 128; c += 16) {      // columns 80..104 = av0[7..32), 105..120 = av1
-        read16(COL_SMALL + c, v);
+        if ((item++ & 1) == wh) {
+          read16(COL_SMALL + c, v);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int col = c + q;
-          if (col < kSmV1) { if (lane_row >= 97 && lane_row < 113) part[lay.offWv1 + (lane_row - 97) * 32 + col - kSmV0] = v[q]; }
-          else if (col < kSmV1 + 16) { if (lane_row == 113) part[lay.offWv2 + col - kSmV1] = v[q]; }
+          for (int q = 0; q < 16; ++q) {
+            const int col = c + q;
+            if (col < kSmV1) { if (lane_row >= 97 && lane_row < 113) part[lay.offWv1 + (lane_row - 97) * 32 + col - kSmV0] = v[q]; }
+            else if (col < kSmV1 + 16) { if (lane_row == 113) part[lay.offWv2 + col - kSmV1] = v[q]; }
+          }
         }
       }
     }
   }
   tc::fence_before_sync();
   __syncthreads();
+  TLP(0, 3);
   if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
 }
 
@@ -505,34 +526,78 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
   const int warp = tc::uniform_warp_idx(), grp = warp >> 3, half = (warp >> 2) & 1;
   const int Dm = L * H + H / 2;
   const int cb = half * HH;
+  TLP(1, 0);
+  griddep_launch();
 
   if (tid == 0) { tc::mbar_init(&mbar[0], 1); tc::mbar_init(&mbar[1], 1); tc::fence_mbar_init(); }
   __syncwarp();
   if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
+  griddep_wait();          // the weights come from the previous step's optimiser launch
   const bool drop_on = dp.p > 0.f;
   const float wscale = drop_on ? dp.scale : 1.0f;
-  stage_tensor_scaled(smem + lay.W0, net.W[0], H * PINN_N_IN, kTanhArg);    // tanh_pre arguments (common.cuh)
-  stage_tensor_scaled(smem + lay.b0, net.b[0], H, kTanhArg);
-  for (int l = 1; l < L; ++l) stage_tensor_scaled(smem + lay.b[l], net.b[l], H, kTanhArg);
-  stage_tensor_scaled(smem + lay.bv0, net.bv0, 32, kTanhArg);
-  stage_tensor(smem + lay.bp, net.bp, 1);
-  stage_tensor(smem + lay.Wv1, net.Wv1, 16 * 32);
-  stage_tensor_scaled(smem + lay.bv1, net.bv1, 16, kTanhArg);
-  stage_tensor(smem + lay.Wv2, net.Wv2, 16);
-  stage_tensor(smem + lay.bv2, net.bv2, 1);
-  if constexpr (RES) {
-    for (int l = 1; l < L; ++l) {
-      stage_plane_rows(smem + lay.wf_hi[l], smem + lay.wf_lo[l], net.W[l], nullptr, H, wscale);
-      stage_plane_transposed(smem + lay.wt_hi[l], smem + lay.wt_lo[l], net.W[l], nullptr, H, wscale);
+  // Weight staging with every global load issued before the first use: the former sequence of 15 load -> store loops
+  // paid one L2 round trip each (6.9 us per launch, a tenth of the whole step at N = 20 000).
+  {
+    // small tensors: one element per thread.  W0 [64 x 8] and Wv1 [16 x 32] are 512 floats each; the biases, Wv2, bp, bv2
+    // are laid over the thread index: [64 l, 64 l + 64) = b[l], [256, 288) = bv0, [288, 304) = bv1, [304, 320) = Wv2, 320 = bp, 321 = bv2
+    const float w0 = __ldg(net.W[0] + tid), wv1 = __ldg(net.Wv1 + tid);
+    const float* sp = nullptr;
+    float* dstp = nullptr;
+    float sc = 1.0f;
+    if (tid < 64 * L) { const int l = tid >> 6, j = tid & 63; sp = net.b[l] + j; dstp = smem + (l == 0 ? lay.b0 : lay.b[l]) + j; sc = kTanhArg; }
+    else if (tid >= 256 && tid < 288) { sp = net.bv0 + (tid - 256); dstp = smem + lay.bv0 + (tid - 256); sc = kTanhArg; }
+    else if (tid >= 288 && tid < 304) { sp = net.bv1 + (tid - 288); dstp = smem + lay.bv1 + (tid - 288); sc = kTanhArg; }
+    else if (tid >= 304 && tid < 320) { sp = net.Wv2 + (tid - 304); dstp = smem + lay.Wv2 + (tid - 304); }
+    else if (tid == 320) { sp = net.bp; dstp = smem + lay.bp; }
+    else if (tid == 321) { sp = net.bv2; dstp = smem + lay.bv2; }
+    const float sv = sp != nullptr ? __ldg(sp) : 0.f;
+    float4 wv[RES ? L : 1][2];
+    if constexpr (RES) {
+#pragma unroll
+      for (int l = 1; l <= L; ++l) {
+        const float* src = l < L ? net.W[l] : net.Wv0;
+        const int J = l < L ? H : 32;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int idx = tid + it * 512, j = idx & 63, kc = idx >> 6;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (j < J) v = __ldg(reinterpret_cast<const float4*>(src + j * 64) + kc);
+          else if (l == L && j == J) v = __ldg(reinterpret_cast<const float4*>(net.Wp) + kc);
+          wv[l - 1][it] = v;
+        }
+      }
     }
-    stage_plane_rows(smem + lay.wf_hi[L], smem + lay.wf_lo[L], net.Wv0, net.Wp, 32, wscale);
-    stage_plane_transposed(smem + lay.wt_hi[L], smem + lay.wt_lo[L], net.Wv0, net.Wp, 32, wscale);
-    tc::fence_proxy_async();
+    smem[lay.W0 + tid] = w0 * kTanhArg;      // tanh_pre arguments (common.cuh)
+    smem[lay.Wv1 + tid] = wv1;
+    if (dstp != nullptr) *dstp = sv * sc;
+    if constexpr (RES) {
+#pragma unroll
+      for (int l = 1; l <= L; ++l) {
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int idx = tid + it * 512, j = idx & 63, kc = idx >> 6;
+          const float4 v = wv[l - 1][it];
+          const float vv[4] = {v.x * wscale, v.y * wscale, v.z * wscale, v.w * wscale};
+          tc::store_split4(smem + lay.wf_hi[l], smem + lay.wf_lo[l], 64 * 16, j, kc, make_float4(vv[0], vv[1], vv[2], vv[3]));
+          float* thi = smem + lay.wt_hi[l];
+          float* tlo = smem + lay.wt_lo[l];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const float h = tc::tf32_hi(vv[r]);
+            const size_t off = (static_cast<size_t>(j >> 2) * kLboT + static_cast<size_t>(4 * kc + r) * 16 + (j & 3) * 4) / 4;
+            thi[off] = h;
+            tlo[off] = vv[r] - h;
+          }
+        }
+      }
+      tc::fence_proxy_async();
+    }
   }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
 
+  TLP(1, 1);
   const uint32_t d_tmem = tmem_base_s + static_cast<uint32_t>(grp * 64);
   const uint32_t d_lane = d_tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
   // A operand (activations forward, deltas backward) in tensor memory: hi plane [128 + 128 g, +64), lo plane +64
@@ -812,6 +877,7 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
       if constexpr (!RES) { if (l > 0) wcommit_transposed(b_hi, b_lo, wpre, t256, wscale); }
     }
   }
+  TLP(1, 2);
   // ---------------------------------------------------------------- loss partials per group
   {
     double vals[4] = {l_nll, l_abs, l_mse, l_cnt};
@@ -832,6 +898,7 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
     for (int wq = 0; wq < 4; ++wq) t += lred[g][wq][k];
     a.loss_partial[(static_cast<size_t>(blockIdx.x) * 2 + g) * 4 + k] = t;
   }
+  TLP(1, 3);
   if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
 }
 
@@ -848,6 +915,8 @@ grad_reduce2_kernel(const float* __restrict__ partial, const double* __restrict_
   __shared__ float consts[2];
   const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kRedCols + c;
+  griddep_launch();
+  griddep_wait();
   int64_t t0 = 0;
   if (fa.params != nullptr) {
     t0 = *fa.step_counter;
@@ -907,6 +976,7 @@ grad_reduce2_kernel(const float* __restrict__ partial, const double* __restrict_
 }
 
 static int g_tc_bwd_enabled = 1;
+static int g_tc_bwd_pdl = 1;      // programmatic dependent launch between K2a, K2b and the reduce (ablation switch below)
 
 struct TcBwdPlan { int grid_a, grid_b; size_t smem_a, smem_b, off_partial, off_scratch, bytes; };
 static TcBwdPlan plan_tc_bwd(int L, int64_t n) {
@@ -954,12 +1024,23 @@ int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropPa
   a.loss_partial = reinterpret_cast<double*>(ws);
   TcbLayout tl = make_tcb_layout(L);
   const bool inj = dp.p > 0.f && dp.masks != nullptr;
+  // Dependent launch pays where launch latency and prologues are a visible share of the step (N = 20 000: 69 -> 66 us,
+  // N = 5 000: 64 -> 57 us); with early-resident successors it costs 1 % at N = 100 000, 2 % at 200 000 and 3-7 % at 1M
+  // (profiles/ab_pdl.py), so only batches of up to two tiles per SM use it by default.
+  const bool pdl = g_tc_bwd_pdl == 2 || (g_tc_bwd_pdl == 1 && (n + kBTile - 1) / kBTile <= static_cast<int64_t>(2) * sm_count());
+  static bool carve_set[64] = {false};
+  int devi = 0;
+  if (cudaGetDevice(&devi) == cudaSuccess && devi >= 0 && devi < 64 && !carve_set[devi]) {
+    // keep the SMs in the max-shared-memory configuration across the three launches of a step
+    cudaFuncSetAttribute(grad_reduce2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    carve_set[devi] = true;
+  }
 #define LAUNCH_A(LL)                                                                                              \
   {                                                                                                               \
     auto kern = inj ? mlp_tc_bwd_kernel<LL, true> : mlp_tc_bwd_kernel<LL, false>;                                 \
     PINN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                         \
                                        static_cast<int>(p.smem_a)));                                              \
-    kern<<<p.grid_a, 512, p.smem_a, st>>>(*net, tl, dp, a);                                                       \
+    PINN_CUDA_TRY(launch_pdl(kern, dim3(p.grid_a), dim3(512), p.smem_a, st, pdl, *net, tl, dp, a));               \
   }
   switch (L) {
     case 2: LAUNCH_A(2) break;
@@ -978,7 +1059,8 @@ int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropPa
   {                                                                                                               \
     PINN_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                        static_cast<int>(p.smem_b)));                                              \
-    wgrad_tc_kernel<LL><<<p.grid_b, kWgLoaders + 32, p.smem_b, st>>>(w, lay, wl, a.rm);                           \
+    PINN_CUDA_TRY(launch_pdl(wgrad_tc_kernel<LL>, dim3(p.grid_b), dim3(kWgLoaders + 32), p.smem_b, st,           \
+                             pdl, w, lay, wl, a.rm));                                                             \
   }
   switch (L) {
     case 2: LAUNCH_B(2) break;
@@ -990,8 +1072,9 @@ int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropPa
   const int rg = static_cast<int>((lay.total + kRedCols - 1) / kRedCols);
   FusedAdam fa{};
   if (fused != nullptr) fa = *fused;
-  grad_reduce2_kernel<<<rg, kRedCols * kRedGroups, 0, st>>>(w.partial, a.loss_partial, p.grid_b, 2 * p.grid_a, lay.total, grad_flat,
-                                                          loss_sums, fa);
+  PINN_CUDA_TRY(launch_pdl(grad_reduce2_kernel, dim3(rg), dim3(kRedCols * kRedGroups), 0, st, pdl,
+                           static_cast<const float*>(w.partial), static_cast<const double*>(a.loss_partial), p.grid_b, 2 * p.grid_a,
+                           lay.total, grad_flat, loss_sums, fa));
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -1001,7 +1084,16 @@ int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropPa
 extern "C" int pinn_debug_timeline_wgrad(long long* host_out) {
   return static_cast<int>(cudaMemcpyFromSymbol(host_out, pinn::g_tlw, sizeof(pinn::g_tlw)));
 }
+extern "C" int pinn_debug_timeline_phases(long long* host_out) {
+  return static_cast<int>(cudaMemcpyFromSymbol(host_out, pinn::g_tlp, sizeof(pinn::g_tlp)));
+}
 #endif
+// Ablation switch: launch K2a / K2b / reduce with (1, default) or without programmatic stream serialization.
+extern "C" int pinn_set_dependent_launch(int enable) {
+  int prev = pinn::g_tc_bwd_pdl;
+  pinn::g_tc_bwd_pdl = enable < 0 ? 0 : (enable > 2 ? 2 : enable);      // 0 off, 1 small batches only (default), 2 always
+  return prev;
+}
 // Ablation / test switch for the tensor-core backward path (1 = on).
 extern "C" int pinn_set_tensor_core_bwd(int enable) {
   int prev = pinn::g_tc_bwd_enabled;

@@ -261,6 +261,11 @@ def set_tensor_core_bwd(enable: bool) -> bool:
     return bool(_abi.lib().pinn_set_tensor_core_bwd(1 if enable else 0))
 
 
+def set_dependent_launch(mode) -> int:
+    """Ablation switch: chain K2a / K2b / reduce with programmatic dependent launch -- 0 never, 1 small batches (default), 2 always."""
+    return int(_abi.lib().pinn_set_dependent_launch(int(mode)))
+
+
 def new_step_counter(device) -> torch.Tensor:
     return torch.zeros(2, device=device, dtype=torch.int64)
 

@@ -12,6 +12,8 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 x, y, sx, sy = make_scaled_dataset(n, seed=1)
 torch.manual_seed(0)
 m = b200pinn.PhysicsInformedNN(torch.tensor(x), torch.tensor(y), [8, 64, 64, 64, 1], sx, sy, 0.2, True)
+if os.environ.get("B200PINN_PDL", "1") == "0":
+    b200pinn.kernels.set_dependent_launch(0)
 m.train_dnn(5, verbose=False)
 torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -20,4 +22,4 @@ a.record()
 m.train_dnn(steps, verbose=False)
 b.record()
 torch.cuda.synchronize()
-print(f"n={n} steps={steps}: wall {1e6 * (time.perf_counter() - t0) / steps:.1f} us/step, device {1e3 * a.elapsed_time(b) / steps:.1f} us/step")
+print(f"n={n} steps={steps} pdl={os.environ.get('B200PINN_PDL', '1')}: wall {1e6 * (time.perf_counter() - t0) / steps:.1f} us/step, device {1e3 * a.elapsed_time(b) / steps:.1f} us/step")
