@@ -299,7 +299,7 @@ def run_ours(args):
     # train_dnn = K2a + K2b + (gradient reduce + Adam) per step; the scalar phases run as persistent launches
     # (pinn_scalar_phase: 1000 optimiser steps per launch, one grid barrier per step)
     c1 = None
-    if world == 1:
+    if world == 1 and not args.no_c1:
         n1 = 20_000
         torch.manual_seed(0)
         m1 = b200pinn.PhysicsInformedNN(X[:n1], Y[:n1], LAYERS, sx, sy, P_TRAIN, True)
@@ -428,6 +428,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=N_PER_GPU, help="samples per GPU (default: configs[1], 1M)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-c1", action="store_true", help="skip the configs[0]-size step timings (thousands of launches: for ncu runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
