@@ -133,7 +133,6 @@ wgrad_tc_kernel(WgradArgs a, ParamLayout lay, WgLayout wl, RowMap rm) {
   const int tid = threadIdx.x, warp = tc::uniform_warp_idx();
   const bool mma_warp = warp == kWgLoaders / 32;
   TLP(0, 0);
-  griddep_launch();
 
   if (tid == 0) {
     tc::mbar_init(&full[0], kWgLoaders); tc::mbar_init(&full[1], kWgLoaders);
@@ -311,6 +310,7 @@ wgrad_tc_kernel(WgradArgs a, ParamLayout lay, WgLayout wl, RowMap rm) {
     }
     tc::fence_after_sync();
     TLP(0, 2);
+    griddep_launch();        // late trigger: the reduce CTAs would otherwise sit resident (and waiting) through the whole streaming phase
     // ---------------------------------------------------------------- accumulators -> this CTA's partial
     float* part = a.partial + static_cast<size_t>(blockIdx.x) * lay.total;
     {
