@@ -259,6 +259,31 @@ int pinn_adam_step_p2p(float* params, const uint64_t* peer_buffers, int32_t rank
                        float* exp_avg_sq, int64_t n, int64_t* step_counter, double lr0,
                        double gamma, int64_t step_size, void* stream);
 
+/* f4 -- the Gaussian-mixture pass behind fit_gmm_and_get_probabilities
+ * (03_unsupervised_gmm_fault_diagnosis 03:360-426; sklearn GaussianMixture, covariance_type
+ * "full", float64).  X[n][d] row-major (d <= 8), n_components <= 32, n_classes <= 16; all
+ * pointers are device pointers.  weights[C], means[C][d], prec_chol[C][d][d] are sklearn's
+ * weights_, means_, precisions_cholesky_.  One pass computes the responsibilities
+ * resp = exp(log_prob - logsumexp) of sklearn's _estimate_log_prob_resp and, per request
+ * (NULL = not wanted):
+ *   resp[n][C]                    = gmm.predict_proba(X)                             03:392,415
+ *   stats[C][1 + d + d(d+1)/2]    = sum resp, sum resp (x - mu_c), upper triangle of
+ *                                   sum resp (x - mu_c)(x - mu_c)^T: the sufficient
+ *                                   statistics of one EM iteration of gmm.fit       03:386-389
+ *   comp_class_weight[C][K]       = sum_i resp[i][c] [labels[i] == k]  (needs labels;
+ *                                   labels outside [0, K) are skipped)              03:394-405
+ *   y_prob[n][K], y_pred[n]       = clip(resp @ comp_class_prob, 1e-12, 1) row-normalised
+ *                                   and its first arg-max (needs comp_class_prob[C][K]) 03:415-423
+ *   log_prob_norm_sum[1]          = sum_i logsumexp_c(...)  (n * gmm.score(X))
+ * Reductions are fixed-order (deterministic).  workspace >= pinn_gmm_workspace_bytes(). */
+size_t pinn_gmm_workspace_bytes(int32_t d, int32_t n_components, int32_t n_classes);
+int pinn_gmm_pass(const double* X, int64_t n, int32_t d, int32_t n_components,
+                  const double* weights, const double* means, const double* prec_chol,
+                  const int32_t* labels, int32_t n_classes, const double* comp_class_prob,
+                  double* resp, double* y_prob, int32_t* y_pred, double* stats,
+                  double* comp_class_weight, double* log_prob_norm_sum, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
 /* Ablation / test switch.  The 64-wide net's forward and MC-dropout kernels run their
  * 64x64 contractions on tcgen05 tensor cores (3xTF32, fp32-accurate); 0 routes them through
  * the fp32 FFMA kernels that serve the other widths.  Returns the previous setting. */

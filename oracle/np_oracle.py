@@ -479,3 +479,62 @@ def first_alarm(series, threshold):
     """``find_first_alarm_index`` (04:289-300), mode 'above'; -1 when never reached."""
     idx = np.where(np.asarray(series) >= threshold)[0]
     return int(idx[0]) if len(idx) else -1
+
+
+# ------------------------------------------------------------------ GMM diagnosis (03:360-426)
+# sklearn.mixture.GaussianMixture (covariance_type="full") is a third-party dependency of the
+# reference (version unpinned by it; the container's sklearn 1.9.0 is what the goldens were made
+# with).  The functions below restate its published E-step / M-step arithmetic
+# (_estimate_log_gaussian_prob, _estimate_log_prob_resp, _estimate_gaussian_parameters) and the
+# reference's own label calibration and class-probability mapping.
+def gmm_resp(X, weights, means, prec_chol):
+    """``(log_prob_norm[n], resp[n, C])`` of sklearn's ``_estimate_log_prob_resp`` (float64)."""
+    X = np.asarray(X, np.float64)
+    n, d = X.shape
+    C = means.shape[0]
+    log_prob = np.empty((n, C))
+    for c in range(C):
+        y = (X - means[c]) @ prec_chol[c]
+        log_det = np.sum(np.log(np.diag(prec_chol[c])))
+        log_prob[:, c] = -0.5 * (d * np.log(2.0 * np.pi) + np.sum(y * y, axis=1)) + log_det
+    wlp = log_prob + np.log(weights)
+    mx = wlp.max(axis=1, keepdims=True)
+    lpn = mx[:, 0] + np.log(np.exp(wlp - mx).sum(axis=1))
+    return lpn, np.exp(wlp - lpn[:, None])
+
+
+def gmm_m_step(X, resp, reg_covar=1e-6):
+    """``(weights, means, covariances)`` of ``_estimate_gaussian_parameters`` + the weight normalisation of ``_m_step``."""
+    X = np.asarray(X, np.float64)
+    nk = resp.sum(axis=0) + 10 * np.finfo(np.float64).eps
+    means = resp.T @ X / nk[:, None]
+    C, d = means.shape
+    cov = np.empty((C, d, d))
+    for c in range(C):
+        diff = X - means[c]
+        cov[c] = (resp[:, c] * diff.T) @ diff / nk[c]
+        cov[c].flat[:: d + 1] += reg_covar
+    return nk / nk.sum(), means, cov
+
+
+def gmm_calibrate(resp_tr, y_tr, n_classes):
+    """P(fault | component) from responsibilities and labels, 03:394-412."""
+    C = resp_tr.shape[1]
+    P = np.zeros((C, n_classes))
+    for c in range(C):
+        w = resp_tr[:, c]
+        if w.sum() <= 0:
+            P[c] = 1.0 / n_classes
+            continue
+        for k in range(n_classes):
+            P[c, k] = w[y_tr == k].sum()
+        s = P[c].sum()
+        P[c] = P[c] / s if s > 0 else 1.0 / n_classes
+    return P
+
+
+def gmm_class_prob(resp_te, comp_fault_prob):
+    """``(y_prob, y_pred)`` of 03:415-423."""
+    y = np.clip(resp_te @ comp_fault_prob, 1e-12, 1.0)
+    y /= y.sum(axis=1, keepdims=True)
+    return y, y.argmax(axis=1)

@@ -9,6 +9,8 @@ from .pinn import PhysicsInformedNN, LAMBDA_NAMES  # noqa: F401
 from .mc import get_MC_samples, mc_dropout_device  # noqa: F401
 from .export import create_comprehensive_results_array_v2, create_fault_labels, export_rows_device  # noqa: F401
 from . import rf  # noqa: F401
+from . import gmm  # noqa: F401
+from .gmm import fit_gmm_and_get_probabilities  # noqa: F401
 from .dropin import install  # noqa: F401
 
 __all__ = ["DNN", "PhysicsInformedNN", "get_MC_samples", "mc_dropout_device", "inject_masks", "install",

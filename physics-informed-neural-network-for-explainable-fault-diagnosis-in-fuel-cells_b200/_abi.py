@@ -94,6 +94,8 @@ _SIGNATURES = {
     "pinn_rf_workspace_bytes": (_sz, [_i64, _i32]),
     "pinn_rf_stats": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _sz, _vp]),
     "pinn_rf_series": (C.c_int, [_vp, _i64, _i32, _vp, C.POINTER(PinnRfParams), _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pinn_gmm_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "pinn_gmm_pass": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pinn_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _dbl, _dbl, _i64, _dbl, _vp, _vp, _vp,
                                  _i32, _vp]),
     "pinn_scalar_phase_workspace_bytes": (_sz, []),
