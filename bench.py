@@ -281,7 +281,20 @@ def run_ours(args):
     rfk = lambda: rf_device(fleet)
     t_rf, _ = timed(rfk, max(3, K_ // 2), 2)
     n_exp = max(3, K_ // 2)
-    del fleet, rows
+    # GMM diagnosis (03:360-426) over the same 8 stacks: one EM iteration = one float64 pass over 8 x n rows x 4 features
+    # (the residual-score columns pV, pT, pH, pO) with 20 components
+    from b200pinn import gmm as G
+    import numpy as np
+    rng = np.random.default_rng(0)
+    feats = fleet[:, :, 13:17].reshape(-1, 4).contiguous()                 # the four residual columns of the export rows
+    mu0 = feats[:: max(1, feats.shape[0] // 20)][:20].clone()
+    sd = feats.std(dim=0).clamp_min(1e-6).cpu().numpy()
+    gw = np.ones(20) / 20
+    gpc = np.stack([np.diag(1.0 / sd)] * 20)
+    gmm_it = lambda: G.gmm_pass(feats, gw, mu0, gpc, want_stats=True)
+    t_gmm, _ = timed(gmm_it, n_exp, 2, do_flush=False)
+    n_gmm = feats.shape[0]
+    del fleet, rows, feats
     # --- wide nets (the reference's own Layers = [8,256,256,256,1], 01:2139; config 4 is 6x256): MC sweep on the per-layer
     # tcgen05 GEMM path (mlp_wide_tc.cu): MC sweep and train step, N = 262144
     wide = {}
@@ -416,7 +429,10 @@ def run_ours(args):
                              "(mu/sigma, dead-zone norms, C(t) scan, logistic, EMA, first alarm)",
                      "export_rows_per_s": world * n * n_exp / t_export, "export_ms_per_stack": 1e3 * t_export / n_exp,
                      "rf_rows_per_s": world * 8 * n * n_exp / t_rf, "rf_ms_per_8_stacks": 1e3 * t_rf / n_exp,
-                     "rf_hbm_gbs": 8 * n * (22 * 8 + 2 * 8) * n_exp / t_rf / 1e9}
+                     "rf_hbm_gbs": 8 * n * (22 * 8 + 2 * 8) * n_exp / t_rf / 1e9,
+                     "gmm_em_iteration_ms": 1e3 * t_gmm / n_exp, "gmm_rows_per_s": world * n_gmm * n_exp / t_gmm,
+                     "gmm_what": "one EM iteration (E-step + M-step statistics, float64) of a 20-component full-covariance "
+                                 "GaussianMixture over the 4 residual-score columns of 8 stacks (03:360-426)"}
     line["wide"] = wide
     if c1 is not None:
         line["c1"] = c1
