@@ -20,12 +20,11 @@
 
 namespace pinn {
 
-constexpr int kGmmThreads = 256;
+constexpr int kGmmThreads = 512;     // 16 warps per SM: the pass is a chain of fp64 latencies, occupancy is what hides them
 constexpr int kGmmWarps = kGmmThreads / 32;
 constexpr int kGmmMaxC = 32;      // components (a lane each in stage 2)
 constexpr int kGmmMaxK = 16;      // fault classes
 constexpr int kGmmMaxD = 8;
-constexpr int kGmmRespStride = kGmmMaxC + 1;     // doubles per row of the responsibility tile (odd: no bank conflicts)
 
 PINN_HD constexpr int gmm_nstat(int d) { return 1 + d + d * (d + 1) / 2; }
 
@@ -40,57 +39,65 @@ struct GmmArgs {
   int want_stats, want_cal;
 };
 
-// shared-memory map (doubles): params, per-warp tiles, CTA accumulators
-template <int D>
+// shared-memory map (offsets in doubles), sized for the actual component / class counts so that 16 warps fit
 struct GmmSmem {
-  static constexpr int NS = gmm_nstat(D);
-  static constexpr int kMeans = 0;                                   // [C][D]
-  static constexpr int kChol = kMeans + kGmmMaxC * D;                // [C][D][D]
-  static constexpr int kConst = kChol + kGmmMaxC * D * D;            // [C]  log w + log det - 0.5 d log 2pi
-  static constexpr int kP = kConst + kGmmMaxC;                       // [C][K]
-  static constexpr int kResp = kP + kGmmMaxC * kGmmMaxK;             // [warps][32][stride]
-  static constexpr int kX = kResp + kGmmWarps * 32 * kGmmRespStride; // [warps][32][D]
-  static constexpr int kCal = kX + kGmmWarps * 32 * D;               // [warps][C][K]
-  static constexpr int kAcc = kCal + kGmmWarps * kGmmMaxC * kGmmMaxK;   // [C][NS] + [C][K] + 1 : CTA accumulators
-  static constexpr int kLab = kAcc + kGmmMaxC * NS + kGmmMaxC * kGmmMaxK + 2;   // int32 [warps][32] (as doubles: half used)
-  static constexpr int kTotal = kLab + kGmmWarps * 32 / 2;
+  int rs;                 // doubles per row of a warp's responsibility tile: C rounded up to odd (no bank conflicts)
+  int kMeans, kChol, kConst, kP, kResp, kX, kCal, kAcc, kLab, total;
 };
+PINN_HD GmmSmem gmm_smem(int D, int C, int K, int nwarps) {
+  GmmSmem m;
+  const int NS = gmm_nstat(D), Kp = K > 0 ? K : 1;
+  m.rs = C | 1;
+  m.kMeans = 0;                                   // [C][D]
+  m.kChol = m.kMeans + C * D;                     // [C][D][D]
+  m.kConst = m.kChol + C * D * D;                 // [C]  log w + log det - 0.5 d log 2pi
+  m.kP = m.kConst + C;                            // [C][K]
+  m.kResp = m.kP + C * Kp;                        // [warps][32][rs]
+  m.kX = m.kResp + nwarps * 32 * m.rs;         // [warps][32][D]
+  m.kCal = m.kX + nwarps * 32 * D;             // [warps][C][K]
+  m.kAcc = m.kCal + nwarps * C * Kp;           // [C][NS] + [C][K] + 1 : CTA accumulators
+  m.kLab = (m.kAcc + C * NS + C * Kp + 2) & ~1;   // int32 [warps][32]
+  m.total = m.kLab + nwarps * 32 / 2;
+  return m;
+}
 
 template <int D>
 __global__ void __launch_bounds__(kGmmThreads, 1) gmm_pass_kernel(const GmmArgs a) {
-  using S = GmmSmem<D>;
-  constexpr int NS = S::NS;
+  constexpr int NS = gmm_nstat(D);
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int C = a.C, K = a.K;
+  const int C = a.C, K = a.K, Kp = K > 0 ? K : 1;
+  const int nthreads = blockDim.x, nwarps = nthreads >> 5;       // 512 threads, or 256 when the tiles of 16 warps do not fit
+  const GmmSmem S = gmm_smem(D, C, K, nwarps);
+  const int RS = S.rs;
   // ---- parameters -> shared memory
-  for (int i = tid; i < C * D; i += kGmmThreads) sm[S::kMeans + i] = a.means[i];
-  for (int i = tid; i < C * D * D; i += kGmmThreads) sm[S::kChol + i] = a.prec_chol[i];
-  for (int c = tid; c < C; c += kGmmThreads) {
+  for (int i = tid; i < C * D; i += nthreads) sm[S.kMeans + i] = a.means[i];
+  for (int i = tid; i < C * D * D; i += nthreads) sm[S.kChol + i] = a.prec_chol[i];
+  for (int c = tid; c < C; c += nthreads) {
     double ld = 0.0;
     for (int j = 0; j < D; ++j) ld += log(a.prec_chol[(static_cast<size_t>(c) * D + j) * D + j]);
-    sm[S::kConst + c] = log(a.weights[c]) + ld - 0.5 * D * 1.8378770664093453;     // log(2 pi)
+    sm[S.kConst + c] = log(a.weights[c]) + ld - 0.5 * D * 1.8378770664093453;     // log(2 pi)
   }
   if (a.comp_class_prob != nullptr)
-    for (int i = tid; i < C * K; i += kGmmThreads) sm[S::kP + (i / K) * kGmmMaxK + (i % K)] = a.comp_class_prob[i];
-  for (int i = tid; i < kGmmWarps * kGmmMaxC * kGmmMaxK; i += kGmmThreads) sm[S::kCal + i] = 0.0;
+    for (int i = tid; i < C * K; i += nthreads) sm[S.kP + i] = a.comp_class_prob[i];
+  for (int i = tid; i < nwarps * C * Kp; i += nthreads) sm[S.kCal + i] = 0.0;
   __syncthreads();
 
-  double* resp_w = sm + S::kResp + warp * 32 * kGmmRespStride;
-  double* x_w = sm + S::kX + warp * 32 * D;
-  double* cal_w = sm + S::kCal + warp * kGmmMaxC * kGmmMaxK;
-  int32_t* lab_w = reinterpret_cast<int32_t*>(sm + S::kLab) + warp * 32;
+  double* resp_w = sm + S.kResp + warp * 32 * RS;
+  double* x_w = sm + S.kX + warp * 32 * D;
+  double* cal_w = sm + S.kCal + warp * C * Kp;
+  int32_t* lab_w = reinterpret_cast<int32_t*>(sm + S.kLab) + warp * 32;
 
   // stage-2 state of lane c: its component's mean and running statistics
   double mu[D], st[NS];
 #pragma unroll
-  for (int i = 0; i < D; ++i) mu[i] = lane < C ? sm[S::kMeans + lane * D + i] : 0.0;
+  for (int i = 0; i < D; ++i) mu[i] = lane < C ? sm[S.kMeans + lane * D + i] : 0.0;
 #pragma unroll
   for (int i = 0; i < NS; ++i) st[i] = 0.0;
   double lpn = 0.0;
 
   const int64_t n_batches = (a.n + 31) / 32;
-  for (int64_t b = static_cast<int64_t>(blockIdx.x) * kGmmWarps + warp; b < n_batches; b += static_cast<int64_t>(gridDim.x) * kGmmWarps) {
+  for (int64_t b = static_cast<int64_t>(blockIdx.x) * nwarps + warp; b < n_batches; b += static_cast<int64_t>(gridDim.x) * nwarps) {
     const int64_t row = b * 32 + lane;
     const bool valid = row < a.n;
     // ---------------------------------------------------------------- stage 1: lane = row
@@ -102,8 +109,8 @@ __global__ void __launch_bounds__(kGmmThreads, 1) gmm_pass_kernel(const GmmArgs 
     if (a.labels != nullptr) lab_w[lane] = valid ? __ldg(a.labels + row) : -1;
     double mx = -1.0e300;
     for (int c = 0; c < C; ++c) {
-      const double* m = sm + S::kMeans + c * D;
-      const double* P = sm + S::kChol + c * D * D;
+      const double* m = sm + S.kMeans + c * D;
+      const double* P = sm + S.kChol + c * D * D;
       double dx[D];
 #pragma unroll
       for (int i = 0; i < D; ++i) dx[i] = x[i] - m[i];
@@ -115,18 +122,18 @@ __global__ void __launch_bounds__(kGmmThreads, 1) gmm_pass_kernel(const GmmArgs 
         for (int i = 0; i < D; ++i) y = fma(dx[i], P[i * D + j], y);
         q = fma(y, y, q);
       }
-      const double lp = sm[S::kConst + c] - 0.5 * q;
-      resp_w[lane * kGmmRespStride + c] = lp;
+      const double lp = sm[S.kConst + c] - 0.5 * q;
+      resp_w[lane * RS + c] = lp;
       mx = fmax(mx, lp);
     }
     double se = 0.0;
     for (int c = 0; c < C; ++c) {
-      const double e = exp(resp_w[lane * kGmmRespStride + c] - mx);
-      resp_w[lane * kGmmRespStride + c] = e;
+      const double e = exp(resp_w[lane * RS + c] - mx);
+      resp_w[lane * RS + c] = e;
       se += e;
     }
     const double inv = 1.0 / se;
-    for (int c = 0; c < C; ++c) resp_w[lane * kGmmRespStride + c] *= inv;
+    for (int c = 0; c < C; ++c) resp_w[lane * RS + c] *= inv;
     if (valid) lpn += mx + log(se);
     __syncwarp();
     // ---------------------------------------------------------------- stage 2: lane = component
@@ -134,11 +141,11 @@ __global__ void __launch_bounds__(kGmmThreads, 1) gmm_pass_kernel(const GmmArgs 
     if (lane < C) {
       if (a.want_stats || a.want_cal || a.resp != nullptr) {
         for (int r = 0; r < rows_here; ++r) {
-          const double w = resp_w[r * kGmmRespStride + lane];
+          const double w = resp_w[r * RS + lane];
           if (a.resp != nullptr) a.resp[(b * 32 + r) * C + lane] = w;
           if (a.want_cal) {
             const int lab = lab_w[r];
-            if (lab >= 0 && lab < K) cal_w[lane * kGmmMaxK + lab] += w;
+            if (lab >= 0 && lab < K) cal_w[lane * Kp + lab] += w;
           }
           if (a.want_stats) {
             double dx[D];
@@ -163,8 +170,8 @@ __global__ void __launch_bounds__(kGmmThreads, 1) gmm_pass_kernel(const GmmArgs 
 #pragma unroll
       for (int k = 0; k < kGmmMaxK; ++k) yk[k] = 0.0;
       for (int c = 0; c < C; ++c) {
-        const double w = resp_w[lane * kGmmRespStride + c];
-        const double* Pc = sm + S::kP + c * kGmmMaxK;
+        const double w = resp_w[lane * RS + c];
+        const double* Pc = sm + S.kP + c * Kp;
 #pragma unroll
         for (int k = 0; k < kGmmMaxK; ++k)
           if (k < K) yk[k] = fma(w, Pc[k], yk[k]);
@@ -188,25 +195,25 @@ __global__ void __launch_bounds__(kGmmThreads, 1) gmm_pass_kernel(const GmmArgs 
   }
 
   // ---- CTA reduction, fixed order: warps add their registers / tiles into the CTA accumulators one after another
-  double* acc = sm + S::kAcc;
+  double* acc = sm + S.kAcc;
   const int n_acc = C * NS + C * K + 1;
-  for (int i = tid; i < n_acc; i += kGmmThreads) acc[i] = 0.0;
+  for (int i = tid; i < n_acc; i += nthreads) acc[i] = 0.0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) lpn += __shfl_xor_sync(0xffffffffu, lpn, o);
   __syncthreads();
-  for (int w = 0; w < kGmmWarps; ++w) {
+  for (int w = 0; w < nwarps; ++w) {
     if (warp == w) {
       if (lane < C) {
 #pragma unroll
         for (int s = 0; s < NS; ++s) acc[lane * NS + s] += st[s];
-        for (int k = 0; k < K; ++k) acc[C * NS + lane * K + k] += cal_w[lane * kGmmMaxK + k];
+        for (int k = 0; k < K; ++k) acc[C * NS + lane * K + k] += cal_w[lane * Kp + k];
       }
       if (lane == 0) acc[C * NS + C * K] += lpn;
     }
     __syncthreads();
   }
   double* part = a.partials + static_cast<size_t>(blockIdx.x) * n_acc;
-  for (int i = tid; i < n_acc; i += kGmmThreads) part[i] = acc[i];
+  for (int i = tid; i < n_acc; i += nthreads) part[i] = acc[i];
 }
 
 // CTA partials -> totals, fixed order: a CTA owns 32 entries, its 8 warps add every 8th partial, folded in warp order.
@@ -230,19 +237,24 @@ __global__ void __launch_bounds__(256) gmm_reduce_kernel(const double* __restric
   }
 }
 
-static int gmm_grid(int64_t n) {
-  const int64_t want = (n + 32 * kGmmWarps - 1) / (32 * kGmmWarps);
+static int gmm_grid(int64_t n, int nwarps) {
+  const int64_t want = (n + 32 * nwarps - 1) / (32 * nwarps);
   const int64_t cap = sm_count();
   return static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
 template <int D>
 static int launch_gmm(GmmArgs& a, double* stats, double* cal, double* lpn, cudaStream_t st) {
-  using S = GmmSmem<D>;
-  const size_t smem = static_cast<size_t>(S::kTotal) * sizeof(double);
+  int threads = kGmmThreads;
+  size_t smem = static_cast<size_t>(gmm_smem(D, a.C, a.K, threads / 32).total) * sizeof(double);
+  if (smem > 227 * 1024) {      // the largest d / component / class counts: eight warps per CTA
+    threads = 256;
+    smem = static_cast<size_t>(gmm_smem(D, a.C, a.K, threads / 32).total) * sizeof(double);
+  }
+  if (smem > 227 * 1024) return PINN_E_SHAPE;
   PINN_CUDA_TRY(cudaFuncSetAttribute(gmm_pass_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  const int grid = gmm_grid(a.n);
-  gmm_pass_kernel<D><<<grid, kGmmThreads, smem, st>>>(a);
+  const int grid = gmm_grid(a.n, threads / 32);
+  gmm_pass_kernel<D><<<grid, threads, smem, st>>>(a);
   PINN_CUDA_TRY(cudaGetLastError());
   const int NS = gmm_nstat(D), n_acc = a.C * NS + a.C * a.K + 1;
   gmm_reduce_kernel<<<(n_acc + 31) / 32, 256, 0, st>>>(a.partials, grid, n_acc, a.C, NS, a.K, stats, cal, lpn);

@@ -72,7 +72,7 @@ def test_drop_in_function_matches_reference_outputs(g):
     assert np.abs(P - g["comp_fault_prob"]).max() < 1e-5
 
 
-@pytest.mark.parametrize("n,d,C,K", [(1, 4, 3, 2), (33, 2, 32, 16), (1000, 8, 5, 3), (4097, 1, 2, 1), (70000, 4, 20, 13)])
+@pytest.mark.parametrize("n,d,C,K", [(1, 4, 3, 2), (33, 2, 32, 16), (1000, 8, 5, 3), (4097, 1, 2, 1), (70000, 4, 20, 13), (600, 8, 32, 16)])
 def test_pass_vs_oracle_shapes_and_edges(n, d, C, K):
     """Ragged row counts, the extreme d / components / classes, labels outside [0, K) skipped, every output at once."""
     from b200pinn import gmm
