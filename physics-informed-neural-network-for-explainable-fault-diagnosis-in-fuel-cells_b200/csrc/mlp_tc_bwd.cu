@@ -663,7 +663,13 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
     return bits;
   };
   const int64_t n_tiles = (a.n + kBTile - 1) / kBTile;
+  // tile -> (CTA, group): group 0 of every CTA first, then group 1 -- with no more tiles than SMs every tile gets an SM
+  // to itself (a lone tile is faster than an interleaved pair; only throughput, not latency, gains from pairing)
+#ifdef PINN_K2A_PAIR_FIRST     // A/B build: the former mapping (tiles 2b, 2b+1 on CTA b)
   for (int64_t tile = static_cast<int64_t>(blockIdx.x) * 2 + grp; tile < n_tiles; tile += static_cast<int64_t>(gridDim.x) * 2) {
+#else
+  for (int64_t tile = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(grp) * gridDim.x; tile < n_tiles; tile += static_cast<int64_t>(gridDim.x) * 2) {
+#endif
     const int64_t s = tile * kBTile + row;
     const bool valid = s < a.n;
     // this sample's column of the tile's row table: slab (row / 16) of the tile, position row % 16 inside each 16-sample row
@@ -984,8 +990,12 @@ static TcBwdPlan plan_tc_bwd(int L, int64_t n) {
   ParamLayout lay = make_layout(kBH, L);
   const int sms = sm_count();
   const int64_t tiles = (n + kBTile - 1) / kBTile;
+#ifdef PINN_K2A_PAIR_FIRST
   int64_t want = (tiles + 1) / 2;
   p.grid_a = static_cast<int>(want < sms ? (want > 0 ? want : 1) : sms);
+#else
+  p.grid_a = static_cast<int>(tiles < sms ? (tiles > 0 ? tiles : 1) : sms);
+#endif
   const int64_t want_b = (tiles * (kBTile / kWgStage) + 3) / 4;       // K2b splits by 16-sample stages: at least four per CTA
   p.grid_b = static_cast<int>(want_b < sms ? (want_b > 0 ? want_b : 1) : sms);
   p.smem_a = static_cast<size_t>(make_tcb_layout(L).total) * sizeof(float);
