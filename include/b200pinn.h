@@ -290,10 +290,11 @@ int pinn_gmm_pass(const double* X, int64_t n, int32_t d, int32_t n_components,
 int pinn_set_tensor_core_path(int enable);
 /* Same switch for the backward kernels (pinn_mlp_bwd). */
 int pinn_set_tensor_core_bwd(int enable);
-/* Ablation switch: the tensor-core backward's three launches (forward+dgrad, weight
- * gradients, reduce[+Adam]) are chained with programmatic dependent launch so that each
- * kernel's launch and prologue overlap its predecessor's tail.  1 (default): for batches
- * up to 2 tiles per SM, where launch latency is a visible share of the step; 2: always;
+/* Ablation switch: the launches of one training step / forward / MC pass on the tensor-core
+ * paths (64-wide: forward+dgrad, weight gradients, reduce[+Adam]; 128/256-wide: the per-layer
+ * GEMM launches) are chained with programmatic dependent launch so that each kernel's launch
+ * (and, on the 64-wide path, its prologue) overlaps its predecessor's tail.  1 (default): for
+ * batches up to 2 tiles per SM, where launch latency is a visible share of the step; 2: always;
  * 0: never.  Results are identical.  Returns the previous setting. */
 int pinn_set_dependent_launch(int enable);
 /* Same switch for the 128- / 256-wide nets' forward and MC-dropout sweep (one tcgen05 GEMM launch

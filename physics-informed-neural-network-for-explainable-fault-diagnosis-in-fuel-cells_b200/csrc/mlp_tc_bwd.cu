@@ -1010,6 +1010,7 @@ static TcBwdPlan plan_tc_bwd(int L, int64_t n) {
   return p;
 }
 
+int dependent_launch_mode() { return g_tc_bwd_pdl; }
 bool tc_bwd_covers(const pinn_net_t* net) {
   if (!g_tc_bwd_enabled || net->width != kBH || net->n_hidden < 2 || net->n_hidden > 4) return false;
   for (int l = 0; l < net->n_hidden; ++l)

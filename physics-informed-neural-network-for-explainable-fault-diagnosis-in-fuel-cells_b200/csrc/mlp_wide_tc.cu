@@ -148,6 +148,8 @@ PINN_D void wide_load8(const unsigned char* tile_planes, int c0, int r, float (&
 }
 // constant rows of a B-side transposed buffer: row `data_rows` = 1 (the bias column of the wgrad product), the rest 0
 __global__ void wide_fill_ones_kernel(unsigned char* buf, int rows, int data_rows, int64_t chunks) {
+  griddep_launch();
+  griddep_wait();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int per = 4 * (rows - data_rows);
   if (i >= chunks * per) return;
@@ -162,6 +164,8 @@ __global__ void wide_fill_ones_kernel(unsigned char* buf, int rows, int data_row
 // transposed weight planes for dgrad: B[n = k][K index = j] = W[j][k] (j < rows_a), = w_b[k] (j == rows_a), 0 beyond; times c
 __global__ void wide_split_weights_T_kernel(const float* __restrict__ src_a, int rows_a, const float* __restrict__ src_b, int N, int K,
                                             float c, unsigned char* __restrict__ dst) {
+  griddep_launch();
+  griddep_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;          // (n, j4): output row n, 4 consecutive K indices
   if (idx >= N * (K / 4)) return;
   const int nrow = idx % N, j4 = idx / N;
@@ -185,6 +189,8 @@ __global__ void wide_split_weights_T_kernel(const float* __restrict__ src_a, int
 // `src_b` (or zero) and the rest are zero; every element multiplied by `c`.
 __global__ void wide_split_weights_kernel(const float* __restrict__ src_a, int rows_a, const float* __restrict__ src_b, int N, int K,
                                           float c, unsigned char* __restrict__ dst) {
+  griddep_launch();
+  griddep_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;          // (row, k4)
   if (idx >= N * (K / 4)) return;
   const int nrow = idx % N, k4 = idx / N;
@@ -203,6 +209,8 @@ template <int H>
 __global__ void __launch_bounds__(256)
 wide_layer0_kernel(const float* __restrict__ x, const float* __restrict__ W0, const float* __restrict__ b0,
                    const __grid_constant__ DropParams dp, WideArgs a) {
+  griddep_launch();
+  griddep_wait();
   __shared__ float sW[H * PINN_N_IN];
   __shared__ float sb[H];
   __shared__ __align__(16) float tpatch[8][kTPatch];
@@ -268,6 +276,8 @@ wide_layer0_kernel(const float* __restrict__ x, const float* __restrict__ W0, co
 template <int N, int EPI>
 __global__ void __launch_bounds__(320, N > 256 ? 1 : 2)
 wide_gemm_kernel(const __grid_constant__ DropParams dp, WideArgs a) {
+  griddep_launch();
+  griddep_wait();
   // A pipeline stage is HALF a plane chunk (8 of its 16 k: the first or second pair of 4-wide sub-chunks of the hi and
   // of the lo plane): four bulk copies, three MMAs.  Twice as many, half as large stages as chunk-sized ones keep more
   // loads in flight per CTA in the same shared memory (TMA latency ~2000 clk vs 384 clk of MMA work per stage).
@@ -564,6 +574,8 @@ wide_gemm_kernel(const __grid_constant__ DropParams dp, WideArgs a) {
 // optionally dstB[j] = sum of column bias_col.  Fixed summation order: deterministic.
 __global__ void wide_wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int nmb, int N, int mb, int row0, int nrows,
                                          int ncols, int bias_col, float* __restrict__ dstW, int ld, float* __restrict__ dstB, float scale) {
+  griddep_launch();
+  griddep_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int per = ncols + (dstB != nullptr ? 1 : 0);
   if (idx >= nrows * per) return;
@@ -589,6 +601,8 @@ __global__ void wide_wgrad_reduce_kernel(const float* __restrict__ partial, int 
 __global__ void __launch_bounds__(256)
 wide_tail_reduce_kernel(const float* __restrict__ tail_partial, const double* __restrict__ loss_partial, int tiles, int n1,
                         float* __restrict__ dWv2, float* __restrict__ dbv2, double* __restrict__ loss) {
+  griddep_launch();
+  griddep_wait();
   __shared__ double sh[256];
   const int k = blockIdx.x, t0 = threadIdx.x;
   double acc = 0.0;
@@ -613,6 +627,13 @@ wide_tail_reduce_kernel(const float* __restrict__ tail_partial, const double* __
 
 // ------------------------------------------------------------------ host side
 static int g_wide_tc_enabled = 1;
+// Programmatic dependent launch for the per-layer launches of a small batch (every kernel of this file starts with
+// griddep_launch + griddep_wait: stream order is kept, only the launch latency and CTA scheduling of the successor overlap
+// the predecessor's tail).  Same size rule and switch as the 64-wide training step (pinn_set_dependent_launch).
+static bool wide_pdl(int64_t n) {
+  const int mode = dependent_launch_mode();
+  return mode == 2 || (mode == 1 && (n + kWT - 1) / kWT <= static_cast<int64_t>(2) * sm_count());
+}
 
 template <int H>
 struct WidePlan {
@@ -650,6 +671,7 @@ static int run_wide(bool mc, const pinn_net_t* net, const float* x, int64_t n, i
   const int L = net->n_hidden;
   const WidePlan<H> p = wide_plan<H>(L, n);
   if (!workspace || workspace_bytes < p.bytes) return PINN_E_WORKSPACE;
+  const bool pdl = wide_pdl(n);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   const int tiles = static_cast<int>((n + kWT - 1) / kWT);
   const bool drop_on = dp.p > 0.f;
@@ -657,7 +679,7 @@ static int run_wide(bool mc, const pinn_net_t* net, const float* x, int64_t n, i
   // ---- weight planes
   auto split = [&](const float* sa, int rows_a, const float* sb, int N, int K, float c, unsigned char* dst) {
     const int items = N * (K / 4);
-    wide_split_weights_kernel<<<(items + 255) / 256, 256, 0, st>>>(sa, rows_a, sb, N, K, c, dst);
+    launch_pdl(wide_split_weights_kernel, dim3((items + 255) / 256), dim3(256), 0, st, pdl, sa, rows_a, sb, N, K, c, dst);
   };
   for (int l = 1; l < L; ++l) split(net->W[l], H, nullptr, H, H, wscale, ws + p.off_w[l]);
   split(net->Wv0, H / 2, net->Wp, NH, H, wscale, ws + p.off_wh);
@@ -696,19 +718,19 @@ static int run_wide(bool mc, const pinn_net_t* net, const float* x, int64_t n, i
     unsigned char* nxt = ws + p.off_p1;
     // layer 0
     a.layer = 0; a.unit_base = 0; a.out = cur;
-    wide_layer0_kernel<H><<<tiles, 256, 0, st>>>(x, net->W[0], net->b[0], dp, a);
+    launch_pdl(wide_layer0_kernel<H>, dim3(tiles), dim3(256), 0, st, pdl, x, net->W[0], net->b[0], dp, a);
     for (int l = 1; l < L; ++l) {
       a.A = cur; a.W = ws + p.off_w[l]; a.out = nxt; a.bias = net->b[l];
       a.layer = static_cast<uint32_t>(l); a.unit_base = static_cast<uint32_t>(l * H); a.nch = H / kWKc;
-      k_hidden<<<tiles, 320, sm_hidden, st>>>(dp, a);
+      launch_pdl(k_hidden, dim3(tiles), dim3(320), sm_hidden, st, pdl, dp, a);
       unsigned char* t = cur; cur = nxt; nxt = t;
     }
     a.A = cur; a.W = ws + p.off_wh; a.out = ws + p.off_pv; a.bias = net->bv0; a.bias2 = net->bp;
     a.layer = static_cast<uint32_t>(L); a.unit_base = static_cast<uint32_t>(L * H); a.nch = H / kWKc;
-    k_heads<<<tiles, 320, sm_heads, st>>>(dp, a);
+    launch_pdl(k_heads, dim3(tiles), dim3(320), sm_heads, st, pdl, dp, a);
     a.A = ws + p.off_pv; a.W = ws + p.off_wv1; a.out = nullptr; a.bias = net->bv1; a.bias2 = net->bv2; a.w2 = net->Wv2;
     a.active = 0; a.nch = (H / 2) / kWKc;
-    k_v1<<<tiles, 320, sm_v1, st>>>(dp, a);
+    launch_pdl(k_v1, dim3(tiles), dim3(320), sm_v1, st, pdl, dp, a);
   }
   return static_cast<int>(cudaGetLastError());
 }
@@ -796,6 +818,7 @@ static int run_wide_bwd(const pinn_net_t* net, const float* x, int64_t n, const 
   const int L = net->n_hidden;
   const P p = wide_bwd_plan<H>(L, n);
   if (!workspace || workspace_bytes < p.bytes) return PINN_E_WORKSPACE;
+  const bool pdl = wide_pdl(n);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   const ParamLayout lay = make_layout(H, L);
   const int tiles = static_cast<int>((n + kWT - 1) / kWT);
@@ -805,11 +828,11 @@ static int run_wide_bwd(const pinn_net_t* net, const float* x, int64_t n, const 
   // ---- weight planes: forward (rows) and dgrad (transposed), dropout scale folded into both
   auto split = [&](const float* sa, int rows_a, const float* sb, int N, int K, unsigned char* dst) {
     const int items = N * (K / 4);
-    wide_split_weights_kernel<<<(items + 255) / 256, 256, 0, st>>>(sa, rows_a, sb, N, K, wscale, dst);
+    launch_pdl(wide_split_weights_kernel, dim3((items + 255) / 256), dim3(256), 0, st, pdl, sa, rows_a, sb, N, K, wscale, dst);
   };
   auto splitT = [&](const float* sa, int rows_a, const float* sb, int N, int K, unsigned char* dst) {
     const int items = N * (K / 4);
-    wide_split_weights_T_kernel<<<(items + 255) / 256, 256, 0, st>>>(sa, rows_a, sb, N, K, wscale, dst);
+    launch_pdl(wide_split_weights_T_kernel, dim3((items + 255) / 256), dim3(256), 0, st, pdl, sa, rows_a, sb, N, K, wscale, dst);
   };
   for (int l = 1; l < L; ++l) { split(net->W[l], H, nullptr, H, H, ws + p.off_wf[l]); splitT(net->W[l], H, nullptr, H, H, ws + p.off_wt[l]); }
   split(net->Wv0, H / 2, net->Wp, NH, H, ws + p.off_wfh);
@@ -819,7 +842,7 @@ static int run_wide_bwd(const pinn_net_t* net, const float* x, int64_t n, const 
   // ---- constant rows (ones + zero padding) of the B-side transposed buffers
   auto ones = [&](unsigned char* buf, int rows, int data_rows) {
     const int64_t items = chunks * 4 * (rows - data_rows);
-    wide_fill_ones_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, st>>>(buf, rows, data_rows, chunks);
+    launch_pdl(wide_fill_ones_kernel, dim3(static_cast<unsigned>((items + 255) / 256)), dim3(256), 0, st, pdl, buf, rows, data_rows, chunks);
   };
   for (int l = 0; l < L; ++l) ones(ws + p.off_at[l], RB, H);
   ones(ws + p.off_v0t, RV, H / 2);
@@ -861,33 +884,33 @@ static int run_wide_bwd(const pinn_net_t* net, const float* x, int64_t n, const 
   // ============================ forward ============================
   a.layer = 0; a.unit_base = 0; a.out = ws + p.off_pa[0];
   a.outT = ws + p.off_at[0]; a.T_rows = RB; a.act = ws + p.off_xt;
-  wide_layer0_kernel<H><<<tiles, 256, 0, st>>>(x, net->W[0], net->b[0], dp, a);
+  launch_pdl(wide_layer0_kernel<H>, dim3(tiles), dim3(256), 0, st, pdl, x, net->W[0], net->b[0], dp, a);
   a.act = nullptr;
   for (int l = 1; l < L; ++l) {
     a.A = ws + p.off_pa[l - 1]; a.W = ws + p.off_wf[l]; a.out = ws + p.off_pa[l]; a.bias = net->b[l];
     a.outT = ws + p.off_at[l]; a.T_rows = RB;
     a.layer = static_cast<uint32_t>(l); a.unit_base = static_cast<uint32_t>(l * H); a.nch = H / kWKc;
-    k_hidden<<<tiles, 320, smem_of(H), st>>>(dp, a);
+    launch_pdl(k_hidden, dim3(tiles), dim3(320), smem_of(H), st, pdl, dp, a);
   }
   a.A = ws + p.off_pa[L - 1]; a.W = ws + p.off_wfh; a.out = ws + p.off_pv0; a.bias = net->bv0; a.bias2 = net->bp;
   a.outT = ws + p.off_v0t; a.T_rows = RV;
   a.layer = static_cast<uint32_t>(L); a.unit_base = static_cast<uint32_t>(L * H); a.nch = H / kWKc;
-  k_heads<<<tiles, 320, smem_of(NH), st>>>(dp, a);
+  launch_pdl(k_heads, dim3(tiles), dim3(320), smem_of(NH), st, pdl, dp, a);
   // ============================ tail: last variance layer forward + backward, loss gradient ============================
   a.A = ws + p.off_pv0; a.W = ws + p.off_wfv1; a.out = ws + p.off_pdz1; a.bias = net->bv1; a.bias2 = net->bv2; a.w2 = net->Wv2;
   a.outT = ws + p.off_dt; a.T_rows = 0; a.nch = (H / 2) / kWKc;
-  k_v1t<<<tiles, 320, smem_of(H / 4), st>>>(dp, a);
-  wide_tail_reduce_kernel<<<H / 4 + 5, 256, 0, st>>>(a.tail_partial, a.loss_partial, tiles, H / 4, grad_flat + lay.offWv2, grad_flat + lay.offbv2,
+  launch_pdl(k_v1t, dim3(tiles), dim3(320), smem_of(H / 4), st, pdl, dp, a);
+  launch_pdl(wide_tail_reduce_kernel, dim3(H / 4 + 5), dim3(256), 0, st, pdl, a.tail_partial, a.loss_partial, tiles, H / 4, grad_flat + lay.offWv2, grad_flat + lay.offbv2,
                                              grad_u ? nullptr : loss_sums);
   // weight-gradient GEMM + reduce helpers
   const int per_split = static_cast<int>((chunks + p.splits - 1) / p.splits);
   auto wgrad = [&](auto kern, int N, int nmb, const unsigned char* Bt) {
     a.A = ws + p.off_dt; a.W = Bt; a.nch = per_split;
-    kern<<<dim3(p.splits, nmb), 320, smem_of(N), st>>>(dp, a);
+    launch_pdl(kern, dim3(p.splits, nmb), dim3(320), smem_of(N), st, pdl, dp, a);
   };
   auto reduce = [&](int nmb, int N, int mb, int row0, int nrows, int ncols, int bias_col, float* dW, int ld, float* dB, float scale) {
     const int items = nrows * (ncols + (dB ? 1 : 0));
-    wide_wgrad_reduce_kernel<<<(items + 255) / 256, 256, 0, st>>>(a.wg_partial, p.splits, nmb, N, mb, row0, nrows, ncols, bias_col, dW, ld,
+    launch_pdl(wide_wgrad_reduce_kernel, dim3((items + 255) / 256), dim3(256), 0, st, pdl, a.wg_partial, p.splits, nmb, N, mb, row0, nrows, ncols, bias_col, dW, ld,
                                                                    dB, scale);
   };
   // dWv1 / dbv1 = dz1^T [v0 | 1]
@@ -897,7 +920,7 @@ static int run_wide_bwd(const pinn_net_t* net, const float* x, int64_t n, const 
   a.A = ws + p.off_pdz1; a.W = ws + p.off_wtv1; a.out = ws + p.off_pdv0h; a.act = ws + p.off_pv0;
   a.outT = ws + p.off_dt; a.T_rows = 0; a.nch = (H / 4) / kWKc;
   a.layer = static_cast<uint32_t>(L); a.unit_base = static_cast<uint32_t>(L * H);
-  k_dv0<<<tiles, 320, smem_of(H / 2), st>>>(dp, a);
+  launch_pdl(k_dv0, dim3(tiles), dim3(320), smem_of(H / 2), st, pdl, dp, a);
   // dWv0 / dbv0 (block 0) and dWp / dbp (block 1, row 0) = [dz_v0 ; du]^T [a_{L-1} | 1]
   constexpr int NMB_V0 = (H / 2 + 16 + kWT - 1) / kWT;         // delta rows: H/2 of dz_v0, then du at row H/2
   wgrad(k_wg_b, RB, NMB_V0, ws + p.off_at[L - 1]);
@@ -908,7 +931,7 @@ static int run_wide_bwd(const pinn_net_t* net, const float* x, int64_t n, const 
   a.A = ws + p.off_pdv0h; a.W = ws + p.off_wth; a.out = ws + p.off_pd[cur]; a.act = ws + p.off_pa[L - 1];
   a.outT = ws + p.off_dt; a.T_rows = 0; a.nch = NH / kWKc;
   a.layer = static_cast<uint32_t>(L - 1); a.unit_base = static_cast<uint32_t>((L - 1) * H);
-  k_dz<<<tiles, 320, smem_of(H), st>>>(dp, a);
+  launch_pdl(k_dz, dim3(tiles), dim3(320), smem_of(H), st, pdl, dp, a);
   for (int l = L - 1; l >= 1; --l) {
     // dW_l / db_l = dz_l^T [a_{l-1} | 1]   (two 128-row blocks)
     wgrad(k_wg_b, RB, H / kWT, ws + p.off_at[l - 1]);
@@ -918,7 +941,7 @@ static int run_wide_bwd(const pinn_net_t* net, const float* x, int64_t n, const 
     a.A = ws + p.off_pd[cur]; a.W = ws + p.off_wt[l]; a.out = ws + p.off_pd[cur ^ 1]; a.act = ws + p.off_pa[l - 1];
     a.outT = ws + p.off_dt; a.T_rows = 0; a.nch = H / kWKc;
     a.layer = static_cast<uint32_t>(l - 1); a.unit_base = static_cast<uint32_t>((l - 1) * H);
-    k_dz<<<tiles, 320, smem_of(H), st>>>(dp, a);
+    launch_pdl(k_dz, dim3(tiles), dim3(320), smem_of(H), st, pdl, dp, a);
     cur ^= 1;
   }
   // dW0 / db0 = dz_0^T [x | 1]
