@@ -10,9 +10,12 @@ own fp32 noise exceeds the tolerance, SURVEY.md section 8c / hazard H2).
 
 Pinning: the reference ships no tests or golden vectors,
 so this oracle is pinned against outputs of the reference itself, generated in
-the build container by ``tests/golden/make_golden.py`` (imports the unmodified
-reference by path) and committed as ``tests/golden/*.npz``;
-``tests/test_oracle_golden.py`` holds the comparison.
+the build container by ``tests/golden/make_golden.py``, ``make_golden_export.py``
+and ``make_golden_gmm.py`` (they import the unmodified reference scripts 01, 04
+and 03 by path) and committed as ``tests/golden/*.npz``;
+``tests/test_oracle_golden.py`` holds the comparison.  The export / RF(t) / GMM
+restatements at the end of the file follow 01:1830-2047, 04:181-300 and
+03:360-426 (the latter on top of sklearn's published GaussianMixture arithmetic).
 
 Parameter dictionaries use the reference's ``state_dict`` keys
 (``layers.layer_{i}.weight`` ... see 01:399-419); weights are ``[out, in]``.
