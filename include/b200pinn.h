@@ -232,7 +232,8 @@ int pinn_adam_step_from_sums(float* params, const double* sums,
  * bodies of train_lambda (01:1008-1055; families = PINN_FAM_V | PINN_FAM_DATA, flags select the physics
  * term), train_thermal (01:1107-1151; PINN_FAM_TS), train_hydrogen (01:1354-1391; PINN_FAM_H) and
  * train_oxygen (01:1204-1274; PINN_FAM_O): residual sums -> mean gradients -> Adam + StepLR + clamp,
- * repeated on the device with one grid barrier per step.  Step for step it computes what
+ * repeated on the device with one barrier per step (cluster barrier for small batches, a grid
+ * barrier in global memory otherwise).  Step for step it computes what
  * pinn_residuals (fast math) followed by pinn_adam_step_from_sums computes.
  * lambdas: all PINN_N_LAMBDA scalars (device, updated in place: only [first, first+count));
  * grad_slot / lo / hi: HOST arrays of `count` (<= 8) entries, meaning as in pinn_adam_step_from_sums
@@ -241,6 +242,10 @@ int pinn_adam_step_from_sums(float* params, const double* sums,
  * reference prints them).  Needs n > 0 and a device that supports cooperative launches;
  * workspace >= pinn_scalar_phase_workspace_bytes(). */
 size_t pinn_scalar_phase_workspace_bytes(void);
+/* Ablation / test switch for pinn_scalar_phase: 1 (default) runs batches of up to 32 768 samples as
+ * ONE thread-block cluster (partials in distributed shared memory, hardware cluster barrier);
+ * 0 always uses the cooperative grid with its global-memory barrier.  Returns the previous setting. */
+int pinn_set_phase_cluster(int enable);
 int pinn_scalar_phase(const float* x, const float* u, const float* y, int64_t n,
                       const pinn_scalers_t* scalers, float* lambdas, uint32_t families,
                       uint32_t flags, int32_t first, int32_t count,

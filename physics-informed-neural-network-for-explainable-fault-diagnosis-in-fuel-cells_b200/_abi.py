@@ -71,6 +71,7 @@ _SIGNATURES = {
     "pinn_set_tensor_core_path": (C.c_int, [C.c_int]),
     "pinn_set_tensor_core_bwd": (C.c_int, [C.c_int]),
     "pinn_set_dependent_launch": (C.c_int, [C.c_int]),
+    "pinn_set_phase_cluster": (C.c_int, [C.c_int]),
     "pinn_set_wide_tensor_core_path": (C.c_int, [C.c_int]),
     "pinn_device_sm_count": (C.c_int, []),
     "pinn_adam_step_p2p": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _u32, _vp, _vp, _i64, _vp, _dbl, _dbl, _i64, _vp]),

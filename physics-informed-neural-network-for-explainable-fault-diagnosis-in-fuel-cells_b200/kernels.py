@@ -266,6 +266,11 @@ def set_dependent_launch(mode) -> int:
     return int(_abi.lib().pinn_set_dependent_launch(int(mode)))
 
 
+def set_phase_cluster(enable: bool) -> bool:
+    """Ablation switch: small batches of ``scalar_phase`` as one thread-block cluster (default) or as a cooperative grid."""
+    return bool(_abi.lib().pinn_set_phase_cluster(1 if enable else 0))
+
+
 def new_step_counter(device) -> torch.Tensor:
     return torch.zeros(2, device=device, dtype=torch.int64)
 

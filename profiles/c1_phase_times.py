@@ -16,8 +16,10 @@ phases = [("train_lambda(A)", lambda k: m.train_lambda(k, False, verbose=False))
           ("train_thermal", lambda k: m.train_thermal(k, verbose=False)),
           ("train_hydrogen", lambda k: m.train_hydrogen(k, verbose=False)),
           ("train_oxygen", lambda k: m.train_oxygen(k, verbose=False))]
-for mode in ("1", "0"):
+from b200pinn import kernels as K
+for mode, cluster in (("1", True), ("1", False), ("0", True)):
     os.environ["B200PINN_PHASE_KERNEL"] = mode
+    K.set_phase_cluster(cluster)
     for name, fn in phases:
         fn(3)
         for rep in range(2):
@@ -26,4 +28,4 @@ for mode in ("1", "0"):
             fn(steps)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
-        print(f"n={n} {'persistent' if mode == '1' else 'per-step  '} {name:16s} {1e6 * dt / steps:7.2f} us/step")
+        print(f"n={n} {('persistent/cluster' if cluster else 'persistent/grid   ') if mode == '1' else 'per-step          '} {name:16s} {1e6 * dt / steps:7.2f} us/step")

@@ -257,8 +257,19 @@ def test_persistent_phase_kernel_matches_step_by_step_path(n, monkeypatch):
                    m.train_oxygen(1203, verbose=False)]
         return snaps, lam_vec(m), np.array(losses, np.float64)
 
-    snap_p, lam_p, loss_p = run("1")
+    from b200pinn import kernels as K
+
+    snap_p, lam_p, loss_p = run("1")                 # n <= 32 768: one thread-block cluster; above: cooperative grid
     snap_s, lam_s, loss_s = run("0")
+    if n <= 32768:                                    # the grid-barrier form at the same size
+        K.set_phase_cluster(False)
+        try:
+            snap_g, lam_g, loss_g = run("1")
+        finally:
+            K.set_phase_cluster(True)
+        assert np.allclose(snap_g[0], snap_s[0], rtol=2e-5, atol=1e-9), (snap_g[0], snap_s[0])
+        assert np.allclose(lam_g[4:], lam_s[4:], rtol=2e-5, atol=2e-6), (lam_g, lam_s)
+        assert np.allclose(loss_g[4:], loss_s[4:], rtol=2e-5), (loss_g, loss_s)
     assert np.all(np.isfinite(lam_p)) and np.all(np.isfinite(loss_p))
     assert abs(snap_p[0][0] - 0.30) > 0.05                                     # it did train
     assert np.allclose(snap_p[0], snap_s[0], rtol=2e-5, atol=1e-9), (snap_p[0], snap_s[0])
