@@ -106,6 +106,15 @@ int pinn_train_dnn_step(const pinn_net_t* net, const float* x, int64_t n,
                         int64_t* step_counter, double lr0, double gamma, int64_t step_size,
                         float* grad_flat, double* loss_sums, void* workspace,
                         size_t workspace_bytes, void* stream);
+/* n_steps consecutive train_dnn steps enqueued by ONE call (same arguments; step i uses
+ * drop->pass_offset + i, so drop->masks must be NULL when n_steps > 1; loss_sums = the last
+ * step's sums).  Takes the host loop off the critical path when a step is ~50 us of GPU work. */
+int pinn_train_dnn_steps(const pinn_net_t* net, const float* x, int64_t n,
+                         const pinn_dropout_t* drop, const float* y, int64_t n_global,
+                         float* params_flat, float* exp_avg, float* exp_avg_sq,
+                         int64_t* step_counter, double lr0, double gamma, int64_t step_size,
+                         int64_t n_steps, float* grad_flat, double* loss_sums, void* workspace,
+                         size_t workspace_bytes, void* stream);
 
 /* K3 -- multi-physics residuals + reductions: net_f_V 01:724-765, net_f_T_simple
  * 01:869-914, net_f_T 01:767-867, net_f_H 01:621-722, net_f_O 01:535-619, the

@@ -458,3 +458,24 @@ extern "C" int pinn_train_dnn_step(const pinn_net_t* net, const float* x, int64_
   return pinn_adam_step(params_flat, grad_flat, exp_avg, exp_avg_sq, lay.total, step_counter, lr0, gamma, step_size, 1.0, nullptr,
                         nullptr, nullptr, 1, stream);
 }
+
+// `n_steps` consecutive train_dnn steps enqueued by one call (the Python loop around pinn_train_dnn_step costs about as
+// much host time per step as the three launches take on the device at the reference's batch sizes).  Step i draws its
+// dropout masks with pass_offset = drop->pass_offset + i -- what the per-step loop passes; injected masks cannot be
+// advanced here, so `drop->masks` must be NULL.  loss_sums holds the sums of the LAST step.
+extern "C" int pinn_train_dnn_steps(const pinn_net_t* net, const float* x, int64_t n, const pinn_dropout_t* drop, const float* y,
+                                    int64_t n_global, float* params_flat, float* exp_avg, float* exp_avg_sq, int64_t* step_counter,
+                                    double lr0, double gamma, int64_t step_size, int64_t n_steps, float* grad_flat,
+                                    double* loss_sums, void* workspace, size_t workspace_bytes, void* stream) {
+  if (n_steps < 0) return PINN_E_ARG;
+  if (drop != nullptr && drop->masks != nullptr && n_steps > 1) return PINN_E_ARG;
+  pinn_dropout_t d{};
+  if (drop != nullptr) d = *drop;
+  for (int64_t i = 0; i < n_steps; ++i) {
+    if (drop != nullptr) d.pass_offset = drop->pass_offset + i;
+    const int r = pinn_train_dnn_step(net, x, n, drop != nullptr ? &d : nullptr, y, n_global, params_flat, exp_avg, exp_avg_sq,
+                                      step_counter, lr0, gamma, step_size, grad_flat, loss_sums, workspace, workspace_bytes, stream);
+    if (r != 0) return r;
+  }
+  return 0;
+}

@@ -1049,8 +1049,12 @@ int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropPa
 #define LAUNCH_A(LL)                                                                                              \
   {                                                                                                               \
     auto kern = inj ? mlp_tc_bwd_kernel<LL, true> : mlp_tc_bwd_kernel<LL, false>;                                 \
-    PINN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                         \
-                                       static_cast<int>(p.smem_a)));                                              \
+    static bool attr_a[64][2] = {};      /* the attribute is per device and function: set it once, not per step */ \
+    if (!attr_a[devi & 63][inj ? 1 : 0]) {                                                                         \
+      PINN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                       \
+                                         static_cast<int>(p.smem_a)));                                            \
+      attr_a[devi & 63][inj ? 1 : 0] = true;                                                                       \
+    }                                                                                                             \
     PINN_CUDA_TRY(launch_pdl(kern, dim3(p.grid_a), dim3(512), p.smem_a, st, pdl, *net, tl, dp, a));               \
   }
   switch (L) {
@@ -1068,8 +1072,12 @@ int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropPa
   const WgLayout wl = make_wg_layout(L);
 #define LAUNCH_B(LL)                                                                                              \
   {                                                                                                               \
-    PINN_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
-                                       static_cast<int>(p.smem_b)));                                              \
+    static bool attr_b[64] = {};                                                                                  \
+    if (!attr_b[devi & 63]) {                                                                                     \
+      PINN_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                         static_cast<int>(p.smem_b)));                                            \
+      attr_b[devi & 63] = true;                                                                                   \
+    }                                                                                                             \
     PINN_CUDA_TRY(launch_pdl(wgrad_tc_kernel<LL>, dim3(p.grid_b), dim3(kWgLoaders + 32), p.smem_b, st,           \
                              pdl, w, lay, wl, a.rm));                                                             \
   }

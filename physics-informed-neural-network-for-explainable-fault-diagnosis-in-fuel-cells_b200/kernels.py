@@ -343,9 +343,11 @@ def scalar_phase(x, u, y, scalers: PinnScalers, lambdas, families: int, flags: i
 
 
 def train_dnn_step(net: Net, x, drop: Optional[PinnDropout], y, n_global: int, params_flat, exp_avg, exp_avg_sq,
-                   step_counter, lr0, gamma, step_size, grad_flat, loss_sums):
+                   step_counter, lr0, gamma, step_size, grad_flat, loss_sums, n_steps: int = 1):
     """One ``train_dnn`` step (01:948-955) in one call: K2a, K2b and the gradient reduce with Adam + StepLR fused
-    into it.  ``net``'s tensors must be views into ``params_flat``.  See ``pinn_train_dnn_step``."""
+    into it; ``n_steps`` > 1 enqueues that many consecutive steps from one call (Philox masks only: step i uses the
+    dropout descriptor's ``pass_offset + i``).  ``net``'s tensors must be views into ``params_flat``.
+    See ``pinn_train_dnn_step`` / ``pinn_train_dnn_steps``."""
     global LAUNCHES
     _require_cuda(x, "x")
     if not x.is_contiguous() or not y.is_contiguous():
@@ -356,8 +358,8 @@ def train_dnn_step(net: Net, x, drop: Optional[PinnDropout], y, n_global: int, p
     nb = L.pinn_mlp_bwd_workspace_bytes(net.width, net.n_hidden, n)
     ws = _workspace("bwd", nb, x.device)
     with torch.cuda.device(x.device):
-        check(L.pinn_train_dnn_step(C.byref(net.desc), ptr(x), n, C.byref(drop) if drop is not None else None, ptr(y),
-                                    int(n_global), ptr(params_flat), ptr(exp_avg), ptr(exp_avg_sq), ptr(step_counter),
-                                    float(lr0), float(gamma), int(step_size), ptr(grad_flat), ptr(loss_sums), ptr(ws), nb,
-                                    _stream()), "pinn_train_dnn_step")
-    LAUNCHES += 3
+        check(L.pinn_train_dnn_steps(C.byref(net.desc), ptr(x), n, C.byref(drop) if drop is not None else None, ptr(y),
+                                     int(n_global), ptr(params_flat), ptr(exp_avg), ptr(exp_avg_sq), ptr(step_counter),
+                                     float(lr0), float(gamma), int(step_size), int(n_steps), ptr(grad_flat), ptr(loss_sums),
+                                     ptr(ws), nb, _stream()), "pinn_train_dnn_steps")
+    LAUNCHES += 3 * int(n_steps)

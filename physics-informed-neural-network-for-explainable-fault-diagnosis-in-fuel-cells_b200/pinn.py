@@ -253,6 +253,28 @@ class PhysicsInformedNN:
             print("  Epoch |    Loss    |    MSE     |    LR    ")
         loss = float("nan")
         fused_step = n_local > 0 and os.environ.get("B200PINN_FUSED_DNN_STEP", "1") != "0"
+        if (world == 1 and fused_step and self.dnn._injected is None
+                and os.environ.get("B200PINN_DNN_STEP_BLOCKS", "1") != "0"):
+            # single GPU, Philox masks: every stretch of epochs up to the next progress line is ONE call that enqueues
+            # all its steps (3 launches each) -- at the reference's batch sizes the Python loop costs as much host time
+            # per step as the step takes on the device
+            epoch = 0
+            while epoch < nIter:
+                stop = min(((epoch + 999) // 1000) * 1000, nIter - 1)
+                k = stop - epoch + 1
+                cfg = self.dnn.next_dropout_cfg(n_local, self.dnn.active_dropout_p())
+                drop = K.make_dropout(**cfg) if cfg is not None else None
+                if cfg is not None:
+                    self.dnn._drop_calls += k - 1               # the call consumes k consecutive pass offsets
+                K.train_dnn_step(net, x, drop, y, n_global, flat, m, v, counter, 1e-2, 0.8, 1000, grad, sums, n_steps=k)
+                s = sums.cpu().numpy()
+                loss = (s[0] + 0.01 * s[1]) / max(s[3], 1.0)
+                if verbose and stop % 1000 == 0:
+                    print(f" {stop:5d}  | {loss:10.3e} | {s[2] / max(s[3], 1.0):10.3e} | {1e-2 * 0.8 ** (stop // 1000):8.1e}")
+                epoch = stop + 1
+            if verbose:
+                print(f"DNN training done, final loss: {loss:.3e}\n")
+            return loss
         for epoch in range(nIter):
             cfg = self.dnn.next_dropout_cfg(n_local, self.dnn.active_dropout_p())
             drop = K.make_dropout(**cfg) if cfg is not None else None

@@ -329,16 +329,19 @@ def test_fused_train_dnn_step_matches_bwd_plus_adam(layers, n, monkeypatch):
 
     x, y, sx, sy = make_scaled_dataset(n, seed=5)
 
-    def run(flag):
+    def run(flag, blocks="1"):
         monkeypatch.setenv("B200PINN_FUSED_DNN_STEP", flag)
+        monkeypatch.setenv("B200PINN_DNN_STEP_BLOCKS", blocks)
         torch.manual_seed(7)
         m = b200pinn.PhysicsInformedNN(torch.tensor(x), torch.tensor(y), layers, sx, sy, 0.2, True)
         loss = m.train_dnn(25, verbose=False)
         return loss, {k: t2n(v).copy() for k, v in m.dnn.state_dict().items()}
 
-    loss_f, sd_f = run("1")
+    loss_f, sd_f = run("1")                       # pinn_train_dnn_steps: all 24 steps after the first from one call
+    loss_s, sd_s = run("1", blocks="0")           # pinn_train_dnn_step once per Python iteration
     loss_u, sd_u = run("0")
     loss_u2, sd_u2 = run("0")
+    assert loss_s == loss_f and all(np.array_equal(sd_s[k], sd_f[k]) for k in sd_f), "blocked vs per-call fused steps"
     assert np.isfinite(loss_f) and np.isfinite(loss_u)
     for k in sd_u:
         assert np.array_equal(sd_u[k], sd_u2[k]), ("step is not deterministic run to run", k)
