@@ -162,7 +162,11 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
     // One issuing warp per group; it walks the group's deterministic schedule (tile -> pass -> layers
     // 1..L-1 -> heads) and sleeps on the group's "ready" barrier in between.
     const int g = warp - 16;
+#ifdef PINN_K2A_PAIR_FIRST
     const int64_t first = static_cast<int64_t>(blockIdx.x) * 2 + g;
+#else
+    const int64_t first = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(g) * gridDim.x;     // same map as the compute warps below
+#endif
     const int64_t tiles = first < n_tiles ? (n_tiles - first + 2 * gridDim.x - 1) / (2 * static_cast<int64_t>(gridDim.x)) : 0;
     const uint32_t d_t = tmem_base_s + static_cast<uint32_t>(g * 64);
     const uint32_t a_hi = tmem_base_s + static_cast<uint32_t>(128 + g * 128);
@@ -254,7 +258,13 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
       tc::fence_after_sync();
     };
 
+    // tile -> (CTA, group): group 0 of every CTA first, then group 1: up to one tile per SM every tile runs alone (a lone
+    // tile finishes ~1.4x sooner than a tile of an interleaved pair; pairing only buys throughput once all SMs are busy)
+#ifdef PINN_K2A_PAIR_FIRST
     for (int64_t tile = static_cast<int64_t>(blockIdx.x) * 2 + grp; tile < n_tiles; tile += static_cast<int64_t>(gridDim.x) * 2) {
+#else
+    for (int64_t tile = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(grp) * gridDim.x; tile < n_tiles; tile += static_cast<int64_t>(gridDim.x) * 2) {
+#endif
       const int64_t s = tile * kTcTile + row;
       const bool valid = s < n;
       // layer 0 (pass-invariant): this thread's 32 columns -> tensor memory
@@ -448,7 +458,11 @@ int launch_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, 
   const size_t smem = static_cast<size_t>(lay.total) * sizeof(float);
   if (smem > 226 * 1024) return 0;          // resident weight planes: 32 KB per hidden layer (7 hidden layers fit)
   const int64_t tiles = (n + kTcTile - 1) / kTcTile;
+#ifdef PINN_K2A_PAIR_FIRST
   const int64_t want = (tiles + 1) / 2;        // two 128-sample tiles in flight per CTA
+#else
+  const int64_t want = tiles;                  // one CTA per tile until the SMs run out, then two tiles in flight per CTA
+#endif
   const int grid = static_cast<int>(want < sm_count() ? (want > 0 ? want : 1) : sm_count());
   const bool inj = dp.p > 0.f && dp.masks != nullptr;
   auto go = [&](auto kern) -> cudaError_t {
