@@ -393,14 +393,14 @@ def run_ours(args):
                      "kernel": "mlp_tc_kernel<MC> (tcgen05.mma kind::tf32 with A in tensor memory, 3xTF32 split, "
                                "one MMA warp per 128-sample group)",
                      "peak_source": pk["src"],
-                     "ncu": {"source": "profiles/r1_final2_mc.summary.txt (same kernel structure, 10.97 ms capture)",
-                             "sm__pipe_tensor_cycles_active_pct": 29.0, "smsp__issue_active_pct": 61.2,
-                             "sm__inst_executed_pipe_alu_pct": 43.8, "sm__inst_executed_pipe_xu_pct": 39.3,
+                     "ncu": {"source": "profiles/r1_final4_mc.summary.txt (ncu --set full of this build's kernel, 10.58 ms capture)",
+                             "sm__pipe_tensor_cycles_active_pct": 29.6, "smsp__issue_active_pct": 57.4,
+                             "sm__inst_executed_pipe_alu_pct": 43.9, "sm__inst_executed_pipe_xu_pct": 40.1,
                              "dram_bytes_per_launch": 32.1e6},
                      "note": "achieved = algorithmic FLOPs (21 664 per sample*pass) / CUDA-event time of the launch. The "
                              "contractions run as 3 TF32 MMAs per product (fp32 parity), and TF32 dense peak is half the "
                              "bf16 figure used as `peak`, so the tensor pipe does 6x this fraction of its own peak "
-                             "(ncu: sm__pipe_tensor_cycles_active, profiles/r1_final2_mc.summary.txt); the kernel is "
+                             "(ncu: sm__pipe_tensor_cycles_active, profiles/r1_final4_mc.summary.txt); the kernel is "
                              "bounded by the CUDA-core epilogue (2 MUFU + ~12 ALU/FMA ops per activation, 5.6 Philox "
                              "instructions per draw) and by the ~1000-clk latency of each 24-MMA batch, see DESIGN.md "
                              "section 4 (tensor pipe active: 29 % here, 43 % in the weight-gradient kernel K2b, 47-51 % in the "
