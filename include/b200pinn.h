@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PINN_ABI_VERSION 1
+#define PINN_ABI_VERSION 2
 #define PINN_N_IN 8        /* operating-condition features, 01:136-137 */
 #define PINN_MAX_HIDDEN 8  /* hidden (tanh) layers supported */
 #define PINN_N_LAMBDA 17   /* lambda_1..4, T1..5, H1..4, O1..4 (01:453-517) */
@@ -43,7 +43,7 @@ typedef struct pinn_net {
   int32_t n_in;      /* must be PINN_N_IN */
   int32_t width;     /* H */
   int32_t n_hidden;  /* L, 1..PINN_MAX_HIDDEN */
-  int32_t reserved;
+  int32_t flags;     /* PINN_NET_* bits below: per-call options (the library keeps no process-global switches) */
   const float* W[PINN_MAX_HIDDEN]; /* layers.layer_i.weight [H, in_i]           */
   const float* b[PINN_MAX_HIDDEN]; /* layers.layer_i.bias   [H]                 */
   const float* Wp;  const float* bp;   /* predict        [1,H]     [1]          */
@@ -51,6 +51,16 @@ typedef struct pinn_net {
   const float* Wv1; const float* bv1;  /* var_layers.3   [H/4,H/2] [H/4]        */
   const float* Wv2; const float* bv2;  /* var_layers.5   [1,H/4]   [1]          */
 } pinn_net_t;
+
+enum { /* pinn_net_t.flags */
+  PINN_NET_NO_TC_FWD = 1,   /* ablation / tests: run the 64-wide forward and MC sweep on the fp32 FFMA kernels   */
+  PINN_NET_NO_TC_BWD = 2,   /* same for the 64-wide backward                                                     */
+  PINN_NET_NO_WIDE_TC = 4,  /* same for the 128- / 256-wide nets (forward, MC sweep and backward)                */
+  PINN_NET_PDL_NEVER = 8,   /* never chain a step's launches with programmatic dependent launch                  */
+  PINN_NET_PDL_ALWAYS = 16, /* always chain them (default: only for batches of up to two tiles per SM)           */
+  PINN_NET_NO_LOGVAR = 32   /* DNN(logvar=False), 01:436: the log-variance output is identically 0, the variance
+                               head receives no gradient and the aleatoric loss reduces to 0.5 * MSE             */
+};
 
 /* Dropout control.  p == 0 means eval mode.  With masks == NULL the keep mask of
  * (sample s, pass t, dropout layer l, unit j) is drawn from Philox4x32-10 keyed by
@@ -135,7 +145,9 @@ enum { /* families bitmask */
 enum { /* flags */
   PINN_RES_ACCURATE_MATH = 1, /* libdevice logf/expf/powf instead of MUFU approximations */
   PINN_RES_NO_MODE_A = 2,     /* skip the normalised-domain sums EA2/GA* (train_lambda dnn_para=True) */
-  PINN_RES_NO_MODE_B = 4      /* skip FV2/GB* (train_lambda dnn_para=False) */
+  PINN_RES_NO_MODE_B = 4,     /* skip FV2/GB* (train_lambda dnn_para=False) */
+  PINN_RES_NO_CLUSTER = 8     /* pinn_scalar_phase only (ablation / tests): always use the cooperative grid with its
+                                 global-memory barrier, never the single thread-block cluster form */
 };
 enum { /* sums[] slots (double) */
   PINN_S_N = 0,
@@ -251,10 +263,8 @@ int pinn_adam_step_from_sums(float* params, const double* sums,
  * reference prints them).  Needs n > 0 and a device that supports cooperative launches;
  * workspace >= pinn_scalar_phase_workspace_bytes(). */
 size_t pinn_scalar_phase_workspace_bytes(void);
-/* Ablation / test switch for pinn_scalar_phase: 1 (default) runs batches of up to 32 768 samples as
- * ONE thread-block cluster (partials in distributed shared memory, hardware cluster barrier);
- * 0 always uses the cooperative grid with its global-memory barrier.  Returns the previous setting. */
-int pinn_set_phase_cluster(int enable);
+/* Batches of up to 8 192 samples run as ONE thread-block cluster (partials in distributed shared memory,
+ * hardware cluster barrier) unless `flags` carries PINN_RES_NO_CLUSTER. */
 int pinn_scalar_phase(const float* x, const float* u, const float* y, int64_t n,
                       const pinn_scalers_t* scalers, float* lambdas, uint32_t families,
                       uint32_t flags, int32_t first, int32_t count,
@@ -297,23 +307,6 @@ int pinn_gmm_pass(const double* X, int64_t n, int32_t d, int32_t n_components,
                   double* resp, double* y_prob, int32_t* y_pred, double* stats,
                   double* comp_class_weight, double* log_prob_norm_sum, void* workspace,
                   size_t workspace_bytes, void* stream);
-
-/* Ablation / test switch.  The 64-wide net's forward and MC-dropout kernels run their
- * 64x64 contractions on tcgen05 tensor cores (3xTF32, fp32-accurate); 0 routes them through
- * the fp32 FFMA kernels that serve the other widths.  Returns the previous setting. */
-int pinn_set_tensor_core_path(int enable);
-/* Same switch for the backward kernels (pinn_mlp_bwd). */
-int pinn_set_tensor_core_bwd(int enable);
-/* Ablation switch: the launches of one training step / forward / MC pass on the tensor-core
- * paths (64-wide: forward+dgrad, weight gradients, reduce[+Adam]; 128/256-wide: the per-layer
- * GEMM launches) are chained with programmatic dependent launch so that each kernel's launch
- * (and, on the 64-wide path, its prologue) overlaps its predecessor's tail.  1 (default): for
- * batches up to 2 tiles per SM, where launch latency is a visible share of the step; 2: always;
- * 0: never.  Results are identical.  Returns the previous setting. */
-int pinn_set_dependent_launch(int enable);
-/* Same switch for the 128- / 256-wide nets' forward and MC-dropout sweep (one tcgen05 GEMM launch
- * per layer, operands as pre-split tf32 planes; 0 = thread-per-sample FFMA kernels). */
-int pinn_set_wide_tensor_core_path(int enable);
 
 int pinn_abi_version(void);
 const char* pinn_error_string(int code);

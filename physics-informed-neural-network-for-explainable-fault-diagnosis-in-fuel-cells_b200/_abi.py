@@ -13,13 +13,16 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200pinn.so")
 
+ABI_VERSION = 2
 N_IN = 8
 MAX_HIDDEN = 8
 N_LAMBDA = 17
 
 # families / flags / slots: keep in sync with include/b200pinn.h (tests check the header)
 FAM_V, FAM_TS, FAM_T, FAM_H, FAM_O, FAM_DATA = 1, 2, 4, 8, 16, 32
-RES_ACCURATE_MATH, RES_NO_MODE_A, RES_NO_MODE_B = 1, 2, 4
+RES_ACCURATE_MATH, RES_NO_MODE_A, RES_NO_MODE_B, RES_NO_CLUSTER = 1, 2, 4, 8
+# pinn_net_t.flags: per-call path selection and model options (the library keeps no process-global switches)
+NET_NO_TC_FWD, NET_NO_TC_BWD, NET_NO_WIDE_TC, NET_PDL_NEVER, NET_PDL_ALWAYS, NET_NO_LOGVAR = 1, 2, 4, 8, 16, 32
 SUM_NAMES = ["N", "FV2", "EA2", "DATA2", "GA1", "GA2", "GA3", "GB1", "GB2", "GB3",
              "FT2", "FTABS", "GT1", "GT3", "GT5", "FTE2",
              "FH2", "GH1", "GH2", "GH3", "HACT", "HTGT",
@@ -35,7 +38,7 @@ C_COUNT = len(COL_NAMES)
 
 
 class PinnNet(C.Structure):
-    _fields_ = [("n_in", C.c_int32), ("width", C.c_int32), ("n_hidden", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("n_in", C.c_int32), ("width", C.c_int32), ("n_hidden", C.c_int32), ("flags", C.c_int32),
                 ("W", C.c_void_p * MAX_HIDDEN), ("b", C.c_void_p * MAX_HIDDEN),
                 ("Wp", C.c_void_p), ("bp", C.c_void_p), ("Wv0", C.c_void_p), ("bv0", C.c_void_p),
                 ("Wv1", C.c_void_p), ("bv1", C.c_void_p), ("Wv2", C.c_void_p), ("bv2", C.c_void_p)]
@@ -68,11 +71,6 @@ class PinnRfParams(C.Structure):
 _vp, _i64, _i32, _u32, _sz, _dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_size_t, C.c_double
 _SIGNATURES = {
     "pinn_abi_version": (C.c_int, []),
-    "pinn_set_tensor_core_path": (C.c_int, [C.c_int]),
-    "pinn_set_tensor_core_bwd": (C.c_int, [C.c_int]),
-    "pinn_set_dependent_launch": (C.c_int, [C.c_int]),
-    "pinn_set_phase_cluster": (C.c_int, [C.c_int]),
-    "pinn_set_wide_tensor_core_path": (C.c_int, [C.c_int]),
     "pinn_device_sm_count": (C.c_int, []),
     "pinn_adam_step_p2p": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _u32, _vp, _vp, _i64, _vp, _dbl, _dbl, _i64, _vp]),
     "pinn_error_string": (C.c_char_p, [C.c_int]),
@@ -125,7 +123,7 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.pinn_abi_version() != 1:
+        if handle.pinn_abi_version() != ABI_VERSION:
             raise RuntimeError("b200pinn: ABI version mismatch between _abi.py and libb200pinn.so")
         _lib = handle
     return _lib

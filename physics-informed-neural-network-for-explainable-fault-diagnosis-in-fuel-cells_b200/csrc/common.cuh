@@ -245,6 +245,9 @@ PINN_D void tanh8_prescaled(const float* z, const float (&bs)[8], float (&t)[8])
 // log(softplus(v) + 1e-6), softplus with torch's threshold 20 (01:432-434).
 PINN_HD float softplus_f(float v) { return v > 20.0f ? v : log1pf(expf(v)); }
 PINN_HD float logvar_from_v(float v) { return logf(softplus_f(v) + 1e-6f); }
+// DNN(logvar=False) (01:436, PINN_NET_NO_LOGVAR): the log-variance output is identically zero and nothing flows
+// back into the variance head
+PINN_HD float logvar_out(float v, bool no_logvar) { return no_logvar ? 0.0f : logvar_from_v(v); }
 // d logvar / d v  
 PINN_HD float dlogvar_dv(float v) {
   float sp = softplus_f(v);

@@ -231,7 +231,8 @@ mlp_bwd_kernel(pinn_net_t net, ParamLayout lay, DropParams dp, BwdArgs a) {
       tps_dense<H / 2, H / 4, 8, LARGE>(col(rowV0), w.Wv1(), w.bv1(), e);
     }
     const float v = tps_dot1<H / 4, LARGE>(col(rowV1), w.Wv2(), w.bv2());
-    const float slv = logvar_from_v(v);
+    const bool no_lv = (net.flags & PINN_NET_NO_LOGVAR) != 0;
+    const float slv = logvar_out(v, no_lv);
     // ------------------------------------------------ upstream gradients
     float du = 0.f, ds = 0.f;
     if (valid) {
@@ -251,7 +252,7 @@ mlp_bwd_kernel(pinn_net_t net, ParamLayout lay, DropParams dp, BwdArgs a) {
       }
     }
     // ------------------------------------------------ variance-head backward (per sample)
-    const float dv = ds * dlogvar_dv(v);
+    const float dv = no_lv ? 0.f : ds * dlogvar_dv(v);
     col(hdv).set(0, dv);
     col(hdu).set(0, du);
     {

@@ -63,7 +63,7 @@ mlp_fwd_kernel(pinn_net_t net, ParamLayout lay, const float* __restrict__ x, int
     float u, v;
     forward_tail<H, LARGE>(w, lay.L, cols.bufA, cols.bufB, dc, u, v);
     out_u[s] = u;
-    out_s[s] = logvar_from_v(v);
+    out_s[s] = logvar_out(v, (net.flags & PINN_NET_NO_LOGVAR) != 0);
   }
 }
 
@@ -113,7 +113,7 @@ mc_dropout_kernel(pinn_net_t net, ParamLayout lay, const float* __restrict__ x, 
       float d = u - mean;
       mean += d / static_cast<float>(t + 1);
       m2 = fmaf(d, u - mean, m2);
-      slv += logvar_from_v(v);
+      slv += logvar_out(v, (net.flags & PINN_NET_NO_LOGVAR) != 0);
     }
     if (raw_mean) raw_mean[s] = mean;
     if (raw_m2) raw_m2[s] = m2;

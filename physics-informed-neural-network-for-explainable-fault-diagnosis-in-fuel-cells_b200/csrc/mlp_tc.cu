@@ -413,7 +413,7 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
               const float a1 = tanh_pre((part[k] + p1[k]) + bv1[k]);
               vraw = fmaf(Wv2[k], a1, vraw);
             }
-            const float lv = logvar_from_v(vraw);
+            const float lv = logvar_out(vraw, (net.flags & PINN_NET_NO_LOGVAR) != 0);
             if (!MC) {
               if (valid) { out.u[s] = u; out.s[s] = lv; }
             } else if (eval_pass) {
@@ -442,15 +442,13 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
   if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
 }
 
-static int g_tc_enabled = 1;
-
 
 // Launch helper used by pinn_mlp_fwd / pinn_mc_dropout.  Returns 1 if the TC path took the
 // call, 0 if the shape is not covered (caller falls through to the FFMA kernels), <0 / >1 on error.
 int launch_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, const DropParams& dp, const TcOut& out,
               cudaStream_t st, int* err) {
   *err = 0;
-  if (!g_tc_enabled || net->width != kTcH || net->n_hidden < 2 || net->n_hidden > PINN_MAX_HIDDEN) return 0;
+  if ((net->flags & PINN_NET_NO_TC_FWD) || net->width != kTcH || net->n_hidden < 2 || net->n_hidden > PINN_MAX_HIDDEN) return 0;
   for (int l = 1; l < net->n_hidden; ++l)
     if (!aligned16(net->W[l])) return 0;
   if (!aligned16(net->Wv0) || !aligned16(net->Wp)) return 0;
@@ -486,9 +484,3 @@ extern "C" int pinn_debug_timeline(long long* host_out) {
   return static_cast<int>(cudaMemcpyFromSymbol(host_out, pinn::g_tl, sizeof(pinn::g_tl)));
 }
 #endif
-// Test / ablation switch: 0 routes the 64-wide net through the FFMA kernels as well.
-extern "C" int pinn_set_tensor_core_path(int enable) {
-  int prev = pinn::g_tc_enabled;
-  pinn::g_tc_enabled = enable ? 1 : 0;
-  return prev;
-}

@@ -787,7 +787,8 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
         v1[k] = tanh_pre(fmaf((acc.x + acc.y) + (acc2.x + acc2.y), kTanhArg, bv1[k]));
         vraw = fmaf(Wv2[k], v1[k], vraw);
       }
-      const float lv = logvar_from_v(vraw);
+      const bool no_lv = (net.flags & PINN_NET_NO_LOGVAR) != 0;
+      const float lv = logvar_out(vraw, no_lv);
       float ds = 0.f;
       if (valid) {
         if (a.grad_u != nullptr) {
@@ -805,7 +806,7 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
           l_cnt += 1.0;
         }
       }
-      const float dv = ds * dlogvar_dv(vraw);
+      const float dv = no_lv ? 0.f : ds * dlogvar_dv(vraw);
       float dz1[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) dz1[k] = dv * Wv2[k] * (1.0f - v1[k] * v1[k]);
@@ -981,8 +982,6 @@ grad_reduce2_kernel(const float* __restrict__ partial, const double* __restrict_
   }
 }
 
-static int g_tc_bwd_enabled = 1;
-static int g_tc_bwd_pdl = 1;      // programmatic dependent launch between K2a, K2b and the reduce (ablation switch below)
 
 struct TcBwdPlan { int grid_a, grid_b; size_t smem_a, smem_b, off_partial, off_scratch, bytes; };
 static TcBwdPlan plan_tc_bwd(int L, int64_t n) {
@@ -1010,9 +1009,11 @@ static TcBwdPlan plan_tc_bwd(int L, int64_t n) {
   return p;
 }
 
-int dependent_launch_mode() { return g_tc_bwd_pdl; }
+// programmatic dependent launch between the launches of a step: 0 never, 1 small batches only (default), 2 always -- chosen per call
+// by pinn_net_t.flags (PINN_NET_PDL_NEVER / PINN_NET_PDL_ALWAYS); there is no process-global switch
+int dependent_launch_mode(const pinn_net_t* net) { return (net->flags & PINN_NET_PDL_NEVER) ? 0 : ((net->flags & PINN_NET_PDL_ALWAYS) ? 2 : 1); }
 bool tc_bwd_covers(const pinn_net_t* net) {
-  if (!g_tc_bwd_enabled || net->width != kBH || net->n_hidden < 2 || net->n_hidden > 4) return false;
+  if ((net->flags & PINN_NET_NO_TC_BWD) || net->width != kBH || net->n_hidden < 2 || net->n_hidden > 4) return false;
   for (int l = 0; l < net->n_hidden; ++l)
     if (!aligned16(net->W[l])) return false;
   return aligned16(net->Wv0) && aligned16(net->Wp);
@@ -1038,7 +1039,8 @@ int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropPa
   // Dependent launch pays where launch latency and prologues are a visible share of the step (N = 20 000: 69 -> 66 us,
   // N = 5 000: 64 -> 57 us); with early-resident successors it costs 1 % at N = 100 000, 2 % at 200 000 and 3-7 % at 1M
   // (profiles/ab_pdl.py), so only batches of up to two tiles per SM use it by default.
-  const bool pdl = g_tc_bwd_pdl == 2 || (g_tc_bwd_pdl == 1 && (n + kBTile - 1) / kBTile <= static_cast<int64_t>(2) * sm_count());
+  const int pdl_mode = dependent_launch_mode(net);
+  const bool pdl = pdl_mode == 2 || (pdl_mode == 1 && (n + kBTile - 1) / kBTile <= static_cast<int64_t>(2) * sm_count());
   static bool carve_set[64] = {false};
   int devi = 0;
   if (cudaGetDevice(&devi) == cudaSuccess && devi >= 0 && devi < 64 && !carve_set[devi]) {
@@ -1107,15 +1109,3 @@ extern "C" int pinn_debug_timeline_phases(long long* host_out) {
   return static_cast<int>(cudaMemcpyFromSymbol(host_out, pinn::g_tlp, sizeof(pinn::g_tlp)));
 }
 #endif
-// Ablation switch: launch K2a / K2b / reduce with (1, default) or without programmatic stream serialization.
-extern "C" int pinn_set_dependent_launch(int enable) {
-  int prev = pinn::g_tc_bwd_pdl;
-  pinn::g_tc_bwd_pdl = enable < 0 ? 0 : (enable > 2 ? 2 : enable);      // 0 off, 1 small batches only (default), 2 always
-  return prev;
-}
-// Ablation / test switch for the tensor-core backward path (1 = on).
-extern "C" int pinn_set_tensor_core_bwd(int enable) {
-  int prev = pinn::g_tc_bwd_enabled;
-  pinn::g_tc_bwd_enabled = enable ? 1 : 0;
-  return prev;
-}

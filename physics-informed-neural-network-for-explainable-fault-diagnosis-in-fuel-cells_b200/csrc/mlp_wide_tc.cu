@@ -62,6 +62,7 @@ struct WideArgs {
   int64_t T_chunks;            // total 16-sample chunks (= 8 * tiles): block stride of an A-side copy
   const unsigned char* act;    // EPI_DV0 / EPI_DZ: saved K-major planes of the activation whose (1 - a^2) multiplies the delta
   const float* y; const float* grad_u; const float* grad_s; float inv_n_global;     // EPI_V1_TRAIN: loss gradient source
+  int no_logvar;               // DNN(logvar=False): log-variance output identically 0 (PINN_NET_NO_LOGVAR)
   float* du;                   // EPI_V1_TRAIN writes d loss / d u per sample; EPI_DV0 reads it
   float* tail_partial;         // EPI_V1_TRAIN: [tile][N + 1] sums of dv * a1[k] and of dv
   double* loss_partial;        // EPI_V1_TRAIN: [tile][4]
@@ -424,7 +425,7 @@ wide_gemm_kernel(const __grid_constant__ DropParams dp, WideArgs a) {
             vraw = fmaf(__ldg(a.w2 + c0 + q), tanh_pre((z[q] + __ldg(a.bias + c0 + q)) * kTanhArg), vraw);
         }
         if (valid) {
-          const float lv = logvar_from_v(vraw), u = a.u_io[s];
+          const float lv = logvar_out(vraw, a.no_logvar != 0), u = a.u_io[s];
           if (a.mode == 0) { a.out_u[s] = u; a.out_s[s] = lv; }
           else if (a.mode == 1) { a.pred_mean[s] = u; }
           else {
@@ -459,7 +460,7 @@ wide_gemm_kernel(const __grid_constant__ DropParams dp, WideArgs a) {
           for (int q = 0; q < 16; ++q)
             vraw = fmaf(__ldg(a.w2 + c0 + q), tanh_pre((z[q] + __ldg(a.bias + c0 + q)) * kTanhArg), vraw);
         }
-        const float lv = logvar_from_v(vraw);
+        const float lv = logvar_out(vraw, a.no_logvar != 0);
         float du = 0.f, ds = 0.f;
         double l4[4] = {0.0, 0.0, 0.0, 0.0};
         if (valid) {
@@ -476,7 +477,7 @@ wide_gemm_kernel(const __grid_constant__ DropParams dp, WideArgs a) {
             l4[3] = 1.0;
           }
         }
-        const float dv = ds * dlogvar_dv(vraw);
+        const float dv = a.no_logvar ? 0.f : ds * dlogvar_dv(vraw);
         a.du[s < a.n ? s : a.n] = du;               // slot n = scratch for the tail rows of the last tile
         unsigned char* tp = a.out + static_cast<size_t>(tile) * w_tile_bytes(N);
 #pragma unroll 1
@@ -626,12 +627,11 @@ wide_tail_reduce_kernel(const float* __restrict__ tail_partial, const double* __
 }
 
 // ------------------------------------------------------------------ host side
-static int g_wide_tc_enabled = 1;
 // Programmatic dependent launch for the per-layer launches of a small batch (every kernel of this file starts with
 // griddep_launch + griddep_wait: stream order is kept, only the launch latency and CTA scheduling of the successor overlap
-// the predecessor's tail).  Same size rule and switch as the 64-wide training step (pinn_set_dependent_launch).
-static bool wide_pdl(int64_t n) {
-  const int mode = dependent_launch_mode();
+// the predecessor's tail).  Same size rule and per-call flags as the 64-wide training step (pinn_net_t.flags).
+static bool wide_pdl(const pinn_net_t* net, int64_t n) {
+  const int mode = dependent_launch_mode(net);
   return mode == 2 || (mode == 1 && (n + kWT - 1) / kWT <= static_cast<int64_t>(2) * sm_count());
 }
 
@@ -658,7 +658,7 @@ static WidePlan<H> wide_plan(int L, int64_t n) {
   return p;
 }
 size_t wide_tc_workspace_bytes(int H, int L, int64_t n) {
-  if (!g_wide_tc_enabled || n <= 0) return 0;
+  if (n <= 0) return 0;
   if (H == 256) return wide_plan<256>(L, n).bytes;
   if (H == 128) return wide_plan<128>(L, n).bytes;
   return 0;
@@ -671,7 +671,7 @@ static int run_wide(bool mc, const pinn_net_t* net, const float* x, int64_t n, i
   const int L = net->n_hidden;
   const WidePlan<H> p = wide_plan<H>(L, n);
   if (!workspace || workspace_bytes < p.bytes) return PINN_E_WORKSPACE;
-  const bool pdl = wide_pdl(n);
+  const bool pdl = wide_pdl(net, n);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   const int tiles = static_cast<int>((n + kWT - 1) / kWT);
   const bool drop_on = dp.p > 0.f;
@@ -705,6 +705,7 @@ static int run_wide(bool mc, const pinn_net_t* net, const float* x, int64_t n, i
     WideArgs a{};
     a.n = n;
     a.mask_row_bytes = L * H + H / 2;
+    a.no_logvar = (net->flags & PINN_NET_NO_LOGVAR) ? 1 : 0;
     a.active = drop_on && !eval_pass ? 1 : 0;
     a.pass = mc ? (do_eval ? pi - 1 : pi) : 0;
     if (a.pass < 0) a.pass = 0;
@@ -739,7 +740,7 @@ static int run_wide(bool mc, const pinn_net_t* net, const float* x, int64_t n, i
 int launch_wide_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, const DropParams& dp, const TcOut& out,
                    void* workspace, size_t workspace_bytes, cudaStream_t st, int* err) {
   *err = 0;
-  if (!g_wide_tc_enabled || (net->width != 256 && net->width != 128) || net->n_hidden < 1) return 0;
+  if ((net->flags & PINN_NET_NO_WIDE_TC) || (net->width != 256 && net->width != 128) || net->n_hidden < 1) return 0;
   if (mc && T <= 0) return 0;
   for (int l = 1; l < net->n_hidden; ++l)
     if (!aligned16(net->W[l])) return 0;
@@ -754,7 +755,6 @@ int launch_wide_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, in
 // forward with every layer's planes kept (K-major for the dgrad epilogues, transposed for the weight gradients) ->
 // variance-head tail + loss gradient -> dgrad GEMMs back through the heads and the trunk, each followed by the
 // weight-gradient GEMM of the layer it just produced the deltas of.
-static int g_wide_tc_bwd_enabled = 1;
 
 template <int H>
 struct WideBwdPlan {
@@ -797,13 +797,13 @@ static WideBwdPlan<H> wide_bwd_plan(int L, int64_t n) {
   return p;
 }
 size_t wide_tc_bwd_workspace_bytes(int H, int L, int64_t n) {
-  if (!g_wide_tc_bwd_enabled || n <= 0) return 0;
+  if (n <= 0) return 0;
   if (H == 256) return wide_bwd_plan<256>(L, n).bytes;
   if (H == 128) return wide_bwd_plan<128>(L, n).bytes;
   return 0;
 }
 bool wide_tc_bwd_covers(const pinn_net_t* net) {
-  if (!g_wide_tc_bwd_enabled || (net->width != 256 && net->width != 128) || net->n_hidden < 1) return false;
+  if ((net->flags & PINN_NET_NO_WIDE_TC) || (net->width != 256 && net->width != 128) || net->n_hidden < 1) return false;
   for (int l = 0; l < net->n_hidden; ++l)
     if (!aligned16(net->W[l])) return false;
   return aligned16(net->Wv0) && aligned16(net->Wp) && aligned16(net->Wv1);
@@ -818,7 +818,7 @@ static int run_wide_bwd(const pinn_net_t* net, const float* x, int64_t n, const 
   const int L = net->n_hidden;
   const P p = wide_bwd_plan<H>(L, n);
   if (!workspace || workspace_bytes < p.bytes) return PINN_E_WORKSPACE;
-  const bool pdl = wide_pdl(n);
+  const bool pdl = wide_pdl(net, n);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   const ParamLayout lay = make_layout(H, L);
   const int tiles = static_cast<int>((n + kWT - 1) / kWT);
@@ -870,6 +870,7 @@ static int run_wide_bwd(const pinn_net_t* net, const float* x, int64_t n, const 
   WideArgs a{};
   a.n = n;
   a.mask_row_bytes = L * H + H / 2;
+  a.no_logvar = (net->flags & PINN_NET_NO_LOGVAR) ? 1 : 0;
   a.active = drop_on ? 1 : 0;
   a.pass = 0;
   a.inact = 1.0f;                      // training forward with p = 0: nothing folded, nothing to undo
@@ -962,10 +963,3 @@ int launch_wide_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const D
 
 }  // namespace pinn
 
-// Test / ablation switch: 0 routes the wide nets through the FFMA kernels.
-extern "C" int pinn_set_wide_tensor_core_path(int enable) {
-  int prev = pinn::g_wide_tc_enabled;
-  pinn::g_wide_tc_enabled = enable ? 1 : 0;
-  pinn::g_wide_tc_bwd_enabled = enable ? 1 : 0;
-  return prev;
-}

@@ -393,7 +393,6 @@ static int res_grid(int64_t n, int ctas_per_sm = kResCtasPerSm, int samples_per_
 // x / u / y never change during a phase, so after the first step they are served from L1 / L2.
 // Two partial buffers make one barrier per step enough: a CTA can be at most one step ahead of the
 // slowest one, so the buffer it writes is never the one a straggler still reads.
-static int g_phase_cluster = 1;      // ablation switch (pinn_set_phase_cluster)
 constexpr int kPhaseMaxThreads = 1024;
 constexpr int kPhaseMaxParams = 8;
 constexpr int kPhaseFold = 16;
@@ -593,7 +592,7 @@ static int launch_phase(PhaseArgs& a, size_t workspace_bytes, void* workspace, c
   const int sms = sm_count();
   // ---- one cluster (<= 8 CTAs x 1024 threads): batches of up to one sample per thread (with more work per thread the
   // 40-CTA grid form wins again: N = 20 000, voltage phase 5.6 us per step as a cluster vs 4.9 us as a grid)
-  if (g_phase_cluster && a.n <= static_cast<int64_t>(8) * kPhaseMaxThreads) {
+  if (!(a.flags & PINN_RES_NO_CLUSTER) && a.n <= static_cast<int64_t>(8) * kPhaseMaxThreads) {
     const int threads = a.n <= 4096 ? 512 : kPhaseMaxThreads;
     int csize = 1;
     while (csize < 8 && static_cast<int64_t>(csize) * threads < a.n) csize *= 2;
@@ -721,10 +720,3 @@ extern "C" int pinn_scalar_phase(const float* x, const float* u, const float* y,
   return PINN_E_ARG;
 }
 
-// Ablation / test switch: 1 (default) runs small batches of pinn_scalar_phase as one thread-block cluster, 0 always uses
-// the cooperative grid with the global-memory barrier.  Returns the previous setting.
-extern "C" int pinn_set_phase_cluster(int enable) {
-  int prev = pinn::g_phase_cluster;
-  pinn::g_phase_cluster = enable ? 1 : 0;
-  return prev;
-}

@@ -19,8 +19,8 @@ size_t wide_tc_bwd_workspace_bytes(int H, int L, int64_t n);
 int launch_wide_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropParams& dp, const float* grad_u, const float* grad_s,
                        const float* y, int64_t n_global, float* grad_flat, double* loss_sums, void* workspace, size_t workspace_bytes,
                        cudaStream_t st);
-// pinn_set_dependent_launch's current mode: 0 never, 1 small batches, 2 always (mlp_tc_bwd.cu)
-int dependent_launch_mode();
+// dependent-launch mode of this call (pinn_net_t.flags): 0 never, 1 small batches, 2 always (mlp_tc_bwd.cu)
+int dependent_launch_mode(const pinn_net_t* net);
 // Tensor-core backward (mlp_tc_bwd.cu): 64-wide nets with 2..4 hidden layers.
 bool tc_bwd_covers(const pinn_net_t* net);
 size_t tc_bwd_workspace_bytes(int L, int64_t n);

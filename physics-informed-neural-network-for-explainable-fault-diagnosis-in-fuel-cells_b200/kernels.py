@@ -3,6 +3,7 @@ streams; every computation below is a call into ``libb200pinn.so``."""
 from __future__ import annotations
 
 import ctypes as C
+from contextlib import contextmanager
 from dataclasses import dataclass
 from typing import Optional
 
@@ -49,15 +50,59 @@ class Net:
     width: int
     n_hidden: int
     tensors: list
+    base_flags: int = 0
+
+    def ref(self):
+        """``byref`` of the descriptor with this call's option bits (model flags | active ``path_flags``)."""
+        self.desc.flags = self.base_flags | _EXTRA_NET_FLAGS
+        return C.byref(self.desc)
 
     @property
     def mask_width(self) -> int:
         return self.n_hidden * self.width + self.width // 2
 
 
+# Per-call option bits (``pinn_net_t.flags``) OR-ed into every descriptor built while a ``path_flags`` block is
+# active: ablation runs and tests route a shape through another kernel family without any state in the library.
+_EXTRA_NET_FLAGS = 0
+_PHASE_FLAGS = 0
+
+
+@contextmanager
+def path_flags(no_tc_fwd=False, no_tc_bwd=False, no_wide_tc=False, dependent_launch=None, no_phase_cluster=False):
+    """``with path_flags(no_tc_fwd=True): ...`` -- inside the block the 64-wide forward / MC sweep run on the FFMA
+    kernels (likewise ``no_tc_bwd``, ``no_wide_tc``); ``dependent_launch`` = 0 never / 2 always chain a step's launches
+    with programmatic dependent launch (default 1: small batches only); ``no_phase_cluster`` keeps ``scalar_phase`` on
+    the cooperative-grid form."""
+    global _EXTRA_NET_FLAGS, _PHASE_FLAGS
+    prev = (_EXTRA_NET_FLAGS, _PHASE_FLAGS)
+    f = (_abi.NET_NO_TC_FWD if no_tc_fwd else 0) | (_abi.NET_NO_TC_BWD if no_tc_bwd else 0) | \
+        (_abi.NET_NO_WIDE_TC if no_wide_tc else 0)
+    if dependent_launch is not None:
+        f |= {0: _abi.NET_PDL_NEVER, 1: 0, 2: _abi.NET_PDL_ALWAYS}[int(dependent_launch)]
+    _EXTRA_NET_FLAGS |= f
+    if no_phase_cluster:
+        _PHASE_FLAGS |= _abi.RES_NO_CLUSTER
+    try:
+        yield
+    finally:
+        _EXTRA_NET_FLAGS, _PHASE_FLAGS = prev
+
+
+def set_default_path_flags(**kw):
+    """Non-scoped form of ``path_flags`` for ablation scripts (``profiles/``): replaces the process defaults held in
+    this Python module -- the shared library itself has no switches."""
+    global _EXTRA_NET_FLAGS, _PHASE_FLAGS
+    _EXTRA_NET_FLAGS = _PHASE_FLAGS = 0
+    cm = path_flags(**kw)
+    cm.__enter__()          # never exited: the flags stay until the next call
+
+
 def net_from_module(dnn) -> Net:
     """Build the descriptor from any module with the reference's DNN structure
-    (``layers.layer_i``, ``predict``, ``var_layers.{0,3,5}``) -- ours or the reference's."""
+    (``layers.layer_i``, ``predict``, ``var_layers.{0,3,5}``) -- ours or the reference's.  A module
+    constructed with ``logvar=False`` (01:436) gets ``NET_NO_LOGVAR``: the kernels then treat the
+    log-variance as identically zero (loss, gradients, a_u)."""
     L = dnn.depth - 1
     lin = [getattr(dnn.layers, f"layer_{i}") for i in range(L)]
     H = lin[0].out_features
@@ -78,7 +123,7 @@ def net_from_module(dnn) -> Net:
     d.Wv0, d.bv0 = heads[1].weight.data_ptr(), heads[1].bias.data_ptr()
     d.Wv1, d.bv1 = heads[2].weight.data_ptr(), heads[2].bias.data_ptr()
     d.Wv2, d.bv2 = heads[3].weight.data_ptr(), heads[3].bias.data_ptr()
-    return Net(d, H, L, tensors)
+    return Net(d, H, L, tensors, _abi.NET_NO_LOGVAR if getattr(dnn, "logvar", True) is False else 0)
 
 
 def param_layout(width: int, n_hidden: int):
@@ -128,7 +173,7 @@ def mlp_forward(net: Net, x: torch.Tensor, drop: Optional[PinnDropout] = None):
     nb = L.pinn_mlp_fwd_workspace_bytes(net.width, net.n_hidden, n)
     ws = _workspace("fwd", nb, x.device)
     with torch.cuda.device(x.device):
-        check(L.pinn_mlp_fwd(C.byref(net.desc), ptr(x), n, C.byref(drop) if drop is not None else None,
+        check(L.pinn_mlp_fwd(net.ref(), ptr(x), n, C.byref(drop) if drop is not None else None,
                              ptr(u), ptr(s), ptr(ws), nb, _stream()), "pinn_mlp_fwd")
     LAUNCHES += 1
     return u, s
@@ -156,7 +201,7 @@ def mlp_backward(net: Net, x: torch.Tensor, drop: Optional[PinnDropout], grad_u=
             if not t.is_contiguous():
                 raise RuntimeError(f"b200pinn: `{nm}` must be contiguous")
     with torch.cuda.device(x.device):
-        check(L.pinn_mlp_bwd(C.byref(net.desc), ptr(x), n, C.byref(drop) if drop is not None else None,
+        check(L.pinn_mlp_bwd(net.ref(), ptr(x), n, C.byref(drop) if drop is not None else None,
                              ptr(grad_u), ptr(grad_logvar), ptr(y), int(n_global), ptr(grad_flat),
                              ptr(loss_sums), ptr(ws), nb, _stream()), "pinn_mlp_bwd")
     LAUNCHES += 2
@@ -238,37 +283,12 @@ def mc_dropout(net: Net, x: torch.Tensor, T: int, drop: PinnDropout, finalize: b
     nb = L.pinn_mc_workspace_bytes(net.width, net.n_hidden, n)
     ws = _workspace("mc", nb, dev)
     with torch.cuda.device(dev):
-        check(L.pinn_mc_dropout(C.byref(net.desc), ptr(x), n, int(T), C.byref(drop), ptr(out["pred_mean"]),
+        check(L.pinn_mc_dropout(net.ref(), ptr(x), n, int(T), C.byref(drop), ptr(out["pred_mean"]),
                                 ptr(out.get("a_u")), ptr(out.get("e_u")), ptr(out.get("mean")),
                                 ptr(out.get("m2")), ptr(out.get("sum_logvar")), ptr(ws), nb, _stream()),
               "pinn_mc_dropout")
     LAUNCHES += 1
     return out
-
-
-def set_tensor_core_path(enable: bool) -> bool:
-    """Ablation switch (tests): route the 64-wide net through the FFMA kernels when False."""
-    return bool(_abi.lib().pinn_set_tensor_core_path(1 if enable else 0))
-
-
-def set_wide_tensor_core_path(enable: bool) -> bool:
-    """Ablation switch (tests): route the 128/256-wide nets' forward / MC sweep through the FFMA kernels when False."""
-    return bool(_abi.lib().pinn_set_wide_tensor_core_path(1 if enable else 0))
-
-
-def set_tensor_core_bwd(enable: bool) -> bool:
-    """Ablation switch (tests): route the 64-wide net's backward through the FFMA kernel when False."""
-    return bool(_abi.lib().pinn_set_tensor_core_bwd(1 if enable else 0))
-
-
-def set_dependent_launch(mode) -> int:
-    """Ablation switch: chain K2a / K2b / reduce with programmatic dependent launch -- 0 never, 1 small batches (default), 2 always."""
-    return int(_abi.lib().pinn_set_dependent_launch(int(mode)))
-
-
-def set_phase_cluster(enable: bool) -> bool:
-    """Ablation switch: small batches of ``scalar_phase`` as one thread-block cluster (default) or as a cooperative grid."""
-    return bool(_abi.lib().pinn_set_phase_cluster(1 if enable else 0))
 
 
 def new_step_counter(device) -> torch.Tensor:
@@ -335,7 +355,8 @@ def scalar_phase(x, u, y, scalers: PinnScalers, lambdas, families: int, flags: i
     nb = L.pinn_scalar_phase_workspace_bytes()
     ws = _workspace("phase", nb, x.device, zero=True)
     with torch.cuda.device(x.device):
-        check(L.pinn_scalar_phase(ptr(x), ptr(u), ptr(y), x.shape[0], C.byref(scalers), ptr(lambdas), families, flags,
+        check(L.pinn_scalar_phase(ptr(x), ptr(u), ptr(y), x.shape[0], C.byref(scalers), ptr(lambdas), families,
+                                  int(flags) | _PHASE_FLAGS,
                                   int(first), cnt, c_slot, c_lo, c_hi, ptr(exp_avg), ptr(exp_avg_sq), ptr(step_counter),
                                   float(lr0), float(gamma), int(step_size), int(n_steps), ptr(sums), ptr(ws), nb,
                                   _stream()), "pinn_scalar_phase")
@@ -358,7 +379,7 @@ def train_dnn_step(net: Net, x, drop: Optional[PinnDropout], y, n_global: int, p
     nb = L.pinn_mlp_bwd_workspace_bytes(net.width, net.n_hidden, n)
     ws = _workspace("bwd", nb, x.device)
     with torch.cuda.device(x.device):
-        check(L.pinn_train_dnn_steps(C.byref(net.desc), ptr(x), n, C.byref(drop) if drop is not None else None, ptr(y),
+        check(L.pinn_train_dnn_steps(net.ref(), ptr(x), n, C.byref(drop) if drop is not None else None, ptr(y),
                                      int(n_global), ptr(params_flat), ptr(exp_avg), ptr(exp_avg_sq), ptr(step_counter),
                                      float(lr0), float(gamma), int(step_size), int(n_steps), ptr(grad_flat), ptr(loss_sums),
                                      ptr(ws), nb, _stream()), "pinn_train_dnn_steps")

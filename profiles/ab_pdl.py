@@ -17,7 +17,7 @@ m = b200pinn.PhysicsInformedNN(torch.tensor(x), torch.tensor(y), [8] + [width] *
 m.train_dnn(5, verbose=False)
 for rep in range(3):
     for mode in (0, 2):
-        K.set_dependent_launch(mode)
+        K.set_default_path_flags(dependent_launch=mode)
         m.train_dnn(3, verbose=False)
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -19,7 +19,7 @@ phases = [("train_lambda(A)", lambda k: m.train_lambda(k, False, verbose=False))
 from b200pinn import kernels as K
 for mode, cluster in (("1", True), ("1", False), ("0", True)):
     os.environ["B200PINN_PHASE_KERNEL"] = mode
-    K.set_phase_cluster(cluster)
+    K.set_default_path_flags(no_phase_cluster=not cluster)
     for name, fn in phases:
         fn(3)
         for rep in range(2):

@@ -15,7 +15,7 @@ x, y, sx, sy = make_scaled_dataset(n, seed=1)
 torch.manual_seed(0)
 m = b200pinn.PhysicsInformedNN(torch.tensor(x), torch.tensor(y), [8] + [width] * hidden + [1], sx, sy, 0.2, True)
 if os.environ.get("B200PINN_PDL", "1") == "0":
-    b200pinn.kernels.set_dependent_launch(0)
+    b200pinn.kernels.set_default_path_flags(dependent_launch=0)
 m.train_dnn(5, verbose=False)
 torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -48,7 +48,9 @@ def test_library_exports_every_declared_symbol():
     for fn in fns:
         assert hasattr(lib, fn), f"{fn} declared in b200pinn.h but not exported"
     assert sorted(abi.EXPORTS) == fns, "ctypes signature table out of sync with the header"
-    assert abi.lib().pinn_abi_version() == 1
+    assert abi.lib().pinn_abi_version() == abi.ABI_VERSION == int(re.search(r"#define PINN_ABI_VERSION (\d+)", header_text()).group(1))
+    # the library keeps no process-global switches: path selection travels in pinn_net_t.flags / `flags`
+    assert not [f for f in fns if f.startswith("pinn_set_")]
 
 
 def test_python_constants_match_header():
@@ -61,8 +63,12 @@ def test_python_constants_match_header():
     assert c.pop("PINN_C_COUNT") == abi.C_COUNT
     assert {k[len("PINN_C_"):]: v for k, v in c.items()} == abi.COL
     r = enum_values("PINN_RES_")
-    assert (r["PINN_RES_ACCURATE_MATH"], r["PINN_RES_NO_MODE_A"], r["PINN_RES_NO_MODE_B"]) == \
-        (abi.RES_ACCURATE_MATH, abi.RES_NO_MODE_A, abi.RES_NO_MODE_B)
+    assert (r["PINN_RES_ACCURATE_MATH"], r["PINN_RES_NO_MODE_A"], r["PINN_RES_NO_MODE_B"], r["PINN_RES_NO_CLUSTER"]) == \
+        (abi.RES_ACCURATE_MATH, abi.RES_NO_MODE_A, abi.RES_NO_MODE_B, abi.RES_NO_CLUSTER)
+    nf = enum_values("PINN_NET_")
+    assert nf == {"PINN_NET_NO_TC_FWD": abi.NET_NO_TC_FWD, "PINN_NET_NO_TC_BWD": abi.NET_NO_TC_BWD,
+                  "PINN_NET_NO_WIDE_TC": abi.NET_NO_WIDE_TC, "PINN_NET_PDL_NEVER": abi.NET_PDL_NEVER,
+                  "PINN_NET_PDL_ALWAYS": abi.NET_PDL_ALWAYS, "PINN_NET_NO_LOGVAR": abi.NET_NO_LOGVAR}
     f = enum_values("PINN_FAM_")
     assert (f["PINN_FAM_V"], f["PINN_FAM_TS"], f["PINN_FAM_T"], f["PINN_FAM_H"], f["PINN_FAM_O"],
             f["PINN_FAM_DATA"]) == (abi.FAM_V, abi.FAM_TS, abi.FAM_T, abi.FAM_H, abi.FAM_O, abi.FAM_DATA)

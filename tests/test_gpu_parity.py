@@ -262,11 +262,8 @@ def test_persistent_phase_kernel_matches_step_by_step_path(n, monkeypatch):
     snap_p, lam_p, loss_p = run("1")                 # n <= 32 768: one thread-block cluster; above: cooperative grid
     snap_s, lam_s, loss_s = run("0")
     if n <= 32768:                                    # the grid-barrier form at the same size
-        K.set_phase_cluster(False)
-        try:
+        with K.path_flags(no_phase_cluster=True):
             snap_g, lam_g, loss_g = run("1")
-        finally:
-            K.set_phase_cluster(True)
         assert np.allclose(snap_g[0], snap_s[0], rtol=2e-5, atol=1e-9), (snap_g[0], snap_s[0])
         assert np.allclose(lam_g[4:], lam_s[4:], rtol=2e-5, atol=2e-6), (lam_g, lam_s)
         assert np.allclose(loss_g[4:], loss_s[4:], rtol=2e-5), (loss_g, loss_s)
@@ -610,9 +607,8 @@ def ffma_path():
     """Route the 64-wide net through the fp32 FFMA kernels for the duration of a test."""
     from b200pinn import kernels as K
 
-    prev = K.set_tensor_core_path(False)
-    yield
-    K.set_tensor_core_path(prev)
+    with K.path_flags(no_tc_fwd=True):
+        yield
 
 
 def test_golden_forward_and_mc_on_ffma_path(ffma_path):
@@ -649,11 +645,8 @@ def test_tensor_core_path_matches_ffma_path_and_oracle(layers):
     xd = torch.tensor(x, device=dev())
     dnn = random_net(layers, 5).eval()
     a = b200pinn.mc_dropout_device(dnn, xd, T, p, seed=77, raw=True)
-    prev = K.set_tensor_core_path(False)
-    try:
+    with K.path_flags(no_tc_fwd=True):
         b = b200pinn.mc_dropout_device(dnn, xd, T, p, seed=77, raw=True)
-    finally:
-        K.set_tensor_core_path(prev)
     for k in ("pred_mean", "mean", "a_u", "e_u"):
         assert nrel(t2n(a[k]), t2n(b[k])) < 5e-6, k
     mk = rand_masks(np.random.default_rng(3), T, n, layers, p)
@@ -666,9 +659,8 @@ def test_tensor_core_path_matches_ffma_path_and_oracle(layers):
 def ffma_bwd():
     from b200pinn import kernels as K
 
-    prev = K.set_tensor_core_bwd(False)
-    yield
-    K.set_tensor_core_bwd(prev)
+    with K.path_flags(no_tc_bwd=True):
+        yield
 
 
 def test_golden_backward_on_ffma_path(ffma_bwd):
@@ -704,11 +696,8 @@ def test_tensor_core_backward_matches_ffma_and_oracle(layers, n):
     xd, yd = torch.tensor(x, device=dev()), torch.tensor(y, device=dev()).reshape(-1).contiguous()
     p = 0.2
     a, sa = K.mlp_backward(net, xd, K.make_dropout(p, seed=5, pass_offset=3), y=yd, n_global=n)
-    prev = K.set_tensor_core_bwd(False)
-    try:
+    with K.path_flags(no_tc_bwd=True):
         b, sb = K.mlp_backward(net, xd, K.make_dropout(p, seed=5, pass_offset=3), y=yd, n_global=n)
-    finally:
-        K.set_tensor_core_bwd(prev)
     assert np.allclose(t2n(sa), t2n(sb), rtol=1e-5)
     names, shapes, offs, _ = K.param_layout(net.width, net.n_hidden)
     fa, fb = t2n(a), t2n(b)
@@ -744,11 +733,8 @@ def test_tensor_core_backward_tile_edges(n):
     net = K.net_from_module(dnn)
     xd, yd = torch.tensor(x, device=dev()), torch.tensor(y, device=dev()).reshape(-1).contiguous()
     a, sa = K.mlp_backward(net, xd, K.make_dropout(p, seed=11, pass_offset=2), y=yd, n_global=n)
-    prev = K.set_tensor_core_bwd(False)
-    try:
+    with K.path_flags(no_tc_bwd=True):
         b, sb = K.mlp_backward(net, xd, K.make_dropout(p, seed=11, pass_offset=2), y=yd, n_global=n)
-    finally:
-        K.set_tensor_core_bwd(prev)
     assert np.allclose(t2n(sa), t2n(sb), rtol=1e-5)
     names, shapes, offs, _ = K.param_layout(net.width, net.n_hidden)
     fa, fb = t2n(a), t2n(b)
@@ -782,11 +768,8 @@ def test_mc_tensor_core_tile_edges(n, T):
     xd = torch.tensor(x[:n], device=dev())
     dnn = random_net(layers, 10)
     a = b200pinn.mc_dropout_device(dnn, xd, T, p, seed=77)
-    prev = K.set_tensor_core_path(False)
-    try:
+    with K.path_flags(no_tc_fwd=True):
         b = b200pinn.mc_dropout_device(dnn, xd, T, p, seed=77)
-    finally:
-        K.set_tensor_core_path(prev)
     for k in ("pred_mean", "a_u", "e_u"):
         assert nrel(t2n(a[k]), t2n(b[k])) < MC_TOL, k
 
@@ -841,11 +824,8 @@ def test_wide_tensor_core_path_matches_ffma_path(layers, n, T):
         return [t2n(v) for v in (u0, s0, u1, s1, mc["pred_mean"], mc["a_u"], mc["e_u"])]
 
     a = run()
-    prev = K.set_wide_tensor_core_path(False)
-    try:
+    with K.path_flags(no_wide_tc=True):
         b = run()
-    finally:
-        K.set_wide_tensor_core_path(prev)
     # two fp32 evaluations against each other (not against fp64): six 256-wide layers with a near-cancelling
     # output leave ~1e-5 of rounding noise between them; the fp64 comparison is test_forward_backward_vs_oracle
     tol = MC_TOL * (3.0 if len(layers) > 6 else 1.0)
@@ -879,11 +859,8 @@ def test_wide_tensor_core_backward_matches_ffma_path(layers, n):
         return t2n(a).copy(), t2n(sa).copy(), t2n(b).copy()
 
     a = run()
-    prev = K.set_wide_tensor_core_path(False)
-    try:
+    with K.path_flags(no_wide_tc=True):
         b = run()
-    finally:
-        K.set_wide_tensor_core_path(prev)
     assert np.allclose(a[1], b[1], rtol=1e-5)
     names, shapes, offs, _ = K.param_layout(net.width, net.n_hidden)
     tol = GRAD_TOL * (3.0 if len(layers) > 6 else 1.0)          # fp32 vs fp32, see the forward test above
