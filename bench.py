@@ -2,16 +2,28 @@
 """bench.py -- the driver's measurement contract for the PINN hot path.
 
     python bench.py --gpus N --steps K --warmup W            (our CUDA path, one rank per GPU)
-    python bench.py --impl reference --gpus N --steps K ...   (reference algorithm on host cores)
+    python bench.py --impl reference --gpus N --steps K ...   (the reference's own classes on host cores)
 
-Workload (BASELINE.json configs[1]): the 3x64 stack-voltage PINN on N = 1M synthetic
-normal-operation samples per GPU.  One "step" is one MC-dropout sweep of T = 50 stochastic
-passes over that batch (kernel K4) -- `metric` is MC-dropout sample*passes/s; the same JSON
-line also carries PINN train steps/s (K2 + reduce + Adam) and the lambda-phase step (K3).
+Headline (`value`): MC-dropout sample*passes/s of the 3x64 stack-voltage PINN on N = 1M synthetic
+normal-operation samples per GPU (the batch of BASELINE.json configs[1]), one "step" = one sweep of
+T = 50 stochastic passes (configs[0]'s T) = one launch of kernel K4.  This is not itself one of the
+BASELINE configs; the configs are carried by blocks of the same JSON line:
+
+    c1     configs[0]  N = 20 000, every trainer's step time + the reference's whole schedule
+    train  configs[1]  N = 1M/GPU full-batch train_dnn step (K2 + reduce + Adam), steps/s, weak efficiency
+    c3     configs[2]  MC sweep T = 1000 x N = 1M TOTAL, sample-sharded over --gpus (strong scaling), gathered
+    c4     configs[3]  6x256 data-parallel train step at 512k samples per GPU (batch 4M on 8 GPUs)
+    fleet  configs[4]  per-GPU share of the 64-stack export + RF(t)
+
 `value` is timed with inputs resident in HBM; `e2e` is the same sweep through the public
-`get_MC_samples` with HOST tensors (H2D of X and D2H of the three result vectors inside).
+`get_MC_samples` with HOST tensors (H2D of X and D2H of the three result vectors inside the timed
+region).  `cpu_baseline` / `--impl reference` run the UNMODIFIED reference (oracle/_ref, staged by
+__graft_entry__.build()) on the host cores; `gpu_eager_baseline` runs the same unmodified classes on
+eager PyTorch-CUDA on this B200 (the reference's own GPU path, 01:21-24).
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import statistics
@@ -33,6 +45,17 @@ FLOP_PER_TRAIN_SAMPLE = 67_040     # SURVEY 8d, fwd + dgrad + wgrad
 RES_BYTES_PER_SAMPLE = 40          # x row 32 B + u 4 B + y 4 B (train_lambda form)
 METRIC = "mc_dropout_sample_passes_per_s"
 UNIT = "sample*passes/s"
+NCU_FILE = os.path.join(ROOT, "profiles", "ncu_current.json")
+
+
+def workload_config(n, world):
+    """The `config` block: identical for the product arm and the reference arm (same workload, same sizes)."""
+    return {"workload": "MC-dropout sweep, T=50 passes over N=1M samples per GPU, 3x64 PINN (layers [8,64,64,64,1]): the batch of "
+                        "BASELINE configs[1] swept with configs[0]'s T -- not itself a BASELINE config (configs[2] = block c3, "
+                        "configs[1] training = block train, configs[3] = c4, configs[4] = fleet, configs[0] = c1)",
+            "layers": LAYERS, "n_per_gpu": n, "T": T_PASSES, "dropout": P_MC,
+            "sharding": "samples" if world > 1 else "none",
+            "l2": "256 MB buffer written between timed steps (inputs 32 MB < 126 MB L2)"}
 
 
 def peaks():
@@ -42,6 +65,16 @@ def peaks():
             p = json.load(f)
         return dict(hbm=float(p["hbm_gbs"]), bf16=float(p["bf16_tflops"]), src="measured (MEASURED_PEAKS.json, burst)")
     return dict(hbm=6650.0, bf16=1590.0, src="fallback (B200_PROFILING.md)")
+
+
+def ncu_record(kernel):
+    """Counters of `kernel` from profiles/ncu_current.json (written by profiles/ncu_to_json.py from an `ncu --set full`
+    capture of THIS build); None when no capture is on file -- nothing here is a literal."""
+    try:
+        with open(NCU_FILE) as f:
+            return json.load(f).get(kernel)
+    except (OSError, ValueError):
+        return None
 
 
 class ClockSampler:
@@ -98,61 +131,129 @@ def build_problem(n, seed):
     return torch.tensor(x), torch.tensor(y), sx, sy
 
 
-# ------------------------------------------------------------------------- reference arm
-def cpu_port_rates(n_mc, n_train, threads):
-    """Time the reference algorithm (oracle/torch_port.py) on the host cores: one
-    get_MC_samples with T'=1 and one train_dnn step."""
-    import torch
-    from oracle.torch_port import PortPINN, get_MC_samples_port
+@contextlib.contextmanager
+def quiet():
+    with contextlib.redirect_stdout(io.StringIO()):
+        yield
 
+
+# ------------------------------------------------------------------------- reference classes
+def reference_classes(device):
+    """(module-like namespace, kind): the unmodified reference (oracle/_ref) when staged, else the op-for-op port."""
+    from oracle import ref_loader
+
+    if ref_loader.available():
+        with quiet():
+            return ref_loader.load("01", device=device), "reference"
+    if device != "cpu":
+        return None, "unavailable"
+    from oracle import torch_port as P
+    import types
+
+    ns = types.SimpleNamespace(
+        PhysicsInformedNN=lambda X, u, layers, xs, us, p, logvar: P.PortPINN(X, u, layers, xs, us, p),
+        get_MC_samples=P.get_MC_samples_port)
+    return ns, "port"
+
+
+def cpu_reference_rates(X, Y, sx, sy, n_mc, n_train, threads):
+    """The reference's own hot loops on the host cores: one get_MC_samples with T'=1 at n_mc rows and train_dnn steps
+    at n_train rows."""
+    import torch
+
+    ref, kind = reference_classes("cpu")
     torch.set_num_threads(threads)
-    X, Y, sx, sy = build_problem(max(n_mc, n_train), 2)
     torch.manual_seed(0)
-    net = PortPINN(X[:n_mc], Y[:n_mc], LAYERS, sx, sy, P_TRAIN)
-    get_MC_samples_port(net, X[:2000], sx, 1, P_MC)            # warm-up
-    t0 = time.perf_counter()
-    get_MC_samples_port(net, X[:n_mc], sx, 1, P_MC)
-    t_mc = time.perf_counter() - t0
-    tr = PortPINN(X[:n_train], Y[:n_train], LAYERS, sx, sy, P_TRAIN)
-    step = tr.make_dnn_trainer()
-    t0 = time.perf_counter()
-    step()
-    t_tr = time.perf_counter() - t0
-    return n_mc / t_mc, (n_train / N_PER_GPU) / t_tr * 1.0, t_mc, t_tr
+    with quiet():
+        net = ref.PhysicsInformedNN(X[:n_mc], Y[:n_mc], LAYERS, sx, sy, P_TRAIN, True)
+        ref.get_MC_samples(net, X[:2000], sx, 1, P_MC)            # warm-up
+        t0 = time.perf_counter()
+        ref.get_MC_samples(net, X[:n_mc], sx, 1, P_MC)
+        t_mc = time.perf_counter() - t0
+        tr = ref.PhysicsInformedNN(X[:n_train], Y[:n_train], LAYERS, sx, sy, P_TRAIN, True)
+        if kind == "reference":
+            tr.train_dnn(1)
+            t0 = time.perf_counter()
+            tr.train_dnn(2)
+            t_tr = (time.perf_counter() - t0) / 2
+        else:
+            step = tr.make_dnn_trainer()
+            step()
+            t0 = time.perf_counter()
+            step()
+            t_tr = time.perf_counter() - t0
+    return kind, n_mc / t_mc, 1.0 / t_tr, t_mc, t_tr
+
+
+def gpu_eager_rates(X, Y, sx, sy, n):
+    """The unmodified reference on eager PyTorch-CUDA on this GPU (its own device selection, 01:21-24): the MC sweep
+    with T'=4 and the train_dnn step at the same N.  Host tensors in, numpy out -- exactly how 01 calls it."""
+    import torch
+
+    ref, kind = reference_classes("cuda")
+    if ref is None:
+        return {"unavailable": "oracle/_ref not staged (run __graft_entry__.build() where /root/reference is mounted)"}
+    torch.manual_seed(0)
+    Tq = 4
+    with quiet():
+        model = ref.PhysicsInformedNN(X[:n], Y[:n], LAYERS, sx, sy, P_TRAIN, True)
+        ref.get_MC_samples(model, X[:20000], sx, 1, P_MC)         # warm-up (cuBLAS handles, allocator)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ref.get_MC_samples(model, X[:n], sx, Tq, P_MC)
+        torch.cuda.synchronize()
+        t_mc = time.perf_counter() - t0
+        model.train_dnn(3)
+        torch.cuda.synchronize()
+        k = 10
+        t0 = time.perf_counter()
+        model.train_dnn(k)
+        torch.cuda.synchronize()
+        t_tr = (time.perf_counter() - t0) / k
+        t0 = time.perf_counter()
+        model.train_lambda(k, True)
+        torch.cuda.synchronize()
+        t_lam = (time.perf_counter() - t0) / k
+    del model
+    torch.cuda.empty_cache()
+    return {"kind": kind, "what": "the unmodified reference classes (oracle/_ref) on eager PyTorch-CUDA, same B200, same N, host "
+                                  "tensors in / numpy out as 01:2141-2158 calls them",
+            "n": n, "mc_sample_passes_per_s": n * Tq / t_mc, "mc_sample": f"get_MC_samples T'={Tq} ({t_mc:.2f} s)",
+            "train_dnn_steps_per_s": 1.0 / t_tr, "train_dnn_ms_per_step": 1e3 * t_tr,
+            "train_lambda_ms_per_step": 1e3 * t_lam}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import io
-    import contextlib
     import torch
-    from oracle.torch_port import PortPINN, get_MC_samples_port
 
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    n = 200_000
+    n = args.n
     X, Y, sx, sy = build_problem(n, 2)
+    ref, kind = reference_classes("cpu")
     torch.manual_seed(0)
-    net = PortPINN(X, Y, LAYERS, sx, sy, P_TRAIN)
+    with quiet():
+        net = ref.PhysicsInformedNN(X, Y, LAYERS, sx, sy, P_TRAIN, True)
     times = []
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        with contextlib.redirect_stdout(io.StringIO()):
-            get_MC_samples_port(net, X, sx, 1, P_MC)
+        with quiet():
+            ref.get_MC_samples(net, X, sx, 1, P_MC)
         dt = time.perf_counter() - t0
         if it >= args.warmup:
             times.append(dt)
     total = sum(times)
     value = n * 1 * len(times) / total
-    sample = f"N={n} x T'=1 per step (1 eval pass + 1 dropout pass, each with the discarded 2nd forward, 01:1407)"
+    sample = (f"one step = get_MC_samples(mc_times=1) over the full N={n} batch: T'=1 of the workload's T={T_PASSES} passes (cost is "
+              "linear in T; 1 eval pass + 1 dropout pass, each with the discarded 2nd forward of predict(), 01:1407)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: 3x64 PINN, N=1M/GPU, MC-dropout sweep T=50 (CPU arm: bounded sample)",
-                       "layers": LAYERS, "dropout": P_MC},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "config": workload_config(n, 1),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -165,6 +266,7 @@ def run_ours(args):
 
     import b200pinn
     from b200pinn import _abi, kernels as K
+    from b200pinn.dist import gather_rows, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -227,6 +329,16 @@ def run_ours(args):
         tot = sum(a.elapsed_time(b) for a, b in evs) / 1e3
         return max_over_ranks(tot), K.LAUNCHES - launches0
 
+    def timed_block(fn, steps):
+        """`steps` back-to-back steps inside ONE pair of events (for loops whose launches are enqueued by one call)."""
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn(steps)
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b) / 1e3)
+
     sampler = ClockSampler(local) if rank == 0 else None
     # --- headline: MC-dropout sweep, inputs resident in HBM
     seed = 1234
@@ -234,16 +346,21 @@ def run_ours(args):
     t_mc, launches = timed(mc, K_, W_)
     clocks = sampler.stop() if sampler else None
     value = world * n * T_PASSES * K_ / t_mc
-    # --- train steps (K2 + reduce + [all-reduce] + Adam), back to back
+
+    # --- configs[1]: full-batch train_dnn steps (K2 + reduce + [gradient sum over NVLink fused into Adam] + Adam), back to back.
+    # Single-GPU step time is measured in the same job (data_parallel = False) so the weak-scaling efficiency of the ONE
+    # step that communicates is stated here, not only for the collective-free sweep.
     steps_tr = max(K_, 5)
+    model.data_parallel = False
     model.train_dnn(max(W_, 1), verbose=False)
-    barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    model.train_dnn(steps_tr, verbose=False)
-    b.record()
-    barrier()
-    t_tr = max_over_ranks(a.elapsed_time(b) / 1e3)
+    t_tr_local = timed_block(lambda k: model.train_dnn(k, verbose=False), steps_tr)
+    model.data_parallel = True
+    if world > 1:
+        model.train_dnn(max(W_, 1), verbose=False)
+        t_tr = timed_block(lambda k: model.train_dnn(k, verbose=False), steps_tr)
+    else:
+        t_tr = t_tr_local
+
     # --- lambda-phase step: residual kernel K3 (HBM-bound), L2 flushed every iteration.
     # (i) at the workload's N = 1M the kernel is a ~10 us launch (40 MB); (ii) the roofline
     # fraction is taken at 8M rows = config 5's per-GPU share (64 stacks x 1M / 8 GPUs), 320 MB.
@@ -268,6 +385,40 @@ def run_ours(args):
     res_exp = lambda: K.residuals(xb, ub, None, sc, lam, fam_all, sums=sums, cols=cols, want_cols=True)
     t_exp, _ = timed(res_exp, K_, W_)
     del xb, ub, yb, cols
+
+    # --- configs[2]: MC sweep T = 1000 over N = 1M samples IN TOTAL, sample-sharded over the ranks (strong scaling), the three
+    # result vectors gathered on every rank inside the timed region.  Every rank also times the unsharded sweep so that the
+    # strong-scaling efficiency t(1 GPU) / (world * t(world GPUs)) comes from one job.
+    T3, n3 = 1000, 1_000_000
+    X3 = X if (rank == 0 and n == n3) else build_problem(n3, 2)[0]
+    lo3, hi3 = shard_range(n3, rank, world)
+    x3_full = X3.to(dev)
+    x3 = x3_full[lo3:hi3].contiguous()
+
+    def sweep3(xs, off, gather):
+        o = b200pinn.mc_dropout_device(model.dnn, xs, T3, P_MC, seed=seed, sample_offset=off)
+        r = torch.stack([o["pred_mean"], o["a_u"], o["e_u"]], dim=1)
+        return gather_rows(r, n3) if gather else r
+
+    n_c3 = 3
+    t_c3, _ = timed(lambda: sweep3(x3, lo3, world > 1), n_c3, 1)
+    t_c3_one = t_c3
+    if world > 1:
+        t_c3_one, _ = timed(lambda: sweep3(x3_full, 0, False), n_c3, 1)
+    tiles3 = -(-(hi3 - lo3) // 128)
+    sm = _abi.lib().pinn_device_sm_count()
+    c3 = {"what": "configs[2]: MC-dropout sweep T=1000 x N=1M samples in total, sample-sharded over the GPUs (strong scaling); no "
+                  "data-path collective, the three result vectors are all-gathered inside the timed region; Philox counters are "
+                  "keyed on global (sample, pass), so every sharding gives the same numbers",
+          "T": T3, "n_total": n3, "rows_per_gpu": hi3 - lo3, "ms_per_sweep": 1e3 * t_c3 / n_c3,
+          "sample_passes_per_s": n3 * T3 * n_c3 / t_c3, "tflops": n3 * T3 * FLOP_PER_SAMPLE_PASS * n_c3 / t_c3 / 1e12,
+          "one_gpu_ms_per_sweep": 1e3 * t_c3_one / n_c3, "strong_scaling_efficiency": t_c3_one / (world * t_c3),
+          "tiles_per_gpu": tiles3, "tile_slots_per_gpu": 2 * sm,
+          "wave_quantisation": tiles3 / (2 * sm * -(-tiles3 // (2 * sm))),
+          "wave_note": "a GPU runs 2 x SMs 128-row tiles at a time; wave_quantisation = tiles / (slots x waves) is the ceiling a "
+                       "static tile->SM map puts on the efficiency at this shard size"}
+    del x3, x3_full, X3
+
     # --- config 5 share (fleet export): one stack of n timesteps -> 22-column float64 rows (K4 sweep at T_PASSES,
     # eval forward, export-form K3, row writer K5) and the RF(t) risk series of 8 such stacks (K5 scans)
     from b200pinn.export import export_rows_device
@@ -285,7 +436,6 @@ def run_ours(args):
     # (the residual-score columns pV, pT, pH, pO) with 20 components
     from b200pinn import gmm as G
     import numpy as np
-    rng = np.random.default_rng(0)
     feats = fleet[:, :, 13:17].reshape(-1, 4).contiguous()                 # the four residual columns of the export rows
     mu0 = feats[:: max(1, feats.shape[0] // 20)][:20].clone()
     sd = feats.std(dim=0).clamp_min(1e-6).cpu().numpy()
@@ -295,35 +445,33 @@ def run_ours(args):
     t_gmm, _ = timed(gmm_it, n_exp, 2, do_flush=False)
     n_gmm = feats.shape[0]
     del fleet, rows, feats
-    # --- wide nets (the reference's own Layers = [8,256,256,256,1], 01:2139; config 4 is 6x256): MC sweep on the per-layer
-    # tcgen05 GEMM path (mlp_wide_tc.cu): MC sweep and train step, N = 262144
+
+    # --- wide nets: the reference's own Layers = [8,256,256,256,1] (01:2139) at N = 262144 (MC sweep T=10 + train step), and
+    # configs[3] = 6x256 data-parallel training at its stated size: batch 4M over 8 GPUs = 524288 samples per GPU
     wide = {}
-    n_w, T_w = 262144, 10
-    for tag, lay_w, fl_pass, fl_train in (("3x256", [8, 256, 256, 256, 1], 344_704, 1_042_304),
-                                          ("6x256", [8, 256, 256, 256, 256, 256, 256, 1], 737_920, 2_221_952)):
+    T_w = 10
+    for tag, lay_w, n_w, fl_pass, fl_train in (("3x256", [8, 256, 256, 256, 1], 262144, 344_704, 1_042_304),
+                                               ("6x256", [8, 256, 256, 256, 256, 256, 256, 1], 524288, 737_920, 2_221_952)):
         torch.manual_seed(0)
         mw = b200pinn.PhysicsInformedNN(X[:n_w], Y[:n_w], lay_w, sx, sy, P_TRAIN, True)
         mw.dnn.eval()
         xw = mw.x.detach()
         t_w, _ = timed(lambda: b200pinn.mc_dropout_device(mw.dnn, xw, T_w, P_MC, seed=seed), 3, 1)
         mw.train_dnn(1, verbose=False)
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        mw.train_dnn(2, verbose=False)
-        b.record()
-        barrier()
-        t_wt = a.elapsed_time(b) / 2e3
-        wide[tag] = {"mc_ms": 1e3 * t_w / 3, "mc_sample_passes_per_s": n_w * T_w * 3 / t_w,
-                     "mc_tflops": n_w * T_w * 3 * fl_pass / t_w / 1e12, "train_ms": 1e3 * t_wt,
-                     "train_tflops": n_w * fl_train / t_wt / 1e12}
+        t_wt = timed_block(lambda k: mw.train_dnn(k, verbose=False), 3) / 3
+        wide[tag] = {"n_per_gpu": n_w, "mc_ms": 1e3 * t_w / 3, "mc_sample_passes_per_s": world * n_w * T_w * 3 / t_w,
+                     "mc_tflops_per_gpu": n_w * T_w * 3 * fl_pass / t_w / 1e12, "train_ms": 1e3 * t_wt,
+                     "train_steps_per_s": 1.0 / t_wt, "global_batch": world * n_w,
+                     "train_tflops_per_gpu": n_w * fl_train / t_wt / 1e12}
         del mw, xw
-    wide["what"] = ("N=262144 per GPU; MC sweep T=10 and train_dnn step on the per-layer tcgen05 3xTF32 GEMM path (operands as "
-                    "pre-split tf32 planes, TMA bulk copies; dgrad = same kernel on transposed weight planes, weight gradients "
-                    "= split-K GEMMs over sample-contiguous copies)")
+        torch.cuda.empty_cache()
+    c4 = dict(wide.pop("6x256"))
+    c4["what"] = ("configs[3]: 6x256 PINN, data-parallel train_dnn step at 524288 samples per GPU (= batch 4M on 8 GPUs; global batch "
+                  "here = n_gpus x 524288), one gradient-bucket exchange (1.49 MB) per step fused into the Adam launch over NVLink "
+                  "peer memory; the MC numbers are the same net's sweep at T=10")
+    wide["what"] = ("the reference's own Layers (01:2139): MC sweep T=10 and train_dnn step on the per-layer tcgen05 3xTF32 GEMM path")
+
     # --- configs[0] scale (N = 20 000, the reference's own CPU-runnable case): every step is latency-bound here.
-    # train_dnn = K2a + K2b + (gradient reduce + Adam) per step; the scalar phases run as persistent launches
-    # (pinn_scalar_phase: 1000 optimiser steps per launch, one grid barrier per step)
     c1 = None
     if world == 1 and not args.no_c1:
         n1 = 20_000
@@ -351,13 +499,12 @@ def run_ours(args):
                                             + 10001 * c1["train_thermal_us_per_step"] + 8001 * c1["train_hydrogen_us_per_step"]
                                             + 8001 * c1["train_oxygen_us_per_step"])
         del m1
+
     # --- e2e: public API, host tensors in pinned memory, results back on the host
     Xp = X.pin_memory()
-    import contextlib
-    import io
 
     def e2e():
-        with contextlib.redirect_stdout(io.StringIO()):
+        with quiet():
             b200pinn.get_MC_samples(model, Xp, sx, mc_times=T_PASSES, dropout=P_MC)
 
     for _ in range(max(1, W_)):
@@ -377,53 +524,48 @@ def run_ours(args):
         return
     pk = peaks()
     mc_tflops = n * T_PASSES * FLOP_PER_SAMPLE_PASS / (t_mc / K_) / 1e12
+    rec_mc, rec_res = ncu_record("mlp_tc_kernel<MC>"), ncu_record("residual_v_fast_kernel")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": W_,
         "ms_per_step": 1e3 * t_mc / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: 3x64 PINN (layers [8,64,64,64,1]), N=1M samples per GPU; step = MC-dropout "
-                               "sweep of T=50 passes (kernel K4)", "n_per_gpu": n, "T": T_PASSES, "dropout": P_MC,
-                   "sharding": "samples" if world > 1 else "none",
-                   "l2": "256 MB buffer written between timed steps (inputs 32 MB < 126 MB L2)"},
+        "config": workload_config(n, world),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 8 * 4, "d2h_bytes_per_step": n * 3 * 4},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": mc_tflops, "peak": pk["bf16"], "unit": "TFLOP/s",
-                     "frac": mc_tflops / pk["bf16"], "traffic": 32.1e6 * n / 1e6,
+                     "frac": mc_tflops / pk["bf16"],
+                     "traffic": (rec_mc["dram_bytes"] * n / rec_mc["n"]) if rec_mc else None,
                      "kernel": "mlp_tc_kernel<MC> (tcgen05.mma kind::tf32 with A in tensor memory, 3xTF32 split, "
                                "one MMA warp per 128-sample group)",
-                     "peak_source": pk["src"],
-                     "ncu": {"source": "profiles/r1_final4_mc.summary.txt (ncu --set full of this build's kernel, 10.58 ms capture)",
-                             "sm__pipe_tensor_cycles_active_pct": 29.6, "smsp__issue_active_pct": 57.4,
-                             "sm__inst_executed_pipe_alu_pct": 43.9, "sm__inst_executed_pipe_xu_pct": 40.1,
-                             "dram_bytes_per_launch": 32.1e6},
+                     "peak_source": pk["src"], "ncu": rec_mc,
                      "note": "achieved = algorithmic FLOPs (21 664 per sample*pass) / CUDA-event time of the launch. The "
                              "contractions run as 3 TF32 MMAs per product (fp32 parity), and TF32 dense peak is half the "
-                             "bf16 figure used as `peak`, so the tensor pipe does 6x this fraction of its own peak "
-                             "(ncu: sm__pipe_tensor_cycles_active, profiles/r1_final4_mc.summary.txt); the kernel is "
-                             "bounded by the CUDA-core epilogue (2 MUFU + ~12 ALU/FMA ops per activation, 5.6 Philox "
-                             "instructions per draw) and by the ~1000-clk latency of each 24-MMA batch, see DESIGN.md "
-                             "section 4 (tensor pipe active: 29 % here, 43 % in the weight-gradient kernel K2b, 47-51 % in the "
-                             "wide-net GEMMs). `traffic` is the ncu dram read+write of one launch at N=1M, scaled by n; "
-                             f"vs the fp32 FFMA peak (74.5 TFLOP/s) the kernel stands at {mc_tflops / 74.5:.2f}x"},
+                             "bf16 figure used as `peak`, so the tensor pipe does 6x this fraction of its own peak; the kernel "
+                             "is bounded by the CUDA-core epilogue (tanh, Philox, tf32 split) and MMA latency, see DESIGN.md "
+                             "section 4. `traffic` / `ncu` are read from profiles/ncu_current.json (ncu --set full of this "
+                             f"kernel), scaled by n; vs the fp32 FFMA peak (74.5 TFLOP/s) the kernel stands at {mc_tflops / 74.5:.2f}x"},
         "train": {"steps_per_s": steps_tr / t_tr, "ms_per_step": 1e3 * t_tr / steps_tr,
                   "global_batch": world * n, "tflops": world * n * FLOP_PER_TRAIN_SAMPLE / (t_tr / steps_tr) / 1e12,
-                  # K2a writes and K2b reads a 496-row x 512 B table per 128-sample tile (3x64 net): 2 x 1.98 KB per sample
-                  "hbm": {"bytes_per_sample": 2 * 496 * 4 + 36, "unit": "GB/s",
-                          "achieved": n * (2 * 496 * 4 + 36) / (t_tr / steps_tr) / 1e9,
-                          "frac_of_peak": n * (2 * 496 * 4 + 36) / (t_tr / steps_tr) / 1e9 / pk["hbm"]},
-                  "what": "train_dnn step: K2a (tcgen05 fwd+loss+dgrad, writes a transposed 2 KB/sample row table) + K2b "
-                          "(tcgen05 3xTF32 weight gradients, HBM-bound on that table: see profiles/) + "
-                          + ("partial reduce + gradient sum over NVLink peer memory fused into the Adam/StepLR launch"
-                             if world > 1 else "partial reduce with Adam/StepLR applied in the same launch")},
+                  "single_gpu_ms_per_step": 1e3 * t_tr_local / steps_tr, "weak_scaling_efficiency": t_tr_local / t_tr,
+                  "frac_of_bf16_peak_per_gpu": n * FLOP_PER_TRAIN_SAMPLE / (t_tr / steps_tr) / 1e12 / pk["bf16"],
+                  "what": "configs[1]: full-batch train_dnn step at N=1M per GPU (01:948-955): K2 forward+loss+dgrad+wgrad on "
+                          "tcgen05 3xTF32, partial reduce, "
+                          + ("gradient sum over NVLink peer memory fused into the Adam/StepLR launch; "
+                             if world > 1 else "Adam/StepLR in the reduce launch; ")
+                          + "single_gpu_ms_per_step is the same model stepping without the exchange, timed in this job"},
         "roofline_residual": {"bound": "hbm", "achieved": nb * RES_BYTES_PER_SAMPLE / (t_resb / K_) / 1e9, "peak": pk["hbm"],
                               "unit": "GB/s", "frac": nb * RES_BYTES_PER_SAMPLE / (t_resb / K_) / 1e9 / pk["hbm"],
-                              "traffic": None, "kernel": "residual_kernel<V|DATA, fast math>", "rows": nb,
+                              "traffic": (rec_res["dram_bytes"] * nb / rec_res["n"]) if rec_res else None, "ncu": rec_res,
+                              "kernel": "residual_v_fast_kernel (V|DATA, MUFU math)", "rows": nb,
                               "ms": 1e3 * t_resb / K_, "accurate_math_ms": 1e3 * t_resb_acc / K_,
-                              "ms_at_1M_rows": 1e3 * t_res / K_, "lambda_steps_per_s_at_1M": K_ / t_res,
+                              "ms_at_1M_rows": 1e3 * t_res / K_, "gbs_at_1M_rows": n * RES_BYTES_PER_SAMPLE / (t_res / K_) / 1e9,
+                              "lambda_steps_per_s_at_1M": K_ / t_res,
                               "export_form": {"bytes_per_sample": 36 + 4 * 21, "ms": 1e3 * t_exp / K_,
                                               "gbs": nb * (36 + 4 * 21) / (t_exp / K_) / 1e9}},
     }
+    line["c3"] = c3
+    line["c4"] = c4
     line["fleet"] = {"what": "config 5 per-GPU share: export of one 1M-timestep stack (MC sweep T=50 + eval forward + export-form "
                              "residuals + float64 22-column row writer with segment smoothing) and RF(t) for 8 stacks "
                              "(mu/sigma, dead-zone norms, C(t) scan, logistic, EMA, first alarm)",
@@ -436,13 +578,19 @@ def run_ours(args):
     line["wide"] = wide
     if c1 is not None:
         line["c1"] = c1
+    if world == 1 and not args.no_eager:
+        line["gpu_eager_baseline"] = gpu_eager_rates(X, Y, sx, sy, n)
+        ge = line["gpu_eager_baseline"]
+        if "mc_sample_passes_per_s" in ge:
+            ge["ours_over_eager_mc_e2e"] = e2e_value / ge["mc_sample_passes_per_s"]
+            ge["ours_over_eager_train"] = (steps_tr / t_tr) / ge["train_dnn_steps_per_s"]
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        mc_rate, tr_rate, t1, t2 = cpu_port_rates(1_000_000, 200_000, threads)
-        line["cpu_baseline"] = {"value": mc_rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"get_MC_samples port, N=1000000 x T'=1 ({t1:.1f} s); train_dnn port 1 step at "
-                                          f"N=200000 ({t2:.1f} s)",
-                                "train_steps_per_s_at_1M": tr_rate}
+        kind, mc_rate, tr_rate, t1, t2 = cpu_reference_rates(X, Y, sx, sy, n, min(n, 200_000), threads)
+        line["cpu_baseline"] = {"value": mc_rate, "unit": UNIT, "cores": threads, "kind": kind,
+                                "sample": f"get_MC_samples, N={n} x T'=1 ({t1:.1f} s); train_dnn steps at "
+                                          f"N={min(n, 200_000)} ({t2:.2f} s per step)",
+                                "train_steps_per_s_at_200k": tr_rate}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -455,8 +603,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=N_PER_GPU, help="samples per GPU (default: configs[1], 1M)")
+    ap.add_argument("--n", type=int, default=N_PER_GPU, help="samples per GPU (default: 1M, the batch of configs[1])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-eager", action="store_true", help="skip the eager-PyTorch-CUDA reference leg")
     ap.add_argument("--no-c1", action="store_true", help="skip the configs[0]-size step timings (thousands of launches: for ncu runs)")
     args = ap.parse_args()
     if args.impl == "reference":

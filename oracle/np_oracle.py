@@ -50,13 +50,15 @@ def softplus_log(v, dtype):
     return np.log(sp + dtype(1e-6)).astype(dtype), sp
 
 
-def dnn_forward(params, x, masks=None, dtype=np.float32, return_cache=False):
+def dnn_forward(params, x, masks=None, dtype=np.float32, return_cache=False, logvar=True):
     """``DNN.forward`` (01:421-438).
 
     ``masks``: ``None`` (eval mode) or a list of ``L+1`` *scaled* masks (values in
     ``{0, 1/(1-p)}``): one per trunk layer ``[N,H]`` and one for the variance
     head ``[N,H/2]`` -- the order in which ``nn.Dropout`` modules fire.
+    ``logvar=False``: the constructor flag of 01:428-436 -- the log-variance output is zeros.
     """
+    logvar_flag = logvar
     P = {k: np.asarray(v, dtype=dtype) for k, v in params.items()}
     L = n_hidden_layers(P)
     h = np.asarray(x, dtype=dtype)
@@ -72,6 +74,8 @@ def dnn_forward(params, x, masks=None, dtype=np.float32, return_cache=False):
     v1 = np.tanh(v0 @ P["var_layers.3.weight"].T + P["var_layers.3.bias"])
     v = v1 @ P["var_layers.5.weight"].T + P["var_layers.5.bias"]
     logvar, sp = softplus_log(v, dtype)
+    if not logvar_flag:
+        logvar = np.zeros_like(out)                                     # 01:436
     if return_cache:
         return out, logvar, dict(acts=acts, hs=hs, a_v0=a_v0, v0=v0, v1=v1, v=v, sp=sp)
     return out, logvar
@@ -94,14 +98,15 @@ def aleatoric_loss_grads(y, u, s, dtype=np.float64):
     return du, ds
 
 
-def dnn_backward(params, x, masks, du, ds, dtype=np.float64):
+def dnn_backward(params, x, masks, du, ds, dtype=np.float64, logvar=True):
     """Gradients of ``sum(du*out) + sum(ds*logvar)`` w.r.t. every DNN parameter
-    (what ``loss.backward()`` at 01:953 produces through autograd)."""
+    (what ``loss.backward()`` at 01:953 produces through autograd).  ``logvar=False``: the log-variance is a
+    constant (01:436), the variance head gets no gradient (keys absent, like ``grad is None``)."""
     P = {k: np.asarray(v, dtype=dtype) for k, v in params.items()}
     L = n_hidden_layers(P)
     _, _, c = dnn_forward(params, x, masks, dtype, return_cache=True)
     du = np.asarray(du, dtype=dtype)
-    ds = np.asarray(ds, dtype=dtype)
+    ds = np.asarray(ds, dtype=dtype) * (1.0 if logvar else 0.0)
     g = {}
     v, sp = c["v"], c["sp"]
     dsp_dv = np.where(v > 20, 1.0, 1.0 / (1.0 + np.exp(-v)))
@@ -128,6 +133,8 @@ def dnn_backward(params, x, masks, du, ds, dtype=np.float64):
         g[f"layers.layer_{i}.weight"] = dz.T @ c["hs"][i]
         g[f"layers.layer_{i}.bias"] = dz.sum(0)
         dh = dz @ P[f"layers.layer_{i}.weight"]
+    if not logvar:
+        g = {k: v for k, v in g.items() if not k.startswith("var_layers")}
     return g
 
 
@@ -372,15 +379,15 @@ def mc_statistics(pred_eval_t, pred_drop_t, logvar_drop_t, dtype=np.float32):
     return pred_mean.squeeze(), a_u.squeeze(), e_u.squeeze()
 
 
-def mc_dropout(params, x, masks_t, dtype=np.float32):
+def mc_dropout(params, x, masks_t, dtype=np.float32, logvar=True):
     """``get_MC_samples`` with injected masks.  ``masks_t[t]`` is the list of
     ``L+1`` scaled masks of pass ``t`` (the first forward of each ``predict``;
     the second, inside ``net_f_V``, is discarded: 01:1407)."""
     T = len(masks_t)
-    pe, _ = dnn_forward(params, x, None, dtype)
+    pe, _ = dnn_forward(params, x, None, dtype, logvar=logvar)
     us, ss = [], []
     for t in range(T):
-        u, s = dnn_forward(params, x, masks_t[t], dtype)
+        u, s = dnn_forward(params, x, masks_t[t], dtype, logvar=logvar)
         us.append(u)
         ss.append(s)
     return mc_statistics(np.stack([pe] * T), np.stack(us), np.stack(ss), dtype)

@@ -6,7 +6,9 @@ reference's own op sequence -- including the costs it chooses to pay: a second, 
 forward plus two scaler round trips inside every ``predict`` (01:1407), T redundant eval
 passes (01:1442-1445), per-pass host copies and the (T,N,1) numpy reduction (01:1475-1486).
 /root/reference cannot travel to the GPU box, hence this port (``cpu_baseline.kind`` =
-"port").  tests/test_oracle_golden.py pins it to the same golden vectors as the numpy oracle.
+"port") -- used only where oracle/_ref (the staged unmodified scripts) is absent.
+tests/test_oracle_golden.py pins its forward, residual, ``get_MC_samples_port`` (same torch RNG stream as the
+reference) and ``make_dnn_trainer`` to the golden vectors.
 """
 from __future__ import annotations
 
@@ -38,21 +40,24 @@ class PortDNN(torch.nn.Module):
     def forward(self, x):
         feats = self.layers(x)
         out = self.predict(feats)
-        logvar = torch.log(F.softplus(self.var_layers(feats)) + 1e-6)
+        if self.logvar:
+            logvar = torch.log(F.softplus(self.var_layers(feats)) + 1e-6)
+        else:
+            logvar = torch.zeros(out.size()).to(out.device)            # 01:436
         return out, logvar
 
 
 class PortPINN:
     """The parts of ``PhysicsInformedNN`` (01:441-1410) the benchmarks drive."""
 
-    def __init__(self, X, u, layers, x_scal, u_scal, p):
+    def __init__(self, X, u, layers, x_scal, u_scal, p, logvar=True):
         self.x = X.clone().detach().requires_grad_(True).float()
         self.u = u.clone().detach().float()
         self.X, self.x_scal, self.u_scal = X, x_scal, u_scal
         self.lambda_1 = torch.nn.Parameter(torch.tensor([0.167897923477715]))
         self.lambda_2 = torch.nn.Parameter(torch.tensor([2.36682075851268e-06]))
         self.lambda_3 = torch.nn.Parameter(torch.tensor([2.43414469188443]))
-        self.dnn = PortDNN(p, True, layers)
+        self.dnn = PortDNN(p, logvar, layers)
 
     def net_u(self, x):
         return self.dnn(x)

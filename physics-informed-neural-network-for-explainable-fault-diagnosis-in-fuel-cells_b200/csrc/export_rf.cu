@@ -125,7 +125,7 @@ PINN_D double rf_strength(const double* __restrict__ r, const double* __restrict
 #pragma unroll
   for (int d = 0; d < 5; ++d) {
     const double z = fabs((r[rf_col(d)] - ms[d]) / ms[5 + d]);
-    a[d] = fmax(0.0, z - z_safe);
+    a[d] = z != z ? z : fmax(0.0, z - z_safe);       // np.maximum propagates NaN (04:238), fmax would drop it
   }
   // layers {res,pV}, {pH,pO}, {pT} with p = 2, unit weights (04:84-96)
   return sqrt(a[0] * a[0] + a[1] * a[1]) + sqrt(a[3] * a[3] + a[4] * a[4]) + sqrt(a[2] * a[2]);

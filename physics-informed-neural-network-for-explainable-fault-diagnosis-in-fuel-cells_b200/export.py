@@ -38,12 +38,14 @@ def _export_scalers(scaler_X, scaler_Y) -> PinnExportScalers:
 
 
 def export_rows_device(model, x, y, boundaries, n_labeled, mc_times, dropout, scaler_X, scaler_Y, masks=None,
-                       window=SMOOTH_WINDOW, seed=None, sample_offset=0):
+                       window=SMOOTH_WINDOW, seed=None, sample_offset=0, pass_offset=0):
     """Device-level export of one stack: ``x [n,8]``, ``y [n]`` CUDA tensors (normalised);
-    returns a CUDA float64 tensor ``[n, 22]``."""
+    returns a CUDA float64 tensor ``[n, 22]``.  ``pass_offset``: first pass index of the sweep in the
+    network's dropout stream (``get_MC_samples`` at the same ``_drop_calls`` draws the same masks)."""
     dnn = model.dnn
     n, dev = x.shape[0], x.device
-    mc = mc_dropout_device(dnn, x, mc_times, float(dropout), seed=seed, sample_offset=sample_offset, masks=masks)
+    mc = mc_dropout_device(dnn, x, mc_times, float(dropout), seed=seed, sample_offset=sample_offset, pass_offset=pass_offset,
+                           masks=masks)
     net = K.net_from_module(dnn)
     u, _ = K.mlp_forward(net, x)                              # eval-mode prediction feeding net_f_V (01:1944-1948)
     fam = _abi.FAM_V | _abi.FAM_TS | _abi.FAM_H | _abi.FAM_O
@@ -78,7 +80,8 @@ def create_comprehensive_results_array_v2(model, dataset, mc_times=2000, dropout
     model.dnn.eval()
     masks = getattr(model.dnn, "_injected_mc", None)
     calls = getattr(model.dnn, "_drop_calls", 0)
-    out = export_rows_device(model, x, y, boundaries, n_labeled, mc_times, dropout, scaler_X, scaler_Y, masks=masks)
+    out = export_rows_device(model, x, y, boundaries, n_labeled, mc_times, dropout, scaler_X, scaler_Y, masks=masks,
+                             pass_offset=calls)
     if hasattr(model.dnn, "_drop_calls"):
         model.dnn._drop_calls = calls + int(mc_times)
     return out.cpu().numpy()

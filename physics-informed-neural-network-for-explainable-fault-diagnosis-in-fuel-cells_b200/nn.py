@@ -75,6 +75,8 @@ class DNN(torch.nn.Module):
         # dropout stream: Philox key + a counter advanced once per stochastic forward
         self._drop_seed = None
         self._drop_calls = 0
+        self._row_offset = 0     # global index of this shard's first row (data-parallel training: Philox counters are keyed on
+                                 # GLOBAL rows, so an N-GPU run draws the masks of the 1-GPU run)
         self._injected = None  # uint8 keep bits [n, D] (or [calls, n, D]) for the next stochastic forwards
         self._inj_idx = 0
 
@@ -104,7 +106,7 @@ class DNN(torch.nn.Module):
             return None
         if self._drop_seed is None:
             self._drop_seed = torch.initial_seed()
-        cfg = dict(p=p, seed=self._drop_seed, sample_offset=0, pass_offset=self._drop_calls)
+        cfg = dict(p=p, seed=self._drop_seed, sample_offset=self._row_offset, pass_offset=self._drop_calls)
         self._drop_calls += 1
         if self._injected is not None:
             m = self._injected

@@ -8,8 +8,9 @@ where the arithmetic runs:
 * the 17 physics scalars live in ONE device vector (each ``nn.Parameter`` is a view),
   the two sklearn scalers are folded once into an in-kernel affine -- the reference's
   per-call host round trips (01:726-737 etc.) are gone;
-* ``net_f_*`` are one launch of the residual kernel K3; their outputs still carry
-  autograd w.r.t. the lambdas (first-order exact) so external ``.backward()`` works;
+* ``net_f_*`` are one launch of the residual kernel K3; the outputs of ``net_f_V / T_simple / H / O`` still
+  carry autograd w.r.t. the lambdas (first-order exact) so external ``.backward()`` works; ``net_f_T`` (the
+  Euler variant, only used for plot statistics, 01:1670) returns plain values without a lambda graph;
 * the five phase trainers run whole steps on the device: K2 (+fused aleatoric loss) or
   K3 -> [one all-reduce when data-parallel] -> fused Adam/StepLR/clamp; the host only
   syncs for the 1-in-1000 progress line the reference prints.
@@ -71,6 +72,30 @@ class PhysicsInformedNN:
             self.dnn.register_parameter(key, getattr(self, name))
         self._scalers_cache = {}
         self._flat = None
+        self.data_parallel = True        # False: ignore an initialised process group (bench: single-GPU step time in a multi-GPU job)
+        self._sync_replicas()
+
+    def _dp_world(self):
+        return _world() if self.data_parallel else 1
+
+    def _sync_replicas(self):
+        """Data-parallel construction (what DDP does in its constructor): rank 0's network weights and physics scalars are
+        broadcast so replicas start identical whatever each rank's torch seed was, the Philox key of the dropout stream is
+        rank 0's, and this shard's first GLOBAL row (exclusive prefix sum of the per-rank row counts, rank order) becomes
+        the dropout stream's ``sample_offset`` -- N-GPU training then draws exactly the masks of the single-GPU run."""
+        import torch.distributed as dist
+        if _world() < 2:
+            return
+        with torch.no_grad():
+            dist.broadcast(self._flatten_dnn(), src=0)
+            dist.broadcast(self._lam, src=0)
+            seed = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF], device=self.device, dtype=torch.int64)
+            dist.broadcast(seed, src=0)
+            self.dnn._drop_seed = int(seed.item())
+            counts = torch.zeros(dist.get_world_size(), device=self.device, dtype=torch.int64)
+            counts[dist.get_rank()] = self.x.shape[0]
+            dist.all_reduce(counts)
+            self.dnn._row_offset = int(counts[:dist.get_rank()].sum().item())
 
     # ------------------------------------------------------------------ internals
     def _lambdas(self) -> torch.Tensor:
@@ -85,11 +110,21 @@ class PhysicsInformedNN:
                 prm.data = view
         return self._lam
 
+    def _scalers_entry(self, x_scal):
+        """(folded affine of the two scalers, its device copy), cached on the scalers' CONTENTS: a re-fitted scaler, or a
+        new object at a recycled ``id``, must not hit a stale entry."""
+        def fp(sc):
+            return tuple(np.asarray(getattr(sc, a), np.float64).tobytes() for a in ("min_", "scale_", "data_min_", "data_max_"))
+        key = (fp(x_scal), fp(self.u_scal), tuple(self.u_scal.feature_range))
+        ent = self._scalers_cache.get(key)
+        if ent is None:
+            sc = K.make_scalers(x_scal, self.u_scal)
+            aff = torch.tensor([list(sc.x_inv_scale), list(sc.x_off)], device=self.device, dtype=torch.float32)
+            ent = self._scalers_cache[key] = (sc, aff)
+        return ent
+
     def _scalers(self, x_scal):
-        key = (id(x_scal), id(self.u_scal))
-        if key not in self._scalers_cache:
-            self._scalers_cache[key] = K.make_scalers(x_scal, self.u_scal)
-        return self._scalers_cache[key]
+        return self._scalers_entry(x_scal)[0]
 
     def _dev(self, X):
         if X is self.X or X is self.x:
@@ -98,10 +133,8 @@ class PhysicsInformedNN:
 
     def _phys(self, x, x_scal):
         """Physical-domain columns in torch (only for attaching lambda-Jacobians)."""
-        sc = self._scalers(x_scal)
-        inv = torch.tensor(list(sc.x_inv_scale), device=x.device)
-        off = torch.tensor(list(sc.x_off), device=x.device)
-        return x * inv - off
+        aff = self._scalers_entry(x_scal)[1]           # device-resident, uploaded once per scaler pair
+        return x * aff[0] - aff[1]
 
     @staticmethod
     def _attach(value, pairs):
@@ -234,7 +267,7 @@ class PhysicsInformedNN:
         counter = K.new_step_counter(self.device)
         x, y = self.x.detach(), self.u.reshape(-1).contiguous()
         n_local = x.shape[0]
-        world = _world()
+        world = self._dp_world()
         n_global = n_local
         if world > 1:
             t = torch.tensor([n_local], device=self.device, dtype=torch.int64)
@@ -319,7 +352,7 @@ class PhysicsInformedNN:
             with torch.no_grad():
                 u = self.net_u(x)[0].reshape(-1).contiguous()
         sc = self._scalers(self.x_scal)
-        world = _world()
+        world = self._dp_world()
         last = None
         if world == 1 and x.shape[0] > 0 and os.environ.get("B200PINN_PHASE_KERNEL", "1") != "0":
             # single GPU: every stretch of epochs up to the next progress line (1 in 1000, 01:1049 etc.)

@@ -105,8 +105,15 @@ def compute_rf_time_series(results, mu, sigma, res_keys=RF_RES_KEYS, feature_wei
     ms = torch.tensor(np.concatenate([np.asarray(mu, np.float64), np.asarray(sigma, np.float64)])[None, :],
                       device=r.device)
     o = rf_device(r, z_safe, lambda_decay, k_logistic, C0_logistic, C_max, alpha_smooth, mu_sigma=ms, want_extra=True)
+    # per-layer strengths (04:243-254) for API parity: plain elementwise torch on the five residual columns (not a hot path)
+    mu_t, sg_t = ms[0, :5], ms[0, 5:]
+    a_tr = torch.clamp(((r[0][:, 12:17] - mu_t) / sg_t).abs() - z_safe, min=0.0)
+    a_tr = torch.where(torch.isnan(r[0][:, 12:17]), torch.full_like(a_tr, float("nan")), a_tr)
+    idx = {k: i for i, k in enumerate(RF_RES_KEYS)}
+    s_layers = {name: torch.sqrt((a_tr[:, [idx[k] for k in keys]] ** 2).sum(dim=1)).cpu().numpy()
+                for name, keys in RF_LAYER_CONFIG.items()}
     return (o["rf_inst"][0].cpu().numpy(), o["rf_smooth"][0].cpu().numpy(),
-            {"S_tot": o["S_tot"][0].cpu().numpy(), "C": o["C"][0].cpu().numpy()})
+            {"S_layers": s_layers, "S_tot": o["S_tot"][0].cpu().numpy(), "C": o["C"][0].cpu().numpy()})
 
 
 def find_first_alarm_index(series, threshold, mode="above"):

@@ -44,12 +44,16 @@ def unpack_masks(packed, layers, p, dtype=np.float32):
     """packed uint8 [N, ceil(D/8)] -> list of L+1 scaled masks ({0, 1/(1-p)})."""
     L, H = len(layers) - 2, int(layers[1])
     widths = [H] * L + [H // 2]
-    bits = np.unpackbits(packed, axis=1)[:, : sum(widths)]
+    bits = np.unpackbits(packed, axis=1)
+    bits = bits[:, : sum(widths)] if bits.shape[1] >= sum(widths) else bits[:, : L * H]
     keep = dtype(1.0 - p)
     scale = dtype(1.0) / keep
     out, o = [], 0
     for w in widths:
-        out.append(bits[:, o:o + w].astype(dtype) * scale)
+        m = bits[:, o:o + w]
+        if m.shape[1] < w:           # logvar=False goldens carry no variance-head mask (01:428-436 never runs that dropout)
+            m = np.ones((bits.shape[0], w), np.uint8)
+        out.append(m.astype(dtype) * scale)
         o += w
     return out
 
@@ -59,12 +63,15 @@ def load_golden(name):
     g["params"] = {k[2:]: v for k, v in g.items() if k.startswith("P:") and not k[2:].startswith("lambda")}
     g["layers"] = [int(v) for v in g["layers"]]
     g["p"] = float(g["p"])
+    g["logvar"] = bool(g["logvar"]) if "logvar" in g else True
     g["sx"] = Scaler(g, "sx")
     g["sy"] = Scaler(g, "sy")
     return g
 
 
-@pytest.fixture(params=["net64", "net32"])
+# net64 / net32: the headline and the narrow net; net256: the reference's own Layers (01:2139) on the wide tcgen05 path;
+# net64nl: DNN(logvar=False) (01:436) -- all four recorded from the unmodified reference by tests/golden/make_golden.py
+@pytest.fixture(params=["net64", "net32", "net256", "net64nl"])
 def golden(request):
     return load_golden(request.param)
 
@@ -80,7 +87,10 @@ def masks_u8(packed, layers):
     """packed golden bits -> uint8 keep matrix [N, L*H + H/2] (the C-ABI injection layout)."""
     L, H = len(layers) - 2, int(layers[1])
     D = L * H + H // 2
-    return np.ascontiguousarray(np.unpackbits(packed, axis=1)[:, :D])
+    bits = np.unpackbits(packed, axis=1)[:, :D]
+    if packed.shape[1] * 8 < D:      # logvar=False goldens: the reference never ran the variance head's dropout (01:428-436)
+        bits = np.concatenate([bits[:, :L * H], np.ones((bits.shape[0], D - L * H), np.uint8)], axis=1)
+    return np.ascontiguousarray(bits)
 
 
 def make_model(g, params_prefix="P:"):
@@ -89,7 +99,7 @@ def make_model(g, params_prefix="P:"):
     import b200pinn
 
     model = b200pinn.PhysicsInformedNN(torch.tensor(g["x"]), torch.tensor(g["y"]), g["layers"], g["sx"], g["sy"],
-                                       g["p"], True)
+                                       g["p"], g["logvar"])
     sd = {k[len(params_prefix):]: torch.tensor(v) for k, v in g.items()
           if k.startswith(params_prefix) and not k[len(params_prefix):].startswith("lambda")}
     missing, unexpected = model.dnn.load_state_dict(sd, strict=False)

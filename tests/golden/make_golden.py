@@ -98,12 +98,12 @@ def pack(masks):
     return np.packbits(cat, axis=1), cat.shape[1]
 
 
-def build(ref, layers, n, seed, p):
+def build(ref, layers, n, seed, p, logvar=True):
     from b200pinn.synthetic import make_scaled_dataset
 
     x, y, sx, sy = make_scaled_dataset(n, seed)
     torch.manual_seed(0)
-    model = ref.PhysicsInformedNN(torch.tensor(x), torch.tensor(y), layers, sx, sy, p, True)
+    model = ref.PhysicsInformedNN(torch.tensor(x), torch.tensor(y), layers, sx, sy, p, logvar)
     # Move lambda_1..3 off the values the synthetic voltages were generated with:
     # at the exact optimum the mode-A gradient is pure cancellation noise (the
     # reference's own fp32 result differs from fp64 by 1 %), useless as a ruler.
@@ -114,9 +114,9 @@ def build(ref, layers, n, seed, p):
     return model, x, y, sx, sy
 
 
-def golden_net(ref, name, layers, n, seed, p=0.2, mc_T=6, mc_p=0.4):
-    model, x, y, sx, sy = build(ref, layers, n, seed, p)
-    g = dict(layers=np.array(layers), p=p, x=x, y=y, **scaler_arrays("sx", sx), **scaler_arrays("sy", sy))
+def golden_net(ref, name, layers, n, seed, p=0.2, mc_T=6, mc_p=0.4, logvar=True):
+    model, x, y, sx, sy = build(ref, layers, n, seed, p, logvar)
+    g = dict(layers=np.array(layers), p=p, x=x, y=y, logvar=logvar, **scaler_arrays("sx", sx), **scaler_arrays("sy", sy))
     g.update(sd_arrays(model.dnn))
     g["lam0"] = lam_vector(model)
     X = torch.tensor(x)
@@ -216,7 +216,7 @@ def golden_net(ref, name, layers, n, seed, p=0.2, mc_T=6, mc_p=0.4):
     tap.take()
     pm, au, eu = ref.get_MC_samples(model, X, sx, mc_times=mc_T, dropout=mc_p)
     mm = tap.take()
-    nd = len(layers) - 2 + 1
+    nd = len(layers) - 2 + (1 if logvar else 0)        # logvar=False never runs var_layers (01:428-436): no mask for its dropout
     assert len(mm) == mc_T * 2 * nd, (len(mm), mc_T, nd)
     for t in range(mc_T):
         g[f"mc_masks{t}"], _ = pack(mm[t * 2 * nd: t * 2 * nd + nd])
@@ -232,5 +232,12 @@ def golden_net(ref, name, layers, n, seed, p=0.2, mc_T=6, mc_p=0.4):
 
 if __name__ == "__main__":
     ref = load_reference()
-    golden_net(ref, "net64", [8, 64, 64, 64, 1], n=320, seed=1)
-    golden_net(ref, "net32", [8, 32, 32, 1], n=97, seed=7, p=0.1, mc_T=4, mc_p=0.5)
+    which = sys.argv[1:] or ["net64", "net32", "net256", "net64nl"]
+    if "net64" in which:
+        golden_net(ref, "net64", [8, 64, 64, 64, 1], n=320, seed=1)
+    if "net32" in which:
+        golden_net(ref, "net32", [8, 32, 32, 1], n=97, seed=7, p=0.1, mc_T=4, mc_p=0.5)
+    if "net256" in which:        # the reference's own Layers (01:2139)
+        golden_net(ref, "net256", [8, 256, 256, 256, 1], n=160, seed=3, mc_T=4)
+    if "net64nl" in which:       # DNN(logvar=False): log-variance identically zero (01:436)
+        golden_net(ref, "net64nl", [8, 64, 64, 64, 1], n=200, seed=5, mc_T=4, logvar=False)

@@ -10,8 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_contract_line():
     env = dict(os.environ, OMP_NUM_THREADS="4")
-    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                         capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--n", "20000"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [ln for ln in res.stdout.strip().splitlines() if ln.startswith("{")]
     assert len(lines) == 1
@@ -21,9 +21,15 @@ def test_reference_arm_prints_one_contract_line():
                 "config", "cpu_baseline", "e2e"):
         assert key in d, key
     assert d["value"] > 0 and d["vs_baseline"] is None and d["higher_is_better"] is True
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import ref_loader
+    # the unmodified reference (oracle/_ref, staged by build()) when present, else the op-for-op port
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_loader.available() else "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    # same workload description as the product arm prints (the driver compares the two config blocks)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config(20000, 1)
 
 
 def test_reference_arm_other_ranks_exit_quietly():
