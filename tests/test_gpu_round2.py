@@ -111,6 +111,12 @@ def big():
     torch.manual_seed(0)
     m = b200pinn.PhysicsInformedNN(torch.tensor(x), torch.tensor(y), LAYERS, sx, sy, 0.2, True)
     m.dnn.eval()
+    with torch.no_grad():
+        # off the values the synthetic voltages were generated with: at the exact optimum the mode-A lambda-gradient is pure
+        # cancellation noise (same reason as tests/golden/make_golden.py::build)
+        m.lambda_1.mul_(1.2)
+        m.lambda_2.mul_(1.5)
+        m.lambda_3.mul_(1.1)
     return dict(n=n, x=x, y=y, sx=sx, sy=sy, m=m)
 
 
@@ -204,9 +210,32 @@ def test_full_size_train_step_gradients_vs_oracle_slice_linearity(big):
     a, sa = a.clone(), sa.clone()
     b, sb = K.mlp_backward(net, x[cut:].contiguous(), K.make_dropout(0.2, seed=9, pass_offset=3, sample_offset=cut),
                            y=y[cut:].contiguous(), n_global=n)
-    assert nrel(t2n(a + b), t2n(full)) < 2e-6
+    # fp32 accumulation order differs between the three launches (per-CTA TMEM accumulators over different sample ranges)
+    assert nrel(t2n(a + b), t2n(full)) < 5e-5
     assert np.allclose(t2n(sa + sb), t2n(sf), rtol=1e-9)
     assert t2n(sf)[3] == n
+
+
+def test_full_size_gradients_vs_fp64_oracle(big):
+    """K2 at the bench's N = 1M against fp64 backprop over the same 1M rows (dropout off, so no mask stream is involved):
+    every gradient tensor within the 1e-4 bar -- this is where accumulation error over ~6 700 samples per CTA would show."""
+    from b200pinn import kernels as K
+
+    m, n = big["m"], big["n"]
+    net = K.net_from_module(m.dnn)
+    flat, sums = K.mlp_backward(net, m.x.detach(), None, y=m.u.reshape(-1).contiguous(), n_global=n)
+    P = params_np(m.dnn)
+    o64, l64 = O.dnn_forward(P, big["x"], None, np.float64)
+    G = O.dnn_backward(P, big["x"], None, *O.aleatoric_loss_grads(big["y"], o64, l64))
+    s = t2n(sums)
+    assert abs((s[0] + 0.01 * s[1]) / s[3] - O.aleatoric_loss(big["y"], o64, l64, np.float64)) < LOSS_TOL
+    names, shapes, offs, _ = K.param_layout(net.width, net.n_hidden)
+    f = t2n(flat)
+    worst = {}
+    for nm, shp, o in zip(names, shapes, offs):
+        worst[nm] = nrel(f[o:o + int(np.prod(shp))].reshape(shp), G[nm].reshape(shp))
+    print("N=1M gradient errors vs fp64:", {k: f"{v:.1e}" for k, v in worst.items()})
+    assert max(worst.values()) < GRAD_TOL, worst
 
 
 # ------------------------------------------------------------------ export sweep sits in the network's dropout stream
