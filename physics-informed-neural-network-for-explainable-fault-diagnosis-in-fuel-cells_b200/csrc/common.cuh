@@ -16,11 +16,18 @@
 
 namespace pinn {
 
-// ------------------------------------------------------------------ Philox4x32-10
+// ------------------------------------------------------------------ Philox4x32-7
 // Counter-based RNG (Salmon et al. 2011).  counter = (sample_lo, sample_hi, pass,
 // layer<<16 | unit/4), key = seed: a mask bit depends only on global indices, so
 // results are identical for any grid, GPU count or sharding.
+#ifndef PINN_PHILOX_ROUNDS
+#define PINN_PHILOX_ROUNDS 7
+#endif
 struct Philox {
+  // Philox4x32-R.  R = 7 is the fewest rounds that pass BigCrush ("Crush-resistant", Salmon et al. 2011, table 2); the
+  // customary 10 adds safety margin a dropout mask does not need, and the generator is a quarter of the MC kernel's
+  // instructions.  Every kernel draws through this one definition, so the mask stream is identical on all paths.
+  static constexpr int kRounds = PINN_PHILOX_ROUNDS;
   static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
   static constexpr uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 
@@ -38,7 +45,7 @@ struct Philox {
   static PINN_HD uint4 gen(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2,
                            uint32_t c3) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < kRounds; ++r) {
       uint32_t hi0, lo0, hi1, lo1;
       mulhilo(M0, c0, hi0, lo0);
       mulhilo(M1, c2, hi1, lo1);
@@ -58,7 +65,7 @@ struct Philox {
     return make_uint4(c0 * M0 + c3, c1 ^ (c3 * M1), c2 + c3 * W0, c3 * W1 ^ rk[0]);
 #endif
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < kRounds; ++r) {
       uint32_t hi0, lo0, hi1, lo1;
       mulhilo(M0, c0, hi0, lo0);
       mulhilo(M1, c2, hi1, lo1);

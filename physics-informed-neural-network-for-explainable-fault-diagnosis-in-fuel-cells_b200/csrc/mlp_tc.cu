@@ -103,7 +103,8 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
   constexpr int H = kTcH, HH = kTcH / 2;
   constexpr uint32_t LBO_B = H * 16, LBO_H = kHeadN * 16;
   extern __shared__ __align__(1024) float smem[];
-  __shared__ __align__(8) uint64_t ready[2], done[2];
+  __shared__ __align__(8) uint64_t ready[2][4], done[2];     // ready[group][chunk]: one barrier per hand-over of a layer, so no
+                                                              // thread can arrive twice on a barrier within one of its phases
   __shared__ uint32_t tmem_base_s;
   const int L = lay.L, tid = threadIdx.x, row = tid & 127;
   const int warp = tc::uniform_warp_idx(), grp = (warp >> 3) & 1, half = (warp >> 2) & 1;  // warp-uniform roles
@@ -116,8 +117,7 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
 
   // ---------------------------------------------------------------- one-time CTA set-up
   if (tid == 0) {
-    tc::mbar_init(&ready[0], 256);
-    tc::mbar_init(&ready[1], 256);
+    for (int c = 0; c < 4; ++c) { tc::mbar_init(&ready[0][c], 256); tc::mbar_init(&ready[1][c], 256); }
     tc::mbar_init(&done[0], 1);
     tc::mbar_init(&done[1], 1);
     tc::fence_mbar_init();
@@ -180,19 +180,25 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
         const bool heads = l == L;
         const uint64_t b_hi_d = tc::make_desc(tc::smem_u32(smem + (heads ? lay.h_hi : lay.b_hi[l])), heads ? LBO_H : LBO_B, 128);
         const uint64_t b_lo_d = tc::make_desc(tc::smem_u32(smem + (heads ? lay.h_lo : lay.b_lo[l])), heads ? LBO_H : LBO_B, 128);
-        tc::mbar_wait(&ready[g], par);
-        par ^= 1u;
-        __syncwarp();
+        // The compute threads hand their new A columns over in four chunks (8 columns of each half = K slabs c and 4 + c):
+        // the products of a slab are issued as soon as it is complete, so the tensor pipe works under the epilogue that
+        // feeds it and only the last slab pair's MMAs (+ the fixed latency) are exposed after the epilogue ends.
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          tc::mbar_wait(&ready[g][c], par);
+          __syncwarp();
 #ifdef PINN_TIMELINE
-        if (blockIdx.x == 0 && g == 0 && !heads && (tid & 31) == 0 && tlm < 64) g_tl[2][tlm][0] = clock64();
+          if (blockIdx.x == 0 && g == 0 && !heads && c == 0 && (tid & 31) == 0 && tlm < 64) g_tl[2][tlm][0] = clock64();
 #endif
-        if (tc::elect_one()) {
-          tc::fence_after_sync();
-          if (heads) tc::issue_3xtf32_ts<H>(d_t, a_hi, a_hi + 64u, b_hi_d, b_lo_d, LBO_H, idesc48);
-          else tc::issue_3xtf32_ts<H>(d_t, a_hi, a_hi + 64u, b_hi_d, b_lo_d, LBO_B, idesc64);
-          tc::umma_commit(&done[g]);
+          if (tc::elect_one()) {
+            tc::fence_after_sync();
+            if (heads) tc::issue_3xtf32_ts_slabs(d_t, a_hi, a_hi + 64u, b_hi_d, b_lo_d, LBO_H, idesc48, c, 4 + c, c == 0);
+            else tc::issue_3xtf32_ts_slabs(d_t, a_hi, a_hi + 64u, b_hi_d, b_lo_d, LBO_B, idesc64, c, 4 + c, c == 0);
+            if (c == 3) tc::umma_commit(&done[g]);
+          }
+          __syncwarp();
         }
-        __syncwarp();
+        par ^= 1u;
 #ifdef PINN_TIMELINE
         if (blockIdx.x == 0 && g == 0 && !heads && (tid & 31) == 0 && tlm < 64) { g_tl[2][tlm][1] = clock64(); ++tlm; }
 #endif
@@ -211,7 +217,11 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
     int tl_i = 0;
 #endif
 
-    auto store8 = [&](int c0, const float (&v)[8]) {        // split -> this row's hi / lo columns in tensor memory
+    // One 8-column chunk of this row's next A operand: split into tf32 hi / lo planes in tensor memory.  The hand-over of
+    // the PREVIOUS chunk (its stores have long landed) goes out between the split and the stores of this one, so the MMA
+    // warp can start on a K slab pair while the rest of the epilogue is still running; the last chunk is handed over by
+    // signal_ready() below.
+    auto store8 = [&](int c0, const float (&v)[8], int chunk) {
       float h[8], lo[8];
 #pragma unroll
       for (int q = 0; q < 8; q += 2) {
@@ -219,11 +229,18 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
         const float2 l2 = __ffma2_rn(make_float2(h[q], h[q + 1]), make_float2(-1.0f, -1.0f), make_float2(v[q], v[q + 1]));   // v - h, exact
         lo[q] = l2.x; lo[q + 1] = l2.y;
       }
+      if (chunk > 0) {
+        tc::tmem_wait_st();
+        tc::fence_before_sync();
+        tc::mbar_arrive(&ready[grp][chunk - 1]);
+      }
       tc::tmem_st8(a_hi_l + static_cast<uint32_t>(c0), h);
       tc::tmem_st8(a_lo_l + static_cast<uint32_t>(c0), lo);
     };
-    // Philox blocks are drawn AHEAD of the MMA wait that precedes their use (they depend on nothing
-    // the tensor core produces), so the integer work fills the group's otherwise idle wait window.
+    // Philox blocks are drawn AHEAD of the MMA wait that precedes their use (they depend on nothing the tensor core
+    // produces) and pinned there.  Tried and measured slower (profiles/README.md, round 2): drawing them one phase ahead
+    // inside the previous epilogue, as raw blocks (11.6 ms) or as packed keep bits (12.4 ms), against 10.3 ms here -- the
+    // epilogue is bound by the MUFU pipe and dependent-issue latency and does not absorb the extra integer work.
     auto draw = [&](uint4* r, int nblk, const KeepSrc<INJ>& ks, uint32_t pass, uint32_t layer, int c0) {
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -245,11 +262,11 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
         for (int q = 0; q < 8; ++q) v[q] = t[q] * inact;
       }
     };
-    // hand the A planes to the MMA warp / wait for its accumulators
+    // hand the last chunk of the A planes to the MMA warp / wait for its accumulators
     auto signal_ready = [&]() {
       tc::tmem_wait_st();
       tc::fence_before_sync();
-      tc::mbar_arrive(&ready[grp]);
+      tc::mbar_arrive(&ready[grp][3]);
     };
     auto wait_done = [&]() {
       tc::mbar_wait(&done[grp], phase);
@@ -323,7 +340,7 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
             const float t8[8] = {a0[g], a0[g + 1], a0[g + 2], a0[g + 3], a0[g + 4], a0[g + 5], a0[g + 6], a0[g + 7]};
             float v[8];
             select8(r0[g / 8], ks, active, 0u, cb + g, t8, v);
-            store8(cb + g, v);
+            store8(cb + g, v, g / 8);
           }
         }
         // ---- hidden layers on the tensor cores
@@ -350,17 +367,22 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
             float t8[8], v[8];
             tanh8_prescaled(z + g, bb, t8);
             select8(rl[g / 8], ks, active, static_cast<uint32_t>(l), cb + g, t8, v);
-            store8(cb + g, v);
+            store8(cb + g, v, g / 8);
           }
+
           TL(5);
           TL_NEXT();
         }
         // ---- heads: [Wv0; Wp] in one N = 48 MMA
+        TL(0);
         signal_ready();
+        TL(1);
         uint4 rv[2] = {};
         if (!INJ && active) draw(rv, 2, ks, ks.pass, static_cast<uint32_t>(L), 16 * half);
         if (!INJ && drop_on && pi + 1 < n_pass) draw(r0, 4, ks, static_cast<uint32_t>(dp.pass_offset + t + 1), 0u, cb);
+        TL(2);
         wait_done();
+        TL(3);
         {
           // Variance head, split between the row's two threads: each activates 16 of the 32 head units
           // and forms its share of the sixteen 32 -> 16 sums; thread (row, 1) parks its share in spare
@@ -382,6 +404,7 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
 #pragma unroll
             for (int q = 0; q < 8; ++q) v0[g + q] = v[q];
           }
+          TL(4);
           const float* Wv1 = smem + lay.Wv1 + 16 * half;     // pre-scaled by 2 log2(e) / (1-p)
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
@@ -394,17 +417,20 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
             }
             part[k] = (acc.x + acc.y) + (acc2.x + acc2.y);
           }
+          TL(5);
           if (half == 1) {
             tc::tmem_st16(x_lane, part);
             tc::tmem_wait_st();
             tc::fence_before_sync();
             bar_arrive_n(1 + grp, 256);
+            TL(6); TL(7);
           } else {
             bar_sync_n(1 + grp, 256);
             tc::fence_after_sync();
             float p1[16];
             tc::tmem_ld16(x_lane, p1);
             tc::tmem_wait_ld();
+            TL(6);
             float vraw = smem[lay.bv2];
             const float* bv1 = smem + lay.bv1;
             const float* Wv2 = smem + lay.Wv2;
@@ -424,8 +450,10 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
               m2 = fmaf(d, u - mean, m2);
               slv += lv;
             }
+            TL(7);
           }
         }
+        TL_NEXT();
       }
       if (MC && valid && half == 0) {
         if (out.raw_mean) out.raw_mean[s] = mean;

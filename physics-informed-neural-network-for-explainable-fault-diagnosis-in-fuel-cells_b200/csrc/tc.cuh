@@ -256,5 +256,19 @@ PINN_D void issue_3xtf32_ts(uint32_t d_tmem, uint32_t a_hi_t, uint32_t a_lo_t, u
   }
 }
 
+// The same product issued slab by slab: the three terms of the two K = 8 slabs `s0`, `s1` (A columns 8 s .. 8 s + 7).
+// `first`: this call starts the accumulation (its very first MMA overwrites D).
+PINN_D void issue_3xtf32_ts_slabs(uint32_t d_tmem, uint32_t a_hi_t, uint32_t a_lo_t, uint64_t b_hi0, uint64_t b_lo0, uint32_t lbo_b,
+                                  uint32_t idesc, int s0, int s1, bool first) {
+  const uint64_t b_step = (2u * lbo_b) >> 4;
+#pragma unroll
+  for (int term = 0; term < 3; ++term) {      // small terms first: lo*hi, hi*lo, then hi*hi
+    const uint32_t a = term == 0 ? a_lo_t : a_hi_t;
+    const uint64_t b = term == 1 ? b_lo0 : b_hi0;
+    umma_tf32_ts(d_tmem, a + 8u * static_cast<uint32_t>(s0), b + static_cast<uint64_t>(s0) * b_step, idesc, (first && term == 0) ? 0u : 1u);
+    umma_tf32_ts(d_tmem, a + 8u * static_cast<uint32_t>(s1), b + static_cast<uint64_t>(s1) * b_step, idesc, 1u);
+  }
+}
+
 }  // namespace tc
 }  // namespace pinn

@@ -30,12 +30,14 @@ else:
     import numpy as np
     t = np.array(buf, dtype=np.int64).reshape(3, 64, 8)
     t0 = t[0, 0, 0]
-    names = ["pre-signal", "post-signal", "post-draw", "post-done", "post-ldtm", "post-epi"]
+    # three phases per pass: hidden layers 1, 2 (stamps 0..5) and heads + tail (stamps 0..7)
     for half in (0, 1):
-        print(f"half {half}:  phase  start   " + "  ".join(f"d({n})" for n in names[1:]) + "   gap-to-next")
-        for i in range(2, 26):
+        print(f"half {half}: phase start | deltas between consecutive stamps | gap to next phase")
+        for i in range(3, 30):
             r = t[half, i]
-            d = [r[k] - r[k - 1] for k in range(1, 6)]
-            gap = t[half, i + 1, 0] - r[5]
-            print(f"   {i:3d} {r[0] - t0:9d}   " + "  ".join(f"{x:10d}" for x in d) + f"   {gap:8d}"
-                  + (f"   mma: wake@{t[2, i, 0] - t0} (+{t[2, i, 0] - r[1]} after this thread's signal), issue {t[2, i, 1] - t[2, i, 0]}, done seen +{r[3] - t[2, i, 1]}" if half == 0 else ""))
+            ks = 8 if i % 3 == 2 else 6
+            d = [r[k] - r[k - 1] for k in range(1, ks)]
+            gap = t[half, i + 1, 0] - r[ks - 1]
+            kind = "heads" if i % 3 == 2 else f"layer{1 + i % 3}"
+            print(f"   {i:3d} {kind:7s} {r[0] - t0:9d} | " + " ".join(f"{x:6d}" for x in d) + f" | {gap:6d}")
+    print("hidden: signal, draw, wait-done, ldtm, epilogue.  heads: signal, draws(6 blocks), wait-done, v0 tanh+select, Wv1 dots, hand-over, v1/logvar/Welford; gap = layer-0 staging of the next pass")

@@ -175,7 +175,7 @@ def test_full_size_mc_sweep_properties(big):
         for key in ("pred_mean", "a_u", "e_u", "mean", "m2", "sum_logvar"):
             assert torch.equal(full[key][lo:lo + k], part[key]), (lo, key)
     u = m.net_u(m.x)[0].detach().reshape(-1)
-    assert nrel(t2n(full["pred_mean"]), t2n(u)) < 1e-6
+    assert nrel(t2n(full["pred_mean"]), t2n(u)) < 5e-6       # (a (1-p)) (w / (1-p)) vs a w: same value, different roundings
     e = t2n(full["e_u"])
     assert np.isfinite(e).all() and (e > 0).all() and np.isfinite(t2n(full["a_u"])).all()
     # Monte-Carlo consistency with the oracle on a slice: E_t[u_t] over independent Bernoulli masks -- the sample mean of 50
