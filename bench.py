@@ -425,12 +425,15 @@ def run_ours(args):
     from b200pinn.rf import rf_device
     seg = [0] + [n * (i + 1) // 13 for i in range(13)]                   # normal segment + 12 labelled fault segments (04:75-80)
     yv32 = model.u.reshape(-1).contiguous()
-    exp = lambda: export_rows_device(model, xd, yv32, seg, 12, T_PASSES, P_MC, sx, sy, seed=seed)
+    exp = lambda: export_rows_device(model, xd, yv32, seg, 12, T_PASSES, P_MC, sx, sy, seed=seed, want_rf_cols=True)
     t_export, _ = timed(exp, max(3, K_ // 2), 2)
-    rows = exp()
+    rows, rf_cols = exp()
     fleet = rows.unsqueeze(0).expand(8, -1, -1).contiguous()
     rfk = lambda: rf_device(fleet)
     t_rf, _ = timed(rfk, max(3, K_ // 2), 2)
+    fleet_c = rf_cols.unsqueeze(0).expand(8, -1, -1).contiguous()         # the dense [n, 6] copy of columns 12..17 the row writer emits
+    t_rfc, _ = timed(lambda: rf_device(fleet_c), max(3, K_ // 2), 2)
+    del fleet_c, rf_cols
     n_exp = max(3, K_ // 2)
     # GMM diagnosis (03:360-426) over the same 8 stacks: one EM iteration = one float64 pass over 8 x n rows x 4 features
     # (the residual-score columns pV, pT, pH, pO) with 20 components
@@ -572,6 +575,12 @@ def run_ours(args):
                      "export_rows_per_s": world * n * n_exp / t_export, "export_ms_per_stack": 1e3 * t_export / n_exp,
                      "rf_rows_per_s": world * 8 * n * n_exp / t_rf, "rf_ms_per_8_stacks": 1e3 * t_rf / n_exp,
                      "rf_hbm_gbs": 8 * n * (22 * 8 + 2 * 8) * n_exp / t_rf / 1e9,
+                     "rf_compact": {"ms_per_8_stacks": 1e3 * t_rfc / n_exp, "rows_per_s": world * 8 * n * n_exp / t_rfc,
+                                    "equivalent_row_gbs": 8 * n * (22 * 8 + 2 * 8) * n_exp / t_rfc / 1e9,
+                                    "actual_gbs": 8 * n * (48 + 48 + 5 * 8) * n_exp / t_rfc / 1e9,
+                                    "what": "same series from the dense [n,6] copy of columns 12..17 that the row writer emits on request: "
+                                            "two passes over 48-byte rows + S, RF_inst, RF_smooth (136 B/row actually moved); "
+                                            "equivalent_row_gbs uses rf_hbm_gbs's accounting (a 22-column row + two outputs)"},
                      "gmm_em_iteration_ms": 1e3 * t_gmm / n_exp, "gmm_rows_per_s": world * n_gmm * n_exp / t_gmm,
                      "gmm_what": "one EM iteration (E-step + M-step statistics, float64) of a 20-component full-covariance "
                                  "GaussianMixture over the 4 residual-score columns of 8 stacks (03:360-426)"}

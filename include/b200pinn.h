@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PINN_ABI_VERSION 2
+#define PINN_ABI_VERSION 3
 #define PINN_N_IN 8        /* operating-condition features, 01:136-137 */
 #define PINN_MAX_HIDDEN 8  /* hidden (tanh) layers supported */
 #define PINN_N_LAMBDA 17   /* lambda_1..4, T1..5, H1..4, O1..4 (01:453-517) */
@@ -198,7 +198,10 @@ size_t pinn_mc_workspace_bytes(int32_t width, int32_t n_hidden, int64_t n);
  * moving average of both uncertainties (smooth_by_segments 01:1848-1872; pandas window
  * span [i-w/2, i+w/2-1], min_periods=1) and the segment labels (create_fault_labels
  * 01:2013-2031).  `cols` is the [PINN_C_COUNT][n] output of pinn_residuals; seg_ends[n_seg]
- * (device, int64) are the exclusive segment ends; segments 1..n_labeled get label = index. */
+ * (device, int64) are the exclusive segment ends; segments 1..n_labeled get label = index.
+ * rf_cols (optional, [n][6] doubles): a dense copy of columns 12..17 (prediction residual, the four physics
+ * residuals, label) = everything the RF(t) entry points below read; feeding them this form instead of the
+ * 22-column rows cuts their DRAM traffic from sparse 176-byte rows to 48 dense bytes per row. */
 typedef struct pinn_export_scalers {
   double x_min[PINN_N_IN], x_scale[PINN_N_IN]; /* scaler_X.min_, scaler_X.scale_       */
   double y_min, y_scale;                       /* scaler_Y.min_[0], scaler_Y.scale_[0] */
@@ -208,10 +211,12 @@ int pinn_export_rows(const float* x, const float* y, const float* pred_mean,
                      const float* a_u, const float* e_u, const float* cols,
                      const int64_t* seg_ends, int32_t n_seg, int32_t n_labeled,
                      int32_t window, const pinn_export_scalers_t* scalers, int64_t n,
-                     double* out, void* stream);
+                     double* out, double* rf_cols, void* stream);
 
 /* f2 -- RF(t) risk function of 04_risk_function_early_warning_index.py, float64, for
- * n_series independent stacks laid out as results[n_series][n][22]:
+ * n_series independent stacks laid out as results[n_series][n][row_cols] whose columns first_col .. first_col+5
+ * are (res, pV, pT, pH, pO, label): row_cols = 22, first_col = 12 for comprehensive_results rows (04:58-62),
+ * row_cols = 6, first_col = 0 for the compact form pinn_export_rows can emit (both even: 16-byte aligned):
  * pinn_rf_stats  = estimate_mu_sigma_normal (04:181-197): nan-mean / nan-std (ddof 1) of
  *                  columns 12..16 over label-0 rows -> mu_sigma[n_series][10] (mu, sigma);
  * pinn_rf_series = compute_rf_time_series (04:201-285) + find_first_alarm_index
@@ -221,10 +226,11 @@ typedef struct pinn_rf_params {
   double z_safe, lambda_decay, k_logistic, c0_logistic, c_max, alpha_smooth, warn_threshold;
 } pinn_rf_params_t;
 size_t pinn_rf_workspace_bytes(int64_t n, int32_t n_series);
-int pinn_rf_stats(const double* results, int64_t n, int32_t n_series, double* mu_sigma,
-                  void* workspace, size_t workspace_bytes, void* stream);
-int pinn_rf_series(const double* results, int64_t n, int32_t n_series,
-                   const double* mu_sigma, const pinn_rf_params_t* params,
+int pinn_rf_stats(const double* results, int64_t n, int32_t n_series, int32_t row_cols,
+                  int32_t first_col, double* mu_sigma, void* workspace, size_t workspace_bytes,
+                  void* stream);
+int pinn_rf_series(const double* results, int64_t n, int32_t n_series, int32_t row_cols,
+                   int32_t first_col, const double* mu_sigma, const pinn_rf_params_t* params,
                    double* rf_inst, double* rf_smooth, double* c_out, double* s_out,
                    int64_t* first_alarm, void* workspace, size_t workspace_bytes,
                    void* stream);

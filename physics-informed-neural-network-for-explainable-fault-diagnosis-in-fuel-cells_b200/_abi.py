@@ -13,7 +13,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200pinn.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 N_IN = 8
 MAX_HIDDEN = 8
 N_LAMBDA = 17
@@ -91,10 +91,11 @@ _SIGNATURES = {
     "pinn_mc_dropout": (C.c_int, [C.POINTER(PinnNet), _vp, _i64, _i32, C.POINTER(PinnDropout),
                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pinn_export_rows": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, C.POINTER(PinnExportScalers),
-                                   _i64, _vp, _vp]),
+                                   _i64, _vp, _vp, _vp]),
     "pinn_rf_workspace_bytes": (_sz, [_i64, _i32]),
-    "pinn_rf_stats": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _sz, _vp]),
-    "pinn_rf_series": (C.c_int, [_vp, _i64, _i32, _vp, C.POINTER(PinnRfParams), _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pinn_rf_stats": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "pinn_rf_series": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, C.POINTER(PinnRfParams), _vp, _vp, _vp, _vp, _vp, _vp, _sz,
+                                 _vp]),
     "pinn_gmm_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "pinn_gmm_pass": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pinn_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _dbl, _dbl, _i64, _dbl, _vp, _vp, _vp,

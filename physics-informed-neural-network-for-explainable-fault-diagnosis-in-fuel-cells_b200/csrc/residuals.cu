@@ -268,22 +268,27 @@ PINN_D void eval_sample(const float* __restrict__ x, const float* __restrict__ u
 // arrive sums all partials in a fixed order (deterministic) with the whole block: thread
 // (slot = t % 32, lane-group = t / 32) adds every 8th CTA's partial, then the 8 groups are
 // folded in order.
+// Only the slots [R0, R1) plus PINN_S_N are reduced (the others are written as zeros): the voltage phase owns 10 of
+// the 28 slots, and at N = 1M the reduction tail is a visible share of the launch.
+template <int R0 = 1, int R1 = PINN_S_COUNT>
 PINN_D void finish_sums(const float* acc, double* __restrict__ partials, unsigned int* ticket, double* __restrict__ sums) {
-  __shared__ double red[kResThreads / 32][PINN_S_COUNT];
+  constexpr int NR = R1 - R0 + 1;                       // slot 0 (N) + the range
+  __shared__ double red[kResThreads / 32][NR];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k < PINN_S_COUNT; ++k) {
+  for (int j = 0; j < NR; ++j) {
+    const int k = j == 0 ? PINN_S_N : R0 + j - 1;
     double v = static_cast<double>(acc[k]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) red[warp][k] = v;
+    if (lane == 0) red[warp][j] = v;
   }
   __syncthreads();
-  if (threadIdx.x < PINN_S_COUNT) {
+  if (threadIdx.x < NR) {
     double v = 0.0;
     for (int wdx = 0; wdx < kResThreads / 32; ++wdx) v += red[wdx][threadIdx.x];
-    partials[static_cast<size_t>(blockIdx.x) * PINN_S_COUNT + threadIdx.x] = v;
+    partials[static_cast<size_t>(blockIdx.x) * NR + threadIdx.x] = v;
   }
   __threadfence();
   __syncthreads();
@@ -294,18 +299,32 @@ PINN_D void finish_sums(const float* acc, double* __restrict__ partials, unsigne
   __syncthreads();
   if (is_last) {
     __threadfence();
-    const int slot = lane, grp = warp;       // 8 warps: warp g sums CTAs g, g+8, ...
+    // fixed order: thread (slot, part) sums CTAs part, part + P, ... with eight independent loads in flight, then the P parts
+    // are folded in order.  (16 slots x 16 parts when the family owns <= 16 slots: at N = 1M this fold was the longest
+    // serial piece of the launch -- 444 partials walked by 8 warps, ~14 dependent L2 round trips.)
+    constexpr int SL = NR <= 16 ? 16 : 32, P = kResThreads / SL;
+    __shared__ double fold[P][SL];
+    const int slot = threadIdx.x % SL, part = threadIdx.x / SL;
     double v = 0.0;
-    if (slot < PINN_S_COUNT)
-      for (unsigned int b = grp; b < gridDim.x; b += kResThreads / 32)
-        v += partials[static_cast<size_t>(b) * PINN_S_COUNT + slot];
-    __syncthreads();
-    if (slot < PINN_S_COUNT) red[grp][slot] = v;
+    if (slot < NR) {
+      double q[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      unsigned int b = part;
+      for (; b + 7 * P < gridDim.x; b += 8 * P) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) q[k] += partials[static_cast<size_t>(b + k * P) * NR + slot];
+      }
+      for (int k = 0; b < gridDim.x; b += P, ++k) q[k] += partials[static_cast<size_t>(b) * NR + slot];
+      v = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+    }
+    fold[part][slot] = v;
     __syncthreads();
     if (threadIdx.x < PINN_S_COUNT) {
+      const int k = threadIdx.x;
+      const int j = k == PINN_S_N ? 0 : ((k >= R0 && k < R1) ? k - R0 + 1 : -1);
       double t = 0.0;
-      for (int g = 0; g < kResThreads / 32; ++g) t += red[g][threadIdx.x];
-      sums[threadIdx.x] = t;
+      if (j >= 0)
+        for (int g = 0; g < P; ++g) t += fold[g][j];
+      sums[k] = t;
     }
     if (threadIdx.x == 0) *ticket = 0u;
   }
@@ -314,7 +333,7 @@ PINN_D void finish_sums(const float* acc, double* __restrict__ partials, unsigne
 // Training-form kernel of the voltage phase (train_lambda, 01:1008-1055), MUFU math: consumes
 // columns 0,3,4,5 of the row plus u and y -- 40 algorithmic bytes per sample; two samples per
 // loop trip so four 128-bit loads are in flight per thread.
-__global__ void __launch_bounds__(kResThreads, 4)
+__global__ void __launch_bounds__(kResThreads, 3)
 residual_v_fast_kernel(const float* __restrict__ x, const float* __restrict__ u, const float* __restrict__ y, int64_t n,
                        pinn_scalers_t sc, const float* __restrict__ lam, uint32_t fam, uint32_t flags,
                        double* __restrict__ partials, unsigned int* ticket, double* __restrict__ sums) {
@@ -334,20 +353,37 @@ residual_v_fast_kernel(const float* __restrict__ x, const float* __restrict__ u,
     if (do_v) eval_V_fast(c, sc.p_h2o, a.x, a.w, b.x, b.y, us, ys, has_y, mode_a, mode_b, acc, nullptr, n, idx);
     if (do_d) { const float e = ys - us; acc[PINN_S_DATA2] = fmaf(e, e, acc[PINN_S_DATA2]); }
   };
-  for (; s + stride < n; s += 2 * stride) {
-    const float4* p0 = reinterpret_cast<const float4*>(x + s * PINN_N_IN);
-    const float4* p1 = reinterpret_cast<const float4*>(x + (s + stride) * PINN_N_IN);
-    const float4 a0 = __ldg(p0), b0 = __ldg(p0 + 1), a1 = __ldg(p1), b1 = __ldg(p1 + 1);
-    const float u0 = __ldg(u + s), u1 = __ldg(u + s + stride);
-    const float y0 = has_y ? __ldg(y + s) : 0.f, y1 = has_y ? __ldg(y + s + stride) : 0.f;
-    one(a0, b0, u0, y0, s);
-    one(a1, b1, u1, y1, s + stride);
+  // two samples per trip, the NEXT trip's loads issued before this trip's math (each thread only makes a few trips at
+  // N = 1M: without the prefetch every trip pays a full DRAM round trip)
+  struct Pair { float4 a0, b0, a1, b1; float u0, u1, y0, y1; };
+  auto load2 = [&](int64_t q) {
+    Pair p;
+    const float4* p0 = reinterpret_cast<const float4*>(x + q * PINN_N_IN);
+    const float4* p1 = reinterpret_cast<const float4*>(x + (q + stride) * PINN_N_IN);
+    p.a0 = __ldg(p0); p.b0 = __ldg(p0 + 1); p.a1 = __ldg(p1); p.b1 = __ldg(p1 + 1);
+    p.u0 = __ldg(u + q); p.u1 = __ldg(u + q + stride);
+    p.y0 = has_y ? __ldg(y + q) : 0.f; p.y1 = has_y ? __ldg(y + q + stride) : 0.f;
+    return p;
+  };
+  if (s + stride < n) {
+    Pair cur = load2(s);
+    for (;;) {
+      const int64_t nx = s + 2 * stride;
+      const bool more = nx + stride < n;
+      Pair nxt = cur;
+      if (more) nxt = load2(nx);
+      one(cur.a0, cur.b0, cur.u0, cur.y0, s);
+      one(cur.a1, cur.b1, cur.u1, cur.y1, s + stride);
+      s = nx;
+      if (!more) break;
+      cur = nxt;
+    }
   }
   if (s < n) {
     const float4* p0 = reinterpret_cast<const float4*>(x + s * PINN_N_IN);
     one(__ldg(p0), __ldg(p0 + 1), __ldg(u + s), has_y ? __ldg(y + s) : 0.f, s);
   }
-  finish_sums(acc, partials, ticket, sums);
+  finish_sums<PINN_S_FV2, PINN_S_GB3 + 1>(acc, partials, ticket, sums);
 }
 
 // Workspace: double partials[grid][PINN_S_COUNT] followed by one uint32 ticket (zeroed
@@ -667,7 +703,7 @@ extern "C" int pinn_residuals(const float* x, const float* u, const float* y, in
   } while (0)
   constexpr uint32_t VD = PINN_FAM_V | PINN_FAM_DATA;
   if ((f & ~VD) == 0 && !accm && cols == nullptr && (n == 0 || u != nullptr)) {
-    const int g4 = res_grid(n, 4, 2);
+    const int g4 = res_grid(n, 3, 2);
     residual_v_fast_kernel<<<g4, kResThreads, 0, st>>>(x, u, y, n, *scalers, lambdas, f, flags, partials, ticket, sums);
     return static_cast<int>(cudaGetLastError());
   }

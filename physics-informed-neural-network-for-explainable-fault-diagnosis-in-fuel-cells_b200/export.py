@@ -38,10 +38,12 @@ def _export_scalers(scaler_X, scaler_Y) -> PinnExportScalers:
 
 
 def export_rows_device(model, x, y, boundaries, n_labeled, mc_times, dropout, scaler_X, scaler_Y, masks=None,
-                       window=SMOOTH_WINDOW, seed=None, sample_offset=0, pass_offset=0):
+                       window=SMOOTH_WINDOW, seed=None, sample_offset=0, pass_offset=0, want_rf_cols=False):
     """Device-level export of one stack: ``x [n,8]``, ``y [n]`` CUDA tensors (normalised);
     returns a CUDA float64 tensor ``[n, 22]``.  ``pass_offset``: first pass index of the sweep in the
-    network's dropout stream (``get_MC_samples`` at the same ``_drop_calls`` draws the same masks)."""
+    network's dropout stream (``get_MC_samples`` at the same ``_drop_calls`` draws the same masks).
+    ``want_rf_cols``: also return the dense ``[n, 6]`` copy of columns 12..17 that ``rf.rf_device(..., compact=True)`` consumes
+    (the fleet pipeline of config 5: the risk series then reads 48 dense bytes per row instead of sparse 176-byte rows)."""
     dnn = model.dnn
     n, dev = x.shape[0], x.device
     mc = mc_dropout_device(dnn, x, mc_times, float(dropout), seed=seed, sample_offset=sample_offset, pass_offset=pass_offset,
@@ -51,14 +53,15 @@ def export_rows_device(model, x, y, boundaries, n_labeled, mc_times, dropout, sc
     fam = _abi.FAM_V | _abi.FAM_TS | _abi.FAM_H | _abi.FAM_O
     _, cols = K.residuals(x, u, None, model._scalers(scaler_X), model._lambdas(), fam, want_cols=True)
     out = torch.empty(n, 22, device=dev, dtype=torch.float64)
+    rf_cols = torch.empty(n, 6, device=dev, dtype=torch.float64) if want_rf_cols else None
     seg = torch.tensor(list(boundaries), device=dev, dtype=torch.int64) if boundaries else None
     sc = _export_scalers(scaler_X, scaler_Y)
     with torch.cuda.device(dev):
         check(_abi.lib().pinn_export_rows(ptr(x), ptr(y), ptr(mc["pred_mean"]), ptr(mc["a_u"]), ptr(mc["e_u"]), ptr(cols),
                                           ptr(seg), 0 if seg is None else seg.numel(), int(n_labeled), int(window),
-                                          C.byref(sc), n, ptr(out), K._stream()), "pinn_export_rows")
+                                          C.byref(sc), n, ptr(out), ptr(rf_cols), K._stream()), "pinn_export_rows")
     K.LAUNCHES += 1
-    return out
+    return (out, rf_cols) if want_rf_cols else out
 
 
 def create_comprehensive_results_array_v2(model, dataset, mc_times=2000, dropout=0.2):

@@ -47,9 +47,14 @@ def _as_device(results, device=None):
 def rf_device(results: torch.Tensor, z_safe=RF_Z_SAFE, lambda_decay=RF_LAMBDA_DECAY, k_logistic=RF_K_LOGISTIC,
               C0_logistic=RF_C0_LOGISTIC, C_max=RF_C_MAX, alpha_smooth=RF_ALPHA_SMOOTH,
               warn_threshold=RF_WARN_THRESHOLD, mu_sigma=None, want_extra=False):
-    """``results``: CUDA float64 ``[S, N, 22]``.  Returns dict of CUDA tensors: ``mu_sigma [S,10]``,
-    ``rf_inst, rf_smooth [S,N]``, ``first_alarm [S]`` (-1 = never), optionally ``C, S_tot``."""
+    """``results``: CUDA float64 ``[S, N, 22]`` (``comprehensive_results`` rows) or the compact ``[S, N, 6]`` form
+    (columns 12..17 only, as ``export_rows_device(..., want_rf_cols=True)`` emits).  Returns dict of CUDA tensors:
+    ``mu_sigma [S,10]``, ``rf_inst, rf_smooth [S,N]``, ``first_alarm [S]`` (-1 = never), optionally ``C, S_tot``."""
     S_, n = results.shape[0], results.shape[1]
+    row_cols = results.shape[2]
+    if row_cols not in (22, 6):
+        raise ValueError("b200pinn.rf: rows must have 22 columns (comprehensive_results) or 6 (compact RF columns)")
+    col0 = 12 if row_cols == 22 else 0
     dev = results.device
     L = _abi.lib()
     nb = L.pinn_rf_workspace_bytes(n, S_)
@@ -59,8 +64,8 @@ def rf_device(results: torch.Tensor, z_safe=RF_Z_SAFE, lambda_decay=RF_LAMBDA_DE
     with torch.cuda.device(dev):
         if mu_sigma is None:
             mu_sigma = torch.empty(S_, 10, device=dev, dtype=torch.float64)
-            check(L.pinn_rf_stats(ptr(results), n, S_, ptr(mu_sigma), ptr(ws), nb, K._stream()), "pinn_rf_stats")
-            K.LAUNCHES += 4
+            check(L.pinn_rf_stats(ptr(results), n, S_, row_cols, col0, ptr(mu_sigma), ptr(ws), nb, K._stream()), "pinn_rf_stats")
+            K.LAUNCHES += 2
         out["mu_sigma"] = mu_sigma
         out["rf_inst"] = torch.empty(S_, n, device=dev, dtype=torch.float64)
         out["rf_smooth"] = torch.empty(S_, n, device=dev, dtype=torch.float64)
@@ -68,10 +73,10 @@ def rf_device(results: torch.Tensor, z_safe=RF_Z_SAFE, lambda_decay=RF_LAMBDA_DE
         if want_extra:
             out["C"] = torch.empty(S_, n, device=dev, dtype=torch.float64)
             out["S_tot"] = torch.empty(S_, n, device=dev, dtype=torch.float64)
-        check(L.pinn_rf_series(ptr(results), n, S_, ptr(mu_sigma), C.byref(prm), ptr(out["rf_inst"]), ptr(out["rf_smooth"]),
+        check(L.pinn_rf_series(ptr(results), n, S_, row_cols, col0, ptr(mu_sigma), C.byref(prm), ptr(out["rf_inst"]), ptr(out["rf_smooth"]),
                                ptr(out.get("C")), ptr(out.get("S_tot")), ptr(out["first_alarm"]), ptr(ws), nb, K._stream()),
               "pinn_rf_series")
-        K.LAUNCHES += 5
+        K.LAUNCHES += 6
     return out
 
 
@@ -86,7 +91,7 @@ def estimate_mu_sigma_normal(results, res_keys=RF_RES_KEYS, normal_labels=NORMAL
     ws = K._workspace("rf", nb, dev)
     ms = torch.empty(r.shape[0], 10, device=dev, dtype=torch.float64)
     with torch.cuda.device(dev):
-        check(L.pinn_rf_stats(ptr(r), r.shape[1], r.shape[0], ptr(ms), ptr(ws), nb, K._stream()), "pinn_rf_stats")
+        check(L.pinn_rf_stats(ptr(r), r.shape[1], r.shape[0], 22, 12, ptr(ms), ptr(ws), nb, K._stream()), "pinn_rf_stats")
     m = ms[0].cpu().numpy()
     return m[:5].copy(), m[5:].copy()
 

@@ -66,21 +66,50 @@ if "res" in what:
     sc, lam = model._scalers(sx), model._lambdas()
     sums = torch.empty(_abi.S_COUNT, device=xd.device, dtype=torch.float64)
     fam = _abi.FAM_V | _abi.FAM_DATA
-    t = timed(lambda: K.residuals(xd, u, yv, sc, lam, fam, sums=sums), reps=10, do_flush=True)
+    def back_to_back(bufs, reps=30):
+        """`reps` launches inside ONE event pair, rotating over input copies that together exceed the 126 MB L2: the GPU
+        never waits for the host between launches, and no launch finds its input in L2."""
+        for xb_, ub_, yb_ in bufs:
+            K.residuals(xb_, ub_, yb_, sc, lam, fam, sums=sums)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()              # one graph of `reps` launches: no host latency between them
+        with torch.cuda.graph(g):
+            for i in range(reps):
+                xb_, ub_, yb_ = bufs[i % len(bufs)]
+                K.residuals(xb_, ub_, yb_, sc, lam, fam, sums=sums)
+        g.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+    small = [(xd.clone(), u.clone(), yv.clone()) for _ in range(6)]          # 6 x 40 MB = 240 MB > L2
+    t = back_to_back(small)
     res["res_1M_us"] = 1e3 * t
     res["res_1M_gbs"] = n * 40 / t / 1e6
     xb, ub, yb = xd.repeat(8, 1).contiguous(), u.repeat(8).contiguous(), yv.repeat(8).contiguous()
-    t = timed(lambda: K.residuals(xb, ub, yb, sc, lam, fam, sums=sums), reps=10, do_flush=True)
+    t = back_to_back([(xb, ub, yb)], reps=20)                                # 320 MB per launch > L2
     res["res_8M_us"] = 1e3 * t
     res["res_8M_gbs"] = 8 * n * 40 / t / 1e6
+    ref = torch.empty_like(sums)
+    K.residuals(xb, ub, yb, sc, lam, fam, sums=ref)
+    res["res_8M_checksum_FV2"] = float(ref[_abi.S["FV2"]])
+    res["res_8M_checksum_GA2"] = float(ref[_abi.S["GA2"]])
 if "rf" in what:
     from b200pinn.export import export_rows_device
     from b200pinn.rf import rf_device
     seg = [0] + [n * (i + 1) // 13 for i in range(13)]
-    rows = export_rows_device(model, xd, model.u.reshape(-1).contiguous(), seg, 12, 5, P_MC, sx, sy, seed=1)
+    rows, cc = export_rows_device(model, xd, model.u.reshape(-1).contiguous(), seg, 12, 5, P_MC, sx, sy, seed=1, want_rf_cols=True)
     fleet = rows.unsqueeze(0).expand(8, -1, -1).contiguous()
     t = timed(lambda: rf_device(fleet), reps=5, do_flush=True)
     res["rf_8x1M_ms"] = t
     res["rf_hbm_gbs"] = 8 * n * (22 * 8 + 16) / t / 1e6
+    fc = cc.unsqueeze(0).expand(8, -1, -1).contiguous()
+    t = timed(lambda: rf_device(fc), reps=5, do_flush=True)
+    res["rf_compact_8x1M_ms"] = t
+    res["rf_compact_equiv_gbs"] = 8 * n * (22 * 8 + 16) / t / 1e6
+    res["rf_compact_actual_gbs"] = 8 * n * (48 + 48 + 8 + 8 + 8 + 8 + 8) / t / 1e6
 for k, v in res.items():
     print(f"{k:28s} {v:.6g}")

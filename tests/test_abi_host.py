@@ -190,8 +190,8 @@ def test_abi_error_codes_without_gpu():
     net.n_in, net.width, net.n_hidden = 8, 64, 3                 # right shape, null weight pointers
     assert L.pinn_mlp_fwd(C.byref(net), None, 0, None, None, None, None, 0, None) == e["PINN_E_ARG"]
     assert L.pinn_residuals(None, None, None, 5, None, None, 1, 0, None, None, None, None, None, 0, None) == e["PINN_E_ARG"]
-    assert L.pinn_rf_series(None, 0, 1, None, None, None, None, None, None, None, None, 0, None) == e["PINN_E_ARG"]
-    assert L.pinn_export_rows(None, None, None, None, None, None, None, 0, 0, 0, None, 5, None, None) == e["PINN_E_ARG"]
+    assert L.pinn_rf_series(None, 0, 1, 22, 12, None, None, None, None, None, None, None, None, 0, None) == e["PINN_E_ARG"]
+    assert L.pinn_export_rows(None, None, None, None, None, None, None, 0, 0, 0, None, 5, None, None, None) == e["PINN_E_ARG"]
     assert L.pinn_param_count(64, 0) == e["PINN_E_SHAPE"]
     # the two whole-step entry points validate before touching the device as well
     assert L.pinn_train_dnn_step(None, None, 0, None, None, 0, None, None, None, None, 1e-2, 0.8, 1000, None, None, None, 0,

@@ -105,3 +105,23 @@ def test_rf_fleet_long_series_vs_oracle():
             assert np.allclose(o["rf_smooth"][s].cpu().numpy(), sm, rtol=1e-10, atol=1e-12)
             assert int(o["first_alarm"][s]) == O.first_alarm(sm, 0.3)
     assert int(o["first_alarm"][0]) == -1
+
+
+def test_rf_compact_columns_match_full_rows():
+    """The row writer's dense [n, 6] copy of columns 12..17 equals those columns of the 22-column rows bit for bit, and RF(t) over
+    the compact form (config 5's fleet pipeline) gives the same series as over the full rows."""
+    from b200pinn import rf
+    from b200pinn.export import export_rows_device
+
+    g = load_golden("export64")
+    m = export_model(g)
+    n = 1100
+    x = torch.tensor(g["x_test"][:n], device=dev())
+    y = torch.tensor(g["y_test"][:n], device=dev()).reshape(-1).contiguous()
+    bl = [int(b) for b in g["boundaries"]]
+    rows, compact = export_rows_device(m, x, y, bl, len(bl) - 1, 4, 0.4, g["sx"], g["sy"], seed=3, want_rf_cols=True)
+    assert compact.shape == (n, 6) and torch.equal(compact, rows[:, 12:18])
+    a = rf.rf_device(rows.unsqueeze(0).contiguous(), want_extra=True)
+    b = rf.rf_device(compact.unsqueeze(0).contiguous(), want_extra=True)
+    for k in ("mu_sigma", "rf_inst", "rf_smooth", "first_alarm", "C", "S_tot"):
+        assert torch.equal(a[k], b[k]), k
