@@ -294,6 +294,17 @@ PINN_HD ParamLayout make_layout(int H, int L) {
   return p;
 }
 
+// Entry i of the flat bucket is alignment padding (behind the two single-element biases bp / bv2, or behind any tensor
+// whose size is not a multiple of four): the gradient reduces write 0 there instead of summing uninitialised partials.
+PINN_HD bool layout_is_padding(const ParamLayout& p, int64_t i) {
+  auto in = [&](int64_t off, int64_t cnt) { return i >= off && i < off + cnt; };
+  const int64_t H = p.H;
+  for (int l = 0; l < p.L; ++l)
+    if (in(p.offW[l], H * (l == 0 ? PINN_N_IN : H)) || in(p.offb[l], H)) return false;
+  return !(in(p.offWp, H) || in(p.offbp, 1) || in(p.offWv0, (H / 2) * H) || in(p.offbv0, H / 2) ||
+           in(p.offWv1, (H / 4) * (H / 2)) || in(p.offbv1, H / 4) || in(p.offWv2, H / 4) || in(p.offbv2, 1));
+}
+
 inline int validate_net(const pinn_net_t* net) {
   if (!net) return PINN_E_ARG;
   if (net->n_in != PINN_N_IN) return PINN_E_SHAPE;

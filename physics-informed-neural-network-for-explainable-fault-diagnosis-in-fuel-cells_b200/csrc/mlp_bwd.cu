@@ -315,11 +315,13 @@ mlp_bwd_kernel(pinn_net_t net, ParamLayout lay, DropParams dp, BwdArgs a) {
 }
 
 __global__ void grad_reduce_kernel(const float* __restrict__ partial, const double* __restrict__ loss_partial,
-                                   int nblk, int64_t total, float* __restrict__ grad, double* __restrict__ loss) {
+                                   int nblk, int64_t total, float* __restrict__ grad, double* __restrict__ loss,
+                                   const ParamLayout lay) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < total) {
     double acc = 0.0;
-    for (int b = 0; b < nblk; ++b) acc += static_cast<double>(partial[static_cast<size_t>(b) * total + i]);
+    if (!layout_is_padding(lay, i))          // alignment padding of the bucket: written as 0
+      for (int b = 0; b < nblk; ++b) acc += static_cast<double>(partial[static_cast<size_t>(b) * total + i]);
     grad[i] = static_cast<float>(acc);
   }
   if (loss != nullptr && blockIdx.x == 0 && threadIdx.x < 4) {
@@ -430,7 +432,7 @@ extern "C" int pinn_mlp_bwd(const pinn_net_t* net, const float* x, int64_t n, co
   PINN_CUDA_TRY(cudaGetLastError());
   const int rb = 256;
   const int rg = static_cast<int>((lay.total + rb - 1) / rb);
-  grad_reduce_kernel<<<rg, rb, 0, st>>>(a.partial, a.loss_partial, p.grid, lay.total, grad_flat, loss_sums);
+  grad_reduce_kernel<<<rg, rb, 0, st>>>(a.partial, a.loss_partial, p.grid, lay.total, grad_flat, loss_sums, lay);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -917,7 +917,7 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
 constexpr int kRedCols = 32, kRedGroups = 8;
 __global__ void __launch_bounds__(kRedCols * kRedGroups)
 grad_reduce2_kernel(const float* __restrict__ partial, const double* __restrict__ loss_partial, int nblk, int nloss, int64_t total,
-                    float* __restrict__ grad, double* __restrict__ loss, const FusedAdam fa) {
+                    float* __restrict__ grad, double* __restrict__ loss, const FusedAdam fa, const ParamLayout lay) {
   __shared__ double fold[kRedGroups][kRedCols];
   __shared__ float consts[2];
   const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
@@ -949,7 +949,7 @@ grad_reduce2_kernel(const float* __restrict__ partial, const double* __restrict_
     double t = 0.0;
 #pragma unroll
     for (int k = 0; k < kRedGroups; ++k) t += fold[k][c];
-    const float gr = static_cast<float>(t);
+    const float gr = layout_is_padding(lay, i) ? 0.0f : static_cast<float>(t);     // padding slots hold no partial sums
     if (grad != nullptr) grad[i] = gr;
     if (fa.params != nullptr) {
       float pp = fa.params[i], mm = fa.m[i], vv = fa.v[i];
@@ -1095,7 +1095,7 @@ int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropPa
   if (fused != nullptr) fa = *fused;
   PINN_CUDA_TRY(launch_pdl(grad_reduce2_kernel, dim3(rg), dim3(kRedCols * kRedGroups), 0, st, pdl,
                            static_cast<const float*>(w.partial), static_cast<const double*>(a.loss_partial), p.grid_b, 2 * p.grid_a,
-                           lay.total, grad_flat, loss_sums, fa));
+                           lay.total, grad_flat, loss_sums, fa, lay));
   return static_cast<int>(cudaGetLastError());
 }
 

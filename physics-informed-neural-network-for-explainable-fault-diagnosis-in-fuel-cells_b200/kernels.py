@@ -189,8 +189,8 @@ def mlp_backward(net: Net, x: torch.Tensor, drop: Optional[PinnDropout], grad_u=
     n = x.shape[0]
     L = _abi.lib()
     total = L.pinn_param_count(net.width, net.n_hidden)
-    if grad_flat is None:
-        grad_flat = torch.empty(total, device=x.device, dtype=torch.float32)
+    if grad_flat is None:       # zeros: the alignment padding of the bucket is never written by the 128/256-wide path
+        grad_flat = torch.zeros(total, device=x.device, dtype=torch.float32)
     if loss_sums is None:
         loss_sums = torch.zeros(4, device=x.device, dtype=torch.float64)
     nb = L.pinn_mlp_bwd_workspace_bytes(net.width, net.n_hidden, n)

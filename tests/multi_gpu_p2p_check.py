@@ -92,6 +92,7 @@ def main():
         # ---- 3b. the single-GPU full-batch run (every rank runs it: same work, no collective) from rank 0's weights
         single = build(x, y, sx, sy, seed=1000, data_parallel=False)      # seed of rank 0 = the broadcast source
         single.dnn._drop_seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
+        single.dnn._row_offset = 0               # constructed inside the process group, it was given this rank's shard offset
         net1 = K.net_from_module(single.dnn)
         drop1 = K.make_dropout(0.2, seed=single.dnn._drop_seed, sample_offset=0, pass_offset=5)
         g_full, _ = K.mlp_backward(net1, single.x.detach(), drop1, y=single.u.reshape(-1).contiguous(), n_global=n_total)
@@ -100,6 +101,9 @@ def main():
         torch.cuda.synchronize()
         p_rel = float((a - flat_params(single)).abs().max() / a.abs().max())
         ok = synced and offs_ok and same and rel < 1e-4 and g_rel < 1e-6 and p_rel < 1e-5
+        if not ok:
+            print(f"rank {rank}: check failed at n_total={n_total}: synced={synced} offs_ok={offs_ok} same={same} rel={rel:.2e} "
+                  f"g_rel={g_rel:.2e} p_rel={p_rel:.2e}", flush=True)
         ok_t = torch.tensor([1 if ok else 0], device=dev)
         dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
         ok_all = ok_all and bool(ok_t.item())
