@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PINN_ABI_VERSION 3
+#define PINN_ABI_VERSION 4
 #define PINN_N_IN 8        /* operating-condition features, 01:136-137 */
 #define PINN_MAX_HIDDEN 8  /* hidden (tanh) layers supported */
 #define PINN_N_LAMBDA 17   /* lambda_1..4, T1..5, H1..4, O1..4 (01:453-517) */
@@ -58,8 +58,10 @@ enum { /* pinn_net_t.flags */
   PINN_NET_NO_WIDE_TC = 4,  /* same for the 128- / 256-wide nets (forward, MC sweep and backward)                */
   PINN_NET_PDL_NEVER = 8,   /* never chain a step's launches with programmatic dependent launch                  */
   PINN_NET_PDL_ALWAYS = 16, /* always chain them (default: only for batches of up to two tiles per SM)           */
-  PINN_NET_NO_LOGVAR = 32   /* DNN(logvar=False), 01:436: the log-variance output is identically 0, the variance
+  PINN_NET_NO_LOGVAR = 32,  /* DNN(logvar=False), 01:436: the log-variance output is identically 0, the variance
                                head receives no gradient and the aleatoric loss reduces to 0.5 * MSE             */
+  PINN_NET_NO_FUSED_BWD = 64 /* ablation / tests: 64-wide backward as the two-kernel form (K2a + row table + K2b)
+                               instead of the one-kernel form with on-chip weight gradients                      */
 };
 
 /* Dropout control.  p == 0 means eval mode.  With masks == NULL the keep mask of
@@ -102,6 +104,11 @@ int pinn_mlp_bwd(const pinn_net_t* net, const float* x, int64_t n,
                  float* grad_flat, double* loss_sums, void* workspace,
                  size_t workspace_bytes, void* stream);
 size_t pinn_mlp_bwd_workspace_bytes(int32_t width, int32_t n_hidden, int64_t n);
+/* Same for one particular call: `flags` = the pinn_net_t.flags that call will carry.  The default
+ * path of the 64-wide net with 2 or 3 hidden layers needs a few MB whatever n is; the
+ * PINN_NET_NO_FUSED_BWD form needs 2 KB per sample for its row table (what the function above,
+ * which covers every path, reports). */
+size_t pinn_mlp_bwd_workspace_bytes_flags(int32_t width, int32_t n_hidden, int64_t n, int32_t flags);
 
 /* One train_dnn step (the loop body 01:948-955: train-mode forward, aleatoric loss, backward,
  * Adam.step with torch's default betas / eps, StepLR.step) as ONE call for a single-GPU trainer.

@@ -13,7 +13,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200pinn.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 N_IN = 8
 MAX_HIDDEN = 8
 N_LAMBDA = 17
@@ -22,7 +22,7 @@ N_LAMBDA = 17
 FAM_V, FAM_TS, FAM_T, FAM_H, FAM_O, FAM_DATA = 1, 2, 4, 8, 16, 32
 RES_ACCURATE_MATH, RES_NO_MODE_A, RES_NO_MODE_B, RES_NO_CLUSTER = 1, 2, 4, 8
 # pinn_net_t.flags: per-call path selection and model options (the library keeps no process-global switches)
-NET_NO_TC_FWD, NET_NO_TC_BWD, NET_NO_WIDE_TC, NET_PDL_NEVER, NET_PDL_ALWAYS, NET_NO_LOGVAR = 1, 2, 4, 8, 16, 32
+NET_NO_TC_FWD, NET_NO_TC_BWD, NET_NO_WIDE_TC, NET_PDL_NEVER, NET_PDL_ALWAYS, NET_NO_LOGVAR, NET_NO_FUSED_BWD = 1, 2, 4, 8, 16, 32, 64
 SUM_NAMES = ["N", "FV2", "EA2", "DATA2", "GA1", "GA2", "GA3", "GB1", "GB2", "GB3",
              "FT2", "FTABS", "GT1", "GT3", "GT5", "FTE2",
              "FH2", "GH1", "GH2", "GH3", "HACT", "HTGT",
@@ -77,6 +77,7 @@ _SIGNATURES = {
     "pinn_param_count": (_i64, [_i32, _i32]),
     "pinn_mlp_fwd_workspace_bytes": (_sz, [_i32, _i32, _i64]),
     "pinn_mlp_bwd_workspace_bytes": (_sz, [_i32, _i32, _i64]),
+    "pinn_mlp_bwd_workspace_bytes_flags": (_sz, [_i32, _i32, _i64, _i32]),
     "pinn_mc_workspace_bytes": (_sz, [_i32, _i32, _i64]),
     "pinn_residuals_workspace_bytes": (_sz, [_i64]),
     "pinn_mlp_fwd": (C.c_int, [C.POINTER(PinnNet), _vp, _i64, C.POINTER(PinnDropout), _vp, _vp, _vp, _sz, _vp]),

@@ -380,6 +380,11 @@ extern "C" size_t pinn_mlp_bwd_workspace_bytes(int32_t width, int32_t n_hidden, 
   return a;
 }
 
+extern "C" size_t pinn_mlp_bwd_workspace_bytes_flags(int32_t width, int32_t n_hidden, int64_t n, int32_t flags) {
+  if (width == 64 && n_hidden >= 2 && n_hidden <= 4 && !(flags & PINN_NET_NO_TC_BWD)) return tc_bwd_workspace_bytes(n_hidden, n, flags);
+  return pinn_mlp_bwd_workspace_bytes(width, n_hidden, n);
+}
+
 extern "C" int pinn_mlp_bwd(const pinn_net_t* net, const float* x, int64_t n, const pinn_dropout_t* drop,
                             const float* grad_u, const float* grad_logvar, const float* y, int64_t n_global,
                             float* grad_flat, double* loss_sums, void* workspace, size_t workspace_bytes,

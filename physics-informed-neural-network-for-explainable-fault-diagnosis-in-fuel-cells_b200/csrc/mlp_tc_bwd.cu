@@ -982,6 +982,9 @@ grad_reduce2_kernel(const float* __restrict__ partial, const double* __restrict_
   }
 }
 
+}  // namespace pinn
+#include "mlp_tc_fused.cuh"
+namespace pinn {
 
 struct TcBwdPlan { int grid_a, grid_b; size_t smem_a, smem_b, off_partial, off_scratch, bytes; };
 static TcBwdPlan plan_tc_bwd(int L, int64_t n) {
@@ -1018,12 +1021,73 @@ bool tc_bwd_covers(const pinn_net_t* net) {
     if (!aligned16(net->W[l])) return false;
   return aligned16(net->Wv0) && aligned16(net->Wp);
 }
-size_t tc_bwd_workspace_bytes(int L, int64_t n) { return plan_tc_bwd(L, n).bytes; }
+bool tc_bwd_fused(int L, int flags) { return (L == 2 || L == 3) && !(flags & PINN_NET_NO_FUSED_BWD); }
+size_t tc_bwd_workspace_bytes(int L, int64_t n, int flags) {
+  if (flags >= 0 && tc_bwd_fused(L, flags)) return plan_fused(L, n).bytes;
+  const size_t two = plan_tc_bwd(L, n).bytes;      // flags < 0: any path
+  const size_t one = (L == 2 || L == 3) ? plan_fused(L, n).bytes : 0;
+  return two > one ? two : one;
+}
+
+// One-kernel form (mlp_tc_fused.cuh): weight images, the fused tile kernel, the fixed-order reduce (+ Adam).
+static int launch_tc_fused(const pinn_net_t* net, const float* x, int64_t n, const DropParams& dp, const float* grad_u,
+                           const float* grad_s, const float* y, int64_t n_global, float* grad_flat, double* loss_sums, void* workspace,
+                           size_t workspace_bytes, cudaStream_t st, const FusedAdam* fused) {
+  const int L = net->n_hidden;
+  const FzPlan p = plan_fused(L, n);
+  if (workspace_bytes < p.bytes) return PINN_E_WORKSPACE;
+  const ParamLayout lay = make_layout(kBH, L);
+  char* ws = static_cast<char*>(workspace);
+  FzArgs a{};
+  a.x = x; a.n = n; a.grad_u = grad_u; a.grad_s = grad_s; a.y = y;
+  a.inv_n_global = grad_u ? 0.f : static_cast<float>(1.0 / static_cast<double>(n_global));
+  a.images = reinterpret_cast<unsigned char*>(ws + p.off_images);
+  a.partial = reinterpret_cast<float*>(ws + p.off_partial);
+  a.loss_partial = reinterpret_cast<double*>(ws);
+  a.park = reinterpret_cast<float*>(ws + p.off_park);
+  const FzSmall sl = make_fz_small(L);
+  const bool inj = dp.p > 0.f && dp.masks != nullptr;
+  const int pdl_mode = dependent_launch_mode(net);
+  const bool pdl = pdl_mode == 2 || (pdl_mode == 1 && (n + kBTile - 1) / kBTile <= static_cast<int64_t>(2) * sm_count());
+  int devi = 0;
+  if (cudaGetDevice(&devi) != cudaSuccess || devi < 0 || devi >= 64) devi = 0;
+  static bool carve_set[64] = {false};
+  if (!carve_set[devi]) {
+    cudaFuncSetAttribute(grad_reduce2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(weight_image_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    carve_set[devi] = true;
+  }
+  PINN_CUDA_TRY(launch_pdl(weight_image_kernel, dim3(4 * L), dim3(256), 0, st, pdl, *net, dp.p > 0.f ? dp.scale : 1.0f,
+                           reinterpret_cast<unsigned char*>(ws + p.off_images)));
+#define LAUNCH_F(LL)                                                                                              \
+  {                                                                                                               \
+    auto kern = inj ? mlp_tc_fused_kernel<LL, true> : mlp_tc_fused_kernel<LL, false>;                             \
+    static bool attr_f[64][2] = {};                                                                               \
+    if (!attr_f[devi][inj ? 1 : 0]) {                                                                             \
+      PINN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                       \
+                                         static_cast<int>(p.smem)));                                              \
+      attr_f[devi][inj ? 1 : 0] = true;                                                                           \
+    }                                                                                                             \
+    PINN_CUDA_TRY(launch_pdl(kern, dim3(p.grid), dim3(kFzThreads + 32), p.smem, st, pdl, *net, sl, dp, a, lay));  \
+  }
+  if (L == 2) LAUNCH_F(2) else LAUNCH_F(3)
+#undef LAUNCH_F
+  PINN_CUDA_TRY(cudaGetLastError());
+  const int rg = static_cast<int>((lay.total + kRedCols - 1) / kRedCols);
+  FusedAdam fa{};
+  if (fused != nullptr) fa = *fused;
+  PINN_CUDA_TRY(launch_pdl(grad_reduce2_kernel, dim3(rg), dim3(kRedCols * kRedGroups), 0, st, pdl,
+                           static_cast<const float*>(a.partial), static_cast<const double*>(a.loss_partial), 2 * p.grid, p.grid,
+                           lay.total, grad_flat, loss_sums, fa, lay));
+  return static_cast<int>(cudaGetLastError());
+}
 
 int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropParams& dp, const float* grad_u,
                   const float* grad_s, const float* y, int64_t n_global, float* grad_flat, double* loss_sums, void* workspace,
                   size_t workspace_bytes, cudaStream_t st, const FusedAdam* fused) {
   const int L = net->n_hidden;
+  if (tc_bwd_fused(L, net->flags))
+    return launch_tc_fused(net, x, n, dp, grad_u, grad_s, y, n_global, grad_flat, loss_sums, workspace, workspace_bytes, st, fused);
   TcBwdPlan p = plan_tc_bwd(L, n);
   if (workspace_bytes < p.bytes) return PINN_E_WORKSPACE;
   ParamLayout lay = make_layout(kBH, L);

@@ -1,0 +1,673 @@
+// mlp_tc_fused.cuh -- K2 for the 64-wide net (2 or 3 hidden layers) as ONE kernel per step: forward recompute,
+// dgrad AND every weight / bias gradient of a 128-sample tile inside the CTA that owns the tile.  Nothing per-sample
+// ever reaches HBM (the two-kernel form, K2a + K2b in mlp_tc_bwd.cu, hands 2 KB per sample over through a row table:
+// 4 GB of traffic per step at N = 1M for a 40 MB problem).  Included by mlp_tc_bwd.cu.
+//
+// CTA = 16 compute warps + 1 MMA / TMA warp, one tile in flight.  Compute thread (q, c): TMEM lane quadrant q = warp & 3,
+// sample row = 32 q + lane, column slice c = warp >> 2 (16 of the 64 units of a layer).
+//
+//   chain (serial per tile, 2L tensor-core products, A operand in tensor memory as in K2a):
+//     a0 -> [W1] -> a1 -> [W2] -> a2 -> [Wv0;Wp] -> tail (CUDA cores) -> [(Wv0;Wp)^T] -> d2 -> [W2^T] -> d1 -> [W1^T] -> d0
+//   weight gradients (L + 1 batches per tile, accumulators RESIDENT in tensor memory for the CTA's whole tile range):
+//     the contraction index is the SAMPLE, so both operands must be sample-contiguous (K-major; MN-major TF32 operands
+//     need the 32-byte-base swizzle, tests/cuda/tc_mn_test.cu).  Thread = sample row means a thread holds one K index of
+//     16 features: it scatters them with 4-byte stores into a K-major plane whose chunk stride (LBO) is padded to
+//     4 banks mod 32, so a warp's 32 stores hit 32 banks.  Two staging planes:
+//       DEL (A operand, M = 128): rows [0,64) = tf32 hi part of up to 64 features, rows [64,128) = their lo part;
+//       ACT (B operand):          rows [0,80) = hi part of up to 80 features, rows [80,160) = lo part.
+//     One product per K = 8 slab and per B part:  D[128 x N] += DEL * ACT_hi^T,  D += DEL * ACT_lo^T  -- with hi and lo
+//     of the A side stacked along M, the two MMAs produce all four cross terms (hi*hi, lo*hi, hi*lo, lo*lo); the read-out
+//     adds lanes j and 64 + j (they go out as two partial vectors, summed by the fixed-order reduce).
+//       batch H : DEL = [dz_v0 (32) | du]            ACT = [a_{L-1} (64) | 1]    -> dWv0, dWp, dbv0, dbp
+//       batch l : DEL = delta_l (64)                 ACT = [a_{l-1} (64) | 1]    -> dW_l, db_l          (l = L-1 .. 1)
+//       batch 0T: DEL = [x (8) | av0 (32) | av1 (16) | 1]   ACT = [delta_0 (64) | dz_v1 (16)]   (roles swapped: the result is
+//                 transposed)  -> dW0, db0, dWv1, dbv1;  dWv2 / dbv2 (17 numbers) are summed on the CUDA cores.
+//     The ones row of ACT (row 64) turns a bias sum into one more accumulator column.
+//   Weight planes do not fit next to the staging planes (2L x 32 KB): they are pre-split once per step by
+//   weight_image_kernel into the exact shared-memory image of each UMMA operand and streamed through a two-slot ring
+//   with one 32 KB bulk copy (TMA) per product, issued one product ahead.
+//   Tensor memory (512 columns): D 64 | A hi 64 | A lo 64 | (L + 1) x 80 accumulator columns.
+//
+// Order of the tensor-core work of a backward phase: the chain product first (the compute warps wait for it), the
+// weight-gradient batch behind it -- it runs under the next epilogue.
+#pragma once
+
+namespace pinn {
+
+constexpr int kFzThreads = 512;
+constexpr uint32_t kFzImgBytes = 32768, kFzPlaneBytes = 16384, kFzImgLbo = 1024;
+constexpr uint32_t kDelLbo = 2064, kActLbo = 2576;          // bytes per 4-sample chunk: 128 / 160 rows x 16 B + 16 B of padding
+constexpr int kActLo = 80;                                  // first lo row of ACT
+constexpr uint32_t kDelBytes = 32 * kDelLbo, kActBytes = 32 * kActLbo;
+constexpr uint32_t kColD = 0, kColAhi = 64, kColAlo = 128, kColAcc = 192, kAccW = 80;
+// rows of the 0T batch's DEL plane
+constexpr int kTX = 0, kTV0 = 8, kTV1 = 40, kTOne = 56;
+
+struct FzSmall {      // float offsets into the small-tensor area of shared memory
+  int W0, b[3], bv0, bv1, Wv1, Wv2, bp, bv2, total;
+};
+PINN_HD FzSmall make_fz_small(int L) {
+  FzSmall t{};
+  int o = 0;
+  t.W0 = o; o += 64 * PINN_N_IN;
+  for (int l = 0; l < 3; ++l) { t.b[l] = o; if (l < L) o += 64; }
+  t.bv0 = o; o += 32; t.bv1 = o; o += 16;
+  t.Wv1 = o; o += 16 * 32; t.Wv2 = o; o += 16;
+  t.bp = o; o += 4; t.bv2 = o; o += 4;
+  t.total = o;
+  return t;
+}
+PINN_HD size_t fz_smem_bytes(int L) { return 2 * kFzImgBytes + kDelBytes + kActBytes + static_cast<size_t>(make_fz_small(L).total) * sizeof(float); }
+
+// UMMA operand images of the step's weights, 2L x 32 KB in product order:
+//   [0, L-1) forward W_1..W_{L-1} | L-1 forward heads [Wv0; Wp; 0] | L heads transposed | L+1.. transposed W_{L-1}..W_1
+// every image = tf32 hi plane (16 KB) + lo plane, K-major, 64 rows x 16 B per 4-element K chunk (LBO = 1024 B), dropout
+// scale folded in (see mlp_tc.cu).  One thread splits one float4 of one matrix into both orientations.
+__global__ void __launch_bounds__(256) weight_image_kernel(pinn_net_t net, float wscale, unsigned char* __restrict__ images) {
+  griddep_launch();
+  griddep_wait();            // the weights come from the previous step's optimiser launch
+  const int L = net.n_hidden;
+  const int m = blockIdx.x >> 2;                                 // 0 .. L-2: W_{m+1};  L-1: heads
+  const int idx = (blockIdx.x & 3) * 256 + threadIdx.x, j = idx & 63, kc = idx >> 6;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (m < L - 1) v = __ldg(reinterpret_cast<const float4*>(net.W[m + 1] + j * 64) + kc);
+  else if (j < 32) v = __ldg(reinterpret_cast<const float4*>(net.Wv0 + j * 64) + kc);
+  else if (j == 32) v = __ldg(reinterpret_cast<const float4*>(net.Wp) + kc);
+  const float vv[4] = {v.x * wscale, v.y * wscale, v.z * wscale, v.w * wscale};
+  float h[4], lo[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) { h[r] = tc::tf32_hi(vv[r]); lo[r] = vv[r] - h[r]; }
+  unsigned char* fw = images + static_cast<size_t>(m) * kFzImgBytes;
+  unsigned char* bw = images + static_cast<size_t>(2 * L - 1 - m) * kFzImgBytes;
+  *reinterpret_cast<float4*>(fw + kc * kFzImgLbo + j * 16) = make_float4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<float4*>(fw + kFzPlaneBytes + kc * kFzImgLbo + j * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {        // transposed: row n = 4 kc + r, K index j
+    const size_t off = static_cast<size_t>(j >> 2) * kFzImgLbo + static_cast<size_t>(4 * kc + r) * 16 + (j & 3) * 4;
+    *reinterpret_cast<float*>(bw + off) = h[r];
+    *reinterpret_cast<float*>(bw + kFzPlaneBytes + off) = lo[r];
+  }
+}
+
+struct FzArgs {
+  const float* x; int64_t n;
+  const float* grad_u; const float* grad_s; const float* y; float inv_n_global;
+  const unsigned char* images;
+  float* partial;            // [2 * grid][lay.total]: per CTA the hi-lane and the lo-lane sums
+  double* loss_partial;      // [grid][4]
+  float* park;               // [grid][L][4][512] float4 (see the kernel)
+};
+
+#ifdef PINN_TIMELINE
+__device__ long long g_tlf[160];      // CTA 0, compute thread 0: clock64 at the stamps below
+#define TLF(i) do { if (blockIdx.x == 0 && tid == 0 && (i) < 160) g_tlf[i] = clock64(); } while (0)
+#else
+#define TLF(i) do { } while (0)
+#endif
+
+template <int L, bool INJ>
+__global__ void __launch_bounds__(kFzThreads + 32, 1)
+mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropParams dp, FzArgs a, ParamLayout pl) {
+  static_assert(L == 2 || L == 3, "tensor memory holds L + 1 <= 4 accumulator blocks");
+  constexpr int H = 64;
+  extern __shared__ __align__(1024) unsigned char fsm[];
+  __shared__ __align__(8) uint64_t bar_ready, bar_chain, bar_wg, bar_full[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ double lred[4][4];
+  __shared__ float wred[16][8];
+  unsigned char* const ring = fsm;
+  unsigned char* const DEL = fsm + 2 * kFzImgBytes;
+  unsigned char* const ACT = DEL + kDelBytes;
+  float* const sm = reinterpret_cast<float*>(ACT + kActBytes);
+  const int tid = threadIdx.x, warp = tc::uniform_warp_idx();
+  const int Dm = L * H + H / 2;
+  griddep_launch();
+
+  if (tid == 0) {
+    tc::mbar_init(&bar_ready, kFzThreads); tc::mbar_init(&bar_chain, 1); tc::mbar_init(&bar_wg, 1);
+    tc::mbar_init(&bar_full[0], 1); tc::mbar_init(&bar_full[1], 1);
+    tc::fence_mbar_init();
+  }
+  __syncwarp();
+  if (warp == 0) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
+  // the ones rows of ACT (hi rows 64..79: row 64 = 1, the others 0; rewritten after every 0T batch, which parks dz_v1 there)
+  for (int i = tid; i < 16 * 128; i += blockDim.x) {
+    const int r = 64 + (i >> 7), s = i & 127;
+    *reinterpret_cast<float*>(ACT + (s >> 2) * kActLbo + r * 16 + (s & 3) * 4) = r == 64 ? 1.0f : 0.0f;
+  }
+  griddep_wait();            // weights (and their images) come from launches earlier in the stream
+  const bool drop_on = dp.p > 0.f;
+  const float wscale = drop_on ? dp.scale : 1.0f;
+  if (tid < kFzThreads) {
+    // small tensors: one element per thread (W0 and Wv1 are 512 floats each); biases / Wv2 / bp / bv2 laid over the thread index
+    sm[sl.W0 + tid] = __ldg(net.W[0] + tid) * kTanhArg;
+    sm[sl.Wv1 + tid] = __ldg(net.Wv1 + tid);
+    if (tid < 64 * L) sm[sl.b[tid >> 6] + (tid & 63)] = __ldg(net.b[tid >> 6] + (tid & 63)) * kTanhArg;
+    else if (tid >= 256 && tid < 288) sm[sl.bv0 + tid - 256] = __ldg(net.bv0 + tid - 256) * kTanhArg;
+    else if (tid >= 288 && tid < 304) sm[sl.bv1 + tid - 288] = __ldg(net.bv1 + tid - 288) * kTanhArg;
+    else if (tid >= 304 && tid < 320) sm[sl.Wv2 + tid - 304] = __ldg(net.Wv2 + tid - 304);
+    else if (tid == 320) sm[sl.bp] = __ldg(net.bp);
+    else if (tid == 321) sm[sl.bv2] = __ldg(net.bv2);
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const int64_t n_tiles = (a.n + 127) / 128;
+
+  if (warp == kFzThreads / 32) {
+    // ======================================================================================== MMA / TMA warp
+    const uint32_t ring_u = tc::smem_u32(ring), del_u = tc::smem_u32(DEL), act_u = tc::smem_u32(ACT);
+    const uint32_t idesc64 = tc::make_idesc_tf32(128, 64), idesc48 = tc::make_idesc_tf32(128, 48), idesc80 = tc::make_idesc_tf32(128, 80);
+    uint32_t rp = 0, fpar = 0, g = 0;
+    if (tc::elect_one()) {
+      tc::mbar_expect_tx(&bar_full[0], kFzImgBytes);
+      tc::bulk_g2s(ring, a.images, kFzImgBytes, &bar_full[0]);
+    }
+    __syncwarp();
+    bool first = true;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const bool has_next = tile + gridDim.x < n_tiles;
+#pragma unroll
+      for (int p = 0; p <= 2 * L; ++p) {
+        tc::mbar_wait(&bar_ready, rp);
+        rp ^= 1u;
+        __syncwarp();
+        if (tc::elect_one()) {
+          tc::fence_after_sync();
+          if (p < 2 * L) {
+            // the other slot's last reader (the product before this one) has completed: the compute warps saw its commit
+            const int nxt = p + 1 < 2 * L ? p + 1 : (has_next ? 0 : -1);
+            if (nxt >= 0) {
+              const uint32_t s2 = (g + 1) & 1u;
+              tc::mbar_expect_tx(&bar_full[s2], kFzImgBytes);
+              tc::bulk_g2s(ring + s2 * kFzImgBytes, a.images + static_cast<size_t>(nxt) * kFzImgBytes, kFzImgBytes, &bar_full[s2]);
+            }
+            const uint32_t s1 = g & 1u;
+            tc::mbar_wait(&bar_full[s1], (fpar >> s1) & 1u);
+            fpar ^= 1u << s1;
+            const uint64_t bh = tc::make_desc(ring_u + s1 * kFzImgBytes, kFzImgLbo, 128);
+            const uint64_t bl = tc::make_desc(ring_u + s1 * kFzImgBytes + kFzPlaneBytes, kFzImgLbo, 128);
+            if (p == L - 1) tc::issue_3xtf32_ts<64>(tmem + kColD, tmem + kColAhi, tmem + kColAlo, bh, bl, kFzImgLbo, idesc48);
+            else if (p == L) tc::issue_3xtf32_ts<48>(tmem + kColD, tmem + kColAhi, tmem + kColAlo, bh, bl, kFzImgLbo, idesc64);
+            else tc::issue_3xtf32_ts<64>(tmem + kColD, tmem + kColAhi, tmem + kColAlo, bh, bl, kFzImgLbo, idesc64);
+            tc::umma_commit(&bar_chain);
+            ++g;
+          }
+          if (p >= L) {
+            // weight-gradient batch of the operands staged for this phase
+            const int acc = p == L ? 0 : (p == 2 * L ? L : 2 * L - p);
+            const uint32_t d = tmem + kColAcc + kAccW * static_cast<uint32_t>(acc);
+            const uint64_t a0 = tc::make_desc(del_u, kDelLbo, 128);
+            const uint64_t bh0 = tc::make_desc(act_u, kActLbo, 128), bl0 = tc::make_desc(act_u + kActLo * 16, kActLbo, 128);
+            const uint32_t id_lo = p == 2 * L ? idesc80 : idesc64;
+            constexpr uint64_t as = (2u * kDelLbo) >> 4, bs = (2u * kActLbo) >> 4;
+#pragma unroll
+            for (int ks = 0; ks < 16; ++ks) {
+              tc::umma_tf32(d, a0 + ks * as, bh0 + ks * bs, idesc80, (ks != 0 || !first) ? 1u : 0u);
+              tc::umma_tf32(d, a0 + ks * as, bl0 + ks * bs, id_lo, 1u);
+            }
+            tc::umma_commit(&bar_wg);
+          }
+        }
+        __syncwarp();
+      }
+      first = false;
+    }
+  } else {
+    // ======================================================================================== compute warps
+    const int q = warp & 3, c = warp >> 2, lane = tid & 31, row = q * 32 + lane, cb = 16 * c;
+    const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t tD = tmem + kColD + lane_sel, tAh = tmem + kColAhi + lane_sel, tAl = tmem + kColAlo + lane_sel;
+    unsigned char* const del_s = DEL + (row >> 2) * kDelLbo + (row & 3) * 4;
+    unsigned char* const act_s = ACT + (row >> 2) * kActLbo + (row & 3) * 4;
+    auto del_st = [&](int f, float h, float l) {
+      *reinterpret_cast<float*>(del_s + f * 16) = h;
+      *reinterpret_cast<float*>(del_s + (64 + f) * 16) = l;
+    };
+    auto act_st = [&](int r, float h, float l) {
+      *reinterpret_cast<float*>(act_s + r * 16) = h;
+      *reinterpret_cast<float*>(act_s + (kActLo + r) * 16) = l;
+    };
+    uint32_t chain_par = 0, wg_par = 0;
+    bool wg_pending = false;
+    auto arrive_ready = [&] {
+      tc::tmem_wait_st();
+      tc::fence_proxy_async();
+      tc::fence_before_sync();
+      tc::mbar_arrive(&bar_ready);
+    };
+    auto wait_chain = [&] {
+      tc::mbar_wait(&bar_chain, chain_par);
+      chain_par ^= 1u;
+      __syncwarp();
+      tc::fence_after_sync();
+    };
+    auto wait_wg = [&] {          // the batch that reads the staging planes has drained them
+      if (wg_pending) { tc::mbar_wait(&bar_wg, wg_par); wg_par ^= 1u; wg_pending = false; }
+      __syncwarp();
+    };
+    auto qbar = [&] {             // the four warps of a lane quadrant (the four column slices of 32 sample rows)
+      tc::tmem_wait_st();
+      tc::fence_before_sync();
+      asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory");
+      tc::fence_after_sync();
+    };
+    auto split16 = [&](const float (&v)[16], float (&h)[16], float (&lo)[16]) {
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) {
+        h[i] = tc::tf32_hi_fast(v[i]); h[i + 1] = tc::tf32_hi_fast(v[i + 1]);
+        const float2 l2 = __ffma2_rn(make_float2(h[i], h[i + 1]), make_float2(-1.0f, -1.0f), make_float2(v[i], v[i + 1]));   // v - h, exact
+        lo[i] = l2.x; lo[i + 1] = l2.y;
+      }
+    };
+    auto keep16 = [&](const KeepSrc<INJ>& ks, bool active, uint32_t layer) {      // bit i = unit cb + i of dropout layer `layer`
+      uint32_t bits = 0xffffu;
+      if (active) {
+        bits = 0u;
+#pragma unroll
+        for (int g8 = 0; g8 < 16; g8 += 8) {
+          bool k[8];
+          ks.get8(dp, layer, static_cast<uint32_t>(cb + g8), layer * H, k);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bits |= (k[i] ? 1u : 0u) << (g8 + i);
+        }
+      }
+      return bits;
+    };
+    const bool no_lv = (net.flags & PINN_NET_NO_LOGVAR) != 0;
+    float l_nll = 0.f, l_abs = 0.f, l_mse = 0.f, l_cnt = 0.f;        // at most one term per tile and thread: fp32 is exact enough, the tree below is double
+    float g_wv2[4] = {0.f, 0.f, 0.f, 0.f}, g_bv2 = 0.f;
+    // Parking lot (global, 32 KB per slot and CTA, L2-resident: rewritten every tile): the activations of layers 0..L-2
+    // and the tail's (av0, v1, dz_v1) wait here between the forward and the backward phase that needs them -- 64 live
+    // registers per thread otherwise (the 17th warp caps the kernel at 96).  Slot layout [4][512] float4: coalesced.
+    float4* const park = reinterpret_cast<float4*>(a.park) + static_cast<size_t>(blockIdx.x) * L * 4 * kFzThreads + tid;
+    auto park_st = [&](int slot, const float (&v)[16]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) park[(slot * 4 + i) * kFzThreads] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    };
+    auto park_ld = [&](int slot, float (&v)[16]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 t = __ldcg(park + (slot * 4 + i) * kFzThreads);
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+      }
+    };
+    int tl = 0;
+    (void)tl;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t s = tile * 128 + row;
+      const bool valid = s < a.n;
+      const bool active = drop_on && (!INJ || valid);       // injected masks: tail rows of the last tile have no mask row
+      const uint64_t sg = static_cast<uint64_t>(dp.sample_offset + s);
+      KeepSrc<INJ> ks;
+      ks.s_lo = static_cast<uint32_t>(sg); ks.s_hi = static_cast<uint32_t>(sg >> 32);
+      ks.pass = static_cast<uint32_t>(dp.pass_offset);
+      ks.mrow = INJ ? dp.masks + static_cast<size_t>(valid ? s : 0) * Dm : nullptr;
+      float acur[16];              // this thread's 16 masked activations of the current trunk layer (without the dropout scale)
+      uint32_t kb[L];
+      TLF(tl++);
+      // ============================ forward ============================
+      {
+        float xr[PINN_N_IN];
+        if (valid) {
+          const float4* px = reinterpret_cast<const float4*>(a.x + s * PINN_N_IN);
+          const float4 q0 = __ldg(px), q1 = __ldg(px + 1);
+          xr[0] = q0.x; xr[1] = q0.y; xr[2] = q0.z; xr[3] = q0.w; xr[4] = q1.x; xr[5] = q1.y; xr[6] = q1.z; xr[7] = q1.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < PINN_N_IN; ++i) xr[i] = 0.f;
+        }
+        kb[0] = keep16(ks, active, 0u);
+        const float* W0 = sm + sl.W0 + cb * PINN_N_IN;
+        const float* b0 = sm + sl.b[0] + cb;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4 w0 = *reinterpret_cast<const float4*>(W0 + i * PINN_N_IN);
+          const float4 w1 = *reinterpret_cast<const float4*>(W0 + i * PINN_N_IN + 4);
+          float z = b0[i];
+          z = fmaf(w0.x, xr[0], z); z = fmaf(w0.y, xr[1], z); z = fmaf(w0.z, xr[2], z); z = fmaf(w0.w, xr[3], z);
+          z = fmaf(w1.x, xr[4], z); z = fmaf(w1.y, xr[5], z); z = fmaf(w1.z, xr[6], z); z = fmaf(w1.w, xr[7], z);
+          acur[i] = ((kb[0] >> i) & 1u) ? tanh_pre(z) : 0.f;
+        }
+        if (L > 1) park_st(0, acur);
+        float h[16], lo[16];
+        split16(acur, h, lo);
+        tc::tmem_st16(tAh + cb, h);
+        tc::tmem_st16(tAl + cb, lo);
+      }
+      arrive_ready();
+#pragma unroll
+      for (int l = 1; l < L; ++l) {
+        kb[l] = keep16(ks, active, static_cast<uint32_t>(l));        // drawn while the tensor core works
+        wait_chain();
+        float z[16];
+        tc::tmem_ld16(tD + cb, z);
+        tc::tmem_wait_ld();
+        const float* bl = sm + sl.b[l] + cb;
+#pragma unroll
+        for (int g8 = 0; g8 < 16; g8 += 8) {
+          const float4 bA = *reinterpret_cast<const float4*>(bl + g8), bB = *reinterpret_cast<const float4*>(bl + g8 + 4);
+          const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+          float t8[8];
+          tanh8_prescaled(z + g8, bb, t8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acur[g8 + i] = ((kb[l] >> (g8 + i)) & 1u) ? t8[i] : 0.f;
+        }
+        if (l < L - 1) park_st(l, acur);
+        float h[16], lo[16];
+        split16(acur, h, lo);
+        tc::tmem_st16(tAh + cb, h);
+        tc::tmem_st16(tAl + cb, lo);
+        arrive_ready();
+      }
+      // ---- heads (rows 0..31 = Wv0, row 32 = Wp) and the variance head's tail, split over the row's four threads:
+      //      thread c owns units 8c..8c+7 of the 32-wide layer and units 4c..4c+3 of the 16-wide layer; three hand-overs
+      //      through free tensor-memory columns (A hi 0..31: av0, A hi 48..51: partial raw variances, A lo 48..63: dz_v1)
+      uint32_t kbv = 0xffu;
+      if (active) {
+        bool k[8];
+        ks.get8(dp, static_cast<uint32_t>(L), static_cast<uint32_t>(8 * c), static_cast<uint32_t>(L * H), k);
+        kbv = 0u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) kbv |= (k[i] ? 1u : 0u) << i;
+      }
+      wait_chain();
+      float dzv0[8], du = 0.f, dv = 0.f;
+      {
+        float tailv[16];           // [0,8) av0 (scaled), [8,12) v1, [12,16) dz_v1: parked for the 0T batch
+        float zv[8], zu[8];
+        tc::tmem_ld8(tD + 8 * c, zv);
+        tc::tmem_ld8(tD + 32, zu);
+        tc::tmem_wait_ld();
+        const float u = zu[0] + sm[sl.bp];
+        const float* bv0 = sm + sl.bv0 + 8 * c;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tailv[i] = ((kbv >> i) & 1u) ? tanh_pre(fmaf(zv[i], kTanhArg, bv0[i])) * wscale : 0.f;
+        tc::tmem_st8(tAh + 8 * c, tailv);
+        qbar();
+        const float* Wv1 = sm + sl.Wv1;
+        float2 acc[4][2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k][0] = acc[k][1] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {          // the 32 av0 of the row, 16 at a time
+          float v0[16];
+          tc::tmem_ld16(tAh + 16 * hf, v0);
+          tc::tmem_wait_ld();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float* wr = Wv1 + (4 * c + k) * 32 + 16 * hf;
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const float4 w = *reinterpret_cast<const float4*>(wr + 4 * i4);
+              acc[k][0] = ffma2(make_float2(w.x, w.y), make_float2(v0[4 * i4], v0[4 * i4 + 1]), acc[k][0]);
+              acc[k][1] = ffma2(make_float2(w.z, w.w), make_float2(v0[4 * i4 + 2], v0[4 * i4 + 3]), acc[k][1]);
+            }
+          }
+        }
+        float pv = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          tailv[8 + k] = tanh_pre(fmaf((acc[k][0].x + acc[k][0].y) + (acc[k][1].x + acc[k][1].y), kTanhArg, sm[sl.bv1 + 4 * c + k]));
+          pv = fmaf(sm[sl.Wv2 + 4 * c + k], tailv[8 + k], pv);
+        }
+        tc::tmem_st1(tAh + 48 + c, pv);
+        qbar();
+        float pvs[4];
+        tc::tmem_ld4(tAh + 48, pvs);
+        tc::tmem_wait_ld();
+        const float vraw = sm[sl.bv2] + ((pvs[0] + pvs[1]) + (pvs[2] + pvs[3]));
+        const float lv = logvar_out(vraw, no_lv);
+        float ds = 0.f;
+        if (valid) {
+          if (a.grad_u != nullptr) {
+            du = __ldg(a.grad_u + s);
+            ds = a.grad_s ? __ldg(a.grad_s + s) : 0.f;
+          } else {
+            const float yv = __ldg(a.y + s);
+            const float e = expf(-lv), diff = yv - u;
+            du = -e * diff * a.inv_n_global;
+            const float sgn = lv > 0.f ? 1.f : (lv < 0.f ? -1.f : 0.f);
+            ds = (-0.5f * e * diff * diff + 0.5f + 0.01f * sgn) * a.inv_n_global;
+            if (c == 0) {
+              l_nll += 0.5f * e * diff * diff + 0.5f * lv;
+              l_abs += fabsf(lv);
+              l_mse += diff * diff;
+              l_cnt += 1.0f;
+            }
+          }
+        }
+        dv = no_lv ? 0.f : ds * dlogvar_dv(vraw);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tailv[12 + k] = dv * sm[sl.Wv2 + 4 * c + k] * (1.0f - tailv[8 + k] * tailv[8 + k]);
+        tc::tmem_st4(tAl + 48 + 4 * c, tailv + 12);
+        qbar();
+        float dzs[16];
+        tc::tmem_ld16(tAl + 48, dzs);
+        tc::tmem_wait_ld();
+        // d v0[i] = sum_k Wv1[k][i] dz1[k];  dz_v0 = d v0 * keep-mask * scale * (1 - a^2)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dzv0[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float4 wa = *reinterpret_cast<const float4*>(Wv1 + k * 32 + 8 * c), wb = *reinterpret_cast<const float4*>(Wv1 + k * 32 + 8 * c + 4);
+          dzv0[0] = fmaf(wa.x, dzs[k], dzv0[0]); dzv0[1] = fmaf(wa.y, dzs[k], dzv0[1]);
+          dzv0[2] = fmaf(wa.z, dzs[k], dzv0[2]); dzv0[3] = fmaf(wa.w, dzs[k], dzv0[3]);
+          dzv0[4] = fmaf(wb.x, dzs[k], dzv0[4]); dzv0[5] = fmaf(wb.y, dzs[k], dzv0[5]);
+          dzv0[6] = fmaf(wb.z, dzs[k], dzv0[6]); dzv0[7] = fmaf(wb.w, dzs[k], dzv0[7]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float av = tailv[i] * (drop_on ? dp.keep : 1.0f);
+          const float mk = ((kbv >> i) & 1u) ? wscale : 0.f;
+          dzv0[i] = dzv0[i] * mk * (1.0f - av * av);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) g_wv2[k] = fmaf(dv, tailv[8 + k], g_wv2[k]);
+        if (c == 0) g_bv2 += dv;
+        park_st(L - 1, tailv);
+        // every thread of the row has passed the third barrier, so the av0 / partial columns are dead and the
+        // heads^T operand may overwrite them
+      }
+      // ============================ backward ============================
+      // chain operand [dz_v0 (32 cols) | du | 0 ...] (K = 48) and batch H
+      {
+        float h8[8], l8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { h8[i] = tc::tf32_hi_fast(dzv0[i]); l8[i] = dzv0[i] - h8[i]; }
+        tc::tmem_st8(tAh + 8 * c, h8);
+        tc::tmem_st8(tAl + 8 * c, l8);
+        const float duh = tc::tf32_hi_fast(du), dul = du - duh;
+        if (c == 0) {
+          const float e8[8] = {duh, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, f8[8] = {dul, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          tc::tmem_st8(tAh + 32, e8);
+          tc::tmem_st8(tAl + 32, f8);
+        } else if (c == 1) {
+          const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          tc::tmem_st8(tAh + 40, z8);
+          tc::tmem_st8(tAl + 40, z8);
+        }
+        wait_wg();                 // the previous tile's 0T batch
+#pragma unroll
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<float*>(act_s + (64 + 4 * c + i) * 16) = (c == 0 && i == 0) ? 1.0f : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) del_st(8 * c + i, h8[i], l8[i]);
+        if (c == 0) del_st(32, duh, dul);
+        float h[16], lo[16];
+        split16(acur, h, lo);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) act_st(cb + i, h[i], lo[i]);
+      }
+      arrive_ready();
+      wg_pending = true;
+#pragma unroll
+      for (int l = L - 1; l >= 0; --l) {
+        float nxt[16];             // l > 0: activations of layer l - 1;  l == 0: the parked tail values
+        park_ld(l > 0 ? l - 1 : L - 1, nxt);          // in flight while the tensor core works
+        float x2[2] = {0.f, 0.f};
+        if (l == 0 && valid) { const float2 t = __ldg(reinterpret_cast<const float2*>(a.x + s * PINN_N_IN) + c); x2[0] = t.x; x2[1] = t.y; }
+        wait_chain();
+        float h[16], lo[16];
+        {
+          float z[16];
+          tc::tmem_ld16(tD + cb, z);
+          tc::tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i)     // z already carries the dropout scale (folded into W^T); dropped units have a = 0
+            z[i] = ((kb[l] >> i) & 1u) ? z[i] * fmaf(-acur[i], acur[i], 1.0f) : 0.f;
+          split16(z, h, lo);
+        }
+        if (l > 0) {
+          tc::tmem_st16(tAh + cb, h);
+          tc::tmem_st16(tAl + cb, lo);
+          wait_wg();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) del_st(cb + i, h[i], lo[i]);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acur[i] = nxt[i];
+          split16(acur, h, lo);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) act_st(cb + i, h[i], lo[i]);
+        } else {
+          // batch 0T (roles swapped): DEL = [x | av0 | av1 | 1], ACT = [delta_0 | dz_v1]
+          wait_wg();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) act_st(cb + i, h[i], lo[i]);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) { const float hh = tc::tf32_hi_fast(x2[i]); del_st(kTX + 2 * c + i, hh, x2[i] - hh); }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { const float hh = tc::tf32_hi_fast(nxt[i]); del_st(kTV0 + 8 * c + i, hh, nxt[i] - hh); }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { const float hh = tc::tf32_hi_fast(nxt[8 + i]); del_st(kTV1 + 4 * c + i, hh, nxt[8 + i] - hh); }
+          if (c == 0) del_st(kTOne, 1.0f, 0.0f);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { const float hh = tc::tf32_hi_fast(nxt[12 + i]); act_st(64 + 4 * c + i, hh, nxt[12 + i] - hh); }
+        }
+        arrive_ready();
+        wg_pending = true;
+      }
+    }
+    TLF(tl++);
+    // ---------------------------------------------------------------- accumulators -> this CTA's two partial vectors
+    wait_wg();
+    tc::fence_after_sync();
+    {
+      float* const part = a.partial + (static_cast<size_t>(2 * blockIdx.x) + (q >> 1)) * pl.total;       // lanes 0..63: hi parts, 64..127: lo parts
+      const int lr = row & 63;
+      const uint32_t tacc = tmem + kColAcc + lane_sel;
+      float v[16];
+      auto store16_scaled = [&](float* dst) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<float4*>(dst + i) = make_float4(v[i] * wscale, v[i + 1] * wscale, v[i + 2] * wscale, v[i + 3] * wscale);
+      };
+#pragma unroll
+      for (int l = 1; l < L; ++l) {
+        tc::tmem_ld16(tacc + kAccW * l + cb, v);
+        tc::tmem_wait_ld();
+        store16_scaled(part + pl.offW[l] + lr * 64 + cb);
+        if (c == 0) {
+          float b8[8];
+          tc::tmem_ld8(tacc + kAccW * l + 64, b8);
+          tc::tmem_wait_ld();
+          part[pl.offb[l] + lr] = b8[0];
+        }
+      }
+      // batch H: lanes 0..31 = dWv0 rows, lane 32 = dWp; column 64 = their biases
+      tc::tmem_ld16(tacc + cb, v);
+      tc::tmem_wait_ld();
+      if (lr < 32) store16_scaled(part + pl.offWv0 + lr * 64 + cb);
+      else if (lr == 32) store16_scaled(part + pl.offWp + cb);
+      if (c == 0) {
+        float b8[8];
+        tc::tmem_ld8(tacc + 64, b8);
+        tc::tmem_wait_ld();
+        if (lr < 32) part[pl.offbv0 + lr] = b8[0];
+        else if (lr == 32) part[pl.offbp] = b8[0];
+      }
+      // batch 0T (transposed): lanes 0..7 = input feature i, columns 0..63 = unit j -> dW0[j][i]; lane 56 -> db0, dbv1;
+      // lanes 8..39 = av0 unit, columns 64..79 = dz_v1 unit k -> dWv1[k][i]
+      tc::tmem_ld16(tacc + kAccW * L + cb, v);
+      tc::tmem_wait_ld();
+      if (lr < 8) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) part[pl.offW[0] + (cb + i) * PINN_N_IN + lr] = v[i];
+      } else if (lr == kTOne) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) part[pl.offb[0] + cb + i] = v[i];
+      }
+      if (c == 1) {
+        tc::tmem_ld16(tacc + kAccW * L + 64, v);
+        tc::tmem_wait_ld();
+        if (lr >= kTV0 && lr < kTV0 + 32) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) part[pl.offWv1 + k * 32 + lr - kTV0] = v[k];
+        } else if (lr == kTOne) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) part[pl.offbv1 + k] = v[k];
+        }
+      }
+    }
+    // dWv2 / dbv2 and the loss sums: xor tree over the warp's 32 rows, then the four quadrants in order
+    {
+      float w5[5] = {g_wv2[0], g_wv2[1], g_wv2[2], g_wv2[3], g_bv2};
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w5[k] += __shfl_xor_sync(0xffffffffu, w5[k], o);
+        if (lane == 0) wred[warp][k] = w5[k];
+      }
+      if (c == 0) {
+        double vals[4] = {static_cast<double>(l_nll), static_cast<double>(l_abs), static_cast<double>(l_mse), static_cast<double>(l_cnt)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          double t = vals[k];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+          if (lane == 0) lred[q][k] = t;
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (tid < 17) {
+    float* const part_hi = a.partial + static_cast<size_t>(2 * blockIdx.x) * pl.total;
+    float* const part_lo = part_hi + pl.total;
+    const int k = tid;                  // 0..15: dWv2[k] (slice c = k / 4, entry k % 4); 16: dbv2 (slice 0, entry 4)
+    const int cc = k < 16 ? k >> 2 : 0, e = k < 16 ? k & 3 : 4;
+    const float t = (wred[4 * cc][e] + wred[4 * cc + 1][e]) + (wred[4 * cc + 2][e] + wred[4 * cc + 3][e]);
+    if (k < 16) { part_hi[pl.offWv2 + k] = t; part_lo[pl.offWv2 + k] = 0.f; }
+    else { part_hi[pl.offbv2] = t; part_lo[pl.offbv2] = 0.f; }
+  } else if (tid >= 32 && tid < 36) {
+    const int k = tid - 32;
+    a.loss_partial[static_cast<size_t>(blockIdx.x) * 4 + k] = (lred[0][k] + lred[1][k]) + (lred[2][k] + lred[3][k]);
+  }
+  if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
+}
+
+struct FzPlan { int grid; size_t smem, off_partial, off_images, off_park, bytes; };
+static FzPlan plan_fused(int L, int64_t n) {
+  FzPlan p{};
+  const ParamLayout lay = make_layout(64, L);
+  const int sms = sm_count();
+  const int64_t tiles = (n + 127) / 128;
+  p.grid = static_cast<int>(tiles < sms ? (tiles > 0 ? tiles : 1) : sms);
+  p.smem = fz_smem_bytes(L);
+  size_t off = static_cast<size_t>(p.grid) * 4 * sizeof(double);
+  off = (off + 255) & ~static_cast<size_t>(255);
+  p.off_partial = off;
+  off += static_cast<size_t>(2 * p.grid) * lay.total * sizeof(float);
+  off = (off + 255) & ~static_cast<size_t>(255);
+  p.off_images = off;
+  off += static_cast<size_t>(2 * L) * kFzImgBytes;
+  p.off_park = off;
+  off += static_cast<size_t>(p.grid) * L * 4 * kFzThreads * sizeof(float4);
+  p.bytes = off;
+  return p;
+}
+
+}  // namespace pinn

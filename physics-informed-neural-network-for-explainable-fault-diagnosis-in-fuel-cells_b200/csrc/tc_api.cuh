@@ -23,7 +23,7 @@ int launch_wide_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const D
 int dependent_launch_mode(const pinn_net_t* net);
 // Tensor-core backward (mlp_tc_bwd.cu): 64-wide nets with 2..4 hidden layers.
 bool tc_bwd_covers(const pinn_net_t* net);
-size_t tc_bwd_workspace_bytes(int L, int64_t n);
+size_t tc_bwd_workspace_bytes(int L, int64_t n, int flags = -1);     // flags < 0: enough for any path
 int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropParams& dp, const float* grad_u,
                   const float* grad_s, const float* y, int64_t n_global, float* grad_flat, double* loss_sums, void* workspace,
                   size_t workspace_bytes, cudaStream_t st, const FusedAdam* fused = nullptr);

@@ -58,6 +58,10 @@ class Net:
         return C.byref(self.desc)
 
     @property
+    def flags(self) -> int:
+        return self.base_flags | _EXTRA_NET_FLAGS
+
+    @property
     def mask_width(self) -> int:
         return self.n_hidden * self.width + self.width // 2
 
@@ -69,15 +73,17 @@ _PHASE_FLAGS = 0
 
 
 @contextmanager
-def path_flags(no_tc_fwd=False, no_tc_bwd=False, no_wide_tc=False, dependent_launch=None, no_phase_cluster=False):
+def path_flags(no_tc_fwd=False, no_tc_bwd=False, no_wide_tc=False, dependent_launch=None, no_phase_cluster=False,
+               no_fused_bwd=False):
     """``with path_flags(no_tc_fwd=True): ...`` -- inside the block the 64-wide forward / MC sweep run on the FFMA
     kernels (likewise ``no_tc_bwd``, ``no_wide_tc``); ``dependent_launch`` = 0 never / 2 always chain a step's launches
     with programmatic dependent launch (default 1: small batches only); ``no_phase_cluster`` keeps ``scalar_phase`` on
-    the cooperative-grid form."""
+    the cooperative-grid form; ``no_fused_bwd`` runs the 64-wide backward as the two-kernel form (K2a + row table +
+    K2b) instead of the one-kernel form."""
     global _EXTRA_NET_FLAGS, _PHASE_FLAGS
     prev = (_EXTRA_NET_FLAGS, _PHASE_FLAGS)
     f = (_abi.NET_NO_TC_FWD if no_tc_fwd else 0) | (_abi.NET_NO_TC_BWD if no_tc_bwd else 0) | \
-        (_abi.NET_NO_WIDE_TC if no_wide_tc else 0)
+        (_abi.NET_NO_WIDE_TC if no_wide_tc else 0) | (_abi.NET_NO_FUSED_BWD if no_fused_bwd else 0)
     if dependent_launch is not None:
         f |= {0: _abi.NET_PDL_NEVER, 1: 0, 2: _abi.NET_PDL_ALWAYS}[int(dependent_launch)]
     _EXTRA_NET_FLAGS |= f
@@ -193,7 +199,7 @@ def mlp_backward(net: Net, x: torch.Tensor, drop: Optional[PinnDropout], grad_u=
         grad_flat = torch.zeros(total, device=x.device, dtype=torch.float32)
     if loss_sums is None:
         loss_sums = torch.zeros(4, device=x.device, dtype=torch.float64)
-    nb = L.pinn_mlp_bwd_workspace_bytes(net.width, net.n_hidden, n)
+    nb = L.pinn_mlp_bwd_workspace_bytes_flags(net.width, net.n_hidden, n, net.flags)
     ws = _workspace("bwd", nb, x.device)
     for t, nm in ((grad_u, "grad_u"), (grad_logvar, "grad_logvar"), (y, "y")):
         if t is not None:
@@ -376,7 +382,7 @@ def train_dnn_step(net: Net, x, drop: Optional[PinnDropout], y, n_global: int, p
     _require_cuda(y, "y")
     n = x.shape[0]
     L = _abi.lib()
-    nb = L.pinn_mlp_bwd_workspace_bytes(net.width, net.n_hidden, n)
+    nb = L.pinn_mlp_bwd_workspace_bytes_flags(net.width, net.n_hidden, n, net.flags)
     ws = _workspace("bwd", nb, x.device)
     with torch.cuda.device(x.device):
         check(L.pinn_train_dnn_steps(net.ref(), ptr(x), n, C.byref(drop) if drop is not None else None, ptr(y),
