@@ -379,6 +379,9 @@ struct FusedAdam {
   float* params; float* m; float* v;
   int64_t* step_counter;
   AdamHyper h;
+  // one-kernel 64-wide backward (mlp_tc_fused.cuh): the optimiser launch also rewrites the UMMA weight images of the
+  // entries it updates, so the next step of the same call needs no image launch (`images_valid`: this step's are in place)
+  unsigned char* images; float wscale; int images_valid;
 };
 
 }  // namespace pinn

@@ -445,10 +445,10 @@ extern "C" int pinn_mlp_bwd(const pinn_net_t* net, const float* x, int64_t n, co
 // ONE call.  On the tensor-core backward path the gradient reduce and the optimiser are the same launch; on the other
 // paths it is pinn_mlp_bwd followed by pinn_adam_step.  `net`'s tensors must be views into `params_flat` in the
 // pinn_param_count layout (that is what makes one flat optimiser launch possible).
-extern "C" int pinn_train_dnn_step(const pinn_net_t* net, const float* x, int64_t n, const pinn_dropout_t* drop, const float* y,
-                                   int64_t n_global, float* params_flat, float* exp_avg, float* exp_avg_sq, int64_t* step_counter,
-                                   double lr0, double gamma, int64_t step_size, float* grad_flat, double* loss_sums, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
+static int train_dnn_step_impl(const pinn_net_t* net, const float* x, int64_t n, const pinn_dropout_t* drop, const float* y,
+                               int64_t n_global, float* params_flat, float* exp_avg, float* exp_avg_sq, int64_t* step_counter,
+                               double lr0, double gamma, int64_t step_size, float* grad_flat, double* loss_sums, void* workspace,
+                               size_t workspace_bytes, void* stream, int images_valid) {
   if (int e = validate_net(net)) return e;
   if (n <= 0 || !x || !y || n_global <= 0 || !params_flat || !exp_avg || !exp_avg_sq || !step_counter || step_size <= 0 ||
       !grad_flat || !workspace)
@@ -457,7 +457,7 @@ extern "C" int pinn_train_dnn_step(const pinn_net_t* net, const float* x, int64_
   if (net->W[0] != params_flat + lay.offW[0] || net->bv2 != params_flat + lay.offbv2) return PINN_E_ARG;
   if (!aligned16(x) || !aligned16(workspace)) return PINN_E_ALIGN;
   if (!wide_tc_bwd_covers(net) && tc_bwd_covers(net)) {
-    FusedAdam fa{params_flat, exp_avg, exp_avg_sq, step_counter, AdamHyper{lr0, gamma, 1.0, step_size}};
+    FusedAdam fa{params_flat, exp_avg, exp_avg_sq, step_counter, AdamHyper{lr0, gamma, 1.0, step_size}, nullptr, 1.0f, images_valid};
     return launch_tc_bwd(net, x, n, make_drop_params(drop), nullptr, nullptr, y, n_global, grad_flat, loss_sums, workspace,
                          workspace_bytes, static_cast<cudaStream_t>(stream), &fa);
   }
@@ -465,6 +465,14 @@ extern "C" int pinn_train_dnn_step(const pinn_net_t* net, const float* x, int64_
     return e;
   return pinn_adam_step(params_flat, grad_flat, exp_avg, exp_avg_sq, lay.total, step_counter, lr0, gamma, step_size, 1.0, nullptr,
                         nullptr, nullptr, 1, stream);
+}
+
+extern "C" int pinn_train_dnn_step(const pinn_net_t* net, const float* x, int64_t n, const pinn_dropout_t* drop, const float* y,
+                                   int64_t n_global, float* params_flat, float* exp_avg, float* exp_avg_sq, int64_t* step_counter,
+                                   double lr0, double gamma, int64_t step_size, float* grad_flat, double* loss_sums, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  return train_dnn_step_impl(net, x, n, drop, y, n_global, params_flat, exp_avg, exp_avg_sq, step_counter, lr0, gamma, step_size,
+                             grad_flat, loss_sums, workspace, workspace_bytes, stream, 0);
 }
 
 // `n_steps` consecutive train_dnn steps enqueued by one call (the Python loop around pinn_train_dnn_step costs about as
@@ -481,8 +489,10 @@ extern "C" int pinn_train_dnn_steps(const pinn_net_t* net, const float* x, int64
   if (drop != nullptr) d = *drop;
   for (int64_t i = 0; i < n_steps; ++i) {
     if (drop != nullptr) d.pass_offset = drop->pass_offset + i;
-    const int r = pinn_train_dnn_step(net, x, n, drop != nullptr ? &d : nullptr, y, n_global, params_flat, exp_avg, exp_avg_sq,
-                                      step_counter, lr0, gamma, step_size, grad_flat, loss_sums, workspace, workspace_bytes, stream);
+    // from the second step on the one-kernel backward finds its weight images written by the previous optimiser launch
+    const int r = train_dnn_step_impl(net, x, n, drop != nullptr ? &d : nullptr, y, n_global, params_flat, exp_avg, exp_avg_sq,
+                                      step_counter, lr0, gamma, step_size, grad_flat, loss_sums, workspace, workspace_bytes, stream,
+                                      i > 0 ? 1 : 0);
     if (r != 0) return r;
   }
   return 0;

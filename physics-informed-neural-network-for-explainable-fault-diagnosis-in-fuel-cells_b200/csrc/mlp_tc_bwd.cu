@@ -909,6 +909,10 @@ mlp_tc_bwd_kernel(pinn_net_t net, TcbLayout lay, const __grid_constant__ DropPar
   if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
 }
 
+}  // namespace pinn
+#include "mlp_tc_fused.cuh"
+namespace pinn {
+
 // Per-CTA partials -> gradient bucket, fixed order (deterministic): a CTA owns 32 consecutive bucket entries (one
 // 128-byte line per partial), its 8 warps sum every 8th partial with four loads in flight, the 8 sub-sums are
 // folded in warp order.  (The first version walked all partials serially in one thread per entry -- 24 us at
@@ -955,6 +959,7 @@ grad_reduce2_kernel(const float* __restrict__ partial, const double* __restrict_
       float pp = fa.params[i], mm = fa.m[i], vv = fa.v[i];
       adam_apply(pp, static_cast<float>(static_cast<double>(gr) * fa.h.grad_scale), mm, vv, consts[0], consts[1], 0.f, 0.f, false);
       fa.params[i] = pp; fa.m[i] = mm; fa.v[i] = vv;
+      if (fa.images != nullptr) image_write_entry(lay, i, pp, fa.wscale, fa.images);
     }
   }
   if (loss != nullptr && blockIdx.x == 0 && g == 1) {
@@ -982,9 +987,6 @@ grad_reduce2_kernel(const float* __restrict__ partial, const double* __restrict_
   }
 }
 
-}  // namespace pinn
-#include "mlp_tc_fused.cuh"
-namespace pinn {
 
 struct TcBwdPlan { int grid_a, grid_b; size_t smem_a, smem_b, off_partial, off_scratch, bytes; };
 static TcBwdPlan plan_tc_bwd(int L, int64_t n) {
@@ -1021,9 +1023,17 @@ bool tc_bwd_covers(const pinn_net_t* net) {
     if (!aligned16(net->W[l])) return false;
   return aligned16(net->Wv0) && aligned16(net->Wp);
 }
-bool tc_bwd_fused(int L, int flags) { return (L == 2 || L == 3) && !(flags & PINN_NET_NO_FUSED_BWD); }
+// One-kernel form unless the caller opts out -- or the batch is between one and 1.6 tiles per SM: there a few CTAs of the
+// one-kernel form run two tiles back to back (2 x 17 us) while the two-kernel form interleaves a tile pair on one SM
+// (N = 20 000, 157 tiles: 59 vs 55 us per step; from 1.6 tiles per SM up, and up to one, the one-kernel form wins:
+// profiles/ab_fused.py)
+bool tc_bwd_fused(int L, int flags, int64_t n) {
+  if (!(L == 2 || L == 3) || (flags & PINN_NET_NO_FUSED_BWD)) return false;
+  const int64_t tiles = (n + kBTile - 1) / kBTile, sms = sm_count();
+  return !(tiles > sms && 10 * tiles <= 16 * sms);
+}
 size_t tc_bwd_workspace_bytes(int L, int64_t n, int flags) {
-  if (flags >= 0 && tc_bwd_fused(L, flags)) return plan_fused(L, n).bytes;
+  if (flags >= 0 && tc_bwd_fused(L, flags, n)) return plan_fused(L, n).bytes;
   const size_t two = plan_tc_bwd(L, n).bytes;      // flags < 0: any path
   const size_t one = (L == 2 || L == 3) ? plan_fused(L, n).bytes : 0;
   return two > one ? two : one;
@@ -1057,8 +1067,10 @@ static int launch_tc_fused(const pinn_net_t* net, const float* x, int64_t n, con
     cudaFuncSetAttribute(weight_image_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     carve_set[devi] = true;
   }
-  PINN_CUDA_TRY(launch_pdl(weight_image_kernel, dim3(4 * L), dim3(256), 0, st, pdl, *net, dp.p > 0.f ? dp.scale : 1.0f,
-                           reinterpret_cast<unsigned char*>(ws + p.off_images)));
+  const float wscale = dp.p > 0.f ? dp.scale : 1.0f;
+  if (!(fused != nullptr && fused->images_valid))      // else: written by the previous step's optimiser launch
+    PINN_CUDA_TRY(launch_pdl(weight_image_kernel, dim3(4 * L), dim3(256), 0, st, pdl, *net, wscale,
+                             reinterpret_cast<unsigned char*>(ws + p.off_images)));
 #define LAUNCH_F(LL)                                                                                              \
   {                                                                                                               \
     auto kern = inj ? mlp_tc_fused_kernel<LL, true> : mlp_tc_fused_kernel<LL, false>;                             \
@@ -1075,9 +1087,9 @@ static int launch_tc_fused(const pinn_net_t* net, const float* x, int64_t n, con
   PINN_CUDA_TRY(cudaGetLastError());
   const int rg = static_cast<int>((lay.total + kRedCols - 1) / kRedCols);
   FusedAdam fa{};
-  if (fused != nullptr) fa = *fused;
+  if (fused != nullptr) { fa = *fused; fa.images = reinterpret_cast<unsigned char*>(ws + p.off_images); fa.wscale = wscale; }
   PINN_CUDA_TRY(launch_pdl(grad_reduce2_kernel, dim3(rg), dim3(kRedCols * kRedGroups), 0, st, pdl,
-                           static_cast<const float*>(a.partial), static_cast<const double*>(a.loss_partial), 2 * p.grid, p.grid,
+                           static_cast<const float*>(a.partial), static_cast<const double*>(a.loss_partial), p.grid, p.grid,
                            lay.total, grad_flat, loss_sums, fa, lay));
   return static_cast<int>(cudaGetLastError());
 }
@@ -1086,7 +1098,7 @@ int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropPa
                   const float* grad_s, const float* y, int64_t n_global, float* grad_flat, double* loss_sums, void* workspace,
                   size_t workspace_bytes, cudaStream_t st, const FusedAdam* fused) {
   const int L = net->n_hidden;
-  if (tc_bwd_fused(L, net->flags))
+  if (tc_bwd_fused(L, net->flags, n))
     return launch_tc_fused(net, x, n, dp, grad_u, grad_s, y, n_global, grad_flat, loss_sums, workspace, workspace_bytes, st, fused);
   TcBwdPlan p = plan_tc_bwd(L, n);
   if (workspace_bytes < p.bytes) return PINN_E_WORKSPACE;
@@ -1156,7 +1168,7 @@ int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropPa
   PINN_CUDA_TRY(cudaGetLastError());
   const int rg = static_cast<int>((lay.total + kRedCols - 1) / kRedCols);
   FusedAdam fa{};
-  if (fused != nullptr) fa = *fused;
+  if (fused != nullptr) { fa = *fused; fa.images = nullptr; }
   PINN_CUDA_TRY(launch_pdl(grad_reduce2_kernel, dim3(rg), dim3(kRedCols * kRedGroups), 0, st, pdl,
                            static_cast<const float*>(w.partial), static_cast<const double*>(a.loss_partial), p.grid_b, 2 * p.grid_a,
                            lay.total, grad_flat, loss_sums, fa, lay));
@@ -1168,6 +1180,9 @@ int launch_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropPa
 #ifdef PINN_TIMELINE
 extern "C" int pinn_debug_timeline_wgrad(long long* host_out) {
   return static_cast<int>(cudaMemcpyFromSymbol(host_out, pinn::g_tlw, sizeof(pinn::g_tlw)));
+}
+extern "C" int pinn_debug_timeline_fused(long long* host_out) {
+  return static_cast<int>(cudaMemcpyFromSymbol(host_out, pinn::g_tlf, sizeof(pinn::g_tlf)));
 }
 extern "C" int pinn_debug_timeline_phases(long long* host_out) {
   return static_cast<int>(cudaMemcpyFromSymbol(host_out, pinn::g_tlp, sizeof(pinn::g_tlp)));

@@ -17,7 +17,7 @@
 //       ACT (B operand):          rows [0,80) = hi part of up to 80 features, rows [80,160) = lo part.
 //     One product per K = 8 slab and per B part:  D[128 x N] += DEL * ACT_hi^T,  D += DEL * ACT_lo^T  -- with hi and lo
 //     of the A side stacked along M, the two MMAs produce all four cross terms (hi*hi, lo*hi, hi*lo, lo*lo); the read-out
-//     adds lanes j and 64 + j (they go out as two partial vectors, summed by the fixed-order reduce).
+//     adds lanes j and 64 + j.
 //       batch H : DEL = [dz_v0 (32) | du]            ACT = [a_{L-1} (64) | 1]    -> dWv0, dWp, dbv0, dbp
 //       batch l : DEL = delta_l (64)                 ACT = [a_{l-1} (64) | 1]    -> dW_l, db_l          (l = L-1 .. 1)
 //       batch 0T: DEL = [x (8) | av0 (32) | av1 (16) | 1]   ACT = [delta_0 (64) | dz_v1 (16)]   (roles swapped: the result is
@@ -89,20 +89,43 @@ __global__ void __launch_bounds__(256) weight_image_kernel(pinn_net_t net, float
   }
 }
 
+// The same image entries for ONE parameter of the flat bucket (entry i, new value p): used by the optimiser launch.
+PINN_D void image_write_entry(const ParamLayout& lay, int64_t i, float p, float wscale, unsigned char* __restrict__ images) {
+  const int L = lay.L;
+  int m = -1, j = 0, k = 0;
+  for (int l = 1; l < L; ++l) {
+    const int64_t r = i - lay.offW[l];
+    if (r >= 0 && r < 64 * 64) { m = l - 1; j = static_cast<int>(r >> 6); k = static_cast<int>(r & 63); }
+  }
+  {
+    const int64_t r = i - lay.offWv0, rp = i - lay.offWp;
+    if (r >= 0 && r < 32 * 64) { m = L - 1; j = static_cast<int>(r >> 6); k = static_cast<int>(r & 63); }
+    if (rp >= 0 && rp < 64) { m = L - 1; j = 32; k = static_cast<int>(rp); }
+  }
+  if (m < 0) return;
+  const float v = p * wscale, h = tc::tf32_hi(v), lo = v - h;
+  unsigned char* fw = images + static_cast<size_t>(m) * kFzImgBytes + static_cast<size_t>(k >> 2) * kFzImgLbo + j * 16 + (k & 3) * 4;
+  unsigned char* bw = images + static_cast<size_t>(2 * L - 1 - m) * kFzImgBytes + static_cast<size_t>(j >> 2) * kFzImgLbo + k * 16 + (j & 3) * 4;
+  *reinterpret_cast<float*>(fw) = h; *reinterpret_cast<float*>(fw + kFzPlaneBytes) = lo;
+  *reinterpret_cast<float*>(bw) = h; *reinterpret_cast<float*>(bw + kFzPlaneBytes) = lo;
+}
+
 struct FzArgs {
   const float* x; int64_t n;
   const float* grad_u; const float* grad_s; const float* y; float inv_n_global;
   const unsigned char* images;
-  float* partial;            // [2 * grid][lay.total]: per CTA the hi-lane and the lo-lane sums
+  float* partial;            // [grid][lay.total]
   double* loss_partial;      // [grid][4]
   float* park;               // [grid][L][4][512] float4 (see the kernel)
 };
 
 #ifdef PINN_TIMELINE
-__device__ long long g_tlf[160];      // CTA 0, compute thread 0: clock64 at the stamps below
-#define TLF(i) do { if (blockIdx.x == 0 && tid == 0 && (i) < 160) g_tlf[i] = clock64(); } while (0)
+__device__ long long g_tlf[2][256];      // CTA 0: [0] compute thread 0, [1] the MMA warp's elected lane; clock64 at the stamps below, 32 per tile
+#define TLF(i) do { if (blockIdx.x == 0 && tid == 0 && (i) < 256) g_tlf[0][i] = clock64(); } while (0)
+#define TLM(i) do { if (blockIdx.x == 0 && (i) < 256) g_tlf[1][i] = clock64(); } while (0)
 #else
 #define TLF(i) do { } while (0)
+#define TLM(i) do { } while (0)
 #endif
 
 template <int L, bool INJ>
@@ -111,9 +134,10 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
   static_assert(L == 2 || L == 3, "tensor memory holds L + 1 <= 4 accumulator blocks");
   constexpr int H = 64;
   extern __shared__ __align__(1024) unsigned char fsm[];
-  __shared__ __align__(8) uint64_t bar_ready, bar_chain, bar_wg, bar_full[2];
+  __shared__ __align__(8) uint64_t bar_ready, bar_stage, bar_chain, bar_wg, bar_full[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ double lred[4][4];
+  __shared__ double lacc[4][128];          // loss terms per sample row, summed over the CTA's tiles by the row's slice-0 thread
   __shared__ float wred[16][8];
   unsigned char* const ring = fsm;
   unsigned char* const DEL = fsm + 2 * kFzImgBytes;
@@ -124,7 +148,7 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
   griddep_launch();
 
   if (tid == 0) {
-    tc::mbar_init(&bar_ready, kFzThreads); tc::mbar_init(&bar_chain, 1); tc::mbar_init(&bar_wg, 1);
+    tc::mbar_init(&bar_ready, kFzThreads); tc::mbar_init(&bar_stage, kFzThreads); tc::mbar_init(&bar_chain, 1); tc::mbar_init(&bar_wg, 1);
     tc::mbar_init(&bar_full[0], 1); tc::mbar_init(&bar_full[1], 1);
     tc::fence_mbar_init();
   }
@@ -160,60 +184,73 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
     // ======================================================================================== MMA / TMA warp
     const uint32_t ring_u = tc::smem_u32(ring), del_u = tc::smem_u32(DEL), act_u = tc::smem_u32(ACT);
     const uint32_t idesc64 = tc::make_idesc_tf32(128, 64), idesc48 = tc::make_idesc_tf32(128, 48), idesc80 = tc::make_idesc_tf32(128, 80);
-    uint32_t rp = 0, fpar = 0, g = 0;
+    uint32_t rp = 0, sp = 0, fpar = 0, g = 0;
     if (tc::elect_one()) {
       tc::mbar_expect_tx(&bar_full[0], kFzImgBytes);
       tc::bulk_g2s(ring, a.images, kFzImgBytes, &bar_full[0]);
     }
     __syncwarp();
     bool first = true;
+    int tm = 0;
+    (void)tm;
+    // weight-gradient batch of the operands the compute warps have just staged (they arrive on bar_stage)
+    auto wgrad_batch = [&](int acc, bool wide_lo) {
+      tc::mbar_wait(&bar_stage, sp);
+      sp ^= 1u;
+      __syncwarp();
+      if (tc::elect_one()) {
+        tc::fence_after_sync();
+        const uint32_t d = tmem + kColAcc + kAccW * static_cast<uint32_t>(acc);
+        const uint64_t a0 = tc::make_desc(del_u, kDelLbo, 128);
+        const uint64_t bh0 = tc::make_desc(act_u, kActLbo, 128), bl0 = tc::make_desc(act_u + kActLo * 16, kActLbo, 128);
+        const uint32_t id_lo = wide_lo ? idesc80 : idesc64;
+        constexpr uint64_t as = (2u * kDelLbo) >> 4, bs = (2u * kActLbo) >> 4;
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks) {
+          tc::umma_tf32(d, a0 + ks * as, bh0 + ks * bs, idesc80, (ks != 0 || !first) ? 1u : 0u);
+          tc::umma_tf32(d, a0 + ks * as, bl0 + ks * bs, id_lo, 1u);
+        }
+        tc::umma_commit(&bar_wg);
+      }
+      __syncwarp();
+    };
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const bool has_next = tile + gridDim.x < n_tiles;
 #pragma unroll
-      for (int p = 0; p <= 2 * L; ++p) {
+      for (int p = 0; p < 2 * L; ++p) {
         tc::mbar_wait(&bar_ready, rp);
         rp ^= 1u;
         __syncwarp();
         if (tc::elect_one()) {
           tc::fence_after_sync();
-          if (p < 2 * L) {
-            // the other slot's last reader (the product before this one) has completed: the compute warps saw its commit
-            const int nxt = p + 1 < 2 * L ? p + 1 : (has_next ? 0 : -1);
-            if (nxt >= 0) {
-              const uint32_t s2 = (g + 1) & 1u;
-              tc::mbar_expect_tx(&bar_full[s2], kFzImgBytes);
-              tc::bulk_g2s(ring + s2 * kFzImgBytes, a.images + static_cast<size_t>(nxt) * kFzImgBytes, kFzImgBytes, &bar_full[s2]);
-            }
-            const uint32_t s1 = g & 1u;
-            tc::mbar_wait(&bar_full[s1], (fpar >> s1) & 1u);
-            fpar ^= 1u << s1;
-            const uint64_t bh = tc::make_desc(ring_u + s1 * kFzImgBytes, kFzImgLbo, 128);
-            const uint64_t bl = tc::make_desc(ring_u + s1 * kFzImgBytes + kFzPlaneBytes, kFzImgLbo, 128);
-            if (p == L - 1) tc::issue_3xtf32_ts<64>(tmem + kColD, tmem + kColAhi, tmem + kColAlo, bh, bl, kFzImgLbo, idesc48);
-            else if (p == L) tc::issue_3xtf32_ts<48>(tmem + kColD, tmem + kColAhi, tmem + kColAlo, bh, bl, kFzImgLbo, idesc64);
-            else tc::issue_3xtf32_ts<64>(tmem + kColD, tmem + kColAhi, tmem + kColAlo, bh, bl, kFzImgLbo, idesc64);
-            tc::umma_commit(&bar_chain);
-            ++g;
+          TLM(tm + 4 * p);
+          // the other slot's last reader (the product before this one) has completed: the compute warps saw its commit
+          const int nxt = p + 1 < 2 * L ? p + 1 : (has_next ? 0 : -1);
+          if (nxt >= 0) {
+            const uint32_t s2 = (g + 1) & 1u;
+            tc::mbar_expect_tx(&bar_full[s2], kFzImgBytes);
+            tc::bulk_g2s(ring + s2 * kFzImgBytes, a.images + static_cast<size_t>(nxt) * kFzImgBytes, kFzImgBytes, &bar_full[s2]);
           }
-          if (p >= L) {
-            // weight-gradient batch of the operands staged for this phase
-            const int acc = p == L ? 0 : (p == 2 * L ? L : 2 * L - p);
-            const uint32_t d = tmem + kColAcc + kAccW * static_cast<uint32_t>(acc);
-            const uint64_t a0 = tc::make_desc(del_u, kDelLbo, 128);
-            const uint64_t bh0 = tc::make_desc(act_u, kActLbo, 128), bl0 = tc::make_desc(act_u + kActLo * 16, kActLbo, 128);
-            const uint32_t id_lo = p == 2 * L ? idesc80 : idesc64;
-            constexpr uint64_t as = (2u * kDelLbo) >> 4, bs = (2u * kActLbo) >> 4;
-#pragma unroll
-            for (int ks = 0; ks < 16; ++ks) {
-              tc::umma_tf32(d, a0 + ks * as, bh0 + ks * bs, idesc80, (ks != 0 || !first) ? 1u : 0u);
-              tc::umma_tf32(d, a0 + ks * as, bl0 + ks * bs, id_lo, 1u);
-            }
-            tc::umma_commit(&bar_wg);
-          }
+          const uint32_t s1 = g & 1u;
+          tc::mbar_wait(&bar_full[s1], (fpar >> s1) & 1u);
+          fpar ^= 1u << s1;
+          TLM(tm + 4 * p + 1);
+          const uint64_t bh = tc::make_desc(ring_u + s1 * kFzImgBytes, kFzImgLbo, 128);
+          const uint64_t bl = tc::make_desc(ring_u + s1 * kFzImgBytes + kFzPlaneBytes, kFzImgLbo, 128);
+          if (p == L - 1) tc::issue_3xtf32_ts<64>(tmem + kColD, tmem + kColAhi, tmem + kColAlo, bh, bl, kFzImgLbo, idesc48);
+          else if (p == L) tc::issue_3xtf32_ts<48>(tmem + kColD, tmem + kColAhi, tmem + kColAlo, bh, bl, kFzImgLbo, idesc64);
+          else tc::issue_3xtf32_ts<64>(tmem + kColD, tmem + kColAhi, tmem + kColAlo, bh, bl, kFzImgLbo, idesc64);
+          tc::umma_commit(&bar_chain);
+          TLM(tm + 4 * p + 2);
         }
         __syncwarp();
+        ++g;
+        if (p >= L) { wgrad_batch(p == L ? 0 : 2 * L - p, false); TLM(tm + 4 * p + 3); }      // staged while the chain product ran
       }
+      wgrad_batch(L, true);          // batch 0T
+      TLM(tm + 8 * L + 3);
       first = false;
+      tm += 32;
     }
   } else {
     // ======================================================================================== compute warps
@@ -237,6 +274,11 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
       tc::fence_proxy_async();
       tc::fence_before_sync();
       tc::mbar_arrive(&bar_ready);
+    };
+    auto arrive_stage = [&] {          // staging planes written: the weight-gradient batch may run
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&bar_stage);
+      wg_pending = true;
     };
     auto wait_chain = [&] {
       tc::mbar_wait(&bar_chain, chain_par);
@@ -277,7 +319,7 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
       return bits;
     };
     const bool no_lv = (net.flags & PINN_NET_NO_LOGVAR) != 0;
-    float l_nll = 0.f, l_abs = 0.f, l_mse = 0.f, l_cnt = 0.f;        // at most one term per tile and thread: fp32 is exact enough, the tree below is double
+    if (c == 0) { lacc[0][row] = 0.0; lacc[1][row] = 0.0; lacc[2][row] = 0.0; lacc[3][row] = 0.0; }
     float g_wv2[4] = {0.f, 0.f, 0.f, 0.f}, g_bv2 = 0.f;
     // Parking lot (global, 32 KB per slot and CTA, L2-resident: rewritten every tile): the activations of layers 0..L-2
     // and the tail's (av0, v1, dz_v1) wait here between the forward and the backward phase that needs them -- 64 live
@@ -297,6 +339,18 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
     int tl = 0;
     (void)tl;
 
+    // x of the first tile; every later tile's row is fetched while the previous tile's last phase runs
+    float4 xq0 = make_float4(0.f, 0.f, 0.f, 0.f), xq1 = xq0;
+    auto load_x = [&](int64_t tile) {
+      const int64_t s = tile * 128 + row;
+      if (tile < n_tiles && s < a.n) {
+        const float4* px = reinterpret_cast<const float4*>(a.x + s * PINN_N_IN);
+        xq0 = __ldg(px); xq1 = __ldg(px + 1);
+      } else {
+        xq0 = xq1 = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    load_x(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t s = tile * 128 + row;
       const bool valid = s < a.n;
@@ -308,18 +362,10 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
       ks.mrow = INJ ? dp.masks + static_cast<size_t>(valid ? s : 0) * Dm : nullptr;
       float acur[16];              // this thread's 16 masked activations of the current trunk layer (without the dropout scale)
       uint32_t kb[L];
-      TLF(tl++);
+      TLF(tl);
       // ============================ forward ============================
       {
-        float xr[PINN_N_IN];
-        if (valid) {
-          const float4* px = reinterpret_cast<const float4*>(a.x + s * PINN_N_IN);
-          const float4 q0 = __ldg(px), q1 = __ldg(px + 1);
-          xr[0] = q0.x; xr[1] = q0.y; xr[2] = q0.z; xr[3] = q0.w; xr[4] = q1.x; xr[5] = q1.y; xr[6] = q1.z; xr[7] = q1.w;
-        } else {
-#pragma unroll
-          for (int i = 0; i < PINN_N_IN; ++i) xr[i] = 0.f;
-        }
+        const float xr[PINN_N_IN] = {xq0.x, xq0.y, xq0.z, xq0.w, xq1.x, xq1.y, xq1.z, xq1.w};
         kb[0] = keep16(ks, active, 0u);
         const float* W0 = sm + sl.W0 + cb * PINN_N_IN;
         const float* b0 = sm + sl.b[0] + cb;
@@ -332,17 +378,20 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
           z = fmaf(w1.x, xr[4], z); z = fmaf(w1.y, xr[5], z); z = fmaf(w1.z, xr[6], z); z = fmaf(w1.w, xr[7], z);
           acur[i] = ((kb[0] >> i) & 1u) ? tanh_pre(z) : 0.f;
         }
-        if (L > 1) park_st(0, acur);
         float h[16], lo[16];
         split16(acur, h, lo);
         tc::tmem_st16(tAh + cb, h);
         tc::tmem_st16(tAl + cb, lo);
       }
       arrive_ready();
+      if (L > 1) park_st(0, acur);
+      TLF(tl + 1);
 #pragma unroll
       for (int l = 1; l < L; ++l) {
         kb[l] = keep16(ks, active, static_cast<uint32_t>(l));        // drawn while the tensor core works
+        TLF(tl + 2 * l);
         wait_chain();
+        TLF(tl + 2 * l + 1);
         float z[16];
         tc::tmem_ld16(tD + cb, z);
         tc::tmem_wait_ld();
@@ -356,16 +405,18 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
 #pragma unroll
           for (int i = 0; i < 8; ++i) acur[g8 + i] = ((kb[l] >> (g8 + i)) & 1u) ? t8[i] : 0.f;
         }
-        if (l < L - 1) park_st(l, acur);
         float h[16], lo[16];
         split16(acur, h, lo);
         tc::tmem_st16(tAh + cb, h);
         tc::tmem_st16(tAl + cb, lo);
         arrive_ready();
+        if (l < L - 1) park_st(l, acur);
       }
       // ---- heads (rows 0..31 = Wv0, row 32 = Wp) and the variance head's tail, split over the row's four threads:
       //      thread c owns units 8c..8c+7 of the 32-wide layer and units 4c..4c+3 of the 16-wide layer; three hand-overs
-      //      through free tensor-memory columns (A hi 0..31: av0, A hi 48..51: partial raw variances, A lo 48..63: dz_v1)
+      //      through free tensor-memory columns (A hi 0..31: av0, A hi 48..63: v1, A lo 48..63: dz_v1, D 56: d loss / d raw variance).
+      //      The scalar part (log-variance, loss, output gradients, all 16 dz_v1) runs on the row's slice-0 thread only:
+      //      the four threads of a row share one scheduler, so doing it four times would cost four times the issue slots.
       uint32_t kbv = 0xffu;
       if (active) {
         bool k[8];
@@ -374,20 +425,28 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
 #pragma unroll
         for (int i = 0; i < 8; ++i) kbv |= (k[i] ? 1u : 0u) << i;
       }
+      // target (or the caller's output gradients) of this row: in flight while the heads product runs
+      float y_pre = 0.f, gs_pre = 0.f;
+      if (c == 0 && valid) {
+        if (a.grad_u != nullptr) { y_pre = __ldg(a.grad_u + s); gs_pre = a.grad_s ? __ldg(a.grad_s + s) : 0.f; }
+        else y_pre = __ldg(a.y + s);
+      }
+      TLF(tl + 6);
       wait_chain();
-      float dzv0[8], du = 0.f, dv = 0.f;
+      TLF(tl + 7);
+      float dzv0[8], du = 0.f;
       {
         float tailv[16];           // [0,8) av0 (scaled), [8,12) v1, [12,16) dz_v1: parked for the 0T batch
         float zv[8], zu[8];
         tc::tmem_ld8(tD + 8 * c, zv);
         tc::tmem_ld8(tD + 32, zu);
         tc::tmem_wait_ld();
-        const float u = zu[0] + sm[sl.bp];
         const float* bv0 = sm + sl.bv0 + 8 * c;
 #pragma unroll
         for (int i = 0; i < 8; ++i) tailv[i] = ((kbv >> i) & 1u) ? tanh_pre(fmaf(zv[i], kTanhArg, bv0[i])) * wscale : 0.f;
         tc::tmem_st8(tAh + 8 * c, tailv);
         qbar();
+        TLF(tl + 8);
         const float* Wv1 = sm + sl.Wv1;
         float2 acc[4][2];
 #pragma unroll
@@ -408,46 +467,62 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
             }
           }
         }
-        float pv = 0.f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 4; ++k)
           tailv[8 + k] = tanh_pre(fmaf((acc[k][0].x + acc[k][0].y) + (acc[k][1].x + acc[k][1].y), kTanhArg, sm[sl.bv1 + 4 * c + k]));
-          pv = fmaf(sm[sl.Wv2 + 4 * c + k], tailv[8 + k], pv);
-        }
-        tc::tmem_st1(tAh + 48 + c, pv);
+        tc::tmem_st4(tAh + 48 + 4 * c, tailv + 8);
+        TLF(tl + 9);
         qbar();
-        float pvs[4];
-        tc::tmem_ld4(tAh + 48, pvs);
-        tc::tmem_wait_ld();
-        const float vraw = sm[sl.bv2] + ((pvs[0] + pvs[1]) + (pvs[2] + pvs[3]));
-        const float lv = logvar_out(vraw, no_lv);
-        float ds = 0.f;
-        if (valid) {
-          if (a.grad_u != nullptr) {
-            du = __ldg(a.grad_u + s);
-            ds = a.grad_s ? __ldg(a.grad_s + s) : 0.f;
-          } else {
-            const float yv = __ldg(a.y + s);
-            const float e = expf(-lv), diff = yv - u;
-            du = -e * diff * a.inv_n_global;
-            const float sgn = lv > 0.f ? 1.f : (lv < 0.f ? -1.f : 0.f);
-            ds = (-0.5f * e * diff * diff + 0.5f + 0.01f * sgn) * a.inv_n_global;
-            if (c == 0) {
-              l_nll += 0.5f * e * diff * diff + 0.5f * lv;
-              l_abs += fabsf(lv);
-              l_mse += diff * diff;
-              l_cnt += 1.0f;
+        TLF(tl + 10);
+        if (c == 0) {
+          float v1a[16], dz[16];
+          tc::tmem_ld16(tAh + 48, v1a);
+          tc::tmem_wait_ld();
+          float vraw = sm[sl.bv2];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) vraw = fmaf(sm[sl.Wv2 + k], v1a[k], vraw);
+          const float u = zu[0] + sm[sl.bp];
+          // log-variance head 01:432-434 with one accurate log1p and MUFU for the rest: with t = softplus(v) + 1e-6,
+          // logvar = log t, exp(-logvar) = 1 / t, d logvar / d v = sigmoid(v) / t, sigmoid(v) = e^v / (1 + e^v) (v <= 20)
+          const bool big = vraw > 20.0f;
+          const float ev = __expf(big ? 0.f : vraw);
+          const float t = (big ? vraw : log1pf(ev)) + 1e-6f;
+          const float rt = __frcp_rn(t);
+          const float lv = no_lv ? 0.f : logf(t);
+          float ds = 0.f;
+          if (valid) {
+            if (a.grad_u != nullptr) {
+              du = y_pre;
+              ds = gs_pre;
+            } else {
+              const float yv = y_pre;
+              const float e = no_lv ? 1.0f : rt, diff = yv - u;
+              du = -e * diff * a.inv_n_global;
+              const float sgn = lv > 0.f ? 1.f : (lv < 0.f ? -1.f : 0.f);
+              ds = (-0.5f * e * diff * diff + 0.5f + 0.01f * sgn) * a.inv_n_global;
+              lacc[0][row] += static_cast<double>(0.5f * e * diff * diff + 0.5f * lv);
+              lacc[1][row] += static_cast<double>(fabsf(lv));
+              lacc[2][row] += static_cast<double>(diff * diff);
+              lacc[3][row] += 1.0;
             }
           }
-        }
-        dv = no_lv ? 0.f : ds * dlogvar_dv(vraw);
+          const float sig = big ? 1.0f : __fdividef(ev, 1.0f + ev);
+          const float dvv = no_lv ? 0.f : ds * sig * rt;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tailv[12 + k] = dv * sm[sl.Wv2 + 4 * c + k] * (1.0f - tailv[8 + k] * tailv[8 + k]);
-        tc::tmem_st4(tAl + 48 + 4 * c, tailv + 12);
+          for (int k = 0; k < 16; ++k) dz[k] = dvv * sm[sl.Wv2 + k] * (1.0f - v1a[k] * v1a[k]);
+          tc::tmem_st16(tAl + 48, dz);
+          tc::tmem_st1(tD + 56, dvv);          // D columns 48..63 are not touched by the heads product; the next chain product comes after every thread's arrive
+        }
+        TLF(tl + 11);
         qbar();
-        float dzs[16];
+        TLF(tl + 12);
+        float dzs[16], dv8[8];
         tc::tmem_ld16(tAl + 48, dzs);
+        tc::tmem_ld8(tD + 56, dv8);
         tc::tmem_wait_ld();
+        const float dv = dv8[0];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tailv[12 + k] = c == 0 ? dzs[k] : (c == 1 ? dzs[4 + k] : (c == 2 ? dzs[8 + k] : dzs[12 + k]));
         // d v0[i] = sum_k Wv1[k][i] dz1[k];  dz_v0 = d v0 * keep-mask * scale * (1 - a^2)
 #pragma unroll
         for (int i = 0; i < 8; ++i) dzv0[i] = 0.f;
@@ -468,13 +543,10 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
 #pragma unroll
         for (int k = 0; k < 4; ++k) g_wv2[k] = fmaf(dv, tailv[8 + k], g_wv2[k]);
         if (c == 0) g_bv2 += dv;
-        park_st(L - 1, tailv);
-        // every thread of the row has passed the third barrier, so the av0 / partial columns are dead and the
-        // heads^T operand may overwrite them
-      }
-      // ============================ backward ============================
-      // chain operand [dz_v0 (32 cols) | du | 0 ...] (K = 48) and batch H
-      {
+        // every thread of the row has passed the third barrier, so the hand-over columns below 48 are dead and the
+        // heads^T operand (columns 0..47 of both planes) may overwrite them
+        // ============================ backward ============================
+        // chain operand [dz_v0 (32 cols) | du | 0 ...] (K = 48)
         float h8[8], l8[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { h8[i] = tc::tf32_hi_fast(dzv0[i]); l8[i] = dzv0[i] - h8[i]; }
@@ -490,7 +562,11 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
           tc::tmem_st8(tAh + 40, z8);
           tc::tmem_st8(tAl + 40, z8);
         }
+        arrive_ready();            // the heads^T product runs while batch H is staged
+        TLF(tl + 13);
+        park_st(L - 1, tailv);
         wait_wg();                 // the previous tile's 0T batch
+        TLF(tl + 14);
 #pragma unroll
         for (int i = 0; i < 4; ++i) *reinterpret_cast<float*>(act_s + (64 + 4 * c + i) * 16) = (c == 0 && i == 0) ? 1.0f : 0.0f;
 #pragma unroll
@@ -500,16 +576,20 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
         split16(acur, h, lo);
 #pragma unroll
         for (int i = 0; i < 16; ++i) act_st(cb + i, h[i], lo[i]);
+        arrive_stage();
+        TLF(tl + 15);
       }
-      arrive_ready();
-      wg_pending = true;
 #pragma unroll
       for (int l = L - 1; l >= 0; --l) {
         float nxt[16];             // l > 0: activations of layer l - 1;  l == 0: the parked tail values
         park_ld(l > 0 ? l - 1 : L - 1, nxt);          // in flight while the tensor core works
-        float x2[2] = {0.f, 0.f};
-        if (l == 0 && valid) { const float2 t = __ldg(reinterpret_cast<const float2*>(a.x + s * PINN_N_IN) + c); x2[0] = t.x; x2[1] = t.y; }
+        float x2[2] = {0.f, 0.f};                       // this thread's two input features for the 0T batch
+        if (l == 0) {
+          if (valid) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(a.x + s * PINN_N_IN) + c); x2[0] = t2.x; x2[1] = t2.y; }
+          load_x(tile + gridDim.x);                     // the next tile's input row
+        }
         wait_chain();
+        TLF(tl + 16 + 4 * (L - 1 - l));
         float h[16], lo[16];
         {
           float z[16];
@@ -523,7 +603,10 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
         if (l > 0) {
           tc::tmem_st16(tAh + cb, h);
           tc::tmem_st16(tAl + cb, lo);
+          arrive_ready();          // the next chain product runs while this layer's batch is staged
+          TLF(tl + 17 + 4 * (L - 1 - l));
           wait_wg();
+          TLF(tl + 18 + 4 * (L - 1 - l));
 #pragma unroll
           for (int i = 0; i < 16; ++i) del_st(cb + i, h[i], lo[i]);
 #pragma unroll
@@ -533,7 +616,9 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
           for (int i = 0; i < 16; ++i) act_st(cb + i, h[i], lo[i]);
         } else {
           // batch 0T (roles swapped): DEL = [x | av0 | av1 | 1], ACT = [delta_0 | dz_v1]
+          TLF(tl + 17 + 4 * (L - 1 - l));
           wait_wg();
+          TLF(tl + 18 + 4 * (L - 1 - l));
 #pragma unroll
           for (int i = 0; i < 16; ++i) act_st(cb + i, h[i], lo[i]);
 #pragma unroll
@@ -546,70 +631,83 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
 #pragma unroll
           for (int i = 0; i < 4; ++i) { const float hh = tc::tf32_hi_fast(nxt[12 + i]); act_st(64 + 4 * c + i, hh, nxt[12 + i] - hh); }
         }
-        arrive_ready();
-        wg_pending = true;
+        arrive_stage();
+        TLF(tl + 19 + 4 * (L - 1 - l));
       }
+      tl += 32;
     }
-    TLF(tl++);
-    // ---------------------------------------------------------------- accumulators -> this CTA's two partial vectors
+    TLF(tl);
+    // ---------------------------------------------------------------- accumulators -> this CTA's partial vector
+    // Lanes j and 64 + j hold the hi and the lo part of the same sum: the lo half of the CTA (quadrants 2, 3) parks its
+    // values in the idle staging plane, the hi half adds them and writes the vector out.
     wait_wg();
     tc::fence_after_sync();
     {
-      float* const part = a.partial + (static_cast<size_t>(2 * blockIdx.x) + (q >> 1)) * pl.total;       // lanes 0..63: hi parts, 64..127: lo parts
+      float* const part = a.partial + static_cast<size_t>(blockIdx.x) * pl.total;
+      float* const lo_sm = reinterpret_cast<float*>(DEL);
       const int lr = row & 63;
       const uint32_t tacc = tmem + kColAcc + lane_sel;
-      float v[16];
-      auto store16_scaled = [&](float* dst) {
+      auto readout = [&](float* dst, const float* add) {
+        float v[16];
+        auto put = [&](int64_t idx, float val) { dst[idx] = add != nullptr ? val + add[idx] : val; };
+        auto put16_scaled = [&](int64_t idx) {          // idx % 4 == 0
 #pragma unroll
-        for (int i = 0; i < 16; i += 4)
-          *reinterpret_cast<float4*>(dst + i) = make_float4(v[i] * wscale, v[i + 1] * wscale, v[i + 2] * wscale, v[i + 3] * wscale);
-      };
+          for (int i = 0; i < 16; i += 4) {
+            float4 o = make_float4(v[i] * wscale, v[i + 1] * wscale, v[i + 2] * wscale, v[i + 3] * wscale);
+            if (add != nullptr) { const float4 t = *reinterpret_cast<const float4*>(add + idx + i); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+            *reinterpret_cast<float4*>(dst + idx + i) = o;
+          }
+        };
 #pragma unroll
-      for (int l = 1; l < L; ++l) {
-        tc::tmem_ld16(tacc + kAccW * l + cb, v);
+        for (int l = 1; l < L; ++l) {
+          tc::tmem_ld16(tacc + kAccW * l + cb, v);
+          tc::tmem_wait_ld();
+          put16_scaled(pl.offW[l] + lr * 64 + cb);
+          if (c == 0) {
+            float b8[8];
+            tc::tmem_ld8(tacc + kAccW * l + 64, b8);
+            tc::tmem_wait_ld();
+            put(pl.offb[l] + lr, b8[0]);
+          }
+        }
+        // batch H: lanes 0..31 = dWv0 rows, lane 32 = dWp; column 64 = their biases
+        tc::tmem_ld16(tacc + cb, v);
         tc::tmem_wait_ld();
-        store16_scaled(part + pl.offW[l] + lr * 64 + cb);
+        if (lr < 32) put16_scaled(pl.offWv0 + lr * 64 + cb);
+        else if (lr == 32) put16_scaled(pl.offWp + cb);
         if (c == 0) {
           float b8[8];
-          tc::tmem_ld8(tacc + kAccW * l + 64, b8);
+          tc::tmem_ld8(tacc + 64, b8);
           tc::tmem_wait_ld();
-          part[pl.offb[l] + lr] = b8[0];
+          if (lr < 32) put(pl.offbv0 + lr, b8[0]);
+          else if (lr == 32) put(pl.offbp, b8[0]);
         }
-      }
-      // batch H: lanes 0..31 = dWv0 rows, lane 32 = dWp; column 64 = their biases
-      tc::tmem_ld16(tacc + cb, v);
-      tc::tmem_wait_ld();
-      if (lr < 32) store16_scaled(part + pl.offWv0 + lr * 64 + cb);
-      else if (lr == 32) store16_scaled(part + pl.offWp + cb);
-      if (c == 0) {
-        float b8[8];
-        tc::tmem_ld8(tacc + 64, b8);
+        // batch 0T (transposed): lanes 0..7 = input feature i, columns 0..63 = unit j -> dW0[j][i]; lane 56 -> db0, dbv1;
+        // lanes 8..39 = av0 unit, columns 64..79 = dz_v1 unit k -> dWv1[k][i]
+        tc::tmem_ld16(tacc + kAccW * L + cb, v);
         tc::tmem_wait_ld();
-        if (lr < 32) part[pl.offbv0 + lr] = b8[0];
-        else if (lr == 32) part[pl.offbp] = b8[0];
-      }
-      // batch 0T (transposed): lanes 0..7 = input feature i, columns 0..63 = unit j -> dW0[j][i]; lane 56 -> db0, dbv1;
-      // lanes 8..39 = av0 unit, columns 64..79 = dz_v1 unit k -> dWv1[k][i]
-      tc::tmem_ld16(tacc + kAccW * L + cb, v);
-      tc::tmem_wait_ld();
-      if (lr < 8) {
+        if (lr < 8) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) part[pl.offW[0] + (cb + i) * PINN_N_IN + lr] = v[i];
-      } else if (lr == kTOne) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) part[pl.offb[0] + cb + i] = v[i];
-      }
-      if (c == 1) {
-        tc::tmem_ld16(tacc + kAccW * L + 64, v);
-        tc::tmem_wait_ld();
-        if (lr >= kTV0 && lr < kTV0 + 32) {
-#pragma unroll
-          for (int k = 0; k < 16; ++k) part[pl.offWv1 + k * 32 + lr - kTV0] = v[k];
+          for (int i = 0; i < 16; ++i) put(pl.offW[0] + (cb + i) * PINN_N_IN + lr, v[i]);
         } else if (lr == kTOne) {
 #pragma unroll
-          for (int k = 0; k < 16; ++k) part[pl.offbv1 + k] = v[k];
+          for (int i = 0; i < 16; ++i) put(pl.offb[0] + cb + i, v[i]);
         }
-      }
+        if (c == 1) {
+          tc::tmem_ld16(tacc + kAccW * L + 64, v);
+          tc::tmem_wait_ld();
+          if (lr >= kTV0 && lr < kTV0 + 32) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) put(pl.offWv1 + k * 32 + lr - kTV0, v[k]);
+          } else if (lr == kTOne) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) put(pl.offbv1 + k, v[k]);
+          }
+        }
+      };
+      if (q >= 2) readout(lo_sm, nullptr);
+      asm volatile("bar.sync 5, 512;" ::: "memory");
+      if (q < 2) readout(part, lo_sm);
     }
     // dWv2 / dbv2 and the loss sums: xor tree over the warp's 32 rows, then the four quadrants in order
     {
@@ -621,7 +719,7 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
         if (lane == 0) wred[warp][k] = w5[k];
       }
       if (c == 0) {
-        double vals[4] = {static_cast<double>(l_nll), static_cast<double>(l_abs), static_cast<double>(l_mse), static_cast<double>(l_cnt)};
+        double vals[4] = {lacc[0][row], lacc[1][row], lacc[2][row], lacc[3][row]};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           double t = vals[k];
@@ -635,13 +733,12 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
   tc::fence_before_sync();
   __syncthreads();
   if (tid < 17) {
-    float* const part_hi = a.partial + static_cast<size_t>(2 * blockIdx.x) * pl.total;
-    float* const part_lo = part_hi + pl.total;
+    float* const part_hi = a.partial + static_cast<size_t>(blockIdx.x) * pl.total;
     const int k = tid;                  // 0..15: dWv2[k] (slice c = k / 4, entry k % 4); 16: dbv2 (slice 0, entry 4)
     const int cc = k < 16 ? k >> 2 : 0, e = k < 16 ? k & 3 : 4;
     const float t = (wred[4 * cc][e] + wred[4 * cc + 1][e]) + (wred[4 * cc + 2][e] + wred[4 * cc + 3][e]);
-    if (k < 16) { part_hi[pl.offWv2 + k] = t; part_lo[pl.offWv2 + k] = 0.f; }
-    else { part_hi[pl.offbv2] = t; part_lo[pl.offbv2] = 0.f; }
+    if (k < 16) part_hi[pl.offWv2 + k] = t;
+    else part_hi[pl.offbv2] = t;
   } else if (tid >= 32 && tid < 36) {
     const int k = tid - 32;
     a.loss_partial[static_cast<size_t>(blockIdx.x) * 4 + k] = (lred[0][k] + lred[1][k]) + (lred[2][k] + lred[3][k]);
@@ -660,7 +757,7 @@ static FzPlan plan_fused(int L, int64_t n) {
   size_t off = static_cast<size_t>(p.grid) * 4 * sizeof(double);
   off = (off + 255) & ~static_cast<size_t>(255);
   p.off_partial = off;
-  off += static_cast<size_t>(2 * p.grid) * lay.total * sizeof(float);
+  off += static_cast<size_t>(p.grid) * lay.total * sizeof(float);
   off = (off + 255) & ~static_cast<size_t>(255);
   p.off_images = off;
   off += static_cast<size_t>(2 * L) * kFzImgBytes;
