@@ -370,7 +370,7 @@ def run_ours(args):
     # --- configs[1]: full-batch train_dnn steps (K2 + reduce + [gradient sum over NVLink fused into Adam] + Adam), back to back.
     # Single-GPU step time is measured in the same job (data_parallel = False) so the weak-scaling efficiency of the ONE
     # step that communicates is stated here, not only for the collective-free sweep.
-    steps_tr = max(K_, 5)
+    steps_tr = max(K_, 40)       # one call enqueues them all; long enough that the call's fixed cost (progress-line read-back) vanishes
     model.data_parallel = False
     model.train_dnn(max(W_, 1), verbose=False)
     t_tr_local = timed_block(lambda k: model.train_dnn(k, verbose=False), steps_tr)

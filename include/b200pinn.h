@@ -132,6 +132,22 @@ int pinn_train_dnn_steps(const pinn_net_t* net, const float* x, int64_t n,
                          int64_t* step_counter, double lr0, double gamma, int64_t step_size,
                          int64_t n_steps, float* grad_flat, double* loss_sums, void* workspace,
                          size_t workspace_bytes, void* stream);
+/* Data-parallel form (one process per GPU): the gradient bucket is summed over the ranks INSIDE the
+ * gradient-reduce launch over NVLink peer memory (posted stores into every rank's symmetric buffer,
+ * per-line flags, rank-ordered sum: bit-identical replicas), Adam + StepLR follow in the same launch and
+ * all n_steps steps are enqueued by this one call.  Replaces the reference's single-process loop
+ * 01:948-955 under torchrun; the only exchange SURVEY 8(e) allows on this path.  peer_buffers: device
+ * array of `world` addresses, entry r = rank r's buffer of pinn_dp_bucket_words() 32-bit words, zeroed
+ * once; step i carries tag first_tag + i (tags grow by one per step over the life of the buffer, > 0).
+ * grad_flat may be NULL.  64-wide nets with 2..4 hidden layers; PINN_E_SHAPE otherwise. */
+int64_t pinn_dp_bucket_words(int32_t width, int32_t n_hidden, int32_t world);
+int pinn_train_dnn_steps_dp(const pinn_net_t* net, const float* x, int64_t n,
+                            const pinn_dropout_t* drop, const float* y, int64_t n_global,
+                            float* params_flat, float* exp_avg, float* exp_avg_sq,
+                            int64_t* step_counter, double lr0, double gamma, int64_t step_size,
+                            int64_t n_steps, const uint64_t* peer_buffers, int32_t rank,
+                            int32_t world, uint32_t first_tag, float* grad_flat, double* loss_sums,
+                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* K3 -- multi-physics residuals + reductions: net_f_V 01:724-765, net_f_T_simple
  * 01:869-914, net_f_T 01:767-867, net_f_H 01:621-722, net_f_O 01:535-619, the

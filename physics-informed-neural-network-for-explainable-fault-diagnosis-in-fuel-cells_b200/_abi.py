@@ -87,6 +87,9 @@ _SIGNATURES = {
                                       _dbl, _dbl, _i64, _vp, _vp, _vp, _sz, _vp]),
     "pinn_train_dnn_steps": (C.c_int, [C.POINTER(PinnNet), _vp, _i64, C.POINTER(PinnDropout), _vp, _i64, _vp, _vp, _vp, _vp,
                                        _dbl, _dbl, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "pinn_dp_bucket_words": (_i64, [_i32, _i32, _i32]),
+    "pinn_train_dnn_steps_dp": (C.c_int, [C.POINTER(PinnNet), _vp, _i64, C.POINTER(PinnDropout), _vp, _i64, _vp, _vp, _vp, _vp,
+                                          _dbl, _dbl, _i64, _i64, _vp, _i32, _i32, _u32, _vp, _vp, _vp, _sz, _vp]),
     "pinn_residuals": (C.c_int, [_vp, _vp, _vp, _i64, C.POINTER(PinnScalers), _vp, _u32, _u32, _vp, _vp,
                                  _vp, _vp, _vp, _sz, _vp]),
     "pinn_mc_dropout": (C.c_int, [C.POINTER(PinnNet), _vp, _i64, _i32, C.POINTER(PinnDropout),

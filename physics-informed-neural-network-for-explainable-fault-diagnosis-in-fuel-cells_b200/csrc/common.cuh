@@ -382,6 +382,14 @@ struct FusedAdam {
   // one-kernel 64-wide backward (mlp_tc_fused.cuh): the optimiser launch also rewrites the UMMA weight images of the
   // entries it updates, so the next step of the same call needs no image launch (`images_valid`: this step's are in place)
   unsigned char* images; float wscale; int images_valid;
+  // data-parallel step: the gradient bucket is exchanged INSIDE the reduce launch over NVLink peer memory (see
+  // grad_reduce2_kernel); peers == nullptr: single GPU
+  const unsigned long long* peers; int rank, world; unsigned int tag;
 };
+// Symmetric buffer of the data-parallel reduce (32-bit words): [world x lines flag words, padded to 64] then, per slot
+// (step parity) and source rank, one copy of the gradient bucket.
+PINN_HD int64_t dp_lines(int64_t total) { return (total + 31) / 32; }
+PINN_HD int64_t dp_flag_words(int64_t total, int world) { return (static_cast<int64_t>(world) * dp_lines(total) + 63) / 64 * 64; }
+PINN_HD int64_t dp_bucket_words(int64_t total, int world) { return dp_flag_words(total, world) + 2 * static_cast<int64_t>(world) * total; }
 
 }  // namespace pinn

@@ -497,3 +497,42 @@ extern "C" int pinn_train_dnn_steps(const pinn_net_t* net, const float* x, int64
   }
   return 0;
 }
+
+// Data-parallel form of pinn_train_dnn_steps (one process per GPU): the sum of the gradient bucket over the ranks happens
+// INSIDE the gradient-reduce launch over NVLink peer memory (mlp_tc_bwd.cu, grad_reduce2_kernel), Adam + StepLR follow in
+// the same launch, and all `n_steps` steps are enqueued by this one call -- no NCCL call, no extra launch and no host
+// round trip per step.  `peer_buffers`: device array of `world` addresses, entry r = rank r's symmetric buffer of
+// pinn_dp_bucket_words() 32-bit words (zeroed once before first use); step i carries tag `first_tag + i` (tags must grow
+// by one per step over the life of the buffer, starting above 0).  Covers the 64-wide net with 2..4 hidden layers
+// (PINN_E_SHAPE otherwise: use pinn_mlp_bwd + pinn_adam_step_p2p).
+extern "C" int64_t pinn_dp_bucket_words(int32_t width, int32_t n_hidden, int32_t world) {
+  if (n_hidden < 1 || n_hidden > PINN_MAX_HIDDEN || world < 1) return PINN_E_SHAPE;
+  return dp_bucket_words(make_layout(width, n_hidden).total, world);
+}
+
+extern "C" int pinn_train_dnn_steps_dp(const pinn_net_t* net, const float* x, int64_t n, const pinn_dropout_t* drop, const float* y,
+                                       int64_t n_global, float* params_flat, float* exp_avg, float* exp_avg_sq, int64_t* step_counter,
+                                       double lr0, double gamma, int64_t step_size, int64_t n_steps, const uint64_t* peer_buffers,
+                                       int32_t rank, int32_t world, uint32_t first_tag, float* grad_flat, double* loss_sums,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = validate_net(net)) return e;
+  if (n <= 0 || !x || !y || n_global <= 0 || !params_flat || !exp_avg || !exp_avg_sq || !step_counter || step_size <= 0 || !workspace ||
+      n_steps < 0 || !peer_buffers || world < 1 || world > 32 || rank < 0 || rank >= world || first_tag == 0)
+    return PINN_E_ARG;
+  if (drop != nullptr && drop->masks != nullptr && n_steps > 1) return PINN_E_ARG;
+  if (wide_tc_bwd_covers(net) || !tc_bwd_covers(net)) return PINN_E_SHAPE;
+  ParamLayout lay = make_layout(net->width, net->n_hidden);
+  if (net->W[0] != params_flat + lay.offW[0] || net->bv2 != params_flat + lay.offbv2) return PINN_E_ARG;
+  if (!aligned16(x) || !aligned16(workspace)) return PINN_E_ALIGN;
+  pinn_dropout_t d{};
+  if (drop != nullptr) d = *drop;
+  for (int64_t i = 0; i < n_steps; ++i) {
+    if (drop != nullptr) d.pass_offset = drop->pass_offset + i;
+    FusedAdam fa{params_flat, exp_avg, exp_avg_sq, step_counter, AdamHyper{lr0, gamma, 1.0, step_size}, nullptr, 1.0f, i > 0 ? 1 : 0,
+                 reinterpret_cast<const unsigned long long*>(peer_buffers), rank, world, first_tag + static_cast<uint32_t>(i)};
+    const int r = launch_tc_bwd(net, x, n, make_drop_params(drop != nullptr ? &d : nullptr), nullptr, nullptr, y, n_global, grad_flat,
+                                loss_sums, workspace, workspace_bytes, static_cast<cudaStream_t>(stream), &fa);
+    if (r != 0) return r;
+  }
+  return 0;
+}

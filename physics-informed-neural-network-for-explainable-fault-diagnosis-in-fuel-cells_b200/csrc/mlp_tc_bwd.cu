@@ -949,17 +949,53 @@ grad_reduce2_kernel(const float* __restrict__ partial, const double* __restrict_
   }
   fold[g][c] = acc;
   __syncthreads();
-  if (g == 0 && i < total) {
-    double t = 0.0;
+  if (g == 0) {
+    float gr = 0.f;
+    if (i < total) {
+      double t = 0.0;
 #pragma unroll
-    for (int k = 0; k < kRedGroups; ++k) t += fold[k][c];
-    const float gr = layout_is_padding(lay, i) ? 0.0f : static_cast<float>(t);     // padding slots hold no partial sums
-    if (grad != nullptr) grad[i] = gr;
-    if (fa.params != nullptr) {
-      float pp = fa.params[i], mm = fa.m[i], vv = fa.v[i];
-      adam_apply(pp, static_cast<float>(static_cast<double>(gr) * fa.h.grad_scale), mm, vv, consts[0], consts[1], 0.f, 0.f, false);
-      fa.params[i] = pp; fa.m[i] = mm; fa.v[i] = vv;
-      if (fa.images != nullptr) image_write_entry(lay, i, pp, fa.wscale, fa.images);
+      for (int k = 0; k < kRedGroups; ++k) t += fold[k][c];
+      gr = layout_is_padding(lay, i) ? 0.0f : static_cast<float>(t);     // padding slots hold no partial sums
+    }
+    if (fa.peers != nullptr) {
+      // Data parallel: this CTA owns one 128-byte line of the bucket on EVERY rank.  Push the local sums of the line into
+      // slot (tag & 1), row `rank`, of every rank's symmetric buffer (posted NVLink stores), raise the line's flag there,
+      // wait for the same line of every rank in the LOCAL buffer, add the rows in rank order (bit-identical replicas).
+      // No grid-wide rendezvous, no NVLink loads; two slots make it race-free without a second barrier (a rank can be at
+      // most one step ahead: step t+1 cannot complete anywhere before every rank has pushed -- hence finished reading -- t).
+      const int64_t lines = dp_lines(total), fw = dp_flag_words(total, fa.world);
+      const size_t row = (static_cast<size_t>(fa.tag & 1u) * fa.world + fa.rank) * total;
+      if (i < total) {
+        for (int r = 0; r < fa.world; ++r)
+          __stcg(reinterpret_cast<float*>(fa.peers[r]) + fw + row + i, gr);
+      }
+      __threadfence_system();
+      __syncwarp();
+      if (c < fa.world) {
+        unsigned int* flag = reinterpret_cast<unsigned int*>(fa.peers[c]) + static_cast<size_t>(fa.rank) * lines + blockIdx.x;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(fa.tag) : "memory");
+        const unsigned int* mine = reinterpret_cast<const unsigned int*>(fa.peers[fa.rank]) + static_cast<size_t>(c) * lines + blockIdx.x;
+        unsigned int seen;
+        do {
+          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+        } while (static_cast<int>(seen - fa.tag) < 0);
+      }
+      __syncwarp();
+      if (i < total) {
+        const float* base = reinterpret_cast<const float*>(fa.peers[fa.rank]) + fw + static_cast<size_t>(fa.tag & 1u) * fa.world * total + i;
+        float sum = 0.f;
+        for (int r = 0; r < fa.world; ++r) sum += __ldcv(base + static_cast<size_t>(r) * total);
+        gr = sum;
+      }
+    }
+    if (i < total) {
+      if (grad != nullptr) grad[i] = gr;
+      if (fa.params != nullptr) {
+        float pp = fa.params[i], mm = fa.m[i], vv = fa.v[i];
+        adam_apply(pp, static_cast<float>(static_cast<double>(gr) * fa.h.grad_scale), mm, vv, consts[0], consts[1], 0.f, 0.f, false);
+        fa.params[i] = pp; fa.m[i] = mm; fa.v[i] = vv;
+        if (fa.images != nullptr) image_write_entry(lay, i, pp, fa.wscale, fa.images);
+      }
     }
   }
   if (loss != nullptr && blockIdx.x == 0 && g == 1) {

@@ -92,7 +92,9 @@ class SymmetricBucket:
         return self.buf[P2P_FLAG_WORDS + i * self.n: P2P_FLAG_WORDS + (i + 1) * self.n]
 
     @staticmethod
-    def create(n, device, group=None):
+    def create(n, device, group=None, words=None):
+        """``words``: total 32-bit words of the buffer when it is not the ``[64 | n | n]`` layout (``train_dnn_steps_dp``
+        uses ``kernels.dp_bucket_words``)."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) < 2:
             return None
         if dist.get_backend(group) != "nccl":
@@ -100,7 +102,7 @@ class SymmetricBucket:
         try:
             import torch.distributed._symmetric_memory as symm
             from .kernels import P2P_FLAG_WORDS
-            buf = symm.empty(P2P_FLAG_WORDS + 2 * n, dtype=torch.float32, device=device)
+            buf = symm.empty(int(words) if words is not None else P2P_FLAG_WORDS + 2 * n, dtype=torch.float32, device=device)
             buf.zero_()
             handle = symm.rendezvous(buf, group if group is not None else dist.group.WORLD)
             torch.cuda.synchronize(device)

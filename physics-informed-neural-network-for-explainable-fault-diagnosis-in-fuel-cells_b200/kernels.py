@@ -327,6 +327,34 @@ def adam_step_p2p(params, peer_ptrs, rank, world, slot, step_tag, exp_avg, exp_a
     LAUNCHES += 1
 
 
+def dp_bucket_words(width: int, n_hidden: int, world: int) -> int:
+    """32-bit words of the symmetric buffer ``train_dnn_steps_dp`` exchanges the gradient bucket through."""
+    return int(_abi.lib().pinn_dp_bucket_words(int(width), int(n_hidden), int(world)))
+
+
+def train_dnn_steps_dp(net: Net, x, drop: Optional[PinnDropout], y, n_global: int, params_flat, exp_avg, exp_avg_sq,
+                       step_counter, lr0, gamma, step_size, n_steps: int, peer_ptrs, rank: int, world: int, first_tag: int,
+                       loss_sums, grad_flat=None):
+    """``n_steps`` data-parallel ``train_dnn`` steps from one call: the gradient sum over the ranks runs inside the
+    gradient-reduce launch over NVLink peer memory, Adam + StepLR in the same launch (``pinn_train_dnn_steps_dp``)."""
+    global LAUNCHES
+    _require_cuda(x, "x")
+    _require_cuda(y, "y")
+    if not x.is_contiguous() or not y.is_contiguous():
+        raise RuntimeError("b200pinn: `x` and `y` must be contiguous")
+    n = x.shape[0]
+    L = _abi.lib()
+    nb = L.pinn_mlp_bwd_workspace_bytes_flags(net.width, net.n_hidden, n, net.flags)
+    ws = _workspace("bwd", nb, x.device)
+    with torch.cuda.device(x.device):
+        check(L.pinn_train_dnn_steps_dp(net.ref(), ptr(x), n, C.byref(drop) if drop is not None else None, ptr(y), int(n_global),
+                                        ptr(params_flat), ptr(exp_avg), ptr(exp_avg_sq), ptr(step_counter), float(lr0),
+                                        float(gamma), int(step_size), int(n_steps), ptr(peer_ptrs), int(rank), int(world),
+                                        int(first_tag) & 0xFFFFFFFF, ptr(grad_flat), ptr(loss_sums), ptr(ws), nb, _stream()),
+              "pinn_train_dnn_steps_dp")
+    LAUNCHES += 2 * int(n_steps) + 1
+
+
 def adam_step_from_sums(params, sums, grad_slot, exp_avg, exp_avg_sq, step_counter, lr0, gamma, step_size,
                         lo=None, hi=None):
     """f3 for the physics scalars: gradient i = sums[grad_slot[i]] / sums[N]."""

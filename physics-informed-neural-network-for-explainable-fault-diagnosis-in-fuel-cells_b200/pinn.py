@@ -46,10 +46,10 @@ def _world():
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
-def _allreduce(t):
+def _allreduce(t, op="sum"):
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(t)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN if op == "min" else dist.ReduceOp.SUM)
     return t
 
 
@@ -268,10 +268,17 @@ class PhysicsInformedNN:
         x, y = self.x.detach(), self.u.reshape(-1).contiguous()
         n_local = x.shape[0]
         world = self._dp_world()
-        n_global = n_local
+        n_global, n_min = n_local, n_local
         if world > 1:
-            t = torch.tensor([n_local], device=self.device, dtype=torch.int64)
-            n_global = int(_allreduce(t).item())
+            # global batch size and the smallest shard: two tiny collectives, once per (shard size, world) -- not per call
+            cached = getattr(self, "_dp_sizes", None)
+            if cached is None or cached[0] != (n_local, world):
+                t = torch.tensor([n_local, -n_local], device=self.device, dtype=torch.int64)
+                tot = _allreduce(t[:1].clone())
+                mn = _allreduce(t[1:].clone(), op="min")
+                cached = ((n_local, world), int(tot.item()), -int(mn.item()))
+                self._dp_sizes = cached
+            n_global, n_min = cached[1], cached[2]
         # data parallel: the all-reduce of the gradient bucket is fused into the Adam launch over NVLink peer memory
         # (dist.SymmetricBucket); without symmetric memory (gloo, no peer access) it is one NCCL / gloo all-reduce
         bucket = None
@@ -286,6 +293,37 @@ class PhysicsInformedNN:
             print("  Epoch |    Loss    |    MSE     |    LR    ")
         loss = float("nan")
         fused_step = n_local > 0 and os.environ.get("B200PINN_FUSED_DNN_STEP", "1") != "0"
+        if (bucket is not None and fused_step and self.dnn._injected is None and net.width == 64 and 2 <= net.n_hidden <= 4
+                and os.environ.get("B200PINN_DNN_STEP_BLOCKS", "1") != "0"
+                and n_min > 0):
+            # data parallel, 64-wide net: every stretch of epochs up to the next progress line is ONE call; the gradient
+            # sum over the ranks runs inside each step's gradient-reduce launch over NVLink peer memory
+            from .dist import SymmetricBucket
+            dpb = getattr(self, "_dp_bucket", None)
+            words = K.dp_bucket_words(net.width, net.n_hidden, world)
+            if dpb is None or dpb.n != words:
+                dpb = SymmetricBucket.create(words, self.device, words=words)
+                self._dp_bucket = dpb
+            if dpb is not None:
+                epoch = 0
+                while epoch < nIter:
+                    stop = min(((epoch + 999) // 1000) * 1000, nIter - 1)
+                    k = stop - epoch + 1
+                    cfg = self.dnn.next_dropout_cfg(n_local, self.dnn.active_dropout_p())
+                    drop = K.make_dropout(**cfg) if cfg is not None else None
+                    if cfg is not None:
+                        self.dnn._drop_calls += k - 1
+                    K.train_dnn_steps_dp(net, x, drop, y, n_global, flat, m, v, counter, 1e-2, 0.8, 1000, k, dpb.ptrs, dpb.rank,
+                                         dpb.world, dpb.tag + 1, sums)
+                    dpb.tag += k
+                    s = _allreduce(sums.clone()).cpu().numpy()
+                    loss = (s[0] + 0.01 * s[1]) / max(s[3], 1.0)
+                    if verbose and stop % 1000 == 0:
+                        print(f" {stop:5d}  | {loss:10.3e} | {s[2] / max(s[3], 1.0):10.3e} | {1e-2 * 0.8 ** (stop // 1000):8.1e}")
+                    epoch = stop + 1
+                if verbose:
+                    print(f"DNN training done, final loss: {loss:.3e}\n")
+                return loss
         if (world == 1 and fused_step and self.dnn._injected is None
                 and os.environ.get("B200PINN_DNN_STEP_BLOCKS", "1") != "0"):
             # single GPU, Philox masks: every stretch of epochs up to the next progress line is ONE call that enqueues
