@@ -49,7 +49,7 @@ struct FzSmall {      // float offsets into the small-tensor area of shared memo
 PINN_HD FzSmall make_fz_small(int L) {
   FzSmall t{};
   int o = 0;
-  t.W0 = o; o += 64 * PINN_N_IN;
+  t.W0 = o; o += 2 * 64 * PINN_N_IN;      // layer 0 as UMMA planes: hi [2 chunks][64 rows][4], then lo
   for (int l = 0; l < 3; ++l) { t.b[l] = o; if (l < L) o += 64; }
   t.bv0 = o; o += 32; t.bv1 = o; o += 16;
   t.Wv1 = o; o += 16 * 32; t.Wv2 = o; o += 16;
@@ -164,7 +164,13 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
   const float wscale = drop_on ? dp.scale : 1.0f;
   if (tid < kFzThreads) {
     // small tensors: one element per thread (W0 and Wv1 are 512 floats each); biases / Wv2 / bp / bv2 laid over the thread index
-    sm[sl.W0 + tid] = __ldg(net.W[0] + tid) * kTanhArg;
+    {   // W0 [64 x 8] -> K-major hi / lo planes (one K = 8 slab: two 4-column chunks of 64 rows x 16 B)
+      const int j = tid >> 3, k = tid & 7;
+      const float w = __ldg(net.W[0] + tid), h = tc::tf32_hi(w);
+      const int off = (k >> 2) * 256 + j * 4 + (k & 3);
+      sm[sl.W0 + off] = h;
+      sm[sl.W0 + 512 + off] = w - h;
+    }
     sm[sl.Wv1 + tid] = __ldg(net.Wv1 + tid);
     if (tid < 64 * L) sm[sl.b[tid >> 6] + (tid & 63)] = __ldg(net.b[tid >> 6] + (tid & 63)) * kTanhArg;
     else if (tid >= 256 && tid < 288) sm[sl.bv0 + tid - 256] = __ldg(net.bv0 + tid - 256) * kTanhArg;
@@ -216,6 +222,19 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
     };
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const bool has_next = tile + gridDim.x < n_tiles;
+      {   // layer 0: x (K = 8, hi / lo in tensor memory) against the resident W0 planes
+        tc::mbar_wait(&bar_ready, rp);
+        rp ^= 1u;
+        __syncwarp();
+        if (tc::elect_one()) {
+          tc::fence_after_sync();
+          const uint32_t w0_u = tc::smem_u32(sm + sl.W0);
+          tc::issue_3xtf32_ts<8>(tmem + kColD, tmem + kColAhi, tmem + kColAlo, tc::make_desc(w0_u, 1024, 128),
+                                 tc::make_desc(w0_u + 2048, 1024, 128), 1024, idesc64);
+          tc::umma_commit(&bar_chain);
+        }
+        __syncwarp();
+      }
 #pragma unroll
       for (int p = 0; p < 2 * L; ++p) {
         tc::mbar_wait(&bar_ready, rp);
@@ -364,34 +383,23 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
       uint32_t kb[L];
       TLF(tl);
       // ============================ forward ============================
-      {
+      // layer 0 runs on the tensor core too (K = 8): the slice-0 thread of a row parks x as hi / lo columns 0..7
+      if (c == 0) {
         const float xr[PINN_N_IN] = {xq0.x, xq0.y, xq0.z, xq0.w, xq1.x, xq1.y, xq1.z, xq1.w};
-        kb[0] = keep16(ks, active, 0u);
-        const float* W0 = sm + sl.W0 + cb * PINN_N_IN;
-        const float* b0 = sm + sl.b[0] + cb;
+        float h8[8], l8[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float4 w0 = *reinterpret_cast<const float4*>(W0 + i * PINN_N_IN);
-          const float4 w1 = *reinterpret_cast<const float4*>(W0 + i * PINN_N_IN + 4);
-          float z = b0[i];
-          z = fmaf(w0.x, xr[0], z); z = fmaf(w0.y, xr[1], z); z = fmaf(w0.z, xr[2], z); z = fmaf(w0.w, xr[3], z);
-          z = fmaf(w1.x, xr[4], z); z = fmaf(w1.y, xr[5], z); z = fmaf(w1.z, xr[6], z); z = fmaf(w1.w, xr[7], z);
-          acur[i] = ((kb[0] >> i) & 1u) ? tanh_pre(z) : 0.f;
-        }
-        float h[16], lo[16];
-        split16(acur, h, lo);
-        tc::tmem_st16(tAh + cb, h);
-        tc::tmem_st16(tAl + cb, lo);
+        for (int i = 0; i < 8; ++i) { h8[i] = tc::tf32_hi_fast(xr[i]); l8[i] = xr[i] - h8[i]; }
+        tc::tmem_st8(tAh, h8);
+        tc::tmem_st8(tAl, l8);
       }
       arrive_ready();
-      if (L > 1) park_st(0, acur);
       TLF(tl + 1);
 #pragma unroll
-      for (int l = 1; l < L; ++l) {
+      for (int l = 0; l < L; ++l) {
         kb[l] = keep16(ks, active, static_cast<uint32_t>(l));        // drawn while the tensor core works
-        TLF(tl + 2 * l);
+        TLF(tl + 2 + 2 * l);
         wait_chain();
-        TLF(tl + 2 * l + 1);
+        TLF(tl + 3 + 2 * l);
         float z[16];
         tc::tmem_ld16(tD + cb, z);
         tc::tmem_wait_ld();
@@ -431,9 +439,9 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
         if (a.grad_u != nullptr) { y_pre = __ldg(a.grad_u + s); gs_pre = a.grad_s ? __ldg(a.grad_s + s) : 0.f; }
         else y_pre = __ldg(a.y + s);
       }
-      TLF(tl + 6);
+      TLF(tl + 8);
       wait_chain();
-      TLF(tl + 7);
+      TLF(tl + 9);
       float dzv0[8], du = 0.f;
       {
         float tailv[16];           // [0,8) av0 (scaled), [8,12) v1, [12,16) dz_v1: parked for the 0T batch
@@ -446,7 +454,7 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
         for (int i = 0; i < 8; ++i) tailv[i] = ((kbv >> i) & 1u) ? tanh_pre(fmaf(zv[i], kTanhArg, bv0[i])) * wscale : 0.f;
         tc::tmem_st8(tAh + 8 * c, tailv);
         qbar();
-        TLF(tl + 8);
+        TLF(tl + 10);
         const float* Wv1 = sm + sl.Wv1;
         float2 acc[4][2];
 #pragma unroll
@@ -471,9 +479,9 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
         for (int k = 0; k < 4; ++k)
           tailv[8 + k] = tanh_pre(fmaf((acc[k][0].x + acc[k][0].y) + (acc[k][1].x + acc[k][1].y), kTanhArg, sm[sl.bv1 + 4 * c + k]));
         tc::tmem_st4(tAh + 48 + 4 * c, tailv + 8);
-        TLF(tl + 9);
+        TLF(tl + 11);
         qbar();
-        TLF(tl + 10);
+        TLF(tl + 12);
         if (c == 0) {
           float v1a[16], dz[16];
           tc::tmem_ld16(tAh + 48, v1a);
@@ -513,9 +521,9 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
           tc::tmem_st16(tAl + 48, dz);
           tc::tmem_st1(tD + 56, dvv);          // D columns 48..63 are not touched by the heads product; the next chain product comes after every thread's arrive
         }
-        TLF(tl + 11);
+        TLF(tl + 13);
         qbar();
-        TLF(tl + 12);
+        TLF(tl + 14);
         float dzs[16], dv8[8];
         tc::tmem_ld16(tAl + 48, dzs);
         tc::tmem_ld8(tD + 56, dv8);
@@ -563,10 +571,10 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
           tc::tmem_st8(tAl + 40, z8);
         }
         arrive_ready();            // the heads^T product runs while batch H is staged
-        TLF(tl + 13);
+        TLF(tl + 15);
         park_st(L - 1, tailv);
         wait_wg();                 // the previous tile's 0T batch
-        TLF(tl + 14);
+        TLF(tl + 16);
 #pragma unroll
         for (int i = 0; i < 4; ++i) *reinterpret_cast<float*>(act_s + (64 + 4 * c + i) * 16) = (c == 0 && i == 0) ? 1.0f : 0.0f;
 #pragma unroll
@@ -577,7 +585,7 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
 #pragma unroll
         for (int i = 0; i < 16; ++i) act_st(cb + i, h[i], lo[i]);
         arrive_stage();
-        TLF(tl + 15);
+        TLF(tl + 17);
       }
 #pragma unroll
       for (int l = L - 1; l >= 0; --l) {
@@ -589,7 +597,7 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
           load_x(tile + gridDim.x);                     // the next tile's input row
         }
         wait_chain();
-        TLF(tl + 16 + 4 * (L - 1 - l));
+        TLF(tl + 18 + 4 * (L - 1 - l));
         float h[16], lo[16];
         {
           float z[16];
@@ -604,9 +612,9 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
           tc::tmem_st16(tAh + cb, h);
           tc::tmem_st16(tAl + cb, lo);
           arrive_ready();          // the next chain product runs while this layer's batch is staged
-          TLF(tl + 17 + 4 * (L - 1 - l));
+          TLF(tl + 19 + 4 * (L - 1 - l));
           wait_wg();
-          TLF(tl + 18 + 4 * (L - 1 - l));
+          TLF(tl + 20 + 4 * (L - 1 - l));
 #pragma unroll
           for (int i = 0; i < 16; ++i) del_st(cb + i, h[i], lo[i]);
 #pragma unroll
@@ -616,9 +624,9 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
           for (int i = 0; i < 16; ++i) act_st(cb + i, h[i], lo[i]);
         } else {
           // batch 0T (roles swapped): DEL = [x | av0 | av1 | 1], ACT = [delta_0 | dz_v1]
-          TLF(tl + 17 + 4 * (L - 1 - l));
+          TLF(tl + 19 + 4 * (L - 1 - l));
           wait_wg();
-          TLF(tl + 18 + 4 * (L - 1 - l));
+          TLF(tl + 20 + 4 * (L - 1 - l));
 #pragma unroll
           for (int i = 0; i < 16; ++i) act_st(cb + i, h[i], lo[i]);
 #pragma unroll
@@ -632,7 +640,7 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
           for (int i = 0; i < 4; ++i) { const float hh = tc::tf32_hi_fast(nxt[12 + i]); act_st(64 + 4 * c + i, hh, nxt[12 + i] - hh); }
         }
         arrive_stage();
-        TLF(tl + 19 + 4 * (L - 1 - l));
+        TLF(tl + 21 + 4 * (L - 1 - l));
       }
       tl += 32;
     }

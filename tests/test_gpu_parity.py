@@ -365,19 +365,19 @@ def test_train_dnn_trajectory_golden(golden):
             # three Adam steps of size lr=1e-2: compare the parameters themselves.  Adam's update lr*m/(sqrt(v)+eps) is
             # ill-conditioned where |gradient| ~ eps = 1e-8: a 1e-9 difference in such a gradient changes the step by a
             # large part of lr, up to its sign, and entries whose gradient is a sum of cancelling terms carry the fp32
-            # noise of BOTH implementations.  The 256-wide golden (n = 160) has such entries (a few per cent of a bias
-            # vector, under 1 % of a weight matrix): there the bars are 2e-4 of the tensor's scale for 95 % of the entries,
-            # 2e-3 for 99.5 %, a median below 5e-5, and for EVERY entry the hard bound of three Adam steps taken in opposite
-            # directions (2 * 3 * lr); the narrower nets meet 2e-4 everywhere.  (The gradients themselves are held to
-            # 1e-4 against the fp64 oracle in test_wide_tensor_core_backward_matches_ffma_path.)
+            # noise of BOTH implementations.  The narrower nets meet 2e-4 of the tensor's scale everywhere.  The 256-wide
+            # golden (n = 160) has such entries (a few per cent of a bias vector, under 1 % of a weight matrix), so there the
+            # error is measured against the distance travelled, 3 * lr: 95 % of a tensor's entries within 0.5 % of it,
+            # 99.5 % within 5 %, and EVERY entry within the hard bound of three steps taken in opposite directions.
+            # (The gradients themselves are held to 1e-4 against the fp64 oracle in
+            # test_wide_tensor_core_backward_matches_ffma_path.)
             got = t2n(sd[k[len("traj:dnn:"):]]).astype(np.float64)
-            scale = np.abs(v).max()
-            err = np.abs(got - v) / scale
             if golden["layers"][1] <= 64:
-                assert err.max() < 2e-4, k
+                assert (np.abs(got - v) / np.abs(v).max()).max() < 2e-4, k
             else:
-                assert (np.mean(err < 2e-4) >= 0.95 and np.mean(err < 2e-3) >= 0.995 and np.median(err) < 5e-5
-                        and err.max() < 6e-2 / scale), (k, err.max(), np.mean(err < 2e-4), np.mean(err < 2e-3), np.median(err))
+                err = np.abs(got - v) / 3e-2
+                assert np.mean(err < 5e-3) >= 0.95 and np.mean(err < 5e-2) >= 0.995 and err.max() < 2.0, \
+                    (k, err.max(), np.mean(err < 5e-3), np.mean(err < 5e-2))
 
 
 # ------------------------------------------------------------------ golden: MC dropout

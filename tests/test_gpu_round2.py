@@ -410,3 +410,68 @@ def test_logvar_false_paths_agree():
                     assert nrel(f[o:o + cnt].reshape(shp), G[nm].reshape(shp)) < GRAD_TOL, nm
             s = t2n(sums)
             assert abs(s[0] / s[3] - 0.5 * np.mean((y - o64) ** 2)) < LOSS_TOL and s[1] == 0.0
+
+
+# ------------------------------------------------------------------ K2 as one kernel vs the two-kernel form vs the oracle
+@pytest.mark.parametrize("layers,n", [([8, 64, 64, 64, 1], 1), ([8, 64, 64, 64, 1], 129), ([8, 64, 64, 64, 1], 5001),
+                                      ([8, 64, 64, 64, 1], 20000), ([8, 64, 64, 64, 1], 40000), ([8, 64, 64, 1], 19077)])
+def test_fused_backward_matches_two_kernel_form_and_oracle(layers, n):
+    """The one-kernel K2 (forward, dgrad and all weight gradients of a tile on chip, mlp_tc_fused.cuh) against the two-kernel
+    form it replaces (`no_fused_bwd`: K2a + row table + K2b) on the same Philox stream -- tile edges, one tile per SM, the
+    1..1.6 tiles-per-SM window where the launcher itself picks the two-kernel form, several tiles per SM, L = 2 and 3 -- and
+    against the fp64 oracle with injected masks; bitwise repeatable; the caller-supplied-gradient form (`grad_u`,
+    `grad_logvar`: the autograd path of 01:953) agrees with the fused-loss form."""
+    from b200pinn import kernels as K
+    from b200pinn.synthetic import make_scaled_dataset
+
+    p = 0.2
+    x, y, _, _ = make_scaled_dataset(max(n, 64), seed=31)
+    x, y = x[:n], y[:n]
+    dnn = random_net(layers, 11)
+    net = K.net_from_module(dnn)
+    xd, yd = torch.tensor(x, device=dev()), torch.tensor(y, device=dev()).reshape(-1).contiguous()
+    drop = lambda: K.make_dropout(p, seed=17, pass_offset=4)
+    a, sa = K.mlp_backward(net, xd, drop(), y=yd, n_global=n)
+    a2, _ = K.mlp_backward(net, xd, drop(), y=yd, n_global=n)
+    assert torch.equal(a, a2), "not bitwise repeatable"
+    with K.path_flags(no_fused_bwd=True):
+        b, sb = K.mlp_backward(net, xd, drop(), y=yd, n_global=n)
+    assert np.allclose(t2n(sa), t2n(sb), rtol=LOSS_TOL)
+    names, shapes, offs, _ = K.param_layout(net.width, net.n_hidden)
+    fa, fb = t2n(a), t2n(b)
+    for nm, shp, o in zip(names, shapes, offs):
+        cnt = int(np.prod(shp))
+        assert nrel(fa[o:o + cnt], fb[o:o + cnt]) < 2e-5, nm
+    if n <= 6000:
+        rng = np.random.default_rng(8)
+        D = (len(layers) - 2) * 64 + 32
+        mk = (rng.random((n, D)) >= p).astype(np.uint8)
+        c, _ = K.mlp_backward(net, xd, K.make_dropout(p, seed=1, masks=torch.tensor(mk, device=dev()), mask_rows=n), y=yd, n_global=n)
+        ms64 = split_masks(mk, layers, p, np.float64)
+        P = params_np(dnn)
+        o64, l64 = O.dnn_forward(P, x, ms64, np.float64)
+        du64, ds64 = O.aleatoric_loss_grads(y, o64, l64)
+        G = O.dnn_backward(P, x, ms64, du64, ds64)
+        fc = t2n(c)
+        for nm, shp, o in zip(names, shapes, offs):
+            ref = G[nm]
+            assert nrel(fc[o:o + ref.size].reshape(shp), ref.reshape(shp)) < GRAD_TOL, nm
+        # the same gradients from caller-supplied output gradients
+        gu = torch.tensor(np.asarray(du64, np.float32).reshape(-1), device=dev())
+        gs = torch.tensor(np.asarray(ds64, np.float32).reshape(-1), device=dev())
+        d, _ = K.mlp_backward(net, xd, K.make_dropout(p, seed=1, masks=torch.tensor(mk, device=dev()), mask_rows=n), grad_u=gu, grad_logvar=gs)
+        fd = t2n(d)
+        for nm, shp, o in zip(names, shapes, offs):
+            ref = G[nm]
+            assert nrel(fd[o:o + ref.size].reshape(shp), ref.reshape(shp)) < GRAD_TOL, nm
+
+
+def test_fused_backward_workspace_is_independent_of_the_batch():
+    """The one-kernel K2 needs per-CTA partial vectors, weight images and an L2-sized parking lot -- a few tens of MB whatever
+    N is; the two-kernel form's row table is 2 KB per sample."""
+    from b200pinn import _abi
+
+    L = _abi.lib()
+    fused = L.pinn_mlp_bwd_workspace_bytes_flags(64, 3, 8_000_000, 0)
+    two = L.pinn_mlp_bwd_workspace_bytes_flags(64, 3, 8_000_000, _abi.NET_NO_FUSED_BWD)
+    assert fused < 64 << 20 and two > 8_000_000 * 1900 and L.pinn_mlp_bwd_workspace_bytes(64, 3, 8_000_000) >= two
