@@ -547,6 +547,7 @@ def run_ours(args):
     pk = peaks()
     mc_tflops = n * T_PASSES * FLOP_PER_SAMPLE_PASS / (t_mc / K_) / 1e12
     rec_mc, rec_res = ncu_record("mlp_tc_kernel<MC>"), ncu_record("residual_v_fast_kernel")
+    rec_tr = ncu_record("mlp_tc_fused_kernel")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": W_,
         "ms_per_step": 1e3 * t_mc / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -571,11 +572,21 @@ def run_ours(args):
                   "global_batch": world * n, "tflops": world * n * FLOP_PER_TRAIN_SAMPLE / (t_tr / steps_tr) / 1e12,
                   "single_gpu_ms_per_step": 1e3 * t_tr_local / steps_tr, "weak_scaling_efficiency": t_tr_local / t_tr,
                   "frac_of_bf16_peak_per_gpu": n * FLOP_PER_TRAIN_SAMPLE / (t_tr / steps_tr) / 1e12 / pk["bf16"],
-                  "what": "configs[1]: full-batch train_dnn step at N=1M per GPU (01:948-955): K2 forward+loss+dgrad+wgrad on "
-                          "tcgen05 3xTF32, partial reduce, "
-                          + ("gradient sum over NVLink peer memory fused into the Adam/StepLR launch; "
+                  "what": "configs[1]: full-batch train_dnn step at N=1M per GPU (01:948-955): ONE fused K2 launch (forward + loss + dgrad "
+                          "+ all weight gradients on tcgen05, on chip) + the fixed-order gradient reduce, "
+                          + ("with the gradient sum over the ranks (NVLink peer memory) and Adam/StepLR inside that reduce launch; "
                              if world > 1 else "Adam/StepLR in the reduce launch; ")
                           + "single_gpu_ms_per_step is the same model stepping without the exchange, timed in this job"},
+        "roofline_train": {"bound": "tensor", "kernel": "mlp_tc_fused_kernel<3> (one launch per step: forward, dgrad and every weight gradient of a "
+                                                        "tile on chip; accumulators resident in tensor memory, TMA-streamed weight images)",
+                           "achieved": n * FLOP_PER_TRAIN_SAMPLE / (t_tr_local / steps_tr) / 1e12, "peak": pk["bf16"], "unit": "TFLOP/s",
+                           "frac": n * FLOP_PER_TRAIN_SAMPLE / (t_tr_local / steps_tr) / 1e12 / pk["bf16"],
+                           "algorithmic_bytes_per_step": 40 * n,
+                           "traffic": (rec_tr["dram_bytes"] * n / rec_tr["n"]) if rec_tr else None, "ncu": rec_tr,
+                           "note": "achieved = algorithmic FLOPs (67 040 per sample) / step time of the single-GPU step (fused K2 + reduce/Adam); "
+                                   "3xTF32 / hi-lo stacked products: the tensor pipe does ~6x this fraction of the TF32 peak.  `traffic` = "
+                                   "dram__bytes of the fused launch from profiles/ncu_current.json (round 1's two-kernel form moved 4.0 GB per "
+                                   "step at N = 1M)"},
         "roofline_residual": {"bound": "hbm", "achieved": nb * RES_BYTES_PER_SAMPLE / t_resb / 1e9, "peak": pk["hbm"],
                               "unit": "GB/s", "frac": nb * RES_BYTES_PER_SAMPLE / t_resb / 1e9 / pk["hbm"],
                               "timing": "per launch, from a CUDA-graph replay of 20-30 back-to-back launches (no host latency between "
