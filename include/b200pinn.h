@@ -208,7 +208,12 @@ size_t pinn_residuals_workspace_bytes(int64_t n);
  * Finalised outputs (any may be NULL): pred_mean[n] = eval forward,
  * a_u[n] = sqrt(exp(mean_t logvar_t)), e_u[n] = sqrt(var_t u_t) (ddof 0).
  * Raw outputs for pass-sharded merging (any may be NULL): raw_mean[n], raw_m2[n],
- * raw_sum_logvar[n] over this call's T passes. */
+ * raw_sum_logvar[n] over this call's T passes.
+ * 64-wide nets cut sweeps of T >= 375 into runs of ~250 passes per tile (a function of T
+ * alone: a sample's numbers never depend on the batch size or its sharding) so that
+ * batches of a few tiles per SM still fill the machine; the runs' Welford triples sit in
+ * `workspace` (pinn_mc_workspace_bytes: 96 B per sample) until a merge launch folds them
+ * in order (Chan's update). */
 int pinn_mc_dropout(const pinn_net_t* net, const float* x, int64_t n, int32_t T,
                     const pinn_dropout_t* drop, float* pred_mean, float* a_u,
                     float* e_u, float* raw_mean, float* raw_m2,

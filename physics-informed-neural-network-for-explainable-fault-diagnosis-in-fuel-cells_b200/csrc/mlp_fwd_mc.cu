@@ -186,13 +186,19 @@ using namespace pinn;
 
 extern "C" size_t pinn_mlp_fwd_workspace_bytes(int32_t width, int32_t n_hidden, int64_t n) {
   Plan p = plan_tps(width, n_hidden, n, 1);
-  const size_t a = p.scratch_floats * sizeof(float), b = wide_tc_workspace_bytes(width, n_hidden, n);
-  return a > b ? a : b;
+  size_t a = p.scratch_floats * sizeof(float);
+  const size_t b = wide_tc_workspace_bytes(width, n_hidden, n);
+  const size_t c = width == 64 ? tc_mc_workspace_bytes(n) : 0;      // per-chunk Welford triples of long sweeps (mlp_tc.cu)
+  if (b > a) a = b;
+  return c > a ? c : a;
 }
 extern "C" size_t pinn_mc_workspace_bytes(int32_t width, int32_t n_hidden, int64_t n) {
   Plan p = plan_tps(width, n_hidden, n, 2);
-  const size_t a = p.scratch_floats * sizeof(float), b = wide_tc_workspace_bytes(width, n_hidden, n);
-  return a > b ? a : b;
+  size_t a = p.scratch_floats * sizeof(float);
+  const size_t b = wide_tc_workspace_bytes(width, n_hidden, n);
+  const size_t c = width == 64 ? tc_mc_workspace_bytes(n) : 0;      // per-chunk Welford triples of long sweeps (mlp_tc.cu)
+  if (b > a) a = b;
+  return c > a ? c : a;
 }
 
 extern "C" int pinn_mlp_fwd(const pinn_net_t* net, const float* x, int64_t n, const pinn_dropout_t* drop,
@@ -246,7 +252,8 @@ extern "C" int pinn_mc_dropout(const pinn_net_t* net, const float* x, int64_t n,
   {
     int err = 0;
     TcOut o{nullptr, nullptr, pred_mean, a_u, e_u, raw_mean, raw_m2, raw_sum_logvar};
-    const int r = launch_tc(true, net, x, n, T, make_drop_params(drop), o, static_cast<cudaStream_t>(stream), &err);
+    const int r = launch_tc(true, net, x, n, T, make_drop_params(drop), o, static_cast<cudaStream_t>(stream), &err, workspace,
+                            workspace_bytes);
     if (r == 1) return 0;
     if (r < 0) return err;
     const int rw = launch_wide_tc(true, net, x, n, T, make_drop_params(drop), o, workspace, workspace_bytes,

@@ -99,7 +99,7 @@ PINN_D void bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r
 template <bool MC, bool INJ>
 __global__ void __launch_bounds__(kTcThreads, 1)
 mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t n, int T, const __grid_constant__ DropParams dp,
-              TcOut out) {
+              TcOut out, int chunks, float* __restrict__ part) {
   constexpr int H = kTcH, HH = kTcH / 2;
   constexpr uint32_t LBO_B = H * 16, LBO_H = kHeadN * 16;
   extern __shared__ __align__(1024) float smem[];
@@ -154,7 +154,15 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
 
   const int64_t n_tiles = (n + kTcTile - 1) / kTcTile;
   const bool do_eval = MC && out.pred_mean != nullptr;
-  const int n_pass = MC ? T + (do_eval ? 1 : 0) : 1;
+  // Work item = (tile, pass chunk): a long sweep is cut into `chunks` runs of Tc consecutive passes per tile (chosen from T
+  // alone, so the arithmetic of a sample does not depend on the batch or its sharding); every run keeps its own Welford
+  // triple, mc_merge_kernel folds them in chunk order (Chan).  With few tiles per SM this is what fills the machine:
+  // 977 tiles x T = 1000 are 3.3 waves of whole-tile items but 13.2 waves of quarter-sweeps.
+  const int C = MC ? chunks : 1, Tc = (T + C - 1) / C;
+  auto item_passes = [&](int chunk) {            // dropout passes of the chunk (+ the eval pass, which rides with chunk 0)
+    const int t0 = chunk * Tc, cnt = (T - t0 < Tc ? T - t0 : Tc);
+    return MC ? (cnt > 0 ? cnt : 0) + ((do_eval && chunk == 0) ? 1 : 0) : 1;
+  };
   const uint32_t idesc64 = tc::make_idesc_tf32(kTcTile, H), idesc48 = tc::make_idesc_tf32(kTcTile, kHeadN);
 
   if (mma_warp) {
@@ -162,19 +170,16 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
     // One issuing warp per group; it walks the group's deterministic schedule (tile -> pass -> layers
     // 1..L-1 -> heads) and sleeps on the group's "ready" barrier in between.
     const int g = warp - 16;
-#ifdef PINN_K2A_PAIR_FIRST
-    const int64_t first = static_cast<int64_t>(blockIdx.x) * 2 + g;
-#else
     const int64_t first = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(g) * gridDim.x;     // same map as the compute warps below
-#endif
-    const int64_t tiles = first < n_tiles ? (n_tiles - first + 2 * gridDim.x - 1) / (2 * static_cast<int64_t>(gridDim.x)) : 0;
+    const int64_t n_items = n_tiles * C;
     const uint32_t d_t = tmem_base_s + static_cast<uint32_t>(g * 64);
     const uint32_t a_hi = tmem_base_s + static_cast<uint32_t>(128 + g * 128);
     uint32_t par = 0u;
 #ifdef PINN_TIMELINE
     int tlm = 0;
 #endif
-    for (int64_t it = 0; it < tiles * n_pass; ++it) {
+    for (int64_t item = first; item < n_items; item += 2 * static_cast<int64_t>(gridDim.x))
+    for (int it = 0, np = item_passes(static_cast<int>(item % C)); it < np; ++it) {
 #pragma unroll 1
       for (int l = 1; l <= L; ++l) {
         const bool heads = l == L;
@@ -277,11 +282,11 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
 
     // tile -> (CTA, group): group 0 of every CTA first, then group 1: up to one tile per SM every tile runs alone (a lone
     // tile finishes ~1.4x sooner than a tile of an interleaved pair; pairing only buys throughput once all SMs are busy)
-#ifdef PINN_K2A_PAIR_FIRST
-    for (int64_t tile = static_cast<int64_t>(blockIdx.x) * 2 + grp; tile < n_tiles; tile += static_cast<int64_t>(gridDim.x) * 2) {
-#else
-    for (int64_t tile = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(grp) * gridDim.x; tile < n_tiles; tile += static_cast<int64_t>(gridDim.x) * 2) {
-#endif
+    for (int64_t item = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(grp) * gridDim.x; item < n_tiles * C; item += static_cast<int64_t>(gridDim.x) * 2) {
+      const int64_t tile = item / C;
+      const int chunk = static_cast<int>(item % C), t0 = chunk * Tc;
+      const bool eval_item = do_eval && chunk == 0;
+      const int n_pass = item_passes(chunk);
       const int64_t s = tile * kTcTile + row;
       const bool valid = s < n;
       // layer 0 (pass-invariant): this thread's 32 columns -> tensor memory
@@ -320,11 +325,12 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
       KeepSrc<INJ> ks;
       ks.s_lo = static_cast<uint32_t>(sg); ks.s_hi = static_cast<uint32_t>(sg >> 32);
       uint4 r0[4] = {};        // draws of the coming pass's layer-0 staging
-      if (!INJ && drop_on && !do_eval) draw(r0, 4, ks, static_cast<uint32_t>(dp.pass_offset), 0u, cb);
+      if (!INJ && drop_on && !eval_item) draw(r0, 4, ks, static_cast<uint32_t>(dp.pass_offset + t0), 0u, cb);
 #pragma unroll 1
       for (int pi = 0; pi < n_pass; ++pi) {
-        const bool eval_pass = MC && do_eval && pi == 0;
-        const int t = MC ? (do_eval ? pi - 1 : pi) : 0;
+        const bool eval_pass = MC && eval_item && pi == 0;
+        const int tl = MC ? (eval_item ? pi - 1 : pi) : 0;      // pass index inside the chunk (Welford count)
+        const int t = t0 + tl;                                  // pass index of the sweep (mask stream)
         // dropout is active on this pass?  (injected masks: tail rows of the last tile have no mask row)
         const bool active = drop_on && !eval_pass && (!INJ || valid);
         ks.pass = static_cast<uint32_t>(dp.pass_offset + t);
@@ -446,7 +452,7 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
               if (valid) out.pred_mean[s] = u;
             } else {
               const float d = u - mean;
-              mean += d / static_cast<float>(t + 1);
+              mean += d / static_cast<float>(tl + 1);
               m2 = fmaf(d, u - mean, m2);
               slv += lv;
             }
@@ -455,7 +461,10 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
         }
         TL_NEXT();
       }
-      if (MC && valid && half == 0) {
+      if (MC && valid && half == 0 && C > 1) {
+        float* pp = part + static_cast<size_t>(chunk) * 3 * n + s;
+        pp[0] = mean; pp[n] = m2; pp[2 * n] = slv;
+      } else if (MC && valid && half == 0) {
         if (out.raw_mean) out.raw_mean[s] = mean;
         if (out.raw_m2) out.raw_m2[s] = m2;
         if (out.raw_slv) out.raw_slv[s] = slv;
@@ -473,8 +482,45 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
 
 // Launch helper used by pinn_mlp_fwd / pinn_mc_dropout.  Returns 1 if the TC path took the
 // call, 0 if the shape is not covered (caller falls through to the FFMA kernels), <0 / >1 on error.
+// Fold the per-chunk Welford triples of a sweep in chunk order (Chan's update, fp32 like the kernel's own running form)
+// and finish the sample: a_u = sqrt(exp(mean_t logvar)), e_u = sqrt(var_t u) (01:1483-1486).
+__global__ void __launch_bounds__(256) mc_merge_kernel(const float* __restrict__ part, int64_t n, int T, int C, TcOut out) {
+  const int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int Tc = (T + C - 1) / C;
+  float cnt = 0.f, mean = 0.f, m2 = 0.f, slv = 0.f;
+  for (int k = 0; k < C; ++k) {
+    const int t0 = k * Tc, ck = T - t0 < Tc ? T - t0 : Tc;
+    if (ck <= 0) break;
+    const float* pp = part + static_cast<size_t>(k) * 3 * n + s;
+    const float mb = pp[0], m2b = pp[n], sb = pp[2 * n], cb = static_cast<float>(ck);
+    if (k == 0) { cnt = cb; mean = mb; m2 = m2b; slv = sb; }
+    else {
+      const float tot = cnt + cb, d = mb - mean;
+      mean = mean + d * (cb / tot);
+      m2 = m2 + m2b + d * d * (cnt * cb / tot);
+      slv += sb;
+      cnt = tot;
+    }
+  }
+  if (out.raw_mean) out.raw_mean[s] = mean;
+  if (out.raw_m2) out.raw_m2[s] = m2;
+  if (out.raw_slv) out.raw_slv[s] = slv;
+  const float invT = 1.0f / static_cast<float>(T > 0 ? T : 1);
+  if (out.a_u) out.a_u[s] = sqrtf(expf(slv * invT));
+  if (out.e_u) out.e_u[s] = sqrtf(fmaxf(m2, 0.f) * invT);
+}
+
+// Pass chunks of a sweep: runs of ~250 passes, at most 8 -- a function of T ALONE, so that a sample's numbers do not depend
+// on the batch size or on how the batch is sharded (tests assert bitwise shard invariance).
+int mc_pass_chunks(int T) {
+  const int c = (T + 125) / 250;
+  return c < 1 ? 1 : (c > 8 ? 8 : c);
+}
+size_t tc_mc_workspace_bytes(int64_t n) { return static_cast<size_t>(8) * 3 * static_cast<size_t>(n > 0 ? n : 0) * sizeof(float); }
+
 int launch_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, const DropParams& dp, const TcOut& out,
-              cudaStream_t st, int* err) {
+              cudaStream_t st, int* err, void* workspace, size_t workspace_bytes) {
   *err = 0;
   if ((net->flags & PINN_NET_NO_TC_FWD) || net->width != kTcH || net->n_hidden < 2 || net->n_hidden > PINN_MAX_HIDDEN) return 0;
   for (int l = 1; l < net->n_hidden; ++l)
@@ -484,23 +530,22 @@ int launch_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, 
   const size_t smem = static_cast<size_t>(lay.total) * sizeof(float);
   if (smem > 226 * 1024) return 0;          // resident weight planes: 32 KB per hidden layer (7 hidden layers fit)
   const int64_t tiles = (n + kTcTile - 1) / kTcTile;
-#ifdef PINN_K2A_PAIR_FIRST
-  const int64_t want = (tiles + 1) / 2;        // two 128-sample tiles in flight per CTA
-#else
-  const int64_t want = tiles;                  // one CTA per tile until the SMs run out, then two tiles in flight per CTA
-#endif
+  const int C = mc ? mc_pass_chunks(T) : 1;
+  const int64_t want = tiles * C;              // one CTA per work item until the SMs run out, then two items in flight per CTA
   const int grid = static_cast<int>(want < sm_count() ? (want > 0 ? want : 1) : sm_count());
   const bool inj = dp.p > 0.f && dp.masks != nullptr;
   auto go = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    kern<<<grid, kTcThreads, smem, st>>>(*net, lay, x, n, T, dp, out);
+    kern<<<grid, kTcThreads, smem, st>>>(*net, lay, x, n, T, dp, out, C, static_cast<float*>(workspace));
     return cudaSuccess;
   };
+  if (C > 1 && (workspace == nullptr || workspace_bytes < static_cast<size_t>(C) * 3 * n * sizeof(float))) { *err = PINN_E_WORKSPACE; return -1; }
   cudaError_t e;
   if (mc) e = inj ? go(mlp_tc_kernel<true, true>) : go(mlp_tc_kernel<true, false>);
   else e = inj ? go(mlp_tc_kernel<false, true>) : go(mlp_tc_kernel<false, false>);
   if (e != cudaSuccess) { *err = static_cast<int>(e); return -1; }
+  if (C > 1) mc_merge_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(static_cast<const float*>(workspace), n, T, C, out);
   *err = static_cast<int>(cudaGetLastError());
   return *err == 0 ? 1 : -1;
 }

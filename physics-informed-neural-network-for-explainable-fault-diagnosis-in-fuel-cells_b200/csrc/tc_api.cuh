@@ -9,7 +9,10 @@ struct TcOut {
 };
 // 1: launched on the tcgen05 path; 0: shape not covered (use the FFMA kernels); -1: error in *err.
 int launch_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, const DropParams& dp, const TcOut& out,
-              cudaStream_t st, int* err);
+              cudaStream_t st, int* err, void* workspace = nullptr, size_t workspace_bytes = 0);
+// long sweeps are cut into pass chunks (a function of T alone) whose Welford triples live in the workspace until merged
+int mc_pass_chunks(int T);
+size_t tc_mc_workspace_bytes(int64_t n);
 // Wide nets (H = 128 / 256) on the tensor cores, one GEMM launch per layer (mlp_wide_tc.cu); same return convention.
 size_t wide_tc_workspace_bytes(int H, int L, int64_t n);
 int launch_wide_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, const DropParams& dp, const TcOut& out,
