@@ -918,7 +918,10 @@ namespace pinn {
 // folded in warp order.  (The first version walked all partials serially in one thread per entry -- 24 us at
 // N = 20 000, a quarter of the whole train_dnn step there.)  With `fa.params` set the same launch applies
 // Adam + StepLR to the bucket entry it just reduced (single-GPU train_dnn: no all-reduce sits in between).
-constexpr int kRedCols = 32, kRedGroups = 8;
+#ifndef PINN_RED_GROUPS
+#define PINN_RED_GROUPS 16      // 8: +0.7..2 us per step at N = 19..20 k, 32: +8 us (profiles/c1_train_dnn_launches.py)
+#endif
+constexpr int kRedCols = 32, kRedGroups = PINN_RED_GROUPS;
 __global__ void __launch_bounds__(kRedCols * kRedGroups)
 grad_reduce2_kernel(const float* __restrict__ partial, const double* __restrict__ loss_partial, int nblk, int nloss, int64_t total,
                     float* __restrict__ grad, double* __restrict__ loss, const FusedAdam fa, const ParamLayout lay) {

@@ -5,6 +5,9 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import b200pinn
+if os.environ.get("B200PINN_LIB"):        # A/B builds (profiles/build_variant.py)
+    import b200pinn._abi as _abi
+    _abi.LIB_PATH = os.environ["B200PINN_LIB"]
 from b200pinn.synthetic import make_scaled_dataset
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
