@@ -44,7 +44,7 @@ constexpr uint32_t kColD = 0, kColAhi = 64, kColAlo = 128, kColAcc = 192, kAccW 
 constexpr int kTX = 0, kTV0 = 8, kTV1 = 40, kTOne = 56;
 
 struct FzSmall {      // float offsets into the small-tensor area of shared memory
-  int W0, b[3], bv0, bv1, Wv1, Wv2, bp, bv2, total;
+  int W0, b[3], bv0, bv1, Wv1f, Wv1t, Wv2, bp, bv2, total;
 };
 PINN_HD FzSmall make_fz_small(int L) {
   FzSmall t{};
@@ -52,7 +52,9 @@ PINN_HD FzSmall make_fz_small(int L) {
   t.W0 = o; o += 2 * 64 * PINN_N_IN;      // layer 0 as UMMA planes: hi [2 chunks][64 rows][4], then lo
   for (int l = 0; l < 3; ++l) { t.b[l] = o; if (l < L) o += 64; }
   t.bv0 = o; o += 32; t.bv1 = o; o += 16;
-  t.Wv1 = o; o += 16 * 32; t.Wv2 = o; o += 16;
+  t.Wv1f = o; o += 2 * 16 * 32;      // Wv1 [16 x 32] as UMMA planes (B of the 32 -> 16 product): hi [8 chunks][16 rows][4], then lo
+  t.Wv1t = o; o += 2 * 16 * 32;      // Wv1^T (B of its dgrad, K = 16): hi [4 chunks][32 rows][4], then lo
+  t.Wv2 = o; o += 16;
   t.bp = o; o += 4; t.bv2 = o; o += 4;
   t.total = o;
   return t;
@@ -116,12 +118,15 @@ struct FzArgs {
   const unsigned char* images;
   float* partial;            // [grid][lay.total]
   double* loss_partial;      // [grid][4]
-  float* park;               // [grid][L][4][512] float4 (see the kernel)
+  float* park;               // [grid][L + 1][4][512] float4 (see the kernel)
 };
 
 #ifdef PINN_TIMELINE
+#ifndef PINN_TL_TID
+#define PINN_TL_TID 0      // the compute thread that stamps (0: warp 0 = quadrant 0, slice 0, on the MMA warp's scheduler)
+#endif
 __device__ long long g_tlf[2][256];      // CTA 0: [0] compute thread 0, [1] the MMA warp's elected lane; clock64 at the stamps below, 32 per tile
-#define TLF(i) do { if (blockIdx.x == 0 && tid == 0 && (i) < 256) g_tlf[0][i] = clock64(); } while (0)
+#define TLF(i) do { if (blockIdx.x == 0 && tid == PINN_TL_TID && (i) < 256) g_tlf[0][i] = clock64(); } while (0)
 #define TLM(i) do { if (blockIdx.x == 0 && (i) < 256) g_tlf[1][i] = clock64(); } while (0)
 #else
 #define TLF(i) do { } while (0)
@@ -137,7 +142,7 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
   __shared__ __align__(8) uint64_t bar_ready, bar_stage, bar_chain, bar_wg, bar_full[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ double lred[4][4];
-  __shared__ double lacc[4][128];          // loss terms per sample row, summed over the CTA's tiles by the row's slice-0 thread
+  __shared__ double lacc[3][128];          // loss terms per sample row, summed over the CTA's tiles by the row's slice-0 thread
   __shared__ float wred[16][8];
   unsigned char* const ring = fsm;
   unsigned char* const DEL = fsm + 2 * kFzImgBytes;
@@ -171,7 +176,13 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
       sm[sl.W0 + off] = h;
       sm[sl.W0 + 512 + off] = w - h;
     }
-    sm[sl.Wv1 + tid] = __ldg(net.Wv1 + tid);
+    {   // Wv1 [16 x 32], element (k, i) = tid: both orientations as K-major hi / lo planes (no dropout scale: av0 carries it)
+      const int k = tid >> 5, i = tid & 31;
+      const float w = __ldg(net.Wv1 + tid), h = tc::tf32_hi(w);
+      const int of = (i >> 2) * 64 + k * 4 + (i & 3), ot = (k >> 2) * 128 + i * 4 + (k & 3);
+      sm[sl.Wv1f + of] = h; sm[sl.Wv1f + 512 + of] = w - h;
+      sm[sl.Wv1t + ot] = h; sm[sl.Wv1t + 512 + ot] = w - h;
+    }
     if (tid < 64 * L) sm[sl.b[tid >> 6] + (tid & 63)] = __ldg(net.b[tid >> 6] + (tid & 63)) * kTanhArg;
     else if (tid >= 256 && tid < 288) sm[sl.bv0 + tid - 256] = __ldg(net.bv0 + tid - 256) * kTanhArg;
     else if (tid >= 288 && tid < 304) sm[sl.bv1 + tid - 288] = __ldg(net.bv1 + tid - 288) * kTanhArg;
@@ -264,6 +275,25 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
         }
         __syncwarp();
         ++g;
+        if (p == L - 1) {
+          // the variance head's two small layers: av0 (K = 32) x Wv1 -> 16 columns, then dz_v1 (K = 16) x Wv1^T -> 32 columns
+#pragma unroll
+          for (int tp = 0; tp < 2; ++tp) {
+            tc::mbar_wait(&bar_ready, rp);
+            rp ^= 1u;
+            __syncwarp();
+            if (tc::elect_one()) {
+              tc::fence_after_sync();
+              const uint32_t w_u = tc::smem_u32(sm + (tp == 0 ? sl.Wv1f : sl.Wv1t));
+              if (tp == 0) tc::issue_3xtf32_ts<32>(tmem + kColD, tmem + kColAhi, tmem + kColAlo, tc::make_desc(w_u, 256, 128),
+                                                   tc::make_desc(w_u + 2048, 256, 128), 256, tc::make_idesc_tf32(128, 16));
+              else tc::issue_3xtf32_ts<16>(tmem + kColD, tmem + kColAhi, tmem + kColAlo, tc::make_desc(w_u, 512, 128),
+                                           tc::make_desc(w_u + 2048, 512, 128), 512, tc::make_idesc_tf32(128, 32));
+              tc::umma_commit(&bar_chain);
+            }
+            __syncwarp();
+          }
+        }
         if (p >= L) { wgrad_batch(p == L ? 0 : 2 * L - p, false); TLM(tm + 4 * p + 3); }      // staged while the chain product ran
       }
       wgrad_batch(L, true);          // batch 0T
@@ -288,9 +318,8 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
     };
     uint32_t chain_par = 0, wg_par = 0;
     bool wg_pending = false;
-    auto arrive_ready = [&] {
+    auto arrive_ready = [&] {          // the chain operand lives in tensor memory: no shared-memory (async-proxy) fence needed here
       tc::tmem_wait_st();
-      tc::fence_proxy_async();
       tc::fence_before_sync();
       tc::mbar_arrive(&bar_ready);
     };
@@ -338,12 +367,12 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
       return bits;
     };
     const bool no_lv = (net.flags & PINN_NET_NO_LOGVAR) != 0;
-    if (c == 0) { lacc[0][row] = 0.0; lacc[1][row] = 0.0; lacc[2][row] = 0.0; lacc[3][row] = 0.0; }
+    if (c == 0) { lacc[0][row] = 0.0; lacc[1][row] = 0.0; lacc[2][row] = 0.0; }
     float g_wv2[4] = {0.f, 0.f, 0.f, 0.f}, g_bv2 = 0.f;
     // Parking lot (global, 32 KB per slot and CTA, L2-resident: rewritten every tile): the activations of layers 0..L-2
     // and the tail's (av0, v1, dz_v1) wait here between the forward and the backward phase that needs them -- 64 live
     // registers per thread otherwise (the 17th warp caps the kernel at 96).  Slot layout [4][512] float4: coalesced.
-    float4* const park = reinterpret_cast<float4*>(a.park) + static_cast<size_t>(blockIdx.x) * L * 4 * kFzThreads + tid;
+    float4* const park = reinterpret_cast<float4*>(a.park) + static_cast<size_t>(blockIdx.x) * (L + 1) * 4 * kFzThreads + tid;
     auto park_st = [&](int slot, const float (&v)[16]) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) park[(slot * 4 + i) * kFzThreads] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -400,25 +429,26 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
         TLF(tl + 2 + 2 * l);
         wait_chain();
         TLF(tl + 3 + 2 * l);
-        float z[16];
-        tc::tmem_ld16(tD + cb, z);
-        tc::tmem_wait_ld();
         const float* bl = sm + sl.b[l] + cb;
 #pragma unroll
-        for (int g8 = 0; g8 < 16; g8 += 8) {
+        for (int g8 = 0; g8 < 16; g8 += 8) {          // eight columns at a time: half the live registers of a 16-wide pass
+          float z[8];
+          tc::tmem_ld8(tD + cb + g8, z);
+          tc::tmem_wait_ld();
           const float4 bA = *reinterpret_cast<const float4*>(bl + g8), bB = *reinterpret_cast<const float4*>(bl + g8 + 4);
           const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
-          float t8[8];
-          tanh8_prescaled(z + g8, bb, t8);
+          float t8[8], h8[8], l8[8];
+          tanh8_prescaled(z, bb, t8);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acur[g8 + i] = ((kb[l] >> (g8 + i)) & 1u) ? t8[i] : 0.f;
+          for (int i = 0; i < 8; ++i) {
+            acur[g8 + i] = ((kb[l] >> (g8 + i)) & 1u) ? t8[i] : 0.f;
+            h8[i] = tc::tf32_hi_fast(acur[g8 + i]); l8[i] = acur[g8 + i] - h8[i];
+          }
+          tc::tmem_st8(tAh + cb + g8, h8);
+          tc::tmem_st8(tAl + cb + g8, l8);
         }
-        float h[16], lo[16];
-        split16(acur, h, lo);
-        tc::tmem_st16(tAh + cb, h);
-        tc::tmem_st16(tAl + cb, lo);
         arrive_ready();
-        if (l < L - 1) park_st(l, acur);
+        park_st(l < L - 1 ? l : L, acur);          // the last layer's activations sit out the tail in slot L
       }
       // ---- heads (rows 0..31 = Wv0, row 32 = Wp) and the variance head's tail, split over the row's four threads:
       //      thread c owns units 8c..8c+7 of the 32-wide layer and units 4c..4c+3 of the 16-wide layer; three hand-overs
@@ -451,36 +481,35 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
         tc::tmem_wait_ld();
         const float* bv0 = sm + sl.bv0 + 8 * c;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) tailv[i] = ((kbv >> i) & 1u) ? tanh_pre(fmaf(zv[i], kTanhArg, bv0[i])) * wscale : 0.f;
-        tc::tmem_st8(tAh + 8 * c, tailv);
-        qbar();
+        for (int i = 0; i < 8; ++i) {          // activation first, select second: a conditional around the MUFU pair compiles to a divergent branch per unit
+          const float t = tanh_pre(fmaf(zv[i], kTanhArg, bv0[i])) * wscale;
+          tailv[i] = ((kbv >> i) & 1u) ? t : 0.f;
+        }
+        {   // av0 = the A operand (K = 32) of the 32 -> 16 product
+          float h8[8], l8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { h8[i] = tc::tf32_hi_fast(tailv[i]); l8[i] = tailv[i] - h8[i]; }
+#ifdef PINN_TIMELINE
+          asm volatile("" : "+f"(h8[0]), "+f"(h8[7]), "+f"(l8[0]), "+f"(l8[7]));      // values complete before the stamp
+#endif
+          TLF(tl + 30);
+          tc::tmem_st8(tAh + 8 * c, h8);
+          tc::tmem_st8(tAl + 8 * c, l8);
+          TLF(tl + 31);
+        }
+        arrive_ready();
         TLF(tl + 10);
-        const float* Wv1 = sm + sl.Wv1;
-        float2 acc[4][2];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) acc[k][0] = acc[k][1] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {          // the 32 av0 of the row, 16 at a time
-          float v0[16];
-          tc::tmem_ld16(tAh + 16 * hf, v0);
+        wait_chain();
+        TLF(tl + 11);
+        {
+          float z1[4];
+          tc::tmem_ld4(tD + 4 * c, z1);
           tc::tmem_wait_ld();
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float* wr = Wv1 + (4 * c + k) * 32 + 16 * hf;
-#pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) {
-              const float4 w = *reinterpret_cast<const float4*>(wr + 4 * i4);
-              acc[k][0] = ffma2(make_float2(w.x, w.y), make_float2(v0[4 * i4], v0[4 * i4 + 1]), acc[k][0]);
-              acc[k][1] = ffma2(make_float2(w.z, w.w), make_float2(v0[4 * i4 + 2], v0[4 * i4 + 3]), acc[k][1]);
-            }
-          }
+          for (int k = 0; k < 4; ++k) tailv[8 + k] = tanh_pre(fmaf(z1[k], kTanhArg, sm[sl.bv1 + 4 * c + k]));
         }
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tailv[8 + k] = tanh_pre(fmaf((acc[k][0].x + acc[k][0].y) + (acc[k][1].x + acc[k][1].y), kTanhArg, sm[sl.bv1 + 4 * c + k]));
         tc::tmem_st4(tAh + 48 + 4 * c, tailv + 8);
-        TLF(tl + 11);
-        qbar();
+        qbar();                    // the slice-0 thread needs the row's 16 v1
         TLF(tl + 12);
         if (c == 0) {
           float v1a[16], dz[16];
@@ -511,37 +540,30 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
               lacc[0][row] += static_cast<double>(0.5f * e * diff * diff + 0.5f * lv);
               lacc[1][row] += static_cast<double>(fabsf(lv));
               lacc[2][row] += static_cast<double>(diff * diff);
-              lacc[3][row] += 1.0;
             }
           }
           const float sig = big ? 1.0f : __fdividef(ev, 1.0f + ev);
           const float dvv = no_lv ? 0.f : ds * sig * rt;
 #pragma unroll
           for (int k = 0; k < 16; ++k) dz[k] = dvv * sm[sl.Wv2 + k] * (1.0f - v1a[k] * v1a[k]);
-          tc::tmem_st16(tAl + 48, dz);
-          tc::tmem_st1(tD + 56, dvv);          // D columns 48..63 are not touched by the heads product; the next chain product comes after every thread's arrive
+          float h[16], lo[16];
+          split16(dz, h, lo);
+          tc::tmem_st16(tAh, h);                   // dz_v1 = the A operand (K = 16) of the product with Wv1^T
+          tc::tmem_st16(tAl, lo);
+          tc::tmem_st16(tAl + 48, dz);             // and as is, for the row's other threads (they park their four for the 0T batch)
+          tc::tmem_st1(tD + 56, dvv);              // D columns 32.. are not touched by the N = 32 product
         }
+        arrive_ready();
         TLF(tl + 13);
-        qbar();
+        wait_chain();
         TLF(tl + 14);
-        float dzs[16], dv8[8];
-        tc::tmem_ld16(tAl + 48, dzs);
+        float dv8[8];
+        tc::tmem_ld8(tD + 8 * c, dzv0);            // sum_k Wv1[k][i] dz_v1[k] for this thread's eight units
+        tc::tmem_ld4(tAl + 48 + 4 * c, tailv + 12);
         tc::tmem_ld8(tD + 56, dv8);
         tc::tmem_wait_ld();
         const float dv = dv8[0];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) tailv[12 + k] = c == 0 ? dzs[k] : (c == 1 ? dzs[4 + k] : (c == 2 ? dzs[8 + k] : dzs[12 + k]));
-        // d v0[i] = sum_k Wv1[k][i] dz1[k];  dz_v0 = d v0 * keep-mask * scale * (1 - a^2)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dzv0[i] = 0.f;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const float4 wa = *reinterpret_cast<const float4*>(Wv1 + k * 32 + 8 * c), wb = *reinterpret_cast<const float4*>(Wv1 + k * 32 + 8 * c + 4);
-          dzv0[0] = fmaf(wa.x, dzs[k], dzv0[0]); dzv0[1] = fmaf(wa.y, dzs[k], dzv0[1]);
-          dzv0[2] = fmaf(wa.z, dzs[k], dzv0[2]); dzv0[3] = fmaf(wa.w, dzs[k], dzv0[3]);
-          dzv0[4] = fmaf(wb.x, dzs[k], dzv0[4]); dzv0[5] = fmaf(wb.y, dzs[k], dzv0[5]);
-          dzv0[6] = fmaf(wb.z, dzs[k], dzv0[6]); dzv0[7] = fmaf(wb.w, dzs[k], dzv0[7]);
-        }
+        // dz_v0 = d v0 * keep-mask * scale * (1 - a^2)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float av = tailv[i] * (drop_on ? dp.keep : 1.0f);
@@ -573,7 +595,8 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
         arrive_ready();            // the heads^T product runs while batch H is staged
         TLF(tl + 15);
         park_st(L - 1, tailv);
-        wait_wg();                 // the previous tile's 0T batch
+        park_ld(L, acur);          // lands while the previous tile's 0T batch drains the planes
+        wait_wg();
         TLF(tl + 16);
 #pragma unroll
         for (int i = 0; i < 4; ++i) *reinterpret_cast<float*>(act_s + (64 + 4 * c + i) * 16) = (c == 0 && i == 0) ? 1.0f : 0.0f;
@@ -589,8 +612,6 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
       }
 #pragma unroll
       for (int l = L - 1; l >= 0; --l) {
-        float nxt[16];             // l > 0: activations of layer l - 1;  l == 0: the parked tail values
-        park_ld(l > 0 ? l - 1 : L - 1, nxt);          // in flight while the tensor core works
         float x2[2] = {0.f, 0.f};                       // this thread's two input features for the 0T batch
         if (l == 0) {
           if (valid) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(a.x + s * PINN_N_IN) + c); x2[0] = t2.x; x2[1] = t2.y; }
@@ -598,37 +619,37 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
         }
         wait_chain();
         TLF(tl + 18 + 4 * (L - 1 - l));
-        float h[16], lo[16];
-        {
-          float z[16];
-          tc::tmem_ld16(tD + cb, z);
-          tc::tmem_wait_ld();
+        float dz[16];
+        tc::tmem_ld16(tD + cb, dz);
+        tc::tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 16; ++i)     // z already carries the dropout scale (folded into W^T); dropped units have a = 0
-            z[i] = ((kb[l] >> i) & 1u) ? z[i] * fmaf(-acur[i], acur[i], 1.0f) : 0.f;
-          split16(z, h, lo);
-        }
+        for (int i = 0; i < 16; ++i)     // z already carries the dropout scale (folded into W^T); dropped units have a = 0
+          dz[i] = ((kb[l] >> i) & 1u) ? dz[i] * fmaf(-acur[i], acur[i], 1.0f) : 0.f;
+        float nxt[16];             // l > 0: activations of layer l - 1;  l == 0: the parked tail values
         if (l > 0) {
-          tc::tmem_st16(tAh + cb, h);
-          tc::tmem_st16(tAl + cb, lo);
+          {
+            float h[16], lo[16];
+            split16(dz, h, lo);
+            tc::tmem_st16(tAh + cb, h);
+            tc::tmem_st16(tAl + cb, lo);
+          }
           arrive_ready();          // the next chain product runs while this layer's batch is staged
           TLF(tl + 19 + 4 * (L - 1 - l));
+          park_ld(l - 1, nxt);     // lands while the previous batch drains the planes
           wait_wg();
           TLF(tl + 20 + 4 * (L - 1 - l));
 #pragma unroll
-          for (int i = 0; i < 16; ++i) del_st(cb + i, h[i], lo[i]);
+          for (int i = 0; i < 16; ++i) { const float hh = tc::tf32_hi_fast(dz[i]); del_st(cb + i, hh, dz[i] - hh); }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) acur[i] = nxt[i];
-          split16(acur, h, lo);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) act_st(cb + i, h[i], lo[i]);
+          for (int i = 0; i < 16; ++i) { acur[i] = nxt[i]; const float hh = tc::tf32_hi_fast(acur[i]); act_st(cb + i, hh, acur[i] - hh); }
         } else {
           // batch 0T (roles swapped): DEL = [x | av0 | av1 | 1], ACT = [delta_0 | dz_v1]
           TLF(tl + 19 + 4 * (L - 1 - l));
+          park_ld(L - 1, nxt);
           wait_wg();
           TLF(tl + 20 + 4 * (L - 1 - l));
 #pragma unroll
-          for (int i = 0; i < 16; ++i) act_st(cb + i, h[i], lo[i]);
+          for (int i = 0; i < 16; ++i) { const float hh = tc::tf32_hi_fast(dz[i]); act_st(cb + i, hh, dz[i] - hh); }
 #pragma unroll
           for (int i = 0; i < 2; ++i) { const float hh = tc::tf32_hi_fast(x2[i]); del_st(kTX + 2 * c + i, hh, x2[i] - hh); }
 #pragma unroll
@@ -727,7 +748,11 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
         if (lane == 0) wred[warp][k] = w5[k];
       }
       if (c == 0) {
-        double vals[4] = {lacc[0][row], lacc[1][row], lacc[2][row], lacc[3][row]};
+        // the fourth loss sum is the number of valid rows this thread has seen: its row of every tile of the CTA
+        double cnt = 0.0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) cnt += (tile * 128 + row < a.n) ? 1.0 : 0.0;
+        if (a.grad_u != nullptr) cnt = 0.0;
+        double vals[4] = {lacc[0][row], lacc[1][row], lacc[2][row], cnt};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           double t = vals[k];
@@ -770,7 +795,7 @@ static FzPlan plan_fused(int L, int64_t n) {
   p.off_images = off;
   off += static_cast<size_t>(2 * L) * kFzImgBytes;
   p.off_park = off;
-  off += static_cast<size_t>(p.grid) * L * 4 * kFzThreads * sizeof(float4);
+  off += static_cast<size_t>(p.grid) * (L + 1) * 4 * kFzThreads * sizeof(float4);
   p.bytes = off;
   return p;
 }

@@ -27,17 +27,18 @@ else:
     assert lib.pinn_debug_timeline_fused(buf) == 0
     t = np.array(buf, dtype=np.int64).reshape(2, 8, 32)
     names = {0: "tile start", 1: "x parked / ready", 2: "kb0 drawn", 3: "chain L0 done", 4: "kb1 drawn", 5: "chain F1 done", 6: "kb2 drawn",
-             7: "chain F2 done", 8: "kbv drawn", 9: "chain FH done", 10: "qbar1", 11: "v1 done", 12: "qbar2", 13: "scalar part done",
-             14: "qbar3", 15: "heads^T operand ready", 16: "wg(0T) waited", 17: "batch H staged", 18: "chain BH done", 19: "dz2 / ready",
+             7: "chain F2 done", 8: "kbv drawn", 9: "chain FH done", 10: "av0 parked / ready", 11: "32->16 product done", 12: "v1 handed over", 13: "scalar part / ready",
+             14: "16->32 product done", 15: "heads^T operand ready", 16: "wg(0T) waited", 17: "batch H staged", 18: "chain BH done", 19: "dz2 / ready",
              20: "wg(H) waited", 21: "batch 2 staged", 22: "chain B2 done", 23: "dz1 / ready", 24: "wg(2) waited", 25: "batch 1 staged",
-             26: "chain B1 done", 27: "dz0 done", 28: "wg(1) waited", 29: "batch 0T staged"}
+             26: "chain B1 done", 27: "dz0 done", 28: "wg(1) waited", 29: "batch 0T staged",
+             30: "(av0 computed)", 31: "(av0 stores issued)"}
     for tile in (1, 2):
         base = t[0, tile, 0]
         if base == 0:
             continue
         print(f"--- n={n} tile #{tile} of CTA 0, compute thread 0 (clk since tile start; delta)")
         prev = base
-        for i in range(30):
+        for i in list(range(10)) + [30, 31] + list(range(10, 30)):
             v = t[0, tile, i]
             if v:
                 print(f"  {names.get(i, i):>18}: {v - base:7d}  (+{v - prev})")
