@@ -430,6 +430,10 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
         wait_chain();
         TLF(tl + 3 + 2 * l);
         const float* bl = sm + sl.b[l] + cb;
+        // an opaque copy of the keep bits: otherwise the compiler extracts all 16 bit tests ahead of the wait, keeps them for the
+        // backward phase that tests the same bits, and spills every one of them (16 STL + 16 LDL per layer and tile)
+        uint32_t kbf = kb[l];
+        asm volatile("" : "+r"(kbf));
 #pragma unroll
         for (int g8 = 0; g8 < 16; g8 += 8) {          // eight columns at a time: half the live registers of a 16-wide pass
           float z[8];
@@ -441,7 +445,7 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
           tanh8_prescaled(z, bb, t8);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            acur[g8 + i] = ((kb[l] >> (g8 + i)) & 1u) ? t8[i] : 0.f;
+            acur[g8 + i] = ((kbf >> (g8 + i)) & 1u) ? t8[i] : 0.f;
             h8[i] = tc::tf32_hi_fast(acur[g8 + i]); l8[i] = acur[g8 + i] - h8[i];
           }
           tc::tmem_st8(tAh + cb + g8, h8);
@@ -480,10 +484,12 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
         tc::tmem_ld8(tD + 32, zu);
         tc::tmem_wait_ld();
         const float* bv0 = sm + sl.bv0 + 8 * c;
+        uint32_t kbv1 = kbv;
+        asm volatile("" : "+r"(kbv1));
 #pragma unroll
         for (int i = 0; i < 8; ++i) {          // activation first, select second: a conditional around the MUFU pair compiles to a divergent branch per unit
           const float t = tanh_pre(fmaf(zv[i], kTanhArg, bv0[i])) * wscale;
-          tailv[i] = ((kbv >> i) & 1u) ? t : 0.f;
+          tailv[i] = ((kbv1 >> i) & 1u) ? t : 0.f;
         }
         {   // av0 = the A operand (K = 32) of the 32 -> 16 product
           float h8[8], l8[8];
@@ -622,9 +628,11 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
         float dz[16];
         tc::tmem_ld16(tD + cb, dz);
         tc::tmem_wait_ld();
+        uint32_t kbb = kb[l];
+        asm volatile("" : "+r"(kbb));      // see the forward pass
 #pragma unroll
         for (int i = 0; i < 16; ++i)     // z already carries the dropout scale (folded into W^T); dropped units have a = 0
-          dz[i] = ((kb[l] >> i) & 1u) ? dz[i] * fmaf(-acur[i], acur[i], 1.0f) : 0.f;
+          dz[i] = ((kbb >> i) & 1u) ? dz[i] * fmaf(-acur[i], acur[i], 1.0f) : 0.f;
         float nxt[16];             // l > 0: activations of layer l - 1;  l == 0: the parked tail values
         if (l > 0) {
           {
