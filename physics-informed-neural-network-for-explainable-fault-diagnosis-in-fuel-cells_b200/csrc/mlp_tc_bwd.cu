@@ -1062,14 +1062,12 @@ bool tc_bwd_covers(const pinn_net_t* net) {
     if (!aligned16(net->W[l])) return false;
   return aligned16(net->Wv0) && aligned16(net->Wp);
 }
-// One-kernel form unless the caller opts out -- or the batch is between one and 1.6 tiles per SM: there a few CTAs of the
-// one-kernel form run two tiles back to back (2 x 17 us) while the two-kernel form interleaves a tile pair on one SM
-// (N = 20 000, 157 tiles: 59 vs 55 us per step; from 1.6 tiles per SM up, and up to one, the one-kernel form wins:
-// profiles/ab_fused.py)
+// One-kernel form unless the caller opts out.  (A first version lost to the two-kernel form between one and 1.6 tiles per SM,
+// where a few CTAs run two tiles back to back; since the tile got down to ~14 us it wins at every batch size:
+// N = 20 000, 157 tiles: 51 vs 56 us per step, profiles/c1_train_dnn_launches.py.)
 bool tc_bwd_fused(int L, int flags, int64_t n) {
-  if (!(L == 2 || L == 3) || (flags & PINN_NET_NO_FUSED_BWD)) return false;
-  const int64_t tiles = (n + kBTile - 1) / kBTile, sms = sm_count();
-  return !(tiles > sms && 10 * tiles <= 16 * sms);
+  (void)n;
+  return (L == 2 || L == 3) && !(flags & PINN_NET_NO_FUSED_BWD);
 }
 size_t tc_bwd_workspace_bytes(int L, int64_t n, int flags) {
   if (flags >= 0 && tc_bwd_fused(L, flags, n)) return plan_fused(L, n).bytes;
