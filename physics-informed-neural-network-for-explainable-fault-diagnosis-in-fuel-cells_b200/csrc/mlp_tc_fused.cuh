@@ -139,7 +139,8 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
   static_assert(L == 2 || L == 3, "tensor memory holds L + 1 <= 4 accumulator blocks");
   constexpr int H = 64;
   extern __shared__ __align__(1024) unsigned char fsm[];
-  __shared__ __align__(8) uint64_t bar_ready, bar_stage, bar_chain, bar_wg, bar_full[2];
+  __shared__ __align__(8) uint64_t bar_ready, bar_chain, bar_full[2];
+  __shared__ __align__(8) uint64_t bar_stage[4], bar_wg[4];      // per lane quadrant = per 32-sample quarter of the staging planes
   __shared__ uint32_t tmem_base_s;
   __shared__ double lred[4][4];
   __shared__ double lacc[3][128];          // loss terms per sample row, summed over the CTA's tiles by the row's slice-0 thread
@@ -153,7 +154,8 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
   griddep_launch();
 
   if (tid == 0) {
-    tc::mbar_init(&bar_ready, kFzThreads); tc::mbar_init(&bar_stage, kFzThreads); tc::mbar_init(&bar_chain, 1); tc::mbar_init(&bar_wg, 1);
+    tc::mbar_init(&bar_ready, kFzThreads); tc::mbar_init(&bar_chain, 1);
+    for (int i = 0; i < 4; ++i) { tc::mbar_init(&bar_stage[i], kFzThreads / 4); tc::mbar_init(&bar_wg[i], 1); }
     tc::mbar_init(&bar_full[0], 1); tc::mbar_init(&bar_full[1], 1);
     tc::fence_mbar_init();
   }
@@ -210,26 +212,32 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
     bool first = true;
     int tm = 0;
     (void)tm;
-    // weight-gradient batch of the operands the compute warps have just staged (they arrive on bar_stage)
+    // Weight-gradient batch of the operands the compute warps have just staged.  The planes are handed over and handed back
+    // by QUARTERS: lane quadrant q owns samples 32q..32q+31 = K slabs 4q..4q+3; it arrives on bar_stage[q] when its quarter
+    // is written, and bar_wg[q] tells it when the tensor core has read that quarter -- so staging of the next batch and the
+    // products of this one overlap slab by slab (both are bound by the same shared-memory port) instead of taking turns.
     auto wgrad_batch = [&](int acc, bool wide_lo) {
-      tc::mbar_wait(&bar_stage, sp);
-      sp ^= 1u;
-      __syncwarp();
-      if (tc::elect_one()) {
-        tc::fence_after_sync();
-        const uint32_t d = tmem + kColAcc + kAccW * static_cast<uint32_t>(acc);
-        const uint64_t a0 = tc::make_desc(del_u, kDelLbo, 128);
-        const uint64_t bh0 = tc::make_desc(act_u, kActLbo, 128), bl0 = tc::make_desc(act_u + kActLo * 16, kActLbo, 128);
-        const uint32_t id_lo = wide_lo ? idesc80 : idesc64;
-        constexpr uint64_t as = (2u * kDelLbo) >> 4, bs = (2u * kActLbo) >> 4;
+      const uint32_t d = tmem + kColAcc + kAccW * static_cast<uint32_t>(acc);
+      const uint64_t a0 = tc::make_desc(del_u, kDelLbo, 128);
+      const uint64_t bh0 = tc::make_desc(act_u, kActLbo, 128), bl0 = tc::make_desc(act_u + kActLo * 16, kActLbo, 128);
+      const uint32_t id_lo = wide_lo ? idesc80 : idesc64;
+      constexpr uint64_t as = (2u * kDelLbo) >> 4, bs = (2u * kActLbo) >> 4;
 #pragma unroll
-        for (int ks = 0; ks < 16; ++ks) {
-          tc::umma_tf32(d, a0 + ks * as, bh0 + ks * bs, idesc80, (ks != 0 || !first) ? 1u : 0u);
-          tc::umma_tf32(d, a0 + ks * as, bl0 + ks * bs, id_lo, 1u);
+      for (int qq = 0; qq < 4; ++qq) {
+        tc::mbar_wait(&bar_stage[qq], sp);
+        __syncwarp();
+        if (tc::elect_one()) {
+          tc::fence_after_sync();
+#pragma unroll
+          for (int ks = 4 * qq; ks < 4 * qq + 4; ++ks) {
+            tc::umma_tf32(d, a0 + ks * as, bh0 + ks * bs, idesc80, (ks != 0 || !first) ? 1u : 0u);
+            tc::umma_tf32(d, a0 + ks * as, bl0 + ks * bs, id_lo, 1u);
+          }
+          tc::umma_commit(&bar_wg[qq]);
         }
-        tc::umma_commit(&bar_wg);
+        __syncwarp();
       }
-      __syncwarp();
+      sp ^= 1u;
     };
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const bool has_next = tile + gridDim.x < n_tiles;
@@ -294,6 +302,8 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
             __syncwarp();
           }
         }
+        // (Tried: issuing a batch in two halves around the next chain product so that the product does not queue behind a whole
+        // batch -- 0.78 -> 0.83 ms: the later release of the second half's quarters costs more than the chain product gains.)
         if (p >= L) { wgrad_batch(p == L ? 0 : 2 * L - p, false); TLM(tm + 4 * p + 3); }      // staged while the chain product ran
       }
       wgrad_batch(L, true);          // batch 0T
@@ -325,7 +335,7 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
     };
     auto arrive_stage = [&] {          // staging planes written: the weight-gradient batch may run
       tc::fence_proxy_async();
-      tc::mbar_arrive(&bar_stage);
+      tc::mbar_arrive(&bar_stage[q]);
       wg_pending = true;
     };
     auto wait_chain = [&] {
@@ -335,7 +345,7 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
       tc::fence_after_sync();
     };
     auto wait_wg = [&] {          // the batch that reads the staging planes has drained them
-      if (wg_pending) { tc::mbar_wait(&bar_wg, wg_par); wg_par ^= 1u; wg_pending = false; }
+      if (wg_pending) { tc::mbar_wait(&bar_wg[q], wg_par); wg_par ^= 1u; wg_pending = false; }
       __syncwarp();
     };
     auto qbar = [&] {             // the four warps of a lane quadrant (the four column slices of 32 sample rows)
@@ -677,7 +687,8 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
     // ---------------------------------------------------------------- accumulators -> this CTA's partial vector
     // Lanes j and 64 + j hold the hi and the lo part of the same sum: the lo half of the CTA (quadrants 2, 3) parks its
     // values in the idle staging plane, the hi half adds them and writes the vector out.
-    wait_wg();
+    if (wg_pending) tc::mbar_wait(&bar_wg[3], wg_par);      // the LAST quarter of the last batch: every product has completed
+    __syncwarp();
     tc::fence_after_sync();
     {
       float* const part = a.partial + static_cast<size_t>(blockIdx.x) * pl.total;
