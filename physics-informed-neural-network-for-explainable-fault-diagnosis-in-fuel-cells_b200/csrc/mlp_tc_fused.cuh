@@ -207,6 +207,8 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
     if (tc::elect_one()) {
       tc::mbar_expect_tx(&bar_full[0], kFzImgBytes);
       tc::bulk_g2s(ring, a.images, kFzImgBytes, &bar_full[0]);
+      tc::mbar_expect_tx(&bar_full[1], kFzImgBytes);
+      tc::bulk_g2s(ring + kFzImgBytes, a.images + kFzImgBytes, kFzImgBytes, &bar_full[1]);
     }
     __syncwarp();
     bool first = true;
@@ -262,15 +264,10 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
         if (tc::elect_one()) {
           tc::fence_after_sync();
           TLM(tm + 4 * p);
-          // the other slot's last reader (the product before this one) has completed: the compute warps saw its commit
-          const int nxt = p + 1 < 2 * L ? p + 1 : (has_next ? 0 : -1);
-          if (nxt >= 0) {
-            const uint32_t s2 = (g + 1) & 1u;
-            tc::mbar_expect_tx(&bar_full[s2], kFzImgBytes);
-            tc::bulk_g2s(ring + s2 * kFzImgBytes, a.images + static_cast<size_t>(nxt) * kFzImgBytes, kFzImgBytes, &bar_full[s2]);
-          }
+          // (the image was requested two products ago by compute thread 0, see wait_chain_ring)
           const uint32_t s1 = g & 1u;
-          tc::mbar_wait(&bar_full[s1], (fpar >> s1) & 1u);
+          tc::mbar_wait(&bar_full[s1], (fpar >> s1) & 1u);      // still ~450 clk late in the timelines (a spin instead of the
+                                                                // suspending wait changes nothing): L2 carries ~4.7 TB/s of images + parking lot
           fpar ^= 1u << s1;
           TLM(tm + 4 * p + 1);
           const uint64_t bh = tc::make_desc(ring_u + s1 * kFzImgBytes, kFzImgLbo, 128);
@@ -344,6 +341,20 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
       __syncwarp();
       tc::fence_after_sync();
     };
+    // A chain product that read ring slot `img & 1` has completed: compute thread 0 -- the first to know -- requests the image
+    // after next into that slot (one bulk copy, 32 KB).  Requested by the MMA warp one product ahead, the copy left that warp
+    // waiting ~600 clk at every chain product: all 148 SMs pull the same image out of L2 at about the same time.
+    auto wait_chain_ring = [&](int img, bool has_next) {
+      wait_chain();
+      if (tid == 0) {
+        const int nxt = img + 2 < 2 * L ? img + 2 : (has_next ? img + 2 - 2 * L : -1);
+        if (nxt >= 0) {
+          tc::mbar_expect_tx(&bar_full[img & 1], kFzImgBytes);
+          tc::bulk_g2s(ring + (img & 1) * kFzImgBytes, a.images + static_cast<size_t>(nxt) * kFzImgBytes, kFzImgBytes, &bar_full[img & 1]);
+        }
+      }
+      __syncwarp();
+    };
     auto wait_wg = [&] {          // the batch that reads the staging planes has drained them
       if (wg_pending) { tc::mbar_wait(&bar_wg[q], wg_par); wg_par ^= 1u; wg_pending = false; }
       __syncwarp();
@@ -411,7 +422,7 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
     load_x(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t s = tile * 128 + row;
-      const bool valid = s < a.n;
+      const bool valid = s < a.n, has_next = tile + gridDim.x < n_tiles;
       const bool active = drop_on && (!INJ || valid);       // injected masks: tail rows of the last tile have no mask row
       const uint64_t sg = static_cast<uint64_t>(dp.sample_offset + s);
       KeepSrc<INJ> ks;
@@ -437,7 +448,7 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
       for (int l = 0; l < L; ++l) {
         kb[l] = keep16(ks, active, static_cast<uint32_t>(l));        // drawn while the tensor core works
         TLF(tl + 2 + 2 * l);
-        wait_chain();
+        if (l == 0) wait_chain(); else wait_chain_ring(l - 1, has_next);
         TLF(tl + 3 + 2 * l);
         const float* bl = sm + sl.b[l] + cb;
         // an opaque copy of the keep bits: otherwise the compiler extracts all 16 bit tests ahead of the wait, keeps them for the
@@ -484,7 +495,7 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
         else y_pre = __ldg(a.y + s);
       }
       TLF(tl + 8);
-      wait_chain();
+      wait_chain_ring(L - 1, has_next);
       TLF(tl + 9);
       float dzv0[8], du = 0.f;
       {
@@ -633,7 +644,7 @@ mlp_tc_fused_kernel(pinn_net_t net, FzSmall sl, const __grid_constant__ DropPara
           if (valid) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(a.x + s * PINN_N_IN) + c); x2[0] = t2.x; x2[1] = t2.y; }
           load_x(tile + gridDim.x);                     // the next tile's input row
         }
-        wait_chain();
+        wait_chain_ring(2 * L - 1 - l, has_next);
         TLF(tl + 18 + 4 * (L - 1 - l));
         float dz[16];
         tc::tmem_ld16(tD + cb, dz);
