@@ -96,7 +96,7 @@ PINN_D void bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r
 //  * biases (and layer 0's weights) are pre-scaled by 2 log2(e): tanh = FFMA, EX2, FADD, RCP, FFMA;
 //  * Philox round keys are constant-bank operands, 16-bit draws are compared in place;
 //  * the tf32 split of an activation is IADD + LOP3 + FADD.
-template <bool MC, bool INJ>
+template <bool MC, bool INJ, bool CH>      // CH: the sweep is cut into pass chunks (long sweeps only; C = 1 folds away otherwise)
 __global__ void __launch_bounds__(kTcThreads, 1)
 mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t n, int T, const __grid_constant__ DropParams dp,
               TcOut out, int chunks, float* __restrict__ part) {
@@ -158,7 +158,7 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
   // alone, so the arithmetic of a sample does not depend on the batch or its sharding); every run keeps its own Welford
   // triple, mc_merge_kernel folds them in chunk order (Chan).  With few tiles per SM this is what fills the machine:
   // 977 tiles x T = 1000 are 3.3 waves of whole-tile items but 13.2 waves of quarter-sweeps.
-  const int C = MC ? chunks : 1, Tc = (T + C - 1) / C;
+  const int C = (MC && CH) ? chunks : 1, Tc = (T + C - 1) / C;
   auto item_passes = [&](int chunk) {            // dropout passes of the chunk (+ the eval pass, which rides with chunk 0)
     const int t0 = chunk * Tc, cnt = (T - t0 < Tc ? T - t0 : Tc);
     return MC ? (cnt > 0 ? cnt : 0) + ((do_eval && chunk == 0) ? 1 : 0) : 1;
@@ -542,8 +542,9 @@ int launch_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, 
   };
   if (C > 1 && (workspace == nullptr || workspace_bytes < static_cast<size_t>(C) * 3 * n * sizeof(float))) { *err = PINN_E_WORKSPACE; return -1; }
   cudaError_t e;
-  if (mc) e = inj ? go(mlp_tc_kernel<true, true>) : go(mlp_tc_kernel<true, false>);
-  else e = inj ? go(mlp_tc_kernel<false, true>) : go(mlp_tc_kernel<false, false>);
+  if (mc && C > 1) e = inj ? go(mlp_tc_kernel<true, true, true>) : go(mlp_tc_kernel<true, false, true>);
+  else if (mc) e = inj ? go(mlp_tc_kernel<true, true, false>) : go(mlp_tc_kernel<true, false, false>);
+  else e = inj ? go(mlp_tc_kernel<false, true, false>) : go(mlp_tc_kernel<false, false, false>);
   if (e != cudaSuccess) { *err = static_cast<int>(e); return -1; }
   if (C > 1) mc_merge_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(static_cast<const float*>(workspace), n, T, C, out);
   *err = static_cast<int>(cudaGetLastError());
