@@ -60,8 +60,10 @@ enum { /* pinn_net_t.flags */
   PINN_NET_PDL_ALWAYS = 16, /* always chain them (default: only for batches of up to two tiles per SM)           */
   PINN_NET_NO_LOGVAR = 32,  /* DNN(logvar=False), 01:436: the log-variance output is identically 0, the variance
                                head receives no gradient and the aleatoric loss reduces to 0.5 * MSE             */
-  PINN_NET_NO_FUSED_BWD = 64 /* ablation / tests: 64-wide backward as the two-kernel form (K2a + row table + K2b)
+  PINN_NET_NO_FUSED_BWD = 64, /* ablation / tests: 64-wide backward as the two-kernel form (K2a + row table + K2b)
                                instead of the one-kernel form with on-chip weight gradients                      */
+  PINN_NET_NO_WIDE_RESIDENT = 128 /* ablation / tests: 256-wide forward / MC sweep as one GEMM launch per layer
+                               (activation planes in HBM) instead of the resident-activation kernel             */
 };
 
 /* Dropout control.  p == 0 means eval mode.  With masks == NULL the keep mask of

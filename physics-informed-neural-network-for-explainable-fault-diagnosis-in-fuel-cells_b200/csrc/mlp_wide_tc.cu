@@ -742,6 +742,8 @@ int launch_wide_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, in
   *err = 0;
   if ((net->flags & PINN_NET_NO_WIDE_TC) || (net->width != 256 && net->width != 128) || net->n_hidden < 1) return 0;
   if (mc && T <= 0) return 0;
+  // 256-wide nets: the resident-activation kernel (mlp_wide_res.cu) unless the call opts out or the shape is not covered
+  if (const int rr = launch_wide_res(mc, net, x, n, T, dp, out, workspace, workspace_bytes, st, err); rr != 0) return rr;
   for (int l = 1; l < net->n_hidden; ++l)
     if (!aligned16(net->W[l])) return 0;
   if (!aligned16(net->Wv0) || !aligned16(net->Wp) || !aligned16(net->Wv1)) return 0;

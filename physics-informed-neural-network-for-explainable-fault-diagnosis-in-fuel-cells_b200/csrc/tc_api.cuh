@@ -17,6 +17,10 @@ size_t tc_mc_workspace_bytes(int64_t n);
 size_t wide_tc_workspace_bytes(int H, int L, int64_t n);
 int launch_wide_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, const DropParams& dp, const TcOut& out,
                    void* workspace, size_t workspace_bytes, cudaStream_t st, int* err);
+// 256-wide nets, forward / MC sweep with the activations resident on the SM (mlp_wide_res.cu); same return convention.
+size_t wide_res_workspace_bytes(int L, int64_t n);
+int launch_wide_res(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, const DropParams& dp, const TcOut& out,
+                    void* workspace, size_t workspace_bytes, cudaStream_t st, int* err);
 bool wide_tc_bwd_covers(const pinn_net_t* net);
 size_t wide_tc_bwd_workspace_bytes(int H, int L, int64_t n);
 int launch_wide_tc_bwd(const pinn_net_t* net, const float* x, int64_t n, const DropParams& dp, const float* grad_u, const float* grad_s,
