@@ -519,6 +519,10 @@ int mc_pass_chunks(int T) {
 }
 size_t tc_mc_workspace_bytes(int64_t n) { return static_cast<size_t>(8) * 3 * static_cast<size_t>(n > 0 ? n : 0) * sizeof(float); }
 
+void launch_mc_merge(const float* part, int64_t n, int T, int C, const TcOut& out, cudaStream_t st) {
+  mc_merge_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(part, n, T, C, out);
+}
+
 int launch_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, const DropParams& dp, const TcOut& out,
               cudaStream_t st, int* err, void* workspace, size_t workspace_bytes) {
   *err = 0;

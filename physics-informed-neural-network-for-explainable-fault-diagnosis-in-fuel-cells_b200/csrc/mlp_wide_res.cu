@@ -38,12 +38,35 @@ constexpr int kRH = 256;                    // width
 constexpr int kRT = 128;                    // rows per tile
 constexpr int kRComputeWarps = 16;
 constexpr int kRThreads = (kRComputeWarps + 2) * 32;   // + producer warp + MMA warp
-constexpr int kRStages = 5;
+#ifndef RES_STAGES
+#define RES_STAGES 5
+#endif
+constexpr int kRStages = RES_STAGES;
 constexpr int kRStageBytes = 64 * kRH;      // one K = 16 slab of a 256-row matrix: [hi 8 KB | lo 8 KB]
 constexpr int kRPlane = kRT * kRH * 2;      // one fp16 plane of a tile's activations (64 KB)
 constexpr int kRSlabA = kRT * 32;           // bytes of one K = 16 slab of one A plane (4 KB)
 constexpr int kRNH = kRH / 2 + 16;          // heads product: 128 variance-head rows + mean row + 15 zero rows
 constexpr int kRNV = kRH / 4;               // variance layer 1: 64 rows
+// A/B switches of the epilogue (profiles/build_variant.py -DRES_...=0/1; measured numbers in DESIGN.md)
+#ifndef RES_PREDRAW
+#define RES_PREDRAW 0      // draw a phase's Philox blocks ahead of the wait that precedes its epilogue
+#endif
+#ifndef RES_UNROLLJ
+#define RES_UNROLLJ 1      // unroll the four 16-column groups of a hidden epilogue
+#endif
+#ifndef RES_WARP_ARRIVE
+#define RES_WARP_ARRIVE 1  // one mbarrier arrival per warp and K slab (after __syncwarp) instead of one per thread
+#endif
+#ifndef RES_LDPF
+#define RES_LDPF 1         // tcgen05.ld of the next 16 columns in flight while the current 16 are processed
+#endif
+constexpr bool kPredraw = RES_PREDRAW != 0, kLdPrefetch = RES_LDPF != 0 && RES_UNROLLJ != 0;
+#if RES_UNROLLJ
+#define RES_J_UNROLL _Pragma("unroll")
+#else
+#define RES_J_UNROLL _Pragma("unroll 1")
+#endif
+static_assert(!kPredraw || RES_UNROLLJ, "pre-drawn blocks are indexed by the group: needs the unrolled form");
 
 PINN_HD constexpr int res_slab_bytes(int N) { return 64 * N; }                              // [hi | lo] of one slab
 PINN_HD constexpr size_t res_img_bytes(int N, int K) { return static_cast<size_t>(K / 16) * res_slab_bytes(N); }
@@ -60,12 +83,21 @@ static ResPlan res_plan(int L, int64_t n) {
   p.off_wh = take(res_img_bytes(kRNH, kRH));
   p.off_wv1 = take(res_img_bytes(kRNV, kRH / 2));
   const int64_t tiles = (n + kRT - 1) / kRT;
-  p.grid = static_cast<int>(tiles < sm_count() ? (tiles > 0 ? tiles : 1) : sm_count());
+  const int64_t items = tiles * 8;                 // up to 8 pass chunks per tile
+  p.grid = static_cast<int>(items < sm_count() ? (items > 0 ? items : 1) : sm_count());
   p.off_a0 = take(static_cast<size_t>(p.grid) * kRT * kRH * sizeof(float));
   p.bytes = o;
   return p;
 }
-size_t wide_res_workspace_bytes(int L, int64_t n) { return n > 0 ? res_plan(L, n).bytes : 0; }
+// Pass chunks of a sweep on this path: runs of ~12 passes (a pass of a tile is ~20 us; the per-item overhead is one layer-0
+// evaluation), at most 8 -- a function of T ALONE (bitwise shard invariance, as in mlp_tc.cu).
+int res_pass_chunks(int T) {
+  const int c = (T + 6) / 12;
+  return c < 1 ? 1 : (c > 8 ? 8 : c);
+}
+size_t wide_res_workspace_bytes(int L, int64_t n) {
+  return n > 0 ? res_plan(L, n).bytes + static_cast<size_t>(8) * 3 * static_cast<size_t>(n) * sizeof(float) : 0;
+}
 
 // two fp32 -> packed fp16 pair (hi) and the packed fp16 pair of the remainders (lo)
 PINN_D void split_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
@@ -120,6 +152,8 @@ struct ResArgs {
   const unsigned char* img_v1;                   // variance layer 1
   float* a0;                                     // [grid][64 column quads][128 rows][4]
   int L, T, mc, do_eval;
+  int chunks;                                    // pass chunks per tile (a function of T alone), work item = (tile, chunk)
+  float* part;                                   // chunks > 1: per-chunk Welford triples [chunk][3][n], folded by mc_merge
   float inact;                                   // multiplier of an un-masked activation (undoes the folded scale)
   int no_logvar;
 };
@@ -147,7 +181,7 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
   const int tid = threadIdx.x, warp = tc::uniform_warp_idx(), lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < kRStages; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
-    for (int c = 0; c < 16; ++c) tc::mbar_init(&ready[c], 128);
+    for (int c = 0; c < 16; ++c) tc::mbar_init(&ready[c], RES_WARP_ARRIVE ? 4 : 128);
     tc::mbar_init(&done, 1);
     tc::fence_mbar_init();
   }
@@ -163,7 +197,17 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
   const uint32_t tb = tmem_base_s;
 
   const int64_t n_tiles = (n + kRT - 1) / kRT;
-  const int n_pass = a.mc ? a.T + (a.do_eval ? 1 : 0) : 1;
+  // Work item = (tile, pass chunk): a sweep is cut into `chunks` runs of Tc consecutive passes (chosen from T alone, so a
+  // sample's arithmetic does not depend on the batch or its sharding); every run keeps its own Welford triple and the
+  // merge launch folds them in chunk order.  At the reference's own size (N = 20 000: 157 tiles on 148 SMs) this is what
+  // fills the machine.
+  const int C = a.chunks, Tc = (a.T + C - 1) / C;
+  const int64_t n_items = n_tiles * C;
+  auto item_passes = [&](int chunk) {            // dropout passes of the chunk (+ the eval pass, which rides with chunk 0)
+    if (!a.mc) return 1;
+    const int t0 = chunk * Tc, cnt = a.T - t0 < Tc ? a.T - t0 : Tc;
+    return (cnt > 0 ? cnt : 0) + ((a.do_eval && chunk == 0) ? 1 : 0);
+  };
   const int n_phase = L + 1;                                   // MMA phases per pass: L-1 hidden, heads, variance layer 1
   // phase ph of a pass: image, rows N, K slabs, slabs per producing quarter
   auto phase_img = [&](int ph) { return ph < L - 1 ? a.img_w[ph + 1] : (ph == L - 1 ? a.img_h : a.img_v1); };
@@ -174,8 +218,8 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
     // ================================================================== producer: weight slabs into the ring
     if (tc::elect_one()) {
       uint32_t cnt = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-        for (int pi = 0; pi < n_pass; ++pi)
+      for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x)
+        for (int pi = 0, n_pass = item_passes(static_cast<int>(item % C)); pi < n_pass; ++pi)
           for (int ph = 0; ph < n_phase; ++ph) {
             const unsigned char* img = phase_img(ph);
             const int N = phase_N(ph), ns = phase_slabs(ph), spq = ns / 4;
@@ -193,8 +237,8 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
     // ================================================================== MMA issuer
     uint32_t cnt = 0, rpar = 0u, acc_sel = 0u;
     const uint32_t a_hi_s = tc::smem_u32(smem), a_lo_s = a_hi_s + kRPlane, ring_s = tc::smem_u32(ring);
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-      for (int pi = 0; pi < n_pass; ++pi)
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x)
+      for (int pi = 0, n_pass = item_passes(static_cast<int>(item % C)); pi < n_pass; ++pi)
         for (int ph = 0; ph < n_phase; ++ph, acc_sel ^= 1u) {
           const int N = phase_N(ph), ns = phase_slabs(ph), spq = ns / 4;
           const uint32_t idesc = make_idesc_f16(kRT, N), d_t = tb + acc_sel * 256u;
@@ -224,7 +268,7 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
   } else {
     // ================================================================== compute warps: thread = (row, column quarter)
     const int q = warp >> 2, r = (warp & 3) * 32 + lane;
-    const uint32_t tl = tb + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const uint32_t tlane = tb + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     unsigned char* const my_a = smem + r * 16;
     float* const my_a0 = a.a0 + static_cast<size_t>(blockIdx.x) * kRT * kRH + static_cast<size_t>(r) * 4;
     const bool drop_on = dp.p > 0.f, inj = dp.masks != nullptr;
@@ -244,7 +288,12 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
       *reinterpret_cast<uint4*>(p + kRPlane) = l0;
       *reinterpret_cast<uint4*>(p + kRPlane + kRT * 16) = l1;
       tc::fence_proxy_async();
+#if RES_WARP_ARRIVE
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&ready[slab]);
+#else
       tc::mbar_arrive(&ready[slab]);
+#endif
     };
     auto wait_done = [&]() {
       tc::mbar_wait(&done, dpar);
@@ -253,13 +302,17 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
       tc::fence_after_sync();
     };
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int64_t tile = item / C;
+      const int chunk = static_cast<int>(item % C), t0 = chunk * Tc, n_pass = item_passes(chunk);
+      const bool eval_item = a.do_eval && chunk == 0;
+      if (n_pass == 0) continue;
       const int64_t s = tile * kRT + r;
       const bool valid = s < n;
       const uint64_t sg = static_cast<uint64_t>(dp.sample_offset + s);
       const uint32_t s_lo = static_cast<uint32_t>(sg), s_hi = static_cast<uint32_t>(sg >> 32);
       // keep-select 16 activations of units [j0, j0 + 16) of dropout layer `layer`
-      auto select16 = [&](float (&v)[16], bool active, uint32_t pass, int tloc, uint32_t layer, uint32_t j0) {
+      auto select16 = [&](float (&v)[16], bool active, const uint4& r0, const uint4& r1, uint32_t pass, int tloc, uint32_t layer, uint32_t j0) {
         if (active) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
@@ -270,8 +323,8 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
 #pragma unroll
               for (int e = 0; e < 4; ++e) { k[e] = ((mb.x >> (8 * e)) & 0xffu) != 0; k[4 + e] = ((mb.y >> (8 * e)) & 0xffu) != 0; }
             } else {
-              const uint4 rr = Philox::gen_rk(dp.rk, s_lo, s_hi, pass, (layer << 16) | ((j0 >> 3) + g));
-              keep8_from(rr, dp.thresh_hi, k);
+              if constexpr (kPredraw) keep8_from(g == 0 ? r0 : r1, dp.thresh_hi, k);
+              else keep8_from(Philox::gen_rk(dp.rk, s_lo, s_hi, pass, (layer << 16) | ((j0 >> 3) + g)), dp.thresh_hi, k);
             }
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[8 * g + e] = k[e] ? v[8 * g + e] : 0.f;
@@ -310,11 +363,27 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
         }
       }
 
+      // Philox blocks of the coming epilogue are drawn AHEAD of the wait that precedes it (they depend on nothing the tensor
+      // core produces): the generator is a third of an epilogue's instructions and the wait is otherwise idle -- the last
+      // four K slabs' products (~1 500 clk) cannot start before the previous epilogue's last stores.
+      uint4 rk[8] = {};
+      auto draw = [&](int nblk, uint32_t pass, uint32_t layer, uint32_t j0) {
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+          if (b < nblk) rk[b] = Philox::gen_rk(dp.rk, s_lo, s_hi, pass, (layer << 16) | ((j0 >> 3) + b));
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+          if (b < nblk) asm volatile("" : "+r"(rk[b].x), "+r"(rk[b].y), "+r"(rk[b].z), "+r"(rk[b].w));   // pin before the wait
+      };
+      const bool drawn = kPredraw && drop_on && !inj;           // masks come from Philox, drawn ahead
+      if (drawn && !eval_item) draw(8, static_cast<uint32_t>(dp.pass_offset + t0), 0u, static_cast<uint32_t>(64 * q));
+
       float mean = 0.f, m2 = 0.f, slv = 0.f;
 #pragma unroll 1
       for (int pi = 0; pi < n_pass; ++pi) {
-        const bool eval_pass = a.mc && a.do_eval && pi == 0;
-        const int t = a.mc ? (a.do_eval ? pi - 1 : pi) : 0;                  // pass index of the sweep (mask stream, Welford count)
+        const bool eval_pass = a.mc && eval_item && pi == 0;
+        const int tl = a.mc ? (eval_item ? pi - 1 : pi) : 0;                 // pass index inside the chunk (Welford count)
+        const int t = t0 + tl;                                               // pass index of the sweep (mask stream)
         const bool active = drop_on && !eval_pass && (!inj || valid);
         const uint32_t pass = static_cast<uint32_t>(dp.pass_offset + t);
         // ---- stage the masked layer-0 activations as the first A operand
@@ -330,7 +399,7 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
             }
             float v[16] = {cur[0].x, cur[0].y, cur[0].z, cur[0].w, cur[1].x, cur[1].y, cur[1].z, cur[1].w,
                            cur[2].x, cur[2].y, cur[2].z, cur[2].w, cur[3].x, cur[3].y, cur[3].z, cur[3].w};
-            select16(v, active, pass, t, 0u, static_cast<uint32_t>(64 * q + 16 * j));
+            select16(v, active, rk[(2 * j) & 7], rk[(2 * j + 1) & 7], pass, t, 0u, static_cast<uint32_t>(64 * q + 16 * j));
             emit_slab(v, 4 * q + j);
 #pragma unroll
             for (int e = 0; e < 4; ++e) cur[e] = nxt[e];
@@ -339,15 +408,24 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
         // ---- hidden layers
 #pragma unroll 1
         for (int l = 1; l < L; ++l) {
+          if (drawn && active) draw(8, pass, static_cast<uint32_t>(l), static_cast<uint32_t>(64 * q));
           wait_done();
-          const uint32_t acc = tl + acc_sel * 256u + static_cast<uint32_t>(64 * q);
+          const uint32_t acc = tlane + acc_sel * 256u + static_cast<uint32_t>(64 * q);
           acc_sel ^= 1u;
           const float* bl = s_b + (l - 1) * kRH + 64 * q;
-#pragma unroll 1
+          float zb[2][16];
+          if constexpr (kLdPrefetch) tc::tmem_ld16(acc, zb[0]);
+          RES_J_UNROLL
           for (int j = 0; j < 4; ++j) {
-            float z[16], v[16];
-            tc::tmem_ld16(acc + 16u * j, z);
-            tc::tmem_wait_ld();
+            float v[16];
+            float* z = zb[kLdPrefetch ? (j & 1) : 0];
+            if constexpr (kLdPrefetch) {
+              tc::tmem_wait_ld();
+              if (j < 3) tc::tmem_ld16(acc + 16u * (j + 1), zb[(j + 1) & 1]);
+            } else {
+              tc::tmem_ld16(acc + 16u * j, z);
+              tc::tmem_wait_ld();
+            }
 #pragma unroll
             for (int g = 0; g < 16; g += 8) {
               const float4 bA = *reinterpret_cast<const float4*>(bl + 16 * j + g), bB = *reinterpret_cast<const float4*>(bl + 16 * j + g + 4);
@@ -357,15 +435,16 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[g + e] = t8[e];
             }
-            select16(v, active, pass, t, static_cast<uint32_t>(l), static_cast<uint32_t>(64 * q + 16 * j));
+            select16(v, active, rk[(2 * j) & 7], rk[(2 * j + 1) & 7], pass, t, static_cast<uint32_t>(l), static_cast<uint32_t>(64 * q + 16 * j));
             emit_slab(v, 4 * q + j);
           }
         }
         // ---- heads: 128 variance-head units (32 per quarter) + the mean head (column 128)
         float u = 0.f;
         {
+          if (drawn && active) draw(4, pass, static_cast<uint32_t>(L), static_cast<uint32_t>(32 * q));
           wait_done();
-          const uint32_t acc = tl + acc_sel * 256u;
+          const uint32_t acc = tlane + acc_sel * 256u;
           acc_sel ^= 1u;
           if (q == 0) {
             float zz[4];
@@ -373,7 +452,7 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
             tc::tmem_wait_ld();
             u = zz[0] + __ldg(net.bp);
           }
-#pragma unroll 1
+          RES_J_UNROLL
           for (int j = 0; j < 2; ++j) {
             const int c0 = 32 * q + 16 * j;
             float z[16], v[16];
@@ -388,14 +467,15 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[g + e] = t8[e];
             }
-            select16(v, active, pass, t, static_cast<uint32_t>(L), static_cast<uint32_t>(c0));
+            select16(v, active, rk[(2 * j) & 7], rk[(2 * j + 1) & 7], pass, t, static_cast<uint32_t>(L), static_cast<uint32_t>(c0));
             emit_slab(v, 2 * q + j);
           }
         }
         // ---- variance layer 1 (64 units, 16 per quarter) + the last dot; thread (row, 0) finishes the sample
         {
+          if (drawn && pi + 1 < n_pass) draw(8, static_cast<uint32_t>(dp.pass_offset + t + 1), 0u, static_cast<uint32_t>(64 * q));   // next pass's layer-0 masks
           wait_done();
-          const uint32_t acc = tl + acc_sel * 256u + static_cast<uint32_t>(16 * q);
+          const uint32_t acc = tlane + acc_sel * 256u + static_cast<uint32_t>(16 * q);
           acc_sel ^= 1u;
           float z[16];
           tc::tmem_ld16(acc, z);
@@ -424,14 +504,17 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
               if (valid) out.pred_mean[s] = u;
             } else {
               const float d = u - mean;
-              mean += d / static_cast<float>(t + 1);
+              mean += d / static_cast<float>(tl + 1);
               m2 = fmaf(d, u - mean, m2);
               slv += lv;
             }
           }
         }
       }
-      if (a.mc && valid && q == 0) {
+      if (a.mc && valid && q == 0 && C > 1) {
+        float* pp = a.part + static_cast<size_t>(chunk) * 3 * n + s;
+        pp[0] = mean; pp[n] = m2; pp[2 * n] = slv;
+      } else if (a.mc && valid && q == 0) {
         if (out.raw_mean) out.raw_mean[s] = mean;
         if (out.raw_m2) out.raw_m2[s] = m2;
         if (out.raw_slv) out.raw_slv[s] = slv;
@@ -474,12 +557,20 @@ int launch_wide_res(bool mc, const pinn_net_t* net, const float* x, int64_t n, i
   split(net->Wv1, kRNV, nullptr, kRNV, kRH / 2, ws + p.off_wv1);
   a.img_h = ws + p.off_wh; a.img_v1 = ws + p.off_wv1;
   a.a0 = reinterpret_cast<float*>(ws + p.off_a0);
+  const int C = mc ? res_pass_chunks(T) : 1;
+  const size_t part_bytes = C > 1 ? static_cast<size_t>(C) * 3 * n * sizeof(float) : 0;
+  if (workspace_bytes < p.bytes + part_bytes) { *err = PINN_E_WORKSPACE; return -1; }
+  a.chunks = C;
+  a.part = reinterpret_cast<float*>(ws + p.bytes);
   a.L = L; a.T = T; a.mc = mc ? 1 : 0; a.do_eval = (mc && out.pred_mean != nullptr) ? 1 : 0;
   a.inact = dp.p > 0.f ? dp.keep : 1.0f;
   a.no_logvar = (net->flags & PINN_NET_NO_LOGVAR) ? 1 : 0;
   cudaError_t e = cudaFuncSetAttribute(wide_res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kRSmemBytes));
   if (e != cudaSuccess) { *err = static_cast<int>(e); return -1; }
-  wide_res_kernel<<<p.grid, kRThreads, kRSmemBytes, st>>>(*net, x, n, dp, a, out);
+  const int64_t items = ((n + kRT - 1) / kRT) * C;
+  const int grid = static_cast<int>(items < sm_count() ? items : sm_count());
+  wide_res_kernel<<<grid, kRThreads, kRSmemBytes, st>>>(*net, x, n, dp, a, out);
+  if (C > 1) launch_mc_merge(a.part, n, T, C, out, st);
   *err = static_cast<int>(cudaGetLastError());
   return *err == 0 ? 1 : -1;
 }

@@ -659,7 +659,10 @@ static WidePlan<H> wide_plan(int L, int64_t n) {
 }
 size_t wide_tc_workspace_bytes(int H, int L, int64_t n) {
   if (n <= 0) return 0;
-  if (H == 256) return wide_plan<256>(L, n).bytes;
+  if (H == 256) {           // enough for either 256-wide path (resident-activation kernel: mlp_wide_res.cu)
+    const size_t a = wide_plan<256>(L, n).bytes, b = wide_res_workspace_bytes(L, n);
+    return a > b ? a : b;
+  }
   if (H == 128) return wide_plan<128>(L, n).bytes;
   return 0;
 }

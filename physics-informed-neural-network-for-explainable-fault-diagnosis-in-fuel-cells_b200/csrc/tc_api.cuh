@@ -13,6 +13,8 @@ int launch_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, 
 // long sweeps are cut into pass chunks (a function of T alone) whose Welford triples live in the workspace until merged
 int mc_pass_chunks(int T);
 size_t tc_mc_workspace_bytes(int64_t n);
+// fold per-chunk Welford triples [chunk][3][n] (chunk k = passes [k Tc, (k+1) Tc), Tc = ceil(T / C)) in chunk order and finish the sample
+void launch_mc_merge(const float* part, int64_t n, int T, int C, const TcOut& out, cudaStream_t st);
 // Wide nets (H = 128 / 256) on the tensor cores, one GEMM launch per layer (mlp_wide_tc.cu); same return convention.
 size_t wide_tc_workspace_bytes(int H, int L, int64_t n);
 int launch_wide_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, const DropParams& dp, const TcOut& out,

@@ -10,6 +10,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
+if os.environ.get("B200PINN_LIB"):        # A/B builds (profiles/build_variant.py)
+    from b200pinn import _abi
+    _abi.LIB_PATH = os.environ["B200PINN_LIB"]
 import b200pinn
 from b200pinn import kernels as K
 from b200pinn.synthetic import make_scaled_dataset
@@ -39,9 +42,10 @@ def run(dnn, xd, T, p, masks=None):
     return dict(u0=u0, s0=s0, u1=u1, s1=s1, pm=mc["pred_mean"], a_u=mc["a_u"], e_u=mc["e_u"], mean=mc["mean"])
 
 
+MODE = sys.argv[1] if len(sys.argv) > 1 else "all"
 worst = 0.0
-for layers, n, T in (([8, 256, 256, 256, 1], 1, 2), ([8, 256, 256, 256, 1], 129, 3), ([8, 256, 256, 1], 1000, 2),
-                     ([8, 256, 256, 256, 256, 256, 256, 1], 300, 2), ([8, 256, 256, 256, 1], 40000, 5)):
+for layers, n, T in () if MODE == "time" else (([8, 256, 256, 256, 1], 1, 2), ([8, 256, 256, 256, 1], 129, 3), ([8, 256, 256, 1], 1000, 2),
+                     ([8, 256, 256, 256, 256, 256, 256, 1], 300, 2), ([8, 256, 256, 256, 1], 40000, 5), ([8, 256, 256, 256, 1], 700, 50)):
     x, _, _, _ = make_scaled_dataset(max(n, 64), seed=41)
     xd = torch.tensor(x[:n], device=dev)
     dnn = random_net(layers, 12)
@@ -65,7 +69,7 @@ for layers, n, T in (([8, 256, 256, 256, 1], 1, 2), ([8, 256, 256, 256, 1], 129,
         print(f"L={L} n={n} T={T} {k:5s} resident vs gemm {e1:.2e}  vs ffma {e2:.2e}  injected vs ffma {e3:.2e}  gemm vs ffma {nrel(b[k], c[k]):.2e}")
 print("WORST", worst, "PASS" if worst < 1e-5 else "FAIL")
 
-if len(sys.argv) > 1 and sys.argv[1] == "quick":
+if MODE == "quick":
     sys.exit(0)
 
 
@@ -82,8 +86,9 @@ def timed(fn, reps=3, warm=1):
     return a.elapsed_time(b) / reps
 
 
-for layers, n, T in (([8, 256, 256, 256, 1], 262144, 10), ([8, 256, 256, 256, 256, 256, 256, 1], 262144, 10),
-                     ([8, 256, 256, 256, 1], 20000, 50), ([8, 256, 256, 256, 1], 1000000, 50)):
+CASES = (([8, 256, 256, 256, 1], 262144, 10), ([8, 256, 256, 256, 256, 256, 256, 1], 262144, 10),
+         ([8, 256, 256, 256, 1], 20000, 50), ([8, 256, 256, 256, 1], 20000, 2000), ([8, 256, 256, 256, 1], 1000000, 50))
+for layers, n, T in CASES[:2] if MODE == "time" else CASES:
     x, _, _, _ = make_scaled_dataset(n, seed=2)
     xd = torch.tensor(x, device=dev)
     dnn = random_net(layers, 3)
@@ -92,6 +97,9 @@ for layers, n, T in (([8, 256, 256, 256, 1], 262144, 10), ([8, 256, 256, 256, 25
     reps = 1 if n * T > 2e7 else 3
     t_res = timed(lambda: b200pinn.mc_dropout_device(dnn, xd, T, 0.4, seed=1), reps=reps)
     t_fwd = timed(lambda: K.mlp_forward(K.net_from_module(dnn), xd), reps=reps)
+    if MODE == "time":
+        print(f"L={L} n={n} T={T}: MC sweep resident {t_res:.3f} ms ({n * T * flop_pass / t_res / 1e9:.1f} TFLOP/s) | eval forward {t_fwd:.3f} ms", flush=True)
+        continue
     with K.path_flags(no_wide_resident=True):
         t_gemm = timed(lambda: b200pinn.mc_dropout_device(dnn, xd, T, 0.4, seed=1), reps=reps)
         t_fwd_g = timed(lambda: K.mlp_forward(K.net_from_module(dnn), xd), reps=reps)
