@@ -493,7 +493,25 @@ def run_ours(args):
     c4["what"] = ("configs[3]: 6x256 PINN, data-parallel train_dnn step at 524288 samples per GPU (= batch 4M on 8 GPUs; global batch "
                   "here = n_gpus x 524288), one gradient-bucket exchange (1.49 MB) per step fused into the Adam launch over NVLink "
                   "peer memory; the MC numbers are the same net's sweep at T=10")
-    wide["what"] = ("the reference's own Layers (01:2139): MC sweep T=10 and train_dnn step on the per-layer tcgen05 3xTF32 GEMM path")
+    wide["what"] = ("the reference's own Layers (01:2139): MC sweep T=10 on the resident-activation kernel (csrc/mlp_wide_res.cu: one "
+                    "persistent CTA per SM, activations as fp16 hi/lo pairs in tensor memory across layers and passes, weights "
+                    "streamed through a TMA ring); train_dnn step on the per-layer tcgen05 3xTF32 GEMM path")
+    # the sweep kernel against the tensor roofline: algorithmic FLOPs, and the FLOPs the tensor pipe actually executes (three
+    # fp16 products per contraction, heads padded to N = 144)
+    rec_w = ncu_record("wide_res_ts_kernel")
+    pkw = peaks()
+    w3 = wide["3x256"]
+    exec_per_pass = 6.0 * (2 * 256 * 256 + 144 * 256 + 64 * 128)
+    wide["roofline"] = {"bound": "tensor", "kernel": "wide_res_ts_kernel (3x256, N = 262144, T = 10 + the eval pass)",
+                        "achieved": w3["mc_tflops_per_gpu"], "peak": pkw["bf16"], "unit": "TFLOP/s",
+                        "frac": w3["mc_tflops_per_gpu"] / pkw["bf16"],
+                        "executed_tflops": w3["n_per_gpu"] * (T_w + 1) * exec_per_pass / (w3["mc_ms"] * 1e-3) / 1e12,
+                        "executed_frac": w3["n_per_gpu"] * (T_w + 1) * exec_per_pass / (w3["mc_ms"] * 1e-3) / 1e12 / pkw["bf16"],
+                        "algorithmic_bytes": 44 * w3["n_per_gpu"],
+                        "traffic": (rec_w["dram_bytes"] * w3["n_per_gpu"] / rec_w["n"]) if rec_w else None, "ncu": rec_w,
+                        "note": "achieved = algorithmic FLOPs (344 704 per sample*pass, T passes) / CUDA-event time of the sweep call; "
+                                "executed = what the tensor pipe runs for fp32 parity (a_l*w_h + a_h*w_l + a_h*w_h as kind::f16 "
+                                "products, T + 1 passes); algorithmic bytes = x in (32 B) + three result vectors out"}
 
     # --- configs[0] scale (N = 20 000, the reference's own CPU-runnable case): every step is latency-bound here.
     c1 = None

@@ -230,7 +230,23 @@ PINN_D float tanh_pre(float a) {       // a = kTanhArg * x
 
 // Two activations per instruction where the ISA allows it: sm_100 has packed fp32x2 FFMA2 / FADD2 (same FLOP rate,
 // half the issue slots -- and issue slots, not FLOPs, bound the tensor-core kernels' epilogues).
+// PAIR: ONE reciprocal for the two activations, 1/d0 = d1 / (d0 d1): 3 MUFU operations per pair instead of 4 (the XU pipe
+// runs 16 lanes per clock and SM and is the busiest pipe of the 64-wide MC kernel's epilogue) for three more FMA-pipe
+// instructions.  The arguments are clamped at 2^40 (tanh is 1.0f to the last bit from 2^25 on) so that the product of the
+// two denominators cannot overflow; the extra product and multiply leave the absolute error within the same 3e-7.
+// Measured (profiles/r2_wide_res_ab4.log): 64-wide sweep T = 1000 x N = 1M 201.5 -> 187.4 ms; no gain for the fused
+// training kernel or the 256-wide kernel (neither is bound by the XU pipe), which keep the two-reciprocal form.
+template <bool PAIR = false>
 PINN_D float2 tanh_pre2(float2 a) {     // a = kTanhArg * x, two lanes
+  if constexpr (PAIR) {
+    float e0, e1, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(a.x, 40.0f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(a.y, 40.0f)));
+    const float2 dd = __fadd2_rn(make_float2(e0, e1), make_float2(1.0f, 1.0f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(dd.x * dd.y));
+    const float2 rr = __fmul2_rn(make_float2(r, r), make_float2(dd.y, dd.x));
+    return __ffma2_rn(rr, make_float2(-2.0f, -2.0f), make_float2(1.0f, 1.0f));
+  }
   float ex, ey, rx, ry;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(a.x));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ey) : "f"(a.y));
@@ -240,11 +256,12 @@ PINN_D float2 tanh_pre2(float2 a) {     // a = kTanhArg * x, two lanes
   return __ffma2_rn(make_float2(rx, ry), make_float2(-2.0f, -2.0f), make_float2(1.0f, 1.0f));
 }
 // t[q] = tanh(z[q] + b[q]) for eight units, biases pre-scaled by kTanhArg
+template <bool PAIR = false>
 PINN_D void tanh8_prescaled(const float* z, const float (&bs)[8], float (&t)[8]) {
 #pragma unroll
   for (int q = 0; q < 8; q += 2) {
     const float2 a2 = __ffma2_rn(make_float2(z[q], z[q + 1]), make_float2(kTanhArg, kTanhArg), make_float2(bs[q], bs[q + 1]));
-    const float2 t2 = tanh_pre2(a2);
+    const float2 t2 = tanh_pre2<PAIR>(a2);
     t[q] = t2.x; t[q + 1] = t2.y;
   }
 }

@@ -371,7 +371,7 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
             const float4 bA = *reinterpret_cast<const float4*>(bl + g), bB = *reinterpret_cast<const float4*>(bl + g + 4);
             const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
             float t8[8], v[8];
-            tanh8_prescaled(z + g, bb, t8);
+            tanh8_prescaled<true>(z + g, bb, t8);
             select8(rl[g / 8], ks, active, static_cast<uint32_t>(l), cb + g, t8, v);
             store8(cb + g, v, g / 8);
           }
@@ -405,7 +405,7 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
             const float4 bA = *reinterpret_cast<const float4*>(bv0 + g), bB = *reinterpret_cast<const float4*>(bv0 + g + 4);
             const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
             float t8[8], v[8];
-            tanh8_prescaled(v0 + g, bb, t8);
+            tanh8_prescaled<true>(v0 + g, bb, t8);
             select8(rv[g / 8], ks, active, static_cast<uint32_t>(L), 16 * half + g, t8, v);
 #pragma unroll
             for (int q = 0; q < 8; ++q) v0[g + q] = v[q];

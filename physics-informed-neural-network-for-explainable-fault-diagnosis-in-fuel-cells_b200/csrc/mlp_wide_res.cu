@@ -3,30 +3,34 @@
 //
 // The per-layer GEMM path (mlp_wide_tc.cu) writes every layer's activations to HBM as 8 B/element tf32 hi/lo planes and
 // reads them back in the next launch: ~3 000x the algorithmic bytes of a sweep.  Here ONE persistent CTA per SM owns a
-// 128-sample tile for ALL passes of the sweep and its activations never leave the SM:
+// 128-sample tile for ALL passes of a work item and its activations never leave the SM:
 //
 //   split    : fp16 pairs instead of tf32 pairs.  a = a_h + a_l with a_h = fp16(a), a_l = fp16(a - a_h) carries 22
 //              significant bits for |a| <= 1/(1-p) (tanh outputs), w likewise; the three products
 //              a_l*w_h + a_h*w_l + a_h*w_h run as `tcgen05.mma.kind::f16` (twice the tf32 rate) with fp32 accumulation.
-//              4 B per element instead of 8: a tile's [128 x 256] activations are 128 KB of shared memory -- resident.
-//   A planes : shared memory, K-major no-swizzle UMMA layout, byte(row, k) = (k/8) * 2048 + row * 16 + (k%8) * 2;
-//              a K = 16 slab of both planes is 2 x 4 KB.  Written by the epilogue, read only by the tensor core.
+//   A planes : TENSOR MEMORY, packed fp16 pairs written by the epilogue with tcgen05.st (lane = sample row, column c of a
+//              plane = features 2c, 2c+1): the tensor core fetches only B from shared memory.
 //   weights  : pre-split fp16 images in global memory (L2-resident, 256 KB per hidden layer), one contiguous
-//              [hi | lo] block per K = 16 slab, streamed by a producer warp with `cp.async.bulk` (1-D TMA, mbarrier
-//              transaction bytes) through a 5 x 16 KB ring.  Dropout scale 1/(1-p) folded in.
-//   accum    : two 256-column fp32 accumulators in tensor memory (all 512 columns), alternating by MMA phase: the
-//              epilogue of phase p reads one while the products of phase p+1 fill the other.
-//   epilogue : 16 warps, thread = (row, 64-column quarter).  Per 16 columns: tcgen05.ld, bias + tanh, Philox keep-select,
-//              fp16 split, four 16-byte shared-memory stores, fence.proxy.async, arrive on the slab's mbarrier -- the MMA
-//              warp issues the next layer's three products of that K slab as soon as the slab and its weights are in, so
-//              the tensor pipe works under the epilogue that feeds it.
-//   layer 0  : K = 8, pass-invariant: computed once per tile on the CUDA cores and parked in a per-CTA
-//              128 KB global scratch (each thread re-reads only what it wrote itself; stays in L2), re-masked per pass.
+//              [hi | lo] block per K = 16 slab (K-major no-swizzle UMMA layout), streamed by a producer warp with
+//              `cp.async.bulk` (1-D TMA, mbarrier transaction bytes) through a 5 x 16 KB ring.  Dropout scale folded in.
+//   tensor memory : [0, 256) the fp32 accumulator | [256, 384) A hi plane | [384, 512) A lo plane.
+//   epilogue : 16 warps, thread = (row, 64-column quarter).  It first pulls all its accumulator columns into registers
+//              and releases the accumulator (`accfree`); then per 16 columns: bias + tanh, Philox keep-select, fp16
+//              split, two tcgen05.st, arrive on the K slab's mbarrier -- the MMA warp issues the next layer's three
+//              products of that slab as soon as the slab and its weights are in, so the tensor pipe works under the
+//              epilogue that feeds it.
+//   layer 0  : K = 8, pass-invariant: computed once per work item on the CUDA cores and parked in shared
+//              memory (128 KB fp32), re-masked per pass.
 //   heads    : [Wv0; Wp; 0] as one N = 144 product, Wv1 (128 -> 64) as an N = 64 product, the last 64-wide dot, the
 //              log-variance and the Welford update on the CUDA cores; the statistics live in registers across passes.
 //
 // MMA phases of a pass: hidden layers 1..L-1, heads, variance layer 1.  HBM traffic of a sweep = x in, three result
 // vectors out.  The mask stream (Philox counters per (sample, pass, layer, unit / 8)) is the one every other path uses.
+//
+// What bounds it (profiles/r2_wide_res_ab*.log): the tensor pipe.  The three products execute ~950 TFLOP/s
+// (58 % of the measured dense bf16 peak) at N = 262 144; a first form with the A planes in shared memory was 2 % slower,
+// and pre-drawn Philox blocks, a prefetched tcgen05.ld, per-warp arrivals or a deeper ring moved nothing -- what is left
+// is the tensor pipe idling at the start of each epilogue until the first K slab of the next layer is ready.
 #include <cuda_fp16.h>
 #include "net.cuh"
 #include "tc.cuh"
@@ -43,49 +47,22 @@ constexpr int kRThreads = (kRComputeWarps + 2) * 32;   // + producer warp + MMA 
 #endif
 constexpr int kRStages = RES_STAGES;
 constexpr int kRStageBytes = 64 * kRH;      // one K = 16 slab of a 256-row matrix: [hi 8 KB | lo 8 KB]
-constexpr int kRPlane = kRT * kRH * 2;      // one fp16 plane of a tile's activations (64 KB)
-constexpr int kRSlabA = kRT * 32;           // bytes of one K = 16 slab of one A plane (4 KB)
 constexpr int kRNH = kRH / 2 + 16;          // heads product: 128 variance-head rows + mean row + 15 zero rows
 constexpr int kRNV = kRH / 4;               // variance layer 1: 64 rows
-// A/B switches of the epilogue (profiles/build_variant.py -DRES_...=0/1; measured numbers in DESIGN.md)
-#ifndef RES_PREDRAW
-#define RES_PREDRAW 0      // draw a phase's Philox blocks ahead of the wait that precedes its epilogue
-#endif
-#ifndef RES_UNROLLJ
-#define RES_UNROLLJ 1      // unroll the four 16-column groups of a hidden epilogue
-#endif
-#ifndef RES_WARP_ARRIVE
-#define RES_WARP_ARRIVE 1  // one mbarrier arrival per warp and K slab (after __syncwarp) instead of one per thread
-#endif
-#ifndef RES_LDPF
-#define RES_LDPF 1         // tcgen05.ld of the next 16 columns in flight while the current 16 are processed
-#endif
-constexpr bool kPredraw = RES_PREDRAW != 0, kLdPrefetch = RES_LDPF != 0 && RES_UNROLLJ != 0;
-#if RES_UNROLLJ
-#define RES_J_UNROLL _Pragma("unroll")
-#else
-#define RES_J_UNROLL _Pragma("unroll 1")
-#endif
-static_assert(!kPredraw || RES_UNROLLJ, "pre-drawn blocks are indexed by the group: needs the unrolled form");
 
 PINN_HD constexpr int res_slab_bytes(int N) { return 64 * N; }                              // [hi | lo] of one slab
 PINN_HD constexpr size_t res_img_bytes(int N, int K) { return static_cast<size_t>(K / 16) * res_slab_bytes(N); }
 
 struct ResPlan {
-  size_t off_w[PINN_MAX_HIDDEN], off_wh, off_wv1, off_a0, bytes;
-  int grid;
+  size_t off_w[PINN_MAX_HIDDEN], off_wh, off_wv1, bytes;
 };
-static ResPlan res_plan(int L, int64_t n) {
+static ResPlan res_plan(int L) {
   ResPlan p{};
   size_t o = 0;
   auto take = [&](size_t b) { size_t r = o; o += (b + 255) & ~static_cast<size_t>(255); return r; };
   for (int l = 1; l < L; ++l) p.off_w[l] = take(res_img_bytes(kRH, kRH));
   p.off_wh = take(res_img_bytes(kRNH, kRH));
   p.off_wv1 = take(res_img_bytes(kRNV, kRH / 2));
-  const int64_t tiles = (n + kRT - 1) / kRT;
-  const int64_t items = tiles * 8;                 // up to 8 pass chunks per tile
-  p.grid = static_cast<int>(items < sm_count() ? (items > 0 ? items : 1) : sm_count());
-  p.off_a0 = take(static_cast<size_t>(p.grid) * kRT * kRH * sizeof(float));
   p.bytes = o;
   return p;
 }
@@ -96,7 +73,7 @@ int res_pass_chunks(int T) {
   return c < 1 ? 1 : (c > 8 ? 8 : c);
 }
 size_t wide_res_workspace_bytes(int L, int64_t n) {
-  return n > 0 ? res_plan(L, n).bytes + static_cast<size_t>(8) * 3 * static_cast<size_t>(n) * sizeof(float) : 0;
+  return n > 0 ? res_plan(L).bytes + static_cast<size_t>(8) * 3 * static_cast<size_t>(n) * sizeof(float) : 0;
 }
 
 // two fp32 -> packed fp16 pair (hi) and the packed fp16 pair of the remainders (lo)
@@ -135,22 +112,10 @@ __global__ void wide_res_split_kernel(const float* __restrict__ src_a, int rows_
 PINN_HD constexpr uint32_t make_idesc_f16(int M, int N) {      // D = F32, A = B = F16, both K-major
   return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
-PINN_D void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-PINN_D float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
-PINN_D void st_cg4(float* p, float4 v) { __stcg(reinterpret_cast<float4*>(p), v); }
-
 struct ResArgs {
   const unsigned char* img_w[PINN_MAX_HIDDEN];   // hidden layers 1..L-1
   const unsigned char* img_h;                    // heads
   const unsigned char* img_v1;                   // variance layer 1
-  float* a0;                                     // [grid][64 column quads][128 rows][4]
   int L, T, mc, do_eval;
   int chunks;                                    // pass chunks per tile (a function of T alone), work item = (tile, chunk)
   float* part;                                   // chunks > 1: per-chunk Welford triples [chunk][3][n], folded by mc_merge
@@ -160,29 +125,62 @@ struct ResArgs {
 
 // slab issued i-th in a phase whose K slabs were produced by the four column quarters, `spq` slabs each: the quarters
 // work in parallel, so their j-th slabs become ready together
-PINN_D int res_slab_order(int i, int spq) { return (i & 3) * spq + (i >> 2); }
+#ifndef RES_PAIR
+#define RES_PAIR 1
+#endif
+// RES_PAIR: the quarters work as two pairs; thread (row, quarter q) owns the 8-column half (q & 1) of the eight K slabs
+// 8 (q >> 1) .. 8 (q >> 1) + 7, so a pair finishes one K slab per 8-column step: the first slabs of the next layer are
+// ready after an eighth of the epilogue instead of a quarter, and only two slabs' products trail its end instead of four.
+constexpr bool kPair = RES_PAIR != 0;
+PINN_D int res_slab_order(int i, int ns) { return kPair ? (i & 1) * (ns >> 1) + (i >> 1) : (i & 3) * (ns >> 2) + (i >> 2); }
+
+// D[tmem] (+)= A[tmem, packed fp16 pairs] * B[smem]^T, one K = 16 slab.  Issued by ONE thread.
+PINN_D void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+#ifdef PINN_TIMELINE
+// Debug build (profiles/timeline_wide.py): clock stamps of CTA 0 -- compute warps 0 (quarter 0) and 12 (quarter 3), lane 0:
+// one record per epilogue [kind, before wait, after wait, after release, after slab 0..3]; MMA warp: one record per phase
+// [after accfree, issue time of every slab, after the last commit].
+__device__ long long g_rtl[2][512][8];
+__device__ long long g_mtl[512][20];
+#define RTL(k) do { if (tl_on && tl_i < 512) g_rtl[tl_w][tl_i][k] = clock64(); } while (0)
+#define RTL_KIND(v) do { if (tl_on && tl_i < 512) g_rtl[tl_w][tl_i][0] = (v); } while (0)
+#define RTL_NEXT() do { ++tl_i; } while (0)
+#else
+#define RTL(k) do {} while (0)
+#define RTL_KIND(v) do {} while (0)
+#define RTL_NEXT() do {} while (0)
+#endif
 
 __global__ void __launch_bounds__(kRThreads, 1)
-wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict__ x, int64_t n, const __grid_constant__ DropParams dp,
-                const __grid_constant__ ResArgs a, TcOut out) {
+wide_res_ts_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict__ x, int64_t n, const __grid_constant__ DropParams dp,
+                   const __grid_constant__ ResArgs a, TcOut out) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) uint64_t full[kRStages], empty[kRStages], ready[16], done;
+  __shared__ __align__(8) uint64_t full[kRStages], empty[kRStages], ready[16], done, accfree;
   __shared__ uint32_t tmem_base_s;
-  unsigned char* const ring = smem + 2 * kRPlane;
+  unsigned char* const ring = smem;
   float* const fsm = reinterpret_cast<float*>(ring + kRStages * kRStageBytes);
-  // float area: b[l] (l = 1..L-1, 256 each, pre-scaled by kTanhArg) | bv0 (128, pre-scaled) | bv1 (64, pre-scaled) | Wv2 (64) | part (4 x 128)
   const int L = a.L;
   float* const s_b = fsm;
   float* const s_bv0 = fsm + (PINN_MAX_HIDDEN - 1) * kRH;
   float* const s_bv1 = s_bv0 + kRH / 2;
   float* const s_wv2 = s_bv1 + kRNV;
   float* const s_part = s_wv2 + kRNV;
+  float4* const a0s = reinterpret_cast<float4*>(s_part + 4 * kRT);        // [64 column quads][128 rows]
 
   const int tid = threadIdx.x, warp = tc::uniform_warp_idx(), lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < kRStages; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
-    for (int c = 0; c < 16; ++c) tc::mbar_init(&ready[c], RES_WARP_ARRIVE ? 4 : 128);
+    for (int c = 0; c < 16; ++c) tc::mbar_init(&ready[c], kPair ? 256 : 128);
     tc::mbar_init(&done, 1);
+    tc::mbar_init(&accfree, kRComputeWarps * 32);
     tc::fence_mbar_init();
   }
   __syncwarp();
@@ -203,13 +201,12 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
   // fills the machine.
   const int C = a.chunks, Tc = (a.T + C - 1) / C;
   const int64_t n_items = n_tiles * C;
-  auto item_passes = [&](int chunk) {            // dropout passes of the chunk (+ the eval pass, which rides with chunk 0)
+  auto item_passes = [&](int chunk) {
     if (!a.mc) return 1;
     const int t0 = chunk * Tc, cnt = a.T - t0 < Tc ? a.T - t0 : Tc;
     return (cnt > 0 ? cnt : 0) + ((a.do_eval && chunk == 0) ? 1 : 0);
   };
-  const int n_phase = L + 1;                                   // MMA phases per pass: L-1 hidden, heads, variance layer 1
-  // phase ph of a pass: image, rows N, K slabs, slabs per producing quarter
+  const int n_phase = L + 1;
   auto phase_img = [&](int ph) { return ph < L - 1 ? a.img_w[ph + 1] : (ph == L - 1 ? a.img_h : a.img_v1); };
   auto phase_N = [&](int ph) { return ph < L - 1 ? kRH : (ph == L - 1 ? kRNH : kRNV); };
   auto phase_slabs = [&](int ph) { return ph <= L - 1 ? kRH / 16 : (kRH / 2) / 16; };
@@ -222,84 +219,114 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
         for (int pi = 0, n_pass = item_passes(static_cast<int>(item % C)); pi < n_pass; ++pi)
           for (int ph = 0; ph < n_phase; ++ph) {
             const unsigned char* img = phase_img(ph);
-            const int N = phase_N(ph), ns = phase_slabs(ph), spq = ns / 4;
+            const int N = phase_N(ph), ns = phase_slabs(ph);
             const uint32_t bytes = static_cast<uint32_t>(res_slab_bytes(N));
             for (int i = 0; i < ns; ++i, ++cnt) {
               const uint32_t s = cnt % kRStages;
               if (cnt >= kRStages) tc::mbar_wait(&empty[s], ((cnt / kRStages) - 1u) & 1u);
               tc::mbar_expect_tx(&full[s], bytes);
-              tc::bulk_g2s(ring + s * kRStageBytes, img + static_cast<size_t>(res_slab_order(i, spq)) * bytes, bytes, &full[s]);
+              tc::bulk_g2s(ring + s * kRStageBytes, img + static_cast<size_t>(res_slab_order(i, ns)) * bytes, bytes, &full[s]);
             }
           }
     }
     __syncwarp();
   } else if (warp == kRComputeWarps + 1) {
     // ================================================================== MMA issuer
-    uint32_t cnt = 0, rpar = 0u, acc_sel = 0u;
-    const uint32_t a_hi_s = tc::smem_u32(smem), a_lo_s = a_hi_s + kRPlane, ring_s = tc::smem_u32(ring);
+    uint32_t cnt = 0, rpar = 0u, fpar = 0u;
+    bool first_phase = true;
+#ifdef PINN_TIMELINE
+    int mtl_i = 0;
+#endif
+    const uint32_t ring_s = tc::smem_u32(ring), a_hi_t = tb + 256u, a_lo_t = tb + 384u;
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x)
       for (int pi = 0, n_pass = item_passes(static_cast<int>(item % C)); pi < n_pass; ++pi)
-        for (int ph = 0; ph < n_phase; ++ph, acc_sel ^= 1u) {
-          const int N = phase_N(ph), ns = phase_slabs(ph), spq = ns / 4;
-          const uint32_t idesc = make_idesc_f16(kRT, N), d_t = tb + acc_sel * 256u;
+        for (int ph = 0; ph < n_phase; ++ph) {
+          const int N = phase_N(ph), ns = phase_slabs(ph);
+          const uint32_t idesc = make_idesc_f16(kRT, N);
           const uint32_t lbo_b = static_cast<uint32_t>(N) * 16u;
+          // the accumulator is free once every compute thread holds its columns of the previous phase in registers
+          if (!first_phase) { tc::mbar_wait(&accfree, fpar); fpar ^= 1u; }
+          first_phase = false;
+#ifdef PINN_TIMELINE
+          const bool mtl_on = blockIdx.x == 0 && lane == 0 && mtl_i < 512;
+          if (mtl_on) { g_mtl[mtl_i][0] = ph; g_mtl[mtl_i][1] = clock64(); }
+#endif
 #pragma unroll 1
           for (int i = 0; i < ns; ++i, ++cnt) {
             const uint32_t s = cnt % kRStages;
-            const int slab = res_slab_order(i, spq);
+            const int slab = res_slab_order(i, ns);
             tc::mbar_wait(&ready[slab], (rpar >> slab) & 1u);
             rpar ^= 1u << slab;
             tc::mbar_wait(&full[s], (cnt / kRStages) & 1u);
             __syncwarp();
+#ifdef PINN_TIMELINE
+            if (mtl_on) g_mtl[mtl_i][2 + i] = clock64();
+#endif
             if (tc::elect_one()) {
               tc::fence_after_sync();
-              const uint64_t ah = tc::make_desc(a_hi_s + slab * kRSlabA, kRT * 16, 128), al = tc::make_desc(a_lo_s + slab * kRSlabA, kRT * 16, 128);
-              const uint32_t sw = ring_s + s * kRStageBytes;
+              const uint32_t sw = ring_s + s * kRStageBytes, ac = 8u * static_cast<uint32_t>(slab);
               const uint64_t bh = tc::make_desc(sw, lbo_b, 128), bl = tc::make_desc(sw + static_cast<uint32_t>(N) * 32u, lbo_b, 128);
-              umma_f16(d_t, al, bh, idesc, i != 0 ? 1u : 0u);      // small terms first: lo*hi, hi*lo, then hi*hi
-              umma_f16(d_t, ah, bl, idesc, 1u);
-              umma_f16(d_t, ah, bh, idesc, 1u);
+              umma_f16_ts(tb, a_lo_t + ac, bh, idesc, i != 0 ? 1u : 0u);      // small terms first: lo*hi, hi*lo, then hi*hi
+              umma_f16_ts(tb, a_hi_t + ac, bl, idesc, 1u);
+              umma_f16_ts(tb, a_hi_t + ac, bh, idesc, 1u);
               tc::umma_commit(&empty[s]);
               if (i == ns - 1) tc::umma_commit(&done);
             }
             __syncwarp();
           }
+#ifdef PINN_TIMELINE
+          if (mtl_on) { g_mtl[mtl_i][18] = clock64(); }
+          ++mtl_i;
+#endif
         }
   } else {
     // ================================================================== compute warps: thread = (row, column quarter)
     const int q = warp >> 2, r = (warp & 3) * 32 + lane;
+#ifdef PINN_TIMELINE
+    const bool tl_on = blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 12);
+    const int tl_w = warp == 0 ? 0 : 1;
+    int tl_i = 0;
+#endif
     const uint32_t tlane = tb + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    unsigned char* const my_a = smem + r * 16;
-    float* const my_a0 = a.a0 + static_cast<size_t>(blockIdx.x) * kRT * kRH + static_cast<size_t>(r) * 4;
+    const uint32_t a_hi_l = tlane + 256u, a_lo_l = tlane + 384u;
+    float4* const my_a0 = a0s + r;
     const bool drop_on = dp.p > 0.f, inj = dp.masks != nullptr;
     const int Dm = L * kRH + kRH / 2;
-    uint32_t dpar = 0u, acc_sel = 0u;
+    uint32_t dpar = 0u;
 
-    // 16 masked activations -> both planes of A slab `slab`, then hand the slab to the MMA warp
+    // 16 masked activations -> packed fp16 pairs in both A planes (8 columns each), then hand the K slab to the MMA warp
     auto emit_slab = [&](const float (&v)[16], int slab) {
-      uint4 h0, h1, l0, l1;
-      split_h2(v[0], v[1], h0.x, l0.x);   split_h2(v[2], v[3], h0.y, l0.y);
-      split_h2(v[4], v[5], h0.z, l0.z);   split_h2(v[6], v[7], h0.w, l0.w);
-      split_h2(v[8], v[9], h1.x, l1.x);   split_h2(v[10], v[11], h1.y, l1.y);
-      split_h2(v[12], v[13], h1.z, l1.z); split_h2(v[14], v[15], h1.w, l1.w);
-      unsigned char* p = my_a + slab * kRSlabA;
-      *reinterpret_cast<uint4*>(p) = h0;
-      *reinterpret_cast<uint4*>(p + kRT * 16) = h1;
-      *reinterpret_cast<uint4*>(p + kRPlane) = l0;
-      *reinterpret_cast<uint4*>(p + kRPlane + kRT * 16) = l1;
-      tc::fence_proxy_async();
-#if RES_WARP_ARRIVE
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&ready[slab]);
-#else
+      uint32_t h[8], lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) split_h2(v[2 * e], v[2 * e + 1], h[e], lo[e]);
+      tc::tmem_st8(a_hi_l + 8u * static_cast<uint32_t>(slab), reinterpret_cast<const float*>(h));
+      tc::tmem_st8(a_lo_l + 8u * static_cast<uint32_t>(slab), reinterpret_cast<const float*>(lo));
+      tc::tmem_wait_st();
+      tc::fence_before_sync();
       tc::mbar_arrive(&ready[slab]);
-#endif
     };
+    // pair form: 8 masked activations = columns [c0, c0 + 8) (one half of K slab c0 / 16)
+    auto emit_half = [&](const float (&v)[8], int c0) {
+      uint32_t h[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split_h2(v[2 * e], v[2 * e + 1], h[e], lo[e]);
+      tc::tmem_st4(a_hi_l + static_cast<uint32_t>(c0 >> 1), reinterpret_cast<const float*>(h));
+      tc::tmem_st4(a_lo_l + static_cast<uint32_t>(c0 >> 1), reinterpret_cast<const float*>(lo));
+      tc::tmem_wait_st();
+      tc::fence_before_sync();
+      tc::mbar_arrive(&ready[c0 >> 4]);
+    };
+    const int pr = q >> 1, hf = q & 1;
     auto wait_done = [&]() {
       tc::mbar_wait(&done, dpar);
       dpar ^= 1u;
       __syncwarp();
       tc::fence_after_sync();
+    };
+    auto release_acc = [&]() {          // this thread's accumulator columns are in registers
+      tc::tmem_wait_ld();
+      tc::fence_before_sync();
+      tc::mbar_arrive(&accfree);
     };
 
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -312,7 +339,7 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
       const uint64_t sg = static_cast<uint64_t>(dp.sample_offset + s);
       const uint32_t s_lo = static_cast<uint32_t>(sg), s_hi = static_cast<uint32_t>(sg >> 32);
       // keep-select 16 activations of units [j0, j0 + 16) of dropout layer `layer`
-      auto select16 = [&](float (&v)[16], bool active, const uint4& r0, const uint4& r1, uint32_t pass, int tloc, uint32_t layer, uint32_t j0) {
+      auto select16 = [&](float (&v)[16], bool active, uint32_t pass, int tloc, uint32_t layer, uint32_t j0) {
         if (active) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
@@ -323,8 +350,7 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
 #pragma unroll
               for (int e = 0; e < 4; ++e) { k[e] = ((mb.x >> (8 * e)) & 0xffu) != 0; k[4 + e] = ((mb.y >> (8 * e)) & 0xffu) != 0; }
             } else {
-              if constexpr (kPredraw) keep8_from(g == 0 ? r0 : r1, dp.thresh_hi, k);
-              else keep8_from(Philox::gen_rk(dp.rk, s_lo, s_hi, pass, (layer << 16) | ((j0 >> 3) + g)), dp.thresh_hi, k);
+              keep8_from(Philox::gen_rk(dp.rk, s_lo, s_hi, pass, (layer << 16) | ((j0 >> 3) + g)), dp.thresh_hi, k);
             }
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[8 * g + e] = k[e] ? v[8 * g + e] : 0.f;
@@ -334,8 +360,43 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
           for (int e = 0; e < 16; ++e) v[e] *= a.inact;
         }
       };
+      auto select8 = [&](float (&v)[8], bool active, uint32_t pass, int tloc, uint32_t layer, uint32_t j0) {
+        if (active) {
+          bool k[8];
+          if (inj) {
+            const uint8_t* mrow = dp.masks + (static_cast<size_t>(tloc) * dp.mask_n + s) * Dm + layer * kRH + j0;
+            const uint2 mb = *reinterpret_cast<const uint2*>(mrow);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { k[e] = ((mb.x >> (8 * e)) & 0xffu) != 0; k[4 + e] = ((mb.y >> (8 * e)) & 0xffu) != 0; }
+          } else {
+            keep8_from(Philox::gen_rk(dp.rk, s_lo, s_hi, pass, (layer << 16) | (j0 >> 3)), dp.thresh_hi, k);
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = k[e] ? v[e] : 0.f;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] *= a.inact;
+        }
+      };
+      auto tanh8b = [&](const float* z, const float* bias, float (&v)[8]) {
+        const float4 bA = *reinterpret_cast<const float4*>(bias), bB = *reinterpret_cast<const float4*>(bias + 4);
+        const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+        tanh8_prescaled(z, bb, v);
+      };
+      // v[0..16) = tanh(z[0..16) + bias)   (biases pre-scaled by 2 log2 e)
+      auto tanh16 = [&](const float* z, const float* bias, float (&v)[16]) {
+#pragma unroll
+        for (int g = 0; g < 16; g += 8) {
+          const float4 bA = *reinterpret_cast<const float4*>(bias + g), bB = *reinterpret_cast<const float4*>(bias + g + 4);
+          const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+          float t8[8];
+          tanh8_prescaled(z + g, bb, t8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[g + e] = t8[e];
+        }
+      };
 
-      // ---- layer 0 (pass-invariant): this thread's 64 columns -> the CTA's scratch
+      // ---- layer 0 (pass-invariant): this thread's 64 columns -> the tile's park in shared memory
       {
         float xr[PINN_N_IN];
         if (valid) {
@@ -347,7 +408,8 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
           for (int i = 0; i < PINN_N_IN; ++i) xr[i] = 0.f;
         }
 #pragma unroll 1
-        for (int c4 = 16 * q; c4 < 16 * q + 16; ++c4) {
+        for (int i4 = 0; i4 < 16; ++i4) {
+          const int c4 = kPair ? 4 * (8 * pr + (i4 >> 1)) + 2 * hf + (i4 & 1) : 16 * q + i4;      // this thread's i4-th column quad
           float o4[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -359,24 +421,9 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
             z = fmaf(w1.x, xr[4], z); z = fmaf(w1.y, xr[5], z); z = fmaf(w1.z, xr[6], z); z = fmaf(w1.w, xr[7], z);
             o4[e] = tanh_pre(z * kTanhArg);
           }
-          st_cg4(my_a0 + static_cast<size_t>(c4) * (kRT * 4), make_float4(o4[0], o4[1], o4[2], o4[3]));
+          my_a0[c4 * kRT] = make_float4(o4[0], o4[1], o4[2], o4[3]);
         }
       }
-
-      // Philox blocks of the coming epilogue are drawn AHEAD of the wait that precedes it (they depend on nothing the tensor
-      // core produces): the generator is a third of an epilogue's instructions and the wait is otherwise idle -- the last
-      // four K slabs' products (~1 500 clk) cannot start before the previous epilogue's last stores.
-      uint4 rk[8] = {};
-      auto draw = [&](int nblk, uint32_t pass, uint32_t layer, uint32_t j0) {
-#pragma unroll
-        for (int b = 0; b < 8; ++b)
-          if (b < nblk) rk[b] = Philox::gen_rk(dp.rk, s_lo, s_hi, pass, (layer << 16) | ((j0 >> 3) + b));
-#pragma unroll
-        for (int b = 0; b < 8; ++b)
-          if (b < nblk) asm volatile("" : "+r"(rk[b].x), "+r"(rk[b].y), "+r"(rk[b].z), "+r"(rk[b].w));   // pin before the wait
-      };
-      const bool drawn = kPredraw && drop_on && !inj;           // masks come from Philox, drawn ahead
-      if (drawn && !eval_item) draw(8, static_cast<uint32_t>(dp.pass_offset + t0), 0u, static_cast<uint32_t>(64 * q));
 
       float mean = 0.f, m2 = 0.f, slv = 0.f;
 #pragma unroll 1
@@ -387,109 +434,119 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
         const bool active = drop_on && !eval_pass && (!inj || valid);
         const uint32_t pass = static_cast<uint32_t>(dp.pass_offset + t);
         // ---- stage the masked layer-0 activations as the first A operand
-        {
-          float4 cur[4], nxt[4];
+        RTL_KIND(100); RTL(1); RTL(2); RTL(3);
+        if constexpr (kPair) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) cur[e] = ld_cg4(my_a0 + static_cast<size_t>(16 * q + e) * (kRT * 4));
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (j < 3) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) nxt[e] = ld_cg4(my_a0 + static_cast<size_t>(16 * q + 4 * (j + 1) + e) * (kRT * 4));
-            }
-            float v[16] = {cur[0].x, cur[0].y, cur[0].z, cur[0].w, cur[1].x, cur[1].y, cur[1].z, cur[1].w,
-                           cur[2].x, cur[2].y, cur[2].z, cur[2].w, cur[3].x, cur[3].y, cur[3].z, cur[3].w};
-            select16(v, active, rk[(2 * j) & 7], rk[(2 * j + 1) & 7], pass, t, 0u, static_cast<uint32_t>(64 * q + 16 * j));
-            emit_slab(v, 4 * q + j);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) cur[e] = nxt[e];
+          for (int k = 0; k < 8; ++k) {
+            const int c0 = 16 * (8 * pr + k) + 8 * hf;
+            const float4 f0 = my_a0[(c0 >> 2) * kRT], f1 = my_a0[((c0 >> 2) + 1) * kRT];
+            float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+            select8(v, active, pass, t, 0u, static_cast<uint32_t>(c0));
+            emit_half(v, c0);
+            if (k & 1) RTL(4 + (k >> 1));
           }
+        } else
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 c0 = my_a0[(16 * q + 4 * j) * kRT], c1 = my_a0[(16 * q + 4 * j + 1) * kRT];
+          const float4 c2 = my_a0[(16 * q + 4 * j + 2) * kRT], c3 = my_a0[(16 * q + 4 * j + 3) * kRT];
+          float v[16] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w};
+          select16(v, active, pass, t, 0u, static_cast<uint32_t>(64 * q + 16 * j));
+          emit_slab(v, 4 * q + j);
+          RTL(4 + j);
         }
+        RTL_NEXT();
         // ---- hidden layers
 #pragma unroll 1
         for (int l = 1; l < L; ++l) {
-          if (drawn && active) draw(8, pass, static_cast<uint32_t>(l), static_cast<uint32_t>(64 * q));
+          RTL_KIND(l); RTL(1);
           wait_done();
-          const uint32_t acc = tlane + acc_sel * 256u + static_cast<uint32_t>(64 * q);
-          acc_sel ^= 1u;
+          RTL(2);
+          float z[64];
+          if constexpr (kPair) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) tc::tmem_ld8(tlane + static_cast<uint32_t>(16 * (8 * pr + k) + 8 * hf), z + 8 * k);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tc::tmem_ld16(tlane + static_cast<uint32_t>(64 * q + 16 * j), z + 16 * j);
+          }
+          release_acc();
+          RTL(3);
           const float* bl = s_b + (l - 1) * kRH + 64 * q;
-          float zb[2][16];
-          if constexpr (kLdPrefetch) tc::tmem_ld16(acc, zb[0]);
-          RES_J_UNROLL
+          if constexpr (kPair) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int c0 = 16 * (8 * pr + k) + 8 * hf;
+              float v[8];
+              tanh8b(z + 8 * k, s_b + (l - 1) * kRH + c0, v);
+              select8(v, active, pass, t, static_cast<uint32_t>(l), static_cast<uint32_t>(c0));
+              emit_half(v, c0);
+              if (k & 1) RTL(4 + (k >> 1));
+            }
+          } else
+#pragma unroll
           for (int j = 0; j < 4; ++j) {
             float v[16];
-            float* z = zb[kLdPrefetch ? (j & 1) : 0];
-            if constexpr (kLdPrefetch) {
-              tc::tmem_wait_ld();
-              if (j < 3) tc::tmem_ld16(acc + 16u * (j + 1), zb[(j + 1) & 1]);
-            } else {
-              tc::tmem_ld16(acc + 16u * j, z);
-              tc::tmem_wait_ld();
-            }
-#pragma unroll
-            for (int g = 0; g < 16; g += 8) {
-              const float4 bA = *reinterpret_cast<const float4*>(bl + 16 * j + g), bB = *reinterpret_cast<const float4*>(bl + 16 * j + g + 4);
-              const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
-              float t8[8];
-              tanh8_prescaled(z + g, bb, t8);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[g + e] = t8[e];
-            }
-            select16(v, active, rk[(2 * j) & 7], rk[(2 * j + 1) & 7], pass, t, static_cast<uint32_t>(l), static_cast<uint32_t>(64 * q + 16 * j));
+            tanh16(z + 16 * j, bl + 16 * j, v);
+            select16(v, active, pass, t, static_cast<uint32_t>(l), static_cast<uint32_t>(64 * q + 16 * j));
             emit_slab(v, 4 * q + j);
+            RTL(4 + j);
           }
+          RTL_NEXT();
         }
         // ---- heads: 128 variance-head units (32 per quarter) + the mean head (column 128)
         float u = 0.f;
         {
-          if (drawn && active) draw(4, pass, static_cast<uint32_t>(L), static_cast<uint32_t>(32 * q));
+          RTL_KIND(200); RTL(1);
           wait_done();
-          const uint32_t acc = tlane + acc_sel * 256u;
-          acc_sel ^= 1u;
-          if (q == 0) {
-            float zz[4];
-            tc::tmem_ld4(acc + static_cast<uint32_t>(kRH / 2), zz);
-            tc::tmem_wait_ld();
-            u = zz[0] + __ldg(net.bp);
+          RTL(2);
+          float z[32], zz[4] = {0.f, 0.f, 0.f, 0.f};
+          if constexpr (kPair) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc::tmem_ld8(tlane + static_cast<uint32_t>(16 * (4 * pr + k) + 8 * hf), z + 8 * k);
+          } else {
+            tc::tmem_ld16(tlane + static_cast<uint32_t>(32 * q), z);
+            tc::tmem_ld16(tlane + static_cast<uint32_t>(32 * q + 16), z + 16);
           }
-          RES_J_UNROLL
+          if (q == 0) tc::tmem_ld4(tlane + static_cast<uint32_t>(kRH / 2), zz);
+          release_acc();
+          RTL(3);
+          u = zz[0] + __ldg(net.bp);
+          if constexpr (kPair) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int c0 = 16 * (4 * pr + k) + 8 * hf;
+              float v[8];
+              tanh8b(z + 8 * k, s_bv0 + c0, v);
+              select8(v, active, pass, t, static_cast<uint32_t>(L), static_cast<uint32_t>(c0));
+              emit_half(v, c0);
+              if (k & 1) RTL(4 + (k >> 1));
+            }
+          } else
+#pragma unroll
           for (int j = 0; j < 2; ++j) {
             const int c0 = 32 * q + 16 * j;
-            float z[16], v[16];
-            tc::tmem_ld16(acc + static_cast<uint32_t>(c0), z);
-            tc::tmem_wait_ld();
-#pragma unroll
-            for (int g = 0; g < 16; g += 8) {
-              const float4 bA = *reinterpret_cast<const float4*>(s_bv0 + c0 + g), bB = *reinterpret_cast<const float4*>(s_bv0 + c0 + g + 4);
-              const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
-              float t8[8];
-              tanh8_prescaled(z + g, bb, t8);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[g + e] = t8[e];
-            }
-            select16(v, active, rk[(2 * j) & 7], rk[(2 * j + 1) & 7], pass, t, static_cast<uint32_t>(L), static_cast<uint32_t>(c0));
+            float v[16];
+            tanh16(z + 16 * j, s_bv0 + c0, v);
+            select16(v, active, pass, t, static_cast<uint32_t>(L), static_cast<uint32_t>(c0));
             emit_slab(v, 2 * q + j);
+            RTL(4 + j);
           }
+          RTL_NEXT();
         }
         // ---- variance layer 1 (64 units, 16 per quarter) + the last dot; thread (row, 0) finishes the sample
         {
-          if (drawn && pi + 1 < n_pass) draw(8, static_cast<uint32_t>(dp.pass_offset + t + 1), 0u, static_cast<uint32_t>(64 * q));   // next pass's layer-0 masks
+          RTL_KIND(300); RTL(1);
           wait_done();
-          const uint32_t acc = tlane + acc_sel * 256u + static_cast<uint32_t>(16 * q);
-          acc_sel ^= 1u;
-          float z[16];
-          tc::tmem_ld16(acc, z);
-          tc::tmem_wait_ld();
+          RTL(2);
+          float z[16], v[16];
+          tc::tmem_ld16(tlane + static_cast<uint32_t>(16 * q), z);
+          release_acc();
+          RTL(3);
+          tanh16(z, s_bv1 + 16 * q, v);
           float part = 0.f;
 #pragma unroll
-          for (int g = 0; g < 16; g += 8) {
-            const float4 bA = *reinterpret_cast<const float4*>(s_bv1 + 16 * q + g), bB = *reinterpret_cast<const float4*>(s_bv1 + 16 * q + g + 4);
-            const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
-            float t8[8];
-            tanh8_prescaled(z + g, bb, t8);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) part = fmaf(s_wv2[16 * q + g + e], t8[e], part);
-          }
+          for (int e = 0; e < 16; ++e) part = fmaf(s_wv2[16 * q + e], v[e], part);
           if (q != 0) {
             s_part[q * kRT + r] = part;
             __threadfence_block();
@@ -509,6 +566,8 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
               slv += lv;
             }
           }
+          RTL(4);
+          RTL_NEXT();
         }
       }
       if (a.mc && valid && q == 0 && C > 1) {
@@ -529,9 +588,9 @@ wide_res_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict_
   if (warp == 0) tc::tmem_dealloc(tb, 512);
 }
 
-constexpr size_t kRSmemBytes = static_cast<size_t>(2) * kRPlane + static_cast<size_t>(kRStages) * kRStageBytes +
-                               (static_cast<size_t>(PINN_MAX_HIDDEN - 1) * kRH + kRH / 2 + 2 * kRNV + 4 * kRT) * sizeof(float);
-
+constexpr size_t kRSmemBytesTs = static_cast<size_t>(kRStages) * kRStageBytes +
+                                 (static_cast<size_t>(PINN_MAX_HIDDEN - 1) * kRH + kRH / 2 + 2 * kRNV + 4 * kRT) * sizeof(float) +
+                                 static_cast<size_t>(kRT) * kRH * sizeof(float);
 // 1: handled; 0: shape not covered (the per-layer GEMM path takes it); -1: error in *err.
 int launch_wide_res(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, const DropParams& dp, const TcOut& out,
                     void* workspace, size_t workspace_bytes, cudaStream_t st, int* err) {
@@ -543,7 +602,7 @@ int launch_wide_res(bool mc, const pinn_net_t* net, const float* x, int64_t n, i
   if (!aligned16(net->Wv0) || !aligned16(net->Wp) || !aligned16(net->Wv1) || !aligned16(x)) return 0;
   if (dp.masks != nullptr && (((net->n_hidden * kRH + kRH / 2) & 7) != 0 || (reinterpret_cast<uintptr_t>(dp.masks) & 7u) != 0)) return 0;
   const int L = net->n_hidden;
-  const ResPlan p = res_plan(L, n);
+  const ResPlan p = res_plan(L);
   if (!workspace || workspace_bytes < p.bytes) { *err = PINN_E_WORKSPACE; return -1; }
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   const float wscale = dp.p > 0.f ? dp.scale : 1.0f;
@@ -556,7 +615,6 @@ int launch_wide_res(bool mc, const pinn_net_t* net, const float* x, int64_t n, i
   split(net->Wv0, kRH / 2, net->Wp, kRNH, kRH, ws + p.off_wh);
   split(net->Wv1, kRNV, nullptr, kRNV, kRH / 2, ws + p.off_wv1);
   a.img_h = ws + p.off_wh; a.img_v1 = ws + p.off_wv1;
-  a.a0 = reinterpret_cast<float*>(ws + p.off_a0);
   const int C = mc ? res_pass_chunks(T) : 1;
   const size_t part_bytes = C > 1 ? static_cast<size_t>(C) * 3 * n * sizeof(float) : 0;
   if (workspace_bytes < p.bytes + part_bytes) { *err = PINN_E_WORKSPACE; return -1; }
@@ -565,14 +623,24 @@ int launch_wide_res(bool mc, const pinn_net_t* net, const float* x, int64_t n, i
   a.L = L; a.T = T; a.mc = mc ? 1 : 0; a.do_eval = (mc && out.pred_mean != nullptr) ? 1 : 0;
   a.inact = dp.p > 0.f ? dp.keep : 1.0f;
   a.no_logvar = (net->flags & PINN_NET_NO_LOGVAR) ? 1 : 0;
-  cudaError_t e = cudaFuncSetAttribute(wide_res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kRSmemBytes));
+  auto kern = wide_res_ts_kernel;
+  const size_t smem_bytes = kRSmemBytesTs;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
   if (e != cudaSuccess) { *err = static_cast<int>(e); return -1; }
   const int64_t items = ((n + kRT - 1) / kRT) * C;
   const int grid = static_cast<int>(items < sm_count() ? items : sm_count());
-  wide_res_kernel<<<grid, kRThreads, kRSmemBytes, st>>>(*net, x, n, dp, a, out);
+  kern<<<grid, kRThreads, smem_bytes, st>>>(*net, x, n, dp, a, out);
   if (C > 1) launch_mc_merge(a.part, n, T, C, out, st);
   *err = static_cast<int>(cudaGetLastError());
   return *err == 0 ? 1 : -1;
 }
 
 }  // namespace pinn
+
+#ifdef PINN_TIMELINE
+extern "C" int pinn_debug_wide_timeline(long long* compute_out, long long* mma_out) {
+  cudaError_t e = cudaMemcpyFromSymbol(compute_out, pinn::g_rtl, sizeof(pinn::g_rtl));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  return static_cast<int>(cudaMemcpyFromSymbol(mma_out, pinn::g_mtl, sizeof(pinn::g_mtl)));
+}
+#endif

@@ -1,5 +1,6 @@
 """Run one kernel a few times (for `ncu -k <name> --launch-skip 2 --launch-count 1 --set full ... python profiles/kernel_once.py <what> [n]`).
-what: res (V|DATA training form), resx (export form), mc (T=50 sweep), train (one train_dnn step), rf (8 stacks)."""
+what: res (V|DATA training form), resx (export form), mc (T=50 sweep), train (one train_dnn step), rf (8 stacks),
+wide (3x256 net, T=10 sweep on the resident-activation kernel; n = 262144)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -9,6 +10,16 @@ from bench import build_problem, LAYERS, P_TRAIN, P_MC, T_PASSES
 
 what = sys.argv[1]
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
+if what == "wide":
+    Xw, Yw, sxw, syw = build_problem(n, 2)
+    torch.manual_seed(0)
+    mw = b200pinn.PhysicsInformedNN(Xw, Yw, [8, 256, 256, 256, 1], sxw, syw, P_TRAIN, True)
+    mw.dnn.eval()
+    for _ in range(4):
+        b200pinn.mc_dropout_device(mw.dnn, mw.x.detach(), 10, P_MC, seed=1234)
+    torch.cuda.synchronize()
+    print("done", what, n)
+    sys.exit(0)
 base = min(n, 1_000_000)
 X, Y, sx, sy = build_problem(base, 2)
 torch.manual_seed(0)

@@ -822,10 +822,14 @@ def test_get_mc_samples_pipelined_host_path_matches_single_launch():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("layers,n,T", [([8, 256, 256, 256, 1], 1, 2), ([8, 256, 256, 256, 1], 129, 3), ([8, 256, 256, 1], 1000, 2),
-                                        ([8, 128, 128, 128, 1], 700, 3), ([8, 256, 256, 256, 256, 256, 256, 1], 300, 2)])
-def test_wide_tensor_core_path_matches_ffma_path(layers, n, T):
-    """Per-layer tcgen05 GEMM path of the 128 / 256-wide nets vs the thread-per-sample FFMA kernels on the same
-    Philox stream: eval forward, train-mode forward and the MC sweep (tile edges, 2..6 hidden layers)."""
+                                        ([8, 128, 128, 128, 1], 700, 3), ([8, 256, 256, 256, 256, 256, 256, 1], 300, 2),
+                                        ([8, 256, 256, 256, 1], 700, 50)])
+@pytest.mark.parametrize("resident", [True, False])
+def test_wide_tensor_core_path_matches_ffma_path(layers, n, T, resident):
+    """Tensor-core paths of the 128 / 256-wide nets vs the thread-per-sample FFMA kernels on the same Philox stream: eval
+    forward, train-mode forward and the MC sweep (tile edges, 2..6 hidden layers).  ``resident``: the resident-activation
+    kernel (csrc/mlp_wide_res.cu, 256-wide only, fp16 hi/lo split; T = 50 runs as four pass chunks) or one tcgen05 3xTF32
+    GEMM launch per layer (csrc/mlp_wide_tc.cu)."""
     import b200pinn
     from b200pinn import kernels as K
     from b200pinn.synthetic import make_scaled_dataset
@@ -842,7 +846,8 @@ def test_wide_tensor_core_path_matches_ffma_path(layers, n, T):
         mc = b200pinn.mc_dropout_device(dnn, xd, T, p, seed=77)
         return [t2n(v) for v in (u0, s0, u1, s1, mc["pred_mean"], mc["a_u"], mc["e_u"])]
 
-    a = run()
+    with K.path_flags(no_wide_resident=not resident):
+        a = run()
     with K.path_flags(no_wide_tc=True):
         b = run()
     # two fp32 evaluations against each other (not against fp64): six 256-wide layers with a near-cancelling

@@ -475,3 +475,37 @@ def test_fused_backward_workspace_is_independent_of_the_batch():
     fused = L.pinn_mlp_bwd_workspace_bytes_flags(64, 3, 8_000_000, 0)
     two = L.pinn_mlp_bwd_workspace_bytes_flags(64, 3, 8_000_000, _abi.NET_NO_FUSED_BWD)
     assert fused < 64 << 20 and two > 8_000_000 * 1900 and L.pinn_mlp_bwd_workspace_bytes(64, 3, 8_000_000) >= two
+
+
+# ------------------------------------------------------------------ 256-wide nets: resident-activation kernel (csrc/mlp_wide_res.cu)
+def test_wide_resident_sweep_is_shard_invariant_and_matches_the_gemm_path():
+    """The reference's own Layers (01:2139) on the resident-activation kernel: (i) a T = 50 sweep (four pass chunks, merged
+    in order) is bitwise independent of how the samples are sharded -- the chunking depends on T alone and the Philox
+    counters on global indices; (ii) it agrees with the per-layer 3xTF32 GEMM path on the same mask stream; (iii) two
+    half-sweeps merged with Chan's update give the whole sweep (pass sharding over GPUs)."""
+    import b200pinn
+    from b200pinn import kernels as K
+    from b200pinn.dist import chan_merge, finalize
+    from b200pinn.synthetic import make_scaled_dataset
+
+    n, T, p = 3000, 50, 0.4
+    x, _, _, _ = make_scaled_dataset(n, seed=2)
+    xd = torch.tensor(x, device=dev())
+    dnn = random_net([8, 256, 256, 256, 1], 8).eval()
+    full = b200pinn.mc_dropout_device(dnn, xd, T, p, seed=1234, raw=True)
+    cut = 1111
+    a = b200pinn.mc_dropout_device(dnn, xd[:cut], T, p, seed=1234, raw=True)
+    b = b200pinn.mc_dropout_device(dnn, xd[cut:].contiguous(), T, p, seed=1234, sample_offset=cut, raw=True)
+    for k in ("pred_mean", "a_u", "e_u", "mean", "m2", "sum_logvar"):
+        assert torch.equal(full[k], torch.cat([a[k], b[k]])), k
+    with K.path_flags(no_wide_resident=True):
+        g = b200pinn.mc_dropout_device(dnn, xd, T, p, seed=1234, raw=True)
+    for k in ("pred_mean", "a_u", "e_u", "mean", "sum_logvar"):
+        assert nrel(t2n(full[k]), t2n(g[k])) < MC_TOL, k
+    h1 = b200pinn.mc_dropout_device(dnn, xd, T // 2, p, seed=1234, raw=True)
+    h2 = b200pinn.mc_dropout_device(dnn, xd, T - T // 2, p, seed=1234, pass_offset=T // 2, raw=True)
+    cnt, mean, m2, slv = chan_merge(T // 2, h1["mean"], h1["m2"], h1["sum_logvar"], T - T // 2, h2["mean"], h2["m2"], h2["sum_logvar"])
+    au, eu = finalize(cnt, m2, slv)
+    assert nrel(t2n(mean), t2n(full["mean"])) < MC_TOL and nrel(t2n(eu), t2n(full["e_u"])) < MC_TOL
+    assert nrel(t2n(au), t2n(full["a_u"])) < MC_TOL
+    assert float(full["e_u"].min()) > 0
