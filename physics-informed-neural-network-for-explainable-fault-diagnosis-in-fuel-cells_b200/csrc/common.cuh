@@ -235,7 +235,9 @@ PINN_D float tanh_pre(float a) {       // a = kTanhArg * x
 // instructions.  The arguments are clamped at 2^40 (tanh is 1.0f to the last bit from 2^25 on) so that the product of the
 // two denominators cannot overflow; the extra product and multiply leave the absolute error within the same 3e-7.
 // Measured (profiles/r2_wide_res_ab4.log): 64-wide sweep T = 1000 x N = 1M 201.5 -> 187.4 ms; no gain for the fused
-// training kernel or the 256-wide kernel (neither is bound by the XU pipe), which keep the two-reciprocal form.
+// training kernel or the 256-wide kernel (neither is bound by the XU pipe), which keep the two-reciprocal form; four
+// activations on one reciprocal (5 MUFU per four, five more multiplies) came out 1.5 % SLOWER than the pair form
+// (profiles/r2_ab_k4_quad.log).
 template <bool PAIR = false>
 PINN_D float2 tanh_pre2(float2 a) {     // a = kTanhArg * x, two lanes
   if constexpr (PAIR) {

@@ -441,9 +441,10 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
             const float* bv1 = smem + lay.bv1;
             const float* Wv2 = smem + lay.Wv2;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              const float a1 = tanh_pre((part[k] + p1[k]) + bv1[k]);
-              vraw = fmaf(Wv2[k], a1, vraw);
+            for (int k = 0; k < 16; k += 2) {
+              const float2 a1 = tanh_pre2<true>(make_float2((part[k] + p1[k]) + bv1[k], (part[k + 1] + p1[k + 1]) + bv1[k + 1]));
+              vraw = fmaf(Wv2[k], a1.x, vraw);
+              vraw = fmaf(Wv2[k + 1], a1.y, vraw);
             }
             const float lv = logvar_out(vraw, (net.flags & PINN_NET_NO_LOGVAR) != 0);
             if (!MC) {
