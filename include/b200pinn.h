@@ -62,8 +62,10 @@ enum { /* pinn_net_t.flags */
                                head receives no gradient and the aleatoric loss reduces to 0.5 * MSE             */
   PINN_NET_NO_FUSED_BWD = 64, /* ablation / tests: 64-wide backward as the two-kernel form (K2a + row table + K2b)
                                instead of the one-kernel form with on-chip weight gradients                      */
-  PINN_NET_NO_WIDE_RESIDENT = 128 /* ablation / tests: 256-wide forward / MC sweep as one GEMM launch per layer
+  PINN_NET_NO_WIDE_RESIDENT = 128, /* ablation / tests: 256-wide forward / MC sweep as one GEMM launch per layer
                                (activation planes in HBM) instead of the resident-activation kernel             */
+  PINN_NET_NO_TMA_INPUT = 256 /* ablation / tests: the tensor-core forward / MC kernels load their input tiles with
+                               plain global loads instead of TMA tensor-map copies                               */
 };
 
 /* Dropout control.  p == 0 means eval mode.  With masks == NULL the keep mask of

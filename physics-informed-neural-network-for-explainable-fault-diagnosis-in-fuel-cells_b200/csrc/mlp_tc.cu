@@ -37,6 +37,7 @@
 #include "net.cuh"
 #include "tc.cuh"
 #include "tc_api.cuh"
+#include <string.h>
 
 namespace pinn {
 
@@ -99,13 +100,19 @@ PINN_D void bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r
 template <bool MC, bool INJ, bool CH>      // CH: the sweep is cut into pass chunks (long sweeps only; C = 1 folds away otherwise)
 __global__ void __launch_bounds__(kTcThreads, 1)
 mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t n, int T, const __grid_constant__ DropParams dp,
-              TcOut out, int chunks, float* __restrict__ part) {
+              TcOut out, int chunks, float* __restrict__ part, const __grid_constant__ CUtensorMap xmap, int use_tma) {
   constexpr int H = kTcH, HH = kTcH / 2;
   constexpr uint32_t LBO_B = H * 16, LBO_H = kHeadN * 16;
   extern __shared__ __align__(1024) float smem[];
   __shared__ __align__(8) uint64_t ready[2][4], done[2];     // ready[group][chunk]: one barrier per hand-over of a layer, so no
                                                               // thread can arrive twice on a barrier within one of its phases
   __shared__ uint32_t tmem_base_s;
+  // input tiles staged by TMA (tensor map of x, [128 rows x 8 features] box, rows past n zero-filled): per group two 4 KB
+  // buffers behind the resident weights (use_tma = their byte offset; < 0 when the seven-layer net leaves no room), the
+  // NEXT work item's tile is requested while the current one runs its passes
+  __shared__ __align__(8) uint64_t xbar[2][2];
+  float (*const xs)[2][kTcTile * PINN_N_IN] =
+      reinterpret_cast<float (*)[2][kTcTile * PINN_N_IN]>(reinterpret_cast<unsigned char*>(smem) + (use_tma >= 0 ? use_tma : 0));
   const int L = lay.L, tid = threadIdx.x, row = tid & 127;
   const int warp = tc::uniform_warp_idx(), grp = (warp >> 3) & 1, half = (warp >> 2) & 1;  // warp-uniform roles
   const bool mma_warp = warp >= 16;
@@ -120,6 +127,7 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
     for (int c = 0; c < 4; ++c) { tc::mbar_init(&ready[0][c], 256); tc::mbar_init(&ready[1][c], 256); }
     tc::mbar_init(&done[0], 1);
     tc::mbar_init(&done[1], 1);
+    for (int g = 0; g < 2; ++g) { tc::mbar_init(&xbar[g][0], 1); tc::mbar_init(&xbar[g][1], 1); }
     tc::fence_mbar_init();
   }
   __syncwarp();
@@ -282,7 +290,15 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
 
     // tile -> (CTA, group): group 0 of every CTA first, then group 1: up to one tile per SM every tile runs alone (a lone
     // tile finishes ~1.4x sooner than a tile of an interleaved pair; pairing only buys throughput once all SMs are busy)
-    for (int64_t item = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(grp) * gridDim.x; item < n_tiles * C; item += static_cast<int64_t>(gridDim.x) * 2) {
+    const int64_t item0 = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(grp) * gridDim.x, item_step = static_cast<int64_t>(gridDim.x) * 2;
+    const bool x_leader = use_tma >= 0 && (tid & 255) == 0;          // one thread per group requests the tiles
+    auto request_x = [&](int64_t it, int buf) {
+      tc::mbar_expect_tx(&xbar[grp][buf], kTcTile * PINN_N_IN * sizeof(float));
+      tc::tma_load_2d(xs[grp][buf], &xmap, 0, static_cast<int>((it / C) * kTcTile), &xbar[grp][buf]);
+    };
+    if (x_leader && item0 < n_tiles * C) request_x(item0, 0);
+    uint32_t xcount = 0;
+    for (int64_t item = item0; item < n_tiles * C; item += item_step, ++xcount) {
       const int64_t tile = item / C;
       const int chunk = static_cast<int>(item % C), t0 = chunk * Tc;
       const bool eval_item = do_eval && chunk == 0;
@@ -292,7 +308,14 @@ mlp_tc_kernel(pinn_net_t net, TcLayout lay, const float* __restrict__ x, int64_t
       // layer 0 (pass-invariant): this thread's 32 columns -> tensor memory
       {
         float xr[PINN_N_IN];
-        if (valid) {
+        if (use_tma >= 0) {
+          const int buf = static_cast<int>(xcount & 1u);
+          if (x_leader && item + item_step < n_tiles * C) request_x(item + item_step, buf ^ 1);    // that buffer was last read one item ago
+          tc::mbar_wait(&xbar[grp][buf], (xcount >> 1) & 1u);
+          const float4* px = reinterpret_cast<const float4*>(xs[grp][buf] + row * PINN_N_IN);
+          const float4 q0 = px[0], q1 = px[1];
+          xr[0] = q0.x; xr[1] = q0.y; xr[2] = q0.z; xr[3] = q0.w; xr[4] = q1.x; xr[5] = q1.y; xr[6] = q1.z; xr[7] = q1.w;
+        } else if (valid) {
           const float4* px = reinterpret_cast<const float4*>(x + s * PINN_N_IN);
           float4 q0 = __ldg(px), q1 = __ldg(px + 1);
           xr[0] = q0.x; xr[1] = q0.y; xr[2] = q0.z; xr[3] = q0.w; xr[4] = q1.x; xr[5] = q1.y; xr[6] = q1.z; xr[7] = q1.w;
@@ -524,6 +547,24 @@ void launch_mc_merge(const float* part, int64_t n, int T, int C, const TcOut& ou
   mc_merge_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(part, n, T, C, out);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+bool make_x_tensor_map(CUtensorMap* map, const float* x, int64_t n) {
+  using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) fn = nullptr;
+    return reinterpret_cast<EncodeFn>(fn);
+  }();
+  if (encode == nullptr || !aligned16(x) || n <= 0 || n >= (static_cast<int64_t>(1) << 31) - kTcTile) return false;
+  const cuuint64_t dims[2] = {PINN_N_IN, static_cast<cuuint64_t>(n)};
+  const cuuint64_t strides[1] = {PINN_N_IN * sizeof(float)};
+  const cuuint32_t box[2] = {PINN_N_IN, kTcTile}, estr[2] = {1, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int launch_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, const DropParams& dp, const TcOut& out,
               cudaStream_t st, int* err, void* workspace, size_t workspace_bytes) {
   *err = 0;
@@ -539,10 +580,17 @@ int launch_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, 
   const int64_t want = tiles * C;              // one CTA per work item until the SMs run out, then two items in flight per CTA
   const int grid = static_cast<int>(want < sm_count() ? (want > 0 ? want : 1) : sm_count());
   const bool inj = dp.p > 0.f && dp.masks != nullptr;
+  alignas(64) CUtensorMap xmap;
+  memset(&xmap, 0, sizeof(xmap));
+  // the TMA-staged input tiles (2 groups x 2 buffers x 4 KB) sit behind the resident weights when they fit
+  const size_t xs_off = (smem + 127) & ~static_cast<size_t>(127), xs_bytes = static_cast<size_t>(4) * kTcTile * PINN_N_IN * sizeof(float);
+  int use_tma = -1;
+  if (!(net->flags & PINN_NET_NO_TMA_INPUT) && xs_off + xs_bytes <= 226 * 1024 && make_x_tensor_map(&xmap, x, n)) use_tma = static_cast<int>(xs_off);
+  const size_t smem_launch = use_tma >= 0 ? xs_off + xs_bytes : smem;
   auto go = [&](auto kern) -> cudaError_t {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_launch));
     if (e != cudaSuccess) return e;
-    kern<<<grid, kTcThreads, smem, st>>>(*net, lay, x, n, T, dp, out, C, static_cast<float*>(workspace));
+    kern<<<grid, kTcThreads, smem_launch, st>>>(*net, lay, x, n, T, dp, out, C, static_cast<float*>(workspace), xmap, use_tma);
     return cudaSuccess;
   };
   if (C > 1 && (workspace == nullptr || workspace_bytes < static_cast<size_t>(C) * 3 * n * sizeof(float))) { *err = PINN_E_WORKSPACE; return -1; }

@@ -32,6 +32,7 @@
 // and pre-drawn Philox blocks, a prefetched tcgen05.ld, per-warp arrivals or a deeper ring moved nothing -- what is left
 // is the tensor pipe idling at the start of each epilogue until the first K slab of the next layer is ready.
 #include <cuda_fp16.h>
+#include <string.h>
 #include "net.cuh"
 #include "tc.cuh"
 #include "tc_api.cuh"
@@ -161,9 +162,10 @@ __device__ long long g_mtl[512][20];
 
 __global__ void __launch_bounds__(kRThreads, 1)
 wide_res_ts_kernel(const __grid_constant__ pinn_net_t net, const float* __restrict__ x, int64_t n, const __grid_constant__ DropParams dp,
-                   const __grid_constant__ ResArgs a, TcOut out) {
+                   const __grid_constant__ ResArgs a, TcOut out, const __grid_constant__ CUtensorMap xmap, int use_tma) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) uint64_t full[kRStages], empty[kRStages], ready[16], done, accfree;
+  __shared__ __align__(8) uint64_t full[kRStages], empty[kRStages], ready[16], done, accfree, xbar;
+  __shared__ __align__(128) float xs[kRT * PINN_N_IN];      // the work item's input tile, staged by TMA (tensor map of x)
   __shared__ uint32_t tmem_base_s;
   unsigned char* const ring = smem;
   float* const fsm = reinterpret_cast<float*>(ring + kRStages * kRStageBytes);
@@ -181,6 +183,7 @@ wide_res_ts_kernel(const __grid_constant__ pinn_net_t net, const float* __restri
     for (int c = 0; c < 16; ++c) tc::mbar_init(&ready[c], kPair ? 256 : 128);
     tc::mbar_init(&done, 1);
     tc::mbar_init(&accfree, kRComputeWarps * 32);
+    tc::mbar_init(&xbar, 1);
     tc::fence_mbar_init();
   }
   __syncwarp();
@@ -292,7 +295,7 @@ wide_res_ts_kernel(const __grid_constant__ pinn_net_t net, const float* __restri
     float4* const my_a0 = a0s + r;
     const bool drop_on = dp.p > 0.f, inj = dp.masks != nullptr;
     const int Dm = L * kRH + kRH / 2;
-    uint32_t dpar = 0u;
+    uint32_t dpar = 0u, xpar = 0u;
 
     // 16 masked activations -> packed fp16 pairs in both A planes (8 columns each), then hand the K slab to the MMA warp
     auto emit_slab = [&](const float (&v)[16], int slab) {
@@ -399,7 +402,19 @@ wide_res_ts_kernel(const __grid_constant__ pinn_net_t net, const float* __restri
       // ---- layer 0 (pass-invariant): this thread's 64 columns -> the tile's park in shared memory
       {
         float xr[PINN_N_IN];
-        if (valid) {
+        if (use_tma) {
+          // [128 rows x 8 features] box of the tensor map, rows past n zero-filled; every earlier reader of `xs` has long
+          // passed (it is read once, at the start of an item)
+          if (tid == 0) {
+            tc::mbar_expect_tx(&xbar, kRT * PINN_N_IN * sizeof(float));
+            tc::tma_load_2d(xs, &xmap, 0, static_cast<int>(tile * kRT), &xbar);
+          }
+          tc::mbar_wait(&xbar, xpar);
+          xpar ^= 1u;
+          const float4* px = reinterpret_cast<const float4*>(xs + r * PINN_N_IN);
+          const float4 q0 = px[0], q1 = px[1];
+          xr[0] = q0.x; xr[1] = q0.y; xr[2] = q0.z; xr[3] = q0.w; xr[4] = q1.x; xr[5] = q1.y; xr[6] = q1.z; xr[7] = q1.w;
+        } else if (valid) {
           const float4* px = reinterpret_cast<const float4*>(x + s * PINN_N_IN);
           const float4 q0 = __ldg(px), q1 = __ldg(px + 1);
           xr[0] = q0.x; xr[1] = q0.y; xr[2] = q0.z; xr[3] = q0.w; xr[4] = q1.x; xr[5] = q1.y; xr[6] = q1.z; xr[7] = q1.w;
@@ -629,7 +644,10 @@ int launch_wide_res(bool mc, const pinn_net_t* net, const float* x, int64_t n, i
   if (e != cudaSuccess) { *err = static_cast<int>(e); return -1; }
   const int64_t items = ((n + kRT - 1) / kRT) * C;
   const int grid = static_cast<int>(items < sm_count() ? items : sm_count());
-  kern<<<grid, kRThreads, smem_bytes, st>>>(*net, x, n, dp, a, out);
+  alignas(64) CUtensorMap xmap;
+  memset(&xmap, 0, sizeof(xmap));
+  const int use_tma = (net->flags & PINN_NET_NO_TMA_INPUT) ? 0 : (make_x_tensor_map(&xmap, x, n) ? 1 : 0);
+  kern<<<grid, kRThreads, smem_bytes, st>>>(*net, x, n, dp, a, out, xmap, use_tma);
   if (C > 1) launch_mc_merge(a.part, n, T, C, out, st);
   *err = static_cast<int>(cudaGetLastError());
   return *err == 0 ? 1 : -1;

@@ -80,6 +80,12 @@ PINN_D void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint6
                ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// TMA tiled copy global -> shared through a tensor map: box at (c0 = innermost coordinate, c1) of a 2-D tensor
+PINN_D void tma_load_2d(void* dst_smem, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
 // generic-proxy smem writes -> visible to the async proxy (UMMA operand reads)
 PINN_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

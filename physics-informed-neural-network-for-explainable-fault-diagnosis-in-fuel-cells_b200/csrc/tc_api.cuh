@@ -1,8 +1,13 @@
 // tc_api.cuh -- entry of the tensor-core path (mlp_tc.cu), called from mlp_fwd_mc.cu.
 #pragma once
+#include <cuda.h>
 #include "common.cuh"
 
 namespace pinn {
+// TMA tensor map of the input matrix x [n][8] fp32 (row-major) with a [128 rows x 8 features] box: one
+// `cp.async.bulk.tensor.2d` stages a tile's 4 KB of inputs into shared memory, rows past n arrive as zeros (mlp_tc.cu).
+// false: no map (x not 16-byte aligned, n >= 2^31, or the driver entry point is missing) -- the kernels then load x with LDG.
+bool make_x_tensor_map(CUtensorMap* map, const float* x, int64_t n);
 struct TcOut {
   float* u; float* s;                                                                   // K1
   float* pred_mean; float* a_u; float* e_u; float* raw_mean; float* raw_m2; float* raw_slv;  // K4

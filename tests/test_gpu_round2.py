@@ -509,3 +509,31 @@ def test_wide_resident_sweep_is_shard_invariant_and_matches_the_gemm_path():
     assert nrel(t2n(mean), t2n(full["mean"])) < MC_TOL and nrel(t2n(eu), t2n(full["e_u"])) < MC_TOL
     assert nrel(t2n(au), t2n(full["a_u"])) < MC_TOL
     assert float(full["e_u"].min()) > 0
+
+
+@pytest.mark.parametrize("layers,n,T", [(LAYERS, 1, 2), (LAYERS, 129, 3), (LAYERS, 40000, 4), ([8, 256, 256, 256, 1], 300, 2),
+                                        ([8, 256, 256, 256, 1], 20000, 14)])
+def test_tma_staged_input_tiles_match_plain_loads(layers, n, T):
+    """The tensor-core forward / MC kernels stage a tile's inputs with one TMA tensor-map copy ([128 rows x 8 features] box,
+    rows past n zero-filled, the next item's tile requested a work item ahead); PINN_NET_NO_TMA_INPUT keeps the plain
+    global loads.  Same arithmetic on the same values: bitwise equal results, ragged last tiles included."""
+    import b200pinn
+    from b200pinn import kernels as K
+    from b200pinn.synthetic import make_scaled_dataset
+
+    x, _, _, _ = make_scaled_dataset(max(n, 64), seed=5)
+    xd = torch.tensor(x[:n], device=dev())
+    dnn = random_net(layers, 3).eval()
+    net = K.net_from_module(dnn)
+
+    def run():
+        u0, s0 = K.mlp_forward(net, xd)
+        u1, s1 = K.mlp_forward(net, xd, K.make_dropout(0.4, seed=9, pass_offset=2))
+        mc = b200pinn.mc_dropout_device(dnn, xd, T, 0.4, seed=11, raw=True)
+        return [u0, s0, u1, s1, mc["pred_mean"], mc["a_u"], mc["e_u"], mc["mean"], mc["m2"]]
+
+    a = run()
+    with K.path_flags(no_tma_input=True):
+        b = run()
+    for i, (u, v) in enumerate(zip(a, b)):
+        assert torch.equal(u, v), i
