@@ -33,10 +33,31 @@ PIPELINE_MIN_ROWS = 1 << 16      # host inputs at least this long are swept in c
 PIPELINE_CHUNKS = 4
 
 
+def _pipeline_chunks(n: int, wave: int):
+    """Row ranges of the host pipeline.  A chunk is a whole number of "waves" (two 128-row tiles per SM) so that no chunk
+    but the last ends on a partial wave; long inputs start with a short chunk (2 waves, then 4) -- the first chunk's upload
+    and the last chunk's download are the only copies that are not hidden behind a sweep."""
+    waves = -(-n // wave)
+    if waves <= 2 * PIPELINE_CHUNKS:
+        sizes = [max(1, -(-waves // PIPELINE_CHUNKS))] * PIPELINE_CHUNKS
+    else:
+        rest = waves - 6
+        k = PIPELINE_CHUNKS - 1
+        sizes = [2, 4] + [rest // k + (1 if i < rest % k else 0) for i in range(k)]
+    out, lo = [], 0
+    for w in sizes:
+        if lo >= n:
+            break
+        hi = min(n, lo + w * wave)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
 def _mc_host_pipelined(dnn, X, mc_times, dropout, pass_offset, dev):
     """Host tensor in, host arrays out, for long inputs: the rows are cut into a few chunks whose
-    H2D copy, sweep (K4) and D2H copy run on three streams, so only the first chunk's upload and the
-    last chunk's download are exposed.  Philox counters are keyed on the global row index
+    H2D copy, sweep (K4, alternating between two streams) and D2H copy overlap, so only the first chunk's
+    upload and the last chunk's download are exposed.  Philox counters are keyed on the global row index
     (``sample_offset``), so the result is identical to the single-launch sweep."""
     n = X.shape[0]
     Xc = X.detach()
@@ -46,28 +67,31 @@ def _mc_host_pipelined(dnn, X, mc_times, dropout, pass_offset, dev):
     xd = torch.empty(n, Xc.shape[1], device=dev, dtype=torch.float32)
     cur = torch.cuda.current_stream(dev)
     if dev not in _SIDE_STREAMS:
-        _SIDE_STREAMS[dev] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
-    s_in, s_out = _SIDE_STREAMS[dev]
+        _SIDE_STREAMS[dev] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+    s_in, s_out, s_alt = _SIDE_STREAMS[dev]
     s_in.wait_stream(cur)
-    # chunk = a whole number of "waves" (two 128-row tiles per SM) so that no chunk but the last ends on a partial wave
-    wave = 256 * torch.cuda.get_device_properties(dev).multi_processor_count
-    step = max(wave, (-(-n // PIPELINE_CHUNKS) + wave - 1) // wave * wave)
-    for lo in range(0, n, step):
-        hi = min(n, lo + step)
+    s_alt.wait_stream(cur)
+    for k, (lo, hi) in enumerate(_pipeline_chunks(n, 256 * torch.cuda.get_device_properties(dev).multi_processor_count)):
         with torch.cuda.stream(s_in):
             xd[lo:hi].copy_(Xc[lo:hi], non_blocking=True)
             up = torch.cuda.Event()
             up.record(s_in)
-        cur.wait_event(up)
-        out = mc_dropout_device(dnn, xd[lo:hi], mc_times, dropout, sample_offset=lo, pass_offset=pass_offset)
-        done = torch.cuda.Event()
-        done.record(cur)
+        # consecutive sweeps alternate between two streams: nothing orders them, so the next chunk's CTAs take over the SMs
+        # the current one's last wave leaves idle (a sweep's CTAs do not finish together)
+        s_k = cur if k % 2 == 0 else s_alt
+        with torch.cuda.stream(s_k):
+            s_k.wait_event(up)
+            out = mc_dropout_device(dnn, xd[lo:hi], mc_times, dropout, sample_offset=lo, pass_offset=pass_offset)
+            done = torch.cuda.Event()
+            done.record(s_k)
         with torch.cuda.stream(s_out):
             s_out.wait_event(done)
-            for i, k in enumerate(("pred_mean", "a_u", "e_u")):
-                host[i, lo:hi].copy_(out[k], non_blocking=True)
-                out[k].record_stream(s_out)
+            for i, name in enumerate(("pred_mean", "a_u", "e_u")):
+                host[i, lo:hi].copy_(out[name], non_blocking=True)
+                out[name].record_stream(s_out)
     xd.record_stream(s_in)
+    xd.record_stream(s_alt)
+    cur.wait_stream(s_alt)
     s_out.synchronize()
     return host[0].numpy(), host[1].numpy(), host[2].numpy()
 

@@ -222,3 +222,17 @@ def test_dropin_install_rebinds_reference_names():
     assert ref.create_comprehensive_results_array_v2 is b200pinn.create_comprehensive_results_array_v2
     with pytest.raises(ValueError):
         b200pinn.install(ref, "Z")
+
+
+@pytest.mark.parametrize("n", [1, 37887, 37888, 65536, 100000, 300000, 1000000, 8000001])
+def test_host_pipeline_chunks_cover_the_rows_in_whole_waves(n):
+    """get_MC_samples' host pipeline (mc._pipeline_chunks): the chunks tile [0, n) without gaps, every chunk but the last
+    is a whole number of waves, and long inputs start with a short chunk so that little of the first upload is exposed."""
+    from b200pinn.mc import _pipeline_chunks
+
+    wave = 256 * 148
+    c = _pipeline_chunks(n, wave)
+    assert c[0][0] == 0 and c[-1][1] == n and all(a[1] == b[0] for a, b in zip(c, c[1:]))
+    assert all((hi - lo) % wave == 0 and hi > lo for lo, hi in c[:-1]) and c[-1][1] > c[-1][0]
+    if n >= 9 * wave:
+        assert c[0][1] - c[0][0] == 2 * wave and len(c) <= 5
