@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PINN_ABI_VERSION 4
+#define PINN_ABI_VERSION 5
 #define PINN_N_IN 8        /* operating-condition features, 01:136-137 */
 #define PINN_MAX_HIDDEN 8  /* hidden (tanh) layers supported */
 #define PINN_N_LAMBDA 17   /* lambda_1..4, T1..5, H1..4, O1..4 (01:453-517) */
@@ -95,6 +95,10 @@ int pinn_mlp_fwd(const pinn_net_t* net, const float* x, int64_t n,
                  const pinn_dropout_t* drop, float* out_u, float* out_logvar,
                  void* workspace, size_t workspace_bytes, void* stream);
 size_t pinn_mlp_fwd_workspace_bytes(int32_t width, int32_t n_hidden, int64_t n);
+/* Same for one particular call: `flags` = the pinn_net_t.flags that call will carry.  The function above covers every
+ * path; for the 256-wide nets that means the per-layer GEMM form's operand planes (5 KB per sample), which the default
+ * resident-activation kernel does not need (weight images + 96 B per sample). */
+size_t pinn_mlp_fwd_workspace_bytes_flags(int32_t width, int32_t n_hidden, int64_t n, int32_t flags);
 
 /* K2 -- backward of DNN.forward (autograd of 01:953) with the forward recomputed
  * in-kernel.  Upstream gradients are either given (grad_u, grad_logvar: [n]) or,
@@ -224,6 +228,7 @@ int pinn_mc_dropout(const pinn_net_t* net, const float* x, int64_t n, int32_t T,
                     float* raw_sum_logvar, void* workspace, size_t workspace_bytes,
                     void* stream);
 size_t pinn_mc_workspace_bytes(int32_t width, int32_t n_hidden, int64_t n);
+size_t pinn_mc_workspace_bytes_flags(int32_t width, int32_t n_hidden, int64_t n, int32_t flags);   /* as above, per call */
 
 /* f1 -- export row writer: the 22-column float64 `comprehensive_results` row of
  * create_comprehensive_results_array_v2 (01:1907-2010), incl. the segment-wise centred

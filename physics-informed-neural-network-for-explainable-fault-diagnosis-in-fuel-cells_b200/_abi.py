@@ -13,7 +13,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200pinn.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 N_IN = 8
 MAX_HIDDEN = 8
 N_LAMBDA = 17
@@ -79,6 +79,8 @@ _SIGNATURES = {
     "pinn_mlp_fwd_workspace_bytes": (_sz, [_i32, _i32, _i64]),
     "pinn_mlp_bwd_workspace_bytes": (_sz, [_i32, _i32, _i64]),
     "pinn_mlp_bwd_workspace_bytes_flags": (_sz, [_i32, _i32, _i64, _i32]),
+    "pinn_mlp_fwd_workspace_bytes_flags": (_sz, [_i32, _i32, _i64, _i32]),
+    "pinn_mc_workspace_bytes_flags": (_sz, [_i32, _i32, _i64, _i32]),
     "pinn_mc_workspace_bytes": (_sz, [_i32, _i32, _i64]),
     "pinn_residuals_workspace_bytes": (_sz, [_i64]),
     "pinn_mlp_fwd": (C.c_int, [C.POINTER(PinnNet), _vp, _i64, C.POINTER(PinnDropout), _vp, _vp, _vp, _sz, _vp]),

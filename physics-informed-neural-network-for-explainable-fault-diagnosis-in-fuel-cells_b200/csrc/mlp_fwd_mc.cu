@@ -184,21 +184,24 @@ static int set_smem(K kernel, size_t bytes) {
 
 using namespace pinn;
 
-extern "C" size_t pinn_mlp_fwd_workspace_bytes(int32_t width, int32_t n_hidden, int64_t n) {
-  Plan p = plan_tps(width, n_hidden, n, 1);
+// ncols = private activation columns per thread of the FFMA path (1 forward, 2 sweep); flags < 0: enough for any path
+static size_t fwd_mc_workspace(int32_t width, int32_t n_hidden, int64_t n, int ncols, int flags) {
+  Plan p = plan_tps(width, n_hidden, n, ncols);
   size_t a = p.scratch_floats * sizeof(float);
-  const size_t b = wide_tc_workspace_bytes(width, n_hidden, n);
+  // a call known to take a tensor-core path of the wide nets does not need the FFMA path's private columns
+  if (flags >= 0 && (width == 128 || width == 256) && !(flags & PINN_NET_NO_WIDE_TC)) a = 0;
+  const size_t b = wide_tc_workspace_bytes(width, n_hidden, n, flags);
   const size_t c = width == 64 ? tc_mc_workspace_bytes(n) : 0;      // per-chunk Welford triples of long sweeps (mlp_tc.cu)
   if (b > a) a = b;
   return c > a ? c : a;
 }
-extern "C" size_t pinn_mc_workspace_bytes(int32_t width, int32_t n_hidden, int64_t n) {
-  Plan p = plan_tps(width, n_hidden, n, 2);
-  size_t a = p.scratch_floats * sizeof(float);
-  const size_t b = wide_tc_workspace_bytes(width, n_hidden, n);
-  const size_t c = width == 64 ? tc_mc_workspace_bytes(n) : 0;      // per-chunk Welford triples of long sweeps (mlp_tc.cu)
-  if (b > a) a = b;
-  return c > a ? c : a;
+extern "C" size_t pinn_mlp_fwd_workspace_bytes(int32_t width, int32_t n_hidden, int64_t n) { return fwd_mc_workspace(width, n_hidden, n, 1, -1); }
+extern "C" size_t pinn_mc_workspace_bytes(int32_t width, int32_t n_hidden, int64_t n) { return fwd_mc_workspace(width, n_hidden, n, 2, -1); }
+extern "C" size_t pinn_mlp_fwd_workspace_bytes_flags(int32_t width, int32_t n_hidden, int64_t n, int32_t flags) {
+  return fwd_mc_workspace(width, n_hidden, n, 1, flags < 0 ? 0 : flags);
+}
+extern "C" size_t pinn_mc_workspace_bytes_flags(int32_t width, int32_t n_hidden, int64_t n, int32_t flags) {
+  return fwd_mc_workspace(width, n_hidden, n, 2, flags < 0 ? 0 : flags);
 }
 
 extern "C" int pinn_mlp_fwd(const pinn_net_t* net, const float* x, int64_t n, const pinn_dropout_t* drop,

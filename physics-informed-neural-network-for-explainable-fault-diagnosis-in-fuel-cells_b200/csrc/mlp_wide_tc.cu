@@ -657,10 +657,12 @@ static WidePlan<H> wide_plan(int L, int64_t n) {
   p.bytes = o;
   return p;
 }
-size_t wide_tc_workspace_bytes(int H, int L, int64_t n) {
+size_t wide_tc_workspace_bytes(int H, int L, int64_t n, int flags) {
   if (n <= 0) return 0;
-  if (H == 256) {           // enough for either 256-wide path (resident-activation kernel: mlp_wide_res.cu)
+  if (flags >= 0 && (flags & PINN_NET_NO_WIDE_TC)) return 0;          // FFMA path: its own scratch only
+  if (H == 256) {           // resident-activation kernel (mlp_wide_res.cu) unless the call opts out; flags < 0: either path
     const size_t a = wide_plan<256>(L, n).bytes, b = wide_res_workspace_bytes(L, n);
+    if (flags >= 0) return (L >= 2 && !(flags & PINN_NET_NO_WIDE_RESIDENT)) ? b : a;
     return a > b ? a : b;
   }
   if (H == 128) return wide_plan<128>(L, n).bytes;

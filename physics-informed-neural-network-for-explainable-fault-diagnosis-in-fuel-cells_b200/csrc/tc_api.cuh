@@ -21,7 +21,9 @@ size_t tc_mc_workspace_bytes(int64_t n);
 // fold per-chunk Welford triples [chunk][3][n] (chunk k = passes [k Tc, (k+1) Tc), Tc = ceil(T / C)) in chunk order and finish the sample
 void launch_mc_merge(const float* part, int64_t n, int T, int C, const TcOut& out, cudaStream_t st);
 // Wide nets (H = 128 / 256) on the tensor cores, one GEMM launch per layer (mlp_wide_tc.cu); same return convention.
-size_t wide_tc_workspace_bytes(int H, int L, int64_t n);
+// flags < 0: enough for either 256-wide path; otherwise what the call carrying these pinn_net_t.flags needs (the resident-
+// activation kernel needs weight images + per-chunk statistics, the per-layer GEMM path 5 KB per sample of operand planes)
+size_t wide_tc_workspace_bytes(int H, int L, int64_t n, int flags = -1);
 int launch_wide_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, const DropParams& dp, const TcOut& out,
                    void* workspace, size_t workspace_bytes, cudaStream_t st, int* err);
 // 256-wide nets, forward / MC sweep with the activations resident on the SM (mlp_wide_res.cu); same return convention.

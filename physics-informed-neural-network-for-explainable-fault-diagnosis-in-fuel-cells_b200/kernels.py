@@ -179,7 +179,7 @@ def mlp_forward(net: Net, x: torch.Tensor, drop: Optional[PinnDropout] = None):
     u = torch.empty(n, device=x.device, dtype=torch.float32)
     s = torch.empty(n, device=x.device, dtype=torch.float32)
     L = _abi.lib()
-    nb = L.pinn_mlp_fwd_workspace_bytes(net.width, net.n_hidden, n)
+    nb = L.pinn_mlp_fwd_workspace_bytes_flags(net.width, net.n_hidden, n, net.flags)
     ws = _workspace("fwd", nb, x.device)
     with torch.cuda.device(x.device):
         check(L.pinn_mlp_fwd(net.ref(), ptr(x), n, C.byref(drop) if drop is not None else None,
@@ -289,7 +289,7 @@ def mc_dropout(net: Net, x: torch.Tensor, T: int, drop: PinnDropout, finalize: b
     if raw:
         out["mean"], out["m2"], out["sum_logvar"] = new(), new(), new()
     L = _abi.lib()
-    nb = L.pinn_mc_workspace_bytes(net.width, net.n_hidden, n)
+    nb = L.pinn_mc_workspace_bytes_flags(net.width, net.n_hidden, n, net.flags)
     ws = _workspace("mc", nb, dev)
     with torch.cuda.device(dev):
         check(L.pinn_mc_dropout(net.ref(), ptr(x), n, int(T), C.byref(drop), ptr(out["pred_mean"]),

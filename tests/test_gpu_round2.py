@@ -537,3 +537,31 @@ def test_tma_staged_input_tiles_match_plain_loads(layers, n, T):
         b = run()
     for i, (u, v) in enumerate(zip(a, b)):
         assert torch.equal(u, v), i
+
+
+def test_per_call_workspace_of_the_wide_paths():
+    """pinn_mc_workspace_bytes_flags: the resident-activation kernel needs the fp16 weight images plus 96 B per sample of
+    per-chunk statistics; the per-layer GEMM form 5 KB per sample of operand planes; the FFMA form its private columns.  The
+    flag-less function covers all of them, and a sweep sized per call runs on each path."""
+    import b200pinn
+    from b200pinn import _abi, kernels as K
+    from b200pinn.synthetic import make_scaled_dataset
+
+    L = _abi.lib()
+    n = 1 << 20
+    res = L.pinn_mc_workspace_bytes_flags(256, 3, n, 0)
+    gemm = L.pinn_mc_workspace_bytes_flags(256, 3, n, _abi.NET_NO_WIDE_RESIDENT)
+    ffma = L.pinn_mc_workspace_bytes_flags(256, 3, n, _abi.NET_NO_WIDE_TC)
+    assert res < 128 * n and gemm > 4096 * n and ffma < gemm
+    assert L.pinn_mc_workspace_bytes(256, 3, n) == max(res, gemm, ffma)
+    assert L.pinn_mc_workspace_bytes_flags(64, 3, n, 0) == L.pinn_mc_workspace_bytes(64, 3, n)
+    x, _, _, _ = make_scaled_dataset(777, seed=3)
+    xd = torch.tensor(x, device=dev())
+    dnn = random_net([8, 256, 256, 256, 1], 4).eval()
+    a = b200pinn.mc_dropout_device(dnn, xd, 3, 0.4, seed=5)
+    with K.path_flags(no_wide_resident=True):
+        b = b200pinn.mc_dropout_device(dnn, xd, 3, 0.4, seed=5)
+    with K.path_flags(no_wide_tc=True):
+        c = b200pinn.mc_dropout_device(dnn, xd, 3, 0.4, seed=5)
+    for k in ("pred_mean", "a_u", "e_u"):
+        assert nrel(t2n(a[k]), t2n(c[k])) < MC_TOL and nrel(t2n(b[k]), t2n(c[k])) < MC_TOL, k
