@@ -151,6 +151,8 @@ PINN_D void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32
 // [after accfree, issue time of every slab, after the last commit].
 __device__ long long g_rtl[2][512][8];
 __device__ long long g_mtl[512][20];
+__device__ long long g_stl[4][8][8];      // fine stamps inside the 8 steps of one hidden epilogue (4th recorded epilogue of each role)
+#define STL(k, j) do { if (tl_on && tl_i == 17) g_stl[tl_w * 2 + (l == 1 ? 0 : 1)][k][j] = clock64(); } while (0)
 #define RTL(k) do { if (tl_on && tl_i < 512) g_rtl[tl_w][tl_i][k] = clock64(); } while (0)
 #define RTL_KIND(v) do { if (tl_on && tl_i < 512) g_rtl[tl_w][tl_i][0] = (v); } while (0)
 #define RTL_NEXT() do { ++tl_i; } while (0)
@@ -158,6 +160,7 @@ __device__ long long g_mtl[512][20];
 #define RTL(k) do {} while (0)
 #define RTL_KIND(v) do {} while (0)
 #define RTL_NEXT() do {} while (0)
+#define STL(k, j) do {} while (0)
 #endif
 
 __global__ void __launch_bounds__(kRThreads, 1)
@@ -493,9 +496,34 @@ wide_res_ts_kernel(const __grid_constant__ pinn_net_t net, const float* __restri
             for (int k = 0; k < 8; ++k) {
               const int c0 = 16 * (8 * pr + k) + 8 * hf;
               float v[8];
+              STL(k, 0);
               tanh8b(z + 8 * k, s_b + (l - 1) * kRH + c0, v);
+#ifdef PINN_TIMELINE
+              asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]));
+#endif
+              STL(k, 1);
               select8(v, active, pass, t, static_cast<uint32_t>(l), static_cast<uint32_t>(c0));
+#ifdef PINN_TIMELINE
+              asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]));
+              STL(k, 2);
+              {
+                uint32_t h[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split_h2(v[2 * e], v[2 * e + 1], h[e], lo[e]);
+                asm volatile("" : "+r"(h[0]), "+r"(h[1]), "+r"(h[2]), "+r"(h[3]), "+r"(lo[0]), "+r"(lo[1]), "+r"(lo[2]), "+r"(lo[3]));
+                STL(k, 3);
+                tc::tmem_st4(a_hi_l + static_cast<uint32_t>(c0 >> 1), reinterpret_cast<const float*>(h));
+                tc::tmem_st4(a_lo_l + static_cast<uint32_t>(c0 >> 1), reinterpret_cast<const float*>(lo));
+                STL(k, 4);
+                tc::tmem_wait_st();
+                STL(k, 5);
+                tc::fence_before_sync();
+                tc::mbar_arrive(&ready[c0 >> 4]);
+                STL(k, 6);
+              }
+#else
               emit_half(v, c0);
+#endif
               if (k & 1) RTL(4 + (k >> 1));
             }
           } else
@@ -661,4 +689,5 @@ extern "C" int pinn_debug_wide_timeline(long long* compute_out, long long* mma_o
   if (e != cudaSuccess) return static_cast<int>(e);
   return static_cast<int>(cudaMemcpyFromSymbol(mma_out, pinn::g_mtl, sizeof(pinn::g_mtl)));
 }
+extern "C" int pinn_debug_wide_steps(long long* out) { return static_cast<int>(cudaMemcpyFromSymbol(out, pinn::g_stl, sizeof(pinn::g_stl))); }
 #endif

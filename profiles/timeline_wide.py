@@ -50,3 +50,19 @@ else:
         r = m[i]
         ph = int(r[0]); ns = 8 if ph == L else 16
         print(f"   ph{ph} {int(r[1] - t0):8d} | " + " ".join(f"{int(r[2 + k] - r[1]):5d}" for k in range(ns)) + f" | {int(r[18] - r[1]):6d}")
+    # fine stamps inside the 8 column steps of one hidden epilogue (record 17 of each stamped warp): tanh | select (Philox) |
+    # fp16 split | tcgen05.st issue | wait::st | fence + arrive
+    sb = (ctypes.c_longlong * (4 * 8 * 8))()
+    lib.pinn_debug_wide_steps.argtypes = [ctypes.c_void_p]
+    if lib.pinn_debug_wide_steps(sb) == 0:
+        st = np.array(sb, dtype=np.int64).reshape(4, 8, 8)
+        for w in range(4):
+            if st[w, 0, 0] == 0:
+                continue
+            print(f" steps of warp {'0' if w < 2 else '12'}, hidden layer {1 + w % 2}: start | tanh select split st wait arrive | gap to next step")
+            for k in range(8):
+                r = st[w, k]
+                d = [int(r[j + 1] - r[j]) for j in range(6)]
+                gap = int(st[w, k + 1, 0] - r[6]) if k < 7 else 0
+                print(f"   step {k}: {int(r[0] - st[w, 0, 0]):6d} | " + " ".join(f"{x:5d}" for x in d) + f" | {gap:5d}")
+
