@@ -126,14 +126,11 @@ struct ResArgs {
 
 // slab issued i-th in a phase whose K slabs were produced by the four column quarters, `spq` slabs each: the quarters
 // work in parallel, so their j-th slabs become ready together
-#ifndef RES_PAIR
-#define RES_PAIR 1
-#endif
-// RES_PAIR: the quarters work as two pairs; thread (row, quarter q) owns the 8-column half (q & 1) of the eight K slabs
-// 8 (q >> 1) .. 8 (q >> 1) + 7, so a pair finishes one K slab per 8-column step: the first slabs of the next layer are
-// ready after an eighth of the epilogue instead of a quarter, and only two slabs' products trail its end instead of four.
-constexpr bool kPair = RES_PAIR != 0;
-PINN_D int res_slab_order(int i, int ns) { return kPair ? (i & 1) * (ns >> 1) + (i >> 1) : (i & 3) * (ns >> 2) + (i >> 2); }
+// K slab issued i-th in a phase: the column quarters work as two pairs, thread (row, quarter q) owning the 8-column half
+// (q & 1) of the K slabs of pair (q >> 1); a pair finishes one slab per 8-column step, so the pairs' slabs alternate.  The
+// first slabs of the next layer are ready after an eighth of the epilogue and only two slabs' products trail its end
+// (whole 16-column steps per quarter: 3.21 vs 3.08 ms).
+PINN_D int res_slab_order(int i, int ns) { return (i & 1) * (ns >> 1) + (i >> 1); }
 
 // D[tmem] (+)= A[tmem, packed fp16 pairs] * B[smem]^T, one K = 16 slab.  Issued by ONE thread.
 PINN_D void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -183,7 +180,7 @@ wide_res_ts_kernel(const __grid_constant__ pinn_net_t net, const float* __restri
   const int tid = threadIdx.x, warp = tc::uniform_warp_idx(), lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < kRStages; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
-    for (int c = 0; c < 16; ++c) tc::mbar_init(&ready[c], kPair ? 256 : 128);
+    for (int c = 0; c < 16; ++c) tc::mbar_init(&ready[c], 256);
     tc::mbar_init(&done, 1);
     tc::mbar_init(&accfree, kRComputeWarps * 32);
     tc::mbar_init(&xbar, 1);
@@ -300,18 +297,8 @@ wide_res_ts_kernel(const __grid_constant__ pinn_net_t net, const float* __restri
     const int Dm = L * kRH + kRH / 2;
     uint32_t dpar = 0u, xpar = 0u;
 
-    // 16 masked activations -> packed fp16 pairs in both A planes (8 columns each), then hand the K slab to the MMA warp
-    auto emit_slab = [&](const float (&v)[16], int slab) {
-      uint32_t h[8], lo[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) split_h2(v[2 * e], v[2 * e + 1], h[e], lo[e]);
-      tc::tmem_st8(a_hi_l + 8u * static_cast<uint32_t>(slab), reinterpret_cast<const float*>(h));
-      tc::tmem_st8(a_lo_l + 8u * static_cast<uint32_t>(slab), reinterpret_cast<const float*>(lo));
-      tc::tmem_wait_st();
-      tc::fence_before_sync();
-      tc::mbar_arrive(&ready[slab]);
-    };
-    // pair form: 8 masked activations = columns [c0, c0 + 8) (one half of K slab c0 / 16)
+    // 8 masked activations = columns [c0, c0 + 8) (one half of K slab c0 / 16) -> packed fp16 pairs in both A planes, then this
+    // thread's arrival on the slab's barrier
     auto emit_half = [&](const float (&v)[8], int c0) {
       uint32_t h[4], lo[4];
 #pragma unroll
@@ -344,28 +331,7 @@ wide_res_ts_kernel(const __grid_constant__ pinn_net_t net, const float* __restri
       const bool valid = s < n;
       const uint64_t sg = static_cast<uint64_t>(dp.sample_offset + s);
       const uint32_t s_lo = static_cast<uint32_t>(sg), s_hi = static_cast<uint32_t>(sg >> 32);
-      // keep-select 16 activations of units [j0, j0 + 16) of dropout layer `layer`
-      auto select16 = [&](float (&v)[16], bool active, uint32_t pass, int tloc, uint32_t layer, uint32_t j0) {
-        if (active) {
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            bool k[8];
-            if (inj) {
-              const uint8_t* mrow = dp.masks + (static_cast<size_t>(tloc) * dp.mask_n + s) * Dm + layer * kRH + j0 + 8 * g;
-              const uint2 mb = *reinterpret_cast<const uint2*>(mrow);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) { k[e] = ((mb.x >> (8 * e)) & 0xffu) != 0; k[4 + e] = ((mb.y >> (8 * e)) & 0xffu) != 0; }
-            } else {
-              keep8_from(Philox::gen_rk(dp.rk, s_lo, s_hi, pass, (layer << 16) | ((j0 >> 3) + g)), dp.thresh_hi, k);
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[8 * g + e] = k[e] ? v[8 * g + e] : 0.f;
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] *= a.inact;
-        }
-      };
+      // keep-select 8 activations of units [j0, j0 + 8) of dropout layer `layer` (one Philox block / 8 injected bytes)
       auto select8 = [&](float (&v)[8], bool active, uint32_t pass, int tloc, uint32_t layer, uint32_t j0) {
         if (active) {
           bool k[8];
@@ -389,19 +355,6 @@ wide_res_ts_kernel(const __grid_constant__ pinn_net_t net, const float* __restri
         const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
         tanh8_prescaled(z, bb, v);
       };
-      // v[0..16) = tanh(z[0..16) + bias)   (biases pre-scaled by 2 log2 e)
-      auto tanh16 = [&](const float* z, const float* bias, float (&v)[16]) {
-#pragma unroll
-        for (int g = 0; g < 16; g += 8) {
-          const float4 bA = *reinterpret_cast<const float4*>(bias + g), bB = *reinterpret_cast<const float4*>(bias + g + 4);
-          const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
-          float t8[8];
-          tanh8_prescaled(z + g, bb, t8);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[g + e] = t8[e];
-        }
-      };
-
       // ---- layer 0 (pass-invariant): this thread's 64 columns -> the tile's park in shared memory
       {
         float xr[PINN_N_IN];
@@ -427,7 +380,7 @@ wide_res_ts_kernel(const __grid_constant__ pinn_net_t net, const float* __restri
         }
 #pragma unroll 1
         for (int i4 = 0; i4 < 16; ++i4) {
-          const int c4 = kPair ? 4 * (8 * pr + (i4 >> 1)) + 2 * hf + (i4 & 1) : 16 * q + i4;      // this thread's i4-th column quad
+          const int c4 = 4 * (8 * pr + (i4 >> 1)) + 2 * hf + (i4 & 1);      // this thread's i4-th column quad
           float o4[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -453,25 +406,14 @@ wide_res_ts_kernel(const __grid_constant__ pinn_net_t net, const float* __restri
         const uint32_t pass = static_cast<uint32_t>(dp.pass_offset + t);
         // ---- stage the masked layer-0 activations as the first A operand
         RTL_KIND(100); RTL(1); RTL(2); RTL(3);
-        if constexpr (kPair) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int c0 = 16 * (8 * pr + k) + 8 * hf;
-            const float4 f0 = my_a0[(c0 >> 2) * kRT], f1 = my_a0[((c0 >> 2) + 1) * kRT];
-            float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-            select8(v, active, pass, t, 0u, static_cast<uint32_t>(c0));
-            emit_half(v, c0);
-            if (k & 1) RTL(4 + (k >> 1));
-          }
-        } else
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 c0 = my_a0[(16 * q + 4 * j) * kRT], c1 = my_a0[(16 * q + 4 * j + 1) * kRT];
-          const float4 c2 = my_a0[(16 * q + 4 * j + 2) * kRT], c3 = my_a0[(16 * q + 4 * j + 3) * kRT];
-          float v[16] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w};
-          select16(v, active, pass, t, 0u, static_cast<uint32_t>(64 * q + 16 * j));
-          emit_slab(v, 4 * q + j);
-          RTL(4 + j);
+        for (int k = 0; k < 8; ++k) {
+          const int c0 = 16 * (8 * pr + k) + 8 * hf;
+          const float4 f0 = my_a0[(c0 >> 2) * kRT], f1 = my_a0[((c0 >> 2) + 1) * kRT];
+          float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+          select8(v, active, pass, t, 0u, static_cast<uint32_t>(c0));
+          emit_half(v, c0);
+          if (k & 1) RTL(4 + (k >> 1));
         }
         RTL_NEXT();
         // ---- hidden layers
@@ -481,17 +423,11 @@ wide_res_ts_kernel(const __grid_constant__ pinn_net_t net, const float* __restri
           wait_done();
           RTL(2);
           float z[64];
-          if constexpr (kPair) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) tc::tmem_ld8(tlane + static_cast<uint32_t>(16 * (8 * pr + k) + 8 * hf), z + 8 * k);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) tc::tmem_ld16(tlane + static_cast<uint32_t>(64 * q + 16 * j), z + 16 * j);
-          }
+          for (int k = 0; k < 8; ++k) tc::tmem_ld8(tlane + static_cast<uint32_t>(16 * (8 * pr + k) + 8 * hf), z + 8 * k);
           release_acc();
           RTL(3);
-          const float* bl = s_b + (l - 1) * kRH + 64 * q;
-          if constexpr (kPair) {
+          {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
               const int c0 = 16 * (8 * pr + k) + 8 * hf;
@@ -526,14 +462,6 @@ wide_res_ts_kernel(const __grid_constant__ pinn_net_t net, const float* __restri
 #endif
               if (k & 1) RTL(4 + (k >> 1));
             }
-          } else
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float v[16];
-            tanh16(z + 16 * j, bl + 16 * j, v);
-            select16(v, active, pass, t, static_cast<uint32_t>(l), static_cast<uint32_t>(64 * q + 16 * j));
-            emit_slab(v, 4 * q + j);
-            RTL(4 + j);
           }
           RTL_NEXT();
         }
@@ -544,36 +472,20 @@ wide_res_ts_kernel(const __grid_constant__ pinn_net_t net, const float* __restri
           wait_done();
           RTL(2);
           float z[32], zz[4] = {0.f, 0.f, 0.f, 0.f};
-          if constexpr (kPair) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc::tmem_ld8(tlane + static_cast<uint32_t>(16 * (4 * pr + k) + 8 * hf), z + 8 * k);
-          } else {
-            tc::tmem_ld16(tlane + static_cast<uint32_t>(32 * q), z);
-            tc::tmem_ld16(tlane + static_cast<uint32_t>(32 * q + 16), z + 16);
-          }
+          for (int k = 0; k < 4; ++k) tc::tmem_ld8(tlane + static_cast<uint32_t>(16 * (4 * pr + k) + 8 * hf), z + 8 * k);
           if (q == 0) tc::tmem_ld4(tlane + static_cast<uint32_t>(kRH / 2), zz);
           release_acc();
           RTL(3);
           u = zz[0] + __ldg(net.bp);
-          if constexpr (kPair) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int c0 = 16 * (4 * pr + k) + 8 * hf;
-              float v[8];
-              tanh8b(z + 8 * k, s_bv0 + c0, v);
-              select8(v, active, pass, t, static_cast<uint32_t>(L), static_cast<uint32_t>(c0));
-              emit_half(v, c0);
-              if (k & 1) RTL(4 + (k >> 1));
-            }
-          } else
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int c0 = 32 * q + 16 * j;
-            float v[16];
-            tanh16(z + 16 * j, s_bv0 + c0, v);
-            select16(v, active, pass, t, static_cast<uint32_t>(L), static_cast<uint32_t>(c0));
-            emit_slab(v, 2 * q + j);
-            RTL(4 + j);
+          for (int k = 0; k < 4; ++k) {
+            const int c0 = 16 * (4 * pr + k) + 8 * hf;
+            float v[8];
+            tanh8b(z + 8 * k, s_bv0 + c0, v);
+            select8(v, active, pass, t, static_cast<uint32_t>(L), static_cast<uint32_t>(c0));
+            emit_half(v, c0);
+            if (k & 1) RTL(4 + (k >> 1));
           }
           RTL_NEXT();
         }
@@ -582,14 +494,17 @@ wide_res_ts_kernel(const __grid_constant__ pinn_net_t net, const float* __restri
           RTL_KIND(300); RTL(1);
           wait_done();
           RTL(2);
-          float z[16], v[16];
+          float z[16], v[8];
           tc::tmem_ld16(tlane + static_cast<uint32_t>(16 * q), z);
           release_acc();
           RTL(3);
-          tanh16(z, s_bv1 + 16 * q, v);
           float part = 0.f;
 #pragma unroll
-          for (int e = 0; e < 16; ++e) part = fmaf(s_wv2[16 * q + e], v[e], part);
+          for (int g = 0; g < 16; g += 8) {
+            tanh8b(z + g, s_bv1 + 16 * q + g, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) part = fmaf(s_wv2[16 * q + g + e], v[e], part);
+          }
           if (q != 0) {
             s_part[q * kRT + r] = part;
             __threadfence_block();
