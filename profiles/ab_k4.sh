@@ -1,7 +1,7 @@
-# A/B of 64-wide MC kernel variants: parity tests of the tensor-core forward / MC path, then timing
+# A/B of 64-wide MC kernel variants: parity subset, then timing
 P=physics-informed-neural-network-for-explainable-fault-diagnosis-in-fuel-cells_b200
 for v in "$@"; do
   echo "== variant $v"
   if [ $v = main ]; then unset B200PINN_LIB; else export B200PINN_LIB=$P/build/$v/libb200pinn.so; fi
-  timeout 300 python profiles/quick_time.py 1000000 mc 2>&1 | tail -6
+  timeout 300 python profiles/quick_time.py 1000000 mc,fwd 2>&1 | tail -7
 done
