@@ -489,6 +489,16 @@ def run_ours(args):
                      "train_tflops_per_gpu": n_w * fl_train / t_wt / 1e12}
         del mw, xw
         torch.cuda.empty_cache()
+    # the reference's own production sweep (01:2139, 01:2156-2158): Layers 3x256, mc_times = 2000, at configs[0]'s N = 20 000
+    torch.manual_seed(0)
+    n_r = 20000
+    mr = b200pinn.PhysicsInformedNN(X[:n_r], Y[:n_r], [8, 256, 256, 256, 1], sx, sy, P_TRAIN, True)
+    mr.dnn.eval()
+    xr_ = mr.x.detach()
+    t_r, _ = timed(lambda: b200pinn.mc_dropout_device(mr.dnn, xr_, 2000, P_MC, seed=seed), 2, 1)
+    wide["3x256"]["mc_T2000_n20000_ms"] = 1e3 * t_r / 2
+    wide["3x256"]["mc_T2000_n20000_sample_passes_per_s"] = n_r * 2000 * 2 / t_r
+    del mr, xr_
     c4 = dict(wide.pop("6x256"))
     c4["what"] = ("configs[3]: 6x256 PINN, data-parallel train_dnn step at 524288 samples per GPU (= batch 4M on 8 GPUs; global batch "
                   "here = n_gpus x 524288), one gradient-bucket exchange (1.49 MB) per step fused into the Adam launch over NVLink "
