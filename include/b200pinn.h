@@ -64,8 +64,10 @@ enum { /* pinn_net_t.flags */
                                instead of the one-kernel form with on-chip weight gradients                      */
   PINN_NET_NO_WIDE_RESIDENT = 128, /* ablation / tests: 256-wide forward / MC sweep as one GEMM launch per layer
                                (activation planes in HBM) instead of the resident-activation kernel             */
-  PINN_NET_NO_TMA_INPUT = 256 /* ablation / tests: the tensor-core forward / MC kernels load their input tiles with
+  PINN_NET_NO_TMA_INPUT = 256, /* ablation / tests: the tensor-core forward / MC kernels load their input tiles with
                                plain global loads instead of TMA tensor-map copies                               */
+  PINN_NET_NO_TC3 = 512     /* ablation / tests: 64-wide forward / MC sweep on the two-group 3xTF32 kernel (mlp_tc.cu)
+                               instead of the three-group fp16-pair kernel (mlp_tc3.cu)                          */
 };
 
 /* Dropout control.  p == 0 means eval mode.  With masks == NULL the keep mask of

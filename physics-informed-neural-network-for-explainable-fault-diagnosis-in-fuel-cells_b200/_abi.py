@@ -23,7 +23,7 @@ FAM_V, FAM_TS, FAM_T, FAM_H, FAM_O, FAM_DATA = 1, 2, 4, 8, 16, 32
 RES_ACCURATE_MATH, RES_NO_MODE_A, RES_NO_MODE_B, RES_NO_CLUSTER = 1, 2, 4, 8
 # pinn_net_t.flags: per-call path selection and model options (the library keeps no process-global switches)
 NET_NO_TC_FWD, NET_NO_TC_BWD, NET_NO_WIDE_TC, NET_PDL_NEVER, NET_PDL_ALWAYS, NET_NO_LOGVAR, NET_NO_FUSED_BWD = 1, 2, 4, 8, 16, 32, 64
-NET_NO_WIDE_RESIDENT, NET_NO_TMA_INPUT = 128, 256
+NET_NO_WIDE_RESIDENT, NET_NO_TMA_INPUT, NET_NO_TC3 = 128, 256, 512
 SUM_NAMES = ["N", "FV2", "EA2", "DATA2", "GA1", "GA2", "GA3", "GB1", "GB2", "GB3",
              "FT2", "FTABS", "GT1", "GT3", "GT5", "FTE2",
              "FH2", "GH1", "GH2", "GH3", "HACT", "HTGT",

@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["mlp_fwd_mc.cu", "mlp_tc.cu", "mlp_tc_bwd.cu", "mlp_wide_tc.cu", "mlp_wide_res.cu", "mlp_bwd.cu", "residuals.cu", "export_rf.cu", "gmm.cu", "adam_misc.cu"]
+SOURCES = ["mlp_fwd_mc.cu", "mlp_tc.cu", "mlp_tc3.cu", "mlp_tc_bwd.cu", "mlp_wide_tc.cu", "mlp_wide_res.cu", "mlp_bwd.cu", "residuals.cu", "export_rf.cu", "gmm.cu", "adam_misc.cu"]
 OUT = os.path.join(HERE, "libb200pinn.so")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]

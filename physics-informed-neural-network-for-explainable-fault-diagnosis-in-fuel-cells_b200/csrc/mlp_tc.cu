@@ -568,6 +568,7 @@ bool make_x_tensor_map(CUtensorMap* map, const float* x, int64_t n) {
 int launch_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, const DropParams& dp, const TcOut& out,
               cudaStream_t st, int* err, void* workspace, size_t workspace_bytes) {
   *err = 0;
+  if (const int r3 = launch_tc3(mc, net, x, n, T, dp, out, st, err, workspace, workspace_bytes); r3 != 0) return r3;
   if ((net->flags & PINN_NET_NO_TC_FWD) || net->width != kTcH || net->n_hidden < 2 || net->n_hidden > PINN_MAX_HIDDEN) return 0;
   for (int l = 1; l < net->n_hidden; ++l)
     if (!aligned16(net->W[l])) return 0;

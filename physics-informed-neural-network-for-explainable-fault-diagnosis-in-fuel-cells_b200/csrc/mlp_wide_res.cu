@@ -31,7 +31,6 @@
 // (58 % of the measured dense bf16 peak) at N = 262 144; a first form with the A planes in shared memory was 2 % slower,
 // and pre-drawn Philox blocks, a prefetched tcgen05.ld, per-warp arrivals or a deeper ring moved nothing -- what is left
 // is the tensor pipe idling at the start of each epilogue until the first K slab of the next layer is ready.
-#include <cuda_fp16.h>
 #include <string.h>
 #include "net.cuh"
 #include "tc.cuh"
@@ -77,15 +76,6 @@ size_t wide_res_workspace_bytes(int L, int64_t n) {
   return n > 0 ? res_plan(L).bytes + static_cast<size_t>(8) * 3 * static_cast<size_t>(n) * sizeof(float) : 0;
 }
 
-// two fp32 -> packed fp16 pair (hi) and the packed fp16 pair of the remainders (lo)
-PINN_D void split_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(a, b);
-  const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-
 // ------------------------------------------------------------------ weight images (once per call)
 // [N x K] matrix whose first `rows_a` rows come from `src_a` ([rows_a][K]), row `rows_a` from `src_b` (or zero), the rest
 // zero; times c; as per-slab [hi | lo] fp16 blocks: byte(n, k) = (k/16) * 64 N + (k%16 / 8) * 16 N + n * 16 + (k%8) * 2.
@@ -103,16 +93,13 @@ __global__ void wide_res_split_kernel(const float* __restrict__ src_a, int rows_
     v0 = __ldg(p); v1 = __ldg(p + 1);
   }
   uint4 h, l;
-  split_h2(v0.x * c, v0.y * c, h.x, l.x); split_h2(v0.z * c, v0.w * c, h.y, l.y);
-  split_h2(v1.x * c, v1.y * c, h.z, l.z); split_h2(v1.z * c, v1.w * c, h.w, l.w);
+  tc::split_h2(v0.x * c, v0.y * c, h.x, l.x); tc::split_h2(v0.z * c, v0.w * c, h.y, l.y);
+  tc::split_h2(v1.x * c, v1.y * c, h.z, l.z); tc::split_h2(v1.z * c, v1.w * c, h.w, l.w);
   unsigned char* p = dst + static_cast<size_t>(k8 >> 1) * res_slab_bytes(N) + (k8 & 1) * (N * 16) + nrow * 16;
   *reinterpret_cast<uint4*>(p) = h;
   *reinterpret_cast<uint4*>(p + N * 32) = l;
 }
 
-PINN_HD constexpr uint32_t make_idesc_f16(int M, int N) {      // D = F32, A = B = F16, both K-major
-  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
-}
 struct ResArgs {
   const unsigned char* img_w[PINN_MAX_HIDDEN];   // hidden layers 1..L-1
   const unsigned char* img_h;                    // heads
@@ -131,16 +118,6 @@ struct ResArgs {
 // first slabs of the next layer are ready after an eighth of the epilogue and only two slabs' products trail its end
 // (whole 16-column steps per quarter: 3.21 vs 3.08 ms).
 PINN_D int res_slab_order(int i, int ns) { return (i & 1) * (ns >> 1) + (i >> 1); }
-
-// D[tmem] (+)= A[tmem, packed fp16 pairs] * B[smem]^T, one K = 16 slab.  Issued by ONE thread.
-PINN_D void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 
 #ifdef PINN_TIMELINE
 // Debug build (profiles/timeline_wide.py): clock stamps of CTA 0 -- compute warps 0 (quarter 0) and 12 (quarter 3), lane 0:
@@ -245,7 +222,7 @@ wide_res_ts_kernel(const __grid_constant__ pinn_net_t net, const float* __restri
       for (int pi = 0, n_pass = item_passes(static_cast<int>(item % C)); pi < n_pass; ++pi)
         for (int ph = 0; ph < n_phase; ++ph) {
           const int N = phase_N(ph), ns = phase_slabs(ph);
-          const uint32_t idesc = make_idesc_f16(kRT, N);
+          const uint32_t idesc = tc::make_idesc_f16(kRT, N);
           const uint32_t lbo_b = static_cast<uint32_t>(N) * 16u;
           // the accumulator is free once every compute thread holds its columns of the previous phase in registers
           if (!first_phase) { tc::mbar_wait(&accfree, fpar); fpar ^= 1u; }
@@ -269,9 +246,9 @@ wide_res_ts_kernel(const __grid_constant__ pinn_net_t net, const float* __restri
               tc::fence_after_sync();
               const uint32_t sw = ring_s + s * kRStageBytes, ac = 8u * static_cast<uint32_t>(slab);
               const uint64_t bh = tc::make_desc(sw, lbo_b, 128), bl = tc::make_desc(sw + static_cast<uint32_t>(N) * 32u, lbo_b, 128);
-              umma_f16_ts(tb, a_lo_t + ac, bh, idesc, i != 0 ? 1u : 0u);      // small terms first: lo*hi, hi*lo, then hi*hi
-              umma_f16_ts(tb, a_hi_t + ac, bl, idesc, 1u);
-              umma_f16_ts(tb, a_hi_t + ac, bh, idesc, 1u);
+              tc::umma_f16_ts(tb, a_lo_t + ac, bh, idesc, i != 0 ? 1u : 0u);      // small terms first: lo*hi, hi*lo, then hi*hi
+              tc::umma_f16_ts(tb, a_hi_t + ac, bl, idesc, 1u);
+              tc::umma_f16_ts(tb, a_hi_t + ac, bh, idesc, 1u);
               tc::umma_commit(&empty[s]);
               if (i == ns - 1) tc::umma_commit(&done);
             }
@@ -302,7 +279,7 @@ wide_res_ts_kernel(const __grid_constant__ pinn_net_t net, const float* __restri
     auto emit_half = [&](const float (&v)[8], int c0) {
       uint32_t h[4], lo[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) split_h2(v[2 * e], v[2 * e + 1], h[e], lo[e]);
+      for (int e = 0; e < 4; ++e) tc::split_h2(v[2 * e], v[2 * e + 1], h[e], lo[e]);
       tc::tmem_st4(a_hi_l + static_cast<uint32_t>(c0 >> 1), reinterpret_cast<const float*>(h));
       tc::tmem_st4(a_lo_l + static_cast<uint32_t>(c0 >> 1), reinterpret_cast<const float*>(lo));
       tc::tmem_wait_st();
@@ -445,7 +422,7 @@ wide_res_ts_kernel(const __grid_constant__ pinn_net_t net, const float* __restri
               {
                 uint32_t h[4], lo[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) split_h2(v[2 * e], v[2 * e + 1], h[e], lo[e]);
+                for (int e = 0; e < 4; ++e) tc::split_h2(v[2 * e], v[2 * e + 1], h[e], lo[e]);
                 asm volatile("" : "+r"(h[0]), "+r"(h[1]), "+r"(h[2]), "+r"(h[3]), "+r"(lo[0]), "+r"(lo[1]), "+r"(lo[2]), "+r"(lo[3]));
                 STL(k, 3);
                 tc::tmem_st4(a_hi_l + static_cast<uint32_t>(c0 >> 1), reinterpret_cast<const float*>(h));

@@ -14,6 +14,7 @@
 // that owns sample `row` writes its 16-byte chunks at  kc*LBO + row*16  -- consecutive
 // lanes hit consecutive 16-byte slots: conflict-free 128-bit stores.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace pinn {
@@ -291,6 +292,31 @@ PINN_D void issue_3xtf32_ts_slabs(uint32_t d_tmem, uint32_t a_hi_t, uint32_t a_l
     umma_tf32_ts(d_tmem, a + 8u * static_cast<uint32_t>(s0), b + static_cast<uint64_t>(s0) * b_step, idesc, (first && term == 0) ? 0u : 1u);
     umma_tf32_ts(d_tmem, a + 8u * static_cast<uint32_t>(s1), b + static_cast<uint64_t>(s1) * b_step, idesc, 1u);
   }
+}
+
+// ------------------------------------------------------------------------------ fp16-pair split (kind::f16 products)
+// a = a_h + a_l with a_h = fp16(a), a_l = fp16(a - a_h): 22 significant bits for O(1) values; the three products
+// a_l*w_h + a_h*w_l + a_h*w_h run as kind::f16 MMAs (twice the tf32 rate, half the operand bytes), fp32 accumulation.
+// two fp32 -> packed fp16 pair (hi) and the packed fp16 pair of the remainders (lo)
+PINN_D void split_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+PINN_HD constexpr uint32_t make_idesc_f16(int M, int N) {      // D = F32, A = B = F16, both K-major
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem, packed fp16 pairs] * B[smem]^T, one K = 16 slab.  Issued by ONE thread.
+PINN_D void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 }  // namespace tc

@@ -15,6 +15,9 @@ struct TcOut {
 // 1: launched on the tcgen05 path; 0: shape not covered (use the FFMA kernels); -1: error in *err.
 int launch_tc(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, const DropParams& dp, const TcOut& out,
               cudaStream_t st, int* err, void* workspace = nullptr, size_t workspace_bytes = 0);
+// Three-group fp16-pair form of the same kernel (mlp_tc3.cu): tried first by launch_tc; same return convention.
+int launch_tc3(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T, const DropParams& dp, const TcOut& out,
+               cudaStream_t st, int* err, void* workspace, size_t workspace_bytes);
 // long sweeps are cut into pass chunks (a function of T alone) whose Welford triples live in the workspace until merged
 int mc_pass_chunks(int T);
 size_t tc_mc_workspace_bytes(int64_t n);

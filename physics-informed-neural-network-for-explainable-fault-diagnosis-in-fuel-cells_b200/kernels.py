@@ -70,23 +70,26 @@ class Net:
 # active: ablation runs and tests route a shape through another kernel family without any state in the library.
 _EXTRA_NET_FLAGS = 0
 _PHASE_FLAGS = 0
+_DEFAULT_CM = None
 
 
 @contextmanager
 def path_flags(no_tc_fwd=False, no_tc_bwd=False, no_wide_tc=False, dependent_launch=None, no_phase_cluster=False,
-               no_fused_bwd=False, no_wide_resident=False, no_tma_input=False):
+               no_fused_bwd=False, no_wide_resident=False, no_tma_input=False, no_tc3=False):
     """``with path_flags(no_tc_fwd=True): ...`` -- inside the block the 64-wide forward / MC sweep run on the FFMA
     kernels (likewise ``no_tc_bwd``, ``no_wide_tc``); ``dependent_launch`` = 0 never / 2 always chain a step's launches
     with programmatic dependent launch (default 1: small batches only); ``no_phase_cluster`` keeps ``scalar_phase`` on
     the cooperative-grid form; ``no_fused_bwd`` runs the 64-wide backward as the two-kernel form (K2a + row table +
     K2b) instead of the one-kernel form; ``no_wide_resident`` runs the 256-wide forward / MC sweep as one GEMM launch
     per layer instead of the resident-activation kernel; ``no_tma_input`` makes the tensor-core forward / MC kernels load
-    their input tiles with plain global loads instead of TMA tensor-map copies."""
+    their input tiles with plain global loads instead of TMA tensor-map copies; ``no_tc3`` keeps the 64-wide forward / MC
+    sweep on the two-group 3xTF32 kernel instead of the three-group fp16-pair kernel."""
     global _EXTRA_NET_FLAGS, _PHASE_FLAGS
     prev = (_EXTRA_NET_FLAGS, _PHASE_FLAGS)
     f = (_abi.NET_NO_TC_FWD if no_tc_fwd else 0) | (_abi.NET_NO_TC_BWD if no_tc_bwd else 0) | \
         (_abi.NET_NO_WIDE_TC if no_wide_tc else 0) | (_abi.NET_NO_FUSED_BWD if no_fused_bwd else 0) | \
-        (_abi.NET_NO_WIDE_RESIDENT if no_wide_resident else 0) | (_abi.NET_NO_TMA_INPUT if no_tma_input else 0)
+        (_abi.NET_NO_WIDE_RESIDENT if no_wide_resident else 0) | (_abi.NET_NO_TMA_INPUT if no_tma_input else 0) | \
+        (_abi.NET_NO_TC3 if no_tc3 else 0)
     if dependent_launch is not None:
         f |= {0: _abi.NET_PDL_NEVER, 1: 0, 2: _abi.NET_PDL_ALWAYS}[int(dependent_launch)]
     _EXTRA_NET_FLAGS |= f
@@ -101,10 +104,12 @@ def path_flags(no_tc_fwd=False, no_tc_bwd=False, no_wide_tc=False, dependent_lau
 def set_default_path_flags(**kw):
     """Non-scoped form of ``path_flags`` for ablation scripts (``profiles/``): replaces the process defaults held in
     this Python module -- the shared library itself has no switches."""
-    global _EXTRA_NET_FLAGS, _PHASE_FLAGS
+    global _EXTRA_NET_FLAGS, _PHASE_FLAGS, _DEFAULT_CM
+    _DEFAULT_CM = None
     _EXTRA_NET_FLAGS = _PHASE_FLAGS = 0
     cm = path_flags(**kw)
-    cm.__enter__()          # never exited: the flags stay until the next call
+    cm.__enter__()          # never exited: the flags stay until the next call ...
+    _DEFAULT_CM = cm        # ... so the generator must stay alive (collecting it would run its `finally` and undo them)
 
 
 def net_from_module(dnn) -> Net:

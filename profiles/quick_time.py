@@ -8,6 +8,8 @@ from b200pinn import _abi, kernels as K
 if os.environ.get("B200PINN_LIB"):        # A/B builds: python -c "...build(extra_flags=[...], out=..., objdir=...)"
     _abi.LIB_PATH = os.environ["B200PINN_LIB"]
 from bench import build_problem, LAYERS, P_TRAIN, P_MC, T_PASSES
+if os.environ.get("B200PINN_NO_TC3"):         # A/B: the two-group 3xTF32 form of the 64-wide forward / MC kernel
+    K.set_default_path_flags(no_tc3=True)
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 what = set(sys.argv[2].split(",")) if len(sys.argv) > 2 else {"mc", "fwd", "train", "res"}

@@ -70,7 +70,7 @@ def test_python_constants_match_header():
                   "PINN_NET_NO_WIDE_TC": abi.NET_NO_WIDE_TC, "PINN_NET_PDL_NEVER": abi.NET_PDL_NEVER,
                   "PINN_NET_PDL_ALWAYS": abi.NET_PDL_ALWAYS, "PINN_NET_NO_LOGVAR": abi.NET_NO_LOGVAR,
                   "PINN_NET_NO_FUSED_BWD": abi.NET_NO_FUSED_BWD, "PINN_NET_NO_WIDE_RESIDENT": abi.NET_NO_WIDE_RESIDENT,
-                  "PINN_NET_NO_TMA_INPUT": abi.NET_NO_TMA_INPUT}
+                  "PINN_NET_NO_TMA_INPUT": abi.NET_NO_TMA_INPUT, "PINN_NET_NO_TC3": abi.NET_NO_TC3}
     f = enum_values("PINN_FAM_")
     assert (f["PINN_FAM_V"], f["PINN_FAM_TS"], f["PINN_FAM_T"], f["PINN_FAM_H"], f["PINN_FAM_O"],
             f["PINN_FAM_DATA"]) == (abi.FAM_V, abi.FAM_TS, abi.FAM_T, abi.FAM_H, abi.FAM_O, abi.FAM_DATA)
