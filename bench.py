@@ -576,7 +576,7 @@ def run_ours(args):
         return
     pk = peaks()
     mc_tflops = n * T_PASSES * FLOP_PER_SAMPLE_PASS / (t_mc / K_) / 1e12
-    rec_mc, rec_res = ncu_record("mlp_tc_kernel<MC>"), ncu_record("residual_v_fast_kernel")
+    rec_mc, rec_res = ncu_record("mlp_tc3_kernel<MC>"), ncu_record("residual_v_fast_kernel")
     rec_tr = ncu_record("mlp_tc_fused_kernel")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": W_,
@@ -589,13 +589,13 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "achieved": mc_tflops, "peak": pk["bf16"], "unit": "TFLOP/s",
                      "frac": mc_tflops / pk["bf16"],
                      "traffic": (rec_mc["dram_bytes"] * n / rec_mc["n"]) if rec_mc else None,
-                     "kernel": "mlp_tc_kernel<MC> (tcgen05.mma kind::tf32 with A in tensor memory, 3xTF32 split, "
-                               "one MMA warp per 128-sample group)",
+                     "kernel": "mlp_tc3_kernel<MC> (three 128-sample groups per CTA, tcgen05.mma kind::f16 on fp16 hi/lo pairs with A in "
+                               "tensor memory, resident K-permuted weight images, one MMA warp per group)",
                      "peak_source": pk["src"], "ncu": rec_mc,
                      "note": "achieved = algorithmic FLOPs (21 664 per sample*pass) / CUDA-event time of the launch. The "
-                             "contractions run as 3 TF32 MMAs per product (fp32 parity), and TF32 dense peak is half the "
-                             "bf16 figure used as `peak`, so the tensor pipe does 6x this fraction of its own peak; the kernel "
-                             "is bounded by the CUDA-core epilogue (tanh, Philox, tf32 split) and MMA latency, see DESIGN.md "
+                             "contractions run as 3 fp16 MMAs per product (a_l*w_h + a_h*w_l + a_h*w_h: fp32 parity), so the "
+                             "tensor pipe does 3x this fraction of its own peak; the kernel is bounded by the CUDA-core "
+                             "epilogue (tanh, Philox, fp16 split: issue slots), see DESIGN.md "
                              "section 4. `traffic` / `ncu` are read from profiles/ncu_current.json (ncu --set full of this "
                              f"kernel), scaled by n; vs the fp32 FFMA peak (74.5 TFLOP/s) the kernel stands at {mc_tflops / 74.5:.2f}x"},
         "train": {"steps_per_s": steps_tr / t_tr, "ms_per_step": 1e3 * t_tr / steps_tr,

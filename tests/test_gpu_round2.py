@@ -565,3 +565,36 @@ def test_per_call_workspace_of_the_wide_paths():
         c = b200pinn.mc_dropout_device(dnn, xd, 3, 0.4, seed=5)
     for k in ("pred_mean", "a_u", "e_u"):
         assert nrel(t2n(a[k]), t2n(c[k])) < MC_TOL and nrel(t2n(b[k]), t2n(c[k])) < MC_TOL, k
+
+
+@pytest.mark.parametrize("layers,n,T", [(LAYERS, 129, 3), ([8, 64, 64, 1], 1000, 4), ([8, 64, 64, 64, 64, 64, 1], 5001, 2), (LAYERS, 50000, 5)])
+def test_three_group_fp16_pair_kernel_matches_two_group_3xtf32_kernel(layers, n, T):
+    """The 64-wide forward / MC sweep on three tile groups per CTA with fp16 hi/lo operands (csrc/mlp_tc3.cu) against the
+    two-group 3xTF32 kernel (csrc/mlp_tc.cu, PINN_NET_NO_TC3) on the same Philox stream and on injected masks: two fp32-exact
+    splits of the same products, so they agree to rounding (2..5 hidden layers, ragged tiles, more tiles than tile slots)."""
+    import b200pinn
+    from b200pinn import kernels as K
+    from b200pinn.synthetic import make_scaled_dataset
+
+    x, _, _, _ = make_scaled_dataset(max(n, 64), seed=6)
+    xd = torch.tensor(x[:n], device=dev())
+    dnn = random_net(layers, 9).eval()
+    net = K.net_from_module(dnn)
+    L, H = len(layers) - 2, 64
+    mk = torch.tensor((np.random.default_rng(1).random((T, n, L * H + H // 2)) >= 0.4).astype(np.uint8), device=dev()) if n <= 5001 else None
+
+    def run():
+        u0, s0 = K.mlp_forward(net, xd)
+        u1, s1 = K.mlp_forward(net, xd, K.make_dropout(0.4, seed=9, pass_offset=2))
+        mc = b200pinn.mc_dropout_device(dnn, xd, T, 0.4, seed=11, raw=True)
+        out = [u0, s0, u1, s1, mc["pred_mean"], mc["a_u"], mc["e_u"], mc["mean"]]
+        if mk is not None:
+            mi = b200pinn.mc_dropout_device(dnn, xd, T, 0.4, masks=mk, raw=True)
+            out += [mi["pred_mean"], mi["a_u"], mi["e_u"], mi["mean"]]
+        return out
+
+    a = run()
+    with K.path_flags(no_tc3=True):
+        b = run()
+    for i, (u, v) in enumerate(zip(a, b)):
+        assert nrel(t2n(u), t2n(v)) < 5e-6, i
