@@ -432,12 +432,12 @@ def run_ours(args):
           "T": T3, "n_total": n3, "rows_per_gpu": hi3 - lo3, "ms_per_sweep": 1e3 * t_c3 / n_c3,
           "sample_passes_per_s": n3 * T3 * n_c3 / t_c3, "tflops": n3 * T3 * FLOP_PER_SAMPLE_PASS * n_c3 / t_c3 / 1e12,
           "one_gpu_ms_per_sweep": 1e3 * t_c3_one / n_c3, "strong_scaling_efficiency": t_c3_one / (world * t_c3),
-          "tiles_per_gpu": tiles3, "tile_slots_per_gpu": 2 * sm, "pass_chunks": 4,
-          "wave_quantisation": 4 * tiles3 / (2 * sm * -(-4 * tiles3 // (2 * sm))),
-          "wave_note": "a GPU runs 2 x SMs work items at a time; an item is a 128-row tile x one run of 250 consecutive passes (T = 1000 "
+          "tiles_per_gpu": tiles3, "tile_slots_per_gpu": 3 * sm, "pass_chunks": 4,
+          "wave_quantisation": 4 * tiles3 / (3 * sm * -(-4 * tiles3 // (3 * sm))),
+          "wave_note": "a GPU runs 3 x SMs work items at a time (three tile groups per CTA, mlp_tc3.cu); an item is a 128-row tile x one run of 250 consecutive passes (T = 1000 "
                        "is cut into 4 runs per tile -- a function of T alone, so the numbers do not depend on the sharding -- whose "
                        "Welford triples a merge launch folds in order); wave_quantisation = items / (slots x waves) is the ceiling "
-                       "of the static item->SM map at this shard size (whole-tile items: 0.825 at 125 000 rows per GPU)"}
+                       "of the static item->SM map at this shard size"}
     del x3, x3_full, X3
 
     # --- config 5 share (fleet export): one stack of n timesteps -> 22-column float64 rows (K4 sweep at T_PASSES,
