@@ -152,12 +152,12 @@ mlp_tc3_kernel(const __grid_constant__ pinn_net_t net, const __grid_constant__ T
   const int64_t n_tiles = (n + k3Tile - 1) / k3Tile;
   const bool do_eval = MC && out.pred_mean != nullptr;
   const int C = (MC && CH) ? chunks : 1, Tc = (T + C - 1) / C;
-  const int64_t n_items = n_tiles * C;
+  const uint32_t n_items = static_cast<uint32_t>(n_tiles * C);        // < 2^31: checked by the launcher (32-bit item arithmetic)
   auto item_passes = [&](int chunk) {
     const int t0 = chunk * Tc, cnt = (T - t0 < Tc ? T - t0 : Tc);
     return MC ? (cnt > 0 ? cnt : 0) + ((do_eval && chunk == 0) ? 1 : 0) : 1;
   };
-  const int64_t item0 = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(grp) * gridDim.x, item_step = static_cast<int64_t>(gridDim.x) * k3NG;
+  const uint32_t item0 = blockIdx.x + static_cast<uint32_t>(grp) * gridDim.x, item_step = gridDim.x * k3NG, uC = static_cast<uint32_t>(C);
   // tensor memory: accumulators [64 g, +64) | A hi planes [192 + 64 g, +32) | A lo planes [224 + 64 g, +32)
   const uint32_t acc_t = tmem_base_s + static_cast<uint32_t>(64 * grp);
   const uint32_t ahi_t = tmem_base_s + static_cast<uint32_t>(192 + 64 * grp), alo_t = ahi_t + 32u;
@@ -166,8 +166,8 @@ mlp_tc3_kernel(const __grid_constant__ pinn_net_t net, const __grid_constant__ T
     // ================================================================== MMA warp of group `grp`
     const uint32_t idesc64 = tc::make_idesc_f16(k3Tile, H), idesc48 = tc::make_idesc_f16(k3Tile, k3HeadN);
     uint32_t par = 0u;
-    for (int64_t item = item0; item < n_items; item += item_step)
-      for (int it = 0, np = item_passes(static_cast<int>(item % C)); it < np; ++it) {
+    for (uint32_t item = item0; item < n_items; item += item_step)
+      for (int it = 0, np = item_passes(static_cast<int>(item % uC)); it < np; ++it) {
 #pragma unroll 1
         for (int l = 1; l <= L; ++l) {
           const bool heads = l == L;
@@ -248,16 +248,16 @@ mlp_tc3_kernel(const __grid_constant__ pinn_net_t net, const __grid_constant__ T
       tc::fence_after_sync();
     };
     const bool x_leader = use_tma && (tid & 255) == 0;
-    auto request_x = [&](int64_t it, int buf) {
+    auto request_x = [&](uint32_t it, int buf) {
       tc::mbar_expect_tx(&xbar[grp][buf], k3Tile * PINN_N_IN * sizeof(float));
-      tc::tma_load_2d(xs + buf * (k3Tile * PINN_N_IN), &xmap, 0, static_cast<int>((it / C) * k3Tile), &xbar[grp][buf]);
+      tc::tma_load_2d(xs + buf * (k3Tile * PINN_N_IN), &xmap, 0, static_cast<int>((it / uC) * k3Tile), &xbar[grp][buf]);
     };
     if (x_leader && item0 < n_items) request_x(item0, 0);
     uint32_t xcount = 0;
 
-    for (int64_t item = item0; item < n_items; item += item_step, ++xcount) {
-      const int64_t tile = item / C;
-      const int chunk = static_cast<int>(item % C), t0 = chunk * Tc;
+    for (uint32_t item = item0; item < n_items; item += item_step, ++xcount) {
+      const int64_t tile = item / uC;
+      const int chunk = static_cast<int>(item % uC), t0 = chunk * Tc;
       const bool eval_item = do_eval && chunk == 0;
       const int n_pass = item_passes(chunk);
       const int64_t s = tile * k3Tile + row;
@@ -448,6 +448,7 @@ int launch_tc3(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T,
   const int64_t tiles = (n + k3Tile - 1) / k3Tile;
   const int C = mc ? mc_pass_chunks(T) : 1;
   const int64_t want = tiles * C;
+  if (want >= (static_cast<int64_t>(1) << 31) - 4 * sm_count()) return 0;      // the kernel indexes work items with 32 bits
   const int grid = static_cast<int>(want < sm_count() ? (want > 0 ? want : 1) : sm_count());
   const bool inj = dp.p > 0.f && dp.masks != nullptr;
   if (C > 1 && (workspace == nullptr || workspace_bytes < static_cast<size_t>(C) * 3 * n * sizeof(float))) { *err = PINN_E_WORKSPACE; return -1; }
