@@ -34,7 +34,7 @@ PIPELINE_CHUNKS = 4
 
 
 def _pipeline_chunks(n: int, wave: int):
-    """Row ranges of the host pipeline.  A chunk is a whole number of "waves" (two 128-row tiles per SM) so that no chunk
+    """Row ranges of the host pipeline.  A chunk is a whole number of "waves" (three 128-row tiles per SM: the MC kernel keeps three in flight) so that no chunk
     but the last ends on a partial wave; long inputs start with a short chunk (2 waves, then 4) -- the first chunk's upload
     and the last chunk's download are the only copies that are not hidden behind a sweep."""
     waves = -(-n // wave)
@@ -71,7 +71,7 @@ def _mc_host_pipelined(dnn, X, mc_times, dropout, pass_offset, dev):
     s_in, s_out, s_alt = _SIDE_STREAMS[dev]
     s_in.wait_stream(cur)
     s_alt.wait_stream(cur)
-    for k, (lo, hi) in enumerate(_pipeline_chunks(n, 256 * torch.cuda.get_device_properties(dev).multi_processor_count)):
+    for k, (lo, hi) in enumerate(_pipeline_chunks(n, 384 * torch.cuda.get_device_properties(dev).multi_processor_count)):
         with torch.cuda.stream(s_in):
             xd[lo:hi].copy_(Xc[lo:hi], non_blocking=True)
             up = torch.cuda.Event()
