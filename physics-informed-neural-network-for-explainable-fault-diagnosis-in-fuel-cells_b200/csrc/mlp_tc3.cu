@@ -444,7 +444,7 @@ int launch_tc3(bool mc, const pinn_net_t* net, const float* x, int64_t n, int T,
     if (!aligned16(net->W[l])) return 0;
   if (!aligned16(net->Wv0) || !aligned16(net->Wp) || !aligned16(x)) return 0;
   const Tc3Layout lay = make_tc3_layout(net->n_hidden);
-  if (lay.total > 226 * 1024) return 0;          // up to five hidden layers next to three layer-0 parks
+  if (lay.total > 226 * 1024) return 0;          // up to six hidden layers next to three layer-0 parks
   const int64_t tiles = (n + k3Tile - 1) / k3Tile;
   const int C = mc ? mc_pass_chunks(T) : 1;
   const int64_t want = tiles * C;
