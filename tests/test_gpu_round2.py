@@ -567,11 +567,13 @@ def test_per_call_workspace_of_the_wide_paths():
         assert nrel(t2n(a[k]), t2n(c[k])) < MC_TOL and nrel(t2n(b[k]), t2n(c[k])) < MC_TOL, k
 
 
-@pytest.mark.parametrize("layers,n,T", [(LAYERS, 129, 3), ([8, 64, 64, 1], 1000, 4), ([8, 64, 64, 64, 64, 64, 1], 5001, 2), (LAYERS, 50000, 5)])
+@pytest.mark.parametrize("layers,n,T", [(LAYERS, 129, 3), ([8, 64, 64, 1], 1000, 4), ([8, 64, 64, 64, 64, 64, 1], 5001, 2), (LAYERS, 50000, 5),
+                                        ([8] + [64] * 6 + [1], 700, 2), ([8] + [64] * 4 + [1], 300, 30)])
 def test_three_group_fp16_pair_kernel_matches_two_group_3xtf32_kernel(layers, n, T):
     """The 64-wide forward / MC sweep on three tile groups per CTA with fp16 hi/lo operands (csrc/mlp_tc3.cu) against the
     two-group 3xTF32 kernel (csrc/mlp_tc.cu, PINN_NET_NO_TC3) on the same Philox stream and on injected masks: two fp32-exact
-    splits of the same products, so they agree to rounding (2..5 hidden layers, ragged tiles, more tiles than tile slots)."""
+    splits of the same products, so they agree to rounding (2..6 hidden layers, ragged tiles, more tiles than tile slots, a
+    chunked sweep)."""
     import b200pinn
     from b200pinn import kernels as K
     from b200pinn.synthetic import make_scaled_dataset
