@@ -301,7 +301,8 @@ PINN_D void issue_3xtf32_ts_slabs(uint32_t d_tmem, uint32_t a_hi_t, uint32_t a_l
 PINN_D void split_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(a, b);
   const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  const float2 d = __ffma2_rn(hf, make_float2(-1.0f, -1.0f), make_float2(a, b));      // a - a_h, exact; one packed instruction
+  const __half2 l = __floats2half2_rn(d.x, d.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
