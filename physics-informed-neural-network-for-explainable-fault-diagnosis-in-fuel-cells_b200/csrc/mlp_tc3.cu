@@ -22,7 +22,10 @@
 
 namespace pinn {
 
-constexpr int k3H = 64, k3HH = 32, k3Tile = 128, k3HeadN = 48, k3NG = 3;
+#ifndef TC3_NG
+#define TC3_NG 3           // tile groups per CTA (2: the fp16-pair form of the two-group kernel, for attribution runs)
+#endif
+constexpr int k3H = 64, k3HH = 32, k3Tile = 128, k3HeadN = 48, k3NG = TC3_NG;
 constexpr int k3Threads = k3NG * 256 + k3NG * 32;
 #ifndef TC3_PREDRAW
 #define TC3_PREDRAW 1      // Philox blocks of a hidden epilogue drawn ahead of the wait that precedes it
